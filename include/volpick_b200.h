@@ -1,0 +1,142 @@
+/*
+ * volpick_b200 -- C ABI of the B200-native continuous-waveform picking path.
+ *
+ * This is the drop-in boundary for the path that the reference runs through SeisBench:
+ *   picker = sbm.EQTransformer.from_pretrained("volpick"); picker.classify(stream, ...).picks
+ *   (/root/reference/README.md:46-66, /root/reference/Final_models/demo.ipynb cells 7-15).
+ * The reference has no C plugin ABI (it is pure Python calling SeisBench); each entry point
+ * below names the SeisBench / reference function it replaces.  All signatures are plain C:
+ * raw pointers, sizes and a CUDA stream passed as void* (cudaStream_t).  No torch types.
+ *
+ * Conventions
+ *   - every function returns VP_OK (0) or a negative VP_ERR_* code; vp_last_error() gives the
+ *     thread-local message of the last failure.  Pick-buffer overflow is an error, never a
+ *     silent truncation.  There is no CPU fallback: without a CUDA device every compute entry
+ *     point fails with VP_ERR_CUDA.
+ *   - "device" pointers are CUDA device memory of the model's device; the caller owns every
+ *     buffer (inputs are never modified); the model handle owns only the folded weights.
+ *   - activations / predictions are planar: windows (B, 3, L), predictions (B, 3, L), stacked
+ *     annotation (3, pred_len).  Label order: EQTransformer Detection,P,S; PhaseNet P,S,N
+ *     (/root/reference/volpick/model/eval_taks0.py:68-72,131-134).
+ *   - launches go to the caller's stream; a handle is immutable after creation and may be
+ *     shared by threads that use different streams and different workspaces.
+ */
+#ifndef VOLPICK_B200_H
+#define VOLPICK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VP_OK 0
+#define VP_ERR_ARG (-1)
+#define VP_ERR_CUDA (-2)
+#define VP_ERR_CAPACITY (-3)
+#define VP_ERR_WORKSPACE (-4)
+#define VP_ERR_UNSUPPORTED (-5)
+
+enum { VP_KIND_EQTRANSFORMER = 0, VP_KIND_PHASENET = 1 };
+enum { VP_STACK_AVG = 0, VP_STACK_MAX = 1 };
+enum { VP_PREC_FP32 = 0, VP_PREC_TF32X3 = 1, VP_PREC_BF16 = 2 };
+enum { VP_DTYPE_F32 = 0, VP_DTYPE_I32 = 1 };
+enum { VP_PEAK_PER_CHANNEL = 0, VP_PEAK_PER_WINDOW = 1 };
+
+typedef struct vp_model vp_model;
+
+/* One trigger: SeisBench Pick / Detection before the index->time conversion. */
+typedef struct vp_trigger {
+    int64_t s0;     /* first sample > threshold inside the run            (start_time) */
+    int64_t s1;     /* last sample of the run of samples > threshold / 2  (end_time)   */
+    int64_t s_peak; /* s0 + argmax(x[s0..s1]), first maximum              (peak_time)  */
+    float value;    /* x[s_peak]                                          (peak_value) */
+    int32_t label;  /* label index (column of the annotation)                          */
+} vp_trigger;
+
+/* kwargs of WaveformModel.annotate / classify (/root/reference/README.md:54-66). */
+typedef struct vp_annotate_params {
+    int64_t overlap;       /* samples                                                   */
+    int64_t blinding[2];   /* (pre, post) samples set to NaN in every window            */
+    int32_t stacking;      /* VP_STACK_AVG | VP_STACK_MAX                               */
+    int32_t precision;     /* VP_PREC_*                                                 */
+    int32_t peak_scope;    /* VP_PEAK_PER_CHANNEL (default) | VP_PEAK_PER_WINDOW        */
+    int32_t chunk_windows; /* windows per forward launch group; <= 0: library default   */
+    float threshold[3];    /* per label; <= 0 or NaN: no picks for that label           */
+} vp_annotate_params;
+
+/* ---- misc ---------------------------------------------------------------------------- */
+int vp_version(void);
+const char *vp_last_error(void);
+/* Number of kernel launches issued by this library on the calling thread since the last reset. */
+int64_t vp_launch_count(int reset);
+
+/* ---- model handle: SeisBenchModel.from_pretrained -> load_state_dict ------------------- */
+/* weights: every float tensor of the SeisBench state dict, concatenated in state-dict order
+ * (num_batches_tracked dropped): 378,823 floats for EQTransformer, 269,675 for PhaseNet
+ * (/root/reference/Final_models/volpick/{eqtransformer,phasenet}/volpick.pt.v1).  BatchNorm
+ * (eps 1e-3) is folded in double precision on the host. */
+int vp_model_create(int kind, const float *weights, int64_t n_floats, int device, vp_model **out);
+int vp_model_destroy(vp_model *m);
+int vp_model_kind(const vp_model *m);
+int vp_model_in_samples(const vp_model *m); /* 6000 / 3001 */
+int64_t vp_model_expected_floats(int kind);
+
+/* ---- host integer math: WaveformModel._cut_fragments_array ----------------------------- */
+int64_t vp_window_count(int64_t n_samples, int64_t in_samples, int64_t overlap);
+int vp_window_starts(int64_t n_samples, int64_t in_samples, int64_t overlap, int64_t *starts, int64_t capacity,
+                     int64_t *count);
+int64_t vp_coverage(int64_t in_samples, int64_t overlap); /* ceil(L / (L - overlap) + 1) */
+
+/* ---- stage kernels (all pointers are device pointers) ---------------------------------- */
+/* _cut_fragments_array + annotate_batch_pre: gather windows, demean, peak-normalise (+1e-10),
+ * EQTransformer 6-sample cosine taper.  trace: (3, n) with channel stride ch_stride elements,
+ * f32 or i32 counts.  out: (n_windows, 3, L) f32. */
+int vp_slice_normalize(const void *trace, int dtype, int64_t n_samples, int64_t ch_stride, const int64_t *starts,
+                       int64_t n_windows, int64_t in_samples, int peak_scope, int taper, float *out, void *stream);
+
+/* EQTransformer.forward / PhaseNet.forward on pre-normalised windows.
+ * x: (n_windows, 3, L) -> y: (n_windows, 3, L) probabilities (sigmoid heads / channel softmax). */
+int64_t vp_forward_workspace_bytes(const vp_model *m, int64_t n_windows, int precision);
+int vp_forward(vp_model *m, const float *x, int64_t n_windows, float *y, void *workspace, int64_t workspace_bytes,
+               int precision, void *stream);
+/* Debug/parity: run the forward and copy the named intermediate activation (device->device) into
+ * tap_out (capacity in floats); *tap_floats receives its size.  Names: see vp_forward_tap_names(). */
+int vp_forward_tap(vp_model *m, const float *x, int64_t n_windows, float *y, void *workspace,
+                   int64_t workspace_bytes, int precision, const char *tap_name, float *tap_out,
+                   int64_t tap_capacity, int64_t *tap_floats, void *stream);
+const char *vp_forward_tap_names(const vp_model *m); /* comma separated */
+
+/* annotate_batch_post (blinding) + _reassemble_blocks_array: y (n_windows,3,L) -> out (3,pred_len). */
+int vp_stack(const float *y, const int64_t *starts, int64_t n_windows, int64_t in_samples, int n_labels,
+             int64_t overlap, int64_t blind0, int64_t blind1, int mode, float *out, int64_t pred_len, void *stream);
+
+/* _trim_nan: first / last non-NaN index per label (first = pred_len, last = -1 when all NaN).
+ * bounds: device int64[2 * n_labels] = {first_0, last_0, first_1, ...}. */
+int vp_nan_bounds(const float *annotation, int n_labels, int64_t pred_len, int64_t *bounds, void *stream);
+
+/* picks_from_annotations / detections_from_annotations (trigger_onset + first argmax;
+ * /root/reference/volpick/model/eval_taks0.py:46-56).  Appends to picks[*count...] (device),
+ * unordered; *count (device int64) may exceed capacity -> caller must treat as overflow.
+ * scratch: device buffer of vp_pick_scratch_bytes(n) bytes. */
+int64_t vp_pick_scratch_bytes(int64_t n_samples);
+int vp_pick(const float *trace, int64_t n_samples, float thr_on, float thr_off, int label, vp_trigger *picks,
+            int64_t capacity, int64_t *count, void *scratch, int64_t scratch_bytes, void *stream);
+
+/* ---- the whole path for one gap-free record: WaveformModel.annotate + classify_aggregate -- */
+int64_t vp_annotate_workspace_bytes(const vp_model *m, int64_t n_samples, const vp_annotate_params *p,
+                                    int trace_on_host, int64_t pick_capacity);
+/* trace: (3, n) f32/i32, on the host (pinned recommended; copied inside) or on the device.
+ * annotation: optional (3, pred_len) output, host or device (NULL to skip).
+ * picks: HOST buffer; sorted by (label, s0); indices relative to the record start.
+ * trim: HOST int64[6] = per label {first non-NaN, last non-NaN} of the stacked annotation.
+ * Synchronises the stream before returning. */
+int vp_annotate(vp_model *m, const void *trace, int trace_on_host, int dtype, int64_t n_samples, int64_t ch_stride,
+                const vp_annotate_params *p, float *annotation, int annotation_on_host, vp_trigger *picks,
+                int64_t pick_capacity, int64_t *n_picks, int64_t *trim, void *workspace, int64_t workspace_bytes,
+                void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VOLPICK_B200_H */

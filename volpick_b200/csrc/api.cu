@@ -1,0 +1,181 @@
+// Host integer math and the whole-record entry point.
+//
+// vp_window_starts  <- WaveformModel._cut_fragments_array (SeisBench)
+// vp_annotate       <- WaveformModel.annotate + classify_aggregate for one gap-free record
+//                      (call sites /root/reference/README.md:54-66, Final_models/demo.ipynb cell 13-15)
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "common.cuh"
+
+using namespace vp;
+
+extern "C" int64_t vp_window_count(int64_t n, int64_t L, int64_t overlap) {
+    const int64_t stride = L - overlap;
+    if (L <= 0 || stride <= 0 || n < L) return 0;
+    int64_t cnt = (n - L) / stride + 1;              // len(arange(0, n - L + 1, stride))
+    if ((cnt - 1) * stride + L < n) ++cnt;           // tail window at n - L
+    return cnt;
+}
+
+extern "C" int vp_window_starts(int64_t n, int64_t L, int64_t overlap, int64_t *starts, int64_t capacity,
+                                int64_t *count) {
+    VP_REQUIRE(count != nullptr, VP_ERR_ARG, "vp_window_starts: null count");
+    VP_REQUIRE(L > 0 && overlap >= 0 && overlap < L, VP_ERR_ARG,
+               "vp_window_starts: need 0 <= overlap (%lld) < in_samples (%lld)", (long long)overlap, (long long)L);
+    const int64_t cnt = vp_window_count(n, L, overlap);
+    *count = cnt;
+    if (cnt == 0) return VP_OK;
+    VP_REQUIRE(starts != nullptr && capacity >= cnt, VP_ERR_CAPACITY, "vp_window_starts: capacity %lld < %lld windows",
+               (long long)capacity, (long long)cnt);
+    const int64_t stride = L - overlap;
+    const int64_t nreg = (n - L) / stride + 1;
+    for (int64_t i = 0; i < nreg; ++i) starts[i] = i * stride;
+    if (cnt > nreg) starts[nreg] = n - L;
+    return VP_OK;
+}
+
+namespace {
+
+struct Layout {
+    int64_t off_trace, off_starts, off_x, off_fwd, off_y, off_annot, off_bounds, off_count, off_picks, off_scratch;
+    int64_t fwd_bytes, total;
+    int64_t nwin, chunk, pred_len;
+};
+
+int64_t default_chunk(const vp_model *m) { return vp_model_kind(m) == VP_KIND_EQTRANSFORMER ? 1024 : 4096; }
+
+int make_layout(const vp_model *m, int64_t n, const vp_annotate_params *p, int trace_on_host, int64_t pick_cap,
+                Layout *lo) {
+    const int64_t L = vp_model_in_samples(m);
+    VP_REQUIRE(p->overlap >= 0 && p->overlap < L, VP_ERR_ARG, "annotate: need 0 <= overlap (%lld) < in_samples (%lld)",
+               (long long)p->overlap, (long long)L);
+    lo->nwin = vp_window_count(n, L, p->overlap);
+    lo->chunk = p->chunk_windows > 0 ? p->chunk_windows : default_chunk(m);
+    lo->chunk = std::min<int64_t>(std::max<int64_t>(lo->chunk, 1), 4096);
+    lo->pred_len = lo->nwin ? n : 0;  // max(starts) + L == n whenever at least one window exists
+    int64_t off = 0;
+    auto take = [&](int64_t bytes) {
+        const int64_t o = align_up(off, 256);
+        off = o + bytes;
+        return o;
+    };
+    lo->off_trace = take(trace_on_host ? 3 * n * 4 : 0);
+    lo->off_starts = take(std::max<int64_t>(lo->nwin, 1) * 8);
+    lo->off_x = take(std::min(lo->chunk, std::max<int64_t>(lo->nwin, 1)) * 3 * L * 4);
+    lo->fwd_bytes = vp_forward_workspace_bytes(m, std::min(lo->chunk, std::max<int64_t>(lo->nwin, 1)), p->precision);
+    if (lo->fwd_bytes < 0) return (int)lo->fwd_bytes;
+    lo->off_fwd = take(lo->fwd_bytes);
+    lo->off_y = take(std::max<int64_t>(lo->nwin, 1) * 3 * L * 4);
+    lo->off_annot = take(3 * std::max<int64_t>(lo->pred_len, 1) * 4);
+    lo->off_bounds = take(6 * 8);
+    lo->off_count = take(8);
+    lo->off_picks = take(std::max<int64_t>(pick_cap, 1) * (int64_t)sizeof(vp_trigger));
+    lo->off_scratch = take(vp_pick_scratch_bytes(std::max<int64_t>(lo->pred_len, 1)));
+    lo->total = align_up(off, 256);
+    return VP_OK;
+}
+
+}  // namespace
+
+extern "C" int64_t vp_annotate_workspace_bytes(const vp_model *m, int64_t n_samples, const vp_annotate_params *p,
+                                               int trace_on_host, int64_t pick_capacity) {
+    if (!m || !p || n_samples < 0) return VP_ERR_ARG;
+    Layout lo;
+    int rc = make_layout(m, n_samples, p, trace_on_host, pick_capacity, &lo);
+    return rc == VP_OK ? lo.total : rc;
+}
+
+extern "C" int vp_annotate(vp_model *m, const void *trace, int trace_on_host, int dtype, int64_t n, int64_t ch_stride,
+                           const vp_annotate_params *p, float *annotation, int annotation_on_host, vp_trigger *picks,
+                           int64_t pick_capacity, int64_t *n_picks, int64_t *trim, void *workspace,
+                           int64_t workspace_bytes, void *stream) {
+    VP_REQUIRE(m && trace && p && workspace && n_picks && trim, VP_ERR_ARG, "vp_annotate: null pointer");
+    VP_REQUIRE(dtype == VP_DTYPE_F32 || dtype == VP_DTYPE_I32, VP_ERR_ARG, "vp_annotate: unknown dtype %d", dtype);
+    VP_REQUIRE(p->stacking == VP_STACK_AVG || p->stacking == VP_STACK_MAX, VP_ERR_ARG,
+               "Stacking method %d unknown. Known methods are: 'avg' (0), 'max' (1)", p->stacking);
+    VP_REQUIRE(pick_capacity == 0 || picks, VP_ERR_ARG, "vp_annotate: pick buffer missing");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int kind = vp_model_kind(m);
+    const int64_t L = vp_model_in_samples(m);
+    Layout lo;
+    int rc = make_layout(m, n, p, trace_on_host, pick_capacity, &lo);
+    if (rc != VP_OK) return rc;
+    VP_REQUIRE(workspace_bytes >= lo.total, VP_ERR_WORKSPACE, "vp_annotate: workspace too small (%lld < %lld bytes)",
+               (long long)workspace_bytes, (long long)lo.total);
+    *n_picks = 0;
+    for (int i = 0; i < 3; ++i) {
+        trim[2 * i] = lo.pred_len;
+        trim[2 * i + 1] = -1;
+    }
+    if (lo.nwin == 0) return VP_OK;  // record shorter than one window: empty output (SeisBench warns)
+
+    char *ws = (char *)workspace;
+    const void *d_trace = trace;
+    int64_t d_stride = ch_stride;
+    if (trace_on_host) {
+        // (3, n) with channel stride ch_stride on the host -> packed (3, n) on the device
+        char *dst = ws + lo.off_trace;
+        for (int c = 0; c < 3; ++c)
+            VP_CUDA_CHECK(cudaMemcpyAsync(dst + (int64_t)c * n * 4, (const char *)trace + (int64_t)c * ch_stride * 4,
+                                          n * 4, cudaMemcpyHostToDevice, s));
+        d_trace = dst;
+        d_stride = n;
+    }
+    int64_t *d_starts = (int64_t *)(ws + lo.off_starts);
+    {
+        std::vector<int64_t> h_starts((size_t)lo.nwin);
+        int64_t cnt = 0;
+        rc = vp_window_starts(n, L, p->overlap, h_starts.data(), lo.nwin, &cnt);
+        if (rc != VP_OK) return rc;
+        // pageable -> the copy is staged by the runtime before the call returns
+        VP_CUDA_CHECK(cudaMemcpyAsync(d_starts, h_starts.data(), (size_t)lo.nwin * 8, cudaMemcpyHostToDevice, s));
+        VP_CUDA_CHECK(cudaStreamSynchronize(s));
+    }
+    float *d_x = (float *)(ws + lo.off_x);
+    float *d_y = (float *)(ws + lo.off_y);
+    const int taper = (kind == VP_KIND_EQTRANSFORMER) ? 1 : 0;
+    for (int64_t w0 = 0; w0 < lo.nwin; w0 += lo.chunk) {
+        const int64_t nw = std::min(lo.chunk, lo.nwin - w0);
+        rc = vp_slice_normalize(d_trace, dtype, n, d_stride, d_starts + w0, nw, L, p->peak_scope, taper, d_x, s);
+        if (rc != VP_OK) return rc;
+        rc = vp_forward(m, d_x, nw, d_y + w0 * 3 * L, ws + lo.off_fwd, lo.fwd_bytes, p->precision, s);
+        if (rc != VP_OK) return rc;
+    }
+    float *d_annot = (float *)(ws + lo.off_annot);
+    rc = vp_stack(d_y, d_starts, lo.nwin, L, 3, p->overlap, p->blinding[0], p->blinding[1], p->stacking, d_annot,
+                  lo.pred_len, s);
+    if (rc != VP_OK) return rc;
+    int64_t *d_bounds = (int64_t *)(ws + lo.off_bounds);
+    rc = vp_nan_bounds(d_annot, 3, lo.pred_len, d_bounds, s);
+    if (rc != VP_OK) return rc;
+    int64_t *d_count = (int64_t *)(ws + lo.off_count);
+    vp_trigger *d_picks = (vp_trigger *)(ws + lo.off_picks);
+    VP_CUDA_CHECK(cudaMemsetAsync(d_count, 0, 8, s));
+    for (int c = 0; c < 3; ++c) {
+        const float thr = p->threshold[c];
+        if (!(thr > 0.f) || pick_capacity == 0) continue;
+        rc = vp_pick(d_annot + (int64_t)c * lo.pred_len, lo.pred_len, thr, thr / 2, c, d_picks, pick_capacity, d_count,
+                     ws + lo.off_scratch, vp_pick_scratch_bytes(lo.pred_len), s);
+        if (rc != VP_OK) return rc;
+    }
+    int64_t h_count = 0;
+    VP_CUDA_CHECK(cudaMemcpyAsync(&h_count, d_count, 8, cudaMemcpyDeviceToHost, s));
+    VP_CUDA_CHECK(cudaMemcpyAsync(trim, d_bounds, 6 * 8, cudaMemcpyDeviceToHost, s));
+    if (annotation)
+        VP_CUDA_CHECK(cudaMemcpyAsync(annotation, d_annot, 3 * lo.pred_len * 4,
+                                      annotation_on_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, s));
+    VP_CUDA_CHECK(cudaStreamSynchronize(s));
+    *n_picks = h_count;
+    VP_REQUIRE(h_count <= pick_capacity, VP_ERR_CAPACITY, "vp_annotate: %lld picks exceed the pick capacity %lld",
+               (long long)h_count, (long long)pick_capacity);
+    if (h_count > 0) {
+        VP_CUDA_CHECK(cudaMemcpyAsync(picks, d_picks, (size_t)h_count * sizeof(vp_trigger), cudaMemcpyDeviceToHost, s));
+        VP_CUDA_CHECK(cudaStreamSynchronize(s));
+        std::sort(picks, picks + h_count, [](const vp_trigger &a, const vp_trigger &b) {
+            return a.label != b.label ? a.label < b.label : a.s0 < b.s0;
+        });
+    }
+    return VP_OK;
+}

@@ -1,0 +1,788 @@
+// Model handle, host-side weight folding / packing, and the forward plans.
+//
+// vp_model_create   <- SeisBenchModel.from_pretrained -> load_state_dict
+//                      (/root/reference/README.md:46-47, /root/reference/volpick/model/train.py:94)
+// vp_forward        <- EQTransformer.forward / PhaseNet.forward (SeisBench; SURVEY.md Appendix A / B;
+//                      call sites /root/reference/volpick/model/eval_taks0.py:68-72,85-89)
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace vp {
+
+// ---- error / launch accounting ------------------------------------------------------------------
+static thread_local std::string g_error;
+static thread_local int64_t g_launches = 0;
+
+void set_error(const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_error = buf;
+}
+void count_launch(int n) { g_launches += n; }
+
+constexpr double BN_EPS = 1e-3;
+constexpr int64_t EQT_FLOATS = 378823;
+constexpr int64_t PN_FLOATS = 269675;
+constexpr int64_t MAX_CHUNK = 4096;  // windows per internal forward chunk (grid.y limit is 65535)
+
+struct Cursor {
+    const float *p;
+    int64_t left;
+    const float *take(int64_t n) {
+        const float *r = p;
+        p += n;
+        left -= n;
+        return r;
+    }
+};
+
+struct BN {
+    const float *w, *b, *rm, *rv;
+    int c;
+};
+static BN take_bn(Cursor &cur, int c) {
+    BN bn;
+    bn.w = cur.take(c);
+    bn.b = cur.take(c);
+    bn.rm = cur.take(c);
+    bn.rv = cur.take(c);
+    bn.c = c;
+    return bn;
+}
+// y = x * scale + shift, folded in double (a denormal running_var must not be flushed on the device)
+static void bn_affine(const BN &bn, std::vector<double> &scale, std::vector<double> &shift) {
+    scale.resize(bn.c);
+    shift.resize(bn.c);
+    for (int i = 0; i < bn.c; ++i) {
+        scale[i] = (double)bn.w[i] / std::sqrt((double)bn.rv[i] + BN_EPS);
+        shift[i] = (double)bn.b[i] - (double)bn.rm[i] * scale[i];
+    }
+}
+
+struct Packed {
+    std::vector<float> host;
+    int64_t add(int64_t n) {
+        const int64_t off = align_up((int64_t)host.size(), 64);  // 256-byte aligned blocks
+        host.resize(off + n, 0.f);
+        return off;
+    }
+};
+
+struct ConvW {
+    int64_t w, b;  // offsets into the packed buffer
+    int cin, cout, coutp, k;
+};
+// W (cout, cin, k) [+ bias] [+ BatchNorm after the conv] -> wt[cin][k][coutp], b[coutp]
+static ConvW pack_conv(Packed &pk, const float *W, const float *bias, const BN *bn, int cout, int cin, int k) {
+    ConvW cw;
+    cw.cin = cin;
+    cw.cout = cout;
+    cw.k = k;
+    cw.coutp = (cout + 3) / 4 * 4;
+    std::vector<double> sc(cout, 1.0), sh(cout, 0.0);
+    if (bn) bn_affine(*bn, sc, sh);
+    cw.w = pk.add((int64_t)cin * k * cw.coutp);
+    cw.b = pk.add(cw.coutp);
+    for (int co = 0; co < cout; ++co) {
+        for (int ci = 0; ci < cin; ++ci)
+            for (int kk = 0; kk < k; ++kk)
+                pk.host[cw.w + ((int64_t)ci * k + kk) * cw.coutp + co] =
+                    (float)((double)W[((int64_t)co * cin + ci) * k + kk] * sc[co]);
+        const double b0 = bias ? (double)bias[co] : 0.0;
+        pk.host[cw.b + co] = (float)(b0 * sc[co] + sh[co]);
+    }
+    return cw;
+}
+// ConvTranspose1d W (cin, cout, 7) + BN -> wt[cin][7][cout], b[cout]
+static ConvW pack_convt(Packed &pk, const float *W, const BN &bn, int cin, int cout) {
+    ConvW cw;
+    cw.cin = cin;
+    cw.cout = cw.coutp = cout;
+    cw.k = 7;
+    std::vector<double> sc, sh;
+    bn_affine(bn, sc, sh);
+    cw.w = pk.add((int64_t)cin * 7 * cout);
+    cw.b = pk.add(cout);
+    for (int ci = 0; ci < cin; ++ci)
+        for (int co = 0; co < cout; ++co)
+            for (int kk = 0; kk < 7; ++kk)
+                pk.host[cw.w + ((int64_t)ci * 7 + kk) * cout + co] =
+                    (float)((double)W[((int64_t)ci * cout + co) * 7 + kk] * sc[co]);
+    for (int co = 0; co < cout; ++co) pk.host[cw.b + co] = (float)sh[co];
+    return cw;
+}
+struct AffW {
+    int64_t scale, shift;
+};
+static AffW pack_affine(Packed &pk, const BN &bn) {
+    std::vector<double> sc, sh;
+    bn_affine(bn, sc, sh);
+    AffW a;
+    a.scale = pk.add(bn.c);
+    a.shift = pk.add(bn.c);
+    for (int i = 0; i < bn.c; ++i) {
+        pk.host[a.scale + i] = (float)sc[i];
+        pk.host[a.shift + i] = (float)sh[i];
+    }
+    return a;
+}
+struct LstmW {
+    int64_t ih, hh, b;
+    int cin, ndir;
+};
+// per direction: w_ih (64, cin), w_hh (64, 16), b_ih (64), b_hh (64); PyTorch gate order i,f,g,o
+static void pack_lstm_dir(Packed &pk, const LstmW &lw, int dir, Cursor &cur) {
+    const int cin = lw.cin;
+    const float *wih = cur.take(64 * cin), *whh = cur.take(64 * 16), *bih = cur.take(64), *bhh = cur.take(64);
+    for (int ci = 0; ci < cin; ++ci)
+        for (int j = 0; j < 16; ++j)
+            for (int g = 0; g < 4; ++g)
+                pk.host[lw.ih + (((int64_t)dir * cin + ci) * 16 + j) * 4 + g] = wih[(g * 16 + j) * cin + ci];
+    for (int k = 0; k < 16; ++k)
+        for (int j = 0; j < 16; ++j)
+            for (int g = 0; g < 4; ++g)
+                pk.host[lw.hh + (((int64_t)dir * 16 + k) * 16 + j) * 4 + g] = whh[(g * 16 + j) * 16 + k];
+    for (int j = 0; j < 16; ++j)
+        for (int g = 0; g < 4; ++g)
+            pk.host[lw.b + ((int64_t)dir * 16 + j) * 4 + g] = bih[g * 16 + j] + bhh[g * 16 + j];
+}
+static LstmW alloc_lstm(Packed &pk, int cin, int ndir) {
+    LstmW lw;
+    lw.cin = cin;
+    lw.ndir = ndir;
+    lw.ih = pk.add((int64_t)ndir * cin * 64);
+    lw.hh = pk.add((int64_t)ndir * 16 * 64);
+    lw.b = pk.add((int64_t)ndir * 64);
+    return lw;
+}
+// attention: Wx (16,32), Wt (16,32), bh (32), Wa (32,1), ba (1) -> AW_* block
+static void pack_attention(Packed &pk, int64_t off, Cursor &cur) {
+    const float *Wx = cur.take(512), *Wt = cur.take(512), *bh = cur.take(32), *Wa = cur.take(32), *ba = cur.take(1);
+    std::memcpy(&pk.host[off + AW_WT], Wt, 512 * sizeof(float));
+    std::memcpy(&pk.host[off + AW_WX], Wx, 512 * sizeof(float));
+    std::memcpy(&pk.host[off + AW_BH], bh, 32 * sizeof(float));
+    std::memcpy(&pk.host[off + AW_WA], Wa, 32 * sizeof(float));
+    pk.host[off + AW_BA] = ba[0];
+}
+
+}  // namespace vp
+
+using namespace vp;
+
+struct vp_model {
+    int kind = 0;
+    int device = 0;
+    int in_samples = 0;
+    float *d_weights = nullptr;
+    int64_t n_packed = 0;
+    // EQTransformer
+    ConvW enc[7];
+    struct {
+        AffW n1, n2;
+        ConvW c1, c2;
+    } res[7];
+    struct {
+        LstmW lstm;
+        ConvW conv;
+    } bil[3];
+    int64_t tr[2] = {0, 0};  // AW blocks (transformer_d0, transformer_d)
+    ConvW dec[3][7];         // [decoder_d, pick_decoders.0, pick_decoders.1][layer]; packed layer-major
+    ConvW head[3];
+    LstmW pick_lstm[2];
+    int64_t pick_attn[2] = {0, 0};
+    // PhaseNet
+    ConvW inc, down_same[5], down_down[4], up_t[4], up_same[4], outc;
+    std::string tap_names;
+};
+
+static const int kEncC[8] = {3, 8, 16, 16, 32, 32, 64, 64};
+static const int kEncK[7] = {11, 9, 7, 7, 5, 5, 3};
+static const int kResK[7] = {3, 3, 3, 3, 2, 3, 2};
+static const int kDecC[8] = {16, 64, 64, 32, 32, 16, 16, 8};
+static const int kDecK[7] = {3, 5, 5, 7, 7, 9, 11};
+static const int kPnC[5] = {8, 16, 32, 64, 128};
+
+static void build_eqt(vp_model *m, Cursor &cur, Packed &pk) {
+    for (int i = 0; i < 7; ++i) {
+        const float *W = cur.take((int64_t)kEncC[i + 1] * kEncC[i] * kEncK[i]);
+        const float *b = cur.take(kEncC[i + 1]);
+        m->enc[i] = pack_conv(pk, W, b, nullptr, kEncC[i + 1], kEncC[i], kEncK[i]);
+    }
+    for (int i = 0; i < 7; ++i) {
+        BN n1 = take_bn(cur, 64);
+        const float *W1 = cur.take(64 * 64 * kResK[i]), *b1 = cur.take(64);
+        BN n2 = take_bn(cur, 64);
+        const float *W2 = cur.take(64 * 64 * kResK[i]), *b2 = cur.take(64);
+        m->res[i].n1 = pack_affine(pk, n1);
+        m->res[i].c1 = pack_conv(pk, W1, b1, nullptr, 64, 64, kResK[i]);
+        m->res[i].n2 = pack_affine(pk, n2);
+        m->res[i].c2 = pack_conv(pk, W2, b2, nullptr, 64, 64, kResK[i]);
+    }
+    for (int i = 0; i < 3; ++i) {
+        const int cin = i == 0 ? 64 : 16;
+        m->bil[i].lstm = alloc_lstm(pk, cin, 2);
+        pack_lstm_dir(pk, m->bil[i].lstm, 0, cur);
+        pack_lstm_dir(pk, m->bil[i].lstm, 1, cur);
+        const float *W = cur.take(16 * 32), *b = cur.take(16);
+        BN bn = take_bn(cur, 16);
+        m->bil[i].conv = pack_conv(pk, W, b, &bn, 16, 32, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+        const int64_t off = pk.add(AW_SIZE);
+        m->tr[i] = off;
+        pack_attention(pk, off, cur);
+        const float *g1 = cur.take(16), *b1 = cur.take(16);
+        const float *l1w = cur.take(128 * 16), *l1b = cur.take(128);
+        const float *l2w = cur.take(16 * 128), *l2b = cur.take(16);
+        const float *g2 = cur.take(16), *b2 = cur.take(16);
+        std::memcpy(&pk.host[off + AW_G1], g1, 16 * sizeof(float));
+        std::memcpy(&pk.host[off + AW_B1], b1, 16 * sizeof(float));
+        std::memcpy(&pk.host[off + AW_L1W], l1w, 2048 * sizeof(float));
+        std::memcpy(&pk.host[off + AW_L1B], l1b, 128 * sizeof(float));
+        for (int c = 0; c < 16; ++c)
+            for (int mm = 0; mm < 128; ++mm) pk.host[off + AW_L2W + mm * 16 + c] = l2w[c * 128 + mm];
+        std::memcpy(&pk.host[off + AW_L2B], l2b, 16 * sizeof(float));
+        std::memcpy(&pk.host[off + AW_G2], g2, 16 * sizeof(float));
+        std::memcpy(&pk.host[off + AW_B2], b2, 16 * sizeof(float));
+    }
+    // state-dict order: decoder_d.*, conv_d, pick_lstms.*, pick_attentions.*, pick_decoders.*, pick_convs.*
+    const float *dW[3][7], *dB[3][7], *hW[3], *hB[3];
+    for (int i = 0; i < 7; ++i) {
+        dW[0][i] = cur.take((int64_t)kDecC[i + 1] * kDecC[i] * kDecK[i]);
+        dB[0][i] = cur.take(kDecC[i + 1]);
+    }
+    hW[0] = cur.take(88);
+    hB[0] = cur.take(1);
+    for (int g = 0; g < 2; ++g) {
+        m->pick_lstm[g] = alloc_lstm(pk, 16, 1);
+        pack_lstm_dir(pk, m->pick_lstm[g], 0, cur);
+    }
+    for (int g = 0; g < 2; ++g) {
+        m->pick_attn[g] = pk.add(AW_SIZE);
+        pack_attention(pk, m->pick_attn[g], cur);
+    }
+    for (int g = 1; g < 3; ++g)
+        for (int i = 0; i < 7; ++i) {
+            dW[g][i] = cur.take((int64_t)kDecC[i + 1] * kDecC[i] * kDecK[i]);
+            dB[g][i] = cur.take(kDecC[i + 1]);
+        }
+    for (int g = 1; g < 3; ++g) {
+        hW[g] = cur.take(88);
+        hB[g] = cur.take(1);
+    }
+    // layer-major packing: the three decoders of one layer are equally sized consecutive blocks,
+    // so one grouped launch addresses them with a constant group stride
+    for (int i = 0; i < 7; ++i)
+        for (int g = 0; g < 3; ++g)
+            m->dec[g][i] = pack_conv(pk, dW[g][i], dB[g][i], nullptr, kDecC[i + 1], kDecC[i], kDecK[i]);
+    for (int g = 0; g < 3; ++g) m->head[g] = pack_conv(pk, hW[g], hB[g], nullptr, 1, 8, 11);
+    m->tap_names =
+        "enc0,enc1,enc2,enc3,enc4,enc5,enc6,res0,res1,res2,res3,res4,res5,res6,bilstm0_lstm,bilstm0,"
+        "bilstm1_lstm,bilstm1,bilstm2_lstm,bilstm2,transformer_d0,transformer_d,pick_lstm,pick_attn,"
+        "dec0,dec1,dec2,dec3,dec4,dec5,dec6";
+}
+
+static void build_pn(vp_model *m, Cursor &cur, Packed &pk) {
+    {
+        const float *W = cur.take(8 * 3 * 7), *b = cur.take(8);
+        BN bn = take_bn(cur, 8);
+        m->inc = pack_conv(pk, W, b, &bn, 8, 3, 7);
+    }
+    int last = 8;
+    for (int i = 0; i < 5; ++i) {
+        const int f = kPnC[i];
+        const float *W = cur.take((int64_t)f * last * 7);
+        BN bn = take_bn(cur, f);
+        m->down_same[i] = pack_conv(pk, W, nullptr, &bn, f, last, 7);
+        last = f;
+        if (i < 4) {
+            const float *W2 = cur.take((int64_t)f * f * 7);
+            BN bn2 = take_bn(cur, f);
+            m->down_down[i] = pack_conv(pk, W2, nullptr, &bn2, f, f, 7);
+        }
+    }
+    for (int i = 0; i < 4; ++i) {
+        const int f = kPnC[3 - i];
+        const float *W = cur.take((int64_t)last * f * 7);
+        BN bn = take_bn(cur, f);
+        m->up_t[i] = pack_convt(pk, W, bn, last, f);
+        last = f;
+        const float *W2 = cur.take((int64_t)f * 2 * f * 7);
+        BN bn2 = take_bn(cur, f);
+        m->up_same[i] = pack_conv(pk, W2, nullptr, &bn2, f, 2 * f, 7);
+    }
+    const float *W = cur.take(3 * 8), *b = cur.take(3);
+    m->outc = pack_conv(pk, W, b, nullptr, 3, 8, 1);
+    m->tap_names =
+        "inc,down0_same,down0_down,down1_same,down1_down,down2_same,down2_down,down3_same,down3_down,down4_same,"
+        "up0_cat,up0_same,up1_cat,up1_same,up2_cat,up2_same,up3_cat,up3_same";
+}
+
+// ---- forward plan ---------------------------------------------------------------------------------
+struct Arena {
+    char *base;
+    int64_t used, cap;
+    float *take(int64_t n_floats) {
+        const int64_t off = align_up(used, 256);
+        used = off + n_floats * (int64_t)sizeof(float);
+        return base ? reinterpret_cast<float *>(base + off) : nullptr;
+    }
+};
+
+struct Tap {
+    const char *name;
+    const float *ptr;
+    int64_t floats;
+};
+
+struct Runner {
+    vp_model *m;
+    cudaStream_t s;
+    int B;
+    bool dry;               // only measure the workspace
+    const char *stop_name;  // stop after this tap (debug)
+    Tap hit{nullptr, nullptr, 0};
+    bool stopped = false;
+    int rc = VP_OK;
+
+    const float *W(int64_t off) const { return m->d_weights + off; }
+
+    bool tap(const char *name, const float *ptr, int64_t floats) {
+        if (stop_name && !stopped && std::strcmp(stop_name, name) == 0) {
+            hit = Tap{name, ptr, floats};
+            stopped = true;
+        }
+        return stopped;
+    }
+    bool go() const { return !dry && !stopped && rc == VP_OK; }
+
+    // generic conv step
+    void conv(const ConvW &cw, int stride, int ups, int pool, int act, const AffW *pre, const float *res, int64_t r_bs,
+              const float *x, int64_t x_bs, int64_t x_gs, int Lin, int Lin_eff, int pad_left, int Lconv, int Lout,
+              float *y, int64_t y_bs, int64_t y_gs, int G, int64_t w_gs, int64_t b_gs) {
+        if (!go()) return;
+        ConvKey key{cw.cin, cw.coutp, cw.k, stride, ups, pool, act, pre ? 1 : 0, res ? 1 : 0};
+        conv_launch_fn fn = find_conv_fp32(key, Lconv);
+        if (!fn) {
+            set_error("no fp32 conv instance for cin=%d coutp=%d k=%d stride=%d ups=%d pool=%d act=%d pre=%d res=%d",
+                      key.cin, key.coutp, key.k, key.stride, key.ups, key.pool, key.act, key.pre, key.res);
+            rc = VP_ERR_UNSUPPORTED;
+            return;
+        }
+        ConvP p;
+        p.x = x;
+        p.x_bs = x_bs;
+        p.x_gs = x_gs;
+        p.w = W(cw.w);
+        p.w_gs = w_gs;
+        p.bias = W(cw.b);
+        p.b_gs = b_gs;
+        p.pre_scale = pre ? W(pre->scale) : nullptr;
+        p.pre_shift = pre ? W(pre->shift) : nullptr;
+        p.res = res;
+        p.r_bs = r_bs;
+        p.y = y;
+        p.y_bs = y_bs;
+        p.y_gs = y_gs;
+        p.Lin = Lin;
+        p.Lin_eff = Lin_eff;
+        p.Lconv = Lconv;
+        p.Lout = Lout;
+        p.pad_left = pad_left;
+        p.cout_store = cw.cout;
+        rc = fn(p, B, G, s);
+    }
+};
+
+static int run_eqt(Runner &r, const float *x, float *y, Arena &ar) {
+    vp_model *m = r.m;
+    const int64_t B = r.B;
+    const int L = m->in_samples;
+    // lengths through the encoder
+    int len[8];
+    len[0] = L;
+    for (int i = 0; i < 7; ++i) len[i + 1] = (len[i] + (len[i] & 1)) / 2;
+    const int T = len[7];
+    // decoder lengths (SeisBench Decoder crops: drop the last sample where the encoder padded)
+    int dlen[8], crop[7];
+    dlen[0] = T;
+    for (int i = 0; i < 7; ++i) {
+        crop[i] = (len[6 - i] & 1) ? 1 : 0;
+        dlen[i + 1] = 2 * dlen[i] - crop[i];
+    }
+    if (dlen[7] != L) {
+        set_error("EQTransformer: decoder length %d != in_samples %d", dlen[7], L);
+        return VP_ERR_ARG;
+    }
+    // workspace
+    int64_t big = 0;
+    for (int i = 0; i < 7; ++i) {
+        big = std::max<int64_t>(big, (int64_t)kEncC[i + 1] * len[i + 1]);
+        big = std::max<int64_t>(big, 3 * (int64_t)kDecC[i + 1] * dlen[i + 1]);
+    }
+    float *P = ar.take(B * big), *Q = ar.take(B * big);
+    float *r0 = ar.take(B * 64 * T), *r1 = ar.take(B * 64 * T), *r2 = ar.take(B * 64 * T);
+    float *lo = ar.take(B * 32 * T);
+    float *s0 = ar.take(B * 16 * T), *s1 = ar.take(B * 16 * T);
+    float *din = ar.take(3 * B * 16 * T);  // [group][B][16][T]: decoder inputs
+    float *plo = ar.take(2 * B * 16 * T);  // pick LSTM outputs [group][B][16][T]
+    if (r.dry) return VP_OK;
+
+    // ---- encoder
+    const float *cur = x;
+    int cur_c = 3;
+    float *pp[2] = {P, Q};
+    static const char *enc_names[7] = {"enc0", "enc1", "enc2", "enc3", "enc4", "enc5", "enc6"};
+    for (int i = 0; i < 7; ++i) {
+        float *dst = (i == 6) ? r0 : pp[i & 1];
+        const ConvW &cw = m->enc[i];
+        r.conv(cw, 1, 1, 2, ACT_RELU, nullptr, nullptr, 0, cur, (int64_t)cur_c * len[i], 0, len[i], len[i], cw.k / 2,
+               len[i], len[i + 1], dst, (int64_t)cw.cout * len[i + 1], 0, 1, 0, 0);
+        if (r.tap(enc_names[i], dst, B * cw.cout * len[i + 1])) return r.rc;
+        cur = dst;
+        cur_c = cw.cout;
+    }
+    // ---- res-CNN stack: x in ra; tmp r1; out rb
+    static const char *res_names[7] = {"res0", "res1", "res2", "res3", "res4", "res5", "res6"};
+    float *ra = r0, *rb = r2;
+    for (int i = 0; i < 7; ++i) {
+        const int k = kResK[i];
+        const int pad = (k == 3) ? 1 : 0;  // k == 2: right-pad one zero == out-of-range reads as 0
+        r.conv(m->res[i].c1, 1, 1, 1, ACT_NONE, &m->res[i].n1, nullptr, 0, ra, 64 * T, 0, T, T, pad, T, T, r1, 64 * T, 0,
+               1, 0, 0);
+        r.conv(m->res[i].c2, 1, 1, 1, ACT_NONE, &m->res[i].n2, ra, 64 * T, r1, 64 * T, 0, T, T, pad, T, T, rb, 64 * T,
+               0, 1, 0, 0);
+        if (r.tap(res_names[i], rb, B * 64 * T)) return r.rc;
+        std::swap(ra, rb);
+    }
+    // ---- BiLSTM blocks
+    static const char *bl_names[3][2] = {{"bilstm0_lstm", "bilstm0"}, {"bilstm1_lstm", "bilstm1"}, {"bilstm2_lstm", "bilstm2"}};
+    const float *seq = ra;
+    int seq_c = 64;
+    float *sp[2] = {s0, s1};
+    for (int i = 0; i < 3; ++i) {
+        if (r.go()) {
+            LstmP p;
+            p.x = seq;
+            p.x_bs = (int64_t)seq_c * T;
+            p.x_gs = 0;
+            p.w_ih = r.W(m->bil[i].lstm.ih);
+            p.w_hh = r.W(m->bil[i].lstm.hh);
+            p.bias = r.W(m->bil[i].lstm.b);
+            p.w_gs_ih = p.w_gs_hh = p.w_gs_b = 0;
+            p.y = lo;
+            p.y_bs = 32 * T;
+            p.y_gs = 0;
+            p.T = T;
+            p.ndir = 2;
+            p.B = (int)B;
+            r.rc = launch_lstm(seq_c, p, 1, r.s);
+        }
+        if (r.tap(bl_names[i][0], lo, B * 32 * T)) return r.rc;
+        float *dst = sp[i & 1];
+        r.conv(m->bil[i].conv, 1, 1, 1, ACT_NONE, nullptr, nullptr, 0, lo, 32 * T, 0, T, T, 0, T, T, dst, 16 * T, 0, 1, 0,
+               0);
+        if (r.tap(bl_names[i][1], dst, B * 16 * T)) return r.rc;
+        seq = dst;
+        seq_c = 16;
+    }
+    // ---- transformers: seq (s0 after 3 blocks) -> s1 -> din[0]
+    {
+        const float *tin = seq;
+        float *tout[2] = {(seq == s0) ? s1 : s0, din};
+        static const char *tn[2] = {"transformer_d0", "transformer_d"};
+        for (int i = 0; i < 2; ++i) {
+            if (r.go()) {
+                AttnP p;
+                p.x = tin;
+                p.x_bs = 16 * T;
+                p.x_gs = 0;
+                p.w = r.W(m->tr[i]);
+                p.w_gs = 0;
+                p.y = tout[i];
+                p.y_bs = 16 * T;
+                p.y_gs = 0;
+                p.T = T;
+                p.B = (int)B;
+                p.width = 0;
+                p.mode = 0;
+                r.rc = launch_attention(p, 1, r.s);
+            }
+            if (r.tap(tn[i], tout[i], B * 16 * T)) return r.rc;
+            tin = tout[i];
+        }
+    }
+    // ---- pick branches: uni-LSTM -> banded attention, both branches as 2 groups
+    if (r.go()) {
+        LstmP p;
+        p.x = din;
+        p.x_bs = 16 * T;
+        p.x_gs = 0;  // both read the shared encoder output
+        p.w_ih = r.W(m->pick_lstm[0].ih);
+        p.w_hh = r.W(m->pick_lstm[0].hh);
+        p.bias = r.W(m->pick_lstm[0].b);
+        p.w_gs_ih = m->pick_lstm[1].ih - m->pick_lstm[0].ih;
+        p.w_gs_hh = m->pick_lstm[1].hh - m->pick_lstm[0].hh;
+        p.w_gs_b = m->pick_lstm[1].b - m->pick_lstm[0].b;
+        p.y = plo;
+        p.y_bs = 16 * T;
+        p.y_gs = B * 16 * T;
+        p.T = T;
+        p.ndir = 1;
+        p.B = (int)B;
+        r.rc = launch_lstm(16, p, 2, r.s);
+    }
+    if (r.tap("pick_lstm", plo, 2 * B * 16 * T)) return r.rc;
+    if (r.go()) {
+        AttnP p;
+        p.x = plo;
+        p.x_bs = 16 * T;
+        p.x_gs = B * 16 * T;
+        p.w = r.W(m->pick_attn[0]);
+        p.w_gs = m->pick_attn[1] - m->pick_attn[0];
+        p.y = din + B * 16 * T;
+        p.y_bs = 16 * T;
+        p.y_gs = B * 16 * T;
+        p.T = T;
+        p.B = (int)B;
+        p.width = 3;
+        p.mode = 1;
+        r.rc = launch_attention(p, 2, r.s);
+    }
+    if (r.tap("pick_attn", din + B * 16 * T, 2 * B * 16 * T)) return r.rc;
+    // ---- the three decoders as 3 groups per layer
+    static const char *dec_names[7] = {"dec0", "dec1", "dec2", "dec3", "dec4", "dec5", "dec6"};
+    const float *dcur = din;
+    for (int i = 0; i < 7; ++i) {
+        float *dst = pp[i & 1];
+        const ConvW &cw = m->dec[0][i];
+        const int64_t w_gs = m->dec[1][i].w - m->dec[0][i].w, b_gs = m->dec[1][i].b - m->dec[0][i].b;
+        r.conv(cw, 1, 2, 1, ACT_RELU, nullptr, nullptr, 0, dcur, (int64_t)cw.cin * dlen[i], B * cw.cin * dlen[i], dlen[i],
+               dlen[i + 1], cw.k / 2, dlen[i + 1], dlen[i + 1], dst, (int64_t)cw.cout * dlen[i + 1],
+               B * cw.cout * dlen[i + 1], 3, w_gs, b_gs);
+        if (r.tap(dec_names[i], dst, 3 * B * cw.cout * dlen[i + 1])) return r.rc;
+        dcur = dst;
+    }
+    // ---- heads: sigmoid(conv k11) -> y (B, 3, L)
+    {
+        const ConvW &cw = m->head[0];
+        const int64_t w_gs = m->head[1].w - m->head[0].w, b_gs = m->head[1].b - m->head[0].b;
+        r.conv(cw, 1, 1, 1, ACT_SIGMOID, nullptr, nullptr, 0, dcur, 8 * (int64_t)L, B * 8 * (int64_t)L, L, L, 5, L, L, y,
+               3 * (int64_t)L, L, 3, w_gs, b_gs);
+    }
+    return r.rc;
+}
+
+static int run_pn(Runner &r, const float *x, float *y, Arena &ar) {
+    vp_model *m = r.m;
+    const int64_t B = r.B;
+    const int L0 = m->in_samples;
+    // SeisBench PhaseNet: manual pads before the stride-4 convs
+    static const int padl[4] = {3, 2, 1, 2}, padr[4] = {3, 3, 3, 3};
+    int len[5];
+    len[0] = L0;
+    for (int i = 0; i < 4; ++i) len[i + 1] = (len[i] + padl[i] + padr[i] - 7) / 4 + 1;
+    float *b_inc = ar.take(B * 8 * len[0]);
+    float *cat[4];  // cat[i]: (B, 2*C_i, len[i]) = [skip_i | up]
+    float *dn[4];
+    for (int i = 0; i < 4; ++i) {
+        cat[i] = ar.take(B * 2 * kPnC[i] * len[i]);
+        dn[i] = ar.take(B * kPnC[i] * len[i + 1]);
+    }
+    float *d4 = ar.take(B * 128 * len[4]);
+    float *us[4];
+    for (int i = 0; i < 4; ++i) us[i] = ar.take(B * kPnC[3 - i] * len[3 - i]);
+    if (r.dry) return VP_OK;
+
+    r.conv(m->inc, 1, 1, 1, ACT_RELU, nullptr, nullptr, 0, x, 3 * (int64_t)L0, 0, L0, L0, 3, L0, L0, b_inc,
+           8 * (int64_t)L0, 0, 1, 0, 0);
+    if (r.tap("inc", b_inc, B * 8 * L0)) return r.rc;
+    static const char *ds_names[5] = {"down0_same", "down1_same", "down2_same", "down3_same", "down4_same"};
+    static const char *dd_names[4] = {"down0_down", "down1_down", "down2_down", "down3_down"};
+    const float *cur = b_inc;
+    int cur_c = 8;
+    for (int i = 0; i < 5; ++i) {
+        const int f = kPnC[i];
+        if (i < 4) {
+            // conv_same writes the skip half of the concat buffer (batch stride 2*f*len)
+            r.conv(m->down_same[i], 1, 1, 1, ACT_RELU, nullptr, nullptr, 0, cur, (int64_t)cur_c * len[i], 0, len[i], len[i],
+                   3, len[i], len[i], cat[i], 2 * (int64_t)f * len[i], 0, 1, 0, 0);
+            if (r.tap(ds_names[i], cat[i], B * 2 * f * len[i])) return r.rc;  // NOTE: strided tap (skip half valid)
+            r.conv(m->down_down[i], 4, 1, 1, ACT_RELU, nullptr, nullptr, 0, cat[i], 2 * (int64_t)f * len[i], 0, len[i],
+                   len[i], padl[i], len[i + 1], len[i + 1], dn[i], (int64_t)f * len[i + 1], 0, 1, 0, 0);
+            if (r.tap(dd_names[i], dn[i], B * f * len[i + 1])) return r.rc;
+            cur = dn[i];
+            cur_c = f;
+        } else {
+            r.conv(m->down_same[i], 1, 1, 1, ACT_RELU, nullptr, nullptr, 0, cur, (int64_t)cur_c * len[i], 0, len[i], len[i],
+                   3, len[i], len[i], d4, (int64_t)f * len[i], 0, 1, 0, 0);
+            if (r.tap(ds_names[i], d4, B * f * len[i])) return r.rc;
+            cur = d4;
+            cur_c = f;
+        }
+    }
+    static const char *uc_names[4] = {"up0_cat", "up1_cat", "up2_cat", "up3_cat"};
+    static const char *us_names[4] = {"up0_same", "up1_same", "up2_same", "up3_same"};
+    int cur_len = len[4];
+    for (int i = 0; i < 4; ++i) {
+        const int lvl = 3 - i;
+        const int f = kPnC[lvl];
+        const int Ls = len[lvl];
+        const int Lt = (cur_len - 1) * 4 + 7 - 3;  // ConvTranspose1d output, cropped [1:-2]
+        const int off = (Lt - Ls) / 2;
+        if (off < 0 || off + Ls > Lt) {
+            set_error("PhaseNet: skip merge mismatch (Lt=%d, Ls=%d)", Lt, Ls);
+            return VP_ERR_ARG;
+        }
+        if (r.go()) {
+            ConvTP p;
+            p.x = cur;
+            p.x_bs = (int64_t)cur_c * cur_len;
+            p.w = r.W(m->up_t[i].w);
+            p.bias = r.W(m->up_t[i].b);
+            p.y = cat[lvl] + (int64_t)f * Ls;  // second half of the concat buffer
+            p.y_bs = 2 * (int64_t)f * Ls;
+            p.Lin = cur_len;
+            p.Lout = Ls;
+            p.shift = 1 + off;
+            r.rc = launch_convt_fp32(cur_c, f, p, (int)B, r.s);
+        }
+        if (r.tap(uc_names[i], cat[lvl], B * 2 * f * Ls)) return r.rc;
+        r.conv(m->up_same[i], 1, 1, 1, ACT_RELU, nullptr, nullptr, 0, cat[lvl], 2 * (int64_t)f * Ls, 0, Ls, Ls, 3, Ls, Ls,
+               us[i], (int64_t)f * Ls, 0, 1, 0, 0);
+        if (r.tap(us_names[i], us[i], B * f * Ls)) return r.rc;
+        cur = us[i];
+        cur_c = f;
+        cur_len = Ls;
+    }
+    r.conv(m->outc, 1, 1, 1, ACT_SOFTMAX3, nullptr, nullptr, 0, cur, 8 * (int64_t)L0, 0, L0, L0, 0, L0, L0, y,
+           3 * (int64_t)L0, 0, 1, 0, 0);
+    return r.rc;
+}
+
+static int run_forward(vp_model *m, const float *x, int64_t B, float *y, void *ws, int64_t ws_bytes, int precision,
+                       const char *stop, Tap *hit, cudaStream_t s, int64_t *need_bytes) {
+    if (precision != VP_PREC_FP32) {
+        set_error("precision mode %d is not available in this build (fp32 only)", precision);
+        return VP_ERR_UNSUPPORTED;
+    }
+    Runner r;
+    r.m = m;
+    r.s = s;
+    r.B = (int)B;
+    r.dry = need_bytes != nullptr;
+    r.stop_name = stop;
+    Arena ar{(char *)ws, 0, ws_bytes};
+    if (r.dry) ar.base = nullptr;
+    int rc = (m->kind == VP_KIND_EQTRANSFORMER) ? run_eqt(r, x, y, ar) : run_pn(r, x, y, ar);
+    if (need_bytes) *need_bytes = align_up(ar.used, 256);
+    if (rc != VP_OK) return rc;
+    if (!r.dry && ar.used > ws_bytes) {
+        set_error("forward workspace too small: need %lld bytes, have %lld", (long long)ar.used, (long long)ws_bytes);
+        return VP_ERR_WORKSPACE;
+    }
+    if (hit) *hit = r.hit;
+    return VP_OK;
+}
+
+// ============================================================================================ C ABI
+extern "C" int vp_version(void) { return 100; }
+extern "C" const char *vp_last_error(void) { return g_error.c_str(); }
+extern "C" int64_t vp_launch_count(int reset) {
+    const int64_t v = g_launches;
+    if (reset) g_launches = 0;
+    return v;
+}
+extern "C" int64_t vp_model_expected_floats(int kind) {
+    return kind == VP_KIND_EQTRANSFORMER ? EQT_FLOATS : kind == VP_KIND_PHASENET ? PN_FLOATS : -1;
+}
+
+extern "C" int vp_model_create(int kind, const float *weights, int64_t n_floats, int device, vp_model **out) {
+    VP_REQUIRE(out && weights, VP_ERR_ARG, "vp_model_create: null pointer");
+    VP_REQUIRE(kind == VP_KIND_EQTRANSFORMER || kind == VP_KIND_PHASENET, VP_ERR_ARG, "vp_model_create: unknown kind %d", kind);
+    VP_REQUIRE(n_floats == vp_model_expected_floats(kind), VP_ERR_ARG,
+               "vp_model_create: expected %lld weight floats for kind %d, got %lld",
+               (long long)vp_model_expected_floats(kind), kind, (long long)n_floats);
+    int ndev = 0;
+    VP_CUDA_CHECK(cudaGetDeviceCount(&ndev));
+    VP_REQUIRE(device >= 0 && device < ndev, VP_ERR_CUDA, "vp_model_create: CUDA device %d not available (%d devices)", device, ndev);
+    VP_CUDA_CHECK(cudaSetDevice(device));
+    vp_model *m = new vp_model();
+    m->kind = kind;
+    m->device = device;
+    m->in_samples = kind == VP_KIND_EQTRANSFORMER ? 6000 : 3001;
+    Cursor cur{weights, n_floats};
+    Packed pk;
+    if (kind == VP_KIND_EQTRANSFORMER) build_eqt(m, cur, pk); else build_pn(m, cur, pk);
+    if (cur.left != 0) {
+        set_error("vp_model_create: weight walk left %lld floats (layout mismatch)", (long long)cur.left);
+        delete m;
+        return VP_ERR_ARG;
+    }
+    m->n_packed = (int64_t)pk.host.size();
+    cudaError_t e = cudaMalloc(&m->d_weights, (pk.host.size() + 64) * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(m->d_weights, pk.host.data(), pk.host.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        set_error("vp_model_create: uploading weights failed: %s", cudaGetErrorString(e));
+        if (m->d_weights) cudaFree(m->d_weights);
+        delete m;
+        return VP_ERR_CUDA;
+    }
+    *out = m;
+    return VP_OK;
+}
+
+extern "C" int vp_model_destroy(vp_model *m) {
+    if (!m) return VP_OK;
+    if (m->d_weights) cudaFree(m->d_weights);
+    delete m;
+    return VP_OK;
+}
+extern "C" int vp_model_kind(const vp_model *m) { return m ? m->kind : VP_ERR_ARG; }
+extern "C" int vp_model_in_samples(const vp_model *m) { return m ? m->in_samples : VP_ERR_ARG; }
+extern "C" const char *vp_forward_tap_names(const vp_model *m) { return m ? m->tap_names.c_str() : ""; }
+
+extern "C" int64_t vp_forward_workspace_bytes(const vp_model *m, int64_t n_windows, int precision) {
+    if (!m || n_windows < 0) return VP_ERR_ARG;
+    const int64_t B = std::min<int64_t>(std::max<int64_t>(n_windows, 1), MAX_CHUNK);
+    int64_t need = 0;
+    int rc = run_forward(const_cast<vp_model *>(m), nullptr, B, nullptr, nullptr, 0, precision, nullptr, nullptr, 0, &need);
+    return rc == VP_OK ? need : rc;
+}
+
+extern "C" int vp_forward(vp_model *m, const float *x, int64_t n_windows, float *y, void *workspace,
+                          int64_t workspace_bytes, int precision, void *stream) {
+    VP_REQUIRE(m && x && y && workspace, VP_ERR_ARG, "vp_forward: null pointer");
+    const int64_t L = m->in_samples;
+    for (int64_t b0 = 0; b0 < n_windows; b0 += MAX_CHUNK) {
+        const int64_t nb = std::min<int64_t>(MAX_CHUNK, n_windows - b0);
+        int rc = run_forward(m, x + b0 * 3 * L, nb, y + b0 * 3 * L, workspace, workspace_bytes, precision, nullptr,
+                             nullptr, (cudaStream_t)stream, nullptr);
+        if (rc != VP_OK) return rc;
+    }
+    return VP_OK;
+}
+
+extern "C" int vp_forward_tap(vp_model *m, const float *x, int64_t n_windows, float *y, void *workspace,
+                              int64_t workspace_bytes, int precision, const char *tap_name, float *tap_out,
+                              int64_t tap_capacity, int64_t *tap_floats, void *stream) {
+    VP_REQUIRE(m && x && y && workspace && tap_name && tap_out && tap_floats, VP_ERR_ARG, "vp_forward_tap: null pointer");
+    VP_REQUIRE(n_windows <= MAX_CHUNK, VP_ERR_ARG, "vp_forward_tap: at most %lld windows", (long long)MAX_CHUNK);
+    Tap hit{nullptr, nullptr, 0};
+    int rc = run_forward(m, x, n_windows, y, workspace, workspace_bytes, precision, tap_name, &hit, (cudaStream_t)stream, nullptr);
+    if (rc != VP_OK) return rc;
+    VP_REQUIRE(hit.ptr != nullptr, VP_ERR_ARG, "vp_forward_tap: unknown tap '%s' (have: %s)", tap_name, m->tap_names.c_str());
+    VP_REQUIRE(hit.floats <= tap_capacity, VP_ERR_CAPACITY, "vp_forward_tap: tap '%s' needs %lld floats, capacity %lld",
+               tap_name, (long long)hit.floats, (long long)tap_capacity);
+    VP_CUDA_CHECK(cudaMemcpyAsync(tap_out, hit.ptr, hit.floats * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    *tap_floats = hit.floats;
+    return VP_OK;
+}

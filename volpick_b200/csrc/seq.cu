@@ -1,0 +1,293 @@
+// Sequence kernels of the EQTransformer bottleneck (T = 47): LSTM recurrences and the additive
+// self-attention / transformer blocks.  fp32, precise transcendentals (expf / tanhf).
+//
+// Replaces nn.LSTM(in, 16[, bidirectional]) inside BiLSTMBlock / pick_lstms, SeqSelfAttention,
+// LayerNormalization, FeedForward and Transformer of seisbench/models/eqtransformer.py
+// (weight shapes from
+// /root/reference/Final_models/volpick/eqtransformer/volpick.pt.v1).
+#include "common.cuh"
+
+namespace vp {
+
+// ---------------------------------------------------------------------------------------------
+// LSTM: 16 lanes = the 16 hidden units of one (window, direction) sequence; a 128-thread CTA runs
+// 8 sequences.  W_hh lives in registers (4 gates x 16), W_ih in shared memory as float4 per
+// (input channel, unit) = the 4 gates; h is exchanged with width-16 shuffles.
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+template <int CIN>
+__global__ void __launch_bounds__(128) lstm_kernel(const LstmP p) {
+    extern __shared__ __align__(16) float smem[];
+    float4 *wih = reinterpret_cast<float4 *>(smem);  // [ndir][CIN][16]
+    const int g = blockIdx.y;
+    const int tid = threadIdx.x;
+    const int ndir = p.ndir;
+    {
+        const float4 *src = reinterpret_cast<const float4 *>(p.w_ih + (int64_t)g * p.w_gs_ih);
+        for (int i = tid; i < ndir * CIN * 16; i += 128) wih[i] = __ldg(src + i);
+    }
+    __syncthreads();
+
+    const int j = tid & 15;
+    const int64_t seq = (int64_t)blockIdx.x * 8 + (tid >> 4);
+    const int64_t nseq = (int64_t)p.B * ndir;
+    const bool active = seq < nseq;
+    const int64_t b = active ? seq / ndir : 0;
+    const int dir = active ? (int)(seq % ndir) : 0;
+    const unsigned hmask = 0xffffu << (tid & 16);
+
+    float4 whh[16];
+    {
+        const float4 *src = reinterpret_cast<const float4 *>(p.w_hh + (int64_t)g * p.w_gs_hh) + dir * 256;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) whh[k] = __ldg(src + k * 16 + j);
+    }
+    const float4 bias = __ldg(reinterpret_cast<const float4 *>(p.bias + (int64_t)g * p.w_gs_b) + dir * 16 + j);
+    const float4 *wi = wih + dir * CIN * 16 + j;
+    const float *xb = p.x + (int64_t)g * p.x_gs + b * p.x_bs;
+    float *yb = p.y + (int64_t)g * p.y_gs + b * p.y_bs + (int64_t)(dir * 16 + j) * p.T;
+    const int T = p.T;
+
+    float h = 0.f, c = 0.f;
+    for (int s = 0; s < T; ++s) {
+        const int t = dir ? (T - 1 - s) : s;
+        float4 a = bias;
+#pragma unroll 8
+        for (int ci = 0; ci < CIN; ++ci) {
+            const float xv = __ldg(xb + (int64_t)ci * T + t);
+            const float4 w = wi[ci * 16];
+            a.x = fmaf(w.x, xv, a.x);
+            a.y = fmaf(w.y, xv, a.y);
+            a.z = fmaf(w.z, xv, a.z);
+            a.w = fmaf(w.w, xv, a.w);
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const float hk = __shfl_sync(hmask, h, k, 16);
+            a.x = fmaf(whh[k].x, hk, a.x);
+            a.y = fmaf(whh[k].y, hk, a.y);
+            a.z = fmaf(whh[k].z, hk, a.z);
+            a.w = fmaf(whh[k].w, hk, a.w);
+        }
+        const float ig = sigmoidf_(a.x), fg = sigmoidf_(a.y), gg = tanhf(a.z), og = sigmoidf_(a.w);
+        c = fmaf(fg, c, ig * gg);
+        h = og * tanhf(c);
+        if (active) yb[t] = h;
+    }
+}
+
+int launch_lstm(int cin, const LstmP &p, int G, cudaStream_t s) {
+    const int64_t nseq = (int64_t)p.B * p.ndir;
+    dim3 grid((unsigned)((nseq + 7) / 8), G);
+    const size_t smem = (size_t)p.ndir * cin * 16 * sizeof(float4);
+    if (cin == 64) {
+        lstm_kernel<64><<<grid, 128, smem, s>>>(p);
+    } else if (cin == 16) {
+        lstm_kernel<16><<<grid, 128, smem, s>>>(p);
+    } else {
+        set_error("no LSTM instance for %d input channels", cin);
+        return VP_ERR_UNSUPPORTED;
+    }
+    VP_LAUNCH_CHECK();
+    return VP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Additive self-attention (+ optional transformer tail).  One thread = one query time step of one
+// window; a 128-thread CTA handles 2 windows.
+constexpr int AT_MAXT = 48;   // T <= 48 (T = 47 for 6000-sample windows)
+constexpr int AT_XP = 17;     // pitch of Xs rows (time-major x)
+constexpr int AT_KP = 36;     // pitch of the k-projection rows (float4 aligned)
+constexpr int AT_EP = 49;     // pitch of the emission rows
+constexpr int AT_OFF_K = (AW_SIZE + 3) & ~3;                      // 16-byte aligned (float4 reads)
+constexpr int AT_OFF_X = AT_OFF_K + 2 * AT_MAXT * AT_KP;
+constexpr int AT_OFF_E = AT_OFF_X + 2 * AT_MAXT * AT_XP;
+constexpr int AT_SMEM_FLOATS = AT_OFF_E + 2 * AT_MAXT * AT_EP;
+
+__global__ void __launch_bounds__(128) attention_kernel(const AttnP p) {
+    extern __shared__ __align__(16) float at_smem[];
+    float *wsm = at_smem;                                               // [AW_SIZE]
+    float(*Ks)[AT_MAXT * AT_KP] = reinterpret_cast<float(*)[AT_MAXT * AT_KP]>(at_smem + AT_OFF_K);
+    float(*Xs)[AT_MAXT * AT_XP] = reinterpret_cast<float(*)[AT_MAXT * AT_XP]>(at_smem + AT_OFF_X);
+    float(*Es)[AT_MAXT * AT_EP] = reinterpret_cast<float(*)[AT_MAXT * AT_EP]>(at_smem + AT_OFF_E);
+
+    const int tid = threadIdx.x;
+    const int g = blockIdx.y;
+    const int T = p.T;
+    {
+        const float *src = p.w + (int64_t)g * p.w_gs;
+        const int n = (p.mode == 0) ? AW_SIZE : AW_G1;
+        for (int i = tid; i < n; i += 128) wsm[i] = __ldg(src + i);
+    }
+    const int wl = tid >> 6;  // window slot in the CTA
+    const int i = tid & 63;   // query time step
+    const int64_t b = (int64_t)blockIdx.x * 2 + wl;
+    const bool bval = b < p.B;
+    const float *xb = p.x + (int64_t)g * p.x_gs + (bval ? b : 0) * p.x_bs;
+    // transpose-load x (16, T) -> Xs[t][c]
+    for (int idx = i; idx < 16 * T; idx += 64) {
+        const int c = idx / T, t = idx - c * T;
+        Xs[wl][t * AT_XP + c] = bval ? __ldg(xb + idx) : 0.f;
+    }
+    __syncthreads();
+
+    const bool act = bval && i < T;
+    float x[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) x[c] = act ? Xs[wl][i * AT_XP + c] : 0.f;
+
+    float q[32];
+#pragma unroll
+    for (int u = 0; u < 32; ++u) q[u] = wsm[AW_BH + u];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+#pragma unroll
+        for (int u = 0; u < 32; ++u) q[u] = fmaf(x[c], wsm[AW_WT + c * 32 + u], q[u]);
+    }
+    if (i < T) {
+#pragma unroll
+        for (int u = 0; u < 32; ++u) {
+            float kv = 0.f;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) kv = fmaf(x[c], wsm[AW_WX + c * 32 + u], kv);
+            Ks[wl][i * AT_KP + u] = kv;
+        }
+    }
+    __syncthreads();
+
+    // emissions e_ij = Wa . tanh(q_i + k_j + bh) + ba, row max
+    float emax = -INFINITY;
+    const float ba = wsm[AW_BA];
+    for (int jj = 0; jj < T; ++jj) {
+        const float4 *kr = reinterpret_cast<const float4 *>(&Ks[wl][jj * AT_KP]);
+        float e = ba;
+#pragma unroll
+        for (int u4 = 0; u4 < 8; ++u4) {
+            const float4 k4 = kr[u4];
+            e = fmaf(wsm[AW_WA + u4 * 4 + 0], tanhf(q[u4 * 4 + 0] + k4.x), e);
+            e = fmaf(wsm[AW_WA + u4 * 4 + 1], tanhf(q[u4 * 4 + 1] + k4.y), e);
+            e = fmaf(wsm[AW_WA + u4 * 4 + 2], tanhf(q[u4 * 4 + 2] + k4.z), e);
+            e = fmaf(wsm[AW_WA + u4 * 4 + 3], tanhf(q[u4 * 4 + 3] + k4.w), e);
+        }
+        if (i < T) Es[wl][i * AT_EP + jj] = e;
+        emax = fmaxf(emax, e);
+    }
+    // softmax over j with the row max over the FULL row, band mask applied after the exp,
+    // denominator + 1e-5 (SeqSelfAttention, original_compatible=False)
+    float v[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) v[c] = 0.f;
+    float ssum = 0.f;
+    const int half = p.width / 2;
+    if (i < T) {
+        for (int jj = 0; jj < T; ++jj) {
+            float w = expf(Es[wl][i * AT_EP + jj] - emax);
+            if (p.width > 0) {
+                const int lower = jj - half;
+                if (!(lower <= i && i < lower + p.width)) w = 0.f;
+            }
+            ssum += w;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) v[c] = fmaf(w, Xs[wl][jj * AT_XP + c], v[c]);
+        }
+    }
+    const float inv = 1.f / (ssum + 1e-5f);
+#pragma unroll
+    for (int c = 0; c < 16; ++c) v[c] *= inv;
+
+    float *yb = p.y + (int64_t)g * p.y_gs + (bval ? b : 0) * p.y_bs;
+    if (p.mode == 1) {
+        if (act) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) yb[c * T + i] = v[c];
+        }
+        return;
+    }
+    // transformer tail: y = LN(x + attn); out = LN(y + lin2(relu(lin1(y))))
+    float y[16];
+    {
+        float mean = 0.f;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            y[c] = x[c] + v[c];
+            mean += y[c];
+        }
+        mean *= (1.f / 16.f);
+        float var = 0.f;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            const float d = y[c] - mean;
+            var = fmaf(d, d, var);
+        }
+        var = var * (1.f / 16.f) + 1e-14f;
+        const float sd = sqrtf(var);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) y[c] = (y[c] - mean) / sd * wsm[AW_G1 + c] + wsm[AW_B1 + c];
+    }
+    float o[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) o[c] = wsm[AW_L2B + c];
+#pragma unroll 4
+    for (int m = 0; m < 128; ++m) {
+        const float4 *w1 = reinterpret_cast<const float4 *>(&wsm[AW_L1W + m * 16]);
+        float hsum = wsm[AW_L1B + m];
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+            const float4 w = w1[c4];
+            hsum = fmaf(w.x, y[c4 * 4 + 0], hsum);
+            hsum = fmaf(w.y, y[c4 * 4 + 1], hsum);
+            hsum = fmaf(w.z, y[c4 * 4 + 2], hsum);
+            hsum = fmaf(w.w, y[c4 * 4 + 3], hsum);
+        }
+        hsum = fmaxf(hsum, 0.f);
+        const float4 *w2 = reinterpret_cast<const float4 *>(&wsm[AW_L2W + m * 16]);
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+            const float4 w = w2[c4];
+            o[c4 * 4 + 0] = fmaf(w.x, hsum, o[c4 * 4 + 0]);
+            o[c4 * 4 + 1] = fmaf(w.y, hsum, o[c4 * 4 + 1]);
+            o[c4 * 4 + 2] = fmaf(w.z, hsum, o[c4 * 4 + 2]);
+            o[c4 * 4 + 3] = fmaf(w.w, hsum, o[c4 * 4 + 3]);
+        }
+    }
+    {
+        float mean = 0.f;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            o[c] += y[c];
+            mean += o[c];
+        }
+        mean *= (1.f / 16.f);
+        float var = 0.f;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            const float d = o[c] - mean;
+            var = fmaf(d, d, var);
+        }
+        var = var * (1.f / 16.f) + 1e-14f;
+        const float sd = sqrtf(var);
+        if (act) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) yb[c * T + i] = (o[c] - mean) / sd * wsm[AW_G2 + c] + wsm[AW_B2 + c];
+        }
+    }
+}
+
+int launch_attention(const AttnP &p, int G, cudaStream_t s) {
+    if (p.T > AT_MAXT) {
+        set_error("attention kernel supports T <= %d (got %d)", AT_MAXT, p.T);
+        return VP_ERR_UNSUPPORTED;
+    }
+    dim3 grid((unsigned)((p.B + 1) / 2), G);
+    constexpr size_t smem = AT_SMEM_FLOATS * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        VP_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    attention_kernel<<<grid, 128, smem, s>>>(p);
+    VP_LAUNCH_CHECK();
+    return VP_OK;
+}
+
+}  // namespace vp

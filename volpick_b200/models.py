@@ -1,0 +1,644 @@
+"""Host-side mirror of SeisBench's ``WaveformModel`` API for the two volpick pickers.
+
+Drop-in surface (reference call sites /root/reference/README.md:46-66,
+/root/reference/Final_models/demo.ipynb cells 7-15, /root/reference/volpick/data/utils.py:708,729):
+
+    picker = EQTransformer.from_pretrained("volpick")        # or PhaseNet.from_pretrained("volpick")
+    picker.cuda()
+    picks = picker.classify(stream, batch_size=256, overlap=5500, blinding=(500, 500), stacking="avg",
+                            parallelism=None, P_threshold=0.2, S_threshold=0.2, copy=True).picks
+    annotations = picker.annotate(stream, overlap=4500, blinding=[1000, 1000])
+    det, p, s = picker(x)                                    # x: (B, 3, 6000) CUDA tensor
+
+Python only does stream bookkeeping (grouping, gap segmentation, time stamps).  Every sample of
+arithmetic runs in the CUDA library behind the C ABI of include/volpick_b200.h: there is no CPU
+path, and a missing library or a model left on "cpu" raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import logging
+import warnings
+from collections import OrderedDict, defaultdict
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib, weights_io
+from .annotations import ClassifyOutput, Detection, DetectionList, Pick, PickList
+from .stream import Stream, Trace, UTCDateTime
+
+logger = logging.getLogger("volpick_b200")
+
+
+# --------------------------------------------------------------------------------------------------
+# state-dict layouts (name, shape) in SeisBench order; checked against the loaded weights
+def _bn(prefix: str, c: int):
+    return [(f"{prefix}.weight", (c,)), (f"{prefix}.bias", (c,)), (f"{prefix}.running_mean", (c,)), (f"{prefix}.running_var", (c,))]
+
+
+def _lstm(prefix: str, cin: int, bidirectional: bool):
+    out = []
+    for suf in ([""] + (["_reverse"] if bidirectional else [])):
+        out += [(f"{prefix}.weight_ih_l0{suf}", (64, cin)), (f"{prefix}.weight_hh_l0{suf}", (64, 16)),
+                (f"{prefix}.bias_ih_l0{suf}", (64,)), (f"{prefix}.bias_hh_l0{suf}", (64,))]
+    return out
+
+
+def _attention(prefix: str):
+    return [(f"{prefix}.Wx", (16, 32)), (f"{prefix}.Wt", (16, 32)), (f"{prefix}.bh", (32,)), (f"{prefix}.Wa", (32, 1)), (f"{prefix}.ba", (1,))]
+
+
+def _decoder(prefix: str):
+    c = [16, 64, 64, 32, 32, 16, 16, 8]
+    k = [3, 5, 5, 7, 7, 9, 11]
+    out = []
+    for i in range(7):
+        out += [(f"{prefix}.convs.{i}.weight", (c[i + 1], c[i], k[i])), (f"{prefix}.convs.{i}.bias", (c[i + 1],))]
+    return out
+
+
+def eqtransformer_spec() -> List[Tuple[str, Tuple[int, ...]]]:
+    spec = []
+    c = [3, 8, 16, 16, 32, 32, 64, 64]
+    k = [11, 9, 7, 7, 5, 5, 3]
+    for i in range(7):
+        spec += [(f"encoder.convs.{i}.weight", (c[i + 1], c[i], k[i])), (f"encoder.convs.{i}.bias", (c[i + 1],))]
+    for i, ker in enumerate([3, 3, 3, 3, 2, 3, 2]):
+        p = f"res_cnn_stack.members.{i}"
+        spec += _bn(p + ".norm1", 64) + [(p + ".conv1.weight", (64, 64, ker)), (p + ".conv1.bias", (64,))]
+        spec += _bn(p + ".norm2", 64) + [(p + ".conv2.weight", (64, 64, ker)), (p + ".conv2.bias", (64,))]
+    for i in range(3):
+        p = f"bi_lstm_stack.members.{i}"
+        spec += _lstm(p + ".lstm", 64 if i == 0 else 16, True)
+        spec += [(p + ".conv.weight", (16, 32, 1)), (p + ".conv.bias", (16,))] + _bn(p + ".norm", 16)
+    for p in ["transformer_d0", "transformer_d"]:
+        spec += _attention(p + ".attention")
+        spec += [(p + ".norm1.gamma", (16, 1)), (p + ".norm1.beta", (16, 1)),
+                 (p + ".ff.lin1.weight", (128, 16)), (p + ".ff.lin1.bias", (128,)),
+                 (p + ".ff.lin2.weight", (16, 128)), (p + ".ff.lin2.bias", (16,)),
+                 (p + ".norm2.gamma", (16, 1)), (p + ".norm2.beta", (16, 1))]
+    spec += _decoder("decoder_d") + [("conv_d.weight", (1, 8, 11)), ("conv_d.bias", (1,))]
+    for i in range(2):
+        spec += _lstm(f"pick_lstms.{i}", 16, False)
+    for i in range(2):
+        spec += _attention(f"pick_attentions.{i}")
+    for i in range(2):
+        spec += _decoder(f"pick_decoders.{i}")
+    for i in range(2):
+        spec += [(f"pick_convs.{i}.weight", (1, 8, 11)), (f"pick_convs.{i}.bias", (1,))]
+    return spec
+
+
+def phasenet_spec() -> List[Tuple[str, Tuple[int, ...]]]:
+    spec = [("inc.weight", (8, 3, 7)), ("inc.bias", (8,))] + _bn("in_bn", 8)
+    last = 8
+    f = [8, 16, 32, 64, 128]
+    for i in range(5):
+        spec += [(f"down_branch.{i}.0.weight", (f[i], last, 7))] + _bn(f"down_branch.{i}.1", f[i])
+        last = f[i]
+        if i < 4:
+            spec += [(f"down_branch.{i}.2.weight", (f[i], f[i], 7))] + _bn(f"down_branch.{i}.3", f[i])
+    for i in range(4):
+        fo = f[3 - i]
+        spec += [(f"up_branch.{i}.0.weight", (last, fo, 7))] + _bn(f"up_branch.{i}.1", fo)
+        spec += [(f"up_branch.{i}.2.weight", (fo, 2 * fo, 7))] + _bn(f"up_branch.{i}.3", fo)
+        last = fo
+    spec += [("out.weight", (3, 8, 1)), ("out.bias", (3,))]
+    return spec
+
+
+def flatten_weights(weights: "OrderedDict[str, np.ndarray]", spec) -> np.ndarray:
+    """Validate names/shapes against ``spec`` and concatenate in state-dict order (C ABI layout)."""
+    names = [k for k in weights if not k.endswith("num_batches_tracked")]
+    expected = [n for n, _ in spec]
+    if names != expected:
+        missing = [n for n in expected if n not in weights]
+        extra = [n for n in names if n not in set(expected)]
+        raise ValueError(f"state dict does not match the architecture: missing {missing[:5]}, unexpected {extra[:5]}")
+    chunks = []
+    for name, shape in spec:
+        a = np.asarray(weights[name], dtype=np.float32)
+        if tuple(a.shape) != tuple(shape):
+            raise ValueError(f"{name}: expected shape {shape}, got {tuple(a.shape)}")
+        chunks.append(a.reshape(-1))
+    return np.ascontiguousarray(np.concatenate(chunks))
+
+
+# --------------------------------------------------------------------------------------------------
+def _group_key(tr) -> str:
+    s = tr.stats
+    return f"{s.network}.{s.station}.{s.location}.{s.channel[:-1]}"
+
+
+def _is_obspy(obj) -> bool:
+    return type(obj).__module__.split(".")[0] == "obspy"
+
+
+def _ns(t) -> int:
+    return int(t.ns)
+
+
+class WaveformModel:
+    """Common machinery; see the module docstring.  Sub-classes: ``EQTransformer``, ``PhaseNet``."""
+
+    _kind: int = -1
+    _model_dir: str = ""
+    in_samples: int = 0
+    _default_overlap: int = 0
+    _default_blinding: Tuple[int, int] = (0, 0)
+    _generic_threshold: float = 0.3
+    _spec = staticmethod(lambda: [])
+    _known_kwargs = {
+        "batch_size", "overlap", "blinding", "stacking", "copy", "parallelism", "strict",
+        "flexible_horizontal_components", "detection_threshold", "precision", "chunk_windows",
+    }
+
+    def __init__(self, component_order: str = "ZNE", norm: str = "peak", sampling_rate: float = 100, **kwargs):
+        if norm != "peak":
+            raise NotImplementedError("only norm='peak' (the volpick weights) is implemented on the GPU path")
+        self.component_order = component_order
+        self.norm = norm
+        self.sampling_rate = float(sampling_rate)
+        self.default_args: Dict[str, Any] = {}
+        self.weights_docstring: Optional[str] = None
+        self.weights_version: Optional[str] = None
+        self.filter_args = None
+        self.filter_kwargs = None
+        self.peak_scope = kwargs.pop("peak_scope", "channel")
+        self.precision = kwargs.pop("precision", "fp32")
+        self._weights: Optional["OrderedDict[str, np.ndarray]"] = None
+        self._flat: Optional[np.ndarray] = None
+        self._handle = C.c_void_p(None)
+        self._device = "cpu"
+        self._device_index: Optional[int] = None
+        self._workspace = None  # torch uint8 tensor on the model's device
+        self._extra_args = kwargs
+
+    # ---- identity ------------------------------------------------------------------------------
+    @property
+    def name(self) -> str:
+        return type(self).__name__
+
+    @property
+    def device(self):
+        import torch
+
+        return torch.device(self._device)
+
+    def __repr__(self) -> str:
+        return f"{self.name}(in_samples={self.in_samples}, labels={self.labels}, norm={self.norm!r}, device={self._device!r})"
+
+    # ---- weights -------------------------------------------------------------------------------
+    @classmethod
+    def from_pretrained(cls, name: str, version_str: Optional[str] = None, update: bool = False,
+                        force: bool = False, wait_for_file: bool = False):
+        """``SeisBenchModel.from_pretrained``: ``<cache>/<modelclass>/<name>.json.v*`` + weights file.
+
+        No download is attempted (no network on the hot path); the volpick weight sets ship with
+        the package (``tools/convert_weights.py``) and a SeisBench cache directory is also searched.
+        """
+        js, wpath = weights_io.find_weights(cls._model_dir, name, version_str)
+        with open(js) as f:
+            meta = json.load(f)
+        model = cls(**meta.get("model_args", {}))
+        model.load_state_dict(weights_io.load_weights(wpath))
+        model.default_args = dict(meta.get("default_args", {}))
+        model.weights_docstring = meta.get("docstring")
+        model.weights_version = str(meta.get("version", js.rsplit(".v", 1)[-1]))
+        model._weights_meta = meta
+        return model
+
+    @classmethod
+    def list_pretrained(cls, details: bool = False):
+        import os
+
+        found = {}
+        for root in weights_io.search_roots():
+            d = os.path.join(root, cls._model_dir)
+            if os.path.isdir(d):
+                for fn in sorted(os.listdir(d)):
+                    if ".json.v" in fn:
+                        nm = fn.split(".json.v")[0]
+                        if details:
+                            with open(os.path.join(d, fn)) as f:
+                                found.setdefault(nm, json.load(f).get("docstring"))
+                        else:
+                            found.setdefault(nm, None)
+        return found if details else sorted(found)
+
+    def load_state_dict(self, state_dict) -> None:
+        weights: "OrderedDict[str, np.ndarray]" = OrderedDict()
+        for k, v in state_dict.items():
+            if k.endswith("num_batches_tracked"):
+                continue
+            weights[k] = v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v)
+        self._flat = flatten_weights(weights, type(self)._spec())
+        self._weights = weights
+        if self._handle:
+            self._create_handle()
+
+    def state_dict(self) -> "OrderedDict[str, np.ndarray]":
+        return OrderedDict(self._weights or {})
+
+    # ---- device --------------------------------------------------------------------------------
+    def _destroy_handle(self) -> None:
+        if self._handle:
+            _lib.load().vp_model_destroy(self._handle)
+            self._handle = C.c_void_p(None)
+
+    def _create_handle(self) -> None:
+        if self._flat is None:
+            raise RuntimeError("model has no weights: use from_pretrained() or load_state_dict() first")
+        lib = _lib.load()
+        self._destroy_handle()
+        h = C.c_void_p(None)
+        _lib.check(lib.vp_model_create(self._kind, self._flat.ctypes.data_as(C.c_void_p), self._flat.size,
+                                       int(self._device_index), C.byref(h)))
+        self._handle = h
+
+    def to(self, device):
+        import torch
+
+        dev = torch.device(device)
+        if dev.type == "cpu":
+            self._destroy_handle()
+            self._device, self._device_index, self._workspace = "cpu", None, None
+            return self
+        if dev.type != "cuda":
+            raise ValueError(f"unsupported device {device!r}")
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        self._device, self._device_index = f"cuda:{idx}", idx
+        self._workspace = None
+        self._create_handle()
+        return self
+
+    def cuda(self, device=None):
+        return self.to("cuda" if device is None else (f"cuda:{device}" if isinstance(device, int) else device))
+
+    def cpu(self):
+        return self.to("cpu")
+
+    def eval(self):
+        return self
+
+    def __del__(self):
+        try:
+            self._destroy_handle()
+        except Exception:
+            pass
+
+    def _require_gpu(self) -> None:
+        if not self._handle:
+            raise RuntimeError(
+                f"{self.name} is on 'cpu': this implementation has no CPU path. Call .cuda() (a B200 is required)."
+            )
+
+    def _get_workspace(self, nbytes: int):
+        import torch
+
+        if self._workspace is None or self._workspace.numel() < nbytes:
+            self._workspace = None
+            self._workspace = torch.empty(int(nbytes), dtype=torch.uint8, device=self._device)
+        return self._workspace
+
+    @staticmethod
+    def _stream_ptr():
+        import torch
+
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    # ---- forward -------------------------------------------------------------------------------
+    def forward(self, x, precision: Optional[str] = None):
+        """Network forward on pre-normalised windows; x: CUDA float32 tensor (B, 3, in_samples)."""
+        import torch
+
+        self._require_gpu()
+        if not (isinstance(x, torch.Tensor) and x.is_cuda):
+            raise TypeError("forward expects a CUDA tensor (no CPU path)")
+        if x.ndim != 3 or x.shape[1] != 3 or x.shape[2] != self.in_samples:
+            raise ValueError(f"expected (B, 3, {self.in_samples}), got {tuple(x.shape)}")
+        x = x.contiguous().float()
+        B = x.shape[0]
+        lib = _lib.load()
+        prec = _lib.PRECISION[precision or self.precision]
+        y = torch.empty((B, 3, self.in_samples), dtype=torch.float32, device=x.device)
+        need = _lib.check(lib.vp_forward_workspace_bytes(self._handle, B, prec))
+        ws = self._get_workspace(need)
+        with torch.cuda.device(x.device):
+            _lib.check(lib.vp_forward(self._handle, C.c_void_p(x.data_ptr()), B, C.c_void_p(y.data_ptr()),
+                                      C.c_void_p(ws.data_ptr()), ws.numel(), prec, self._stream_ptr()))
+        return self._split_outputs(y)
+
+    __call__ = forward
+
+    def forward_tap(self, x, tap: str):
+        """Debug/parity helper: the named intermediate activation as a flat CUDA tensor."""
+        import torch
+
+        self._require_gpu()
+        x = x.contiguous().float()
+        B = x.shape[0]
+        lib = _lib.load()
+        y = torch.empty((B, 3, self.in_samples), dtype=torch.float32, device=x.device)
+        need = _lib.check(lib.vp_forward_workspace_bytes(self._handle, B, 0))
+        ws = self._get_workspace(need)
+        cap = B * 3 * 48000 * 2
+        out = torch.empty(cap, dtype=torch.float32, device=x.device)
+        n = C.c_int64(0)
+        _lib.check(lib.vp_forward_tap(self._handle, C.c_void_p(x.data_ptr()), B, C.c_void_p(y.data_ptr()),
+                                      C.c_void_p(ws.data_ptr()), ws.numel(), 0, tap.encode(),
+                                      C.c_void_p(out.data_ptr()), cap, C.byref(n), self._stream_ptr()))
+        return out[: n.value]
+
+    def tap_names(self) -> List[str]:
+        self._require_gpu()
+        return _lib.load().vp_forward_tap_names(self._handle).decode().split(",")
+
+    def _split_outputs(self, y):
+        return y
+
+    # ---- argument handling ---------------------------------------------------------------------
+    def _argdict(self, kwargs: Dict[str, Any]) -> Dict[str, Any]:
+        argdict = dict(self.default_args)
+        argdict.update(kwargs)
+        for k in kwargs:
+            if k not in self._known_kwargs and not k.endswith("_threshold"):
+                warnings.warn(f"Unknown argument '{k}' will be ignored.")
+        argdict.setdefault("overlap", self._default_overlap)
+        argdict.setdefault("blinding", self._default_blinding)
+        argdict.setdefault("stacking", "avg")
+        argdict.setdefault("batch_size", 256)
+        argdict.setdefault("strict", False)
+        argdict.setdefault("flexible_horizontal_components", True)
+        if argdict["stacking"] not in _lib.STACK:
+            raise ValueError(f"Stacking method {argdict['stacking']} unknown. Known methods are: {list(_lib.STACK)}")
+        overlap = int(argdict["overlap"])
+        if not 0 <= overlap < self.in_samples:
+            raise ValueError(f"overlap must satisfy 0 <= overlap < in_samples ({self.in_samples}), got {overlap}")
+        b = tuple(int(v) for v in argdict["blinding"])
+        if len(b) != 2 or b[0] < 0 or b[1] < 0:
+            raise ValueError(f"blinding must be a pair of non-negative sample counts, got {argdict['blinding']}")
+        argdict["overlap"], argdict["blinding"] = overlap, b
+        return argdict
+
+    def _thresholds(self, argdict: Dict[str, Any]) -> List[float]:
+        """Per-label trigger thresholds (0 = label is not picked)."""
+        thr = []
+        for label in self.labels:
+            if label == "N":
+                thr.append(0.0)
+            elif label == "Detection":
+                thr.append(float(argdict.get("detection_threshold", 0.3)))
+            else:
+                thr.append(float(argdict.get(f"{label}_threshold", argdict.get("*_threshold", self._generic_threshold))))
+        return thr
+
+    # ---- stream handling (host) ----------------------------------------------------------------
+    def annotate_stream_pre(self, stream, argdict):
+        if self.filter_args is not None or self.filter_kwargs is not None:
+            if hasattr(stream, "filter"):
+                stream.filter(*(self.filter_args or ()), **(self.filter_kwargs or {}))
+            else:
+                raise NotImplementedError("stream filtering needs an ObsPy stream")
+        for tr in stream:
+            if abs(float(tr.stats.sampling_rate) - self.sampling_rate) > 1e-6:
+                if hasattr(tr, "resample") and _is_obspy(tr):
+                    tr.resample(self.sampling_rate)
+                else:
+                    raise NotImplementedError(
+                        f"trace {tr.id} has sampling rate {tr.stats.sampling_rate} Hz; resampling to "
+                        f"{self.sampling_rate} Hz needs an ObsPy stream"
+                    )
+
+    def stream_to_arrays(self, traces: Sequence, argdict) -> List[Tuple[Any, np.ndarray]]:
+        """SeisBench ``stream_to_array`` (cf. the fork at /root/reference/volpick/data/convert.py:26-70):
+        traces of ONE instrument -> [(t0, float32 (3, n))] per gap-free segment, component order
+        ``component_order``, missing components zero-filled (``strict=False``) or dropped (``strict=True``)."""
+        rate = self.sampling_rate
+        comp = {c: i for i, c in enumerate(self.component_order)}
+        present = {tr.stats.channel[-1] for tr in traces if len(tr.data) > 0}
+        if argdict.get("flexible_horizontal_components", True):
+            for a, b in zip("NE", "12"):
+                if a in present and b in present:
+                    warnings.warn(f"Station has both {a} and {b} components; using {a}.")
+                elif a in comp and a not in present and b in present:
+                    comp[b] = comp[a]
+                elif b in comp and b not in present and a in present:
+                    comp[a] = comp[b]
+        use = [tr for tr in traces if tr.stats.channel[-1] in comp and len(tr.data) > 0]
+        if not use:
+            return []
+        use.sort(key=lambda t: _ns(t.stats.starttime))
+        segments: List[List] = []
+        seg_end = None
+        for tr in use:
+            start = _ns(tr.stats.starttime)
+            end = start + int(round(len(tr.data) / rate * 1e9))
+            if seg_end is None or start > seg_end + int(0.5 / rate * 1e9):
+                segments.append([tr])
+                seg_end = end
+            else:
+                segments[-1].append(tr)
+                seg_end = max(seg_end, end)
+        out = []
+        for seg in segments:
+            t0 = seg[0].stats.starttime
+            t0ns = _ns(t0)
+            offs = [int(round((_ns(tr.stats.starttime) - t0ns) * rate / 1e9)) for tr in seg]
+            n = max(o + len(tr.data) for o, tr in zip(offs, seg))
+            arr = np.zeros((len(self.component_order), n), dtype=np.float32)
+            have = np.zeros((len(self.component_order), n), dtype=bool)
+            for o, tr in zip(offs, seg):
+                ci = comp[tr.stats.channel[-1]]
+                arr[ci, o : o + len(tr.data)] = tr.data
+                have[ci, o : o + len(tr.data)] = True
+            if argdict.get("strict", False):
+                allc = have.all(axis=0)
+                edges = np.flatnonzero(np.diff(np.concatenate([[0], allc.astype(np.int8), [0]])))
+                for a, b in zip(edges[::2], edges[1::2]):
+                    out.append((t0 + a / rate, np.ascontiguousarray(arr[:, a:b])))
+            else:
+                out.append((t0, arr))
+        return out
+
+    # ---- the path ------------------------------------------------------------------------------
+    def _params(self, argdict, thresholds: Sequence[float]) -> "_lib.AnnotateParams":
+        p = _lib.AnnotateParams()
+        p.overlap = argdict["overlap"]
+        p.blinding[0], p.blinding[1] = argdict["blinding"]
+        p.stacking = _lib.STACK[argdict["stacking"]]
+        p.precision = _lib.PRECISION[argdict.get("precision", self.precision)]
+        p.peak_scope = _lib.PEAK_SCOPE[self.peak_scope]
+        p.chunk_windows = int(argdict.get("chunk_windows", 0) or 0)
+        for i in range(3):
+            p.threshold[i] = float(thresholds[i])
+        return p
+
+    def annotate_array(self, trace, argdict: Optional[Dict[str, Any]] = None, want_annotation: bool = True,
+                       thresholds: Optional[Sequence[float]] = None, pick_capacity: int = 1 << 16):
+        """One gap-free (3, n) record through ``vp_annotate``.
+
+        ``trace``: float32/int32 NumPy array or pinned CPU tensor (copied host->device inside the
+        call) or a CUDA tensor (used in place).  Returns ``(annotation, triggers, trim)`` with
+        ``annotation`` a float32 NumPy array (3, pred_len) or None, ``triggers`` a structured
+        NumPy array (s0, s1, s_peak, value, label) sorted by (label, s0), ``trim`` int64 (3, 2).
+        """
+        import torch
+
+        self._require_gpu()
+        argdict = self._argdict({}) if argdict is None else argdict
+        thresholds = [0.0, 0.0, 0.0] if thresholds is None else thresholds
+        lib = _lib.load()
+        on_host = not (isinstance(trace, torch.Tensor) and trace.is_cuda)
+        if isinstance(trace, torch.Tensor):
+            t = trace
+            if t.dtype not in (torch.float32, torch.int32):
+                t = t.float()
+            if t.stride(-1) != 1:
+                t = t.contiguous()
+            n, ch_stride, ptr = t.shape[1], t.stride(0), t.data_ptr()
+            dtype = _lib.DTYPE_F32 if t.dtype == torch.float32 else _lib.DTYPE_I32
+            keep = t
+        else:
+            a = np.asarray(trace)
+            if a.dtype not in (np.float32, np.int32):
+                a = a.astype(np.float32)
+            if a.strides[-1] != a.itemsize:
+                a = np.ascontiguousarray(a)
+            n, ch_stride, ptr = a.shape[1], a.strides[0] // a.itemsize, a.ctypes.data
+            dtype = _lib.DTYPE_F32 if a.dtype == np.float32 else _lib.DTYPE_I32
+            keep = a
+        if keep.shape[0] != 3:
+            raise ValueError(f"expected a (3, n) record, got {tuple(keep.shape)}")
+        params = self._params(argdict, thresholds)
+        need = _lib.check(lib.vp_annotate_workspace_bytes(self._handle, n, C.byref(params), int(on_host), pick_capacity))
+        ws = self._get_workspace(need)
+        pred_len = n if lib.vp_window_count(n, self.in_samples, params.overlap) > 0 else 0
+        annotation = np.empty((3, pred_len), dtype=np.float32) if want_annotation else None
+        trig = (_lib.Trigger * pick_capacity)()
+        n_picks = C.c_int64(0)
+        trim = np.zeros(6, dtype=np.int64)
+        with torch.cuda.device(self._device_index):
+            _lib.check(lib.vp_annotate(
+                self._handle, C.c_void_p(ptr), int(on_host), dtype, n, ch_stride, C.byref(params),
+                C.c_void_p(annotation.ctypes.data) if want_annotation and pred_len else None, 1,
+                C.cast(trig, C.c_void_p), pick_capacity, C.byref(n_picks), C.c_void_p(trim.ctypes.data),
+                C.c_void_p(ws.data_ptr()), ws.numel(), self._stream_ptr()))
+        trig_dtype = np.dtype([("s0", "<i8"), ("s1", "<i8"), ("s_peak", "<i8"), ("value", "<f4"), ("label", "<i4")])
+        triggers = np.frombuffer(trig, dtype=trig_dtype, count=n_picks.value).copy()
+        return annotation, triggers, trim.reshape(3, 2)
+
+    def _run(self, stream, kwargs, want_annotation: bool, want_picks: bool):
+        self._require_gpu()
+        argdict = self._argdict(kwargs)
+        if kwargs.get("copy", True):
+            stream = stream.copy()
+        stream.merge(-1)
+        self.annotate_stream_pre(stream, argdict)
+        groups: Dict[str, List] = defaultdict(list)
+        for tr in stream:
+            groups[_group_key(tr)].append(tr)
+        obspy_out = _is_obspy(stream)
+        if obspy_out:
+            import obspy
+
+            StreamT, TraceT = obspy.Stream, obspy.Trace
+        else:
+            StreamT, TraceT = Stream, Trace
+        thresholds = self._thresholds(argdict) if want_picks else [0.0, 0.0, 0.0]
+        rate = self.sampling_rate
+        out_traces = []
+        picks, detections = [], []
+        for key in groups:
+            trs = groups[key]
+            s0 = trs[0].stats
+            trace_id = f"{s0.network}.{s0.station}.{s0.location}"
+            for t0, arr in self.stream_to_arrays(trs, argdict):
+                if arr.shape[1] < self.in_samples:
+                    logger.warning("Parts of the input stream consist of fragments shorter than the number of "
+                                   "input samples. Output might be empty.")
+                    continue
+                annotation, triggers, trim = self.annotate_array(arr, argdict, want_annotation, thresholds)
+                for li, label in enumerate(self.labels):
+                    first, last = int(trim[li, 0]), int(trim[li, 1])
+                    if last < first:
+                        continue
+                    tstart = t0 + first / rate  # _predictions_to_stream: t0 + f / rate
+                    if want_annotation:
+                        out_traces.append(TraceT(annotation[li, first : last + 1].copy(), {
+                            "starttime": tstart, "sampling_rate": rate, "network": s0.network,
+                            "station": s0.station, "location": s0.location, "channel": f"{self.name}_{label}"}))
+                    if want_picks:
+                        for tg in triggers[triggers["label"] == li]:
+                            # picks_from_annotations: starttime + times()[idx], times() = arange(npts) / rate
+                            ts = tstart + float((int(tg["s0"]) - first) / rate)
+                            te = tstart + float((int(tg["s1"]) - first) / rate)
+                            if label == "Detection":
+                                detections.append(Detection(trace_id, ts, te, float(tg["value"])))
+                            else:
+                                tp = tstart + float((int(tg["s_peak"]) - first) / rate)
+                                picks.append(Pick(trace_id, ts, te, tp, float(tg["value"]), label))
+        return StreamT(out_traces), PickList(sorted(picks)), DetectionList(sorted(detections))
+
+    def annotate(self, stream, copy: bool = True, **kwargs):
+        """``WaveformModel.annotate``: stream -> stream of probability traces ``"{ClassName}_{label}"``."""
+        kwargs["copy"] = copy
+        return self._run(stream, kwargs, want_annotation=True, want_picks=False)[0]
+
+    def classify(self, stream, **kwargs) -> ClassifyOutput:
+        """``WaveformModel.classify``: stream -> ``ClassifyOutput(picks=PickList[, detections=...])``."""
+        _, picks, detections = self._run(stream, kwargs, want_annotation=False, want_picks=True)
+        return self._classify_output(picks, detections)
+
+    def _classify_output(self, picks, detections) -> ClassifyOutput:
+        return ClassifyOutput(self.name, picks=picks)
+
+
+class EQTransformer(WaveformModel):
+    """volpick EQTransformer (L = 6000, labels Detection/P/S)."""
+
+    _kind = _lib.KIND_EQTRANSFORMER
+    _model_dir = "eqtransformer"
+    in_samples = 6000
+    _default_overlap = 1800
+    _default_blinding = (500, 500)
+    _generic_threshold = 0.1
+    _spec = staticmethod(eqtransformer_spec)
+
+    def __init__(self, in_channels: int = 3, in_samples: int = 6000, classes: int = 2, phases: str = "PS",
+                 lstm_blocks: int = 3, sampling_rate: float = 100, norm: str = "peak", **kwargs):
+        if (in_channels, in_samples, classes, phases, lstm_blocks) != (3, 6000, 2, "PS", 3):
+            raise NotImplementedError("only the volpick architecture (3 x 6000, phases 'PS', 3 LSTM blocks) is built")
+        super().__init__(norm=norm, sampling_rate=sampling_rate, **kwargs)
+        self.phases = phases
+        self.labels = ["Detection"] + list(phases)
+
+    def _split_outputs(self, y):
+        return tuple(y[:, i, :] for i in range(3))
+
+    def _classify_output(self, picks, detections) -> ClassifyOutput:
+        return ClassifyOutput(self.name, picks=picks, detections=detections)
+
+
+class PhaseNet(WaveformModel):
+    """volpick PhaseNet (L = 3001, labels P/S/N)."""
+
+    _kind = _lib.KIND_PHASENET
+    _model_dir = "phasenet"
+    in_samples = 3001
+    _default_overlap = 1500
+    _default_blinding = (0, 0)
+    _generic_threshold = 0.3
+    _spec = staticmethod(phasenet_spec)
+
+    def __init__(self, in_channels: int = 3, classes: int = 3, phases: str = "PSN", sampling_rate: float = 100,
+                 norm: str = "peak", **kwargs):
+        if (in_channels, classes) != (3, 3) or sorted(phases) != sorted("PSN"):
+            raise NotImplementedError("only the volpick architecture (3 channels, classes P/S/N) is built")
+        if phases != "PSN":
+            raise NotImplementedError("label order must be 'PSN' (volpick weights)")
+        super().__init__(norm=norm, sampling_rate=sampling_rate, **kwargs)
+        self.phases = phases
+        self.labels = list(phases)
