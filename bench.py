@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""Benchmark of the continuous-waveform picking path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this framework (CUDA through the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (oracle port)
+
+A "step" is one station-day (8,640,000 samples x 3 components, synthetic, 100 Hz) per rank through
+the whole path of BASELINE.json configs[1]: EQTransformer-volpick, 6000-sample windows,
+overlap=5500 (17,269 windows), blinding=(500,500), stacking="avg", P/S threshold 0.2.
+``value`` = station-days/s over all ranks with the record resident in HBM; ``e2e`` = the same through
+the host-buffer entry point (pinned host record -> vp_annotate -> picks on the host).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_DAY = 8_640_000
+N_HOUR = 360_000
+FLOP_PER_WINDOW = {"eqtransformer": 257.04e6, "phasenet": 38.92e6}
+CONFIGS = {
+    "eqtransformer": dict(overlap=5500, blinding=(500, 500), stacking="avg", P_threshold=0.2, S_threshold=0.2),
+    "phasenet": dict(overlap=1500, blinding=(0, 0), stacking="avg", P_threshold=0.2, S_threshold=0.2),
+}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sustained=p["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU every 200 ms while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples, self.reasons, self.sm_max = [], set(), None
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            names = {
+                pynvml.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                pynvml.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                pynvml.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                pynvml.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+            }
+            while not self._stop_evt.is_set():
+                self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, nm in names.items():
+                    if mask & bit:
+                        self.reasons.add(nm)
+                self._stop_evt.wait(0.2)
+        except Exception:
+            self._fallback()
+
+    def _fallback(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(int(out[0]))
+                self.sm_max = int(out[1])
+                for nm, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], out[2:]):
+                    if v.strip().lower() == "active":
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=5)
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.sm_max,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_model() -> str:
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def oracle_station_hours_per_s(kind: str, steps: int, warmup: int, n_samples: int = N_HOUR):
+    """The reference's CPU path (oracle port: torch-CPU nets + NumPy pipeline) on one station-hour per step."""
+    import torch
+
+    from oracle import nets, pipeline
+    from volpick_b200 import weights_io
+    from volpick_b200.synthetic import synthetic_record
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = CONFIGS[kind]
+    sd = nets.state_dict_from_numpy(weights_io.load_weights(weights_io.find_weights(kind, "volpick")[1]))
+    x = synthetic_record(1000, n_samples)
+    thr = {"P_threshold": cfg["P_threshold"], "S_threshold": cfg["S_threshold"], "detection_threshold": 0.3}
+    times = []
+    n_picks = 0
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        ann = pipeline.annotate_array(kind, sd, x, cfg["overlap"], cfg["blinding"], cfg["stacking"], batch_size=256)
+        picks, _ = pipeline.classify_array(kind, ann, thr)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+        n_picks = sum(len(v) for v in picks.values())
+    nwin = len(pipeline.window_starts(n_samples, pipeline.IN_SAMPLES[kind], cfg["overlap"]))
+    return times, nwin, cores, n_picks
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    kind = args.model
+    times, nwin, cores, n_picks = oracle_station_hours_per_s(kind, args.steps, args.warmup)
+    total = sum(times)
+    frac_day = N_HOUR / N_DAY
+    value = frac_day * len(times) / total
+    line = {
+        "impl": "reference", "metric": "station_days_per_s", "value": value, "unit": "station-days/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "windows_per_s": nwin * len(times) / total,
+        "config": workload_config(kind, "one station-hour (1/24 of the station-day) per step on the host CPU, extrapolated to station-days"),
+        "cpu_baseline": {"value": value, "unit": "station-days/s", "cores": cores, "kind": "port",
+                         "sample": f"{len(times)} x 1 synthetic station-hour ({nwin} windows each), oracle port "
+                                   f"(torch-CPU fp32 + NumPy), {cpu_model()}"},
+        "e2e": {"value": value, "unit": "station-days/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(kind: str, note: str = ""):
+    cfg = CONFIGS[kind]
+    L = 6000 if kind == "eqtransformer" else 3001
+    stride = L - cfg["overlap"]
+    nwin = (N_DAY - L) // stride + 1
+    if (nwin - 1) * stride + L < N_DAY:
+        nwin += 1
+    d = {"workload": f"{'EQTransformer' if kind == 'eqtransformer' else 'PhaseNet'}-volpick classify() on one synthetic "
+                     f"3-C 100 Hz station-day per GPU per step (BASELINE.json configs[1])",
+         "samples_per_record": N_DAY, "window": L, "overlap": cfg["overlap"], "blinding": list(cfg["blinding"]),
+         "stacking": cfg["stacking"], "P_threshold": cfg["P_threshold"], "S_threshold": cfg["S_threshold"],
+         "windows_per_record": nwin, "l2": "per-step working set (1.2 GB of window predictions) exceeds the 126 MB L2"}
+    if note:
+        d["note"] = note
+    return d
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import volpick_b200 as vb
+    from volpick_b200 import _lib, shard
+    from volpick_b200.synthetic import synthetic_record
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    kind = args.model
+    cls = vb.EQTransformer if kind == "eqtransformer" else vb.PhaseNet
+    model = cls.from_pretrained("volpick").cuda(local_rank)
+    lib = _lib.load()
+    cfg = dict(CONFIGS[kind], precision=args.precision)
+    argdict = model._argdict(cfg)
+    thresholds = model._thresholds(argdict)
+    thresholds[0] = 0.3 if kind == "eqtransformer" else thresholds[0]
+    n = args.samples
+    # two distinct records per rank, alternated between steps (host pinned + device resident copies)
+    recs_host = [torch.from_numpy(synthetic_record(1000 + rank + world * j, n)).pin_memory() for j in range(2)]
+    recs_dev = [r.cuda(non_blocking=True) for r in recs_host]
+    torch.cuda.synchronize()
+
+    def step_device(i):
+        return model.annotate_array(recs_dev[i & 1], argdict, False, thresholds)
+
+    def step_host(i):
+        return model.annotate_array(recs_host[i & 1], argdict, False, thresholds)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, sample_clocks=False):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        sampler = ClockSampler(local_rank) if sample_clocks else None
+        if sampler:
+            sampler.start()
+        lib.vp_launch_count(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        last = None
+        for i in range(steps):
+            last = fn(i)
+        e1.record()
+        barrier()
+        launches = lib.vp_launch_count(1)
+        clocks = sampler.stop() if sampler else None
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches, clocks, last
+
+    ms, launches, clocks, last = timed(step_device, args.steps, args.warmup, sample_clocks=True)
+    ms_e2e, _, _, last_e2e = timed(step_host, args.steps, max(1, args.warmup // 2))
+    n_trig = len(last[1])
+    nwin = int(lib.vp_window_count(n, model.in_samples, argdict["overlap"]))
+    days = n / N_DAY
+    value = world * args.steps * days / (ms / 1e3)
+    e2e_value = world * args.steps * days / (ms_e2e / 1e3)
+
+    # final gather of picks (the only exchange; outside the timed region)
+    t0 = time.perf_counter()
+    merged = shard.gather_picks([(rank, last[1])], rank, world)
+    gather_ms = 1e3 * (time.perf_counter() - t0)
+
+    # ---- per-stage device timings (rank 0) for the roofline objects ---------------------------
+    stages = {}
+    if rank == 0:
+        stages = stage_timings(model, lib, recs_dev[0], argdict, thresholds, kind)
+    peaks = measured_peaks()
+    line = None
+    if rank == 0:
+        fwd_ms = stages.get("forward_ms")
+        flops = FLOP_PER_WINDOW[kind] * nwin
+        achieved = flops / (fwd_ms / 1e3) / 1e12 if fwd_ms else None
+        roofline = {"kernel": "forward (conv1d/convT/LSTM/attention kernels of vp_forward)", "bound": "tensor",
+                    "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                    "frac": (achieved / peaks["tf_sustained"]) if achieved else None, "traffic": None,
+                    "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['src']})",
+                    "note": "fp32 exact mode runs on the CUDA cores (FFMA); fraction is against the bf16 tensor peak"}
+        line = {
+            "metric": "station_days_per_s", "value": value, "unit": "station-days/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else args.precision,
+            "data": "synthetic", "windows_per_s": value * nwin / days,
+            "config": workload_config(kind),
+            "e2e": {"value": e2e_value, "unit": "station-days/s", "h2d_bytes_per_step": 3 * n * 4,
+                    "d2h_bytes_per_step": int(len(last_e2e[1]) * 32 + 56), "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "stages": stages,
+            "picks_per_record": n_trig, "gather_ms": gather_ms,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            times, cw, cores, _ = oracle_station_hours_per_s(kind, 1, 1)
+            v = (N_HOUR / N_DAY) * len(times) / sum(times)
+            line["cpu_baseline"] = {"value": v, "unit": "station-days/s", "cores": cores, "kind": "port",
+                                    "sample": f"1 synthetic station-hour ({cw} windows, {sum(times):.1f} s) after 1 warm-up, "
+                                              f"oracle port (torch-CPU fp32 + NumPy), extrapolated x24; {cpu_model()}"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return line
+
+
+def stage_timings(model, lib, rec_dev, argdict, thresholds, kind, reps: int = 3):
+    """CUDA-event timings of the four stages on the current stream, through the stage-level C ABI."""
+    import torch
+
+    from volpick_b200 import _lib
+
+    L = model.in_samples
+    n = rec_dev.shape[1]
+    ov = argdict["overlap"]
+    nwin = int(lib.vp_window_count(n, L, ov))
+    starts = np.zeros(nwin, dtype=np.int64)
+    cnt = C.c_int64(0)
+    lib.vp_window_starts(n, L, ov, starts.ctypes.data, nwin, C.byref(cnt))
+    d_starts = torch.from_numpy(starts).cuda()
+    chunk = 1024 if kind == "eqtransformer" else 4096
+    d_x = torch.empty((chunk, 3, L), dtype=torch.float32, device="cuda")
+    d_y = torch.empty((nwin, 3, L), dtype=torch.float32, device="cuda")
+    d_ann = torch.empty((3, n), dtype=torch.float32, device="cuda")
+    ws_bytes = int(lib.vp_forward_workspace_bytes(model._handle, chunk, 0))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    sb = int(lib.vp_pick_scratch_bytes(n))
+    scratch = torch.empty(sb, dtype=torch.uint8, device="cuda")
+    picks = torch.empty(65536 * 32, dtype=torch.uint8, device="cuda")
+    count = torch.zeros(1, dtype=torch.int64, device="cuda")
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    peaks = measured_peaks()
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    acc = {"slice": 0.0, "forward": 0.0, "stack": 0.0, "pick": 0.0}
+    for rep in range(reps + 1):
+        t = {k: 0.0 for k in acc}
+        evs = []
+        for w0 in range(0, nwin, chunk):
+            nw = min(chunk, nwin - w0)
+            a, b, c = ev(), ev(), ev()
+            a.record()
+            _lib.check(lib.vp_slice_normalize(rec_dev.data_ptr(), 0, n, rec_dev.stride(0), d_starts.data_ptr() + 8 * w0, nw, L,
+                                              0, 1 if kind == "eqtransformer" else 0, d_x.data_ptr(), stream))
+            b.record()
+            _lib.check(lib.vp_forward(model._handle, d_x.data_ptr(), nw, d_y.data_ptr() + 4 * 3 * L * w0, ws.data_ptr(), ws_bytes, 0, stream))
+            c.record()
+            evs.append((a, b, c))
+        a, b, c = ev(), ev(), ev()
+        a.record()
+        _lib.check(lib.vp_stack(d_y.data_ptr(), d_starts.data_ptr(), nwin, L, 3, ov, argdict["blinding"][0], argdict["blinding"][1],
+                                _lib.STACK[argdict["stacking"]], d_ann.data_ptr(), n, stream))
+        b.record()
+        count.zero_()
+        for li in range(3):
+            if thresholds[li] > 0:
+                _lib.check(lib.vp_pick(d_ann.data_ptr() + 4 * n * li, n, thresholds[li], thresholds[li] / 2, li, picks.data_ptr(), 65536,
+                                       count.data_ptr(), scratch.data_ptr(), sb, stream))
+        c.record()
+        torch.cuda.synchronize()
+        for (x0, x1, x2) in evs:
+            t["slice"] += x0.elapsed_time(x1)
+            t["forward"] += x1.elapsed_time(x2)
+        t["stack"] = a.elapsed_time(b)
+        t["pick"] = b.elapsed_time(c)
+        if rep > 0:
+            for k in acc:
+                acc[k] += t[k] / reps
+    n_labels_picked = sum(1 for v in thresholds if v > 0)
+    bytes_slice = 3 * n * 4 + nwin * 3 * L * 4
+    bytes_stack = nwin * 3 * L * 4 + 3 * n * 4
+    bytes_pick = n_labels_picked * n * 4
+    out = {f"{k}_ms": v for k, v in acc.items()}
+    for k, by in (("slice", bytes_slice), ("stack", bytes_stack), ("pick", bytes_pick)):
+        gbs = by / (acc[k] / 1e3) / 1e9 if acc[k] > 0 else None
+        out[f"{k}_hbm"] = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s",
+                           "frac": gbs / peaks["hbm"] if gbs else None, "algorithmic_bytes": by}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="eqtransformer", choices=["eqtransformer", "phasenet"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32x3", "bf16"])
+    ap.add_argument("--samples", type=int, default=N_DAY, help="samples per record (default: one station-day)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -30,6 +30,12 @@
 extern "C" {
 #endif
 
+#if defined(__GNUC__)
+#define VP_API __attribute__((visibility("default")))
+#else
+#define VP_API
+#endif
+
 #define VP_OK 0
 #define VP_ERR_ARG (-1)
 #define VP_ERR_CUDA (-2)
@@ -66,72 +72,72 @@ typedef struct vp_annotate_params {
 } vp_annotate_params;
 
 /* ---- misc ---------------------------------------------------------------------------- */
-int vp_version(void);
-const char *vp_last_error(void);
+VP_API int vp_version(void);
+VP_API const char *vp_last_error(void);
 /* Number of kernel launches issued by this library on the calling thread since the last reset. */
-int64_t vp_launch_count(int reset);
+VP_API int64_t vp_launch_count(int reset);
 
 /* ---- model handle: SeisBenchModel.from_pretrained -> load_state_dict ------------------- */
 /* weights: every float tensor of the SeisBench state dict, concatenated in state-dict order
  * (num_batches_tracked dropped): 378,823 floats for EQTransformer, 269,675 for PhaseNet
  * (/root/reference/Final_models/volpick/{eqtransformer,phasenet}/volpick.pt.v1).  BatchNorm
  * (eps 1e-3) is folded in double precision on the host. */
-int vp_model_create(int kind, const float *weights, int64_t n_floats, int device, vp_model **out);
-int vp_model_destroy(vp_model *m);
-int vp_model_kind(const vp_model *m);
-int vp_model_in_samples(const vp_model *m); /* 6000 / 3001 */
-int64_t vp_model_expected_floats(int kind);
+VP_API int vp_model_create(int kind, const float *weights, int64_t n_floats, int device, vp_model **out);
+VP_API int vp_model_destroy(vp_model *m);
+VP_API int vp_model_kind(const vp_model *m);
+VP_API int vp_model_in_samples(const vp_model *m); /* 6000 / 3001 */
+VP_API int64_t vp_model_expected_floats(int kind);
 
 /* ---- host integer math: WaveformModel._cut_fragments_array ----------------------------- */
-int64_t vp_window_count(int64_t n_samples, int64_t in_samples, int64_t overlap);
-int vp_window_starts(int64_t n_samples, int64_t in_samples, int64_t overlap, int64_t *starts, int64_t capacity,
+VP_API int64_t vp_window_count(int64_t n_samples, int64_t in_samples, int64_t overlap);
+VP_API int vp_window_starts(int64_t n_samples, int64_t in_samples, int64_t overlap, int64_t *starts, int64_t capacity,
                      int64_t *count);
-int64_t vp_coverage(int64_t in_samples, int64_t overlap); /* ceil(L / (L - overlap) + 1) */
+VP_API int64_t vp_coverage(int64_t in_samples, int64_t overlap); /* ceil(L / (L - overlap) + 1) */
 
 /* ---- stage kernels (all pointers are device pointers) ---------------------------------- */
 /* _cut_fragments_array + annotate_batch_pre: gather windows, demean, peak-normalise (+1e-10),
  * EQTransformer 6-sample cosine taper.  trace: (3, n) with channel stride ch_stride elements,
  * f32 or i32 counts.  out: (n_windows, 3, L) f32. */
-int vp_slice_normalize(const void *trace, int dtype, int64_t n_samples, int64_t ch_stride, const int64_t *starts,
+VP_API int vp_slice_normalize(const void *trace, int dtype, int64_t n_samples, int64_t ch_stride, const int64_t *starts,
                        int64_t n_windows, int64_t in_samples, int peak_scope, int taper, float *out, void *stream);
 
 /* EQTransformer.forward / PhaseNet.forward on pre-normalised windows.
  * x: (n_windows, 3, L) -> y: (n_windows, 3, L) probabilities (sigmoid heads / channel softmax). */
-int64_t vp_forward_workspace_bytes(const vp_model *m, int64_t n_windows, int precision);
-int vp_forward(vp_model *m, const float *x, int64_t n_windows, float *y, void *workspace, int64_t workspace_bytes,
+VP_API int64_t vp_forward_workspace_bytes(const vp_model *m, int64_t n_windows, int precision);
+VP_API int vp_forward(vp_model *m, const float *x, int64_t n_windows, float *y, void *workspace, int64_t workspace_bytes,
                int precision, void *stream);
 /* Debug/parity: run the forward and copy the named intermediate activation (device->device) into
  * tap_out (capacity in floats); *tap_floats receives its size.  Names: see vp_forward_tap_names(). */
-int vp_forward_tap(vp_model *m, const float *x, int64_t n_windows, float *y, void *workspace,
+VP_API int vp_forward_tap(vp_model *m, const float *x, int64_t n_windows, float *y, void *workspace,
                    int64_t workspace_bytes, int precision, const char *tap_name, float *tap_out,
                    int64_t tap_capacity, int64_t *tap_floats, void *stream);
-const char *vp_forward_tap_names(const vp_model *m); /* comma separated */
+VP_API const char *vp_forward_tap_names(const vp_model *m); /* comma separated */
 
 /* annotate_batch_post (blinding) + _reassemble_blocks_array: y (n_windows,3,L) -> out (3,pred_len). */
-int vp_stack(const float *y, const int64_t *starts, int64_t n_windows, int64_t in_samples, int n_labels,
+VP_API int vp_stack(const float *y, const int64_t *starts, int64_t n_windows, int64_t in_samples, int n_labels,
              int64_t overlap, int64_t blind0, int64_t blind1, int mode, float *out, int64_t pred_len, void *stream);
 
 /* _trim_nan: first / last non-NaN index per label (first = pred_len, last = -1 when all NaN).
  * bounds: device int64[2 * n_labels] = {first_0, last_0, first_1, ...}. */
-int vp_nan_bounds(const float *annotation, int n_labels, int64_t pred_len, int64_t *bounds, void *stream);
+VP_API int vp_nan_bounds(const float *annotation, int n_labels, int64_t pred_len, int64_t *bounds, void *stream);
 
 /* picks_from_annotations / detections_from_annotations (trigger_onset + first argmax;
  * /root/reference/volpick/model/eval_taks0.py:46-56).  Appends to picks[*count...] (device),
  * unordered; *count (device int64) may exceed capacity -> caller must treat as overflow.
  * scratch: device buffer of vp_pick_scratch_bytes(n) bytes. */
-int64_t vp_pick_scratch_bytes(int64_t n_samples);
-int vp_pick(const float *trace, int64_t n_samples, float thr_on, float thr_off, int label, vp_trigger *picks,
+VP_API int64_t vp_pick_scratch_bytes(int64_t n_samples);
+VP_API int vp_pick(const float *trace, int64_t n_samples, float thr_on, float thr_off, int label, vp_trigger *picks,
             int64_t capacity, int64_t *count, void *scratch, int64_t scratch_bytes, void *stream);
 
 /* ---- the whole path for one gap-free record: WaveformModel.annotate + classify_aggregate -- */
-int64_t vp_annotate_workspace_bytes(const vp_model *m, int64_t n_samples, const vp_annotate_params *p,
+VP_API int64_t vp_annotate_workspace_bytes(const vp_model *m, int64_t n_samples, const vp_annotate_params *p,
                                     int trace_on_host, int64_t pick_capacity);
 /* trace: (3, n) f32/i32, on the host (pinned recommended; copied inside) or on the device.
  * annotation: optional (3, pred_len) output, host or device (NULL to skip).
  * picks: HOST buffer; sorted by (label, s0); indices relative to the record start.
  * trim: HOST int64[6] = per label {first non-NaN, last non-NaN} of the stacked annotation.
  * Synchronises the stream before returning. */
-int vp_annotate(vp_model *m, const void *trace, int trace_on_host, int dtype, int64_t n_samples, int64_t ch_stride,
+VP_API int vp_annotate(vp_model *m, const void *trace, int trace_on_host, int dtype, int64_t n_samples, int64_t ch_stride,
                 const vp_annotate_params *p, float *annotation, int annotation_on_host, vp_trigger *picks,
                 int64_t pick_capacity, int64_t *n_picks, int64_t *trim, void *workspace, int64_t workspace_bytes,
                 void *stream);

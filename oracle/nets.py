@@ -156,7 +156,7 @@ def transformer(x: torch.Tensor, sd: SD, prefix: str) -> torch.Tensor:
     return layer_norm_channels(y2, sd[prefix + ".norm2.gamma"], sd[prefix + ".norm2.beta"])
 
 
-def _eqt_decoder(x: torch.Tensor, sd: SD, prefix: str, crops: List[int]) -> torch.Tensor:
+def _eqt_decoder(x: torch.Tensor, sd: SD, prefix: str, crops: List[int], tap=None, tap_prefix: str = "") -> torch.Tensor:
     i = 0
     while f"{prefix}.convs.{i}.weight" in sd:
         w = sd[f"{prefix}.convs.{i}.weight"]
@@ -164,6 +164,8 @@ def _eqt_decoder(x: torch.Tensor, sd: SD, prefix: str, crops: List[int]) -> torc
         if i in crops:
             x = x[:, :, :-1]
         x = torch.relu(F.conv1d(x, w, sd[f"{prefix}.convs.{i}.bias"], padding=w.shape[2] // 2))
+        if tap is not None:
+            tap(f"{tap_prefix}_dec{i}", x)
         i += 1
     return x
 
@@ -243,7 +245,7 @@ def eqtransformer_forward(
         tap("transformer_d", x)
 
         crops = eqt_decoder_crops(in_samples, n_enc)
-        d = _eqt_decoder(x, sd, "decoder_d", crops)
+        d = _eqt_decoder(x, sd, "decoder_d", crops, tap, "d0")
         tap("decoder_d", d)
         det = torch.sigmoid(F.conv1d(d, sd["conv_d.weight"], sd["conv_d.bias"], padding=sd["conv_d.weight"].shape[2] // 2))
         outputs = [det.squeeze(1)]
@@ -254,7 +256,7 @@ def eqtransformer_forward(
             tap(f"pick{i}_lstm", px)
             px = seq_self_attention(px, sd, f"pick_attentions.{i}", width=3)
             tap(f"pick{i}_attn", px)
-            px = _eqt_decoder(px, sd, f"pick_decoders.{i}", crops)
+            px = _eqt_decoder(px, sd, f"pick_decoders.{i}", crops, tap, f"d{i + 1}")
             w = sd[f"pick_convs.{i}.weight"]
             pred = torch.sigmoid(F.conv1d(px, w, sd[f"pick_convs.{i}.bias"], padding=w.shape[2] // 2))
             outputs.append(pred.squeeze(1))
@@ -352,3 +354,8 @@ def macs_per_window(sd: SD, kind: str) -> float:
         m += (sd[f"pick_lstms.{i}.weight_ih_l0"].numel() + sd[f"pick_lstms.{i}.weight_hh_l0"].numel()) * T
         m += 2 * T * 16 * 32 + T * T * 32 + T * 3 * 16
     return m
+
+
+def state_dict_from_numpy(weights) -> SD:
+    """Build the torch state dict from the torch-free VPW1 container (volpick_b200.weights_io.read_vpw)."""
+    return {k: torch.from_numpy(v.copy()).float() for k, v in weights.items() if not k.endswith("num_batches_tracked")}

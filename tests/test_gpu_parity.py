@@ -1,0 +1,399 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Bars (BASELINE.json north_star): window / stacking / pick indices bit-exact given identical
+probability traces; fp32 probabilities within 1e-4 absolute of the oracle.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import volpick_b200 as vb
+from oracle import nets, pipeline
+from volpick_b200 import _lib
+from volpick_b200.synthetic import synthetic_record, synthetic_stream, station_start
+
+pytestmark = pytest.mark.gpu
+
+PROB_ATOL = 1e-4  # north_star: fp32 probability traces agree within 1e-4 absolute
+
+
+@pytest.fixture(scope="module")
+def lib():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return _lib.load()
+
+
+@pytest.fixture(scope="module")
+def eqt(lib):
+    return vb.EQTransformer.from_pretrained("volpick").cuda()
+
+
+@pytest.fixture(scope="module")
+def pn(lib):
+    return vb.PhaseNet.from_pretrained("volpick").cuda()
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _windows(kind, n_windows, seed):
+    """Pre-normalised windows cut from a synthetic record with events (so probabilities are not all ~0)."""
+    L = pipeline.IN_SAMPLES[kind]
+    x = synthetic_record(seed, L + 500 * (n_windows - 1))
+    starts = np.arange(n_windows, dtype=np.int64) * 500
+    return pipeline.prenorm(pipeline.cut_windows(x, starts, L), kind)
+
+
+# ------------------------------------------------------------------------------------------ K1
+@pytest.mark.parametrize("kind,L,taper", [("eqtransformer", 6000, 1), ("phasenet", 3001, 0)])
+@pytest.mark.parametrize("scope", ["channel", "window"])
+@pytest.mark.parametrize("dtype", ["f32", "i32"])
+def test_slice_normalize(lib, kind, L, taper, scope, dtype):
+    n = 40_123
+    x = synthetic_record(11, n)
+    x[2, :] = 0.0  # zero-filled missing component must stay exactly 0
+    if dtype == "i32":
+        x = np.round(x).astype(np.int32)
+    starts = pipeline.window_starts(n, L, L - 777)
+    ref = pipeline.prenorm(pipeline.cut_windows(x.astype(np.float32), starts, L), kind, "peak", scope)
+    d_x = torch.from_numpy(x).cuda()
+    d_s = torch.from_numpy(starts).cuda()
+    out = torch.empty((len(starts), 3, L), dtype=torch.float32, device="cuda")
+    _lib.check(lib.vp_slice_normalize(d_x.data_ptr(), 0 if dtype == "f32" else 1, n, n, d_s.data_ptr(), len(starts), L,
+                                      _lib.PEAK_SCOPE[scope], taper, out.data_ptr(), _stream()))
+    got = out.cpu().numpy()
+    assert np.all(got[:, 2] == 0)
+    np.testing.assert_allclose(got, ref, atol=2e-6, rtol=0)
+
+
+# ------------------------------------------------------------------------------------------ forward
+def _tap_report(model, kind, sd, x, groups_of):
+    taps = {}
+    xt = torch.from_numpy(x)
+    if kind == "eqtransformer":
+        ref_out = torch.stack(nets.eqtransformer_forward(sd, xt, taps), dim=1).numpy()
+    else:
+        ref_out = nets.phasenet_forward(sd, xt, taps).numpy()
+    xd = xt.cuda()
+    B = x.shape[0]
+    report = []
+    for name in model.tap_names():
+        got = model.forward_tap(xd, name).cpu().numpy()
+        ref = groups_of(name, taps, B)
+        if ref is None:
+            continue
+        got = got.reshape(ref.shape) if got.size == ref.size else got
+        if got.shape != ref.shape:  # concat buffers: compare the valid half
+            got = got.reshape(B, -1, ref.shape[-1])[:, : ref.shape[1]]
+        err = float(np.abs(got - ref).max())
+        scale = float(np.abs(ref).max())
+        report.append((name, err, scale))
+    out = model(xd)
+    got_out = (torch.stack(out, dim=1) if isinstance(out, tuple) else out).cpu().numpy()
+    return report, got_out, ref_out
+
+
+def _eqt_ref(name, taps, B):
+    if name in taps:
+        return taps[name].numpy()
+    if name == "pick_lstm":
+        return np.stack([taps["pick0_lstm"].numpy(), taps["pick1_lstm"].numpy()])
+    if name == "pick_attn":
+        return np.stack([taps["pick0_attn"].numpy(), taps["pick1_attn"].numpy()])
+    if name.startswith("dec"):
+        return np.stack([taps[f"d{g}_{name}"].numpy() for g in range(3)])
+    return None
+
+
+def _pn_ref(name, taps, B):
+    return taps[name].numpy() if name in taps else None
+
+
+def test_eqt_forward_layerwise(eqt, sd_eqt):
+    x = _windows("eqtransformer", 6, seed=21)
+    report, got, ref = _tap_report(eqt, "eqtransformer", sd_eqt, x, _eqt_ref)
+    lines = [f"{n:16s} max|diff|={e:.3e}  max|ref|={s:.3e}" for n, e, s in report]
+    print("\n".join(lines))
+    assert len(report) >= 31
+    worst = [(n, e, s) for n, e, s in report if e > 1e-4 * max(1.0, s)]
+    assert not worst, "\n".join(lines)
+    assert ref.max() > 0.5, "test windows must contain detections"
+    assert float(np.abs(got - ref).max()) <= PROB_ATOL, float(np.abs(got - ref).max())
+
+
+def test_pn_forward_layerwise(pn, sd_pn):
+    x = _windows("phasenet", 6, seed=22)
+    report, got, ref = _tap_report(pn, "phasenet", sd_pn, x, _pn_ref)
+    lines = [f"{n:16s} max|diff|={e:.3e}  max|ref|={s:.3e}" for n, e, s in report]
+    print("\n".join(lines))
+    assert len(report) >= 17
+    worst = [(n, e, s) for n, e, s in report if e > 1e-4 * max(1.0, s)]
+    assert not worst, "\n".join(lines)
+    assert ref[:, :2].max() > 0.5
+    assert float(np.abs(got - ref).max()) <= PROB_ATOL
+    np.testing.assert_allclose(got.sum(1), 1.0, atol=1e-5)
+
+
+@pytest.mark.parametrize("kind,B", [("eqtransformer", 1), ("eqtransformer", 37), ("phasenet", 1), ("phasenet", 130)])
+def test_forward_batch_sizes(eqt, pn, sd_eqt, sd_pn, kind, B):
+    model, sd = (eqt, sd_eqt) if kind == "eqtransformer" else (pn, sd_pn)
+    x = _windows(kind, B, seed=30 + B)
+    out = model(torch.from_numpy(x).cuda())
+    got = (torch.stack(out, dim=1) if isinstance(out, tuple) else out).cpu().numpy()
+    ref = pipeline.forward_batches(kind, sd, x, 64).transpose(0, 2, 1)
+    assert float(np.abs(got - ref).max()) <= PROB_ATOL
+
+
+def test_golden_window_probabilities(eqt, pn, golden):
+    for name, g in golden.items():
+        model = eqt if str(g["kind"]) == "eqtransformer" else pn
+        out = model(torch.from_numpy(g["windows01"]).cuda())
+        got = (torch.stack(out, dim=1) if isinstance(out, tuple) else out).cpu().numpy()
+        ref = g["probs01"].transpose(0, 2, 1)
+        assert float(np.abs(got - ref).max()) <= PROB_ATOL, name
+
+
+# ------------------------------------------------------------------------------------------ K9
+@pytest.mark.parametrize("L,ov,n,blind,mode", [
+    (6000, 5500, 30_000, (500, 500), "avg"), (6000, 5500, 30_123, (500, 500), "max"), (3001, 1500, 20_000, (0, 0), "avg"),
+    (3001, 1500, 20_000, (100, 50), "max"), (6000, 1800, 25_000, (500, 500), "avg"), (3001, 2900, 9_000, (0, 0), "avg"),
+    (6000, 0, 18_500, (500, 500), "avg"), (6000, 5500, 6_000, (0, 0), "avg"),
+])
+def test_stack_bit_exact(lib, L, ov, n, blind, mode):
+    rng = np.random.default_rng(n + ov)
+    starts = pipeline.window_starts(n, L, ov)
+    y = rng.random((len(starts), L, 3), dtype=np.float32)
+    if mode == "max":
+        y[rng.random(y.shape) < 0.001] = np.nan
+    ref = pipeline.reassemble(pipeline.blind(y, blind), starts, L, ov, mode).astype(np.float32)
+    d_y = torch.from_numpy(np.ascontiguousarray(y.transpose(0, 2, 1))).cuda()
+    d_s = torch.from_numpy(starts).cuda()
+    out = torch.empty((3, n), dtype=torch.float32, device="cuda")
+    _lib.check(lib.vp_stack(d_y.data_ptr(), d_s.data_ptr(), len(starts), L, 3, ov, blind[0], blind[1], _lib.STACK[mode],
+                            out.data_ptr(), n, _stream()))
+    got = out.cpu().numpy().T
+    np.testing.assert_array_equal(np.isnan(got), np.isnan(ref))
+    ok = ~np.isnan(ref)
+    np.testing.assert_array_equal(got[ok].view(np.uint32), ref[ok].view(np.uint32))  # NumPy summation order reproduced
+    bounds = torch.empty(6, dtype=torch.int64, device="cuda")
+    _lib.check(lib.vp_nan_bounds(out.data_ptr(), 3, n, bounds.data_ptr(), _stream()))
+    b = bounds.cpu().numpy().reshape(3, 2)
+    for c in range(3):
+        _, f, back = pipeline.trim_nan(ref[:, c])
+        assert (b[c, 0], b[c, 1]) == (f, n - 1 - back)
+
+
+def test_stack_rejects_bad_arguments(lib):
+    t = torch.zeros(16, device="cuda")
+    s = torch.zeros(1, dtype=torch.int64, device="cuda")
+    assert lib.vp_stack(t.data_ptr(), s.data_ptr(), 1, 4, 1, 0, 0, 0, 7, t.data_ptr(), 4, _stream()) == _lib.VP_ERR_ARG
+    assert b"Stacking method" in lib.vp_last_error()
+    assert lib.vp_stack(t.data_ptr(), s.data_ptr(), 1, 4, 1, 4, 0, 0, 0, t.data_ptr(), 4, _stream()) == _lib.VP_ERR_ARG
+
+
+# ------------------------------------------------------------------------------------------ K10
+def _gpu_picks(lib, x, thr, cap=None):
+    n = len(x)
+    cap = cap or max(n, 1)
+    d_x = torch.from_numpy(x).cuda()
+    picks = torch.zeros(cap * 32, dtype=torch.uint8, device="cuda")
+    count = torch.zeros(1, dtype=torch.int64, device="cuda")
+    sb = lib.vp_pick_scratch_bytes(n)
+    scratch = torch.empty(sb, dtype=torch.uint8, device="cuda")
+    _lib.check(lib.vp_pick(d_x.data_ptr(), n, thr, np.float32(thr) / np.float32(2), 1, picks.data_ptr(), cap, count.data_ptr(),
+                           scratch.data_ptr(), sb, _stream()))
+    k = int(count.item())
+    dt = np.dtype([("s0", "<i8"), ("s1", "<i8"), ("s_peak", "<i8"), ("value", "<f4"), ("label", "<i4")])
+    arr = np.frombuffer(picks.cpu().numpy().tobytes(), dtype=dt, count=min(k, cap))
+    return k, np.sort(arr, order="s0")
+
+
+def test_picks_bit_exact_random(lib):
+    rng = np.random.default_rng(3)
+    for trial in range(40):
+        n = int(rng.integers(1, 5000))
+        if trial % 4 == 0:
+            x = rng.random(n, dtype=np.float32)
+        else:
+            x = np.abs(np.cumsum(rng.standard_normal(n))).astype(np.float32)
+            x /= max(float(x.max()), 1e-6)
+            x[rng.random(n) < 0.01] = np.nan
+        if trial % 5 == 0:
+            x = np.round(x, 1)  # plateaus: first-argmax tie rule
+        thr = float(np.float32(rng.uniform(0.05, 0.9)))
+        ref = pipeline.picks_from_trace(x, np.float32(thr))
+        k, got = _gpu_picks(lib, x, thr)
+        assert k == len(ref), (trial, k, len(ref))
+        for g, r in zip(got, ref):
+            assert (g["s0"], g["s1"], g["s_peak"]) == r[:3] and g["value"] == np.float32(r[3]) and g["label"] == 1
+
+
+def test_picks_long_runs_and_edges(lib):
+    n = 1_000_003
+    x = np.full(n, 0.5, np.float32)  # one run spanning the whole trace, peak in the middle of a chunk
+    x[777_777] = 0.9
+    x[777_778] = 0.9  # tie -> first
+    k, got = _gpu_picks(lib, x, 0.4)
+    assert k == 1 and (got[0]["s0"], got[0]["s1"], got[0]["s_peak"]) == (0, n - 1, 777_777)
+    k, got = _gpu_picks(lib, np.zeros(100, np.float32), 0.3)
+    assert k == 0
+    x = np.zeros(64, np.float32)
+    x[63] = 1.0  # trigger on the last sample
+    k, got = _gpu_picks(lib, x, 0.3)
+    assert k == 1 and (got[0]["s0"], got[0]["s1"], got[0]["s_peak"]) == (63, 63, 63)
+    # overflow is reported through the count, never silently truncated
+    x = np.tile(np.array([1.0, 0.0], np.float32), 50)
+    k, got = _gpu_picks(lib, x, 0.3, cap=8)
+    assert k == 50 and len(got) == 8
+
+
+# ------------------------------------------------------------------------------------------ whole path
+def _oracle_triggers(kind, sd, x, overlap, blinding, stacking, thr):
+    ann = pipeline.annotate_array(kind, sd, x, overlap, blinding, stacking)
+    picks, offsets = pipeline.classify_array(kind, ann, thr)
+    return ann, picks, offsets
+
+
+@pytest.mark.parametrize("kind,n,overlap,blinding,stacking", [
+    ("phasenet", 360_000, 1500, (0, 0), "avg"),          # BASELINE.json configs[0]: one station-hour, defaults
+    ("eqtransformer", 60_000, 5500, (500, 500), "avg"),  # configs[1] settings on ten minutes
+    ("eqtransformer", 21_234, 1800, (500, 500), "max"),
+    ("phasenet", 10_000, 2000, (200, 300), "max"),
+])
+def test_annotate_matches_oracle(eqt, pn, sd_eqt, sd_pn, kind, n, overlap, blinding, stacking):
+    model, sd = (eqt, sd_eqt) if kind == "eqtransformer" else (pn, sd_pn)
+    x = synthetic_record(40, n)
+    thr = {"P_threshold": 0.2, "S_threshold": 0.2, "detection_threshold": 0.3}
+    ann, picks, offsets = _oracle_triggers(kind, sd, x, overlap, blinding, stacking, thr)
+    argdict = model._argdict(dict(overlap=overlap, blinding=blinding, stacking=stacking, **thr))
+    got_ann, trig, trim = model.annotate_array(x, argdict, True, model._thresholds(argdict))
+    # also from a CUDA-resident trace
+    got_ann2, trig2, _ = model.annotate_array(torch.from_numpy(x).cuda(), argdict, True, model._thresholds(argdict))
+    np.testing.assert_array_equal(got_ann, got_ann2)
+    np.testing.assert_array_equal(trig, trig2)
+    np.testing.assert_array_equal(np.isnan(got_ann.T), np.isnan(ann))
+    ok = ~np.isnan(ann)
+    assert float(np.abs(got_ann.T[ok] - ann[ok]).max()) <= PROB_ATOL
+    labels = pipeline.LABELS[kind]
+    for li, lab in enumerate(labels):
+        assert trim[li, 0] == offsets[lab]
+    # picks from the GPU trace == oracle pick rule applied to the SAME (GPU) probability trace: bit-exact
+    th_by_label = model._thresholds(argdict)
+    for li, lab in enumerate(labels):
+        if th_by_label[li] <= 0:
+            continue
+        col, f, _ = pipeline.trim_nan(got_ann[li])
+        ref = [(s0 + f, s1 + f, sp + f, v) for s0, s1, sp, v in pipeline.picks_from_trace(col, np.float32(th_by_label[li]))]
+        mine = trig[trig["label"] == li]
+        assert len(mine) == len(ref)
+        for g, r in zip(mine, ref):
+            assert (g["s0"], g["s1"], g["s_peak"]) == r[:3] and g["value"] == np.float32(r[3])
+        # and against the oracle's own end-to-end picks: same count, peaks within 1 sample
+        assert len(mine) == len(picks[lab]), (lab, len(mine), len(picks[lab]))
+        for g, r in zip(mine, picks[lab]):
+            assert abs(int(g["s_peak"]) - r[2]) <= 1 and abs(float(g["value"]) - r[3]) <= PROB_ATOL
+
+
+def test_golden_annotations(eqt, pn, golden):
+    for name, g in golden.items():
+        model = eqt if str(g["kind"]) == "eqtransformer" else pn
+        x = synthetic_record(int(g["station"]), int(g["n_samples"]))
+        thr = {"P_threshold": 0.2, "S_threshold": 0.2, "detection_threshold": float(g["thresholds"][0])}
+        argdict = model._argdict(dict(overlap=int(g["overlap"]), blinding=tuple(int(v) for v in g["blinding"]),
+                                      stacking=str(g["stacking"]), **thr))
+        ann, trig, trim = model.annotate_array(x, argdict, True, model._thresholds(argdict))
+        ref = g["annotation"]
+        np.testing.assert_array_equal(np.isnan(ann.T), np.isnan(ref))
+        ok = ~np.isnan(ref)
+        assert float(np.abs(ann.T[ok] - ref[ok]).max()) <= PROB_ATOL, name
+        np.testing.assert_array_equal(trim[:, 0], g["trim"])
+        gt = g["triggers"]
+        assert len(trig) == len(gt), name
+        for a, b in zip(trig, gt):
+            assert a["label"] == int(b[0]) and abs(int(a["s_peak"]) - int(b[3])) <= 1 and abs(float(a["value"]) - b[4]) <= PROB_ATOL
+
+
+def test_classify_stream_api(eqt, pn, sd_pn):
+    """The README call (/root/reference/README.md:54-66) end to end on a stream."""
+    st = synthetic_stream(0, 60_000)
+    out = eqt.classify(st, batch_size=256, overlap=5500, blinding=(500, 500), stacking="avg", parallelism=None,
+                       P_threshold=0.2, S_threshold=0.2, copy=True)
+    assert str(out).startswith("ClassifyOutput from EQTransformer")
+    assert len(out.picks) > 0 and {p.phase for p in out.picks} <= {"P", "S"}
+    assert out.picks == sorted(out.picks) and all(p.trace_id == "XX.S0000." for p in out.picks)
+    assert all(p.start_time <= p.peak_time <= p.end_time for p in out.picks)
+    assert len(out.detections) > 0
+    ann = eqt.annotate(st, overlap=4500, blinding=[1000, 1000])  # demo.ipynb cell 14
+    assert [t.stats.channel for t in ann] == ["EQTransformer_Detection", "EQTransformer_P", "EQTransformer_S"]
+    assert all(t.stats.npts == 60_000 - 2000 and t.stats.starttime == station_start(0) + 10.0 for t in ann)
+    assert not np.isnan(ann[1].data).any() and ann[1].data.dtype == np.float32
+    # PhaseNet: picks against the oracle run on the same record, as times
+    x = synthetic_record(0, 60_000)
+    picks = pn.classify(st).picks  # JSON thresholds P 0.39 / S 0.34, overlap 1500
+    ref_ann = pipeline.annotate_array("phasenet", sd_pn, x)
+    ref, _ = pipeline.classify_array("phasenet", ref_ann, {"P_threshold": 0.39, "S_threshold": 0.34})
+    for phase in "PS":
+        mine = [p for p in picks if p.phase == phase]
+        assert len(mine) == len(ref[phase])
+        for p, r in zip(mine, ref[phase]):
+            assert abs((p.peak_time - station_start(0)) * 100 - r[2]) <= 1 + 1e-6
+    pn_ann = pn.annotate(st, overlap=2500, blinding=[500, 500])  # demo.ipynb cell 13
+    assert [t.stats.channel for t in pn_ann] == ["PhaseNet_P", "PhaseNet_S", "PhaseNet_N"]
+
+
+def test_edge_records(eqt, pn):
+    # shorter than one window: empty output, no error
+    ann, trig, trim = pn.annotate_array(synthetic_record(1, 3000), None, True, [0.3, 0.3, 0.0])
+    assert ann.shape == (3, 0) and len(trig) == 0
+    out = pn.classify(synthetic_stream(1, 2000))
+    assert len(out.picks) == 0
+    # exactly one window
+    ann, trig, trim = pn.annotate_array(synthetic_record(1, 3001), None, True, [0.3, 0.3, 0.0])
+    assert ann.shape == (3, 3001) and not np.isnan(ann).any()
+    # single-component stream (demo.ipynb cell 12 feeds one EHZ trace): the others are zero-filled
+    st = synthetic_stream(2, 20_000).select(channel="HHZ")
+    a = eqt.annotate(st)
+    assert len(a) == 3 and a[0].stats.npts == 20_000 - 1000
+    # gap: two segments -> two annotation traces per label
+    full = synthetic_stream(3, 30_000)
+    parts = vb.Stream()
+    for tr in full:
+        parts.append(vb.Trace(tr.data[:12_000], dict(network="XX", station="G", location="", channel=tr.stats.channel,
+                                                      starttime=tr.stats.starttime, sampling_rate=100.0)))
+        parts.append(vb.Trace(tr.data[15_000:], dict(network="XX", station="G", location="", channel=tr.stats.channel,
+                                                      starttime=tr.stats.starttime + 150.0, sampling_rate=100.0)))
+    a = pn.annotate(parts)
+    assert len(a) == 6 and sorted({t.stats.npts for t in a}) == [12_000, 15_000]
+    # pick buffer overflow is an error, never a truncation
+    with pytest.raises(_lib.VolpickError, match="exceed the pick capacity"):
+        pn.annotate_array(synthetic_record(4, 30_000), None, False, [1e-6, 1e-6, 0.0], pick_capacity=1)
+
+
+def test_station_day_properties(eqt):
+    """Full-size config (BASELINE.json configs[1]) through size-independent properties."""
+    n = 8_640_000
+    x = synthetic_record(1000, n)
+    argdict = eqt._argdict(dict(overlap=5500, blinding=(500, 500), stacking="avg", P_threshold=0.2, S_threshold=0.2))
+    ann, trig, trim = eqt.annotate_array(x, argdict, True, eqt._thresholds(argdict))
+    assert ann.shape == (3, n)
+    assert np.all(trim[:, 0] == 500) and np.all(trim[:, 1] == n - 501)  # blinding trims 5 s on both ends
+    body = ann[:, 500 : n - 500]
+    assert not np.isnan(body).any() and body.min() >= 0 and body.max() <= 1
+    assert np.isnan(ann[:, :500]).all() and np.isnan(ann[:, n - 500 :]).all()
+    # idempotence / determinism
+    ann2, trig2, _ = eqt.annotate_array(x, argdict, True, eqt._thresholds(argdict))
+    np.testing.assert_array_equal(ann, ann2)
+    np.testing.assert_array_equal(trig, trig2)
+    # picks are exactly what the pick rule gives on the returned trace (bit-exact indices)
+    for li in (1, 2):
+        ref = pipeline.picks_from_trace(body[li], np.float32(0.2))
+        mine = trig[trig["label"] == li]
+        assert len(mine) == len(ref) and len(ref) > 100
+        assert [(int(g["s0"]), int(g["s1"]), int(g["s_peak"])) for g in mine] == [(a + 500, b + 500, c + 500) for a, b, c, _ in ref]
+    # translation property: the first hour annotated alone agrees with the day wherever the same windows cover it
+    sub, _, _ = eqt.annotate_array(x[:, :360_000], argdict, True, [0, 0, 0])
+    np.testing.assert_allclose(sub[:, 6000:354_000], ann[:, 6000:354_000], atol=1e-6)

@@ -1,0 +1,164 @@
+"""CPU tests of the host side: containers, stream bookkeeping, argument handling, weight layout,
+and that the C-ABI library loads and exports every symbol of include/volpick_b200.h."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import volpick_b200 as vb
+from oracle import pipeline
+from volpick_b200 import _lib, models, weights_io
+from volpick_b200.stream import Stream, Trace, UTCDateTime
+from volpick_b200.synthetic import synthetic_record, synthetic_stream, station_start
+
+
+def test_header_symbols_are_exported(repo_root, built_lib):
+    hdr = open(os.path.join(repo_root, "include", "volpick_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(vp_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 20
+    assert names == set(_lib.SIGNATURES), names ^ set(_lib.SIGNATURES)
+    for n in names:
+        assert hasattr(built_lib, n), n
+    assert built_lib.vp_version() >= 100
+    assert C.sizeof(_lib.Trigger) == 32 and C.sizeof(_lib.AnnotateParams) == 56
+
+
+@pytest.mark.parametrize("n,L,ov", [(360_000, 6000, 5500), (8_640_000, 3001, 1500), (6001, 6000, 100), (5999, 6000, 0),
+                                     (12345, 3001, 3000), (3001, 3001, 1500)])
+def test_vp_window_starts_matches_oracle(built_lib, n, L, ov):
+    ref = pipeline.window_starts(n, L, ov)
+    assert built_lib.vp_window_count(n, L, ov) == len(ref)
+    buf = np.zeros(max(len(ref), 1), dtype=np.int64)
+    cnt = C.c_int64(-1)
+    assert built_lib.vp_window_starts(n, L, ov, buf.ctypes.data, len(buf), C.byref(cnt)) == 0
+    assert cnt.value == len(ref)
+    np.testing.assert_array_equal(buf[: cnt.value], ref)
+    assert built_lib.vp_coverage(L, ov) == pipeline.coverage(L, ov)
+
+
+def test_vp_errors_are_loud(built_lib):
+    cnt = C.c_int64(0)
+    assert built_lib.vp_window_starts(100, 10, 10, None, 0, C.byref(cnt)) == _lib.VP_ERR_ARG
+    assert b"overlap" in built_lib.vp_last_error()
+    buf = np.zeros(1, dtype=np.int64)
+    assert built_lib.vp_window_starts(100, 10, 5, buf.ctypes.data, 1, C.byref(cnt)) == _lib.VP_ERR_CAPACITY
+    with pytest.raises(_lib.VolpickError):
+        _lib.check(_lib.VP_ERR_CAPACITY)
+    assert built_lib.vp_model_expected_floats(0) == 378_823 and built_lib.vp_model_expected_floats(1) == 269_675
+
+
+def test_utcdatetime():
+    t = UTCDateTime("2005-05-31T21:04:52.110000Z")
+    assert str(t + 18.86) == "2005-05-31T21:05:10.970000Z"
+    assert (t + 1.5) - t == 1.5 and t < t + 0.01 and t == UTCDateTime(t)
+    assert UTCDateTime("2020-01-01") + 86400.0 == UTCDateTime("2020-01-02T00:00:00")
+    assert str(station_start(3)) == "2020-01-04T00:00:00.000000Z"
+    # 100 Hz sample arithmetic is exact in integer nanoseconds
+    assert (t + 8_639_999 / 100.0).ns - t.ns == 8_639_999 * 10_000_000
+
+
+def test_stream_merge_and_segments():
+    m = vb.PhaseNet.from_pretrained("volpick")
+    x = synthetic_record(1, 9000)
+    t0 = UTCDateTime("2021-03-04T05:06:07.5")
+    hdr = dict(network="XX", station="A", location="00", sampling_rate=100.0)
+    st = Stream([
+        Trace(x[0, :4000], dict(hdr, channel="EHZ", starttime=t0)),
+        Trace(x[0, 4000:], dict(hdr, channel="EHZ", starttime=t0 + 40.0)),       # contiguous -> merged
+        Trace(x[1, :3000], dict(hdr, channel="EHN", starttime=t0)),              # N ends early, gap, resumes
+        Trace(x[1, 5000:], dict(hdr, channel="EHN", starttime=t0 + 50.0)),
+    ])
+    st.merge(-1)
+    assert len(st) == 3
+    segs = m.stream_to_arrays(list(st), m._argdict({}))
+    assert len(segs) == 1
+    s0, arr = segs[0]
+    assert s0 == t0 and arr.shape == (3, 9000) and arr.dtype == np.float32
+    np.testing.assert_array_equal(arr[0], x[0])
+    np.testing.assert_array_equal(arr[1, :3000], x[1, :3000])
+    assert np.all(arr[1, 3000:5000] == 0) and np.all(arr[2] == 0)  # missing data / component zero-filled
+    np.testing.assert_array_equal(arr[1, 5000:], x[1, 5000:])
+    # a real gap on all components splits the record
+    st2 = Stream([Trace(x[0, :3500], dict(hdr, channel="EHZ", starttime=t0)),
+                  Trace(x[0, 4000:], dict(hdr, channel="EHZ", starttime=t0 + 40.0))])
+    segs = m.stream_to_arrays(list(st2), m._argdict({}))
+    assert [a.shape[1] for _, a in segs] == [3500, 5000] and segs[1][0] == t0 + 40.0
+    # strict: only spans with all three components
+    st3 = Stream([Trace(x[i, o:], dict(hdr, channel="EH" + c, starttime=t0 + o / 100.0)) for i, (c, o) in enumerate(zip("ZNE", (0, 100, 250)))])
+    segs = m.stream_to_arrays(list(st3), m._argdict({"strict": True}))
+    assert len(segs) == 1 and segs[0][1].shape[1] == 8750 and segs[0][0] == t0 + 2.5
+    # Z12 instead of ZNE
+    st4 = Stream([Trace(x[i], dict(hdr, channel="HH" + c, starttime=t0)) for i, c in enumerate("Z12")])
+    (_, arr4), = m.stream_to_arrays(list(st4), m._argdict({}))
+    np.testing.assert_array_equal(arr4, x)
+
+
+def test_argdict_defaults_and_validation():
+    e = vb.EQTransformer.from_pretrained("volpick")
+    p = vb.PhaseNet.from_pretrained("volpick")
+    a = e._argdict({})
+    assert (a["overlap"], a["blinding"], a["stacking"], a["batch_size"]) == (1800, (500, 500), "avg", 256)
+    assert e._thresholds(a) == [pytest.approx(0.10141666), 0.22, 0.22]  # JSON default_args
+    a = e._argdict(dict(overlap=5500, blinding=[500, 500], P_threshold=0.2, S_threshold=0.2, parallelism=None, copy=True))
+    assert e._thresholds(a)[1:] == [0.2, 0.2] and a["blinding"] == (500, 500)
+    b = p._argdict({})
+    assert (b["overlap"], b["blinding"]) == (1500, (0, 0)) and p._thresholds(b) == [0.39, 0.34, 0.0]
+    assert e.labels == ["Detection", "P", "S"] and p.labels == ["P", "S", "N"]
+    assert e.in_samples == 6000 and p.in_samples == 3001 and e.norm == "peak" and e.component_order == "ZNE"
+    with pytest.raises(ValueError, match="Stacking"):
+        e._argdict(dict(stacking="median"))
+    with pytest.raises(ValueError):
+        e._argdict(dict(overlap=6000))
+    with pytest.warns(UserWarning, match="Unknown argument"):
+        e._argdict(dict(bogus=1))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        e.classify(synthetic_stream(0, 7000))
+    assert "Zhong" in e.weights_docstring and str(e.device) == "cpu"
+    assert vb.PhaseNet.list_pretrained() == ["volpick", "volpick_95train"]
+
+
+def test_weight_layout_roundtrip(tmp_path, sd_eqt):
+    w = weights_io.load_weights(weights_io.find_weights("eqtransformer", "volpick")[1])
+    flat = models.flatten_weights(w, models.eqtransformer_spec())
+    assert flat.size == 378_823 and flat.dtype == np.float32
+    np.testing.assert_array_equal(flat[: 8 * 3 * 11], sd_eqt["encoder.convs.0.weight"].numpy().reshape(-1))
+    np.testing.assert_array_equal(flat[-1:], sd_eqt["pick_convs.1.bias"].numpy())
+    wp = weights_io.load_weights(weights_io.find_weights("phasenet", "volpick_95train")[1])
+    assert models.flatten_weights(wp, models.phasenet_spec()).size == 269_675
+    path = tmp_path / "x.vpw.v1"
+    weights_io.write_vpw(str(path), w)
+    w2 = weights_io.read_vpw(str(path))
+    assert list(w2) == list(w) and all(np.array_equal(w[k], w2[k]) for k in w)
+    bad = dict(w)
+    bad["encoder.convs.0.weight"] = np.zeros((8, 3, 9), np.float32)
+    with pytest.raises(ValueError, match="expected shape"):
+        models.flatten_weights(bad, models.eqtransformer_spec())
+    m = vb.EQTransformer()
+    m.load_state_dict(sd_eqt)  # torch tensors are accepted like SeisBench's load_state_dict
+    np.testing.assert_array_equal(m._flat, flat)
+
+
+def test_reference_pt_files_convert_identically():
+    ref = "/root/reference/Final_models/volpick/phasenet/volpick.pt.v1"
+    if not os.path.exists(ref):
+        pytest.skip("reference tree not mounted (GPU box)")
+    a = weights_io.read_pt(ref)
+    b = weights_io.load_weights(weights_io.find_weights("phasenet", "volpick")[1])
+    assert list(a) == list(b) and all(np.array_equal(a[k], b[k]) for k in a)
+
+
+def test_pick_containers():
+    t = UTCDateTime("2020-01-01T00:00:10")
+    p1 = vb.Pick("XX.A.", t + 1, t + 3, t + 2, 0.9, "P")
+    p2 = vb.Pick("XX.A.", t, t + 3, t + 1, 0.5, "S")
+    pl = vb.PickList(sorted([p1, p2]))
+    assert pl[0] is p2 and len(pl.select(phase="P")) == 1 and len(pl.select(min_confidence=0.6)) == 1
+    df = pl.to_dataframe()
+    assert list(df.columns) == ["trace_id", "start_time", "end_time", "peak_time", "peak_value", "phase"]  # README.md:69-80
+    out = vb.ClassifyOutput("EQTransformer", picks=pl, detections=vb.DetectionList())
+    assert out.picks is pl and "picks" in str(out)
+    with pytest.raises(ValueError):
+        vb.Pick("XX.A.", t + 2, t + 3, t + 1, 0.9, "P")
