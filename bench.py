@@ -215,6 +215,12 @@ def run_ours(args):
     def step_host(i):
         return model.annotate_array(recs_host[i & 1], argdict, False, thresholds)
 
+    if args.profile_steps > 0:
+        for i in range(args.profile_steps):
+            step_device(i)
+        torch.cuda.synchronize()
+        return None
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -382,6 +388,8 @@ def main():
     ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32x3", "bf16"])
     ap.add_argument("--samples", type=int, default=N_DAY, help="samples per record (default: one station-day)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-steps", type=int, default=0,
+                    help="profiling aid (ncu): run this many device-resident steps and exit without timing")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

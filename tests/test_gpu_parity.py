@@ -41,10 +41,12 @@ def _stream():
 
 
 def _windows(kind, n_windows, seed):
-    """Pre-normalised windows cut from a synthetic record with events (so probabilities are not all ~0)."""
+    """Pre-normalised windows cut around the first synthetic event of a record (so that the
+    probabilities are not all ~0), starts 250 samples apart."""
     L = pipeline.IN_SAMPLES[kind]
-    x = synthetic_record(seed, L + 500 * (n_windows - 1))
-    starts = np.arange(n_windows, dtype=np.int64) * 500
+    x, events = synthetic_record(seed, 120_000, return_events=True)
+    ip = next(p for p, _ in events if p > L)
+    starts = np.clip(ip - L // 2 - 250 * (n_windows // 2) + 250 * np.arange(n_windows, dtype=np.int64), 0, x.shape[1] - L)
     return pipeline.prenorm(pipeline.cut_windows(x, starts, L), kind)
 
 
