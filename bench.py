@@ -385,7 +385,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="eqtransformer", choices=["eqtransformer", "phasenet"])
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32x3", "bf16"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "f16x3", "bf16"])
     ap.add_argument("--samples", type=int, default=N_DAY, help="samples per record (default: one station-day)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=0,

@@ -45,7 +45,9 @@ extern "C" {
 
 enum { VP_KIND_EQTRANSFORMER = 0, VP_KIND_PHASENET = 1 };
 enum { VP_STACK_AVG = 0, VP_STACK_MAX = 1 };
-enum { VP_PREC_FP32 = 0, VP_PREC_TF32X3 = 1, VP_PREC_BF16 = 2 };
+/* fp32: CUDA-core FFMA kernels.  f16x3: tcgen05 tensor cores on fp16 hi/lo split operands, three MMAs per
+ * K step into fp32 TMEM accumulators (fp32-equivalent).  bf16: tcgen05, one bf16 pass. */
+enum { VP_PREC_FP32 = 0, VP_PREC_F16X3 = 1, VP_PREC_BF16 = 2 };
 enum { VP_DTYPE_F32 = 0, VP_DTYPE_I32 = 1 };
 enum { VP_PEAK_PER_CHANNEL = 0, VP_PEAK_PER_WINDOW = 1 };
 
@@ -112,6 +114,13 @@ VP_API int vp_forward_tap(vp_model *m, const float *x, int64_t n_windows, float 
                    int64_t workspace_bytes, int precision, const char *tap_name, float *tap_out,
                    int64_t tap_capacity, int64_t *tap_floats, void *stream);
 VP_API const char *vp_forward_tap_names(const vp_model *m); /* comma separated */
+
+/* Debug/parity: ONE Conv1d through the tcgen05 path (volpick_b200/csrc/tcconv.cu).  x: device fp32
+ * (NS, CIN, T_in); w_host / bias_host: HOST fp32 (COUT, CIN, K) / (COUT) or NULL; y: device fp32
+ * (NS, COUT, T_out).  mode 0: 'same' conv; 1: x2 nearest up-sampling folded into the weights; 2: conv on
+ * the x2 up-sampled input minus `crop` trailing samples.  act: 0 none, 1 ReLU, 2 sigmoid.  pool: 1 | 2. */
+VP_API int vp_tcconv_debug(const float *x, int NS, int CIN, int T_in, const float *w_host, const float *bias_host, int COUT,
+                           int K, int mode, int crop, int act, int pool, int precision, float *y, void *stream);
 
 /* annotate_batch_post (blinding) + _reassemble_blocks_array: y (n_windows,3,L) -> out (3,pred_len). */
 VP_API int vp_stack(const float *y, const int64_t *starts, int64_t n_windows, int64_t in_samples, int n_labels,

@@ -16,7 +16,7 @@ VP_OK = 0
 VP_ERR_ARG, VP_ERR_CUDA, VP_ERR_CAPACITY, VP_ERR_WORKSPACE, VP_ERR_UNSUPPORTED = -1, -2, -3, -4, -5
 KIND_EQTRANSFORMER, KIND_PHASENET = 0, 1
 STACK = {"avg": 0, "max": 1}
-PRECISION = {"fp32": 0, "tf32x3": 1, "bf16": 2}
+PRECISION = {"fp32": 0, "f16x3": 1, "bf16": 2}
 DTYPE_F32, DTYPE_I32 = 0, 1
 PEAK_SCOPE = {"channel": 0, "window": 1}
 
@@ -61,6 +61,7 @@ SIGNATURES = {
     "vp_forward": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _i32, _vp]),
     "vp_forward_tap": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _i32, C.c_char_p, _vp, _i64, C.POINTER(_i64), _vp]),
     "vp_forward_tap_names": (C.c_char_p, [_vp]),
+    "vp_tcconv_debug": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "vp_stack": (_i32, [_vp, _vp, _i64, _i64, _i32, _i64, _i64, _i64, _i32, _vp, _i64, _vp]),
     "vp_nan_bounds": (_i32, [_vp, _i32, _i64, _vp, _vp]),
     "vp_pick_scratch_bytes": (_i64, [_i64]),

@@ -1,0 +1,79 @@
+// tcgen05 / TMEM implicit-GEMM Conv1d layer (sm_100a) -- shared declarations.
+#pragma once
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace vp {
+
+constexpr int TC_MAX_MMA = 48;
+
+struct TcMma {
+    int a_row;    // first staged row of the A operand for this MMA (tap offset)
+    int a_plane;  // first 8-channel plane of the A operand
+    int a_rowk;   // 1: the two K halves are consecutive ROWS (taps-in-K, 8-channel inputs); 0: consecutive planes
+    int b_block;  // weight block index
+};
+
+// Kernel parameters of one tensor-core conv layer launch (see tcconv.cu for the data layouts).
+struct TcP {
+    const uint16_t *x;  // channel-last 16-bit activations [SPLIT][G][NS][T_in][CIN]
+    int64_t x_split, x_gs;
+    int T_in, T_eff, ups, Tp, NS, row0, n_rows, cin8;
+    const uint16_t *w;  // [G][n_blocks][SPLIT][2][NOUT][8]
+    int64_t w_gs;
+    int n_blocks;
+    const float *bias;  // [G][NOUT]
+    int64_t b_gs;
+    int n_mma;
+    TcMma mma[TC_MAX_MMA];
+    int fmt16;  // 0: fp16, 1: bf16
+    int act, pool, ph, cout, coutp, T_valid, T_out;
+    int out_fmt;  // 0: channel-last 16-bit [SPLIT][G][NS][T_out][cout_cl]; 1: fp32 (seq stride y_ss, channel stride y_cs)
+    void *y;
+    int64_t y_split, y_gs, y_ss, y_cs;
+    int cout_cl;
+};
+
+// Host-side description of one layer: packed weight blocks + MMA schedule.
+struct TcLayer {
+    int cin = 0, cout = 0, k = 0;
+    int nout = 0;      // MMA N (phases * padded cout)
+    int ph = 1;        // 1: direct, 2: polyphase x2 up-sampling folded into the weights
+    int ups = 1;       // loader-side x2 nearest up-sampling (direct form)
+    int crop = 0;      // samples dropped at the end of the up-sampled signal
+    int split = 2;     // 2: fp16 hi/lo operands, 3 MMAs per K step (fp32-equivalent); 1: single bf16 pass
+    int row0 = 0, halo = 0, n_blocks = 0, groups = 1;
+    std::vector<TcMma> mma;
+    std::vector<uint16_t> blocks;  // [G][n_blocks][split][2][nout][8]
+    std::vector<float> bias;       // [G][nout]
+    int64_t w_off = -1, b_off = -1;  // offsets (bytes / floats) once uploaded
+};
+
+enum { TC_DIRECT = 0, TC_POLYPHASE = 1, TC_DIRECT_UPS = 2 };
+
+// weights: per group (cout, cin, k) fp32 with BatchNorm already folded; bias per group (cout) or nullptr
+int tc_build_layer(TcLayer &L, int mode, int cin, int cout, int k, int crop, int split, int groups,
+                   const float *const *weights, const float *const *bias);
+
+struct TcIO {
+    const uint16_t *x;
+    int64_t x_split, x_gs;
+    int T_in, NS;
+    const uint16_t *w_dev;
+    const float *b_dev;
+    int act, pool;
+    int out_fmt;
+    void *y;
+    int64_t y_split, y_gs, y_ss, y_cs;
+    int cout_cl;
+};
+int tc_out_len(const TcLayer &L, int T_in, int pool);
+int tc_launch(const TcLayer &L, const TcIO &io, cudaStream_t s);
+
+// fp32 channel-first (NS, C, T) [strides] -> channel-last 16-bit [SPLIT][NS][T][C8]
+int launch_pack_cl16(const float *x, int64_t x_ss, int64_t x_cs, int NS, int C, int T, int split, uint16_t *y,
+                     int64_t y_split, int c8, cudaStream_t s);
+
+}  // namespace vp
