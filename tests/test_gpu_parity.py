@@ -150,6 +150,50 @@ def test_forward_batch_sizes(eqt, pn, sd_eqt, sd_pn, kind, B):
     assert float(np.abs(got - ref).max()) <= PROB_ATOL
 
 
+@pytest.mark.parametrize("precision,atol", [("f16x3", PROB_ATOL), ("bf16", 5e-2)])
+def test_eqt_forward_tensor_core(eqt, sd_eqt, precision, atol):
+    """tcgen05 path: f16x3 (fp16 hi/lo split, 3 MMAs) must hold the fp32 tolerance; bf16 is reported with its own."""
+    x = _windows("eqtransformer", 9, seed=21)
+    xd = torch.from_numpy(x).cuda()
+    ref = torch.stack(nets.eqtransformer_forward(sd_eqt, torch.from_numpy(x)), dim=1).numpy()
+    got = torch.stack(eqt.forward(xd, precision=precision), dim=1).cpu().numpy()
+    taps = {}
+    nets.eqtransformer_forward(sd_eqt, torch.from_numpy(x), taps)
+    e6 = eqt.forward_tap(xd, "enc6", precision=precision).cpu().numpy().reshape(taps["enc6"].shape)
+    print(f"{precision}: enc6 max|diff| = {np.abs(e6 - taps['enc6'].numpy()).max():.3e} (max|ref| {taps['enc6'].abs().max():.2f}); "
+          f"probabilities max|diff| = {np.abs(got - ref).max():.3e}")
+    assert ref.max() > 0.5
+    assert float(np.abs(got - ref).max()) <= atol
+
+
+def test_annotate_tensor_core_exact_mode(eqt, sd_eqt):
+    """f16x3 end to end: probabilities within 1e-4 of the oracle and identical picks to the fp32 CUDA-core path."""
+    x = synthetic_record(40, 60_000)
+    thr = {"P_threshold": 0.2, "S_threshold": 0.2, "detection_threshold": 0.3}
+    a32 = eqt._argdict(dict(overlap=5500, blinding=(500, 500), stacking="avg", **thr))
+    atc = eqt._argdict(dict(overlap=5500, blinding=(500, 500), stacking="avg", precision="f16x3", **thr))
+    ann32, trig32, _ = eqt.annotate_array(x, a32, True, eqt._thresholds(a32))
+    anntc, trigtc, _ = eqt.annotate_array(x, atc, True, eqt._thresholds(atc))
+    ref = pipeline.annotate_array("eqtransformer", sd_eqt, x, 5500, (500, 500), "avg")
+    ok = ~np.isnan(ref)
+    np.testing.assert_array_equal(np.isnan(anntc.T), np.isnan(ref))
+    err = float(np.abs(anntc.T[ok] - ref[ok]).max())
+    print(f"f16x3 annotate: max|prob - oracle| = {err:.3e}; fp32 path: {np.abs(ann32.T[ok] - ref[ok]).max():.3e}")
+    assert err <= PROB_ATOL
+    assert len(trigtc) == len(trig32) and len(trig32) > 0
+    assert np.array_equal(trigtc["label"], trig32["label"])
+    assert np.abs(trigtc["s_peak"] - trig32["s_peak"]).max() <= 1
+    abf = eqt._argdict(dict(overlap=5500, blinding=(500, 500), stacking="avg", precision="bf16", **thr))
+    annbf, trigbf, _ = eqt.annotate_array(x, abf, True, eqt._thresholds(abf))
+    errbf = float(np.abs(annbf.T[ok] - ref[ok]).max())
+    match = 0
+    for t in trig32:
+        cand = trigbf[trigbf["label"] == t["label"]]
+        match += int(len(cand) > 0 and np.abs(cand["s_peak"] - t["s_peak"]).min() <= 1)
+    print(f"bf16 annotate: max|prob - oracle| = {errbf:.3e}; picks {len(trigbf)} vs {len(trig32)}, matched within 1 sample: {match}")
+    assert errbf <= 5e-2
+
+
 def test_golden_window_probabilities(eqt, pn, golden):
     for name, g in golden.items():
         model = eqt if str(g["kind"]) == "eqtransformer" else pn

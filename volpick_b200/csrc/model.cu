@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "tcconv.cuh"
 
 namespace vp {
 
@@ -201,7 +202,38 @@ struct vp_model {
     // PhaseNet
     ConvW inc, down_same[5], down_down[4], up_t[4], up_same[4], outc;
     std::string tap_names;
+    // tensor-core (tcgen05) weight sets: [0] = fp16 hi/lo split (f16x3), [1] = bf16
+    struct TcSet {
+        TcLayer enc[7], dec[7], head;
+        uint16_t *d_w = nullptr;
+        float *d_b = nullptr;
+        bool ready = false;
+    } tc[2];
 };
+
+static int upload_tc(vp_model::TcSet &ts) {
+    std::vector<TcLayer *> layers;
+    for (int i = 0; i < 7; ++i) layers.push_back(&ts.enc[i]);
+    for (int i = 0; i < 7; ++i) layers.push_back(&ts.dec[i]);
+    layers.push_back(&ts.head);
+    size_t nw = 0, nb = 0;
+    for (TcLayer *L : layers) {
+        L->w_off = (int64_t)nw;
+        L->b_off = (int64_t)nb;
+        nw += (L->blocks.size() + 63) / 64 * 64;
+        nb += (L->bias.size() + 63) / 64 * 64;
+    }
+    VP_CUDA_CHECK(cudaMalloc(&ts.d_w, nw * sizeof(uint16_t) + 256));
+    VP_CUDA_CHECK(cudaMalloc(&ts.d_b, nb * sizeof(float) + 256));
+    for (TcLayer *L : layers) {
+        VP_CUDA_CHECK(cudaMemcpy(ts.d_w + L->w_off, L->blocks.data(), L->blocks.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+        VP_CUDA_CHECK(cudaMemcpy(ts.d_b + L->b_off, L->bias.data(), L->bias.size() * sizeof(float), cudaMemcpyHostToDevice));
+        L->blocks.clear();
+        L->blocks.shrink_to_fit();
+    }
+    ts.ready = true;
+    return VP_OK;
+}
 
 static const int kEncC[8] = {3, 8, 16, 16, 32, 32, 64, 64};
 static const int kEncK[7] = {11, 9, 7, 7, 5, 5, 3};
@@ -210,10 +242,13 @@ static const int kDecC[8] = {16, 64, 64, 32, 32, 16, 16, 8};
 static const int kDecK[7] = {3, 5, 5, 7, 7, 9, 11};
 static const int kPnC[5] = {8, 16, 32, 64, 128};
 
-static void build_eqt(vp_model *m, Cursor &cur, Packed &pk) {
+static int build_eqt(vp_model *m, Cursor &cur, Packed &pk) {
+    const float *eW[7], *eB[7];
     for (int i = 0; i < 7; ++i) {
         const float *W = cur.take((int64_t)kEncC[i + 1] * kEncC[i] * kEncK[i]);
         const float *b = cur.take(kEncC[i + 1]);
+        eW[i] = W;
+        eB[i] = b;
         m->enc[i] = pack_conv(pk, W, b, nullptr, kEncC[i + 1], kEncC[i], kEncK[i]);
     }
     for (int i = 0; i < 7; ++i) {
@@ -288,6 +323,39 @@ static void build_eqt(vp_model *m, Cursor &cur, Packed &pk) {
         "enc0,enc1,enc2,enc3,enc4,enc5,enc6,res0,res1,res2,res3,res4,res5,res6,bilstm0_lstm,bilstm0,"
         "bilstm1_lstm,bilstm1,bilstm2_lstm,bilstm2,transformer_d0,transformer_d,pick_lstm,pick_attn,"
         "dec0,dec1,dec2,dec3,dec4,dec5,dec6";
+    // ---- tensor-core weight sets (tcconv.cu): encoder direct convs, decoders with the x2 up-sampling
+    // folded into the weights (layer 2 keeps the explicit up-sampling because of its crop), heads
+    for (int set = 0; set < 2; ++set) {
+        const int split = set == 0 ? 2 : 1;
+        vp_model::TcSet &ts = m->tc[set];
+        for (int i = 0; i < 7; ++i) {
+            int cin = kEncC[i];
+            std::vector<float> wpad;
+            const float *W = eW[i];
+            if (cin == 3) {  // pad the 3 input components to one 8-channel plane
+                wpad.assign((size_t)kEncC[i + 1] * 8 * kEncK[i], 0.f);
+                for (int co = 0; co < kEncC[i + 1]; ++co)
+                    for (int ci = 0; ci < 3; ++ci)
+                        for (int kk = 0; kk < kEncK[i]; ++kk)
+                            wpad[((size_t)co * 8 + ci) * kEncK[i] + kk] = W[((size_t)co * 3 + ci) * kEncK[i] + kk];
+                W = wpad.data();
+                cin = 8;
+            }
+            const float *wl[1] = {W}, *bl[1] = {eB[i]};
+            int rc = tc_build_layer(ts.enc[i], TC_DIRECT, cin, kEncC[i + 1], kEncK[i], 0, split, 1, wl, bl);
+            if (rc != VP_OK) return rc;
+        }
+        for (int i = 0; i < 7; ++i) {
+            const float *wl[3] = {dW[0][i], dW[1][i], dW[2][i]}, *bl[3] = {dB[0][i], dB[1][i], dB[2][i]};
+            const int mode = (i == 2) ? TC_DIRECT_UPS : TC_POLYPHASE;  // decoder stage 2 crops one sample (376 -> 375)
+            int rc = tc_build_layer(ts.dec[i], mode, kDecC[i], kDecC[i + 1], kDecK[i], i == 2 ? 1 : 0, split, 3, wl, bl);
+            if (rc != VP_OK) return rc;
+        }
+        const float *wl[3] = {hW[0], hW[1], hW[2]}, *bl[3] = {hB[0], hB[1], hB[2]};
+        int rc = tc_build_layer(ts.head, TC_DIRECT, 8, 1, 11, 0, split, 3, wl, bl);
+        if (rc != VP_OK) return rc;
+    }
+    return VP_OK;
 }
 
 static void build_pn(vp_model *m, Cursor &cur, Packed &pk) {
@@ -347,6 +415,7 @@ struct Runner {
     vp_model *m;
     cudaStream_t s;
     int B;
+    int precision = VP_PREC_FP32;
     bool dry;               // only measure the workspace
     const char *stop_name;  // stop after this tap (debug)
     Tap hit{nullptr, nullptr, 0};
@@ -428,27 +497,87 @@ static int run_eqt(Runner &r, const float *x, float *y, Arena &ar) {
         big = std::max<int64_t>(big, (int64_t)kEncC[i + 1] * len[i + 1]);
         big = std::max<int64_t>(big, 3 * (int64_t)kDecC[i + 1] * dlen[i + 1]);
     }
-    float *P = ar.take(B * big), *Q = ar.take(B * big);
+    const bool tc = r.precision != VP_PREC_FP32;
+    const int split = (r.precision == VP_PREC_F16X3) ? 2 : 1;
+    vp_model::TcSet &ts = m->tc[split == 2 ? 0 : 1];
+    // 16-bit channel-last ping-pong buffers of the tensor-core path: [split][B * big16] elements each
+    const int64_t big16 = std::max<int64_t>(big, (int64_t)8 * L);
+    float *P = nullptr, *Q = nullptr;
+    uint16_t *P16 = nullptr, *Q16 = nullptr;
+    if (tc) {
+        P16 = reinterpret_cast<uint16_t *>(ar.take((B * big16 * split + 1) / 2));
+        Q16 = reinterpret_cast<uint16_t *>(ar.take((B * big16 * split + 1) / 2));
+    } else {
+        P = ar.take(B * big);
+        Q = ar.take(B * big);
+    }
+    const int64_t split16 = B * big16;  // elements between the hi and lo planes
     float *r0 = ar.take(B * 64 * T), *r1 = ar.take(B * 64 * T), *r2 = ar.take(B * 64 * T);
     float *lo = ar.take(B * 32 * T);
     float *s0 = ar.take(B * 16 * T), *s1 = ar.take(B * 16 * T);
     float *din = ar.take(3 * B * 16 * T);  // [group][B][16][T]: decoder inputs
     float *plo = ar.take(2 * B * 16 * T);  // pick LSTM outputs [group][B][16][T]
     if (r.dry) return VP_OK;
+    if (tc && !ts.ready) {
+        set_error("tensor-core weight set is not available");
+        return VP_ERR_UNSUPPORTED;
+    }
 
-    // ---- encoder
-    const float *cur = x;
-    int cur_c = 3;
     float *pp[2] = {P, Q};
+    uint16_t *pp16[2] = {P16, Q16};
     static const char *enc_names[7] = {"enc0", "enc1", "enc2", "enc3", "enc4", "enc5", "enc6"};
-    for (int i = 0; i < 7; ++i) {
-        float *dst = (i == 6) ? r0 : pp[i & 1];
-        const ConvW &cw = m->enc[i];
-        r.conv(cw, 1, 1, 2, ACT_RELU, nullptr, nullptr, 0, cur, (int64_t)cur_c * len[i], 0, len[i], len[i], cw.k / 2,
-               len[i], len[i + 1], dst, (int64_t)cw.cout * len[i + 1], 0, 1, 0, 0);
-        if (r.tap(enc_names[i], dst, B * cw.cout * len[i + 1])) return r.rc;
-        cur = dst;
-        cur_c = cw.cout;
+    if (!tc) {
+        // ---- encoder (fp32 CUDA cores)
+        const float *cur = x;
+        int cur_c = 3;
+        for (int i = 0; i < 7; ++i) {
+            float *dst = (i == 6) ? r0 : pp[i & 1];
+            const ConvW &cw = m->enc[i];
+            r.conv(cw, 1, 1, 2, ACT_RELU, nullptr, nullptr, 0, cur, (int64_t)cur_c * len[i], 0, len[i], len[i], cw.k / 2,
+                   len[i], len[i + 1], dst, (int64_t)cw.cout * len[i + 1], 0, 1, 0, 0);
+            if (r.tap(enc_names[i], dst, B * cw.cout * len[i + 1])) return r.rc;
+            cur = dst;
+            cur_c = cw.cout;
+        }
+    } else {
+        // ---- encoder on the tensor cores: x (B,3,L) fp32 -> channel-last 16-bit [B][L][8] -> 7 x (conv, ReLU, pool)
+        if (r.go()) r.rc = launch_pack_cl16(x, 3 * (int64_t)L, L, (int)B, 3, L, split, Q16, split16, 1, r.s);
+        const uint16_t *cur16 = Q16;
+        for (int i = 0; i < 7; ++i) {
+            const TcLayer &tl = ts.enc[i];
+            if (r.go()) {
+                TcIO io;
+                io.x = cur16;
+                io.x_split = split16;
+                io.x_gs = 0;
+                io.T_in = len[i];
+                io.NS = (int)B;
+                io.w_dev = ts.d_w + tl.w_off;
+                io.b_dev = ts.d_b + tl.b_off;
+                io.act = ACT_RELU;
+                io.pool = 2;
+                if (i == 6) {  // last encoder stage feeds the fp32 bottleneck: (B, 64, T) channel-first
+                    io.out_fmt = 1;
+                    io.y = r0;
+                    io.y_split = 0;
+                    io.y_gs = 0;
+                    io.y_ss = 64 * (int64_t)T;
+                    io.y_cs = T;
+                    io.cout_cl = 0;
+                } else {
+                    io.out_fmt = 0;
+                    io.y = pp16[i & 1];
+                    io.y_split = split16;
+                    io.y_gs = 0;
+                    io.y_ss = 0;
+                    io.y_cs = 0;
+                    io.cout_cl = tl.cout;
+                }
+                r.rc = tc_launch(tl, io, r.s);
+            }
+            if (i == 6 && r.tap(enc_names[i], r0, B * 64 * T)) return r.rc;
+            cur16 = pp16[i & 1];
+        }
     }
     // ---- res-CNN stack: x in ra; tmp r1; out rb
     static const char *res_names[7] = {"res0", "res1", "res2", "res3", "res4", "res5", "res6"};
@@ -558,6 +687,58 @@ static int run_eqt(Runner &r, const float *x, float *y, Arena &ar) {
         r.rc = launch_attention(p, 2, r.s);
     }
     if (r.tap("pick_attn", din + B * 16 * T, 2 * B * 16 * T)) return r.rc;
+    if (tc) {
+        // ---- decoders + heads on the tensor cores: din (3, B, 16, T) fp32 -> [3][B][T][16] 16-bit
+        if (r.go()) r.rc = launch_pack_cl16(din, 16 * (int64_t)T, T, (int)(3 * B), 16, T, split, Q16, split16, 2, r.s);
+        const uint16_t *cur16 = Q16;
+        for (int i = 0; i < 7; ++i) {
+            const TcLayer &tl = ts.dec[i];
+            uint16_t *dst = pp16[i & 1];
+            if (r.go()) {
+                TcIO io;
+                io.x = cur16;
+                io.x_split = split16;
+                io.x_gs = B * (int64_t)tl.cin * dlen[i];
+                io.T_in = dlen[i];
+                io.NS = (int)B;
+                io.w_dev = ts.d_w + tl.w_off;
+                io.b_dev = ts.d_b + tl.b_off;
+                io.act = ACT_RELU;
+                io.pool = 1;
+                io.out_fmt = 0;
+                io.y = dst;
+                io.y_split = split16;
+                io.y_gs = B * (int64_t)tl.cout * dlen[i + 1];
+                io.y_ss = 0;
+                io.y_cs = 0;
+                io.cout_cl = tl.cout;
+                r.rc = tc_launch(tl, io, r.s);
+            }
+            cur16 = dst;
+        }
+        if (r.go()) {
+            const TcLayer &tl = ts.head;
+            TcIO io;
+            io.x = cur16;
+            io.x_split = split16;
+            io.x_gs = B * 8 * (int64_t)L;
+            io.T_in = L;
+            io.NS = (int)B;
+            io.w_dev = ts.d_w + tl.w_off;
+            io.b_dev = ts.d_b + tl.b_off;
+            io.act = ACT_SIGMOID;
+            io.pool = 1;
+            io.out_fmt = 1;
+            io.y = y;
+            io.y_split = 0;
+            io.y_gs = L;
+            io.y_ss = 3 * (int64_t)L;
+            io.y_cs = 0;
+            io.cout_cl = 0;
+            r.rc = tc_launch(tl, io, r.s);
+        }
+        return r.rc;
+    }
     // ---- the three decoders as 3 groups per layer
     static const char *dec_names[7] = {"dec0", "dec1", "dec2", "dec3", "dec4", "dec5", "dec6"};
     const float *dcur = din;
@@ -670,11 +851,16 @@ static int run_pn(Runner &r, const float *x, float *y, Arena &ar) {
 
 static int run_forward(vp_model *m, const float *x, int64_t B, float *y, void *ws, int64_t ws_bytes, int precision,
                        const char *stop, Tap *hit, cudaStream_t s, int64_t *need_bytes) {
-    if (precision != VP_PREC_FP32) {
-        set_error("precision mode %d is not available in this build (fp32 only)", precision);
+    if (precision != VP_PREC_FP32 && precision != VP_PREC_F16X3 && precision != VP_PREC_BF16) {
+        set_error("unknown precision mode %d", precision);
+        return VP_ERR_ARG;
+    }
+    if (precision != VP_PREC_FP32 && m->kind != VP_KIND_EQTRANSFORMER) {
+        set_error("the tensor-core precision modes are implemented for EQTransformer only (PhaseNet: fp32)");
         return VP_ERR_UNSUPPORTED;
     }
     Runner r;
+    r.precision = precision;
     r.m = m;
     r.s = s;
     r.B = (int)B;
@@ -721,7 +907,15 @@ extern "C" int vp_model_create(int kind, const float *weights, int64_t n_floats,
     m->in_samples = kind == VP_KIND_EQTRANSFORMER ? 6000 : 3001;
     Cursor cur{weights, n_floats};
     Packed pk;
-    if (kind == VP_KIND_EQTRANSFORMER) build_eqt(m, cur, pk); else build_pn(m, cur, pk);
+    if (kind == VP_KIND_EQTRANSFORMER) {
+        int rc = build_eqt(m, cur, pk);
+        if (rc != VP_OK) {
+            delete m;
+            return rc;
+        }
+    } else {
+        build_pn(m, cur, pk);
+    }
     if (cur.left != 0) {
         set_error("vp_model_create: weight walk left %lld floats (layout mismatch)", (long long)cur.left);
         delete m;
@@ -736,6 +930,15 @@ extern "C" int vp_model_create(int kind, const float *weights, int64_t n_floats,
         delete m;
         return VP_ERR_CUDA;
     }
+    if (kind == VP_KIND_EQTRANSFORMER) {
+        for (int set = 0; set < 2; ++set) {
+            int rc = upload_tc(m->tc[set]);
+            if (rc != VP_OK) {
+                vp_model_destroy(m);
+                return rc;
+            }
+        }
+    }
     *out = m;
     return VP_OK;
 }
@@ -743,6 +946,10 @@ extern "C" int vp_model_create(int kind, const float *weights, int64_t n_floats,
 extern "C" int vp_model_destroy(vp_model *m) {
     if (!m) return VP_OK;
     if (m->d_weights) cudaFree(m->d_weights);
+    for (int set = 0; set < 2; ++set) {
+        if (m->tc[set].d_w) cudaFree(m->tc[set].d_w);
+        if (m->tc[set].d_b) cudaFree(m->tc[set].d_b);
+    }
     delete m;
     return VP_OK;
 }

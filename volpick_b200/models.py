@@ -333,7 +333,7 @@ class WaveformModel:
 
     __call__ = forward
 
-    def forward_tap(self, x, tap: str):
+    def forward_tap(self, x, tap: str, precision: Optional[str] = None):
         """Debug/parity helper: the named intermediate activation as a flat CUDA tensor."""
         import torch
 
@@ -341,14 +341,15 @@ class WaveformModel:
         x = x.contiguous().float()
         B = x.shape[0]
         lib = _lib.load()
+        prec = _lib.PRECISION[precision or self.precision]
         y = torch.empty((B, 3, self.in_samples), dtype=torch.float32, device=x.device)
-        need = _lib.check(lib.vp_forward_workspace_bytes(self._handle, B, 0))
+        need = _lib.check(lib.vp_forward_workspace_bytes(self._handle, B, prec))
         ws = self._get_workspace(need)
         cap = B * 3 * 48000 * 2
         out = torch.empty(cap, dtype=torch.float32, device=x.device)
         n = C.c_int64(0)
         _lib.check(lib.vp_forward_tap(self._handle, C.c_void_p(x.data_ptr()), B, C.c_void_p(y.data_ptr()),
-                                      C.c_void_p(ws.data_ptr()), ws.numel(), 0, tap.encode(),
+                                      C.c_void_p(ws.data_ptr()), ws.numel(), prec, tap.encode(),
                                       C.c_void_p(out.data_ptr()), cap, C.byref(n), self._stream_ptr()))
         return out[: n.value]
 
