@@ -266,7 +266,7 @@ def run_ours(args):
     # ---- per-stage device timings (rank 0) for the roofline objects ---------------------------
     stages = {}
     if rank == 0:
-        stages = stage_timings(model, lib, recs_dev[0], argdict, thresholds, kind)
+        stages = stage_timings(model, lib, recs_dev[0], argdict, thresholds, kind, precision=_lib.PRECISION[args.precision])
     peaks = measured_peaks()
     line = None
     if rank == 0:
@@ -302,7 +302,7 @@ def run_ours(args):
     return line
 
 
-def stage_timings(model, lib, rec_dev, argdict, thresholds, kind, reps: int = 3):
+def stage_timings(model, lib, rec_dev, argdict, thresholds, kind, reps: int = 3, precision: int = 0):
     """CUDA-event timings of the four stages on the current stream, through the stage-level C ABI."""
     import torch
 
@@ -320,7 +320,7 @@ def stage_timings(model, lib, rec_dev, argdict, thresholds, kind, reps: int = 3)
     d_x = torch.empty((chunk, 3, L), dtype=torch.float32, device="cuda")
     d_y = torch.empty((nwin, 3, L), dtype=torch.float32, device="cuda")
     d_ann = torch.empty((3, n), dtype=torch.float32, device="cuda")
-    ws_bytes = int(lib.vp_forward_workspace_bytes(model._handle, chunk, 0))
+    ws_bytes = int(lib.vp_forward_workspace_bytes(model._handle, chunk, precision))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
     sb = int(lib.vp_pick_scratch_bytes(n))
     scratch = torch.empty(sb, dtype=torch.uint8, device="cuda")
@@ -343,7 +343,7 @@ def stage_timings(model, lib, rec_dev, argdict, thresholds, kind, reps: int = 3)
             _lib.check(lib.vp_slice_normalize(rec_dev.data_ptr(), 0, n, rec_dev.stride(0), d_starts.data_ptr() + 8 * w0, nw, L,
                                               0, 1 if kind == "eqtransformer" else 0, d_x.data_ptr(), stream))
             b.record()
-            _lib.check(lib.vp_forward(model._handle, d_x.data_ptr(), nw, d_y.data_ptr() + 4 * 3 * L * w0, ws.data_ptr(), ws_bytes, 0, stream))
+            _lib.check(lib.vp_forward(model._handle, d_x.data_ptr(), nw, d_y.data_ptr() + 4 * 3 * L * w0, ws.data_ptr(), ws_bytes, precision, stream))
             c.record()
             evs.append((a, b, c))
         a, b, c = ev(), ev(), ev()

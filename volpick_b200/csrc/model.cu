@@ -504,9 +504,11 @@ static int run_eqt(Runner &r, const float *x, float *y, Arena &ar) {
     const int64_t big16 = std::max<int64_t>(big, (int64_t)8 * L);
     float *P = nullptr, *Q = nullptr;
     uint16_t *P16 = nullptr, *Q16 = nullptr;
+    float *hbuf = nullptr;  // tensor-core path: last decoder stage in fp32 (3, B, 8, L) for the CUDA-core heads
     if (tc) {
         P16 = reinterpret_cast<uint16_t *>(ar.take((B * big16 * split + 1) / 2));
         Q16 = reinterpret_cast<uint16_t *>(ar.take((B * big16 * split + 1) / 2));
+        hbuf = ar.take(3 * B * 8 * (int64_t)L);
     } else {
         P = ar.take(B * big);
         Q = ar.take(B * big);
@@ -705,37 +707,32 @@ static int run_eqt(Runner &r, const float *x, float *y, Arena &ar) {
                 io.b_dev = ts.d_b + tl.b_off;
                 io.act = ACT_RELU;
                 io.pool = 1;
-                io.out_fmt = 0;
-                io.y = dst;
-                io.y_split = split16;
-                io.y_gs = B * (int64_t)tl.cout * dlen[i + 1];
-                io.y_ss = 0;
-                io.y_cs = 0;
-                io.cout_cl = tl.cout;
+                if (i == 6) {  // N = 1 heads run on the CUDA cores: hand them fp32 channel-first activations
+                    io.out_fmt = 1;
+                    io.y = hbuf;
+                    io.y_split = 0;
+                    io.y_gs = B * 8 * (int64_t)L;
+                    io.y_ss = 8 * (int64_t)L;
+                    io.y_cs = L;
+                    io.cout_cl = 0;
+                } else {
+                    io.out_fmt = 0;
+                    io.y = dst;
+                    io.y_split = split16;
+                    io.y_gs = B * (int64_t)tl.cout * dlen[i + 1];
+                    io.y_ss = 0;
+                    io.y_cs = 0;
+                    io.cout_cl = tl.cout;
+                }
                 r.rc = tc_launch(tl, io, r.s);
             }
             cur16 = dst;
         }
-        if (r.go()) {
-            const TcLayer &tl = ts.head;
-            TcIO io;
-            io.x = cur16;
-            io.x_split = split16;
-            io.x_gs = B * 8 * (int64_t)L;
-            io.T_in = L;
-            io.NS = (int)B;
-            io.w_dev = ts.d_w + tl.w_off;
-            io.b_dev = ts.d_b + tl.b_off;
-            io.act = ACT_SIGMOID;
-            io.pool = 1;
-            io.out_fmt = 1;
-            io.y = y;
-            io.y_split = 0;
-            io.y_gs = L;
-            io.y_ss = 3 * (int64_t)L;
-            io.y_cs = 0;
-            io.cout_cl = 0;
-            r.rc = tc_launch(tl, io, r.s);
+        {
+            const ConvW &cw = m->head[0];
+            const int64_t w_gs = m->head[1].w - m->head[0].w, b_gs = m->head[1].b - m->head[0].b;
+            r.conv(cw, 1, 1, 1, ACT_SIGMOID, nullptr, nullptr, 0, hbuf, 8 * (int64_t)L, B * 8 * (int64_t)L, L, L, 5, L, L, y,
+                   3 * (int64_t)L, L, 3, w_gs, b_gs);
         }
         return r.rc;
     }

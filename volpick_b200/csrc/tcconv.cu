@@ -116,146 +116,213 @@ __device__ __forceinline__ void split16(float v, int fmt16, int split, uint16_t 
 }
 
 // ------------------------------------------------------------------------------------------ the layer kernel
+// Persistent, warp-specialised CTA (256 threads):
+//   warps 0-3  epilogue: TMEM lane quarter -> registers -> bias/act/pool -> global
+//   warp  4    MMA issuer (one elected lane) + TMEM allocation (2 accumulator buffers)
+//   warps 5-7  producers: cp.async (zero-fill) of the A tiles into an NSTAGE ring
+// Barriers: full[stage] (96 producer arrivals via cp.async.mbarrier.arrive.noinc), empty[stage]
+// (tcgen05.commit), accf[acc] (tcgen05.commit), acce[acc] (128 epilogue arrivals).  The weights of the
+// layer are loaded once per CTA and stay resident in shared memory.
+constexpr int TC_THREADS = 256;
+constexpr int TC_PRODUCERS = 96;
+constexpr int TC_MAX_STAGES = 4;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t *bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 template <int NOUT, int SPLIT>
-__global__ void __launch_bounds__(128) tcconv_kernel(const __grid_constant__ TcP p) {
+__global__ void __launch_bounds__(TC_THREADS) tcconv_kernel(const __grid_constant__ TcP p) {
     extern __shared__ __align__(128) uint8_t tc_smem[];
-    __shared__ __align__(8) uint64_t mbar;
+    __shared__ __align__(8) uint64_t full_bar[TC_MAX_STAGES], empty_bar[TC_MAX_STAGES], accf_bar[2], acce_bar[2];
     __shared__ uint32_t tmem_base_s;
     constexpr int NCOLS = NOUT < 32 ? 32 : NOUT;
 
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = blockIdx.y;
-    const int64_t m0 = (int64_t)blockIdx.x * 128;
-    const int n_rows = p.n_rows, cin8 = p.cin8;
+    const int n_rows = p.n_rows, cin8 = p.cin8, nstage = p.n_stages;
     const uint32_t PL = (uint32_t)n_rows * 16u;  // bytes per 8-channel plane
     const uint32_t a_bytes = ((uint32_t)SPLIT * cin8 * PL + 127u) & ~127u;
-    uint8_t *sA = tc_smem;
-    uint8_t *sB = tc_smem + a_bytes;
-    const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
+    const uint32_t w_bytes = ((uint32_t)p.n_blocks * SPLIT * 2 * NOUT * 16u + 127u) & ~127u;
+    const uint32_t sB_u = smem_u32(tc_smem);
+    const uint32_t sA_u = sB_u + w_bytes;
+    const int64_t n_tiles = ((int64_t)p.NS * p.Tp + 127) / 128;
 
     if (tid == 0) {
-        mbar_init(&mbar, 1);
+        for (int i = 0; i < nstage; ++i) {
+            mbar_init(&full_bar[i], TC_PRODUCERS);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&accf_bar[i], 1);
+            mbar_init(&acce_bar[i], 128);
+        }
         fence_barrier_init();
     }
-    if (warp == 0) tmem_alloc(&tmem_base_s, NCOLS);
-
-    // ---- stage A: (split, row, plane) 16-byte pieces; rows outside a sequence are zero-filled
-    {
-        const int CIN = cin8 * 8;
-        const int total = SPLIT * n_rows * cin8;
-        const uint16_t *xg = p.x + (int64_t)g * p.x_gs;
-        for (int idx = tid; idx < total; idx += 128) {
-            const int c = idx % cin8;
-            const int rr = idx / cin8;
-            const int r = rr % n_rows;
-            const int s = rr / n_rows;
-            const int64_t v = m0 + p.row0 + r;
-            bool valid = v >= 0;
-            int64_t seq = 0;
-            int u = 0;
-            if (valid) {
-                seq = v / p.Tp;
-                u = (int)(v - seq * p.Tp);
-                valid = (seq < p.NS) && (u < p.T_eff);
-            }
-            const int srow = (p.ups == 2) ? (u >> 1) : u;
-            const uint16_t *src = valid ? (xg + (int64_t)s * p.x_split + (seq * p.T_in + srow) * CIN + c * 8) : xg;
-            cp_async16(sA_u + (uint32_t)((s * cin8 + c) * n_rows + r) * 16u, src, valid ? 16u : 0u);
-        }
+    if (warp == 4) tmem_alloc(&tmem_base_s, 2 * NCOLS);
+    {   // resident weights
         const int wpieces = p.n_blocks * SPLIT * 2 * NOUT;
         const uint4 *wg = reinterpret_cast<const uint4 *>(p.w + (int64_t)g * p.w_gs);
-        for (int idx = tid; idx < wpieces; idx += 128) cp_async16(sB_u + (uint32_t)idx * 16u, wg + idx, 16u);
+        for (int idx = tid; idx < wpieces; idx += TC_THREADS) cp_async16(sB_u + (uint32_t)idx * 16u, wg + idx, 16u);
+        cp_async_wait_all();
+        fence_proxy_async();
     }
-    cp_async_wait_all();
-    fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
 
-    // ---- one thread issues the whole MMA chain of the tile
-    if (tid == 0) {
-        const uint32_t idesc = umma_idesc(NOUT, p.fmt16);
-        uint32_t acc = 0;
-        for (int i = 0; i < p.n_mma; ++i) {
-            const TcMma e = p.mma[i];
-            const uint32_t lbo = e.a_rowk ? 16u : PL;
+    if (warp >= 5) {
+        // ================= producers =================
+        const int ptid = tid - 160;
+        const int CIN = cin8 * 8;
+        const uint16_t *xg = p.x + (int64_t)g * p.x_gs;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            const int64_t m0 = tile * 128;
+            const uint32_t sbase = sA_u + (uint32_t)stage * a_bytes;
+            for (int r = ptid; r < n_rows; r += TC_PRODUCERS) {
+                const int64_t v = m0 + p.row0 + r;
+                bool valid = v >= 0;
+                int64_t seq = 0;
+                int u = 0;
+                if (valid) {
+                    seq = v / p.Tp;
+                    u = (int)(v - seq * p.Tp);
+                    valid = (seq < p.NS) && (u < p.T_eff);
+                }
+                const int srow = (p.ups == 2) ? (u >> 1) : u;
+                const uint16_t *src = valid ? (xg + (seq * p.T_in + srow) * CIN) : xg;
+                const uint32_t nb = valid ? 16u : 0u;
 #pragma unroll
-            for (int t = 0; t < (SPLIT == 2 ? 3 : 1); ++t) {
-                const int sa = (t == 2) ? 1 : 0;  // hi*hi, hi*lo, lo*hi
-                const int sb = (t == 1) ? 1 : 0;
-                const uint32_t a_addr = sA_u + (uint32_t)((sa * cin8 + e.a_plane) * n_rows + e.a_row) * 16u;
-                const uint32_t b_addr = sB_u + (uint32_t)((e.b_block * SPLIT + sb) * 2 * NOUT) * 16u;
-                umma_f16(tmem_base, umma_desc(a_addr, lbo, 128u), umma_desc(b_addr, (uint32_t)NOUT * 16u, 128u), idesc, acc);
-                acc = 1;
+                for (int s = 0; s < SPLIT; ++s) {
+                    const uint16_t *ss = valid ? (src + (int64_t)s * p.x_split) : xg;
+                    for (int c = 0; c < cin8; ++c)
+                        cp_async16(sbase + (uint32_t)((s * cin8 + c) * n_rows + r) * 16u, ss + c * 8, nb);
+                }
+            }
+            cp_async_mbar_arrive_noinc(&full_bar[stage]);
+            if (++stage == nstage) {
+                stage = 0;
+                phase ^= 1u;
             }
         }
-        umma_commit(&mbar);
-    }
-    mbar_wait(&mbar, 0);
-    tc_fence_after();
-
-    // ---- epilogue: thread = accumulator row (TMEM lane), NOUT fp32 columns
-    const int64_t v = m0 + tid;
-    const int64_t seq = v / p.Tp;
-    const int srow = (int)(v - seq * p.Tp);
-    const bool row_ok = (seq < p.NS) && (srow < p.T_valid);
-    const float *bias = p.bias + (int64_t)g * p.b_gs;
-    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+        cp_async_wait_all();
+    } else if (warp == 4) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc(NOUT, p.fmt16);
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                mbar_wait(&acce_bar[acc], acc_phase ^ 1u);
+                mbar_wait(&full_bar[stage], phase);
+                fence_proxy_async();
+                tc_fence_after();
+                const uint32_t sbase = sA_u + (uint32_t)stage * a_bytes;
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * NCOLS);
+                uint32_t accum = 0;
+                for (int i = 0; i < p.n_mma; ++i) {
+                    const TcMma e = p.mma[i];
+                    const uint32_t lbo = e.a_rowk ? 16u : PL;
+#pragma unroll
+                    for (int t = 0; t < (SPLIT == 2 ? 3 : 1); ++t) {
+                        const int sa = (t == 2) ? 1 : 0;  // hi*hi, hi*lo, lo*hi
+                        const int sb = (t == 1) ? 1 : 0;
+                        const uint32_t a_addr = sbase + (uint32_t)((sa * cin8 + e.a_plane) * n_rows + e.a_row) * 16u;
+                        const uint32_t b_addr = sB_u + (uint32_t)((e.b_block * SPLIT + sb) * 2 * NOUT) * 16u;
+                        umma_f16(d_tmem, umma_desc(a_addr, lbo, 128u), umma_desc(b_addr, (uint32_t)NOUT * 16u, 128u), idesc, accum);
+                        accum = 1;
+                    }
+                }
+                umma_commit(&empty_bar[stage]);
+                umma_commit(&accf_bar[acc]);
+                if (++stage == nstage) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1u;
+            }
+        }
+    } else {
+        // ================= epilogue =================
+        const float *bias = p.bias + (int64_t)g * p.b_gs;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            mbar_wait(&accf_bar[acc], acc_phase);
+            tc_fence_after();
+            const int64_t v = tile * 128 + tid;
+            const int64_t seq = v / p.Tp;
+            const int srow = (int)(v - seq * p.Tp);
+            const bool row_ok = (seq < p.NS) && (srow < p.T_valid);
+            const uint32_t trow = tmem_base + (uint32_t)(acc * NCOLS) + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
-    for (int n0 = 0; n0 < NOUT; n0 += 8) {
-        float a[8];
-        tmem_ld8(trow + (uint32_t)n0, a);
-        const int phi = n0 / p.coutp;
-        const int c0 = n0 - phi * p.coutp;
-        if (phi >= p.ph || c0 >= p.cout) continue;  // padding columns (warp-uniform)
+            for (int n0 = 0; n0 < NOUT; n0 += 8) {
+                const int phi = n0 / p.coutp;
+                const int c0 = n0 - phi * p.coutp;
+                if (phi >= p.ph || c0 >= p.cout) continue;  // padding columns (warp-uniform)
+                float a[8];
+                tmem_ld8(trow + (uint32_t)n0, a);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            float t = a[i] + __ldg(bias + n0 + i);
-            if (p.act == ACT_RELU) t = fmaxf(t, 0.f);
-            if (p.act == ACT_SIGMOID) t = 1.f / (1.f + expf(-t));
-            a[i] = t;
-        }
-        int t_out = p.ph * srow + phi;
-        bool st = row_ok;
-        if (p.pool == 2) {
+                for (int i = 0; i < 8; ++i) {
+                    float t = a[i] + __ldg(bias + n0 + i);
+                    if (p.act == ACT_RELU) t = fmaxf(t, 0.f);
+                    if (p.act == ACT_SIGMOID) t = 1.f / (1.f + expf(-t));
+                    a[i] = t;
+                }
+                int t_out = p.ph * srow + phi;
+                bool st = row_ok;
+                if (p.pool == 2) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float mine = row_ok ? a[i] : -1e10f;  // SeisBench pads odd lengths with -1e10 before MaxPool1d(2)
-                a[i] = fmaxf(mine, __shfl_xor_sync(0xffffffffu, mine, 1));
+                    for (int i = 0; i < 8; ++i) {
+                        const float mine = row_ok ? a[i] : -1e10f;  // SeisBench pads odd lengths with -1e10 before MaxPool1d(2)
+                        a[i] = fmaxf(mine, __shfl_xor_sync(0xffffffffu, mine, 1));
+                    }
+                    st = row_ok && !(tid & 1);
+                    t_out = srow >> 1;
+                }
+                if (!st || t_out >= p.T_out) continue;
+                if (p.out_fmt == 0) {
+                    uint16_t hi[8], lo[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) split16(a[i], p.fmt16, SPLIT, hi[i], lo[i]);
+                    uint16_t *yb = reinterpret_cast<uint16_t *>(p.y) + (int64_t)g * p.y_gs + (seq * p.T_out + t_out) * p.cout_cl + c0;
+                    uint4 ph4, pl4;
+                    ph4.x = hi[0] | ((uint32_t)hi[1] << 16);
+                    ph4.y = hi[2] | ((uint32_t)hi[3] << 16);
+                    ph4.z = hi[4] | ((uint32_t)hi[5] << 16);
+                    ph4.w = hi[6] | ((uint32_t)hi[7] << 16);
+                    *reinterpret_cast<uint4 *>(yb) = ph4;
+                    if (SPLIT == 2) {
+                        pl4.x = lo[0] | ((uint32_t)lo[1] << 16);
+                        pl4.y = lo[2] | ((uint32_t)lo[3] << 16);
+                        pl4.z = lo[4] | ((uint32_t)lo[5] << 16);
+                        pl4.w = lo[6] | ((uint32_t)lo[7] << 16);
+                        *reinterpret_cast<uint4 *>(yb + p.y_split) = pl4;
+                    }
+                } else {
+                    float *yb = reinterpret_cast<float *>(p.y) + (int64_t)g * p.y_gs + seq * p.y_ss + t_out;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if (c0 + i < p.cout) yb[(int64_t)(c0 + i) * p.y_cs] = a[i];
+                }
             }
-            st = row_ok && !(tid & 1);
-            t_out = srow >> 1;
-        }
-        if (!st || t_out >= p.T_out) continue;
-        if (p.out_fmt == 0) {
-            uint16_t hi[8], lo[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) split16(a[i], p.fmt16, SPLIT, hi[i], lo[i]);
-            uint16_t *yb = reinterpret_cast<uint16_t *>(p.y) + (int64_t)g * p.y_gs + (seq * p.T_out + t_out) * p.cout_cl + c0;
-            uint4 ph4, pl4;
-            ph4.x = hi[0] | ((uint32_t)hi[1] << 16);
-            ph4.y = hi[2] | ((uint32_t)hi[3] << 16);
-            ph4.z = hi[4] | ((uint32_t)hi[5] << 16);
-            ph4.w = hi[6] | ((uint32_t)hi[7] << 16);
-            *reinterpret_cast<uint4 *>(yb) = ph4;
-            if (SPLIT == 2) {
-                pl4.x = lo[0] | ((uint32_t)lo[1] << 16);
-                pl4.y = lo[2] | ((uint32_t)lo[3] << 16);
-                pl4.z = lo[4] | ((uint32_t)lo[5] << 16);
-                pl4.w = lo[6] | ((uint32_t)lo[7] << 16);
-                *reinterpret_cast<uint4 *>(yb + p.y_split) = pl4;
-            }
-        } else {
-            float *yb = reinterpret_cast<float *>(p.y) + (int64_t)g * p.y_gs + seq * p.y_ss + t_out;
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                if (c0 + i < p.cout) yb[(int64_t)(c0 + i) * p.y_cs] = a[i];
+            tc_fence_before();
+            mbar_arrive(&acce_bar[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1u;
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base, NCOLS);
+    if (warp == 4) tmem_dealloc(tmem_base, 2 * NCOLS);
 }
 
 // ------------------------------------------------------------------------------------------ pack kernel
@@ -417,7 +484,7 @@ static int launch_tc(const TcP &p, dim3 grid, size_t smem, cudaStream_t s) {
         VP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = smem;
     }
-    kern<<<grid, 128, smem, s>>>(p);
+    kern<<<grid, TC_THREADS, smem, s>>>(p);
     VP_LAUNCH_CHECK();
     return VP_OK;
 }
@@ -463,10 +530,24 @@ int tc_launch(const TcLayer &L, const TcIO &io, cudaStream_t s) {
     p.cout_cl = io.cout_cl;
     VP_REQUIRE(!(io.pool == 2 && L.ph == 2), VP_ERR_UNSUPPORTED, "tc conv: pooling with polyphase output is not supported");
     const int64_t rows = (int64_t)io.NS * Tp;
-    dim3 grid((unsigned)((rows + 127) / 128), L.groups);
+    const int64_t n_tiles = (rows + 127) / 128;
     const size_t a_bytes = ((size_t)L.split * p.cin8 * p.n_rows * 16 + 127) & ~(size_t)127;
-    const size_t smem = a_bytes + (size_t)L.n_blocks * L.split * 2 * L.nout * 16;
-    VP_REQUIRE(smem <= 227 * 1024, VP_ERR_UNSUPPORTED, "tc conv: %zu bytes of shared memory exceed 227 KB", smem);
+    const size_t w_bytes = ((size_t)L.n_blocks * L.split * 2 * L.nout * 16 + 127) & ~(size_t)127;
+    // ring depth / residency: two CTAs per SM when a >= 2-stage ring fits in half the shared memory
+    const size_t kHalf = 110 * 1024, kFull = 224 * 1024;
+    int occ = 1, stages = 0;
+    if (w_bytes + 2 * a_bytes <= kHalf) {
+        occ = 2;
+        stages = (int)std::min<size_t>(TC_MAX_STAGES, (kHalf - w_bytes) / a_bytes);
+    } else {
+        VP_REQUIRE(w_bytes + a_bytes <= kFull, VP_ERR_UNSUPPORTED, "tc conv: %zu bytes of shared memory exceed the SM", w_bytes + a_bytes);
+        stages = (int)std::min<size_t>(TC_MAX_STAGES, (kFull - w_bytes) / a_bytes);
+    }
+    p.n_stages = stages;
+    const size_t smem = w_bytes + (size_t)stages * a_bytes;
+    int64_t ctas = (148 * occ + L.groups - 1) / L.groups;
+    ctas = std::max<int64_t>(1, std::min<int64_t>(ctas, n_tiles));
+    dim3 grid((unsigned)ctas, L.groups);
 #define VP_TC_CASE(N, S) \
     if (L.nout == N && L.split == S) return launch_tc<N, S>(p, grid, smem, s)
     VP_TC_CASE(16, 2);

@@ -20,7 +20,7 @@ struct TcMma {
 struct TcP {
     const uint16_t *x;  // channel-last 16-bit activations [SPLIT][G][NS][T_in][CIN]
     int64_t x_split, x_gs;
-    int T_in, T_eff, ups, Tp, NS, row0, n_rows, cin8;
+    int T_in, T_eff, ups, Tp, NS, row0, n_rows, cin8, n_stages;
     const uint16_t *w;  // [G][n_blocks][SPLIT][2][NOUT][8]
     int64_t w_gs;
     int n_blocks;
