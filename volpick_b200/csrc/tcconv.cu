@@ -19,10 +19,8 @@
 // step issues hi*hi + hi*lo + lo*hi into the fp32 TMEM accumulator -> fp32-equivalent results on the
 // tensor cores ("f16x3" mode).  split = 1: one bf16 pass.
 //
-// CTA = 128 threads: all threads stage A and W with cp.async (zero-fill outside the sequences), one
-// thread issues the tcgen05.mma chain and commits to an mbarrier, then the four warps read their TMEM
-// lane quarter (tcgen05.ld 32x32b) and run the fused epilogue (bias, ReLU/sigmoid, pool, fp16 split,
-// channel-last or fp32 store).  Several CTAs are resident per SM, which overlaps load / MMA / epilogue.
+// Execution: persistent warp-specialised CTAs (producers -> cp.async ring -> one tcgen05 issuer -> TMEM
+// double buffer -> four epilogue warps), see tcconv_kernel below.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -127,6 +125,17 @@ constexpr int TC_THREADS = 256;
 constexpr int TC_PRODUCERS = 96;
 constexpr int TC_MAX_STAGES = 4;
 
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "elect.sync _|P1, 0xFFFFFFFF;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -215,40 +224,36 @@ __global__ void __launch_bounds__(TC_THREADS) tcconv_kernel(const __grid_constan
         cp_async_wait_all();
     } else if (warp == 4) {
         // ================= MMA issuer =================
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc(NOUT, p.fmt16);
-            int stage = 0, acc = 0;
-            uint32_t phase = 0, acc_phase = 0;
-            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                mbar_wait(&acce_bar[acc], acc_phase ^ 1u);
-                mbar_wait(&full_bar[stage], phase);
-                fence_proxy_async();
-                tc_fence_after();
-                const uint32_t sbase = sA_u + (uint32_t)stage * a_bytes;
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * NCOLS);
-                uint32_t accum = 0;
-                for (int i = 0; i < p.n_mma; ++i) {
-                    const TcMma e = p.mma[i];
-                    const uint32_t lbo = e.a_rowk ? 16u : PL;
-#pragma unroll
-                    for (int t = 0; t < (SPLIT == 2 ? 3 : 1); ++t) {
-                        const int sa = (t == 2) ? 1 : 0;  // hi*hi, hi*lo, lo*hi
-                        const int sb = (t == 1) ? 1 : 0;
-                        const uint32_t a_addr = sbase + (uint32_t)((sa * cin8 + e.a_plane) * n_rows + e.a_row) * 16u;
-                        const uint32_t b_addr = sB_u + (uint32_t)((e.b_block * SPLIT + sb) * 2 * NOUT) * 16u;
-                        umma_f16(d_tmem, umma_desc(a_addr, lbo, 128u), umma_desc(b_addr, (uint32_t)NOUT * 16u, 128u), idesc, accum);
-                        accum = 1;
-                    }
-                }
+        // The whole warp runs the loop (uniform control flow keeps the descriptors in uniform registers);
+        // one elected lane issues.  Per MMA only two adds remain: the schedule was precomputed on the host.
+        const uint32_t idesc = umma_idesc(NOUT, p.fmt16);
+        const uint32_t sB16 = sB_u >> 4;
+        const uint64_t desc_hi = (uint64_t)(0x4000u | (128u >> 4)) << 32;  // version 1 (Blackwell), SBO = 128 B
+        int stage = 0, acc = 0;
+        uint32_t phase = 0, acc_phase = 0;
+        const int n_terms = p.n_terms;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            mbar_wait(&acce_bar[acc], acc_phase ^ 1u);
+            mbar_wait(&full_bar[stage], phase);
+            fence_proxy_async();
+            tc_fence_after();
+            const uint32_t sA16 = (sA_u + (uint32_t)stage * a_bytes) >> 4;
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * NCOLS);
+            if (elect_one()) {
+                umma_f16(d_tmem, desc_hi | (uint64_t)(sA16 + p.term_a[0]), desc_hi | (uint64_t)(sB16 + p.term_b[0]), idesc, 0u);
+#pragma unroll 4
+                for (int i = 1; i < n_terms; ++i)
+                    umma_f16(d_tmem, desc_hi | (uint64_t)(sA16 + p.term_a[i]), desc_hi | (uint64_t)(sB16 + p.term_b[i]), idesc, 1u);
                 umma_commit(&empty_bar[stage]);
                 umma_commit(&accf_bar[acc]);
-                if (++stage == nstage) {
-                    stage = 0;
-                    phase ^= 1u;
-                }
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1u;
             }
+            __syncwarp();
+            if (++stage == nstage) {
+                stage = 0;
+                phase ^= 1u;
+            }
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1u;
         }
     } else {
         // ================= epilogue =================
@@ -511,8 +516,22 @@ int tc_launch(const TcLayer &L, const TcIO &io, cudaStream_t s) {
     p.n_blocks = L.n_blocks;
     p.bias = io.b_dev;
     p.b_gs = L.nout;
-    p.n_mma = (int)L.mma.size();
-    for (int i = 0; i < p.n_mma; ++i) p.mma[i] = L.mma[i];
+    {
+        const uint32_t PL16 = (uint32_t)p.n_rows;  // plane pitch in 16-byte units
+        const int nterm = (L.split == 2) ? 3 : 1;
+        p.n_terms = 0;
+        for (const TcMma &e : L.mma)
+            for (int t = 0; t < nterm; ++t) {
+                const int sa = (t == 2) ? 1 : 0;  // hi*hi, hi*lo, lo*hi
+                const int sb = (t == 1) ? 1 : 0;
+                const uint32_t a_off = (uint32_t)((sa * p.cin8 + e.a_plane) * p.n_rows + e.a_row);
+                const uint32_t lbo16 = e.a_rowk ? 1u : PL16;
+                const uint32_t b_off = (uint32_t)((e.b_block * L.split + sb) * 2 * L.nout);
+                p.term_a[p.n_terms] = a_off | (lbo16 << 16);
+                p.term_b[p.n_terms] = b_off | ((uint32_t)L.nout << 16);
+                ++p.n_terms;
+            }
+    }
     p.fmt16 = (L.split == 2) ? 0 : 1;
     p.act = io.act;
     p.pool = io.pool;
@@ -534,14 +553,17 @@ int tc_launch(const TcLayer &L, const TcIO &io, cudaStream_t s) {
     const size_t a_bytes = ((size_t)L.split * p.cin8 * p.n_rows * 16 + 127) & ~(size_t)127;
     const size_t w_bytes = ((size_t)L.n_blocks * L.split * 2 * L.nout * 16 + 127) & ~(size_t)127;
     // ring depth / residency: two CTAs per SM when a >= 2-stage ring fits in half the shared memory
-    const size_t kHalf = 110 * 1024, kFull = 224 * 1024;
+    // ring depth / residency: several CTAs per SM (one MMA issuer each) when >= 2 stages fit in the share
+    const size_t kFull = 224 * 1024;
+    const int ncols2 = 2 * (L.nout < 32 ? 32 : L.nout);
     int occ = 1, stages = 0;
-    if (w_bytes + 2 * a_bytes <= kHalf) {
-        occ = 2;
-        stages = (int)std::min<size_t>(TC_MAX_STAGES, (kHalf - w_bytes) / a_bytes);
-    } else {
-        VP_REQUIRE(w_bytes + a_bytes <= kFull, VP_ERR_UNSUPPORTED, "tc conv: %zu bytes of shared memory exceed the SM", w_bytes + a_bytes);
-        stages = (int)std::min<size_t>(TC_MAX_STAGES, (kFull - w_bytes) / a_bytes);
+    for (int o = 4; o >= 1; --o) {
+        const size_t share = kFull / o - 1024;  // 1 KB per CTA reserved by the driver
+        if (o > 1 && (o * ncols2 > 512 || w_bytes + 2 * a_bytes > share)) continue;
+        VP_REQUIRE(w_bytes + a_bytes <= share, VP_ERR_UNSUPPORTED, "tc conv: %zu bytes of shared memory exceed the SM", w_bytes + a_bytes);
+        occ = o;
+        stages = (int)std::min<size_t>(TC_MAX_STAGES, (share - w_bytes) / a_bytes);
+        break;
     }
     p.n_stages = stages;
     const size_t smem = w_bytes + (size_t)stages * a_bytes;

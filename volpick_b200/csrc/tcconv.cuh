@@ -8,6 +8,7 @@
 namespace vp {
 
 constexpr int TC_MAX_MMA = 48;
+constexpr int TC_MAX_TERMS = 3 * TC_MAX_MMA;
 
 struct TcMma {
     int a_row;    // first staged row of the A operand for this MMA (tap offset)
@@ -26,8 +27,10 @@ struct TcP {
     int n_blocks;
     const float *bias;  // [G][NOUT]
     int64_t b_gs;
-    int n_mma;
-    TcMma mma[TC_MAX_MMA];
+    // MMA schedule of one tile, one entry per tcgen05.mma: low words of the A / B shared-memory
+    // descriptors relative to the stage base / weight base (16-byte units | LBO << 16)
+    int n_terms;
+    uint32_t term_a[TC_MAX_TERMS], term_b[TC_MAX_TERMS];
     int fmt16;  // 0: fp16, 1: bf16
     int act, pool, ph, cout, coutp, T_valid, T_out;
     int out_fmt;  // 0: channel-last 16-bit [SPLIT][G][NS][T_out][cout_cl]; 1: fp32 (seq stride y_ss, channel stride y_cs)
