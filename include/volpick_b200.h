@@ -122,6 +122,10 @@ VP_API const char *vp_forward_tap_names(const vp_model *m); /* comma separated *
 VP_API int vp_tcconv_debug(const float *x, int NS, int CIN, int T_in, const float *w_host, const float *bias_host, int COUT,
                            int K, int mode, int crop, int act, int pool, int precision, float *y, void *stream);
 
+/* Profiling aid: device time (ms per launch) of one tcgen05 conv layer on synthetic data. */
+VP_API int vp_tcconv_bench(int NS, int CIN, int T_in, int COUT, int K, int mode, int crop, int pool, int precision,
+                           int out_fmt, int iters, float *ms_out);
+
 /* annotate_batch_post (blinding) + _reassemble_blocks_array: y (n_windows,3,L) -> out (3,pred_len). */
 VP_API int vp_stack(const float *y, const int64_t *starts, int64_t n_windows, int64_t in_samples, int n_labels,
              int64_t overlap, int64_t blind0, int64_t blind1, int mode, float *out, int64_t pred_len, void *stream);

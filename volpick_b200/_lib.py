@@ -62,6 +62,7 @@ SIGNATURES = {
     "vp_forward_tap": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _i32, C.c_char_p, _vp, _i64, C.POINTER(_i64), _vp]),
     "vp_forward_tap_names": (C.c_char_p, [_vp]),
     "vp_tcconv_debug": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "vp_tcconv_bench": (_i32, [_i32] * 11 + [C.POINTER(C.c_float)]),
     "vp_stack": (_i32, [_vp, _vp, _i64, _i64, _i32, _i64, _i64, _i64, _i32, _vp, _i64, _vp]),
     "vp_nan_bounds": (_i32, [_vp, _i32, _i64, _vp, _vp]),
     "vp_pick_scratch_bytes": (_i64, [_i64]),

@@ -26,6 +26,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "tcconv.cuh"
@@ -195,7 +196,7 @@ __global__ void __launch_bounds__(TC_THREADS) tcconv_kernel(const __grid_constan
             mbar_wait(&empty_bar[stage], phase ^ 1u);
             const int64_t m0 = tile * 128;
             const uint32_t sbase = sA_u + (uint32_t)stage * a_bytes;
-            for (int r = ptid; r < n_rows; r += TC_PRODUCERS) {
+            for (int r = ptid; r < n_rows && !(p.dbg & 1); r += TC_PRODUCERS) {
                 const int64_t v = m0 + p.row0 + r;
                 bool valid = v >= 0;
                 int64_t seq = 0;
@@ -242,7 +243,7 @@ __global__ void __launch_bounds__(TC_THREADS) tcconv_kernel(const __grid_constan
             if (elect_one()) {
                 umma_f16(d_tmem, desc_hi | (uint64_t)(sA16 + p.term_a[0]), desc_hi | (uint64_t)(sB16 + p.term_b[0]), idesc, 0u);
 #pragma unroll 4
-                for (int i = 1; i < n_terms; ++i)
+                for (int i = 1; i < ((p.dbg & 2) ? 1 : n_terms); ++i)
                     umma_f16(d_tmem, desc_hi | (uint64_t)(sA16 + p.term_a[i]), desc_hi | (uint64_t)(sB16 + p.term_b[i]), idesc, 1u);
                 umma_commit(&empty_bar[stage]);
                 umma_commit(&accf_bar[acc]);
@@ -269,7 +270,7 @@ __global__ void __launch_bounds__(TC_THREADS) tcconv_kernel(const __grid_constan
             const bool row_ok = (seq < p.NS) && (srow < p.T_valid);
             const uint32_t trow = tmem_base + (uint32_t)(acc * NCOLS) + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
-            for (int n0 = 0; n0 < NOUT; n0 += 8) {
+            for (int n0 = 0; n0 < ((p.dbg & 4) ? 0 : NOUT); n0 += 8) {
                 const int phi = n0 / p.coutp;
                 const int c0 = n0 - phi * p.coutp;
                 if (phi >= p.ph || c0 >= p.cout) continue;  // padding columns (warp-uniform)
@@ -533,6 +534,10 @@ int tc_launch(const TcLayer &L, const TcIO &io, cudaStream_t s) {
             }
     }
     p.fmt16 = (L.split == 2) ? 0 : 1;
+    {
+        const char *e = getenv("VP_TC_DBG");
+        p.dbg = e ? atoi(e) : 0;
+    }
     p.act = io.act;
     p.pool = io.pool;
     p.ph = L.ph;
@@ -650,6 +655,72 @@ extern "C" VP_API int vp_tcconv_debug(const float *x, int NS, int CIN, int T_in,
     cudaFree(d_b);
     if (rc == VP_OK && e != cudaSuccess) {
         set_error("vp_tcconv_debug: %s", cudaGetErrorString(e));
+        return VP_ERR_CUDA;
+    }
+    return rc;
+}
+
+
+// Micro-benchmark of one tensor-core layer on synthetic data (device time per launch, CUDA events).
+extern "C" VP_API int vp_tcconv_bench(int NS, int CIN, int T_in, int COUT, int K, int mode, int crop, int pool, int precision,
+                                      int out_fmt, int iters, float *ms_out) {
+    VP_REQUIRE(ms_out && iters > 0, VP_ERR_ARG, "vp_tcconv_bench: bad argument");
+    const int split = precision == VP_PREC_F16X3 ? 2 : 1;
+    const int c8 = (CIN + 7) / 8, cin_p = c8 * 8;
+    std::vector<float> w((size_t)COUT * cin_p * K), b(COUT, 0.1f);
+    for (size_t i = 0; i < w.size(); ++i) w[i] = 0.01f * (float)((int)(i * 2654435761u % 200) - 100) / 100.f;
+    TcLayer L;
+    const float *wl[1] = {w.data()}, *bl[1] = {b.data()};
+    int rc = tc_build_layer(L, mode, cin_p, COUT, K, crop, split, 1, wl, bl);
+    if (rc != VP_OK) return rc;
+    const int T_out = tc_out_len(L, T_in, pool);
+    const int cout_cl = (COUT + 7) / 8 * 8;
+    uint16_t *d_x = nullptr, *d_w = nullptr, *d_y = nullptr;
+    float *d_b = nullptr;
+    const int64_t xs = (int64_t)NS * T_in * cin_p, ys = (int64_t)NS * T_out * cout_cl;
+    VP_CUDA_CHECK(cudaMalloc(&d_x, (size_t)split * xs * 2 + 64));
+    VP_CUDA_CHECK(cudaMalloc(&d_y, (size_t)std::max<int64_t>(split * ys * 2, ys * 4) + 64));
+    VP_CUDA_CHECK(cudaMalloc(&d_w, L.blocks.size() * 2));
+    VP_CUDA_CHECK(cudaMalloc(&d_b, L.bias.size() * 4));
+    VP_CUDA_CHECK(cudaMemset(d_x, 0, (size_t)split * xs * 2));
+    VP_CUDA_CHECK(cudaMemcpy(d_w, L.blocks.data(), L.blocks.size() * 2, cudaMemcpyHostToDevice));
+    VP_CUDA_CHECK(cudaMemcpy(d_b, L.bias.data(), L.bias.size() * 4, cudaMemcpyHostToDevice));
+    TcIO io;
+    io.x = d_x;
+    io.x_split = xs;
+    io.x_gs = 0;
+    io.T_in = T_in;
+    io.NS = NS;
+    io.w_dev = d_w;
+    io.b_dev = d_b;
+    io.act = ACT_RELU;
+    io.pool = pool;
+    io.out_fmt = out_fmt;
+    io.y = d_y;
+    io.y_split = ys;
+    io.y_gs = 0;
+    io.y_ss = (int64_t)COUT * T_out;
+    io.y_cs = T_out;
+    io.cout_cl = cout_cl;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    for (int i = 0; i < 2 && rc == VP_OK; ++i) rc = tc_launch(L, io, 0);
+    cudaEventRecord(e0, 0);
+    for (int i = 0; i < iters && rc == VP_OK; ++i) rc = tc_launch(L, io, 0);
+    cudaEventRecord(e1, 0);
+    cudaError_t e = cudaDeviceSynchronize();
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    *ms_out = ms / iters;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_x);
+    cudaFree(d_y);
+    cudaFree(d_w);
+    cudaFree(d_b);
+    if (rc == VP_OK && e != cudaSuccess) {
+        set_error("vp_tcconv_bench: %s", cudaGetErrorString(e));
         return VP_ERR_CUDA;
     }
     return rc;

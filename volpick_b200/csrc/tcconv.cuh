@@ -32,6 +32,7 @@ struct TcP {
     int n_terms;
     uint32_t term_a[TC_MAX_TERMS], term_b[TC_MAX_TERMS];
     int fmt16;  // 0: fp16, 1: bf16
+    int dbg;    // profiling aid (env VP_TC_DBG): 1 skip A loads, 2 skip MMAs, 4 skip epilogue body
     int act, pool, ph, cout, coutp, T_valid, T_out;
     int out_fmt;  // 0: channel-last 16-bit [SPLIT][G][NS][T_out][cout_cl]; 1: fp32 (seq stride y_ss, channel stride y_cs)
     void *y;
