@@ -385,7 +385,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="eqtransformer", choices=["eqtransformer", "phasenet"])
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "f16x3", "bf16"])
+    ap.add_argument("--precision", default="f16x3", choices=["fp32", "f16x3", "bf16"],
+                    help="f16x3 (default): tcgen05 on fp16 hi/lo split operands, fp32 accumulate -- the exact mode (<= 1e-4 vs the oracle); "
+                         "fp32: CUDA-core FFMA; bf16: single-pass tensor cores (reported separately, looser tolerance)")
     ap.add_argument("--samples", type=int, default=N_DAY, help="samples per record (default: one station-day)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=0,

@@ -8,5 +8,5 @@ echo "pytest exit: $?" >> gpurun_out/pytest_gpu.log
 tail -40 gpurun_out/pytest_gpu.log
 timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke exit: $?" >> gpurun_out/smoke.log
 tail -5 gpurun_out/smoke.log
-timeout 600 python bench.py --steps ${BENCH_STEPS:-3} --warmup ${BENCH_WARMUP:-3} > gpurun_out/bench.log 2>&1; echo "bench exit: $?" >> gpurun_out/bench.log
+timeout 600 python bench.py --precision ${BENCH_PREC:-f16x3} --steps ${BENCH_STEPS:-3} --warmup ${BENCH_WARMUP:-3} > gpurun_out/bench.log 2>&1; echo "bench exit: $?" >> gpurun_out/bench.log
 tail -5 gpurun_out/bench.log
