@@ -12,12 +12,16 @@
 // Tiles overlap by the receptive-field halo (5-6 rows per level), recomputed per tile; rows outside the
 // sequence are written as zeros (they are the convs' zero padding).  Every layer is the polyphase implicit
 // GEMM of tcconv.cu: a tap is a row offset of the SAME shared-memory activation buffer (no-swizzle K-major
-// UMMA descriptors), accumulators in TMEM, f16x3 (fp16 hi/lo split, fp32-equivalent) or bf16 operands.
+// UMMA descriptors), accumulators in TMEM, f16x3 (fp16 hi/lo split, fp32-equivalent) or bf16 operands.  The
+// bias enters through one extra MMA per tile (a constant [1,1,1,0..] A tile times the bias split in three
+// 16-bit terms), so the epilogue is ReLU + 16-bit split + store only.
 //
-// Roles (320 threads): warp 0 cp.async loader of the next item's input rows (double buffered); warp 1 the
-// tcgen05 issuer walking a host-built step list (layer, tile) with per-step producer dependencies; warps 2-9
-// two epilogue groups (TMEM -> bias/ReLU -> fp16 hi/lo planes of the next layer's A operand), alternating
-// steps over FZ_NBUF TMEM accumulators; all eight epilogue warps then run the head.
+// A CTA runs FZ_NPIPE independent pipelines over alternating work items (the layer chain of one item is a
+// dependency chain: while one pipeline's epilogue converts a tile, the other pipeline's MMAs own the tensor
+// pipe).  Per pipeline: one cp.async loader warp (next item's input rows, double buffered), one tcgen05
+// issuer warp walking a host-built step list (layer, tile) with per-step producer dependencies, four epilogue
+// warps (TMEM -> ReLU -> fp16 hi/lo planes of the next layer's A operand) that also run the head.  The
+// decoder's weights are resident in shared memory and shared by the pipelines.
 #include <algorithm>
 #include <cstring>
 
@@ -28,18 +32,19 @@ namespace vp {
 
 // ------------------------------------------------------------------------------------------ epilogues
 template <int SPLIT>
-__device__ __forceinline__ void fz_pack8(const float (&f)[8], uint4 &hi, uint4 &lo) {
+__device__ __forceinline__ void fz_pack8_relu(const uint32_t *v, uint4 &hi, uint4 &lo) {
     uint32_t h[4], l[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
+        const float a = fmaxf(__uint_as_float(v[2 * i]), 0.f), b = fmaxf(__uint_as_float(v[2 * i + 1]), 0.f);
         if (SPLIT == 2) {
-            const __half2 hh = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+            const __half2 hh = __floats2half2_rn(a, b);
             const float2 hf = __half22float2(hh);
-            const __half2 ll = __floats2half2_rn(f[2 * i] - hf.x, f[2 * i + 1] - hf.y);
+            const __half2 ll = __floats2half2_rn(a - hf.x, b - hf.y);
             h[i] = *reinterpret_cast<const uint32_t *>(&hh);
             l[i] = *reinterpret_cast<const uint32_t *>(&ll);
         } else {
-            const __nv_bfloat162 bb = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+            const __nv_bfloat162 bb = __floats2bfloat162_rn(a, b);
             h[i] = *reinterpret_cast<const uint32_t *>(&bb);
             l[i] = 0u;
         }
@@ -50,12 +55,12 @@ __device__ __forceinline__ void fz_pack8(const float (&f)[8], uint4 &hi, uint4 &
 
 // Polyphase layer -> 16-bit planes of the next layer.  Thread = one input row s; it owns output rows 2s, 2s+1.
 template <int COUTP, int SPLIT>
-__device__ __forceinline__ void fz_epi16(const FzLayer &L, uint32_t tacc, int t, int r, int j, const float *bias,
-                                         uint8_t *smem) {
+__device__ __forceinline__ void fz_epi16(const FzLayer &L, uint32_t tacc, int t, int r, int j, uint8_t *arena) {
     constexpr int P = COUTP / 8;
     const int s_rel = L.s_lo + 128 * t + r;
     const int lrow0 = 2 * s_rel - L.out_lo;
     const int grow0 = 2 * (L.c_in * j + s_rel);
+    const uint32_t plane = (uint32_t)L.out_rows * 16u;
 #pragma unroll
     for (int phi = 0; phi < 2; ++phi) {
         const int lrow = lrow0 + phi;
@@ -63,30 +68,26 @@ __device__ __forceinline__ void fz_epi16(const FzLayer &L, uint32_t tacc, int t,
         const bool valid = (unsigned)(grow0 + phi) < (unsigned)L.T_out;
         uint32_t v[COUTP];
 #pragma unroll
-        for (int c0 = 0; c0 < COUTP; c0 += 8) {
-            uint32_t(&v8)[8] = *reinterpret_cast<uint32_t(*)[8]>(&v[c0]);
-            tmem_ld8_nowait(tacc + (uint32_t)(phi * COUTP + c0), v8);
+        for (int c0 = 0; c0 < COUTP; c0 += 16) {
+            uint32_t(&v16)[16] = *reinterpret_cast<uint32_t(*)[16]>(&v[c0]);
+            tmem_ld16_nowait(tacc + (uint32_t)(phi * COUTP + c0), v16);
         }
         tmem_ld_wait();
         if (inb) {
-            uint8_t *dst = smem + L.out_off + (size_t)lrow * 16;
+            uint8_t *dst = arena + L.out_off + (size_t)lrow * 16;
 #pragma unroll
             for (int pl = 0; pl < P; ++pl) {
-                float f[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e)
-                    f[e] = valid ? fmaxf(__uint_as_float(v[pl * 8 + e]) + bias[phi * COUTP + pl * 8 + e], 0.f) : 0.f;
-                uint4 hi, lo;
-                fz_pack8<SPLIT>(f, hi, lo);
-                *reinterpret_cast<uint4 *>(dst + (size_t)pl * L.out_rows * 16) = hi;
-                if (SPLIT == 2) *reinterpret_cast<uint4 *>(dst + (size_t)(P + pl) * L.out_rows * 16) = lo;
+                uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
+                if (valid) fz_pack8_relu<SPLIT>(&v[pl * 8], hi, lo);
+                *reinterpret_cast<uint4 *>(dst + pl * plane) = hi;
+                if (SPLIT == 2) *reinterpret_cast<uint4 *>(dst + (P + pl) * plane) = lo;
             }
         }
     }
 }
 
 // Last polyphase layer (8 channels per phase) -> fp32 planar [c][row] for the CUDA-core head.
-__device__ __forceinline__ void fz_epi32(const FzLayer &L, uint32_t tacc, int t, int r, int j, const float *bias, uint8_t *smem) {
+__device__ __forceinline__ void fz_epi32(const FzLayer &L, uint32_t tacc, int t, int r, int j, uint8_t *arena) {
     const int s_rel = L.s_lo + 128 * t + r;
     const int lrow0 = 2 * s_rel - L.out_lo;  // even
     const int grow0 = 2 * (L.c_in * j + s_rel);
@@ -95,62 +96,63 @@ __device__ __forceinline__ void fz_epi32(const FzLayer &L, uint32_t tacc, int t,
     tmem_ld_wait();
     if ((unsigned)lrow0 < (unsigned)L.out_rows) {  // out_rows is even: both phases are in range together
         const bool valid = (unsigned)grow0 < (unsigned)L.T_out;  // T_out even: both phases valid together
-        float *d = reinterpret_cast<float *>(smem + L.out_off) + lrow0;
+        float *d = reinterpret_cast<float *>(arena + L.out_off) + lrow0;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
             float2 o;
-            o.x = valid ? fmaxf(__uint_as_float(v[c]) + bias[c], 0.f) : 0.f;
-            o.y = valid ? fmaxf(__uint_as_float(v[8 + c]) + bias[8 + c], 0.f) : 0.f;
+            o.x = valid ? fmaxf(__uint_as_float(v[c]), 0.f) : 0.f;
+            o.y = valid ? fmaxf(__uint_as_float(v[8 + c]), 0.f) : 0.f;
             *reinterpret_cast<float2 *>(d + (size_t)c * L.out_rp) = o;
         }
     }
 }
 
-// sigmoid(conv k11, 8 -> 1) on the CUDA cores: thread = 4 consecutive output samples.
-__device__ __forceinline__ void fz_head(const FzDecB &p, int g, int b, int j, int e, const uint8_t *smem) {
-    const float *d6 = reinterpret_cast<const float *>(smem + p.head_in_off);
+// sigmoid(conv k11, 8 -> 1) on the CUDA cores: thread e = OPT consecutive output samples.
+template <int OPT>
+__device__ __forceinline__ void fz_head(const FzDecB &p, int g, int b, int j, int e, const uint8_t *arena) {
+    const int tl0 = OPT * e;
+    if (tl0 >= p.W) return;
+    const float *d6 = reinterpret_cast<const float *>(arena + p.head_in_off) + tl0;
     const int RP = p.head_rp;
-    const float hb = p.head_b[g];
-    for (int task = e; task * 4 < p.W; task += 256) {
-        const int t_out = p.W * j + task * 4;
-        if (t_out >= p.L_out) break;
-        float acc[4] = {hb, hb, hb, hb};
+    float acc[OPT];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const float4 *src = reinterpret_cast<const float4 *>(d6 + (size_t)c * RP + task * 4);
-            float xv[16];
+    for (int o = 0; o < OPT; ++o) acc[o] = p.head_b[g];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float4 v4 = src[q];
-                xv[4 * q + 0] = v4.x;
-                xv[4 * q + 1] = v4.y;
-                xv[4 * q + 2] = v4.z;
-                xv[4 * q + 3] = v4.w;
-            }
+    for (int c = 0; c < 8; ++c) {
+        float xv[OPT + 12];
 #pragma unroll
-            for (int k = 0; k < 11; ++k) {
-                const float w = p.head_w[g][c * 11 + k];
-#pragma unroll
-                for (int o = 0; o < 4; ++o) acc[o] = fmaf(w, xv[o + k + 1], acc[o]);  // head_row0 == 1
-            }
+        for (int q = 0; q < (OPT + 12) / 2; ++q) {
+            const float2 v2 = *reinterpret_cast<const float2 *>(d6 + (size_t)c * RP + 2 * q);
+            xv[2 * q] = v2.x;
+            xv[2 * q + 1] = v2.y;
         }
-        float4 o4;
-        o4.x = 1.f / (1.f + expf(-acc[0]));
-        o4.y = 1.f / (1.f + expf(-acc[1]));
-        o4.z = 1.f / (1.f + expf(-acc[2]));
-        o4.w = 1.f / (1.f + expf(-acc[3]));
-        *reinterpret_cast<float4 *>(p.y + ((size_t)b * 3 + g) * p.L_out + t_out) = o4;
+#pragma unroll
+        for (int k = 0; k < 11; ++k) {
+            const float w = p.head_w[g][c * 11 + k];
+#pragma unroll
+            for (int o = 0; o < OPT; ++o) acc[o] = fmaf(w, xv[o + k + 1], acc[o]);  // buffer row 0 = output - 6
+        }
+    }
+    const int t_out = p.W * j + tl0;
+    float *yb = p.y + ((size_t)b * 3 + g) * p.L_out + t_out;
+#pragma unroll
+    for (int o = 0; o < OPT; o += 2) {
+        if (tl0 + o < p.W && t_out + o < p.L_out) {  // W and L_out are even
+            float2 o2;
+            o2.x = 1.f / (1.f + expf(-acc[o]));
+            o2.y = 1.f / (1.f + expf(-acc[o + 1]));
+            *reinterpret_cast<float2 *>(yb + o) = o2;
+        }
     }
 }
 
 // ------------------------------------------------------------------------------------------ the kernel
-template <int SPLIT>
+template <int SPLIT, int OPT>
 __global__ void __launch_bounds__(FZ_THREADS, 1) decb_kernel(const __grid_constant__ FzDecB p) {
     extern __shared__ __align__(128) uint8_t fz_smem[];
-    __shared__ __align__(8) uint64_t in_full[2], in_empty[2], acc_full[FZ_NBUF], done_bar[FZ_NBUF];
+    __shared__ __align__(8) uint64_t in_full[FZ_NPIPE][2], in_empty[FZ_NPIPE][2], acc_full[FZ_NPIPE][FZ_NBUF],
+        done_bar[FZ_NPIPE][FZ_NBUF];
     __shared__ uint32_t tmem_base_s;
-    __shared__ float bias_s[FZ_MAX_LAYERS * 128];
-    constexpr int NCOLS = 64;  // max MMA N of the chain (decoder.convs.3: 2 x 32)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = blockIdx.y;
@@ -158,22 +160,31 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) decb_kernel(const __grid_consta
     const int n_items = p.B * p.tiles_per_seq;
 
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&in_full[i], 32);
-            mbar_init(&in_empty[i], 1);
-        }
-        for (int i = 0; i < FZ_NBUF; ++i) {
-            mbar_init(&acc_full[i], 1);
-            mbar_init(&done_bar[i], 4);
+        for (int pp = 0; pp < FZ_NPIPE; ++pp) {
+            for (int i = 0; i < 2; ++i) {
+                mbar_init(&in_full[pp][i], 32);
+                mbar_init(&in_empty[pp][i], 1);
+            }
+            for (int i = 0; i < FZ_NBUF; ++i) {
+                mbar_init(&acc_full[pp][i], 1);
+                mbar_init(&done_bar[pp][i], 4);
+            }
         }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(&tmem_base_s, FZ_NBUF * NCOLS);
-    for (int l = 0; l < p.n_layers; ++l) {  // resident weights + biases of this decoder
-        const FzLayer &L = p.L[l];
-        const uint4 *wg = reinterpret_cast<const uint4 *>(p.w + L.w_goff + (long long)g * L.w_gs);
-        for (int idx = tid; idx < L.w_bytes / 16; idx += FZ_THREADS) cp_async16(sbase + L.w_off + idx * 16, wg + idx, 16u);
-        for (int n = tid; n < L.nout; n += FZ_THREADS) bias_s[L.bias_soff + n] = p.bias[L.b_goff + g * L.b_gs + n];
+    if (warp == 0) tmem_alloc(&tmem_base_s, FZ_NPIPE * FZ_NBUF * FZ_NCOLS);
+    {   // resident weights + bias blocks of this decoder, and the constant A tile of the bias MMA
+        const uint4 *wg = reinterpret_cast<const uint4 *>(p.blob + (long long)g * (p.blob_bytes / 2));
+        for (int idx = tid; idx < p.blob_bytes / 16; idx += FZ_THREADS) cp_async16(sbase + p.blob_off + idx * 16, wg + idx, 16u);
+        const uint32_t one = (SPLIT == 2) ? 0x3C00u : 0x3F80u;  // 1.0 in fp16 / bf16
+        for (int idx = tid; idx < 256; idx += FZ_THREADS) {
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (idx < 128) {
+                v.x = one | (one << 16);
+                v.y = one;
+            }
+            *reinterpret_cast<uint4 *>(fz_smem + p.ones_off + idx * 16) = v;
+        }
     }
     cp_async_wait_all();
     fence_proxy_async();
@@ -182,18 +193,19 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) decb_kernel(const __grid_consta
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
 
-    if (warp == 0) {
-        // ================= loader: input rows of the next work item (zero rows outside the sequence) =========
+    if (warp < FZ_NPIPE) {
+        // ================= loaders: input rows of the pipeline's next work item (zero rows outside the sequence)
+        const int pp = warp;
         const int R0 = p.L[0].in_rows, c8 = p.L[0].cin8;
         const int per_split = R0 * c8;
         const uint16_t *xg = p.x + (long long)g * p.x_gs;
         int n = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+        for (int item = blockIdx.x + pp * gridDim.x; item < n_items; item += FZ_NPIPE * gridDim.x, ++n) {
             const int slot = n & 1;
-            mbar_wait(&in_empty[slot], ((n >> 1) & 1) ^ 1);
+            mbar_wait(&in_empty[pp][slot], ((n >> 1) & 1) ^ 1);
             const int b = item / p.tiles_per_seq, j = item - b * p.tiles_per_seq;
             const int row_base = p.c0 * j + p.in_lo0;
-            const uint32_t dst0 = sbase + p.L[0].in_off + slot * p.in_slot_bytes;
+            const uint32_t dst0 = sbase + pp * p.pipe_stride + p.L[0].in_off + slot * p.in_slot_bytes;
             for (int idx = lane; idx < per_split; idx += 32) {
                 const int pl = idx % c8, r = idx / c8;
                 const int gr = row_base + r;
@@ -203,93 +215,115 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) decb_kernel(const __grid_consta
                 for (int s = 0; s < SPLIT; ++s)
                     cp_async16(dst0 + (uint32_t)(((s * c8 + pl) * R0 + r) * 16), ok ? src + (long long)s * p.x_split : xg, ok ? 16u : 0u);
             }
-            cp_async_mbar_arrive_noinc(&in_full[slot]);
+            cp_async_mbar_arrive_noinc(&in_full[pp][slot]);
         }
         cp_async_wait_all();
-    } else if (warp == 1) {
-        // ================= tcgen05 issuer =================
+    } else if (warp < 2 * FZ_NPIPE) {
+        // ================= tcgen05 issuers =================
+        const int pp = warp - FZ_NPIPE;
         const uint64_t desc_hi = (uint64_t)(0x4000u | (128u >> 4)) << 32;  // version 1, SBO = 128 B
         const uint32_t sB16 = sbase >> 4;
+        const uint32_t ones_lo = (sB16 + ((uint32_t)p.ones_off >> 4)) | (128u << 16);
+        const uint32_t arena16 = (sbase + pp * p.pipe_stride) >> 4;
         uint32_t i = 0;
         int n = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+        for (int item = blockIdx.x + pp * gridDim.x; item < n_items; item += FZ_NPIPE * gridDim.x, ++n) {
             const int slot = n & 1;
             for (int l = 0; l < p.n_layers; ++l) {
                 const FzLayer &L = p.L[l];
                 const uint32_t idesc = umma_idesc(L.nout, SPLIT == 2 ? 0 : 1);
-                const uint32_t in16 = (sbase + L.in_off + (l == 0 ? slot * p.in_slot_bytes : 0)) >> 4;
-                const uint32_t w16 = sB16 + (L.w_off >> 4);
+                const uint32_t in16 = arena16 + ((uint32_t)(L.in_off + (l == 0 ? slot * p.in_slot_bytes : 0)) >> 4);
+                const uint32_t w16 = sB16 + ((uint32_t)L.w_off >> 4);
+                const uint32_t bias_lo = (sB16 + ((uint32_t)L.bias_off >> 4)) | ((uint32_t)L.nout << 16);
                 for (int t = 0; t < L.n_tiles; ++t, ++i) {
                     const uint32_t buf = i & (FZ_NBUF - 1);
-                    mbar_wait(&done_bar[buf], ((i / FZ_NBUF) & 1) ^ 1);  // accumulator free: step i - NBUF retired
+                    mbar_wait(&done_bar[pp][buf], ((i / FZ_NBUF) & 1) ^ 1);  // accumulator free: step i - NBUF retired
 #pragma unroll
                     for (int dd = 0; dd < 2; ++dd) {
                         const uint32_t rel = L.dep[t][dd];
                         if (rel != 0 && rel < FZ_NBUF) {
                             const uint32_t d = i - rel;
-                            mbar_wait(&done_bar[d & (FZ_NBUF - 1)], (d / FZ_NBUF) & 1);
+                            mbar_wait(&done_bar[pp][d & (FZ_NBUF - 1)], (d / FZ_NBUF) & 1);
                         }
                     }
-                    if (l == 0 && t == 0) mbar_wait(&in_full[slot], (n >> 1) & 1);
+                    if (l == 0 && t == 0) mbar_wait(&in_full[pp][slot], (n >> 1) & 1);
                     fence_proxy_async();
                     tc_fence_after();
                     const uint32_t a16 = in16 + (uint32_t)t * 128u;
-                    const uint32_t d_tmem = tmem_base + buf * NCOLS;
+                    const uint32_t d_tmem = tmem_base + (pp * FZ_NBUF + buf) * FZ_NCOLS;
                     if (elect_one()) {
-                        umma_f16(d_tmem, desc_hi | (uint64_t)(a16 + L.term_a[0]), desc_hi | (uint64_t)(w16 + L.term_b[0]), idesc, 0u);
+                        umma_f16(d_tmem, desc_hi | (uint64_t)ones_lo, desc_hi | (uint64_t)bias_lo, idesc, 0u);  // D = bias
 #pragma unroll 4
-                        for (int k = 1; k < L.n_terms; ++k)
+                        for (int k = 0; k < L.n_terms; ++k)
                             umma_f16(d_tmem, desc_hi | (uint64_t)(a16 + L.term_a[k]), desc_hi | (uint64_t)(w16 + L.term_b[k]), idesc, 1u);
-                        umma_commit(&acc_full[buf]);
-                        if (l == 0 && t == L.n_tiles - 1) umma_commit(&in_empty[slot]);
+                        umma_commit(&acc_full[pp][buf]);
+                        if (l == 0 && t == L.n_tiles - 1) umma_commit(&in_empty[pp][slot]);
                     }
                     __syncwarp();
                 }
             }
         }
     } else {
-        // ================= epilogue groups + head =================
-        const int grp = (warp - 2) >> 2, q = warp & 3;
+        // ================= epilogue warps + head =================
+        const int pp = (warp - 2 * FZ_NPIPE) >> 2, q = warp & 3;
         const int r = q * 32 + lane;
-        const int e = (warp - 2) * 32 + lane;
+        uint8_t *arena = fz_smem + pp * p.pipe_stride;
         uint32_t i = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        for (int item = blockIdx.x + pp * gridDim.x; item < n_items; item += FZ_NPIPE * gridDim.x) {
             const int b = item / p.tiles_per_seq, j = item - b * p.tiles_per_seq;
             for (int l = 0; l < p.n_layers; ++l) {
                 const FzLayer &L = p.L[l];
                 for (int t = 0; t < L.n_tiles; ++t, ++i) {
-                    if ((int)(i & 1) != grp) continue;
                     const uint32_t buf = i & (FZ_NBUF - 1);
-                    mbar_wait(&acc_full[buf], (i / FZ_NBUF) & 1);
+                    mbar_wait(&acc_full[pp][buf], (i / FZ_NBUF) & 1);
                     tc_fence_after();
-                    const uint32_t tacc = tmem_base + buf * NCOLS + ((uint32_t)(q * 32) << 16);
-                    const float *bias = bias_s + L.bias_soff;
-                    if (L.out_kind == 1) fz_epi32(L, tacc, t, r, j, bias, fz_smem);
-                    else if (L.coutp == 32) fz_epi16<32, SPLIT>(L, tacc, t, r, j, bias, fz_smem);
-                    else fz_epi16<16, SPLIT>(L, tacc, t, r, j, bias, fz_smem);
+                    const uint32_t tacc = tmem_base + (pp * FZ_NBUF + buf) * FZ_NCOLS + ((uint32_t)(q * 32) << 16);
+                    if (L.out_kind == 1) fz_epi32(L, tacc, t, r, j, arena);
+                    else if (L.coutp == 32) fz_epi16<32, SPLIT>(L, tacc, t, r, j, arena);
+                    else fz_epi16<16, SPLIT>(L, tacc, t, r, j, arena);
                     fence_proxy_async();  // generic-proxy writes -> visible to the tensor-core (async) proxy
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&done_bar[buf]);
+                    if (lane == 0) mbar_arrive(&done_bar[pp][buf]);
                 }
             }
-            named_bar_sync(1, 256);  // the last layer's rows of both groups are in shared memory
-            fz_head(p, g, b, j, e, fz_smem);
-            named_bar_sync(1, 256);  // head done reading X before the next item's epilogues overwrite it
+            named_bar_sync(1 + pp, 128);  // the last layer's rows are in shared memory
+            fz_head<OPT>(p, g, b, j, r, arena);
+            named_bar_sync(1 + pp, 128);  // head done reading X before the next item's epilogues overwrite it
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, FZ_NBUF * NCOLS);
+    if (warp == 0) tmem_dealloc(tmem_base, FZ_NPIPE * FZ_NBUF * FZ_NCOLS);
 }
 
 // ------------------------------------------------------------------------------------------ host: plan
 static inline int fdiv2(int a) { return (a >= 0) ? a / 2 : -((-a + 1) / 2); }
 static inline int cdiv2(int a) { return -fdiv2(-a); }
 
-int decb_build(FzDecB &p, const TcLayer *dec, int split, int m, const float (*head_w)[88], const float *head_b) {
+static void bias_terms(float b, int split, uint16_t out[3]) {
+    float rem = b;
+    for (int k = 0; k < 3; ++k) {
+        float v;
+        if (split == 2) {
+            const __half h = __float2half_rn(rem);
+            out[k] = __half_as_ushort(h);
+            v = __half2float(h);
+        } else {
+            const __nv_bfloat16 h = __float2bfloat16_rn(rem);
+            out[k] = __bfloat16_as_ushort(h);
+            v = __bfloat162float(h);
+        }
+        rem -= v;
+    }
+}
+
+int decb_build(DecBPlan &plan, const TcLayer *dec, int split, int m, const float (*head_w)[88], const float *head_b) {
+    FzDecB &p = plan.p;
     std::memset(&p, 0, sizeof(p));
-    const int NL = 4;
+    plan.split = split;
+    plan.ready = false;
+    const int NL = 4, G = 3;
     p.n_layers = NL;
     p.T0 = 375;
     p.cin0 = dec[3].cin;
@@ -297,16 +331,17 @@ int decb_build(FzDecB &p, const TcLayer *dec, int split, int m, const float (*he
     p.tiles_per_seq = (p.T0 + m - 1) / m;
     p.W = 16 * m;
     p.L_out = 6000;
-    VP_REQUIRE(m % 1 == 0 && p.W % 4 == 0, VP_ERR_ARG, "decb: bad tile size %d", m);
+    plan.opt = ((p.W + 127) / 128 + 1) & ~1;
+    VP_REQUIRE(plan.opt == 6 || plan.opt == 10, VP_ERR_UNSUPPORTED, "decb: no head instance for %d outputs per thread", plan.opt);
     int lo[5], hi[5], c[5];
     for (int k = 0; k <= NL; ++k) c[k] = m << k;
-    lo[NL] = -6;  // head k11 needs -5; even so that both phases of a row land on an aligned float2
-    hi[NL] = c[NL] + 5 + 1;
-    hi[NL] += (hi[NL] - lo[NL]) & 1;  // even row count
+    lo[NL] = -6;  // the head (k11) needs -5; even so that both phases of a row land on an aligned float2
+    hi[NL] = c[NL] + 6;
     int s_lo[4], n_tiles[4];
     for (int l = NL - 1; l >= 0; --l) {
         const TcLayer &TL = dec[3 + l];
-        VP_REQUIRE(TL.ph == 2 && TL.cin % 16 == 0, VP_ERR_UNSUPPORTED, "decb: layer %d is not a polyphase layer", 3 + l);
+        VP_REQUIRE(TL.ph == 2 && TL.cin % 16 == 0 && TL.groups == G, VP_ERR_UNSUPPORTED, "decb: layer %d is not a 3-group polyphase layer", 3 + l);
+        VP_REQUIRE(!TL.blocks.empty(), VP_ERR_ARG, "decb: host weight blocks of layer %d are gone", 3 + l);
         const int ntaps = TL.halo + 1, o_min = TL.row0;
         s_lo[l] = fdiv2(lo[l + 1]);
         const int s_hi = cdiv2(hi[l + 1]);
@@ -316,7 +351,7 @@ int decb_build(FzDecB &p, const TcLayer *dec, int split, int m, const float (*he
         hi[l] = s_hi + o_min + ntaps - 1;
         if (l > 0 && (lo[l] & 1)) --lo[l];
     }
-    // shared-memory arena: in[2] | X | Y | weights
+    // shared memory: per pipeline { in[2] | X | Y }, then the bias-MMA A tile, then the weight blob
     const int esz = 16 * split;  // bytes per (row, plane)
     auto lvl_bytes = [&](int k) {
         if (k == NL) return (size_t)8 * (size_t)(((hi[k] - lo[k]) + 12 + 3) & ~3) * 4;
@@ -326,12 +361,24 @@ int decb_build(FzDecB &p, const TcLayer *dec, int split, int m, const float (*he
     auto up128 = [](size_t v) { return (v + 127) & ~(size_t)127; };
     p.in_slot_bytes = (int)up128(lvl_bytes(0));
     const size_t off_x = 2 * (size_t)p.in_slot_bytes;
-    const size_t x_bytes = up128(std::max(lvl_bytes(2), lvl_bytes(4)));
-    const size_t off_y = off_x + x_bytes;
-    const size_t y_bytes = up128(std::max(lvl_bytes(1), lvl_bytes(3)));
-    size_t off_w = off_y + y_bytes;
+    const size_t off_y = off_x + up128(std::max(lvl_bytes(2), lvl_bytes(4)));
+    p.pipe_stride = (int)(off_y + up128(std::max(lvl_bytes(1), lvl_bytes(3))));
+    p.ones_off = FZ_NPIPE * p.pipe_stride;
+    p.blob_off = p.ones_off + 4096;
     const size_t lvl_off[5] = {0, off_y, off_x, off_y, off_x};
-    int step = 0, bias_soff = 0;
+    // blob per group: for each layer { weight blocks, bias block }
+    size_t blob = 0;
+    size_t w_rel[4], b_rel[4];
+    for (int l = 0; l < NL; ++l) {
+        const TcLayer &TL = dec[3 + l];
+        w_rel[l] = blob;
+        blob += up128((size_t)TL.n_blocks * split * 2 * TL.nout * 16);
+        b_rel[l] = blob;
+        blob += up128((size_t)2 * TL.nout * 16);
+    }
+    p.blob_bytes = (int)blob;
+    plan.blob.assign((size_t)G * blob / 2, 0);
+    int step = 0;
     int step0[4];
     for (int l = 0; l < NL; ++l) {
         const TcLayer &TL = dec[3 + l];
@@ -339,7 +386,7 @@ int decb_build(FzDecB &p, const TcLayer *dec, int split, int m, const float (*he
         L.cin8 = TL.cin / 8;
         L.nout = TL.nout;
         L.coutp = (TL.cout + 7) / 8 * 8;
-        VP_REQUIRE(L.nout == 2 * L.coutp && L.nout <= 64, VP_ERR_UNSUPPORTED, "decb: layer %d N=%d coutp=%d", 3 + l, L.nout, L.coutp);
+        VP_REQUIRE(L.nout == 2 * L.coutp && L.nout <= FZ_NCOLS, VP_ERR_UNSUPPORTED, "decb: layer %d N=%d coutp=%d", 3 + l, L.nout, L.coutp);
         L.n_tiles = n_tiles[l];
         L.in_off = (int)lvl_off[l];
         L.in_rows = hi[l] - lo[l];
@@ -351,17 +398,20 @@ int decb_build(FzDecB &p, const TcLayer *dec, int split, int m, const float (*he
         L.out_lo = lo[l + 1];
         L.T_out = p.T0 << (l + 1);
         L.out_kind = (l == NL - 1) ? 1 : 0;
-        VP_REQUIRE(L.out_kind == 0 || L.coutp == 8, VP_ERR_UNSUPPORTED, "decb: last layer must have 8 channels");
+        VP_REQUIRE(L.out_kind == 0 || (L.coutp == 8 && L.out_rows % 2 == 0), VP_ERR_UNSUPPORTED, "decb: last layer must have 8 channels");
         VP_REQUIRE(L.out_kind == 1 || L.coutp == 32 || L.coutp == 16, VP_ERR_UNSUPPORTED, "decb: coutp %d", L.coutp);
-        L.w_off = (int)off_w;
-        L.w_bytes = TL.n_blocks * split * 2 * TL.nout * 16;
-        off_w += up128((size_t)L.w_bytes);
-        L.bias_soff = bias_soff;
-        bias_soff += 128;
-        L.w_goff = TL.w_off;
-        L.w_gs = (long long)TL.n_blocks * split * 2 * TL.nout * 8;
-        L.b_goff = (int)TL.b_off;
-        L.b_gs = TL.nout;
+        L.w_off = p.blob_off + (int)w_rel[l];
+        L.bias_off = p.blob_off + (int)b_rel[l];
+        const size_t wl_elems = (size_t)TL.n_blocks * split * 2 * TL.nout * 8;
+        for (int g = 0; g < G; ++g) {
+            uint16_t *dst = plan.blob.data() + (size_t)g * blob / 2;
+            std::memcpy(dst + w_rel[l] / 2, TL.blocks.data() + (size_t)g * wl_elems, wl_elems * sizeof(uint16_t));
+            for (int n = 0; n < TL.nout; ++n) {  // bias block [k-half][n][8]: k-half 0 holds the three bias terms
+                uint16_t t3[3];
+                bias_terms(TL.bias[(size_t)g * TL.nout + n], split, t3);
+                for (int k = 0; k < 3; ++k) dst[b_rel[l] / 2 + (size_t)n * 8 + k] = t3[k];
+            }
+        }
         // MMA schedule: tap j of channel pair q reads rows [a_row0 + j, ...) of planes 2q, 2q+1
         const int a_row0 = (s_lo[l] + TL.row0) - lo[l];
         const int nterm = (split == 2) ? 3 : 1;
@@ -384,13 +434,13 @@ int decb_build(FzDecB &p, const TcLayer *dec, int split, int m, const float (*he
             const int ntaps = TL.halo + 1;
             const int first = a_row0 + 128 * t;
             const int last = std::min(first + 127 + ntaps - 1, L.in_rows - 1);
-            const int e0 = 2 * s_lo[l - 1] - lo[l];  // local row written by (tile 0, lane 0, phase 0) of the producer
-            int ta = fdiv2(fdiv2(first - e0)) / 64, tb = fdiv2(fdiv2(last - e0)) / 64;  // floor(x / 256) for x >= -1
-            ta = std::max(0, std::min(ta, n_tiles[l - 1] - 1));
-            tb = std::max(0, std::min(tb, n_tiles[l - 1] - 1));
+            VP_REQUIRE(2 * s_lo[l - 1] - lo[l] == 0 && first >= 0, VP_ERR_UNSUPPORTED, "decb: producer rows are not tile aligned");
+            int ta = first / 256, tb = last / 256;  // producer tile t' writes local rows [256 t', 256 t' + 256)
+            ta = std::min(ta, n_tiles[l - 1] - 1);
+            tb = std::min(tb, n_tiles[l - 1] - 1);
+            VP_REQUIRE(tb - ta <= 1, VP_ERR_UNSUPPORTED, "decb: tile depends on more than two producer tiles");
             L.dep[t][0] = (uint8_t)((step + t) - (step0[l - 1] + ta));
             if (tb != ta) L.dep[t][1] = (uint8_t)((step + t) - (step0[l - 1] + tb));
-            VP_REQUIRE(tb - ta <= 1, VP_ERR_UNSUPPORTED, "decb: tile depends on more than two producer tiles");
         }
         step += L.n_tiles;
     }
@@ -398,39 +448,62 @@ int decb_build(FzDecB &p, const TcLayer *dec, int split, int m, const float (*he
     p.in_lo0 = lo[0];
     p.head_in_off = (int)off_x;
     p.head_rp = p.L[NL - 1].out_rp;
-    p.head_row0 = -5 - lo[NL];
-    VP_REQUIRE(p.head_row0 == 1, VP_ERR_UNSUPPORTED, "decb: head row offset");
-    for (int g = 0; g < 3; ++g) {
+    VP_REQUIRE(-5 - lo[NL] == 1, VP_ERR_UNSUPPORTED, "decb: head row offset");
+    for (int g = 0; g < G; ++g) {
         std::memcpy(p.head_w[g], head_w[g], 88 * sizeof(float));
         p.head_b[g] = head_b[g];
     }
-    p.smem_bytes = off_w;
-    VP_REQUIRE(p.smem_bytes <= 226 * 1024, VP_ERR_UNSUPPORTED, "decb: %zu bytes of shared memory", p.smem_bytes);
+    p.smem_bytes = p.blob_off + p.blob_bytes;
+    VP_REQUIRE(p.smem_bytes <= 226 * 1024, VP_ERR_UNSUPPORTED, "decb: %d bytes of shared memory", p.smem_bytes);
     return VP_OK;
 }
 
-int decb_launch(const FzDecB &plan, int split, const uint16_t *x, long long x_split, long long x_gs, int B,
-                const uint16_t *w_dev, const float *b_dev, float *y, cudaStream_t s) {
-    FzDecB p = plan;
-    p.x = x;
-    p.x_split = x_split;
-    p.x_gs = x_gs;
-    p.B = B;
-    p.w = w_dev;
-    p.bias = b_dev;
-    p.y = y;
-    const int n_items = B * p.tiles_per_seq;
-    if (n_items == 0) return VP_OK;
-    dim3 grid((unsigned)std::min(49, n_items), 3);
-    auto kern = (split == 2) ? decb_kernel<2> : decb_kernel<1>;
-    static size_t attr[2] = {0, 0};
-    if (p.smem_bytes > attr[split - 1]) {
-        VP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
-        attr[split - 1] = p.smem_bytes;
+int decb_upload(DecBPlan &plan) {
+    VP_CUDA_CHECK(cudaMalloc(&plan.d_blob, plan.blob.size() * sizeof(uint16_t)));
+    VP_CUDA_CHECK(cudaMemcpy(plan.d_blob, plan.blob.data(), plan.blob.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    plan.blob.clear();
+    plan.blob.shrink_to_fit();
+    plan.ready = true;
+    return VP_OK;
+}
+
+void decb_free(DecBPlan &plan) {
+    if (plan.d_blob) cudaFree(plan.d_blob);
+    plan.d_blob = nullptr;
+    plan.ready = false;
+}
+
+template <int SPLIT, int OPT>
+static int decb_launch_t(const FzDecB &p, dim3 grid, cudaStream_t s) {
+    auto kern = decb_kernel<SPLIT, OPT>;
+    static int attr = 0;
+    if (p.smem_bytes > attr) {
+        VP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes));
+        attr = p.smem_bytes;
     }
     kern<<<grid, FZ_THREADS, p.smem_bytes, s>>>(p);
     VP_LAUNCH_CHECK();
     return VP_OK;
+}
+
+int decb_launch(const DecBPlan &plan, const uint16_t *x, long long x_split, long long x_gs, int B, float *y, cudaStream_t s) {
+    VP_REQUIRE(plan.ready, VP_ERR_UNSUPPORTED, "decb: plan not uploaded");
+    FzDecB p = plan.p;
+    p.x = x;
+    p.x_split = x_split;
+    p.x_gs = x_gs;
+    p.B = B;
+    p.blob = plan.d_blob;
+    p.y = y;
+    const int n_items = B * p.tiles_per_seq;
+    if (n_items == 0) return VP_OK;
+    dim3 grid((unsigned)std::min(49, (n_items + FZ_NPIPE - 1) / FZ_NPIPE), 3);
+    if (plan.split == 2 && plan.opt == 6) return decb_launch_t<2, 6>(p, grid, s);
+    if (plan.split == 2 && plan.opt == 10) return decb_launch_t<2, 10>(p, grid, s);
+    if (plan.split == 1 && plan.opt == 6) return decb_launch_t<1, 6>(p, grid, s);
+    if (plan.split == 1 && plan.opt == 10) return decb_launch_t<1, 10>(p, grid, s);
+    set_error("decb: no kernel instance for split %d, %d outputs per thread", plan.split, plan.opt);
+    return VP_ERR_UNSUPPORTED;
 }
 
 }  // namespace vp

@@ -204,16 +204,13 @@ struct vp_model {
     // PhaseNet
     ConvW inc, down_same[5], down_down[4], up_t[4], up_same[4], outc;
     std::string tap_names;
-    float head_w_host[3][88];
-    float head_b_host[3];
     // tensor-core (tcgen05) weight sets: [0] = fp16 hi/lo split (f16x3), [1] = bf16
     struct TcSet {
         TcLayer enc[7], dec[7], head;
         uint16_t *d_w = nullptr;
         float *d_b = nullptr;
         bool ready = false;
-        FzDecB decb;  // fused decoder tail (fused_dec.cu)
-        bool decb_ready = false;
+        DecBPlan decb;  // fused decoder tail (fused_dec.cu)
     } tc[2];
 };
 
@@ -360,10 +357,16 @@ static int build_eqt(vp_model *m, Cursor &cur, Packed &pk) {
         const float *wl[3] = {hW[0], hW[1], hW[2]}, *bl[3] = {hB[0], hB[1], hB[2]};
         int rc = tc_build_layer(ts.head, TC_DIRECT, 8, 1, 11, 0, split, 3, wl, bl);
         if (rc != VP_OK) return rc;
-    }
-    for (int g = 0; g < 3; ++g) {
-        std::memcpy(m->head_w_host[g], hW[g], 88 * sizeof(float));  // (1, 8, 11) -> [c * 11 + k]
-        m->head_b_host[g] = hB[g][0];
+        // fused decoder tail: (1, 8, 11) head weights -> [c * 11 + k]; tile = 47 / 75 rows of the 375-sample level
+        float head_w[3][88], head_b[3];
+        for (int g = 0; g < 3; ++g) {
+            std::memcpy(head_w[g], hW[g], 88 * sizeof(float));
+            head_b[g] = hB[g][0];
+        }
+        int tile_m = split == 2 ? 47 : 75;
+        if (const char *e = getenv(split == 2 ? "VP_DECB_M2" : "VP_DECB_M1")) tile_m = atoi(e);  // tuning / debugging aid
+        rc = decb_build(ts.decb, ts.dec, split, tile_m, head_w, head_b);
+        if (rc != VP_OK) return rc;
     }
     return VP_OK;
 }
@@ -704,13 +707,13 @@ static int run_eqt(Runner &r, const float *x, float *y, Arena &ar) {
         if (r.go()) r.rc = launch_pack_cl16(din, 16 * (int64_t)T, T, (int)(3 * B), 16, T, split, Q16, split16, 2, r.s);
         const uint16_t *cur16 = Q16;
         static const bool fused_off = getenv("VP_FUSED") && atoi(getenv("VP_FUSED")) == 0;
-        const bool fused = ts.decb_ready && !fused_off;
+        const bool fused = ts.decb.ready && !fused_off;
         for (int i = 0; i < 7; ++i) {
             const TcLayer &tl = ts.dec[i];
             uint16_t *dst = pp16[i & 1];
             if (fused && i == 3) {  // decoder.convs.3-6 + heads in one kernel, activations in shared memory
                 if (r.go())
-                    r.rc = decb_launch(ts.decb, split, cur16, split16, B * (int64_t)tl.cin * dlen[i], (int)B, ts.d_w, ts.d_b, y, r.s);
+                    r.rc = decb_launch(ts.decb, cur16, split16, B * (int64_t)tl.cin * dlen[i], (int)B, y, r.s);
                 return r.rc;
             }
             if (r.go()) {
@@ -947,10 +950,7 @@ extern "C" int vp_model_create(int kind, const float *weights, int64_t n_floats,
     if (kind == VP_KIND_EQTRANSFORMER) {
         for (int set = 0; set < 2; ++set) {
             int rc = upload_tc(m->tc[set]);
-            if (rc == VP_OK) {
-                rc = decb_build(m->tc[set].decb, m->tc[set].dec, set == 0 ? 2 : 1, 75, m->head_w_host, m->head_b_host);
-                m->tc[set].decb_ready = (rc == VP_OK);
-            }
+            if (rc == VP_OK) rc = decb_upload(m->tc[set].decb);
             if (rc != VP_OK) {
                 vp_model_destroy(m);
                 return rc;
@@ -967,6 +967,7 @@ extern "C" int vp_model_destroy(vp_model *m) {
     for (int set = 0; set < 2; ++set) {
         if (m->tc[set].d_w) cudaFree(m->tc[set].d_w);
         if (m->tc[set].d_b) cudaFree(m->tc[set].d_b);
+        decb_free(m->tc[set].decb);
     }
     delete m;
     return VP_OK;
