@@ -28,6 +28,7 @@ struct FzLayer {
     int out_off;   // output buffer byte offset inside the pipeline's arena
     int out_rows;  // rows per output plane / valid rows of the fp32 planar buffer
     int out_rp;    // fp32 planar output: row pitch in floats
+    int a_row0;    // input-buffer row read by (tile 0, lane 0, tap 0)
     int s_lo;      // relative input row of (tile 0, lane 0)
     int c_in;      // input-level rows per tile index
     int out_lo;    // relative row of output-buffer row 0 (even)
@@ -38,6 +39,12 @@ struct FzLayer {
     uint32_t term_a[FZ_MAX_TERMS], term_b[FZ_MAX_TERMS];
     uint8_t dep[FZ_MAX_TILES][2];  // producer steps this tile waits for, as distances back in the step sequence (0: none)
 };
+
+// Compile-time MMA schedules of the decoder tail (decoder.convs.3-6 in polyphase form): MMA N, taps, 16-channel
+// pairs.  decb_build() checks them against the host-built layers.
+constexpr int FZ_DEC_NOUT[4] = {64, 32, 32, 16};
+constexpr int FZ_DEC_NTAPS[4] = {5, 5, 5, 7};
+constexpr int FZ_DEC_NQ[4] = {2, 2, 1, 1};
 
 // Decoder tail: decoder.convs.3-6 + sigmoid(conv k11) head for the three EQTransformer decoders.
 struct FzDecB {

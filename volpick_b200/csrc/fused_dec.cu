@@ -146,6 +146,48 @@ __device__ __forceinline__ void fz_head(const FzDecB &p, int g, int b, int j, in
     }
 }
 
+// One layer of one work item on the issuer warp: per M tile wait for the accumulator buffer and the producer
+// tiles, then issue the bias MMA + the layer's compile-time MMA schedule.
+template <int LYR, int SPLIT>
+__device__ __forceinline__ void fz_issue_layer(const FzDecB &p, int pp, int slot, int n, uint32_t &i, uint32_t tmem_base,
+                                               uint32_t arena16, uint32_t sB16, uint32_t ones_lo, uint64_t (*in_full)[2],
+                                               uint64_t (*in_empty)[2], uint64_t (*acc_full)[FZ_NBUF],
+                                               uint64_t (*done_bar)[FZ_NBUF]) {
+    constexpr int l = LYR;
+    constexpr int NOUT = FZ_DEC_NOUT[l];
+    const uint64_t desc_hi = (uint64_t)(0x4000u | (128u >> 4)) << 32;  // version 1, SBO = 128 B
+    const FzLayer &L = p.L[l];
+    const uint32_t idesc = umma_idesc(NOUT, SPLIT == 2 ? 0 : 1);
+    const uint32_t in16 = arena16 + ((uint32_t)(L.in_off + (l == 0 ? slot * p.in_slot_bytes : 0)) >> 4) + (uint32_t)L.a_row0;
+    const uint32_t w16 = sB16 + ((uint32_t)L.w_off >> 4);
+    const uint32_t bias_lo = (sB16 + ((uint32_t)L.bias_off >> 4)) | ((uint32_t)NOUT << 16);
+    const uint32_t in_rows = (uint32_t)L.in_rows;
+    for (int t = 0; t < L.n_tiles; ++t, ++i) {
+        const uint32_t buf = i & (FZ_NBUF - 1);
+        mbar_wait(&done_bar[pp][buf], ((i / FZ_NBUF) & 1) ^ 1);  // accumulator free: step i - NBUF retired
+#pragma unroll
+        for (int dd = 0; dd < 2; ++dd) {
+            const uint32_t rel = L.dep[t][dd];
+            if (rel != 0 && rel < FZ_NBUF) {
+                const uint32_t d = i - rel;
+                mbar_wait(&done_bar[pp][d & (FZ_NBUF - 1)], (d / FZ_NBUF) & 1);
+            }
+        }
+        if (l == 0 && t == 0) mbar_wait(&in_full[pp][slot], (n >> 1) & 1);
+        fence_proxy_async();
+        tc_fence_after();
+        const uint32_t a16 = in16 + (uint32_t)t * 128u;
+        const uint32_t d_tmem = tmem_base + (pp * FZ_NBUF + buf) * FZ_NCOLS;
+        if (elect_one()) {
+            umma_f16(d_tmem, desc_hi | (uint64_t)ones_lo, desc_hi | (uint64_t)bias_lo, idesc, 0u);  // D = bias
+            umma_conv_tile<NOUT, SPLIT, FZ_DEC_NTAPS[l], FZ_DEC_NQ[l]>(d_tmem, a16, in_rows, w16, idesc, 1u);
+            umma_commit(&acc_full[pp][buf]);
+            if (l == 0 && t == L.n_tiles - 1) umma_commit(&in_empty[pp][slot]);
+        }
+        __syncwarp();
+    }
+}
+
 // ------------------------------------------------------------------------------------------ the kernel
 template <int SPLIT, int OPT>
 __global__ void __launch_bounds__(FZ_THREADS, 1) decb_kernel(const __grid_constant__ FzDecB p) {
@@ -221,7 +263,6 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) decb_kernel(const __grid_consta
     } else if (warp < 2 * FZ_NPIPE) {
         // ================= tcgen05 issuers =================
         const int pp = warp - FZ_NPIPE;
-        const uint64_t desc_hi = (uint64_t)(0x4000u | (128u >> 4)) << 32;  // version 1, SBO = 128 B
         const uint32_t sB16 = sbase >> 4;
         const uint32_t ones_lo = (sB16 + ((uint32_t)p.ones_off >> 4)) | (128u << 16);
         const uint32_t arena16 = (sbase + pp * p.pipe_stride) >> 4;
@@ -229,39 +270,10 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) decb_kernel(const __grid_consta
         int n = 0;
         for (int item = blockIdx.x + pp * gridDim.x; item < n_items; item += FZ_NPIPE * gridDim.x, ++n) {
             const int slot = n & 1;
-            for (int l = 0; l < p.n_layers; ++l) {
-                const FzLayer &L = p.L[l];
-                const uint32_t idesc = umma_idesc(L.nout, SPLIT == 2 ? 0 : 1);
-                const uint32_t in16 = arena16 + ((uint32_t)(L.in_off + (l == 0 ? slot * p.in_slot_bytes : 0)) >> 4);
-                const uint32_t w16 = sB16 + ((uint32_t)L.w_off >> 4);
-                const uint32_t bias_lo = (sB16 + ((uint32_t)L.bias_off >> 4)) | ((uint32_t)L.nout << 16);
-                for (int t = 0; t < L.n_tiles; ++t, ++i) {
-                    const uint32_t buf = i & (FZ_NBUF - 1);
-                    mbar_wait(&done_bar[pp][buf], ((i / FZ_NBUF) & 1) ^ 1);  // accumulator free: step i - NBUF retired
-#pragma unroll
-                    for (int dd = 0; dd < 2; ++dd) {
-                        const uint32_t rel = L.dep[t][dd];
-                        if (rel != 0 && rel < FZ_NBUF) {
-                            const uint32_t d = i - rel;
-                            mbar_wait(&done_bar[pp][d & (FZ_NBUF - 1)], (d / FZ_NBUF) & 1);
-                        }
-                    }
-                    if (l == 0 && t == 0) mbar_wait(&in_full[pp][slot], (n >> 1) & 1);
-                    fence_proxy_async();
-                    tc_fence_after();
-                    const uint32_t a16 = in16 + (uint32_t)t * 128u;
-                    const uint32_t d_tmem = tmem_base + (pp * FZ_NBUF + buf) * FZ_NCOLS;
-                    if (elect_one()) {
-                        umma_f16(d_tmem, desc_hi | (uint64_t)ones_lo, desc_hi | (uint64_t)bias_lo, idesc, 0u);  // D = bias
-#pragma unroll 4
-                        for (int k = 0; k < L.n_terms; ++k)
-                            umma_f16(d_tmem, desc_hi | (uint64_t)(a16 + L.term_a[k]), desc_hi | (uint64_t)(w16 + L.term_b[k]), idesc, 1u);
-                        umma_commit(&acc_full[pp][buf]);
-                        if (l == 0 && t == L.n_tiles - 1) umma_commit(&in_empty[pp][slot]);
-                    }
-                    __syncwarp();
-                }
-            }
+            fz_issue_layer<0, SPLIT>(p, pp, slot, n, i, tmem_base, arena16, sB16, ones_lo, in_full, in_empty, acc_full, done_bar);
+            fz_issue_layer<1, SPLIT>(p, pp, slot, n, i, tmem_base, arena16, sB16, ones_lo, in_full, in_empty, acc_full, done_bar);
+            fz_issue_layer<2, SPLIT>(p, pp, slot, n, i, tmem_base, arena16, sB16, ones_lo, in_full, in_empty, acc_full, done_bar);
+            fz_issue_layer<3, SPLIT>(p, pp, slot, n, i, tmem_base, arena16, sB16, ones_lo, in_full, in_empty, acc_full, done_bar);
         }
     } else {
         // ================= epilogue warps + head =================
@@ -414,6 +426,10 @@ int decb_build(DecBPlan &plan, const TcLayer *dec, int split, int m, const float
         }
         // MMA schedule: tap j of channel pair q reads rows [a_row0 + j, ...) of planes 2q, 2q+1
         const int a_row0 = (s_lo[l] + TL.row0) - lo[l];
+        L.a_row0 = a_row0;
+        VP_REQUIRE(TL.nout == FZ_DEC_NOUT[l] && TL.sched_taps == FZ_DEC_NTAPS[l] && TL.sched_nq == FZ_DEC_NQ[l] && a_row0 >= 0,
+                   VP_ERR_UNSUPPORTED, "decb: layer %d (N=%d, %d taps, %d pairs) differs from the compiled schedule", 3 + l,
+                   TL.nout, TL.sched_taps, TL.sched_nq);
         const int nterm = (split == 2) ? 3 : 1;
         L.n_terms = 0;
         for (const TcMma &e : TL.mma)
@@ -426,6 +442,19 @@ int decb_build(DecBPlan &plan, const TcLayer *dec, int split, int m, const float
                 L.term_b[L.n_terms] = b_off | ((uint32_t)TL.nout << 16);
                 ++L.n_terms;
             }
+        {   // the kernel issues umma_conv_tile<NOUT, SPLIT, NTAPS, NQ>: its descriptors must equal the host-built schedule
+            int kk = 0;
+            bool same = L.n_terms == FZ_DEC_NTAPS[l] * FZ_DEC_NQ[l] * nterm;
+            for (int j = 0; same && j < FZ_DEC_NTAPS[l]; ++j)
+                for (int q = 0; q < FZ_DEC_NQ[l]; ++q)
+                    for (int t = 0; t < nterm; ++t, ++kk) {
+                        const int sa = (t == 2) ? 1 : 0, sb = (t == 1) ? 1 : 0;
+                        const uint32_t ea = (uint32_t)((sa * L.cin8 + 2 * q) * L.in_rows + a_row0 + j) | ((uint32_t)L.in_rows << 16);
+                        const uint32_t eb = (uint32_t)(((j * FZ_DEC_NQ[l] + q) * split + sb) * 2 * TL.nout) | ((uint32_t)TL.nout << 16);
+                        same = same && L.term_a[kk] == ea && L.term_b[kk] == eb;
+                    }
+            VP_REQUIRE(same, VP_ERR_UNSUPPORTED, "decb: compiled MMA schedule of layer %d differs from the host-built one", 3 + l);
+        }
         // producer dependencies (previous layer's tiles that write the rows this tile reads)
         step0[l] = step;
         for (int t = 0; t < L.n_tiles; ++t) {

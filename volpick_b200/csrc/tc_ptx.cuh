@@ -127,4 +127,36 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// All tcgen05.mma of one 128-row tile of an implicit-GEMM conv layer, fully unrolled at compile time so that
+// every descriptor is (base + immediate): the issuing thread spends ~3 uniform instructions per MMA instead of
+// a dependent constant-bank load per descriptor (measured: ~80 cycles per MMA with run-time schedule tables).
+//   NQ > 0: input of 16*NQ channels, tap j of channel pair q reads rows [j, j+128) of planes 2q, 2q+1
+//           (LBO = plane pitch `rows`);  NQ == 0: 8-channel input, K step = taps 2j, 2j+1 (LBO = one row).
+//   a16 / w16: shared-memory addresses (16-byte units) of staged row 0 (hi split) / weight block 0.
+//   Weight blocks: [block][split][k-half][NOUT][8]; activation planes: [split][plane][rows][8].
+// Order = (tap, pair, split term), the order of the host-built schedule (TcLayer::mma).
+template <int NOUT, int SPLIT, int NTAPS, int NQ>
+__device__ __forceinline__ void umma_conv_tile(uint32_t d_tmem, uint32_t a16, uint32_t rows, uint32_t w16, uint32_t idesc,
+                                               uint32_t accumulate_first) {
+    constexpr int NTERM = SPLIT == 2 ? 3 : 1;  // hi*hi, hi*lo, lo*hi
+    constexpr int CIN8 = NQ == 0 ? 1 : 2 * NQ;
+    constexpr int QN = NQ == 0 ? 1 : NQ;
+    const uint64_t desc_hi = (uint64_t)(0x4000u | (128u >> 4)) << 32;  // version 1 (Blackwell), SBO = 128 B
+    const uint32_t a_base = a16 | ((NQ == 0 ? 1u : rows) << 16);
+    const uint32_t b_base = w16 | ((uint32_t)NOUT << 16);
+#pragma unroll
+    for (int j = 0; j < NTAPS; ++j)
+#pragma unroll
+        for (int q = 0; q < QN; ++q)
+#pragma unroll
+            for (int t = 0; t < NTERM; ++t) {
+                const int sa = (t == 2) ? 1 : 0, sb = (t == 1) ? 1 : 0;
+                const uint32_t a_off = (uint32_t)(sa * CIN8 + (NQ == 0 ? 0 : 2 * q)) * rows + (uint32_t)(NQ == 0 ? 2 * j : j);
+                const uint32_t b_off = (uint32_t)(((NQ == 0 ? j : j * NQ + q) * SPLIT + sb) * 2 * NOUT);
+                const bool first = (j == 0 && q == 0 && t == 0);
+                umma_f16(d_tmem, desc_hi | (uint64_t)(a_base + a_off), desc_hi | (uint64_t)(b_base + b_off), idesc,
+                         first ? accumulate_first : 1u);
+            }
+}
+
 }  // namespace vp

@@ -35,24 +35,52 @@
 namespace vp {
 
 // ------------------------------------------------------------------------------------------ the layer kernel
-// Persistent, warp-specialised CTA (256 threads):
-//   warps 0-3  epilogue: TMEM lane quarter -> registers -> bias/act/pool -> global
-//   warp  4    MMA issuer (one elected lane) + TMEM allocation (2 accumulator buffers)
-//   warps 5-7  producers: cp.async (zero-fill) of the A tiles into an NSTAGE ring
+// Persistent, warp-specialised CTA of 32 * (EW + 4) threads:
+//   warps 0..EW-1   epilogue: TMEM lane quarter (warp & 3), column half (warp >> 2 when EW == 8) -> registers ->
+//                   bias / residual / act / pool -> global
+//   warp  EW        MMA issuer (one elected lane) + TMEM allocation (2 accumulator buffers)
+//   warps EW+1..+3  producers: cp.async (zero-fill) of the A tiles into an NSTAGE ring
 // Barriers: full[stage] (96 producer arrivals via cp.async.mbarrier.arrive.noinc), empty[stage]
-// (tcgen05.commit), accf[acc] (tcgen05.commit), acce[acc] (128 epilogue arrivals).  The weights of the
+// (tcgen05.commit), accf[acc] (tcgen05.commit), acce[acc] (32 * EW epilogue arrivals).  The weights and the bias of the
 // layer are loaded once per CTA and stay resident in shared memory.
-constexpr int TC_THREADS = 256;
+// EW = 8 is used when only one or two CTAs fit an SM (wide N / large resident weights): with four epilogue
+// warps the TMEM -> convert -> store chain of a 128 x 128 tile was the measured bottleneck (dec1: 245 us with,
+// 33 us without the epilogue).
 constexpr int TC_PRODUCERS = 96;
 constexpr int TC_MAX_STAGES = 4;
 
+template <int SPLIT>
+__device__ __forceinline__ void tc_pack8(const float *v, uint4 &hi, uint4 &lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float a = v[2 * i], b = v[2 * i + 1];
+        if (SPLIT == 2) {
+            const __half2 hh = __floats2half2_rn(a, b);
+            const float2 hf = __half22float2(hh);
+            const __half2 ll = __floats2half2_rn(a - hf.x, b - hf.y);
+            h[i] = *reinterpret_cast<const uint32_t *>(&hh);
+            l[i] = *reinterpret_cast<const uint32_t *>(&ll);
+        } else {
+            const __nv_bfloat162 bb = __floats2bfloat162_rn(a, b);
+            h[i] = *reinterpret_cast<const uint32_t *>(&bb);
+            l[i] = 0u;
+        }
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
 
-template <int NOUT, int SPLIT>
-__global__ void __launch_bounds__(TC_THREADS) tcconv_kernel(const __grid_constant__ TcP p) {
+// NTAPS > 0: the tile's MMA schedule is fixed at compile time (umma_conv_tile); NTAPS == 0: generic
+// instance that walks the host-built schedule table (any layer shape; slower issue).
+template <int NOUT, int SPLIT, int NTAPS, int NQ, int EW>
+__global__ void __launch_bounds__(32 * (EW + 4), EW == 8 ? 2 : 4) tcconv_kernel(const __grid_constant__ TcP p) {
     extern __shared__ __align__(128) uint8_t tc_smem[];
     __shared__ __align__(8) uint64_t full_bar[TC_MAX_STAGES], empty_bar[TC_MAX_STAGES], accf_bar[2], acce_bar[2];
     __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(16) float s_bias[NOUT], s_psc[NOUT], s_psh[NOUT];
     constexpr int NCOLS = NOUT < 32 ? 32 : NOUT;
+    constexpr int THREADS = 32 * (EW + 4);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = blockIdx.y;
@@ -62,7 +90,7 @@ __global__ void __launch_bounds__(TC_THREADS) tcconv_kernel(const __grid_constan
     const uint32_t w_bytes = ((uint32_t)p.n_blocks * SPLIT * 2 * NOUT * 16u + 127u) & ~127u;
     const uint32_t sB_u = smem_u32(tc_smem);
     const uint32_t sA_u = sB_u + w_bytes;
-    const int64_t n_tiles = ((int64_t)p.NS * p.Tp + 127) / 128;
+    const int n_tiles = (int)(((int64_t)p.NS * p.Tp + 127) / 128);
 
     if (tid == 0) {
         for (int i = 0; i < nstage; ++i) {
@@ -71,15 +99,20 @@ __global__ void __launch_bounds__(TC_THREADS) tcconv_kernel(const __grid_constan
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&accf_bar[i], 1);
-            mbar_init(&acce_bar[i], 128);
+            mbar_init(&acce_bar[i], 32 * EW);
         }
         fence_barrier_init();
     }
-    if (warp == 4) tmem_alloc(&tmem_base_s, 2 * NCOLS);
-    {   // resident weights
+    if (warp == EW) tmem_alloc(&tmem_base_s, 2 * NCOLS);
+    {   // resident weights, bias, optional post-affine of the 16-bit output
         const int wpieces = p.n_blocks * SPLIT * 2 * NOUT;
         const uint4 *wg = reinterpret_cast<const uint4 *>(p.w + (int64_t)g * p.w_gs);
-        for (int idx = tid; idx < wpieces; idx += TC_THREADS) cp_async16(sB_u + (uint32_t)idx * 16u, wg + idx, 16u);
+        for (int idx = tid; idx < wpieces; idx += THREADS) cp_async16(sB_u + (uint32_t)idx * 16u, wg + idx, 16u);
+        for (int idx = tid; idx < NOUT; idx += THREADS) {
+            s_bias[idx] = __ldg(p.bias + (int64_t)g * p.b_gs + idx);
+            s_psc[idx] = p.post_scale ? __ldg(p.post_scale + idx) : 1.f;
+            s_psh[idx] = p.post_shift ? __ldg(p.post_shift + idx) : 0.f;
+        }
         cp_async_wait_all();
         fence_proxy_async();
     }
@@ -88,29 +121,28 @@ __global__ void __launch_bounds__(TC_THREADS) tcconv_kernel(const __grid_constan
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
 
-    if (warp >= 5) {
+    if (warp > EW) {
         // ================= producers =================
-        const int ptid = tid - 160;
+        const int ptid = tid - 32 * (EW + 1);
         const int CIN = cin8 * 8;
         const uint16_t *xg = p.x + (int64_t)g * p.x_gs;
         int stage = 0;
         uint32_t phase = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             mbar_wait(&empty_bar[stage], phase ^ 1u);
-            const int64_t m0 = tile * 128;
+            const int m0 = tile * 128;
             const uint32_t sbase = sA_u + (uint32_t)stage * a_bytes;
             for (int r = ptid; r < n_rows && !(p.dbg & 1); r += TC_PRODUCERS) {
-                const int64_t v = m0 + p.row0 + r;
+                const int v = m0 + p.row0 + r;
                 bool valid = v >= 0;
-                int64_t seq = 0;
-                int u = 0;
+                int seq = 0, u = 0;
                 if (valid) {
                     seq = v / p.Tp;
-                    u = (int)(v - seq * p.Tp);
+                    u = v - seq * p.Tp;
                     valid = (seq < p.NS) && (u < p.T_eff);
                 }
                 const int srow = (p.ups == 2) ? (u >> 1) : u;
-                const uint16_t *src = valid ? (xg + (seq * p.T_in + srow) * CIN) : xg;
+                const uint16_t *src = valid ? (xg + ((int64_t)seq * p.T_in + srow) * CIN) : xg;
                 const uint32_t nb = valid ? 16u : 0u;
 #pragma unroll
                 for (int s = 0; s < SPLIT; ++s) {
@@ -126,17 +158,17 @@ __global__ void __launch_bounds__(TC_THREADS) tcconv_kernel(const __grid_constan
             }
         }
         cp_async_wait_all();
-    } else if (warp == 4) {
+    } else if (warp == EW) {
         // ================= MMA issuer =================
         // The whole warp runs the loop (uniform control flow keeps the descriptors in uniform registers);
-        // one elected lane issues.  Per MMA only two adds remain: the schedule was precomputed on the host.
+        // one elected lane issues.
         const uint32_t idesc = umma_idesc(NOUT, p.fmt16);
         const uint32_t sB16 = sB_u >> 4;
         const uint64_t desc_hi = (uint64_t)(0x4000u | (128u >> 4)) << 32;  // version 1 (Blackwell), SBO = 128 B
         int stage = 0, acc = 0;
         uint32_t phase = 0, acc_phase = 0;
         const int n_terms = p.n_terms;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             mbar_wait(&acce_bar[acc], acc_phase ^ 1u);
             mbar_wait(&full_bar[stage], phase);
             fence_proxy_async();
@@ -144,10 +176,15 @@ __global__ void __launch_bounds__(TC_THREADS) tcconv_kernel(const __grid_constan
             const uint32_t sA16 = (sA_u + (uint32_t)stage * a_bytes) >> 4;
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * NCOLS);
             if (elect_one()) {
-                umma_f16(d_tmem, desc_hi | (uint64_t)(sA16 + p.term_a[0]), desc_hi | (uint64_t)(sB16 + p.term_b[0]), idesc, 0u);
+                if constexpr (NTAPS > 0) {
+                    constexpr uint32_t ROWS = 128 + (NQ == 0 ? 2 * NTAPS - 1 : NTAPS - 1);  // == p.n_rows
+                    umma_conv_tile<NOUT, SPLIT, NTAPS, NQ>(d_tmem, sA16, ROWS, sB16, idesc, 0u);
+                } else {
+                    umma_f16(d_tmem, desc_hi | (uint64_t)(sA16 + p.term_a[0]), desc_hi | (uint64_t)(sB16 + p.term_b[0]), idesc, 0u);
 #pragma unroll 4
-                for (int i = 1; i < ((p.dbg & 2) ? 1 : n_terms); ++i)
-                    umma_f16(d_tmem, desc_hi | (uint64_t)(sA16 + p.term_a[i]), desc_hi | (uint64_t)(sB16 + p.term_b[i]), idesc, 1u);
+                    for (int i = 1; i < ((p.dbg & 2) ? 1 : n_terms); ++i)
+                        umma_f16(d_tmem, desc_hi | (uint64_t)(sA16 + p.term_a[i]), desc_hi | (uint64_t)(sB16 + p.term_b[i]), idesc, 1u);
+                }
                 umma_commit(&empty_bar[stage]);
                 umma_commit(&accf_bar[acc]);
             }
@@ -161,66 +198,97 @@ __global__ void __launch_bounds__(TC_THREADS) tcconv_kernel(const __grid_constan
         }
     } else {
         // ================= epilogue =================
-        const float *bias = p.bias + (int64_t)g * p.b_gs;
+        constexpr int NHALF = EW / 4;                  // column splits per lane quarter
+        constexpr int COLS = NOUT / NHALF;             // columns per epilogue warp
+        constexpr int CH = COLS >= 16 ? 16 : 8;        // columns per TMEM load
+        const int quarter = warp & 3, half = warp >> 2;
+        const int coutp = p.coutp;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             mbar_wait(&accf_bar[acc], acc_phase);
             tc_fence_after();
-            const int64_t v = tile * 128 + tid;
-            const int64_t seq = v / p.Tp;
-            const int srow = (int)(v - seq * p.Tp);
+            const int v = tile * 128 + quarter * 32 + lane;
+            const int seq = v / p.Tp;
+            const int srow = v - seq * p.Tp;
             const bool row_ok = (seq < p.NS) && (srow < p.T_valid);
-            const uint32_t trow = tmem_base + (uint32_t)(acc * NCOLS) + ((uint32_t)(warp * 32) << 16);
-#pragma unroll 1
-            for (int n0 = 0; n0 < ((p.dbg & 4) ? 0 : NOUT); n0 += 8) {
-                const int phi = n0 / p.coutp;
-                const int c0 = n0 - phi * p.coutp;
-                if (phi >= p.ph || c0 >= p.cout) continue;  // padding columns (warp-uniform)
-                float a[8];
-                tmem_ld8(trow + (uint32_t)n0, a);
+            const uint32_t trow = tmem_base + (uint32_t)(acc * NCOLS) + ((uint32_t)(quarter * 32) << 16);
+            // output row bases (polyphase: row 2 srow + phi; pool: row srow >> 1, written by the even lane)
+            const bool st = (p.pool == 2) ? (row_ok && !(lane & 1)) : row_ok;
+            const int t0 = (p.pool == 2) ? (srow >> 1) : p.ph * srow;
+            const int64_t orow0 = (int64_t)seq * p.T_out + t0;
+            if (!(p.dbg & 4)) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    float t = a[i] + __ldg(bias + n0 + i);
-                    if (p.act == ACT_RELU) t = fmaxf(t, 0.f);
-                    if (p.act == ACT_SIGMOID) t = 1.f / (1.f + expf(-t));
-                    a[i] = t;
-                }
-                int t_out = p.ph * srow + phi;
-                bool st = row_ok;
-                if (p.pool == 2) {
+                for (int cc = 0; cc < COLS; cc += CH) {
+                    const int nb = half * COLS + cc;  // first accumulator column of this chunk
+                    float a[CH];
+                    {
+                        uint32_t r[CH];
+                        if constexpr (CH == 16) {
+                            uint32_t(&r16)[16] = *reinterpret_cast<uint32_t(*)[16]>(&r[0]);
+                            tmem_ld16_nowait(trow + (uint32_t)nb, r16);
+                        } else {
+                            uint32_t(&r8)[8] = *reinterpret_cast<uint32_t(*)[8]>(&r[0]);
+                            tmem_ld8_nowait(trow + (uint32_t)nb, r8);
+                        }
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float mine = row_ok ? a[i] : -1e10f;  // SeisBench pads odd lengths with -1e10 before MaxPool1d(2)
-                        a[i] = fmaxf(mine, __shfl_xor_sync(0xffffffffu, mine, 1));
+                        for (int i = 0; i < CH; ++i) a[i] = __uint_as_float(r[i]);
                     }
-                    st = row_ok && !(tid & 1);
-                    t_out = srow >> 1;
-                }
-                if (!st || t_out >= p.T_out) continue;
-                if (p.out_fmt == 0) {
-                    uint16_t hi[8], lo[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) split16(a[i], p.fmt16, SPLIT, hi[i], lo[i]);
-                    uint16_t *yb = reinterpret_cast<uint16_t *>(p.y) + (int64_t)g * p.y_gs + (seq * p.T_out + t_out) * p.cout_cl + c0;
-                    uint4 ph4, pl4;
-                    ph4.x = hi[0] | ((uint32_t)hi[1] << 16);
-                    ph4.y = hi[2] | ((uint32_t)hi[3] << 16);
-                    ph4.z = hi[4] | ((uint32_t)hi[5] << 16);
-                    ph4.w = hi[6] | ((uint32_t)hi[7] << 16);
-                    *reinterpret_cast<uint4 *>(yb) = ph4;
-                    if (SPLIT == 2) {
-                        pl4.x = lo[0] | ((uint32_t)lo[1] << 16);
-                        pl4.y = lo[2] | ((uint32_t)lo[3] << 16);
-                        pl4.z = lo[4] | ((uint32_t)lo[5] << 16);
-                        pl4.w = lo[6] | ((uint32_t)lo[7] << 16);
-                        *reinterpret_cast<uint4 *>(yb + p.y_split) = pl4;
+                    for (int g8 = 0; g8 < CH; g8 += 8) {
+                        const int n0 = nb + g8;
+                        const int phi = (n0 >= coutp) ? 1 : 0;
+                        const int c0 = n0 - phi * coutp;
+                        if (phi >= p.ph || c0 >= p.cout) continue;  // padding columns (warp-uniform)
+                        float *w8 = &a[g8];
+                        const float4 b0 = *reinterpret_cast<const float4 *>(&s_bias[n0]), b1 = *reinterpret_cast<const float4 *>(&s_bias[n0 + 4]);
+                        w8[0] += b0.x, w8[1] += b0.y, w8[2] += b0.z, w8[3] += b0.w;
+                        w8[4] += b1.x, w8[5] += b1.y, w8[6] += b1.z, w8[7] += b1.w;
+                        const int t_out = t0 + phi;
+                        const bool ok = st && t_out < p.T_out;
+                        if (p.res != nullptr && ok) {  // residual stream, fp32 row-major [seq][t][cout]
+                            const float4 *rp = reinterpret_cast<const float4 *>(p.res + (orow0 + phi) * p.cout + c0);
+                            const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+                            w8[0] += r0.x, w8[1] += r0.y, w8[2] += r0.z, w8[3] += r0.w;
+                            w8[4] += r1.x, w8[5] += r1.y, w8[6] += r1.z, w8[7] += r1.w;
+                        }
+                        if (p.y32 != nullptr && ok) {  // second output: the un-activated fp32 value, row-major
+                            float4 *yp = reinterpret_cast<float4 *>(p.y32 + (orow0 + phi) * p.cout + c0);
+                            yp[0] = make_float4(w8[0], w8[1], w8[2], w8[3]);
+                            yp[1] = make_float4(w8[4], w8[5], w8[6], w8[7]);
+                        }
+                        if (p.post_scale != nullptr) {  // pre-activation BatchNorm + ReLU of the next conv
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) w8[i] = fmaxf(fmaf(w8[i], s_psc[n0 + i], s_psh[n0 + i]), 0.f);
+                        } else if (p.act == ACT_RELU) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) w8[i] = fmaxf(w8[i], 0.f);
+                        } else if (p.act == ACT_SIGMOID) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) w8[i] = 1.f / (1.f + expf(-w8[i]));
+                        }
+                        if (p.pool == 2) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const float mine = row_ok ? w8[i] : -1e10f;  // SeisBench pads odd lengths with -1e10 before MaxPool1d(2)
+                                w8[i] = fmaxf(mine, __shfl_xor_sync(0xffffffffu, mine, 1));
+                            }
+                        }
+                        if (!ok) continue;
+                        if (p.out_fmt == 0) {
+                            uint4 hi, lo;
+                            tc_pack8<SPLIT>(w8, hi, lo);
+                            uint16_t *yb = reinterpret_cast<uint16_t *>(p.y) + (int64_t)g * p.y_gs + (orow0 + phi) * p.cout_cl + c0;
+                            *reinterpret_cast<uint4 *>(yb) = hi;
+                            if (SPLIT == 2) *reinterpret_cast<uint4 *>(yb + p.y_split) = lo;
+                        } else {
+                            float *yb = reinterpret_cast<float *>(p.y) + (int64_t)g * p.y_gs + (int64_t)seq * p.y_ss + t_out;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                if (c0 + i < p.cout) yb[(int64_t)(c0 + i) * p.y_cs] = w8[i];
+                        }
                     }
-                } else {
-                    float *yb = reinterpret_cast<float *>(p.y) + (int64_t)g * p.y_gs + seq * p.y_ss + t_out;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        if (c0 + i < p.cout) yb[(int64_t)(c0 + i) * p.y_cs] = a[i];
                 }
             }
             tc_fence_before();
@@ -231,7 +299,7 @@ __global__ void __launch_bounds__(TC_THREADS) tcconv_kernel(const __grid_constan
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) tmem_dealloc(tmem_base, 2 * NCOLS);
+    if (warp == EW) tmem_dealloc(tmem_base, 2 * NCOLS);
 }
 
 // ------------------------------------------------------------------------------------------ pack kernel
@@ -369,6 +437,8 @@ int tc_build_layer(TcLayer &L, int mode, int cin, int cout, int k, int crop, int
                 L.bias[(size_t)g * nout + n] = (bias && bias[g]) ? bias[g][co] : 0.f;
             }
     }
+    L.sched_taps = (cin == 8) ? npairs : ntaps;
+    L.sched_nq = (cin == 8) ? 0 : nq;
     L.mma.clear();
     if (cin == 8) {
         for (int jp = 0; jp < npairs; ++jp) L.mma.push_back(TcMma{2 * jp, 0, 1, jp});
@@ -385,15 +455,35 @@ int tc_out_len(const TcLayer &L, int T_in, int pool) {
     return pool == 2 ? (T_conv + 1) / 2 : T_conv;
 }
 
-template <int NOUT, int SPLIT>
+// CTAs per SM for a layer: as many (<= 4) as leave every CTA a >= 2-stage ring and 2 TMEM accumulators.
+constexpr int tc_occupancy(size_t w_bytes, size_t a_bytes, int ncols2) {
+    for (int o = 4; o > 1; --o) {
+        const size_t share = (size_t)224 * 1024 / o - 3072;  // per CTA: 1 KB reserved by the driver + static shared memory
+        if (o * ncols2 > 512 || w_bytes + 2 * a_bytes > share) continue;
+        return o;
+    }
+    return 1;
+}
+constexpr size_t tc_up128(size_t v) { return (v + 127) & ~(size_t)127; }
+// epilogue warps of a compile-time layer shape: 8 when at most two CTAs share an SM
+template <int NOUT, int SPLIT, int NTAPS, int NQ>
+constexpr int tc_epi_warps() {
+    constexpr int blocks = NQ == 0 ? NTAPS : NTAPS * NQ;
+    constexpr int cin8 = NQ == 0 ? 1 : 2 * NQ;
+    constexpr int rows = 128 + (NQ == 0 ? 2 * NTAPS - 1 : NTAPS - 1);
+    return tc_occupancy(tc_up128((size_t)blocks * SPLIT * 2 * NOUT * 16), tc_up128((size_t)SPLIT * cin8 * rows * 16),
+                        2 * (NOUT < 32 ? 32 : NOUT)) <= 2 ? 8 : 4;
+}
+
+template <int NOUT, int SPLIT, int NTAPS, int NQ, int EW>
 static int launch_tc(const TcP &p, dim3 grid, size_t smem, cudaStream_t s) {
-    auto kern = tcconv_kernel<NOUT, SPLIT>;
+    auto kern = tcconv_kernel<NOUT, SPLIT, NTAPS, NQ, EW>;
     static size_t attr = 0;
     if (smem > attr) {
         VP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = smem;
     }
-    kern<<<grid, TC_THREADS, smem, s>>>(p);
+    kern<<<grid, 32 * (EW + 4), smem, s>>>(p);
     VP_LAUNCH_CHECK();
     return VP_OK;
 }
@@ -455,6 +545,12 @@ int tc_launch(const TcLayer &L, const TcIO &io, cudaStream_t s) {
     p.y_ss = io.y_ss;
     p.y_cs = io.y_cs;
     p.cout_cl = io.cout_cl;
+    p.post_scale = io.post_scale;
+    p.post_shift = io.post_shift;
+    p.res = io.res;
+    p.y32 = io.y32;
+    VP_REQUIRE(!(io.res || io.y32) || (L.ph == 1 && io.pool == 1 && L.cout % 8 == 0 && L.groups == 1), VP_ERR_UNSUPPORTED,
+               "tc conv: residual / fp32 second output need a direct, un-pooled, single-group layer");
     VP_REQUIRE(!(io.pool == 2 && L.ph == 2), VP_ERR_UNSUPPORTED, "tc conv: pooling with polyphase output is not supported");
     const int64_t rows = (int64_t)io.NS * Tp;
     const int64_t n_tiles = (rows + 127) / 128;
@@ -464,22 +560,38 @@ int tc_launch(const TcLayer &L, const TcIO &io, cudaStream_t s) {
     // ring depth / residency: several CTAs per SM (one MMA issuer each) when >= 2 stages fit in the share
     const size_t kFull = 224 * 1024;
     const int ncols2 = 2 * (L.nout < 32 ? 32 : L.nout);
-    int occ = 1, stages = 0;
-    for (int o = 4; o >= 1; --o) {
-        const size_t share = kFull / o - 1024;  // 1 KB per CTA reserved by the driver
-        if (o > 1 && (o * ncols2 > 512 || w_bytes + 2 * a_bytes > share)) continue;
-        VP_REQUIRE(w_bytes + a_bytes <= share, VP_ERR_UNSUPPORTED, "tc conv: %zu bytes of shared memory exceed the SM", w_bytes + a_bytes);
-        occ = o;
-        stages = (int)std::min<size_t>(TC_MAX_STAGES, (share - w_bytes) / a_bytes);
-        break;
-    }
+    const int occ = tc_occupancy(w_bytes, a_bytes, ncols2);
+    const size_t share = kFull / occ - 3072;
+    VP_REQUIRE(w_bytes + a_bytes <= share, VP_ERR_UNSUPPORTED, "tc conv: %zu bytes of shared memory exceed the SM", w_bytes + a_bytes);
+    const int stages = (int)std::min<size_t>(TC_MAX_STAGES, (share - w_bytes) / a_bytes);
     p.n_stages = stages;
     const size_t smem = w_bytes + (size_t)stages * a_bytes;
     int64_t ctas = (148 * occ + L.groups - 1) / L.groups;
     ctas = std::max<int64_t>(1, std::min<int64_t>(ctas, n_tiles));
     dim3 grid((unsigned)ctas, L.groups);
+    // compile-time MMA schedules for the layer shapes of the EQTransformer (N, taps | tap pairs, channel pairs)
+    static const bool generic_only = getenv("VP_TC_GENERIC") && atoi(getenv("VP_TC_GENERIC")) != 0;
+    const int st = L.sched_taps, sq = L.sched_nq;
+#define VP_TC_FIXED(N, T, Q)                                                                      \
+    if (!generic_only && !p.dbg && L.nout == N && st == T && sq == Q) {                           \
+        if (L.split == 2) return launch_tc<N, 2, T, Q, tc_epi_warps<N, 2, T, Q>()>(p, grid, smem, s); \
+        return launch_tc<N, 1, T, Q, tc_epi_warps<N, 1, T, Q>()>(p, grid, smem, s);               \
+    }
+    VP_TC_FIXED(16, 6, 0);   // encoder.convs.0 (3 -> 8, k11), heads (8 -> 1, k11)
+    VP_TC_FIXED(16, 5, 0);   // encoder.convs.1 (8 -> 16, k9)
+    VP_TC_FIXED(16, 7, 1);   // encoder.convs.2 (16 -> 16, k7), decoder.convs.6 polyphase
+    VP_TC_FIXED(32, 7, 1);   // encoder.convs.3 (16 -> 32, k7)
+    VP_TC_FIXED(32, 5, 2);   // encoder.convs.4 (32 -> 32, k5), decoder.convs.4 polyphase
+    VP_TC_FIXED(64, 5, 2);   // encoder.convs.5 (32 -> 64, k5), decoder.convs.3 polyphase
+    VP_TC_FIXED(64, 3, 4);   // encoder.convs.6, res-CNN k3 (64 -> 64)
+    VP_TC_FIXED(64, 2, 4);   // res-CNN k2 (64 -> 64)
+    VP_TC_FIXED(128, 3, 1);  // decoder.convs.0 polyphase (16 -> 2 x 64)
+    VP_TC_FIXED(128, 3, 4);  // decoder.convs.1 polyphase (64 -> 2 x 64)
+    VP_TC_FIXED(32, 5, 4);   // decoder.convs.2 (64 -> 32, k5, loader-side up-sampling)
+    VP_TC_FIXED(32, 5, 1);   // decoder.convs.5 polyphase (16 -> 2 x 16)
+#undef VP_TC_FIXED
 #define VP_TC_CASE(N, S) \
-    if (L.nout == N && L.split == S) return launch_tc<N, S>(p, grid, smem, s)
+    if (L.nout == N && L.split == S) return launch_tc<N, S, 0, 0, 4>(p, grid, smem, s)
     VP_TC_CASE(16, 2);
     VP_TC_CASE(32, 2);
     VP_TC_CASE(64, 2);

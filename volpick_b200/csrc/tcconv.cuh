@@ -38,6 +38,10 @@ struct TcP {
     void *y;
     int64_t y_split, y_gs, y_ss, y_cs;
     int cout_cl;
+    // epilogue extras (single group, direct, un-pooled layers: the res-CNN stack)
+    const float *post_scale, *post_shift;  // [NOUT]: 16-bit output = relu(v * scale + shift) (pre-activation BN + ReLU of the next conv)
+    const float *res;                      // fp32 row-major [NS][T_out][cout] added to v
+    float *y32;                            // second output: v as fp32 row-major [NS][T_out][cout]
 };
 
 // Host-side description of one layer: packed weight blocks + MMA schedule.
@@ -49,6 +53,7 @@ struct TcLayer {
     int crop = 0;      // samples dropped at the end of the up-sampled signal
     int split = 2;     // 2: fp16 hi/lo operands, 3 MMAs per K step (fp32-equivalent); 1: single bf16 pass
     int row0 = 0, halo = 0, n_blocks = 0, groups = 1;
+    int sched_taps = 0, sched_nq = 0;  // taps (tap pairs when sched_nq == 0) and 16-channel pairs of the MMA schedule
     std::vector<TcMma> mma;
     std::vector<uint16_t> blocks;  // [G][n_blocks][split][2][nout][8]
     std::vector<float> bias;       // [G][nout]
@@ -72,6 +77,8 @@ struct TcIO {
     void *y;
     int64_t y_split, y_gs, y_ss, y_cs;
     int cout_cl;
+    const float *post_scale = nullptr, *post_shift = nullptr, *res = nullptr;
+    float *y32 = nullptr;
 };
 int tc_out_len(const TcLayer &L, int T_in, int pool);
 int tc_launch(const TcLayer &L, const TcIO &io, cudaStream_t s);
