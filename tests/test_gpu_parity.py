@@ -160,9 +160,13 @@ def test_eqt_forward_tensor_core(eqt, sd_eqt, precision, atol):
     taps = {}
     nets.eqtransformer_forward(sd_eqt, torch.from_numpy(x), taps)
     e6 = eqt.forward_tap(xd, "enc6", precision=precision).cpu().numpy().reshape(taps["enc6"].shape)
+    r6 = eqt.forward_tap(xd, "res6", precision=precision).cpu().numpy().reshape(taps["res6"].shape)
     print(f"{precision}: enc6 max|diff| = {np.abs(e6 - taps['enc6'].numpy()).max():.3e} (max|ref| {taps['enc6'].abs().max():.2f}); "
+          f"res6 max|diff| = {np.abs(r6 - taps['res6'].numpy()).max():.3e} (max|ref| {taps['res6'].abs().max():.2f}); "
           f"probabilities max|diff| = {np.abs(got - ref).max():.3e}")
     assert ref.max() > 0.5
+    if precision == "f16x3":  # the res-CNN stack on the tensor cores (k = 3 and right-padded k = 2 convs, fp32 residual stream)
+        assert float(np.abs(r6 - taps["res6"].numpy()).max()) <= 1e-4 * float(taps["res6"].abs().max())
     assert float(np.abs(got - ref).max()) <= atol
 
 

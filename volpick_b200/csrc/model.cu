@@ -207,6 +207,7 @@ struct vp_model {
     // tensor-core (tcgen05) weight sets: [0] = fp16 hi/lo split (f16x3), [1] = bf16
     struct TcSet {
         TcLayer enc[7], dec[7], head;
+        TcLayer res1[7], res2[7];  // res-CNN convs (BatchNorm + ReLU of their inputs live in the producer's epilogue)
         uint16_t *d_w = nullptr;
         float *d_b = nullptr;
         bool ready = false;
@@ -219,6 +220,10 @@ static int upload_tc(vp_model::TcSet &ts) {
     for (int i = 0; i < 7; ++i) layers.push_back(&ts.enc[i]);
     for (int i = 0; i < 7; ++i) layers.push_back(&ts.dec[i]);
     layers.push_back(&ts.head);
+    for (int i = 0; i < 7; ++i) {
+        layers.push_back(&ts.res1[i]);
+        layers.push_back(&ts.res2[i]);
+    }
     size_t nw = 0, nb = 0;
     for (TcLayer *L : layers) {
         L->w_off = (int64_t)nw;
@@ -254,11 +259,13 @@ static int build_eqt(vp_model *m, Cursor &cur, Packed &pk) {
         eB[i] = b;
         m->enc[i] = pack_conv(pk, W, b, nullptr, kEncC[i + 1], kEncC[i], kEncK[i]);
     }
+    const float *rW[7][2], *rB[7][2];
     for (int i = 0; i < 7; ++i) {
         BN n1 = take_bn(cur, 64);
         const float *W1 = cur.take(64 * 64 * kResK[i]), *b1 = cur.take(64);
         BN n2 = take_bn(cur, 64);
         const float *W2 = cur.take(64 * 64 * kResK[i]), *b2 = cur.take(64);
+        rW[i][0] = W1, rB[i][0] = b1, rW[i][1] = W2, rB[i][1] = b2;
         m->res[i].n1 = pack_affine(pk, n1);
         m->res[i].c1 = pack_conv(pk, W1, b1, nullptr, 64, 64, kResK[i]);
         m->res[i].n2 = pack_affine(pk, n2);
@@ -357,6 +364,12 @@ static int build_eqt(vp_model *m, Cursor &cur, Packed &pk) {
         const float *wl[3] = {hW[0], hW[1], hW[2]}, *bl[3] = {hB[0], hB[1], hB[2]};
         int rc = tc_build_layer(ts.head, TC_DIRECT, 8, 1, 11, 0, split, 3, wl, bl);
         if (rc != VP_OK) return rc;
+        for (int i = 0; i < 7; ++i)
+            for (int j = 0; j < 2; ++j) {  // k = 3: pad (1, 1); k = 2: SeisBench pads one zero on the right only
+                const float *w1[1] = {rW[i][j]}, *b1[1] = {rB[i][j]};
+                rc = tc_build_layer(j == 0 ? ts.res1[i] : ts.res2[i], TC_DIRECT, 64, 64, kResK[i], 0, split, 1, w1, b1, kResK[i] == 3 ? 1 : 0);
+                if (rc != VP_OK) return rc;
+            }
         // fused decoder tail: (1, 8, 11) head weights -> [c * 11 + k]; tile = 47 / 75 rows of the 375-sample level
         float head_w[3][88], head_b[3];
         for (int g = 0; g < 3; ++g) {
@@ -528,6 +541,7 @@ static int run_eqt(Runner &r, const float *x, float *y, Arena &ar) {
     }
     const int64_t split16 = B * big16;  // elements between the hi and lo planes
     float *r0 = ar.take(B * 64 * T), *r1 = ar.take(B * 64 * T), *r2 = ar.take(B * 64 * T);
+    float *xres = tc ? ar.take(B * 64 * T) : nullptr;  // tensor-core path: residual stream, fp32 row-major [B][T][64]
     float *lo = ar.take(B * 32 * T);
     float *s0 = ar.take(B * 16 * T), *s1 = ar.take(B * 16 * T);
     float *din = ar.take(3 * B * 16 * T);  // [group][B][16][T]: decoder inputs
@@ -558,6 +572,7 @@ static int run_eqt(Runner &r, const float *x, float *y, Arena &ar) {
         // ---- encoder on the tensor cores: x (B,3,L) fp32 -> channel-last 16-bit [B][L][8] -> 7 x (conv, ReLU, pool)
         if (r.go()) r.rc = launch_pack_cl16(x, 3 * (int64_t)L, L, (int)B, 3, L, split, Q16, split16, 1, r.s);
         const uint16_t *cur16 = Q16;
+        const bool enc6_tap = r.stop_name && std::strcmp(r.stop_name, "enc6") == 0;
         for (int i = 0; i < 7; ++i) {
             const TcLayer &tl = ts.enc[i];
             if (r.go()) {
@@ -571,7 +586,20 @@ static int run_eqt(Runner &r, const float *x, float *y, Arena &ar) {
                 io.b_dev = ts.d_b + tl.b_off;
                 io.act = ACT_RELU;
                 io.pool = 2;
-                if (i == 6) {  // last encoder stage feeds the fp32 bottleneck: (B, 64, T) channel-first
+                if (i == 6 && !enc6_tap) {
+                    // last encoder stage feeds the res-CNN stack: fp32 residual stream (row-major) + the 16-bit
+                    // relu(bn1(x)) operand of res_cnn_stack.members.0.conv1
+                    io.out_fmt = 0;
+                    io.y = pp16[0];
+                    io.y_split = split16;
+                    io.y_gs = 0;
+                    io.y_ss = 0;
+                    io.y_cs = 0;
+                    io.cout_cl = 64;
+                    io.y32 = xres;
+                    io.post_scale = r.W(m->res[0].n1.scale);
+                    io.post_shift = r.W(m->res[0].n1.shift);
+                } else if (i == 6) {  // debug tap: (B, 64, T) channel-first fp32
                     io.out_fmt = 1;
                     io.y = r0;
                     io.y_split = 0;
@@ -597,7 +625,63 @@ static int run_eqt(Runner &r, const float *x, float *y, Arena &ar) {
     // ---- res-CNN stack: x in ra; tmp r1; out rb
     static const char *res_names[7] = {"res0", "res1", "res2", "res3", "res4", "res5", "res6"};
     float *ra = r0, *rb = r2;
-    for (int i = 0; i < 7; ++i) {
+    if (tc) {
+        // tensor cores: conv1 reads relu(bn1(x)) (16-bit, written by the previous epilogue) and writes relu(bn2(y));
+        // conv2 adds the fp32 residual stream in place and writes the next block's relu(bn1(x))
+        for (int i = 0; i < 7 && r.go(); ++i) {
+            TcIO io;
+            io.x = pp16[0];
+            io.x_split = split16;
+            io.x_gs = 0;
+            io.T_in = T;
+            io.NS = (int)B;
+            io.w_dev = ts.d_w + ts.res1[i].w_off;
+            io.b_dev = ts.d_b + ts.res1[i].b_off;
+            io.act = ACT_NONE;
+            io.pool = 1;
+            io.out_fmt = 0;
+            io.y = pp16[1];
+            io.y_split = split16;
+            io.y_gs = io.y_ss = io.y_cs = 0;
+            io.cout_cl = 64;
+            io.post_scale = r.W(m->res[i].n2.scale);
+            io.post_shift = r.W(m->res[i].n2.shift);
+            r.rc = tc_launch(ts.res1[i], io, r.s);
+            if (r.rc != VP_OK) break;
+            TcIO io2;
+            io2.x = pp16[1];
+            io2.x_split = split16;
+            io2.x_gs = 0;
+            io2.T_in = T;
+            io2.NS = (int)B;
+            io2.w_dev = ts.d_w + ts.res2[i].w_off;
+            io2.b_dev = ts.d_b + ts.res2[i].b_off;
+            io2.act = ACT_NONE;
+            io2.pool = 1;
+            io2.res = xres;
+            io2.y_gs = 0;
+            if (i < 6) {
+                io2.out_fmt = 0;
+                io2.y = pp16[0];
+                io2.y_split = split16;
+                io2.y_ss = io2.y_cs = 0;
+                io2.cout_cl = 64;
+                io2.y32 = xres;
+                io2.post_scale = r.W(m->res[i + 1].n1.scale);
+                io2.post_shift = r.W(m->res[i + 1].n1.shift);
+            } else {  // stack output -> BiLSTM input, fp32 (B, 64, T) channel-first
+                io2.out_fmt = 1;
+                io2.y = ra;
+                io2.y_split = 0;
+                io2.y_ss = 64 * (int64_t)T;
+                io2.y_cs = T;
+                io2.cout_cl = 0;
+            }
+            r.rc = tc_launch(ts.res2[i], io2, r.s);
+        }
+        if (r.tap("res6", ra, B * 64 * T)) return r.rc;
+    }
+    for (int i = 0; i < 7 && !tc; ++i) {
         const int k = kResK[i];
         const int pad = (k == 3) ? 1 : 0;  // k == 2: right-pad one zero == out-of-range reads as 0
         r.conv(m->res[i].c1, 1, 1, 1, ACT_NONE, &m->res[i].n1, nullptr, 0, ra, 64 * T, 0, T, T, pad, T, T, r1, 64 * T, 0,

@@ -249,19 +249,11 @@ __global__ void __launch_bounds__(32 * (EW + 4), EW == 8 ? 2 : 4) tcconv_kernel(
                         const bool ok = st && t_out < p.T_out;
                         if (p.res != nullptr && ok) {  // residual stream, fp32 row-major [seq][t][cout]
                             const float4 *rp = reinterpret_cast<const float4 *>(p.res + (orow0 + phi) * p.cout + c0);
-                            const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+                            const float4 r0 = rp[0], r1 = rp[1];  // plain loads: y32 may alias res (in-place residual stream)
                             w8[0] += r0.x, w8[1] += r0.y, w8[2] += r0.z, w8[3] += r0.w;
                             w8[4] += r1.x, w8[5] += r1.y, w8[6] += r1.z, w8[7] += r1.w;
                         }
-                        if (p.y32 != nullptr && ok) {  // second output: the un-activated fp32 value, row-major
-                            float4 *yp = reinterpret_cast<float4 *>(p.y32 + (orow0 + phi) * p.cout + c0);
-                            yp[0] = make_float4(w8[0], w8[1], w8[2], w8[3]);
-                            yp[1] = make_float4(w8[4], w8[5], w8[6], w8[7]);
-                        }
-                        if (p.post_scale != nullptr) {  // pre-activation BatchNorm + ReLU of the next conv
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) w8[i] = fmaxf(fmaf(w8[i], s_psc[n0 + i], s_psh[n0 + i]), 0.f);
-                        } else if (p.act == ACT_RELU) {
+                        if (p.act == ACT_RELU) {
 #pragma unroll
                             for (int i = 0; i < 8; ++i) w8[i] = fmaxf(w8[i], 0.f);
                         } else if (p.act == ACT_SIGMOID) {
@@ -274,6 +266,15 @@ __global__ void __launch_bounds__(32 * (EW + 4), EW == 8 ? 2 : 4) tcconv_kernel(
                                 const float mine = row_ok ? w8[i] : -1e10f;  // SeisBench pads odd lengths with -1e10 before MaxPool1d(2)
                                 w8[i] = fmaxf(mine, __shfl_xor_sync(0xffffffffu, mine, 1));
                             }
+                        }
+                        if (p.y32 != nullptr && ok) {  // second output: the layer's fp32 value, row-major [seq][t][cout]
+                            float4 *yp = reinterpret_cast<float4 *>(p.y32 + (orow0 + phi) * p.cout + c0);
+                            yp[0] = make_float4(w8[0], w8[1], w8[2], w8[3]);
+                            yp[1] = make_float4(w8[4], w8[5], w8[6], w8[7]);
+                        }
+                        if (p.post_scale != nullptr) {  // pre-activation BatchNorm + ReLU of the next conv, applied to the main output
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) w8[i] = fmaxf(fmaf(w8[i], s_psc[n0 + i], s_psh[n0 + i]), 0.f);
                         }
                         if (!ok) continue;
                         if (p.out_fmt == 0) {
@@ -361,7 +362,7 @@ static void to16(float w, int split, uint16_t &hi, uint16_t &lo) {
 }
 
 int tc_build_layer(TcLayer &L, int mode, int cin, int cout, int k, int crop, int split, int groups,
-                   const float *const *weights, const float *const *bias) {
+                   const float *const *weights, const float *const *bias, int pad_left) {
     VP_REQUIRE(cin % 8 == 0 && (cin == 8 || cin % 16 == 0), VP_ERR_UNSUPPORTED, "tc conv: cin %d unsupported", cin);
     VP_REQUIRE(!(mode == TC_POLYPHASE && (cin == 8 || crop != 0)), VP_ERR_UNSUPPORTED, "tc conv: polyphase needs cin>=16, no crop");
     L = TcLayer();
@@ -378,7 +379,8 @@ int tc_build_layer(TcLayer &L, int mode, int cin, int cout, int k, int crop, int
     nout = nout <= 16 ? 16 : nout <= 32 ? 32 : nout <= 64 ? 64 : 128;
     VP_REQUIRE(L.ph * coutp <= 128, VP_ERR_UNSUPPORTED, "tc conv: %d output columns exceed 128", L.ph * coutp);
     L.nout = nout;
-    const int p = k / 2;
+    const int p = (pad_left >= 0) ? pad_left : k / 2;  // zeros on the left of the input ('same' conv: k / 2)
+    VP_REQUIRE(pad_left < 0 || mode == TC_DIRECT, VP_ERR_UNSUPPORTED, "tc conv: explicit left padding needs the direct form");
     const int nq = cin / 16;
     // effective taps: weff[phi][tap][co][ci]
     int ntaps, o_min;
@@ -549,8 +551,8 @@ int tc_launch(const TcLayer &L, const TcIO &io, cudaStream_t s) {
     p.post_shift = io.post_shift;
     p.res = io.res;
     p.y32 = io.y32;
-    VP_REQUIRE(!(io.res || io.y32) || (L.ph == 1 && io.pool == 1 && L.cout % 8 == 0 && L.groups == 1), VP_ERR_UNSUPPORTED,
-               "tc conv: residual / fp32 second output need a direct, un-pooled, single-group layer");
+    VP_REQUIRE(!(io.res || io.y32 || io.post_scale) || (L.ph == 1 && L.cout % 8 == 0 && L.groups == 1 && (!io.res || io.pool == 1)),
+               VP_ERR_UNSUPPORTED, "tc conv: residual / post-affine / fp32 second output need a direct single-group layer");
     VP_REQUIRE(!(io.pool == 2 && L.ph == 2), VP_ERR_UNSUPPORTED, "tc conv: pooling with polyphase output is not supported");
     const int64_t rows = (int64_t)io.NS * Tp;
     const int64_t n_tiles = (rows + 127) / 128;

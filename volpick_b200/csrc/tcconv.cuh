@@ -64,7 +64,7 @@ enum { TC_DIRECT = 0, TC_POLYPHASE = 1, TC_DIRECT_UPS = 2 };
 
 // weights: per group (cout, cin, k) fp32 with BatchNorm already folded; bias per group (cout) or nullptr
 int tc_build_layer(TcLayer &L, int mode, int cin, int cout, int k, int crop, int split, int groups,
-                   const float *const *weights, const float *const *bias);
+                   const float *const *weights, const float *const *bias, int pad_left = -1);
 
 struct TcIO {
     const uint16_t *x;
