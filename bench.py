@@ -199,7 +199,7 @@ def run_ours(args):
     cls = vb.EQTransformer if kind == "eqtransformer" else vb.PhaseNet
     model = cls.from_pretrained("volpick").cuda(local_rank)
     lib = _lib.load()
-    cfg = dict(CONFIGS[kind], precision=args.precision)
+    cfg = dict(CONFIGS[kind], precision=args.precision, chunk_windows=args.chunk)
     argdict = model._argdict(cfg)
     thresholds = model._thresholds(argdict)
     thresholds[0] = 0.3 if kind == "eqtransformer" else thresholds[0]
@@ -266,7 +266,8 @@ def run_ours(args):
     # ---- per-stage device timings (rank 0) for the roofline objects ---------------------------
     stages = {}
     if rank == 0:
-        stages = stage_timings(model, lib, recs_dev[0], argdict, thresholds, kind, precision=_lib.PRECISION[args.precision])
+        stages = stage_timings(model, lib, recs_dev[0], argdict, thresholds, kind, precision=_lib.PRECISION[args.precision],
+                               chunk=args.chunk)
     peaks = measured_peaks()
     line = None
     if rank == 0:
@@ -302,7 +303,7 @@ def run_ours(args):
     return line
 
 
-def stage_timings(model, lib, rec_dev, argdict, thresholds, kind, reps: int = 3, precision: int = 0):
+def stage_timings(model, lib, rec_dev, argdict, thresholds, kind, reps: int = 3, precision: int = 0, chunk: int = 0):
     """CUDA-event timings of the four stages on the current stream, through the stage-level C ABI."""
     import torch
 
@@ -316,7 +317,7 @@ def stage_timings(model, lib, rec_dev, argdict, thresholds, kind, reps: int = 3,
     cnt = C.c_int64(0)
     lib.vp_window_starts(n, L, ov, starts.ctypes.data, nwin, C.byref(cnt))
     d_starts = torch.from_numpy(starts).cuda()
-    chunk = 1024 if kind == "eqtransformer" else 4096
+    chunk = chunk if chunk > 0 else 4096
     d_x = torch.empty((chunk, 3, L), dtype=torch.float32, device="cuda")
     d_y = torch.empty((nwin, 3, L), dtype=torch.float32, device="cuda")
     d_ann = torch.empty((3, n), dtype=torch.float32, device="cuda")
@@ -389,6 +390,7 @@ def main():
                     help="f16x3 (default): tcgen05 on fp16 hi/lo split operands, fp32 accumulate -- the exact mode (<= 1e-4 vs the oracle); "
                          "fp32: CUDA-core FFMA; bf16: single-pass tensor cores (reported separately, looser tolerance)")
     ap.add_argument("--samples", type=int, default=N_DAY, help="samples per record (default: one station-day)")
+    ap.add_argument("--chunk", type=int, default=0, help="windows per forward launch group (0: library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=0,
                     help="profiling aid (ncu): run this many device-resident steps and exit without timing")

