@@ -74,7 +74,7 @@ class ClockSampler(threading.Thread):
                 for bit, nm in names.items():
                     if mask & bit:
                         self.reasons.add(nm)
-                self._stop_evt.wait(0.2)
+                self._stop_evt.wait(0.02)
         except Exception:
             self._fallback()
 
@@ -91,7 +91,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(nm)
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.02)
 
     def stop(self):
         self._stop_evt.set()

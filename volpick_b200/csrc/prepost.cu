@@ -10,6 +10,7 @@
 #include <math_constants.h>
 
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -245,6 +246,127 @@ __global__ void __launch_bounds__(256) stack_kernel(const float *__restrict__ y,
     }
 }
 
+// Vectorised K9 for the compile-time coverages (3, 13): one thread = 4 consecutive output samples, all labels.
+//  * window range [first, hi] of the group from a closed-form guess (n / stride) that is then VERIFIED against
+//    starts[] and corrected, so any sorted starts array gives the same result as the binary search above;
+//  * slots are visited in slot order k = i % COV (consecutive windows map to distinct slots), which is the
+//    order np.nanmean sums in; a group covered by more than COV windows (the reference would overwrite slots)
+//    takes the generic per-sample path;
+//  * 16-byte loads of y when the window offset is 4-aligned (regular strides), scalar loads otherwise (tail window).
+template <int COV>
+__global__ void __launch_bounds__(256) stack4_kernel(const float *__restrict__ y, const int64_t *__restrict__ starts,
+                                                     int nwin, int L, int nlab, int stride, int b0, int b1, int mode,
+                                                     float *__restrict__ out, int64_t pred_len) {
+    const int64_t n0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (n0 >= pred_len) return;
+    const int64_t n3 = (n0 + 3 < pred_len) ? n0 + 3 : pred_len - 1;
+    // hi = last window with start <= n3; first = first window with start + L > n0
+    int hi = (int)((n3 / stride < nwin - 1) ? n3 / stride : nwin - 1);
+    while (hi + 1 < nwin && __ldg(starts + hi + 1) <= n3) ++hi;
+    while (hi >= 0 && __ldg(starts + hi) > n3) --hi;
+    int first = (int)((n0 - L + 1 > 0) ? (n0 - L + stride) / stride : 0);
+    if (first > hi + 1) first = hi + 1;
+    while (first > 0 && __ldg(starts + first - 1) + L > n0) --first;
+    while (first <= hi && __ldg(starts + first) + L <= n0) ++first;
+    const bool vec_out = ((pred_len & 3) == 0) && (n0 + 3 < pred_len);
+    if (hi - first + 1 > COV) {
+        // more covering windows than slots: reproduce the reference's slot overwrite per sample
+        for (int e = 0; e < 4 && n0 + e < pred_len; ++e) {
+            const int64_t n = n0 + e;
+            for (int c = 0; c < nlab; ++c) {
+                float slot[COV];
+#pragma unroll
+                for (int k = 0; k < COV; ++k) slot[k] = CUDART_NAN_F;
+                for (int i = first; i <= hi; ++i) {
+                    const int64_t off = n - __ldg(starts + i);
+                    if (off < 0 || off >= L) continue;
+                    const float val = (off < b0 || off >= L - b1) ? CUDART_NAN_F : __ldg(y + ((int64_t)i * nlab + c) * L + off);
+                    const int sl = i % COV;
+#pragma unroll
+                    for (int k = 0; k < COV; ++k)
+                        if (k == sl) slot[k] = val;
+                }
+                float res;
+                if (mode == VP_STACK_AVG) {
+                    int cnt = 0;
+#pragma unroll
+                    for (int k = 0; k < COV; ++k) {
+                        if (!isnan(slot[k])) ++cnt; else slot[k] = 0.f;
+                    }
+                    const float tot = 0.0f + np_pairwise_sum<COV, true>(slot, COV);
+                    res = cnt ? __fdiv_rn(tot, (float)cnt) : CUDART_NAN_F;
+                } else {
+                    res = CUDART_NAN_F;
+#pragma unroll
+                    for (int k = 0; k < COV; ++k)
+                        if (!isnan(slot[k]) && (isnan(res) || slot[k] > res)) res = slot[k];
+                }
+                out[(int64_t)c * pred_len + n] = res;
+            }
+        }
+        return;
+    }
+    const int fm = first % COV;
+    // per slot: window index and offset of sample n0 inside it (same for all labels)
+    int widx[COV];
+    int woff[COV];
+#pragma unroll
+    for (int k = 0; k < COV; ++k) {
+        const int i = first + ((k - fm + COV) % COV);
+        widx[k] = (i <= hi) ? i : -1;
+        woff[k] = (i <= hi) ? (int)(n0 - __ldg(starts + i)) : 0;
+    }
+    for (int c = 0; c < nlab; ++c) {
+        float slot[4][COV];
+#pragma unroll
+        for (int k = 0; k < COV; ++k) {
+            float v[4] = {CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F};
+            if (widx[k] >= 0) {
+                const int off = woff[k];
+                const float *row = y + ((int64_t)widx[k] * nlab + c) * L;
+                // the 4 samples that are inside the window and outside the blinded margins
+                if (off >= b0 && off + 3 < L - b1 && ((off & 3) == 0) && ((L & 3) == 0)) {
+                    const float4 q = __ldg(reinterpret_cast<const float4 *>(row + off));
+                    v[0] = q.x, v[1] = q.y, v[2] = q.z, v[3] = q.w;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int o = off + e;
+                        if (o >= b0 && o < L - b1 && o >= 0 && o < L) v[e] = __ldg(row + o);
+                    }
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) slot[e][k] = v[e];
+        }
+        float res[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (mode == VP_STACK_AVG) {
+                int cnt = 0;
+#pragma unroll
+                for (int k = 0; k < COV; ++k) {
+                    if (!isnan(slot[e][k])) ++cnt; else slot[e][k] = 0.f;
+                }
+                const float tot = 0.0f + np_pairwise_sum<COV, true>(slot[e], COV);
+                res[e] = cnt ? __fdiv_rn(tot, (float)cnt) : CUDART_NAN_F;
+            } else {
+                float r = CUDART_NAN_F;
+#pragma unroll
+                for (int k = 0; k < COV; ++k)
+                    if (!isnan(slot[e][k]) && (isnan(r) || slot[e][k] > r)) r = slot[e][k];
+                res[e] = r;
+            }
+        }
+        float *ob = out + (int64_t)c * pred_len + n0;
+        if (vec_out) {
+            *reinterpret_cast<float4 *>(ob) = make_float4(res[0], res[1], res[2], res[3]);
+        } else {
+            for (int e = 0; e < 4 && n0 + e < pred_len; ++e) ob[e] = res[e];
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------ trim
 __global__ void nan_bounds_init_kernel(int64_t *bounds, int nlab, int64_t pred_len) {
     const int i = threadIdx.x;
@@ -407,7 +529,17 @@ extern "C" int vp_stack(const float *y, const int64_t *starts, int64_t n_windows
 #define VP_STACK_LAUNCH(COV, EXACT)                                                                              \
     stack_kernel<COV, EXACT><<<grid, 256, 0, s>>>(y, starts, n_windows, (int)in_samples, n_labels, (int)cov, blind0, \
                                                   blind1, mode, out, pred_len)
-    if (cov == 3) VP_STACK_LAUNCH(3, true);
+    const int64_t stride = in_samples - overlap;
+    const bool small = n_windows < (1LL << 30) && in_samples < (1LL << 30) && blind0 <= in_samples && blind1 <= in_samples;
+    const unsigned grid4 = (unsigned)((pred_len + 1023) / 1024);
+    static const bool scalar_only = getenv("VP_STACK_SCALAR") && atoi(getenv("VP_STACK_SCALAR")) != 0;  // debugging aid
+    if (cov == 3 && small && !scalar_only)
+        stack4_kernel<3><<<grid4, 256, 0, s>>>(y, starts, (int)n_windows, (int)in_samples, n_labels, (int)stride, (int)blind0,
+                                               (int)blind1, mode, out, pred_len);
+    else if (cov == 13 && small && !scalar_only)
+        stack4_kernel<13><<<grid4, 256, 0, s>>>(y, starts, (int)n_windows, (int)in_samples, n_labels, (int)stride, (int)blind0,
+                                                (int)blind1, mode, out, pred_len);
+    else if (cov == 3) VP_STACK_LAUNCH(3, true);
     else if (cov == 13) VP_STACK_LAUNCH(13, true);
     else if (cov <= 16) VP_STACK_LAUNCH(16, false);
     else VP_STACK_LAUNCH(STACK_MAXCOV, false);

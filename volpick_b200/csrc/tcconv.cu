@@ -177,8 +177,10 @@ __global__ void __launch_bounds__(32 * (EW + 4), EW == 8 ? 2 : 4) tcconv_kernel(
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * NCOLS);
             if (elect_one()) {
                 if constexpr (NTAPS > 0) {
+                    if (p.dbg & 2) umma_f16(d_tmem, desc_hi | (uint64_t)(sA16 + p.term_a[0]), desc_hi | (uint64_t)(sB16 + p.term_b[0]), idesc, 0u); else {
                     constexpr uint32_t ROWS = 128 + (NQ == 0 ? 2 * NTAPS - 1 : NTAPS - 1);  // == p.n_rows
                     umma_conv_tile<NOUT, SPLIT, NTAPS, NQ>(d_tmem, sA16, ROWS, sB16, idesc, 0u);
+                    }
                 } else {
                     umma_f16(d_tmem, desc_hi | (uint64_t)(sA16 + p.term_a[0]), desc_hi | (uint64_t)(sB16 + p.term_b[0]), idesc, 0u);
 #pragma unroll 4
@@ -575,7 +577,7 @@ int tc_launch(const TcLayer &L, const TcIO &io, cudaStream_t s) {
     static const bool generic_only = getenv("VP_TC_GENERIC") && atoi(getenv("VP_TC_GENERIC")) != 0;
     const int st = L.sched_taps, sq = L.sched_nq;
 #define VP_TC_FIXED(N, T, Q)                                                                      \
-    if (!generic_only && !p.dbg && L.nout == N && st == T && sq == Q) {                           \
+    if (!generic_only && L.nout == N && st == T && sq == Q) {                           \
         if (L.split == 2) return launch_tc<N, 2, T, Q, tc_epi_warps<N, 2, T, Q>()>(p, grid, smem, s); \
         return launch_tc<N, 1, T, Q, tc_epi_warps<N, 1, T, Q>()>(p, grid, smem, s);               \
     }
