@@ -344,7 +344,8 @@ def stage_timings(model, lib, rec_dev, argdict, thresholds, kind, reps: int = 3,
             _lib.check(lib.vp_slice_normalize(rec_dev.data_ptr(), 0, n, rec_dev.stride(0), d_starts.data_ptr() + 8 * w0, nw, L,
                                               0, 1 if kind == "eqtransformer" else 0, d_x.data_ptr(), stream))
             b.record()
-            _lib.check(lib.vp_forward(model._handle, d_x.data_ptr(), nw, d_y.data_ptr() + 4 * 3 * L * w0, ws.data_ptr(), ws_bytes, precision, stream))
+            _lib.check(lib.vp_forward_range(model._handle, d_x.data_ptr(), nw, d_y.data_ptr() + 4 * 3 * L * w0, ws.data_ptr(), ws_bytes, precision,
+                                            argdict["blinding"][0], L - argdict["blinding"][1], stream))
             c.record()
             evs.append((a, b, c))
         a, b, c = ev(), ev(), ev()

@@ -108,6 +108,11 @@ VP_API int vp_slice_normalize(const void *trace, int dtype, int64_t n_samples, i
 VP_API int64_t vp_forward_workspace_bytes(const vp_model *m, int64_t n_windows, int precision);
 VP_API int vp_forward(vp_model *m, const float *x, int64_t n_windows, float *y, void *workspace, int64_t workspace_bytes,
                int precision, void *stream);
+/* vp_forward for a caller that discards the first keep_lo and the samples from keep_hi on of every window
+ * (annotate_batch_post blinding, /root/reference/README.md:58): only y[:, :, keep_lo:keep_hi] is guaranteed to be
+ * written; work that only feeds the discarded samples may be skipped. */
+VP_API int vp_forward_range(vp_model *m, const float *x, int64_t n_windows, float *y, void *workspace,
+                            int64_t workspace_bytes, int precision, int64_t keep_lo, int64_t keep_hi, void *stream);
 /* Debug/parity: run the forward and copy the named intermediate activation (device->device) into
  * tap_out (capacity in floats); *tap_floats receives its size.  Names: see vp_forward_tap_names(). */
 VP_API int vp_forward_tap(vp_model *m, const float *x, int64_t n_windows, float *y, void *workspace,

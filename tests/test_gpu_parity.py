@@ -170,6 +170,25 @@ def test_eqt_forward_tensor_core(eqt, sd_eqt, precision, atol):
     assert float(np.abs(got - ref).max()) <= atol
 
 
+@pytest.mark.parametrize("precision", ["f16x3", "bf16", "fp32"])
+@pytest.mark.parametrize("lo,hi", [(500, 5500), (0, 6000), (496, 5505), (1234, 2345), (5999, 6000), (0, 1), (3000, 3000)])
+def test_forward_range_matches_full_forward(lib, eqt, precision, lo, hi):
+    """vp_forward_range (blinding-aware decoder tail): the kept samples are bit-identical to vp_forward's."""
+    x = torch.from_numpy(_windows("eqtransformer", 5, seed=23)).cuda()
+    full = torch.stack(eqt.forward(x, precision=precision), dim=1)
+    prec = _lib.PRECISION[precision]
+    y = torch.full((5, 3, 6000), -7.0, dtype=torch.float32, device="cuda")
+    need = _lib.check(lib.vp_forward_workspace_bytes(eqt._handle, 5, prec))
+    ws = torch.empty(need, dtype=torch.uint8, device="cuda")
+    _lib.check(lib.vp_forward_range(eqt._handle, C.c_void_p(x.data_ptr()), 5, C.c_void_p(y.data_ptr()), C.c_void_p(ws.data_ptr()),
+                                    need, prec, lo, hi, _stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(y[:, :, lo:hi], full[:, :, lo:hi])
+    with pytest.raises(_lib.VolpickError, match="bad sample range"):
+        _lib.check(lib.vp_forward_range(eqt._handle, C.c_void_p(x.data_ptr()), 5, C.c_void_p(y.data_ptr()), C.c_void_p(ws.data_ptr()),
+                                        need, prec, 10, 5, _stream()))
+
+
 def test_annotate_tensor_core_exact_mode(eqt, sd_eqt):
     """f16x3 end to end: probabilities within 1e-4 of the oracle and identical picks to the fp32 CUDA-core path."""
     x = synthetic_record(40, 60_000)

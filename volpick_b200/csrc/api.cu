@@ -140,7 +140,10 @@ extern "C" int vp_annotate(vp_model *m, const void *trace, int trace_on_host, in
         const int64_t nw = std::min(lo.chunk, lo.nwin - w0);
         rc = vp_slice_normalize(d_trace, dtype, n, d_stride, d_starts + w0, nw, L, p->peak_scope, taper, d_x, s);
         if (rc != VP_OK) return rc;
-        rc = vp_forward(m, d_x, nw, d_y + w0 * 3 * L, ws + lo.off_fwd, lo.fwd_bytes, p->precision, s);
+        // vp_stack discards the blinded margins of every window: the forward need not compute them
+        const int64_t keep_lo = std::min(std::max<int64_t>(p->blinding[0], 0), L);
+        const int64_t keep_hi = std::min(std::max<int64_t>(L - p->blinding[1], keep_lo), L);
+        rc = vp_forward_range(m, d_x, nw, d_y + w0 * 3 * L, ws + lo.off_fwd, lo.fwd_bytes, p->precision, keep_lo, keep_hi, s);
         if (rc != VP_OK) return rc;
     }
     float *d_annot = (float *)(ws + lo.off_annot);

@@ -28,6 +28,7 @@ struct FzLayer {
     int out_off;   // output buffer byte offset inside the pipeline's arena
     int out_rows;  // rows per output plane / valid rows of the fp32 planar buffer
     int out_rp;    // fp32 planar output: row pitch in floats
+    int lvl;       // level of the layer's input: its rows are (375-level rows << lvl)
     int a_row0;    // input-buffer row read by (tile 0, lane 0, tap 0)
     int s_lo;      // relative input row of (tile 0, lane 0)
     int c_in;      // input-level rows per tile index
@@ -54,6 +55,7 @@ struct FzDecB {
     long long x_split, x_gs;
     int T0, cin0, in_lo0, c0, in_slot_bytes;
     int tiles_per_seq, B;
+    int row_off0;        // 375-level row of tile 0 (> 0 when the leading output samples are blinded and need not be computed)
     int pipe_stride;     // bytes of one pipeline's arena (in[2] | X | Y)
     int ones_off;        // A operand of the bias MMA ([1,1,1,0,...] rows)
     int blob_off;        // resident weight blob: smem byte offset, bytes per group
@@ -79,6 +81,9 @@ struct DecBPlan {
 int decb_build(DecBPlan &plan, const TcLayer *dec, int split, int m, const float (*head_w)[88], const float *head_b);
 int decb_upload(DecBPlan &plan);
 void decb_free(DecBPlan &plan);
-int decb_launch(const DecBPlan &plan, const uint16_t *x, long long x_split, long long x_gs, int B, float *y, cudaStream_t s);
+// keep_lo / keep_hi: only output samples [keep_lo, keep_hi) of every window have to be computed (annotate's blinding
+// discards the rest): tiles that lie entirely outside are skipped and their part of y is left untouched.
+int decb_launch(const DecBPlan &plan, const uint16_t *x, long long x_split, long long x_gs, int B, float *y, int keep_lo,
+                int keep_hi, cudaStream_t s);
 
 }  // namespace vp

@@ -55,11 +55,11 @@ __device__ __forceinline__ void fz_pack8_relu(const uint32_t *v, uint4 &hi, uint
 
 // Polyphase layer -> 16-bit planes of the next layer.  Thread = one input row s; it owns output rows 2s, 2s+1.
 template <int COUTP, int SPLIT>
-__device__ __forceinline__ void fz_epi16(const FzLayer &L, uint32_t tacc, int t, int r, int j, uint8_t *arena) {
+__device__ __forceinline__ void fz_epi16(const FzLayer &L, uint32_t tacc, int t, int r, int R0, uint8_t *arena) {
     constexpr int P = COUTP / 8;
     const int s_rel = L.s_lo + 128 * t + r;
     const int lrow0 = 2 * s_rel - L.out_lo;
-    const int grow0 = 2 * (L.c_in * j + s_rel);
+    const int grow0 = 2 * ((R0 << L.lvl) + s_rel);  // R0: 375-level row of the work item's origin
     const uint32_t plane = (uint32_t)L.out_rows * 16u;
 #pragma unroll
     for (int phi = 0; phi < 2; ++phi) {
@@ -87,10 +87,10 @@ __device__ __forceinline__ void fz_epi16(const FzLayer &L, uint32_t tacc, int t,
 }
 
 // Last polyphase layer (8 channels per phase) -> fp32 planar [c][row] for the CUDA-core head.
-__device__ __forceinline__ void fz_epi32(const FzLayer &L, uint32_t tacc, int t, int r, int j, uint8_t *arena) {
+__device__ __forceinline__ void fz_epi32(const FzLayer &L, uint32_t tacc, int t, int r, int R0, uint8_t *arena) {
     const int s_rel = L.s_lo + 128 * t + r;
     const int lrow0 = 2 * s_rel - L.out_lo;  // even
-    const int grow0 = 2 * (L.c_in * j + s_rel);
+    const int grow0 = 2 * ((R0 << L.lvl) + s_rel);  // R0: 375-level row of the work item's origin
     uint32_t v[16];
     tmem_ld16_nowait(tacc, v);
     tmem_ld_wait();
@@ -109,7 +109,7 @@ __device__ __forceinline__ void fz_epi32(const FzLayer &L, uint32_t tacc, int t,
 
 // sigmoid(conv k11, 8 -> 1) on the CUDA cores: thread e = OPT consecutive output samples.
 template <int OPT>
-__device__ __forceinline__ void fz_head(const FzDecB &p, int g, int b, int j, int e, const uint8_t *arena) {
+__device__ __forceinline__ void fz_head(const FzDecB &p, int g, int b, int R0, int e, const uint8_t *arena) {
     const int tl0 = OPT * e;
     if (tl0 >= p.W) return;
     const float *d6 = reinterpret_cast<const float *>(arena + p.head_in_off) + tl0;
@@ -133,7 +133,7 @@ __device__ __forceinline__ void fz_head(const FzDecB &p, int g, int b, int j, in
             for (int o = 0; o < OPT; ++o) acc[o] = fmaf(w, xv[o + k + 1], acc[o]);  // buffer row 0 = output - 6
         }
     }
-    const int t_out = p.W * j + tl0;
+    const int t_out = 16 * R0 + tl0;
     float *yb = p.y + ((size_t)b * 3 + g) * p.L_out + t_out;
 #pragma unroll
     for (int o = 0; o < OPT; o += 2) {
@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) decb_kernel(const __grid_consta
             const int slot = n & 1;
             mbar_wait(&in_empty[pp][slot], ((n >> 1) & 1) ^ 1);
             const int b = item / p.tiles_per_seq, j = item - b * p.tiles_per_seq;
-            const int row_base = p.c0 * j + p.in_lo0;
+            const int row_base = p.c0 * j + p.row_off0 + p.in_lo0;
             const uint32_t dst0 = sbase + pp * p.pipe_stride + p.L[0].in_off + slot * p.in_slot_bytes;
             for (int idx = lane; idx < per_split; idx += 32) {
                 const int pl = idx % c8, r = idx / c8;
@@ -283,6 +283,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) decb_kernel(const __grid_consta
         uint32_t i = 0;
         for (int item = blockIdx.x + pp * gridDim.x; item < n_items; item += FZ_NPIPE * gridDim.x) {
             const int b = item / p.tiles_per_seq, j = item - b * p.tiles_per_seq;
+            const int R0 = p.c0 * j + p.row_off0;
             for (int l = 0; l < p.n_layers; ++l) {
                 const FzLayer &L = p.L[l];
                 for (int t = 0; t < L.n_tiles; ++t, ++i) {
@@ -290,9 +291,9 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) decb_kernel(const __grid_consta
                     mbar_wait(&acc_full[pp][buf], (i / FZ_NBUF) & 1);
                     tc_fence_after();
                     const uint32_t tacc = tmem_base + (pp * FZ_NBUF + buf) * FZ_NCOLS + ((uint32_t)(q * 32) << 16);
-                    if (L.out_kind == 1) fz_epi32(L, tacc, t, r, j, arena);
-                    else if (L.coutp == 32) fz_epi16<32, SPLIT>(L, tacc, t, r, j, arena);
-                    else fz_epi16<16, SPLIT>(L, tacc, t, r, j, arena);
+                    if (L.out_kind == 1) fz_epi32(L, tacc, t, r, R0, arena);
+                    else if (L.coutp == 32) fz_epi16<32, SPLIT>(L, tacc, t, r, R0, arena);
+                    else fz_epi16<16, SPLIT>(L, tacc, t, r, R0, arena);
                     fence_proxy_async();  // generic-proxy writes -> visible to the tensor-core (async) proxy
                     tc_fence_before();
                     __syncwarp();
@@ -300,7 +301,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) decb_kernel(const __grid_consta
                 }
             }
             named_bar_sync(1 + pp, 128);  // the last layer's rows are in shared memory
-            fz_head<OPT>(p, g, b, j, r, arena);
+            fz_head<OPT>(p, g, b, R0, r, arena);
             named_bar_sync(1 + pp, 128);  // head done reading X before the next item's epilogues overwrite it
         }
     }
@@ -406,6 +407,7 @@ int decb_build(DecBPlan &plan, const TcLayer *dec, int split, int m, const float
         L.out_rows = hi[l + 1] - lo[l + 1];
         L.out_rp = (l == NL - 1) ? ((L.out_rows + 12 + 3) & ~3) : 0;
         L.s_lo = s_lo[l];
+        L.lvl = l;
         L.c_in = c[l];
         L.out_lo = lo[l + 1];
         L.T_out = p.T0 << (l + 1);
@@ -515,9 +517,17 @@ static int decb_launch_t(const FzDecB &p, dim3 grid, cudaStream_t s) {
     return VP_OK;
 }
 
-int decb_launch(const DecBPlan &plan, const uint16_t *x, long long x_split, long long x_gs, int B, float *y, cudaStream_t s) {
+int decb_launch(const DecBPlan &plan, const uint16_t *x, long long x_split, long long x_gs, int B, float *y, int keep_lo,
+                int keep_hi, cudaStream_t s) {
     VP_REQUIRE(plan.ready, VP_ERR_UNSUPPORTED, "decb: plan not uploaded");
     FzDecB p = plan.p;
+    {   // tiles that produce at least one kept output sample: tile t covers samples [16 (row_off0 + m t), 16 (row_off0 + m (t + 1)))
+        keep_lo = std::max(0, std::min(keep_lo, p.L_out));
+        keep_hi = std::max(keep_lo, std::min(keep_hi, p.L_out));
+        if (keep_hi == keep_lo) return VP_OK;
+        p.row_off0 = keep_lo / 16;
+        p.tiles_per_seq = (keep_hi - 16 * p.row_off0 + p.W - 1) / p.W;
+    }
     p.x = x;
     p.x_split = x_split;
     p.x_gs = x_gs;

@@ -442,6 +442,7 @@ struct Runner {
     cudaStream_t s;
     int B;
     int precision = VP_PREC_FP32;
+    int keep_lo = 0, keep_hi = 1 << 30;  // output samples per window that must be computed (the rest is blinded by the caller)
     bool dry;               // only measure the workspace
     const char *stop_name;  // stop after this tap (debug)
     Tap hit{nullptr, nullptr, 0};
@@ -797,7 +798,7 @@ static int run_eqt(Runner &r, const float *x, float *y, Arena &ar) {
             uint16_t *dst = pp16[i & 1];
             if (fused && i == 3) {  // decoder.convs.3-6 + heads in one kernel, activations in shared memory
                 if (r.go())
-                    r.rc = decb_launch(ts.decb, cur16, split16, B * (int64_t)tl.cin * dlen[i], (int)B, y, r.s);
+                    r.rc = decb_launch(ts.decb, cur16, split16, B * (int64_t)tl.cin * dlen[i], (int)B, y, r.keep_lo, r.keep_hi, r.s);
                 return r.rc;
             }
             if (r.go()) {
@@ -951,7 +952,7 @@ static int run_pn(Runner &r, const float *x, float *y, Arena &ar) {
 }
 
 static int run_forward(vp_model *m, const float *x, int64_t B, float *y, void *ws, int64_t ws_bytes, int precision,
-                       const char *stop, Tap *hit, cudaStream_t s, int64_t *need_bytes) {
+                       const char *stop, Tap *hit, cudaStream_t s, int64_t *need_bytes, int keep_lo = 0, int keep_hi = 1 << 30) {
     if (precision != VP_PREC_FP32 && precision != VP_PREC_F16X3 && precision != VP_PREC_BF16) {
         set_error("unknown precision mode %d", precision);
         return VP_ERR_ARG;
@@ -962,6 +963,8 @@ static int run_forward(vp_model *m, const float *x, int64_t B, float *y, void *w
     }
     Runner r;
     r.precision = precision;
+    r.keep_lo = keep_lo;
+    r.keep_hi = keep_hi;
     r.m = m;
     r.s = s;
     r.B = (int)B;
@@ -1076,6 +1079,21 @@ extern "C" int vp_forward(vp_model *m, const float *x, int64_t n_windows, float 
         const int64_t nb = std::min<int64_t>(MAX_CHUNK, n_windows - b0);
         int rc = run_forward(m, x + b0 * 3 * L, nb, y + b0 * 3 * L, workspace, workspace_bytes, precision, nullptr,
                              nullptr, (cudaStream_t)stream, nullptr);
+        if (rc != VP_OK) return rc;
+    }
+    return VP_OK;
+}
+
+extern "C" int vp_forward_range(vp_model *m, const float *x, int64_t n_windows, float *y, void *workspace,
+                                int64_t workspace_bytes, int precision, int64_t keep_lo, int64_t keep_hi, void *stream) {
+    VP_REQUIRE(m && x && y && workspace, VP_ERR_ARG, "vp_forward_range: null pointer");
+    const int64_t L = m->in_samples;
+    VP_REQUIRE(keep_lo >= 0 && keep_lo <= keep_hi, VP_ERR_ARG, "vp_forward_range: bad sample range [%lld, %lld)", (long long)keep_lo,
+               (long long)keep_hi);
+    for (int64_t b0 = 0; b0 < n_windows; b0 += MAX_CHUNK) {
+        const int64_t nb = std::min<int64_t>(MAX_CHUNK, n_windows - b0);
+        int rc = run_forward(m, x + b0 * 3 * L, nb, y + b0 * 3 * L, workspace, workspace_bytes, precision, nullptr, nullptr,
+                             (cudaStream_t)stream, nullptr, (int)std::min<int64_t>(keep_lo, L), (int)std::min<int64_t>(keep_hi, L));
         if (rc != VP_OK) return rc;
     }
     return VP_OK;
