@@ -84,7 +84,7 @@ def _tap_report(model, kind, sd, x, groups_of):
     B = x.shape[0]
     report = []
     for name in model.tap_names():
-        got = model.forward_tap(xd, name).cpu().numpy()
+        got = model.forward_tap(xd, name, precision="fp32").cpu().numpy()
         ref = groups_of(name, taps, B)
         if ref is None:
             continue
@@ -94,7 +94,7 @@ def _tap_report(model, kind, sd, x, groups_of):
         err = float(np.abs(got - ref).max())
         scale = float(np.abs(ref).max())
         report.append((name, err, scale))
-    out = model(xd)
+    out = model.forward(xd, precision="fp32")
     got_out = (torch.stack(out, dim=1) if isinstance(out, tuple) else out).cpu().numpy()
     return report, got_out, ref_out
 
@@ -193,7 +193,7 @@ def test_annotate_tensor_core_exact_mode(eqt, sd_eqt):
     """f16x3 end to end: probabilities within 1e-4 of the oracle and identical picks to the fp32 CUDA-core path."""
     x = synthetic_record(40, 60_000)
     thr = {"P_threshold": 0.2, "S_threshold": 0.2, "detection_threshold": 0.3}
-    a32 = eqt._argdict(dict(overlap=5500, blinding=(500, 500), stacking="avg", **thr))
+    a32 = eqt._argdict(dict(overlap=5500, blinding=(500, 500), stacking="avg", precision="fp32", **thr))
     atc = eqt._argdict(dict(overlap=5500, blinding=(500, 500), stacking="avg", precision="f16x3", **thr))
     ann32, trig32, _ = eqt.annotate_array(x, a32, True, eqt._thresholds(a32))
     anntc, trigtc, _ = eqt.annotate_array(x, atc, True, eqt._thresholds(atc))
@@ -333,12 +333,16 @@ def _oracle_triggers(kind, sd, x, overlap, blinding, stacking, thr):
     ("eqtransformer", 21_234, 1800, (500, 500), "max"),
     ("phasenet", 10_000, 2000, (200, 300), "max"),
 ])
-def test_annotate_matches_oracle(eqt, pn, sd_eqt, sd_pn, kind, n, overlap, blinding, stacking):
+@pytest.mark.parametrize("precision", ["default", "fp32"])
+def test_annotate_matches_oracle(eqt, pn, sd_eqt, sd_pn, kind, n, overlap, blinding, stacking, precision):
     model, sd = (eqt, sd_eqt) if kind == "eqtransformer" else (pn, sd_pn)
+    if precision == "fp32" and model.precision == "fp32":
+        pytest.skip("fp32 is this model's default")
     x = synthetic_record(40, n)
     thr = {"P_threshold": 0.2, "S_threshold": 0.2, "detection_threshold": 0.3}
     ann, picks, offsets = _oracle_triggers(kind, sd, x, overlap, blinding, stacking, thr)
-    argdict = model._argdict(dict(overlap=overlap, blinding=blinding, stacking=stacking, **thr))
+    extra = {} if precision == "default" else {"precision": precision}
+    argdict = model._argdict(dict(overlap=overlap, blinding=blinding, stacking=stacking, **thr, **extra))
     got_ann, trig, trim = model.annotate_array(x, argdict, True, model._thresholds(argdict))
     # also from a CUDA-resident trace
     got_ann2, trig2, _ = model.annotate_array(torch.from_numpy(x).cuda(), argdict, True, model._thresholds(argdict))

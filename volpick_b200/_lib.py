@@ -60,6 +60,7 @@ SIGNATURES = {
     "vp_forward_workspace_bytes": (_i64, [_vp, _i64, _i32]),
     "vp_forward": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _i32, _vp]),
     "vp_forward_range": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _i32, _i64, _i64, _vp]),
+    "vp_slice_forward": (_i32, [_vp, _vp, _i32, _i64, _i64, _vp, _i64, _i32, _i32, _vp, _vp, _i64, _i32, _i64, _i64, _vp]),
     "vp_forward_tap": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _i32, C.c_char_p, _vp, _i64, C.POINTER(_i64), _vp]),
     "vp_forward_tap_names": (C.c_char_p, [_vp]),
     "vp_tcconv_debug": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),

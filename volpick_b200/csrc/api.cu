@@ -5,6 +5,7 @@
 //                      (call sites /root/reference/README.md:54-66, Final_models/demo.ipynb cell 13-15)
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -136,13 +137,21 @@ extern "C" int vp_annotate(vp_model *m, const void *trace, int trace_on_host, in
     float *d_x = (float *)(ws + lo.off_x);
     float *d_y = (float *)(ws + lo.off_y);
     const int taper = (kind == VP_KIND_EQTRANSFORMER) ? 1 : 0;
+    static const bool fused_off = getenv("VP_FUSED_SLICE") && atoi(getenv("VP_FUSED_SLICE")) == 0;  // debugging aid
+    const bool fused_slice = !fused_off && kind == VP_KIND_EQTRANSFORMER && (p->precision == VP_PREC_F16X3 || p->precision == VP_PREC_BF16);
     for (int64_t w0 = 0; w0 < lo.nwin; w0 += lo.chunk) {
         const int64_t nw = std::min(lo.chunk, lo.nwin - w0);
-        rc = vp_slice_normalize(d_trace, dtype, n, d_stride, d_starts + w0, nw, L, p->peak_scope, taper, d_x, s);
-        if (rc != VP_OK) return rc;
         // vp_stack discards the blinded margins of every window: the forward need not compute them
         const int64_t keep_lo = std::min(std::max<int64_t>(p->blinding[0], 0), L);
         const int64_t keep_hi = std::min(std::max<int64_t>(L - p->blinding[1], keep_lo), L);
+        if (fused_slice) {  // K1 lives inside the first encoder kernel: the fp32 windows are never materialised
+            rc = vp_slice_forward(m, d_trace, dtype, n, d_stride, d_starts + w0, nw, p->peak_scope, taper, d_y + w0 * 3 * L,
+                                  ws + lo.off_fwd, lo.fwd_bytes, p->precision, keep_lo, keep_hi, s);
+            if (rc != VP_OK) return rc;
+            continue;
+        }
+        rc = vp_slice_normalize(d_trace, dtype, n, d_stride, d_starts + w0, nw, L, p->peak_scope, taper, d_x, s);
+        if (rc != VP_OK) return rc;
         rc = vp_forward_range(m, d_x, nw, d_y + w0 * 3 * L, ws + lo.off_fwd, lo.fwd_bytes, p->precision, keep_lo, keep_hi, s);
         if (rc != VP_OK) return rc;
     }

@@ -204,6 +204,7 @@ struct vp_model {
     // PhaseNet
     ConvW inc, down_same[5], down_down[4], up_t[4], up_same[4], outc;
     std::string tap_names;
+    float enc0_w[8 * 3 * 11] = {0}, enc0_b[8] = {0};  // host copy of encoder.convs.0 for the fused slicer kernel (kernel parameter)
     // tensor-core (tcgen05) weight sets: [0] = fp16 hi/lo split (f16x3), [1] = bf16
     struct TcSet {
         TcLayer enc[7], dec[7], head;
@@ -257,6 +258,10 @@ static int build_eqt(vp_model *m, Cursor &cur, Packed &pk) {
         const float *b = cur.take(kEncC[i + 1]);
         eW[i] = W;
         eB[i] = b;
+        if (i == 0) {
+            std::memcpy(m->enc0_w, W, sizeof(m->enc0_w));
+            std::memcpy(m->enc0_b, b, sizeof(m->enc0_b));
+        }
         m->enc[i] = pack_conv(pk, W, b, nullptr, kEncC[i + 1], kEncC[i], kEncK[i]);
     }
     const float *rW[7][2], *rB[7][2];
@@ -443,6 +448,11 @@ struct Runner {
     int B;
     int precision = VP_PREC_FP32;
     int keep_lo = 0, keep_hi = 1 << 30;  // output samples per window that must be computed (the rest is blinded by the caller)
+    // when set, the windows are cut from this trace by the fused slicer + encoder.convs.0 kernel (tensor-core path)
+    const void *trace = nullptr;
+    int trace_dtype = 0, peak_scope = 0, taper = 0;
+    int64_t ch_stride = 0;
+    const int64_t *starts = nullptr;
     bool dry;               // only measure the workspace
     const char *stop_name;  // stop after this tap (debug)
     Tap hit{nullptr, nullptr, 0};
@@ -571,10 +581,19 @@ static int run_eqt(Runner &r, const float *x, float *y, Arena &ar) {
         }
     } else {
         // ---- encoder on the tensor cores: x (B,3,L) fp32 -> channel-last 16-bit [B][L][8] -> 7 x (conv, ReLU, pool)
-        if (r.go()) r.rc = launch_pack_cl16(x, 3 * (int64_t)L, L, (int)B, 3, L, split, Q16, split16, 1, r.s);
         const uint16_t *cur16 = Q16;
+        int first_layer = 0;
+        if (r.trace) {  // K1 + encoder.convs.0 + ReLU + pool on the CUDA cores, straight from the record
+            if (r.go())
+                r.rc = launch_slice_enc0(r.trace, r.trace_dtype, r.ch_stride, r.starts, B, L, r.peak_scope, r.taper, m->enc0_w,
+                                         m->enc0_b, split, P16, split16, r.s);
+            cur16 = P16;
+            first_layer = 1;
+        } else if (r.go()) {
+            r.rc = launch_pack_cl16(x, 3 * (int64_t)L, L, (int)B, 3, L, split, Q16, split16, 1, r.s);
+        }
         const bool enc6_tap = r.stop_name && std::strcmp(r.stop_name, "enc6") == 0;
-        for (int i = 0; i < 7; ++i) {
+        for (int i = first_layer; i < 7; ++i) {
             const TcLayer &tl = ts.enc[i];
             if (r.go()) {
                 TcIO io;
@@ -952,7 +971,8 @@ static int run_pn(Runner &r, const float *x, float *y, Arena &ar) {
 }
 
 static int run_forward(vp_model *m, const float *x, int64_t B, float *y, void *ws, int64_t ws_bytes, int precision,
-                       const char *stop, Tap *hit, cudaStream_t s, int64_t *need_bytes, int keep_lo = 0, int keep_hi = 1 << 30) {
+                       const char *stop, Tap *hit, cudaStream_t s, int64_t *need_bytes, int keep_lo = 0, int keep_hi = 1 << 30,
+                       const Runner *src = nullptr) {
     if (precision != VP_PREC_FP32 && precision != VP_PREC_F16X3 && precision != VP_PREC_BF16) {
         set_error("unknown precision mode %d", precision);
         return VP_ERR_ARG;
@@ -965,6 +985,14 @@ static int run_forward(vp_model *m, const float *x, int64_t B, float *y, void *w
     r.precision = precision;
     r.keep_lo = keep_lo;
     r.keep_hi = keep_hi;
+    if (src) {
+        r.trace = src->trace;
+        r.trace_dtype = src->trace_dtype;
+        r.peak_scope = src->peak_scope;
+        r.taper = src->taper;
+        r.ch_stride = src->ch_stride;
+        r.starts = src->starts;
+    }
     r.m = m;
     r.s = s;
     r.B = (int)B;
@@ -1094,6 +1122,33 @@ extern "C" int vp_forward_range(vp_model *m, const float *x, int64_t n_windows, 
         const int64_t nb = std::min<int64_t>(MAX_CHUNK, n_windows - b0);
         int rc = run_forward(m, x + b0 * 3 * L, nb, y + b0 * 3 * L, workspace, workspace_bytes, precision, nullptr, nullptr,
                              (cudaStream_t)stream, nullptr, (int)std::min<int64_t>(keep_lo, L), (int)std::min<int64_t>(keep_hi, L));
+        if (rc != VP_OK) return rc;
+    }
+    return VP_OK;
+}
+
+extern "C" int vp_slice_forward(vp_model *m, const void *trace, int dtype, int64_t n_samples, int64_t ch_stride,
+                                const int64_t *starts, int64_t n_windows, int peak_scope, int taper, float *y, void *workspace,
+                                int64_t workspace_bytes, int precision, int64_t keep_lo, int64_t keep_hi, void *stream) {
+    VP_REQUIRE(m && trace && starts && y && workspace, VP_ERR_ARG, "vp_slice_forward: null pointer");
+    VP_REQUIRE(m->kind == VP_KIND_EQTRANSFORMER && (precision == VP_PREC_F16X3 || precision == VP_PREC_BF16), VP_ERR_UNSUPPORTED,
+               "vp_slice_forward: implemented for the EQTransformer tensor-core modes (use vp_slice_normalize + vp_forward otherwise)");
+    VP_REQUIRE(dtype == VP_DTYPE_F32 || dtype == VP_DTYPE_I32, VP_ERR_ARG, "vp_slice_forward: unknown dtype %d", dtype);
+    VP_REQUIRE(keep_lo >= 0 && keep_lo <= keep_hi, VP_ERR_ARG, "vp_slice_forward: bad sample range [%lld, %lld)", (long long)keep_lo,
+               (long long)keep_hi);
+    (void)n_samples;
+    const int64_t L = m->in_samples;
+    for (int64_t b0 = 0; b0 < n_windows; b0 += MAX_CHUNK) {
+        const int64_t nb = std::min<int64_t>(MAX_CHUNK, n_windows - b0);
+        Runner src;
+        src.trace = trace;
+        src.trace_dtype = dtype;
+        src.peak_scope = peak_scope;
+        src.taper = taper;
+        src.ch_stride = ch_stride;
+        src.starts = starts + b0;
+        int rc = run_forward(m, nullptr, nb, y + b0 * 3 * L, workspace, workspace_bytes, precision, nullptr, nullptr, (cudaStream_t)stream,
+                             nullptr, (int)std::min<int64_t>(keep_lo, L), (int)std::min<int64_t>(keep_hi, L), &src);
         if (rc != VP_OK) return rc;
     }
     return VP_OK;

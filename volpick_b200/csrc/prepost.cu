@@ -11,8 +11,10 @@
 
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace vp {
 
@@ -136,6 +138,162 @@ __global__ void __launch_bounds__(NT) slice_normalize_kernel(const Tin *__restri
             ob[2 * (int64_t)L + idx] = (v[2][j] / den.z) * tp;
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------ K1 + encoder.convs.0
+// Tensor-core path of the EQTransformer: the window slicer / normaliser fused with the first encoder stage
+// (Conv1d 3 -> 8, k = 11, 'same') + ReLU + MaxPool1d(2), written as the 16-bit channel-last operand of
+// encoder.convs.1 ([split][window][L / 2][8]; fp16 hi/lo or bf16).  With 3 input channels the implicit GEMM
+// keeps 5 % of the tensor pipe busy (K padded 3 -> 8, N padded 8 -> 16) and needs a 32-byte-per-sample packed
+// copy of the windows first; on the CUDA cores the stage is 264 fp32 FMAs per sample straight from the
+// normalised window in shared memory, and the fp32 windows never reach HBM.
+// Normalisation arithmetic (summation order included) is that of slice_normalize_kernel<Tin, 12, 512>.
+struct Enc0W {
+    float w[8 * 3 * 11];  // [co][ci][k]
+    float b[8];
+};
+constexpr int E0_NT = 512, E0_PT = 12, E0_HALO = 5;
+
+template <typename Tin, int SPLIT>
+__global__ void __launch_bounds__(E0_NT, 2) slice_enc0_kernel(const Tin *__restrict__ trace, int64_t ch_stride,
+                                                              const int64_t *__restrict__ starts, int L, int peak_scope,
+                                                              int taper, Taper tap, const __grid_constant__ Enc0W wt,
+                                                              uint16_t *__restrict__ out, int64_t out_split) {
+    extern __shared__ __align__(16) float e0_smem[];
+    __shared__ float red[96];
+    const int XP = L + 12;  // xs[c][i + 5] = normalised sample i; zero halo on both sides
+    float *xs = e0_smem;
+    const int64_t w = blockIdx.x;
+    const int64_t s = __ldg(starts + w);
+    const int tid = threadIdx.x;
+    float3 sum = make_float3(0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < E0_PT; ++j) {
+        const int idx = tid + j * E0_NT;
+        const bool ok = idx < L;
+        const float v0 = ok ? ld_as_float(trace + s + idx) : 0.f;
+        const float v1 = ok ? ld_as_float(trace + ch_stride + s + idx) : 0.f;
+        const float v2 = ok ? ld_as_float(trace + 2 * ch_stride + s + idx) : 0.f;
+        sum.x += v0;
+        sum.y += v1;
+        sum.z += v2;
+        if (ok) {
+            xs[idx + E0_HALO] = v0;
+            xs[XP + idx + E0_HALO] = v1;
+            xs[2 * XP + idx + E0_HALO] = v2;
+        }
+    }
+    block_reduce_sum3(sum, red);
+    const float invL = 1.0f / (float)L;
+    const float3 mean = make_float3(sum.x * invL, sum.y * invL, sum.z * invL);
+    float3 pk = make_float3(0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < E0_PT; ++j) {
+        const int idx = tid + j * E0_NT;
+        if (idx < L) {  // each thread re-reads exactly what it wrote
+            const float v0 = xs[idx + E0_HALO] - mean.x, v1 = xs[XP + idx + E0_HALO] - mean.y, v2 = xs[2 * XP + idx + E0_HALO] - mean.z;
+            xs[idx + E0_HALO] = v0;
+            xs[XP + idx + E0_HALO] = v1;
+            xs[2 * XP + idx + E0_HALO] = v2;
+            pk.x = fmaxf(pk.x, fabsf(v0));
+            pk.y = fmaxf(pk.y, fabsf(v1));
+            pk.z = fmaxf(pk.z, fabsf(v2));
+        }
+    }
+    block_reduce_max3(pk, red);
+    if (peak_scope == VP_PEAK_PER_WINDOW) {
+        const float m = fmaxf(pk.x, fmaxf(pk.y, pk.z));
+        pk = make_float3(m, m, m);
+    }
+    const float3 den = make_float3(pk.x + 1e-10f, pk.y + 1e-10f, pk.z + 1e-10f);
+#pragma unroll
+    for (int j = 0; j < E0_PT; ++j) {
+        const int idx = tid + j * E0_NT;
+        if (idx < L) {
+            float tp = 1.f;
+            if (taper) {
+                if (idx < 6) tp = tap.t[idx];
+                if (idx >= L - 6) tp = tap.t[L - 1 - idx];
+            }
+            xs[idx + E0_HALO] = (xs[idx + E0_HALO] / den.x) * tp;
+            xs[XP + idx + E0_HALO] = (xs[XP + idx + E0_HALO] / den.y) * tp;
+            xs[2 * XP + idx + E0_HALO] = (xs[2 * XP + idx + E0_HALO] / den.z) * tp;
+        }
+    }
+    if (tid < 3 * 12) {  // zero padding of the 'same' conv: 5 samples before, 7 after (one spare for the float2 reads)
+        const int c = tid / 12, q = tid - c * 12;
+        xs[c * XP + (q < E0_HALO ? q : L + q)] = 0.f;
+    }
+    __syncthreads();
+
+    // conv + ReLU + pool: one thread = one pooled output sample p (conv outputs 2p, 2p + 1), all 8 channels
+    const int LP = L >> 1;
+    for (int p = tid; p < LP; p += E0_NT) {
+        float in[3][12];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+                const float2 v2 = *reinterpret_cast<const float2 *>(xs + c * XP + 2 * p + 2 * q);
+                in[c][2 * q] = v2.x;
+                in[c][2 * q + 1] = v2.y;
+            }
+        float a0[8], a1[8];
+#pragma unroll
+        for (int co = 0; co < 8; ++co) a0[co] = a1[co] = wt.b[co];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int q = 0; q < 12; ++q) {
+                const float x = in[c][q];
+#pragma unroll
+                for (int co = 0; co < 8; ++co) {
+                    if (q < 11) a0[co] = fmaf(x, wt.w[(co * 3 + c) * 11 + q], a0[co]);
+                    if (q >= 1) a1[co] = fmaf(x, wt.w[(co * 3 + c) * 11 + q - 1], a1[co]);
+                }
+            }
+        float v[8];
+#pragma unroll
+        for (int co = 0; co < 8; ++co) v[co] = fmaxf(fmaxf(a0[co], a1[co]), 0.f);
+        uint4 hi, lo;
+        pack8_split16<SPLIT>(v, hi, lo);
+        uint16_t *yb = out + (w * LP + p) * 8;
+        *reinterpret_cast<uint4 *>(yb) = hi;
+        if (SPLIT == 2) *reinterpret_cast<uint4 *>(yb + out_split) = lo;
+    }
+}
+
+int launch_slice_enc0(const void *trace, int dtype, int64_t ch_stride, const int64_t *starts, int64_t nw, int L, int scope,
+                      int taper, const float *w_host /*(8,3,11)*/, const float *b_host /*(8)*/, int split, uint16_t *out,
+                      int64_t out_split, cudaStream_t s) {
+    VP_REQUIRE(L % 2 == 0 && L <= E0_PT * E0_NT, VP_ERR_UNSUPPORTED, "fused slicer + encoder.convs.0: window length %d unsupported", L);
+    if (nw == 0) return VP_OK;
+    Taper tap;
+    for (int i = 0; i < 6; ++i) {
+        const double a = M_PI + (M_PI * i) / 5.0;
+        tap.t[i] = (float)(0.5 * (1.0 + std::cos(a)));
+    }
+    Enc0W wt;
+    std::memcpy(wt.w, w_host, sizeof(wt.w));
+    std::memcpy(wt.b, b_host, sizeof(wt.b));
+    const size_t smem = (size_t)3 * (L + 12) * sizeof(float);
+#define VP_E0_LAUNCH(T, S)                                                                                                  \
+    do {                                                                                                                    \
+        auto kern = slice_enc0_kernel<T, S>;                                                                                \
+        static bool attr = false;                                                                                           \
+        if (!attr) {                                                                                                        \
+            VP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (E0_PT * E0_NT + 12) * 4)); \
+            attr = true;                                                                                                    \
+        }                                                                                                                   \
+        kern<<<(unsigned)nw, E0_NT, smem, s>>>((const T *)trace, ch_stride, starts, L, scope, taper, tap, wt, out, out_split); \
+    } while (0)
+    if (dtype == VP_DTYPE_F32 && split == 2) VP_E0_LAUNCH(float, 2);
+    else if (dtype == VP_DTYPE_F32) VP_E0_LAUNCH(float, 1);
+    else if (split == 2) VP_E0_LAUNCH(int32_t, 2);
+    else VP_E0_LAUNCH(int32_t, 1);
+#undef VP_E0_LAUNCH
+    VP_LAUNCH_CHECK();
+    return VP_OK;
 }
 
 template <typename Tin>

@@ -88,6 +88,29 @@ __device__ __forceinline__ void split16(float v, int fmt16, int split, uint16_t 
     }
 }
 
+// 8 fp32 values -> 8 x 16-bit (one 16-byte row of an 8-channel plane): fp16 hi + fp16 lo (SPLIT == 2) or bf16.
+template <int SPLIT>
+__device__ __forceinline__ void pack8_split16(const float *v, uint4 &hi, uint4 &lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float a = v[2 * i], b = v[2 * i + 1];
+        if (SPLIT == 2) {
+            const __half2 hh = __floats2half2_rn(a, b);
+            const float2 hf = __half22float2(hh);
+            const __half2 ll = __floats2half2_rn(a - hf.x, b - hf.y);
+            h[i] = *reinterpret_cast<const uint32_t *>(&hh);
+            l[i] = *reinterpret_cast<const uint32_t *>(&ll);
+        } else {
+            const __nv_bfloat162 bb = __floats2bfloat162_rn(a, b);
+            h[i] = *reinterpret_cast<const uint32_t *>(&bb);
+            l[i] = 0u;
+        }
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred = 0;
     asm volatile(

@@ -148,6 +148,7 @@ class WaveformModel:
     in_samples: int = 0
     _default_overlap: int = 0
     _default_blinding: Tuple[int, int] = (0, 0)
+    _default_precision: str = "fp32"  # arithmetic of the network forward ("fp32" CUDA cores | "f16x3" | "bf16" tensor cores)
     _generic_threshold: float = 0.3
     _spec = staticmethod(lambda: [])
     _known_kwargs = {
@@ -167,7 +168,7 @@ class WaveformModel:
         self.filter_args = None
         self.filter_kwargs = None
         self.peak_scope = kwargs.pop("peak_scope", "channel")
-        self.precision = kwargs.pop("precision", "fp32")
+        self.precision = kwargs.pop("precision", self._default_precision)
         self._weights: Optional["OrderedDict[str, np.ndarray]"] = None
         self._flat: Optional[np.ndarray] = None
         self._handle = C.c_void_p(None)
@@ -605,6 +606,9 @@ class EQTransformer(WaveformModel):
     in_samples = 6000
     _default_overlap = 1800
     _default_blinding = (500, 500)
+    # tcgen05 on fp16 hi/lo split operands with fp32 accumulation: within the 1e-4 tolerance of the fp32 oracle
+    # (measured 2e-5 on probabilities) and ~4x faster than the CUDA-core fp32 path
+    _default_precision = "f16x3"
     _generic_threshold = 0.1
     _spec = staticmethod(eqtransformer_spec)
 
