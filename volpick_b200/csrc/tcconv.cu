@@ -71,10 +71,100 @@ __device__ __forceinline__ void tc_pack8(const float *v, uint4 &hi, uint4 &lo) {
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+// Epilogue of one 128-row tile with the layer's options fixed at compile time (FLAGS bits: 1 MaxPool1d(2),
+// 2 polyphase (two output rows per accumulator row), 4 res-CNN extras = fp32 residual in / fp32 row-major out /
+// pre-activation BatchNorm + ReLU of the next conv).  16-bit channel-last output, ReLU unless the extras carry
+// the activation, NOUT == phases * cout (no padding columns).  The run-time-flag epilogue in the kernel body had
+// ~1000 instructions per warp and tile, most of them flag tests, re-derived indices and dead output formats; the
+// measured cost was ~22 K cycles per 128 x 128 tile, ten times the MMA time.
+template <int NOUT, int SPLIT, int EW, int FLAGS>
+__device__ __forceinline__ void tc_epilogue_fixed(const TcP &p, uint32_t trow, int half, int lane, int seq, int srow, bool row_ok,
+                                                  int g, const float *s_bias, const float *s_psc, const float *s_psh) {
+    constexpr bool POOL = (FLAGS & 1) != 0, PH2 = (FLAGS & 2) != 0, EXTRA = (FLAGS & 4) != 0;
+    constexpr int NHALF = EW / 4, COLS = NOUT / NHALF, COUT = PH2 ? NOUT / 2 : NOUT;
+    constexpr int RC = COLS < 32 ? COLS : 32;  // accumulator columns in flight per thread
+    static_assert(COLS % 8 == 0 && COLS % RC == 0, "column split");
+    const bool st = POOL ? (row_ok && !(lane & 1)) : row_ok;
+    const int t0 = POOL ? (srow >> 1) : (PH2 ? 2 * srow : srow);
+    const int64_t orow0 = (int64_t)seq * p.T_out + t0;
+    uint16_t *y16 = reinterpret_cast<uint16_t *>(p.y) + (int64_t)g * p.y_gs + orow0 * COUT;
+#pragma unroll
+    for (int rc = 0; rc < COLS; rc += RC) {
+        const int nb = half * COLS + rc;
+        uint32_t r[RC];
+#pragma unroll
+        for (int c = 0; c < RC; c += 16) {
+            if constexpr (RC >= 16) {
+                uint32_t(&r16)[16] = *reinterpret_cast<uint32_t(*)[16]>(&r[c]);
+                tmem_ld16_nowait(trow + (uint32_t)(nb + c), r16);
+            } else {
+                uint32_t(&r8)[8] = *reinterpret_cast<uint32_t(*)[8]>(&r[c]);
+                tmem_ld8_nowait(trow + (uint32_t)(nb + c), r8);
+            }
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int g8 = 0; g8 < RC; g8 += 8) {
+            const int n0 = nb + g8;
+            const int phi = (PH2 && n0 >= COUT) ? 1 : 0;
+            const int c0 = n0 - phi * COUT;
+            const bool ok = st && (t0 + phi) < p.T_out;
+            float w8[8];
+            const float4 b0 = *reinterpret_cast<const float4 *>(&s_bias[n0]), b1 = *reinterpret_cast<const float4 *>(&s_bias[n0 + 4]);
+            w8[0] = __uint_as_float(r[g8 + 0]) + b0.x, w8[1] = __uint_as_float(r[g8 + 1]) + b0.y;
+            w8[2] = __uint_as_float(r[g8 + 2]) + b0.z, w8[3] = __uint_as_float(r[g8 + 3]) + b0.w;
+            w8[4] = __uint_as_float(r[g8 + 4]) + b1.x, w8[5] = __uint_as_float(r[g8 + 5]) + b1.y;
+            w8[6] = __uint_as_float(r[g8 + 6]) + b1.z, w8[7] = __uint_as_float(r[g8 + 7]) + b1.w;
+            if constexpr (EXTRA) {
+                if (p.res != nullptr && ok) {  // residual stream, fp32 row-major [seq][t][cout]; may alias y32 (in place)
+                    const float4 *rp = reinterpret_cast<const float4 *>(p.res + orow0 * COUT + c0);
+                    const float4 r0 = rp[0], r1 = rp[1];
+                    w8[0] += r0.x, w8[1] += r0.y, w8[2] += r0.z, w8[3] += r0.w;
+                    w8[4] += r1.x, w8[5] += r1.y, w8[6] += r1.z, w8[7] += r1.w;
+                }
+            }
+            if (!EXTRA || p.act == ACT_RELU) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) w8[i] = fmaxf(w8[i], 0.f);
+            }
+            if constexpr (POOL) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float mine = row_ok ? w8[i] : -1e10f;  // SeisBench pads odd lengths with -1e10 before MaxPool1d(2)
+                    w8[i] = fmaxf(mine, __shfl_xor_sync(0xffffffffu, mine, 1));
+                }
+            }
+            if constexpr (EXTRA) {
+                if (p.y32 != nullptr && ok) {
+                    float4 *yp = reinterpret_cast<float4 *>(p.y32 + orow0 * COUT + c0);
+                    yp[0] = make_float4(w8[0], w8[1], w8[2], w8[3]);
+                    yp[1] = make_float4(w8[4], w8[5], w8[6], w8[7]);
+                }
+                if (p.post_scale != nullptr) {
+                    const float4 s0 = *reinterpret_cast<const float4 *>(&s_psc[n0]), s1 = *reinterpret_cast<const float4 *>(&s_psc[n0 + 4]);
+                    const float4 h0 = *reinterpret_cast<const float4 *>(&s_psh[n0]), h1 = *reinterpret_cast<const float4 *>(&s_psh[n0 + 4]);
+                    w8[0] = fmaxf(fmaf(w8[0], s0.x, h0.x), 0.f), w8[1] = fmaxf(fmaf(w8[1], s0.y, h0.y), 0.f);
+                    w8[2] = fmaxf(fmaf(w8[2], s0.z, h0.z), 0.f), w8[3] = fmaxf(fmaf(w8[3], s0.w, h0.w), 0.f);
+                    w8[4] = fmaxf(fmaf(w8[4], s1.x, h1.x), 0.f), w8[5] = fmaxf(fmaf(w8[5], s1.y, h1.y), 0.f);
+                    w8[6] = fmaxf(fmaf(w8[6], s1.z, h1.z), 0.f), w8[7] = fmaxf(fmaf(w8[7], s1.w, h1.w), 0.f);
+                }
+            }
+            if (ok) {
+                uint4 hi, lo;
+                pack8_split16<SPLIT>(w8, hi, lo);
+                uint16_t *yb = y16 + phi * COUT + c0;
+                *reinterpret_cast<uint4 *>(yb) = hi;
+                if (SPLIT == 2) *reinterpret_cast<uint4 *>(yb + p.y_split) = lo;
+            }
+        }
+    }
+}
+
 // NTAPS > 0: the tile's MMA schedule is fixed at compile time (umma_conv_tile); NTAPS == 0: generic
 // instance that walks the host-built schedule table (any layer shape; slower issue).
-template <int NOUT, int SPLIT, int NTAPS, int NQ, int EW>
-__global__ void __launch_bounds__(32 * (EW + 4), EW == 8 ? 2 : 4) tcconv_kernel(const __grid_constant__ TcP p) {
+// FLAGS >= 0: epilogue options fixed at compile time (tc_epilogue_fixed); FLAGS < 0: run-time options (any layer).
+template <int NOUT, int SPLIT, int NTAPS, int NQ, int EW, int FLAGS>
+__global__ void __launch_bounds__(32 * (EW + 4), EW == 16 ? 1 : EW == 8 ? 2 : 4) tcconv_kernel(const __grid_constant__ TcP p) {
     extern __shared__ __align__(128) uint8_t tc_smem[];
     __shared__ __align__(8) uint64_t full_bar[TC_MAX_STAGES], empty_bar[TC_MAX_STAGES], accf_bar[2], acce_bar[2];
     __shared__ uint32_t tmem_base_s;
@@ -219,7 +309,9 @@ __global__ void __launch_bounds__(32 * (EW + 4), EW == 8 ? 2 : 4) tcconv_kernel(
             const bool st = (p.pool == 2) ? (row_ok && !(lane & 1)) : row_ok;
             const int t0 = (p.pool == 2) ? (srow >> 1) : p.ph * srow;
             const int64_t orow0 = (int64_t)seq * p.T_out + t0;
-            if (!(p.dbg & 4)) {
+            if constexpr (FLAGS >= 0) {
+                if (!(p.dbg & 4)) tc_epilogue_fixed<NOUT, SPLIT, EW, FLAGS>(p, trow, half, lane, seq, srow, row_ok, g, s_bias, s_psc, s_psh);
+            } else if (!(p.dbg & 4)) {
 #pragma unroll
                 for (int cc = 0; cc < COLS; cc += CH) {
                     const int nb = half * COLS + cc;  // first accumulator column of this chunk
@@ -469,19 +561,24 @@ constexpr int tc_occupancy(size_t w_bytes, size_t a_bytes, int ncols2) {
     return 1;
 }
 constexpr size_t tc_up128(size_t v) { return (v + 127) & ~(size_t)127; }
-// epilogue warps of a compile-time layer shape: 8 when at most two CTAs share an SM
+// CTAs per SM of a compile-time layer shape; epilogue warps: 16 / 8 / 4 for 1 / 2 / more CTAs per SM
+constexpr int tc_epi_warps_for(int occ, int nout) { return occ == 1 && nout >= 64 ? 16 : occ <= 2 ? 8 : 4; }
 template <int NOUT, int SPLIT, int NTAPS, int NQ>
-constexpr int tc_epi_warps() {
+constexpr int tc_occ_fixed() {
     constexpr int blocks = NQ == 0 ? NTAPS : NTAPS * NQ;
     constexpr int cin8 = NQ == 0 ? 1 : 2 * NQ;
     constexpr int rows = 128 + (NQ == 0 ? 2 * NTAPS - 1 : NTAPS - 1);
     return tc_occupancy(tc_up128((size_t)blocks * SPLIT * 2 * NOUT * 16), tc_up128((size_t)SPLIT * cin8 * rows * 16),
-                        2 * (NOUT < 32 ? 32 : NOUT)) <= 2 ? 8 : 4;
+                        2 * (NOUT < 32 ? 32 : NOUT));
+}
+template <int NOUT, int SPLIT, int NTAPS, int NQ>
+constexpr int tc_epi_warps() {
+    return tc_epi_warps_for(tc_occ_fixed<NOUT, SPLIT, NTAPS, NQ>(), NOUT);
 }
 
-template <int NOUT, int SPLIT, int NTAPS, int NQ, int EW>
+template <int NOUT, int SPLIT, int NTAPS, int NQ, int EW, int FLAGS>
 static int launch_tc(const TcP &p, dim3 grid, size_t smem, cudaStream_t s) {
-    auto kern = tcconv_kernel<NOUT, SPLIT, NTAPS, NQ, EW>;
+    auto kern = tcconv_kernel<NOUT, SPLIT, NTAPS, NQ, EW, FLAGS>;
     static size_t attr = 0;
     if (smem > attr) {
         VP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -576,26 +673,31 @@ int tc_launch(const TcLayer &L, const TcIO &io, cudaStream_t s) {
     // compile-time MMA schedules for the layer shapes of the EQTransformer (N, taps | tap pairs, channel pairs)
     static const bool generic_only = getenv("VP_TC_GENERIC") && atoi(getenv("VP_TC_GENERIC")) != 0;
     const int st = L.sched_taps, sq = L.sched_nq;
-#define VP_TC_FIXED(N, T, Q)                                                                      \
-    if (!generic_only && L.nout == N && st == T && sq == Q) {                           \
-        if (L.split == 2) return launch_tc<N, 2, T, Q, tc_epi_warps<N, 2, T, Q>()>(p, grid, smem, s); \
-        return launch_tc<N, 1, T, Q, tc_epi_warps<N, 1, T, Q>()>(p, grid, smem, s);               \
+    // epilogue options of this launch; the compile-time epilogue needs the common case: 16-bit output, ReLU (or the
+    // res-CNN extras carrying the activation), no padding columns
+    const bool extra = io.res || io.y32 || io.post_scale;
+    const bool plain = io.out_fmt == 0 && L.nout == L.ph * L.cout && io.cout_cl == L.cout && !p.dbg &&
+                       (extra ? (io.act == ACT_RELU || io.act == ACT_NONE) : io.act == ACT_RELU);
+    const int flags = plain ? ((io.pool == 2 ? 1 : 0) | (L.ph == 2 ? 2 : 0) | (extra ? 4 : 0)) : -1;
+#define VP_TC_FIXED(N, T, Q, F)                                                                                  \
+    if (!generic_only && L.nout == N && st == T && sq == Q && flags == F) {                                      \
+        if (L.split == 2) return launch_tc<N, 2, T, Q, tc_epi_warps<N, 2, T, Q>(), F>(p, grid, smem, s);         \
+        return launch_tc<N, 1, T, Q, tc_epi_warps<N, 1, T, Q>(), F>(p, grid, smem, s);                           \
     }
-    VP_TC_FIXED(16, 6, 0);   // encoder.convs.0 (3 -> 8, k11), heads (8 -> 1, k11)
-    VP_TC_FIXED(16, 5, 0);   // encoder.convs.1 (8 -> 16, k9)
-    VP_TC_FIXED(16, 7, 1);   // encoder.convs.2 (16 -> 16, k7), decoder.convs.6 polyphase
-    VP_TC_FIXED(32, 7, 1);   // encoder.convs.3 (16 -> 32, k7)
-    VP_TC_FIXED(32, 5, 2);   // encoder.convs.4 (32 -> 32, k5), decoder.convs.4 polyphase
-    VP_TC_FIXED(64, 5, 2);   // encoder.convs.5 (32 -> 64, k5), decoder.convs.3 polyphase
-    VP_TC_FIXED(64, 3, 4);   // encoder.convs.6, res-CNN k3 (64 -> 64)
-    VP_TC_FIXED(64, 2, 4);   // res-CNN k2 (64 -> 64)
-    VP_TC_FIXED(128, 3, 1);  // decoder.convs.0 polyphase (16 -> 2 x 64)
-    VP_TC_FIXED(128, 3, 4);  // decoder.convs.1 polyphase (64 -> 2 x 64)
-    VP_TC_FIXED(32, 5, 4);   // decoder.convs.2 (64 -> 32, k5, loader-side up-sampling)
-    VP_TC_FIXED(32, 5, 1);   // decoder.convs.5 polyphase (16 -> 2 x 16)
+    VP_TC_FIXED(16, 5, 0, 1);   // encoder.convs.1 (8 -> 16, k9) + pool
+    VP_TC_FIXED(16, 7, 1, 1);   // encoder.convs.2 (16 -> 16, k7) + pool
+    VP_TC_FIXED(32, 7, 1, 1);   // encoder.convs.3 (16 -> 32, k7) + pool
+    VP_TC_FIXED(32, 5, 2, 1);   // encoder.convs.4 (32 -> 32, k5) + pool
+    VP_TC_FIXED(64, 5, 2, 1);   // encoder.convs.5 (32 -> 64, k5) + pool
+    VP_TC_FIXED(64, 3, 4, 5);   // encoder.convs.6 (64 -> 64, k3) + pool -> residual stream + relu(bn(x))
+    VP_TC_FIXED(64, 3, 4, 4);   // res-CNN k3 convs
+    VP_TC_FIXED(64, 2, 4, 4);   // res-CNN k2 convs
+    VP_TC_FIXED(128, 3, 1, 2);  // decoder.convs.0 polyphase (16 -> 2 x 64)
+    VP_TC_FIXED(128, 3, 4, 2);  // decoder.convs.1 polyphase (64 -> 2 x 64)
+    VP_TC_FIXED(32, 5, 4, 0);   // decoder.convs.2 (64 -> 32, k5, loader-side up-sampling)
 #undef VP_TC_FIXED
 #define VP_TC_CASE(N, S) \
-    if (L.nout == N && L.split == S) return launch_tc<N, S, 0, 0, 4>(p, grid, smem, s)
+    if (L.nout == N && L.split == S) return launch_tc<N, S, 0, 0, 4, -1>(p, grid, smem, s)
     VP_TC_CASE(16, 2);
     VP_TC_CASE(32, 2);
     VP_TC_CASE(64, 2);
