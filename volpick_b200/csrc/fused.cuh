@@ -36,8 +36,6 @@ struct FzLayer {
     int T_out;     // valid global rows of the output level: rows outside [0, T_out) are conv zero padding
     int out_kind;  // 0: 16-bit planes for the next MMA layer, 1: fp32 planar [c][row] for the head
     int w_off;     // resident weights: byte offset in dynamic shared memory
-    int bias_off;  // resident bias block (B operand of the bias MMA): byte offset in dynamic shared memory
-    uint32_t term_a[FZ_MAX_TERMS], term_b[FZ_MAX_TERMS];
     uint8_t dep[FZ_MAX_TILES][2];  // producer steps this tile waits for, as distances back in the step sequence (0: none)
 };
 
@@ -46,6 +44,10 @@ struct FzLayer {
 constexpr int FZ_DEC_NOUT[4] = {64, 32, 32, 16};
 constexpr int FZ_DEC_NTAPS[4] = {5, 5, 5, 7};
 constexpr int FZ_DEC_NQ[4] = {2, 2, 1, 1};
+// f16x3 only: layers whose hi / lo weight splits are stacked along the MMA N (A_hi is then read once for the two
+// terms A_hi W_hi and A_hi W_lo: 2 instead of 3 A-tile reads per K step; the MMAs here are bound by the
+// shared-memory operand reads, 4 KB of A per MMA against 0.5 - 2 KB of B).  Needs 2 N <= FZ_NCOLS accumulator columns.
+constexpr bool FZ_DEC_STACK[4] = {false, true, true, true};
 
 // Decoder tail: decoder.convs.3-6 + sigmoid(conv k11) head for the three EQTransformer decoders.
 struct FzDecB {
@@ -57,9 +59,9 @@ struct FzDecB {
     int tiles_per_seq, B;
     int row_off0;        // 375-level row of tile 0 (> 0 when the leading output samples are blinded and need not be computed)
     int pipe_stride;     // bytes of one pipeline's arena (in[2] | X | Y)
-    int ones_off;        // A operand of the bias MMA ([1,1,1,0,...] rows)
     int blob_off;        // resident weight blob: smem byte offset, bytes per group
     int blob_bytes;
+    int bias_off;        // fp32 biases [layer][FZ_NCOLS] inside the blob: smem byte offset
     const uint16_t *blob;  // device: [group][blob_bytes / 2]
     float head_w[3][88];  // [group][c * 11 + k]
     float head_b[3];

@@ -13,8 +13,9 @@
 // sequence are written as zeros (they are the convs' zero padding).  Every layer is the polyphase implicit
 // GEMM of tcconv.cu: a tap is a row offset of the SAME shared-memory activation buffer (no-swizzle K-major
 // UMMA descriptors), accumulators in TMEM, f16x3 (fp16 hi/lo split, fp32-equivalent) or bf16 operands.  The
-// bias enters through one extra MMA per tile (a constant [1,1,1,0..] A tile times the bias split in three
-// 16-bit terms), so the epilogue is ReLU + 16-bit split + store only.
+// kernel is bound by the shared-memory reads of the MMA operands (4 KB of A per MMA for N = 16 .. 64), so in
+// f16x3 mode the layers with N <= 32 stack W_hi and W_lo along N (two A-tile reads per K step instead of three)
+// and the epilogue adds the two column halves, the bias and the ReLU before the 16-bit split + store.
 //
 // A CTA runs FZ_NPIPE independent pipelines over alternating work items (the layer chain of one item is a
 // dependency chain: while one pipeline's epilogue converts a tile, the other pipeline's MMAs own the tensor
@@ -32,76 +33,89 @@ namespace vp {
 
 // ------------------------------------------------------------------------------------------ epilogues
 template <int SPLIT>
-__device__ __forceinline__ void fz_pack8_relu(const uint32_t *v, uint4 &hi, uint4 &lo) {
-    uint32_t h[4], l[4];
+__device__ __forceinline__ void fz_pack8(const float *v, bool valid, uint4 &hi, uint4 &lo) {
+    if (valid) {
+        pack8_split16<SPLIT>(v, hi, lo);
+    } else {
+        hi = make_uint4(0u, 0u, 0u, 0u);
+        lo = hi;
+    }
+}
+
+// Accumulator columns [phase][channel] of this thread's row -> v[2 * COUTP] = relu(acc (+ stacked half) + bias).
+template <int COUTP, bool STACK>
+__device__ __forceinline__ void fz_load_row(const float *bias /*shared memory, [2 * COUTP]*/, uint32_t tacc, float (&v)[2 * COUTP]) {
+    constexpr int N = 2 * COUTP;
+    uint32_t r[STACK ? 2 * N : N];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float a = fmaxf(__uint_as_float(v[2 * i]), 0.f), b = fmaxf(__uint_as_float(v[2 * i + 1]), 0.f);
-        if (SPLIT == 2) {
-            const __half2 hh = __floats2half2_rn(a, b);
-            const float2 hf = __half22float2(hh);
-            const __half2 ll = __floats2half2_rn(a - hf.x, b - hf.y);
-            h[i] = *reinterpret_cast<const uint32_t *>(&hh);
-            l[i] = *reinterpret_cast<const uint32_t *>(&ll);
-        } else {
-            const __nv_bfloat162 bb = __floats2bfloat162_rn(a, b);
-            h[i] = *reinterpret_cast<const uint32_t *>(&bb);
-            l[i] = 0u;
+    for (int c0 = 0; c0 < (STACK ? 2 * N : N); c0 += 16) {
+        uint32_t(&r16)[16] = *reinterpret_cast<uint32_t(*)[16]>(&r[c0]);
+        tmem_ld16_nowait(tacc + (uint32_t)c0, r16);
+    }
+    tmem_ld_wait();
+#pragma unroll
+    for (int n = 0; n < N; n += 4) {
+        const float4 b4 = *reinterpret_cast<const float4 *>(bias + n);
+        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float a = __uint_as_float(r[n + e]);
+            if (STACK) a += __uint_as_float(r[N + n + e]);
+            v[n + e] = fmaxf(a + bb[e], 0.f);
         }
     }
-    hi = make_uint4(h[0], h[1], h[2], h[3]);
-    lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 // Polyphase layer -> 16-bit planes of the next layer.  Thread = one input row s; it owns output rows 2s, 2s+1.
-template <int COUTP, int SPLIT>
-__device__ __forceinline__ void fz_epi16(const FzLayer &L, uint32_t tacc, int t, int r, int R0, uint8_t *arena) {
+// The two rows are 32 bytes apart: a plain "phase 0, then phase 1" store has consecutive lanes 32 bytes apart
+// (2-way bank conflict).  Instead lanes with bit 2 set store phase 1 first: every quarter warp then covers eight
+// distinct 16-byte bank groups.
+template <int COUTP, int SPLIT, bool STACK>
+__device__ __forceinline__ void fz_epi16(const FzLayer &L, const float *bias, uint32_t tacc, int t, int r, int R0, uint8_t *arena) {
     constexpr int P = COUTP / 8;
     const int s_rel = L.s_lo + 128 * t + r;
     const int lrow0 = 2 * s_rel - L.out_lo;
     const int grow0 = 2 * ((R0 << L.lvl) + s_rel);  // R0: 375-level row of the work item's origin
     const uint32_t plane = (uint32_t)L.out_rows * 16u;
+    float v[2 * COUTP];
+    fz_load_row<COUTP, STACK>(bias, tacc, v);
+    const int sel = (r >> 2) & 1;  // phase stored first by this lane
+    const int rowA = lrow0 + sel, rowB = lrow0 + 1 - sel;
+    const bool inA = (unsigned)rowA < (unsigned)L.out_rows, inB = (unsigned)rowB < (unsigned)L.out_rows;
+    const bool valid0 = (unsigned)grow0 < (unsigned)L.T_out, valid1 = (unsigned)(grow0 + 1) < (unsigned)L.T_out;
+    uint8_t *dstA = arena + L.out_off + (size_t)rowA * 16, *dstB = arena + L.out_off + (size_t)rowB * 16;
 #pragma unroll
-    for (int phi = 0; phi < 2; ++phi) {
-        const int lrow = lrow0 + phi;
-        const bool inb = (unsigned)lrow < (unsigned)L.out_rows;
-        const bool valid = (unsigned)(grow0 + phi) < (unsigned)L.T_out;
-        uint32_t v[COUTP];
-#pragma unroll
-        for (int c0 = 0; c0 < COUTP; c0 += 16) {
-            uint32_t(&v16)[16] = *reinterpret_cast<uint32_t(*)[16]>(&v[c0]);
-            tmem_ld16_nowait(tacc + (uint32_t)(phi * COUTP + c0), v16);
-        }
-        tmem_ld_wait();
-        if (inb) {
-            uint8_t *dst = arena + L.out_off + (size_t)lrow * 16;
-#pragma unroll
-            for (int pl = 0; pl < P; ++pl) {
-                uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
-                if (valid) fz_pack8_relu<SPLIT>(&v[pl * 8], hi, lo);
-                *reinterpret_cast<uint4 *>(dst + pl * plane) = hi;
-                if (SPLIT == 2) *reinterpret_cast<uint4 *>(dst + (P + pl) * plane) = lo;
-            }
+    for (int pl = 0; pl < P; ++pl) {
+        uint4 h0, l0, h1, l1;
+        fz_pack8<SPLIT>(&v[pl * 8], valid0, h0, l0);
+        fz_pack8<SPLIT>(&v[COUTP + pl * 8], valid1, h1, l1);
+        const uint4 hA = sel ? h1 : h0, hB = sel ? h0 : h1;
+        if (inA) *reinterpret_cast<uint4 *>(dstA + pl * plane) = hA;
+        if (inB) *reinterpret_cast<uint4 *>(dstB + pl * plane) = hB;
+        if (SPLIT == 2) {
+            const uint4 lA = sel ? l1 : l0, lB = sel ? l0 : l1;
+            if (inA) *reinterpret_cast<uint4 *>(dstA + (P + pl) * plane) = lA;
+            if (inB) *reinterpret_cast<uint4 *>(dstB + (P + pl) * plane) = lB;
         }
     }
 }
 
 // Last polyphase layer (8 channels per phase) -> fp32 planar [c][row] for the CUDA-core head.
-__device__ __forceinline__ void fz_epi32(const FzLayer &L, uint32_t tacc, int t, int r, int R0, uint8_t *arena) {
+template <bool STACK>
+__device__ __forceinline__ void fz_epi32(const FzLayer &L, const float *bias, uint32_t tacc, int t, int r, int R0, uint8_t *arena) {
     const int s_rel = L.s_lo + 128 * t + r;
     const int lrow0 = 2 * s_rel - L.out_lo;  // even
-    const int grow0 = 2 * ((R0 << L.lvl) + s_rel);  // R0: 375-level row of the work item's origin
-    uint32_t v[16];
-    tmem_ld16_nowait(tacc, v);
-    tmem_ld_wait();
+    const int grow0 = 2 * ((R0 << L.lvl) + s_rel);
+    float v[16];
+    fz_load_row<8, STACK>(bias, tacc, v);
     if ((unsigned)lrow0 < (unsigned)L.out_rows) {  // out_rows is even: both phases are in range together
         const bool valid = (unsigned)grow0 < (unsigned)L.T_out;  // T_out even: both phases valid together
         float *d = reinterpret_cast<float *>(arena + L.out_off) + lrow0;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
             float2 o;
-            o.x = valid ? fmaxf(__uint_as_float(v[c]), 0.f) : 0.f;
-            o.y = valid ? fmaxf(__uint_as_float(v[8 + c]), 0.f) : 0.f;
+            o.x = valid ? v[c] : 0.f;
+            o.y = valid ? v[8 + c] : 0.f;
             *reinterpret_cast<float2 *>(d + (size_t)c * L.out_rp) = o;
         }
     }
@@ -147,20 +161,18 @@ __device__ __forceinline__ void fz_head(const FzDecB &p, int g, int b, int R0, i
 }
 
 // One layer of one work item on the issuer warp: per M tile wait for the accumulator buffer and the producer
-// tiles, then issue the bias MMA + the layer's compile-time MMA schedule.
+// tiles, then issue the layer's compile-time MMA schedule (the first MMA overwrites the accumulator).
 template <int LYR, int SPLIT>
 __device__ __forceinline__ void fz_issue_layer(const FzDecB &p, int pp, int slot, int n, uint32_t &i, uint32_t tmem_base,
-                                               uint32_t arena16, uint32_t sB16, uint32_t ones_lo, uint64_t (*in_full)[2],
-                                               uint64_t (*in_empty)[2], uint64_t (*acc_full)[FZ_NBUF],
-                                               uint64_t (*done_bar)[FZ_NBUF]) {
+                                               uint32_t arena16, uint32_t sB16, uint64_t (*in_full)[2], uint64_t (*in_empty)[2],
+                                               uint64_t (*acc_full)[FZ_NBUF], uint64_t (*done_bar)[FZ_NBUF]) {
     constexpr int l = LYR;
     constexpr int NOUT = FZ_DEC_NOUT[l];
-    const uint64_t desc_hi = (uint64_t)(0x4000u | (128u >> 4)) << 32;  // version 1, SBO = 128 B
+    constexpr bool STACK = SPLIT == 2 && FZ_DEC_STACK[l];
     const FzLayer &L = p.L[l];
     const uint32_t idesc = umma_idesc(NOUT, SPLIT == 2 ? 0 : 1);
     const uint32_t in16 = arena16 + ((uint32_t)(L.in_off + (l == 0 ? slot * p.in_slot_bytes : 0)) >> 4) + (uint32_t)L.a_row0;
     const uint32_t w16 = sB16 + ((uint32_t)L.w_off >> 4);
-    const uint32_t bias_lo = (sB16 + ((uint32_t)L.bias_off >> 4)) | ((uint32_t)NOUT << 16);
     const uint32_t in_rows = (uint32_t)L.in_rows;
     for (int t = 0; t < L.n_tiles; ++t, ++i) {
         const uint32_t buf = i & (FZ_NBUF - 1);
@@ -179,8 +191,10 @@ __device__ __forceinline__ void fz_issue_layer(const FzDecB &p, int pp, int slot
         const uint32_t a16 = in16 + (uint32_t)t * 128u;
         const uint32_t d_tmem = tmem_base + (pp * FZ_NBUF + buf) * FZ_NCOLS;
         if (elect_one()) {
-            umma_f16(d_tmem, desc_hi | (uint64_t)ones_lo, desc_hi | (uint64_t)bias_lo, idesc, 0u);  // D = bias
-            umma_conv_tile<NOUT, SPLIT, FZ_DEC_NTAPS[l], FZ_DEC_NQ[l]>(d_tmem, a16, in_rows, w16, idesc, 1u);
+            if constexpr (STACK)
+                umma_conv_tile_stacked<NOUT, FZ_DEC_NTAPS[l], FZ_DEC_NQ[l]>(d_tmem, a16, in_rows, w16, umma_idesc(2 * NOUT, 0), idesc, 0u);
+            else
+                umma_conv_tile<NOUT, SPLIT, FZ_DEC_NTAPS[l], FZ_DEC_NQ[l]>(d_tmem, a16, in_rows, w16, idesc, 0u);
             umma_commit(&acc_full[pp][buf]);
             if (l == 0 && t == L.n_tiles - 1) umma_commit(&in_empty[pp][slot]);
         }
@@ -215,18 +229,9 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) decb_kernel(const __grid_consta
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(&tmem_base_s, FZ_NPIPE * FZ_NBUF * FZ_NCOLS);
-    {   // resident weights + bias blocks of this decoder, and the constant A tile of the bias MMA
+    {   // resident weights of this decoder
         const uint4 *wg = reinterpret_cast<const uint4 *>(p.blob + (long long)g * (p.blob_bytes / 2));
         for (int idx = tid; idx < p.blob_bytes / 16; idx += FZ_THREADS) cp_async16(sbase + p.blob_off + idx * 16, wg + idx, 16u);
-        const uint32_t one = (SPLIT == 2) ? 0x3C00u : 0x3F80u;  // 1.0 in fp16 / bf16
-        for (int idx = tid; idx < 256; idx += FZ_THREADS) {
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (idx < 128) {
-                v.x = one | (one << 16);
-                v.y = one;
-            }
-            *reinterpret_cast<uint4 *>(fz_smem + p.ones_off + idx * 16) = v;
-        }
     }
     cp_async_wait_all();
     fence_proxy_async();
@@ -264,16 +269,15 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) decb_kernel(const __grid_consta
         // ================= tcgen05 issuers =================
         const int pp = warp - FZ_NPIPE;
         const uint32_t sB16 = sbase >> 4;
-        const uint32_t ones_lo = (sB16 + ((uint32_t)p.ones_off >> 4)) | (128u << 16);
         const uint32_t arena16 = (sbase + pp * p.pipe_stride) >> 4;
         uint32_t i = 0;
         int n = 0;
         for (int item = blockIdx.x + pp * gridDim.x; item < n_items; item += FZ_NPIPE * gridDim.x, ++n) {
             const int slot = n & 1;
-            fz_issue_layer<0, SPLIT>(p, pp, slot, n, i, tmem_base, arena16, sB16, ones_lo, in_full, in_empty, acc_full, done_bar);
-            fz_issue_layer<1, SPLIT>(p, pp, slot, n, i, tmem_base, arena16, sB16, ones_lo, in_full, in_empty, acc_full, done_bar);
-            fz_issue_layer<2, SPLIT>(p, pp, slot, n, i, tmem_base, arena16, sB16, ones_lo, in_full, in_empty, acc_full, done_bar);
-            fz_issue_layer<3, SPLIT>(p, pp, slot, n, i, tmem_base, arena16, sB16, ones_lo, in_full, in_empty, acc_full, done_bar);
+            fz_issue_layer<0, SPLIT>(p, pp, slot, n, i, tmem_base, arena16, sB16, in_full, in_empty, acc_full, done_bar);
+            fz_issue_layer<1, SPLIT>(p, pp, slot, n, i, tmem_base, arena16, sB16, in_full, in_empty, acc_full, done_bar);
+            fz_issue_layer<2, SPLIT>(p, pp, slot, n, i, tmem_base, arena16, sB16, in_full, in_empty, acc_full, done_bar);
+            fz_issue_layer<3, SPLIT>(p, pp, slot, n, i, tmem_base, arena16, sB16, in_full, in_empty, acc_full, done_bar);
         }
     } else {
         // ================= epilogue warps + head =================
@@ -291,9 +295,11 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) decb_kernel(const __grid_consta
                     mbar_wait(&acc_full[pp][buf], (i / FZ_NBUF) & 1);
                     tc_fence_after();
                     const uint32_t tacc = tmem_base + (pp * FZ_NBUF + buf) * FZ_NCOLS + ((uint32_t)(q * 32) << 16);
-                    if (L.out_kind == 1) fz_epi32(L, tacc, t, r, R0, arena);
-                    else if (L.coutp == 32) fz_epi16<32, SPLIT>(L, tacc, t, r, R0, arena);
-                    else fz_epi16<16, SPLIT>(L, tacc, t, r, R0, arena);
+                    constexpr bool ST = SPLIT == 2;  // stacked layers: FZ_DEC_STACK (layers 1-3)
+                    const float *bias = reinterpret_cast<const float *>(fz_smem + p.bias_off) + l * FZ_NCOLS;
+                    if (l == 0) fz_epi16<32, SPLIT, ST && FZ_DEC_STACK[0]>(L, bias, tacc, t, r, R0, arena);
+                    else if (l == 3) fz_epi32<ST && FZ_DEC_STACK[3]>(L, bias, tacc, t, r, R0, arena);
+                    else fz_epi16<16, SPLIT, ST && FZ_DEC_STACK[1]>(L, bias, tacc, t, r, R0, arena);
                     fence_proxy_async();  // generic-proxy writes -> visible to the tensor-core (async) proxy
                     tc_fence_before();
                     __syncwarp();
@@ -313,23 +319,6 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) decb_kernel(const __grid_consta
 // ------------------------------------------------------------------------------------------ host: plan
 static inline int fdiv2(int a) { return (a >= 0) ? a / 2 : -((-a + 1) / 2); }
 static inline int cdiv2(int a) { return -fdiv2(-a); }
-
-static void bias_terms(float b, int split, uint16_t out[3]) {
-    float rem = b;
-    for (int k = 0; k < 3; ++k) {
-        float v;
-        if (split == 2) {
-            const __half h = __float2half_rn(rem);
-            out[k] = __half_as_ushort(h);
-            v = __half2float(h);
-        } else {
-            const __nv_bfloat16 h = __float2bfloat16_rn(rem);
-            out[k] = __bfloat16_as_ushort(h);
-            v = __bfloat162float(h);
-        }
-        rem -= v;
-    }
-}
 
 int decb_build(DecBPlan &plan, const TcLayer *dec, int split, int m, const float (*head_w)[88], const float *head_b) {
     FzDecB &p = plan.p;
@@ -364,7 +353,8 @@ int decb_build(DecBPlan &plan, const TcLayer *dec, int split, int m, const float
         hi[l] = s_hi + o_min + ntaps - 1;
         if (l > 0 && (lo[l] & 1)) --lo[l];
     }
-    // shared memory: per pipeline { in[2] | X | Y }, then the bias-MMA A tile, then the weight blob
+    static_assert(FZ_DEC_STACK[1] == FZ_DEC_STACK[2] && !FZ_DEC_STACK[0], "epilogue dispatch in decb_kernel");
+    // shared memory: per pipeline { in[2] | X | Y }, then the weight blob
     const int esz = 16 * split;  // bytes per (row, plane)
     auto lvl_bytes = [&](int k) {
         if (k == NL) return (size_t)8 * (size_t)(((hi[k] - lo[k]) + 12 + 3) & ~3) * 4;
@@ -376,20 +366,20 @@ int decb_build(DecBPlan &plan, const TcLayer *dec, int split, int m, const float
     const size_t off_x = 2 * (size_t)p.in_slot_bytes;
     const size_t off_y = off_x + up128(std::max(lvl_bytes(2), lvl_bytes(4)));
     p.pipe_stride = (int)(off_y + up128(std::max(lvl_bytes(1), lvl_bytes(3))));
-    p.ones_off = FZ_NPIPE * p.pipe_stride;
-    p.blob_off = p.ones_off + 4096;
+    p.blob_off = FZ_NPIPE * p.pipe_stride;
     const size_t lvl_off[5] = {0, off_y, off_x, off_y, off_x};
-    // blob per group: for each layer { weight blocks, bias block }
+    // blob per group: the weight blocks of the four layers
     size_t blob = 0;
-    size_t w_rel[4], b_rel[4];
+    size_t w_rel[4];
     for (int l = 0; l < NL; ++l) {
         const TcLayer &TL = dec[3 + l];
         w_rel[l] = blob;
         blob += up128((size_t)TL.n_blocks * split * 2 * TL.nout * 16);
-        b_rel[l] = blob;
-        blob += up128((size_t)2 * TL.nout * 16);
     }
+    const size_t bias_rel = blob;  // fp32 [layer][FZ_NCOLS]
+    blob += up128((size_t)NL * FZ_NCOLS * sizeof(float));
     p.blob_bytes = (int)blob;
+    p.bias_off = p.blob_off + (int)bias_rel;
     plan.blob.assign((size_t)G * blob / 2, 0);
     int step = 0;
     int step0[4];
@@ -399,7 +389,9 @@ int decb_build(DecBPlan &plan, const TcLayer *dec, int split, int m, const float
         L.cin8 = TL.cin / 8;
         L.nout = TL.nout;
         L.coutp = (TL.cout + 7) / 8 * 8;
-        VP_REQUIRE(L.nout == 2 * L.coutp && L.nout <= FZ_NCOLS, VP_ERR_UNSUPPORTED, "decb: layer %d N=%d coutp=%d", 3 + l, L.nout, L.coutp);
+        const bool stack = split == 2 && FZ_DEC_STACK[l];
+        VP_REQUIRE(L.nout == 2 * L.coutp && (stack ? 2 : 1) * L.nout <= FZ_NCOLS, VP_ERR_UNSUPPORTED, "decb: layer %d N=%d coutp=%d", 3 + l,
+                   L.nout, L.coutp);
         L.n_tiles = n_tiles[l];
         L.in_off = (int)lvl_off[l];
         L.in_rows = hi[l] - lo[l];
@@ -413,56 +405,47 @@ int decb_build(DecBPlan &plan, const TcLayer *dec, int split, int m, const float
         L.T_out = p.T0 << (l + 1);
         L.out_kind = (l == NL - 1) ? 1 : 0;
         VP_REQUIRE(L.out_kind == 0 || (L.coutp == 8 && L.out_rows % 2 == 0), VP_ERR_UNSUPPORTED, "decb: last layer must have 8 channels");
-        VP_REQUIRE(L.out_kind == 1 || L.coutp == 32 || L.coutp == 16, VP_ERR_UNSUPPORTED, "decb: coutp %d", L.coutp);
+        VP_REQUIRE(L.out_kind == 1 || L.coutp == (l == 0 ? 32 : 16), VP_ERR_UNSUPPORTED, "decb: coutp %d of layer %d", L.coutp, 3 + l);
         L.w_off = p.blob_off + (int)w_rel[l];
-        L.bias_off = p.blob_off + (int)b_rel[l];
-        const size_t wl_elems = (size_t)TL.n_blocks * split * 2 * TL.nout * 8;
+        // TcLayer blocks: [group][block][split][k-half][nout][8]; stacked layers want [block][k-half][split * nout + n][8]
+        const size_t blk_elems = (size_t)split * 2 * TL.nout * 8;
         for (int g = 0; g < G; ++g) {
-            uint16_t *dst = plan.blob.data() + (size_t)g * blob / 2;
-            std::memcpy(dst + w_rel[l] / 2, TL.blocks.data() + (size_t)g * wl_elems, wl_elems * sizeof(uint16_t));
-            for (int n = 0; n < TL.nout; ++n) {  // bias block [k-half][n][8]: k-half 0 holds the three bias terms
-                uint16_t t3[3];
-                bias_terms(TL.bias[(size_t)g * TL.nout + n], split, t3);
-                for (int k = 0; k < 3; ++k) dst[b_rel[l] / 2 + (size_t)n * 8 + k] = t3[k];
+            uint16_t *dst = plan.blob.data() + (size_t)g * blob / 2 + w_rel[l] / 2;
+            const uint16_t *src = TL.blocks.data() + (size_t)g * TL.n_blocks * blk_elems;
+            if (!stack) {
+                std::memcpy(dst, src, (size_t)TL.n_blocks * blk_elems * sizeof(uint16_t));
+            } else {
+                for (int b = 0; b < TL.n_blocks; ++b)
+                    for (int sp = 0; sp < 2; ++sp)
+                        for (int kh = 0; kh < 2; ++kh)
+                            std::memcpy(dst + (size_t)b * blk_elems + ((size_t)kh * 2 * TL.nout + (size_t)sp * TL.nout) * 8,
+                                        src + (size_t)b * blk_elems + ((size_t)sp * 2 + kh) * TL.nout * 8, (size_t)TL.nout * 8 * sizeof(uint16_t));
             }
         }
-        // MMA schedule: tap j of channel pair q reads rows [a_row0 + j, ...) of planes 2q, 2q+1
+        for (int g = 0; g < G; ++g) {  // fp32 biases of this decoder, read by the epilogue from shared memory
+            float *bd = reinterpret_cast<float *>(plan.blob.data() + (size_t)g * blob / 2 + bias_rel / 2) + (size_t)l * FZ_NCOLS;
+            for (int n = 0; n < TL.nout; ++n) bd[n] = TL.bias[(size_t)g * TL.nout + n];
+        }
         const int a_row0 = (s_lo[l] + TL.row0) - lo[l];
         L.a_row0 = a_row0;
         VP_REQUIRE(TL.nout == FZ_DEC_NOUT[l] && TL.sched_taps == FZ_DEC_NTAPS[l] && TL.sched_nq == FZ_DEC_NQ[l] && a_row0 >= 0,
                    VP_ERR_UNSUPPORTED, "decb: layer %d (N=%d, %d taps, %d pairs) differs from the compiled schedule", 3 + l,
                    TL.nout, TL.sched_taps, TL.sched_nq);
-        const int nterm = (split == 2) ? 3 : 1;
-        L.n_terms = 0;
-        for (const TcMma &e : TL.mma)
-            for (int t = 0; t < nterm; ++t) {
-                const int sa = (t == 2) ? 1 : 0, sb = (t == 1) ? 1 : 0;
-                VP_REQUIRE(L.n_terms < FZ_MAX_TERMS, VP_ERR_UNSUPPORTED, "decb: too many MMAs per tile");
-                const uint32_t a_off = (uint32_t)((sa * L.cin8 + e.a_plane) * L.in_rows + a_row0 + e.a_row);
-                const uint32_t b_off = (uint32_t)((e.b_block * split + sb) * 2 * TL.nout);
-                L.term_a[L.n_terms] = a_off | ((uint32_t)L.in_rows << 16);
-                L.term_b[L.n_terms] = b_off | ((uint32_t)TL.nout << 16);
-                ++L.n_terms;
+        VP_REQUIRE((int)TL.mma.size() == FZ_DEC_NTAPS[l] * FZ_DEC_NQ[l], VP_ERR_UNSUPPORTED, "decb: layer %d has %d K steps", 3 + l,
+                   (int)TL.mma.size());
+        for (int j = 0, kk = 0; j < FZ_DEC_NTAPS[l]; ++j)  // the compiled schedule walks (tap, pair) with block j * NQ + q
+            for (int q = 0; q < FZ_DEC_NQ[l]; ++q, ++kk) {
+                const TcMma &e = TL.mma[kk];
+                VP_REQUIRE(e.a_row == j && e.a_plane == 2 * q && e.a_rowk == 0 && e.b_block == kk, VP_ERR_UNSUPPORTED,
+                           "decb: compiled MMA schedule of layer %d differs from the host-built one", 3 + l);
             }
-        {   // the kernel issues umma_conv_tile<NOUT, SPLIT, NTAPS, NQ>: its descriptors must equal the host-built schedule
-            int kk = 0;
-            bool same = L.n_terms == FZ_DEC_NTAPS[l] * FZ_DEC_NQ[l] * nterm;
-            for (int j = 0; same && j < FZ_DEC_NTAPS[l]; ++j)
-                for (int q = 0; q < FZ_DEC_NQ[l]; ++q)
-                    for (int t = 0; t < nterm; ++t, ++kk) {
-                        const int sa = (t == 2) ? 1 : 0, sb = (t == 1) ? 1 : 0;
-                        const uint32_t ea = (uint32_t)((sa * L.cin8 + 2 * q) * L.in_rows + a_row0 + j) | ((uint32_t)L.in_rows << 16);
-                        const uint32_t eb = (uint32_t)(((j * FZ_DEC_NQ[l] + q) * split + sb) * 2 * TL.nout) | ((uint32_t)TL.nout << 16);
-                        same = same && L.term_a[kk] == ea && L.term_b[kk] == eb;
-                    }
-            VP_REQUIRE(same, VP_ERR_UNSUPPORTED, "decb: compiled MMA schedule of layer %d differs from the host-built one", 3 + l);
-        }
-        // producer dependencies (previous layer's tiles that write the rows this tile reads)
         step0[l] = step;
+        const int ntaps_l = TL.halo + 1;
+        // producer dependencies (previous layer's tiles that write the rows this tile reads)
         for (int t = 0; t < L.n_tiles; ++t) {
             L.dep[t][0] = L.dep[t][1] = 0;
             if (l == 0) continue;
-            const int ntaps = TL.halo + 1;
+            const int ntaps = ntaps_l;
             const int first = a_row0 + 128 * t;
             const int last = std::min(first + 127 + ntaps - 1, L.in_rows - 1);
             VP_REQUIRE(2 * s_lo[l - 1] - lo[l] == 0 && first >= 0, VP_ERR_UNSUPPORTED, "decb: producer rows are not tile aligned");

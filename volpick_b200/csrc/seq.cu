@@ -63,57 +63,38 @@ __global__ void __launch_bounds__(128) lstm_kernel(const LstmP p) {
     float *yb = p.y + (int64_t)g * p.y_gs + b * p.y_bs + (int64_t)(dir * 16 + j) * p.T;
     const int T = p.T;
 
-    // Input projection W_ih x_t + b: independent of the recurrence, computed for TB time steps at once so that
-    // one shared-memory read of a W_ih column serves TB steps (with one step per read the 64-channel LSTM was
-    // bound by shared-memory bandwidth: 64 LDS.128 per thread per step), and one block ahead of the recurrence.
-    constexpr int TB = 4;
-    auto in_proj = [&](int s0, float4 (&a)[TB]) {
-#pragma unroll
-        for (int u = 0; u < TB; ++u) a[u] = bias;
-        int tt[TB];
-#pragma unroll
-        for (int u = 0; u < TB; ++u) {
-            const int sidx = (s0 + u < T) ? (s0 + u) : (T - 1);
-            tt[u] = dir ? (T - 1 - sidx) : sidx;
+    // input projection of one time step: independent of the recurrence, computed one step ahead so that its
+    // loads and FMAs overlap the shuffle / transcendental chain of the current step.  (Blocking it over 4 steps to
+    // save W_ih reads was measured SLOWER: 168 registers, one CTA fewer per SM, 1.31 -> 1.66 ms per station-day.)
+    auto in_proj = [&](int t) {
+        float4 a0 = bias, a1 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+        for (int ci = 0; ci < CIN; ci += 2) {
+            const float x0 = __ldg(xb + (int64_t)ci * T + t), x1 = __ldg(xb + (int64_t)(ci + 1) * T + t);
+            const float4 w0 = wi[ci * 16], w1 = wi[(ci + 1) * 16];
+            a0.x = fmaf(w0.x, x0, a0.x), a0.y = fmaf(w0.y, x0, a0.y), a0.z = fmaf(w0.z, x0, a0.z), a0.w = fmaf(w0.w, x0, a0.w);
+            a1.x = fmaf(w1.x, x1, a1.x), a1.y = fmaf(w1.y, x1, a1.y), a1.z = fmaf(w1.z, x1, a1.z), a1.w = fmaf(w1.w, x1, a1.w);
         }
-#pragma unroll 4
-        for (int ci = 0; ci < CIN; ++ci) {
-            const float4 w = wi[ci * 16];
-            const float *xr = xb + (int64_t)ci * T;
-#pragma unroll
-            for (int u = 0; u < TB; ++u) {
-                const float xv = __ldg(xr + tt[u]);
-                a[u].x = fmaf(w.x, xv, a[u].x), a[u].y = fmaf(w.y, xv, a[u].y), a[u].z = fmaf(w.z, xv, a[u].z), a[u].w = fmaf(w.w, xv, a[u].w);
-            }
-        }
+        return make_float4(a0.x + a1.x, a0.y + a1.y, a0.z + a1.z, a0.w + a1.w);
     };
 
     float h = 0.f, c = 0.f;
-    float4 ain[TB], anext[TB];
-    in_proj(0, ain);
-    for (int s0 = 0; s0 < T; s0 += TB) {
-        if (s0 + TB < T) in_proj(s0 + TB, anext);
+    float4 ain = in_proj(dir ? (T - 1) : 0);
+    for (int s = 0; s < T; ++s) {
+        const int t = dir ? (T - 1 - s) : s;
+        float4 a = ain, a2 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int u = 0; u < TB; ++u) {
-            const int s = s0 + u;
-            if (s < T) {
-                const int t = dir ? (T - 1 - s) : s;
-                float4 a = ain[u], a2 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int k = 0; k < 16; k += 2) {
-                    const float h0 = __shfl_sync(hmask, h, k, 16), h1 = __shfl_sync(hmask, h, k + 1, 16);
-                    a.x = fmaf(whh[k].x, h0, a.x), a.y = fmaf(whh[k].y, h0, a.y), a.z = fmaf(whh[k].z, h0, a.z), a.w = fmaf(whh[k].w, h0, a.w);
-                    a2.x = fmaf(whh[k + 1].x, h1, a2.x), a2.y = fmaf(whh[k + 1].y, h1, a2.y), a2.z = fmaf(whh[k + 1].z, h1, a2.z),
-                    a2.w = fmaf(whh[k + 1].w, h1, a2.w);
-                }
-                const float ig = sigmoidf_(a.x + a2.x), fg = sigmoidf_(a.y + a2.y), gg = tanhf_(a.z + a2.z), og = sigmoidf_(a.w + a2.w);
-                c = fmaf(fg, c, ig * gg);
-                h = og * tanhf_(c);
-                if (active) yb[t] = h;
-            }
+        for (int k = 0; k < 16; k += 2) {
+            const float h0 = __shfl_sync(hmask, h, k, 16), h1 = __shfl_sync(hmask, h, k + 1, 16);
+            a.x = fmaf(whh[k].x, h0, a.x), a.y = fmaf(whh[k].y, h0, a.y), a.z = fmaf(whh[k].z, h0, a.z), a.w = fmaf(whh[k].w, h0, a.w);
+            a2.x = fmaf(whh[k + 1].x, h1, a2.x), a2.y = fmaf(whh[k + 1].y, h1, a2.y), a2.z = fmaf(whh[k + 1].z, h1, a2.z),
+            a2.w = fmaf(whh[k + 1].w, h1, a2.w);
         }
-#pragma unroll
-        for (int u = 0; u < TB; ++u) ain[u] = anext[u];
+        if (s + 1 < T) ain = in_proj(dir ? (T - 2 - s) : (s + 1));
+        const float ig = sigmoidf_(a.x + a2.x), fg = sigmoidf_(a.y + a2.y), gg = tanhf_(a.z + a2.z), og = sigmoidf_(a.w + a2.w);
+        c = fmaf(fg, c, ig * gg);
+        h = og * tanhf_(c);
+        if (active) yb[t] = h;
     }
 }
 

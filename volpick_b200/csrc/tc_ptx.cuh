@@ -182,4 +182,29 @@ __device__ __forceinline__ void umma_conv_tile(uint32_t d_tmem, uint32_t a16, ui
             }
 }
 
+// f16x3 variant with the weight splits stacked along N: weight blocks [block][k-half][2 NOUT][8] (rows 0..NOUT-1 =
+// W_hi, NOUT..2 NOUT-1 = W_lo).  Per K step:  D[:, 0:2N] += A_hi [W_hi ; W_lo]   and   D[:, 0:N] += A_lo W_hi,
+// so the epilogue adds columns n and NOUT + n.  The first MMA (accumulate_first == 0) initialises all 2 NOUT columns.
+template <int NOUT, int NTAPS, int NQ>
+__device__ __forceinline__ void umma_conv_tile_stacked(uint32_t d_tmem, uint32_t a16, uint32_t rows, uint32_t w16, uint32_t idesc_2n,
+                                                       uint32_t idesc_n, uint32_t accumulate_first) {
+    static_assert(NQ > 0, "stacked schedule is for >= 16-channel inputs");
+    constexpr int CIN8 = 2 * NQ;
+    const uint64_t desc_hi = (uint64_t)(0x4000u | (128u >> 4)) << 32;  // version 1 (Blackwell), SBO = 128 B
+    const uint32_t a_base = a16 | (rows << 16);
+    const uint32_t b_base = w16 | ((uint32_t)(2 * NOUT) << 16);  // k-half stride = 2 NOUT rows
+#pragma unroll
+    for (int j = 0; j < NTAPS; ++j)
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const uint32_t a_hi = (uint32_t)(2 * q) * rows + (uint32_t)j;
+            const uint32_t a_lo = (uint32_t)(CIN8 + 2 * q) * rows + (uint32_t)j;
+            const uint32_t b_off = (uint32_t)((j * NQ + q) * 4 * NOUT);
+            const bool first = (j == 0 && q == 0);
+            umma_f16(d_tmem, desc_hi | (uint64_t)(a_base + a_hi), desc_hi | (uint64_t)(b_base + b_off), idesc_2n,
+                     first ? accumulate_first : 1u);
+            umma_f16(d_tmem, desc_hi | (uint64_t)(a_base + a_lo), desc_hi | (uint64_t)(b_base + b_off), idesc_n, 1u);
+        }
+}
+
 }  // namespace vp
