@@ -297,9 +297,14 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) decb_kernel(const __grid_consta
                     const uint32_t tacc = tmem_base + (pp * FZ_NBUF + buf) * FZ_NCOLS + ((uint32_t)(q * 32) << 16);
                     constexpr bool ST = SPLIT == 2;  // stacked layers: FZ_DEC_STACK (layers 1-3)
                     const float *bias = reinterpret_cast<const float *>(fz_smem + p.bias_off) + l * FZ_NCOLS;
-                    if (l == 0) fz_epi16<32, SPLIT, ST && FZ_DEC_STACK[0]>(L, bias, tacc, t, r, R0, arena);
-                    else if (l == 3) fz_epi32<ST && FZ_DEC_STACK[3]>(L, bias, tacc, t, r, R0, arena);
-                    else fz_epi16<16, SPLIT, ST && FZ_DEC_STACK[1]>(L, bias, tacc, t, r, R0, arena);
+                    // rows of this warp: outputs [2 (s_lo + 128 t + 32 q) - out_lo, + 64); a warp whose rows all fall
+                    // outside the output buffer (partially filled last tile of a layer) has nothing to convert
+                    const int wrow0 = 2 * (L.s_lo + 128 * t + 32 * q) - L.out_lo;
+                    if (wrow0 < L.out_rows && wrow0 + 64 > 0) {
+                        if (l == 0) fz_epi16<32, SPLIT, ST && FZ_DEC_STACK[0]>(L, bias, tacc, t, r, R0, arena);
+                        else if (l == 3) fz_epi32<ST && FZ_DEC_STACK[3]>(L, bias, tacc, t, r, R0, arena);
+                        else fz_epi16<16, SPLIT, ST && FZ_DEC_STACK[1]>(L, bias, tacc, t, r, R0, arena);
+                    }
                     fence_proxy_async();  // generic-proxy writes -> visible to the tensor-core (async) proxy
                     tc_fence_before();
                     __syncwarp();
