@@ -45,6 +45,26 @@ struct Layout {
     int64_t nwin, chunk, pred_len;
 };
 
+// Per host thread and device: a second stream + events for the piecewise H2D copy of host records.
+struct CopyPipe {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_ready = nullptr, ev_piece = nullptr;
+    int device = -1;
+};
+CopyPipe *copy_pipe() {
+    static thread_local CopyPipe pipes[16];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    CopyPipe &cp = pipes[dev];
+    if (cp.device != dev) {
+        if (cudaStreamCreateWithFlags(&cp.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&cp.ev_ready, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&cp.ev_piece, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        cp.device = dev;
+    }
+    return &cp;
+}
+
 int64_t default_chunk(const vp_model *) { return 4096; }  // measured: 1024 -> 4096 windows per launch group = -10 % forward time (EQTransformer)
 
 int make_layout(const vp_model *m, int64_t n, const vp_annotate_params *p, int trace_on_host, int64_t pick_cap,
@@ -115,24 +135,39 @@ extern "C" int vp_annotate(vp_model *m, const void *trace, int trace_on_host, in
     char *ws = (char *)workspace;
     const void *d_trace = trace;
     int64_t d_stride = ch_stride;
+    // Host record: (3, n) with channel stride ch_stride -> packed (3, n) on the device.  The copy is issued piecewise
+    // on a second stream, one piece per forward chunk (the samples that chunk's windows read), so that the H2D
+    // transfer of the record (104 MB for a station-day, ~2 ms over PCIe) overlaps the network instead of preceding it.
+    CopyPipe *pipe = nullptr;
+    int64_t copied = 0;  // samples [0, copied) of every channel are on their way
     if (trace_on_host) {
-        // (3, n) with channel stride ch_stride on the host -> packed (3, n) on the device
-        char *dst = ws + lo.off_trace;
-        for (int c = 0; c < 3; ++c)
-            VP_CUDA_CHECK(cudaMemcpyAsync(dst + (int64_t)c * n * 4, (const char *)trace + (int64_t)c * ch_stride * 4,
-                                          n * 4, cudaMemcpyHostToDevice, s));
-        d_trace = dst;
+        pipe = copy_pipe();
+        VP_REQUIRE(pipe != nullptr, VP_ERR_CUDA, "vp_annotate: cannot create the copy stream");
+        VP_CUDA_CHECK(cudaEventRecord(pipe->ev_ready, s));  // workspace reuse: earlier work of `s` reads the old record
+        VP_CUDA_CHECK(cudaStreamWaitEvent(pipe->stream, pipe->ev_ready, 0));
+        d_trace = ws + lo.off_trace;
         d_stride = n;
     }
+    auto copy_upto = [&](int64_t end) -> int {  // make samples [0, end) available to stream s
+        if (!trace_on_host || end <= copied) return VP_OK;
+        end = std::min(end, n);
+        char *dst = ws + lo.off_trace;
+        for (int c = 0; c < 3; ++c)
+            VP_CUDA_CHECK(cudaMemcpyAsync(dst + ((int64_t)c * n + copied) * 4, (const char *)trace + ((int64_t)c * ch_stride + copied) * 4,
+                                          (end - copied) * 4, cudaMemcpyHostToDevice, pipe->stream));
+        copied = end;
+        VP_CUDA_CHECK(cudaEventRecord(pipe->ev_piece, pipe->stream));
+        VP_CUDA_CHECK(cudaStreamWaitEvent(s, pipe->ev_piece, 0));
+        return VP_OK;
+    };
     int64_t *d_starts = (int64_t *)(ws + lo.off_starts);
+    std::vector<int64_t> h_starts((size_t)lo.nwin);
     {
-        std::vector<int64_t> h_starts((size_t)lo.nwin);
         int64_t cnt = 0;
         rc = vp_window_starts(n, L, p->overlap, h_starts.data(), lo.nwin, &cnt);
         if (rc != VP_OK) return rc;
-        // pageable -> the copy is staged by the runtime before the call returns
+        // pageable source: the runtime stages the copy before the call returns, h_starts may be reused freely
         VP_CUDA_CHECK(cudaMemcpyAsync(d_starts, h_starts.data(), (size_t)lo.nwin * 8, cudaMemcpyHostToDevice, s));
-        VP_CUDA_CHECK(cudaStreamSynchronize(s));
     }
     float *d_x = (float *)(ws + lo.off_x);
     float *d_y = (float *)(ws + lo.off_y);
@@ -141,6 +176,12 @@ extern "C" int vp_annotate(vp_model *m, const void *trace, int trace_on_host, in
     const bool fused_slice = !fused_off && kind == VP_KIND_EQTRANSFORMER && (p->precision == VP_PREC_F16X3 || p->precision == VP_PREC_BF16);
     for (int64_t w0 = 0; w0 < lo.nwin; w0 += lo.chunk) {
         const int64_t nw = std::min(lo.chunk, lo.nwin - w0);
+        {   // the record samples this chunk's windows read (starts ascend; the tail window ends at n)
+            int64_t need = 0;
+            for (int64_t i = w0 + nw - 1; i >= w0 && i >= w0 + nw - 2; --i) need = std::max(need, h_starts[(size_t)i] + L);
+            rc = copy_upto(w0 + nw >= lo.nwin ? n : need);
+            if (rc != VP_OK) return rc;
+        }
         // vp_stack discards the blinded margins of every window: the forward need not compute them
         const int64_t keep_lo = std::min(std::max<int64_t>(p->blinding[0], 0), L);
         const int64_t keep_hi = std::min(std::max<int64_t>(L - p->blinding[1], keep_lo), L);
