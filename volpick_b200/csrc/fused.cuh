@@ -88,4 +88,33 @@ void decb_free(DecBPlan &plan);
 int decb_launch(const DecBPlan &plan, const uint16_t *x, long long x_split, long long x_gs, int B, float *y, int keep_lo,
                 int keep_hi, cudaStream_t s);
 
+// Decoder middle: decoder.convs.1 + decoder.convs.2 (fused_deca.cu).
+struct FzDecA {
+    const uint16_t *x;  // [split][group][B][94][64] channel-last 16-bit (decoder.convs.0 output)
+    long long x_split, x_gs;
+    uint16_t *y;        // [split][group][B][375][32] channel-last 16-bit (input of the decoder tail)
+    long long y_split, y_gs;
+    const uint16_t *blob;  // device: per group { convs.1 blocks | convs.2 polyphase blocks | fp32 biases [128 + 64] }
+    const float *fixw;     // device: per group [2][32][64] = w[:, :, 4], w[:, :, 3] of decoder.convs.2 (crop correction)
+    int blob_off, blob_bytes, w1_off, w2_off, bias_off;  // shared-memory byte offsets
+    int B, smem_bytes;
+};
+
+struct DecAPlan {
+    FzDecA p;
+    int split = 0;
+    std::vector<uint16_t> blob;
+    std::vector<float> fixw;
+    uint16_t *d_blob = nullptr;
+    float *d_fixw = nullptr;
+    bool ready = false;
+};
+// dec1: decoder.convs.1 polyphase layer; dec2p: decoder.convs.2 built as a polyphase layer WITHOUT the crop;
+// w2: the three raw (32, 64, 5) weight tensors of decoder.convs.2
+int deca_build(DecAPlan &plan, const TcLayer &dec1, const TcLayer &dec2p, int split, const float *const *w2);
+int deca_upload(DecAPlan &plan);
+void deca_free(DecAPlan &plan);
+int deca_launch(const DecAPlan &plan, const uint16_t *x, long long x_split, long long x_gs, int B, uint16_t *y, long long y_split,
+                long long y_gs, cudaStream_t s);
+
 }  // namespace vp

@@ -1,0 +1,351 @@
+// Fused decoder middle on tcgen05 (sm_100a): decoder.convs.1 -> decoder.convs.2 in ONE kernel.
+//
+// Replaces, for the three EQTransformer decoders (decoder_d, pick_decoders.0/1; SURVEY.md Appendix A,
+// seisbench/models/eqtransformer.py Decoder), two nn.Upsample(x2) + F.conv1d + ReLU stages
+//     (B, 64, 94) --up x2, conv k5--> (B, 64, 188) --up x2, drop last, conv k5--> (B, 32, 375)
+// that the layer-by-layer path ran as two kernels with 48 KB per (window, decoder) of 16-bit activations written
+// to and re-read from HBM in 16-byte pieces (the measured bottleneck of both: their epilogues / loaders, not
+// their MMAs).  One work item = one (window, decoder) sequence; the 188-row intermediate lives in shared memory.
+//
+// Both layers run in the polyphase form of tcconv.cu (x2 up-sampling folded into the weights: row s yields
+// outputs 2s, 2s + 1 from taps s - 1, s, s + 1).  decoder.convs.2 crops the up-sampled signal to 375 samples
+// BEFORE the conv, i.e. u[375] is zero padding instead of x[187]; polyphase assumes u[375] = x[187], which only
+// touches outputs 373 (through w[:, :, 4]) and 374 (through w[:, :, 3]).  The two 32 x 64 matrix-vector products
+// are subtracted in fp32 on the CUDA cores (512 threads x 8 FMAs per work item).
+//
+// CTA = 18 warps: loader, tcgen05 issuer, 16 epilogue warps (TMEM lane quarter = warp % 4, four column slices).
+// Weights of both layers (147 KB in f16x3) stay resident in shared memory; one input slot and the intermediate
+// fill the rest, so a CTA runs ONE work item at a time and overlaps the next item's first layer with the
+// epilogues of the current one.
+#include <algorithm>
+#include <cstring>
+
+#include "fused.cuh"
+#include "tc_ptx.cuh"
+
+namespace vp {
+
+constexpr int DA_T0 = 94, DA_T1 = 188, DA_T2 = 375;
+constexpr int DA_IN_ROWS = DA_T0 + 2, DA_MID_ROWS = DA_T1 + 2;  // one zero row before and after the sequence
+constexpr int DA_EW = 16;
+constexpr int DA_THREADS = 32 * (2 + DA_EW);
+
+template <int SPLIT>
+__device__ __forceinline__ void da_pack8(const float *v, uint4 &hi, uint4 &lo) {
+    pack8_split16<SPLIT>(v, hi, lo);
+}
+
+template <int SPLIT>
+__global__ void __launch_bounds__(DA_THREADS, 1) deca_kernel(const __grid_constant__ FzDecA p) {
+    extern __shared__ __align__(128) uint8_t da_smem[];
+    __shared__ __align__(8) uint64_t in_full, in_free, acc_full[3], done_bar[3];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(16) float s_fix[2][32];  // crop correction of outputs 373 / 374
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = blockIdx.y;
+    const uint32_t sbase = smem_u32(da_smem);
+    constexpr uint32_t IN_BYTES = SPLIT * 8 * DA_IN_ROWS * 16, MID_BYTES = SPLIT * 8 * DA_MID_ROWS * 16;
+    uint8_t *s_in = da_smem, *s_mid = da_smem + IN_BYTES;
+    const float *s_bias = reinterpret_cast<const float *>(da_smem + p.bias_off);  // [128] dec1, [64] dec2
+
+    if (tid == 0) {
+        mbar_init(&in_full, 32);
+        mbar_init(&in_free, 1);
+        for (int i = 0; i < 3; ++i) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&done_bar[i], DA_EW);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_s, 256);
+    {   // resident weights + biases; zero rows around the sequences (never written again)
+        const uint4 *wg = reinterpret_cast<const uint4 *>(p.blob + (long long)g * (p.blob_bytes / 2));
+        for (int idx = tid; idx < p.blob_bytes / 16; idx += DA_THREADS) cp_async16(sbase + p.blob_off + idx * 16, wg + idx, 16u);
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        for (int idx = tid; idx < SPLIT * 8 * 2; idx += DA_THREADS) {
+            const int pl = idx >> 1, e = idx & 1;
+            *reinterpret_cast<uint4 *>(s_in + ((size_t)pl * DA_IN_ROWS + (e ? DA_IN_ROWS - 1 : 0)) * 16) = z;
+            *reinterpret_cast<uint4 *>(s_mid + ((size_t)pl * DA_MID_ROWS + (e ? DA_MID_ROWS - 1 : 0)) * 16) = z;
+        }
+    }
+    cp_async_wait_all();
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    const int n_items = p.B;
+
+    if (warp == 0) {
+        // ================= loader: rows 1 .. 94 of the input planes =================
+        const uint16_t *xg = p.x + (long long)g * p.x_gs;
+        int n = 0;
+        for (int b = blockIdx.x; b < n_items; b += gridDim.x, ++n) {
+            mbar_wait(&in_free, (n & 1) ^ 1);
+            const uint16_t *src0 = xg + (long long)b * DA_T0 * 64;
+            for (int idx = lane; idx < DA_T0 * 8; idx += 32) {
+                const int pl = idx & 7, t = idx >> 3;
+#pragma unroll
+                for (int s = 0; s < SPLIT; ++s)
+                    cp_async16(sbase + (uint32_t)(((s * 8 + pl) * DA_IN_ROWS + 1 + t) * 16), src0 + (long long)s * p.x_split + t * 64 + pl * 8, 16u);
+            }
+            cp_async_mbar_arrive_noinc(&in_full);
+        }
+        cp_async_wait_all();
+    } else if (warp == 1) {
+        // ================= tcgen05 issuer =================
+        const uint32_t fmt = SPLIT == 2 ? 0 : 1;
+        const uint32_t in16 = sbase >> 4, mid16 = (sbase + IN_BYTES) >> 4;
+        const uint32_t w1 = (sbase + p.w1_off) >> 4, w2 = (sbase + p.w2_off) >> 4;
+        int n = 0;
+        for (int b = blockIdx.x; b < n_items; b += gridDim.x, ++n) {
+            const uint32_t par = n & 1;
+            // ---- decoder.convs.1: rows s = 0 .. 127 (94 valid), N = 2 x 64
+            mbar_wait(&done_bar[0], par ^ 1);  // accumulator 0 drained (previous item)
+            mbar_wait(&in_full, par);
+            fence_proxy_async();
+            tc_fence_after();
+            if (elect_one()) {
+                umma_conv_tile<128, SPLIT, 3, 4>(tmem_base, in16, DA_IN_ROWS, w1, umma_idesc(128, fmt), 0u);
+                umma_commit(&acc_full[0]);
+                umma_commit(&in_free);
+            }
+            __syncwarp();
+            // ---- decoder.convs.2: two tiles of 128 rows (188 valid), N = 2 x 32; needs the whole intermediate
+            mbar_wait(&done_bar[0], par);
+            fence_proxy_async();
+            tc_fence_after();
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                mbar_wait(&done_bar[1 + t], par ^ 1);
+                tc_fence_after();
+                if (elect_one()) {
+                    umma_conv_tile<64, SPLIT, 3, 4>(tmem_base + 128u + 64u * t, mid16 + 128u * t, DA_MID_ROWS, w2, umma_idesc(64, fmt), 0u);
+                    umma_commit(&acc_full[1 + t]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ================= epilogue warps =================
+        const int e = warp - 2;
+        const int lq = warp & 3;   // TMEM lane quarter this warp may read
+        const int cs = e >> 2;     // column slice 0 .. 3
+        const int r = lq * 32 + lane;
+        const int etid = e * 32 + lane;  // 0 .. 511
+        const float *fixw = p.fixw + (long long)g * 2 * 32 * 64;
+        uint16_t *yg = p.y + (long long)g * p.y_gs;
+        int n = 0;
+        for (int b = blockIdx.x; b < n_items; b += gridDim.x, ++n) {
+            const uint32_t par = n & 1;
+            // ---- decoder.convs.1 -> intermediate rows 1 + 2s, 2 + 2s; this warp: channels [16 cs, 16 cs + 16) of both phases
+            mbar_wait(&acc_full[0], par);
+            tc_fence_after();
+            if (lq < 3) {  // rows 96 .. 127 do not exist
+                const uint32_t tacc = tmem_base + ((uint32_t)(lq * 32) << 16);
+                uint32_t r0[16], r1[16];
+                tmem_ld16_nowait(tacc + (uint32_t)(16 * cs), r0);
+                tmem_ld16_nowait(tacc + (uint32_t)(64 + 16 * cs), r1);
+                tmem_ld_wait();
+                if (r < DA_T0) {
+                    float v0[16], v1[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        v0[i] = fmaxf(__uint_as_float(r0[i]) + s_bias[16 * cs + i], 0.f);
+                        v1[i] = fmaxf(__uint_as_float(r1[i]) + s_bias[64 + 16 * cs + i], 0.f);
+                    }
+                    // lanes with bit 2 set store phase 1 first: a quarter warp covers 8 distinct 16-byte bank groups
+                    const int sel = (lane >> 2) & 1;
+                    uint8_t *dA = s_mid + (size_t)(1 + 2 * r + sel) * 16, *dB = s_mid + (size_t)(2 + 2 * r - sel) * 16;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int pl = 2 * cs + h;
+                        uint4 h0, l0, h1, l1;
+                        da_pack8<SPLIT>(&v0[8 * h], h0, l0);
+                        da_pack8<SPLIT>(&v1[8 * h], h1, l1);
+                        *reinterpret_cast<uint4 *>(dA + (size_t)pl * DA_MID_ROWS * 16) = sel ? h1 : h0;
+                        *reinterpret_cast<uint4 *>(dB + (size_t)pl * DA_MID_ROWS * 16) = sel ? h0 : h1;
+                        if (SPLIT == 2) {
+                            *reinterpret_cast<uint4 *>(dA + (size_t)(8 + pl) * DA_MID_ROWS * 16) = sel ? l1 : l0;
+                            *reinterpret_cast<uint4 *>(dB + (size_t)(8 + pl) * DA_MID_ROWS * 16) = sel ? l0 : l1;
+                        }
+                    }
+                }
+            }
+            // ---- crop correction: fix[0][co] = sum_ci w[co][ci][4] x187[ci], fix[1][co] = sum_ci w[co][ci][3] x187[ci]
+            named_bar_sync(1, 32 * DA_EW);  // intermediate row 187 written; previous item's readers of s_fix are done
+            {
+                const int which = etid >> 8, co = (etid >> 3) & 31, sl = etid & 7;
+                const uint4 xh = *reinterpret_cast<const uint4 *>(s_mid + ((size_t)sl * DA_MID_ROWS + DA_T1) * 16);
+                const __half2 *hh = reinterpret_cast<const __half2 *>(&xh);
+                const __nv_bfloat162 *bb = reinterpret_cast<const __nv_bfloat162 *>(&xh);
+                float x8[8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 f = SPLIT == 2 ? __half22float2(hh[i]) : __bfloat1622float2(bb[i]);
+                    x8[2 * i] = f.x;
+                    x8[2 * i + 1] = f.y;
+                }
+                if (SPLIT == 2) {
+                    const uint4 xl = *reinterpret_cast<const uint4 *>(s_mid + ((size_t)(8 + sl) * DA_MID_ROWS + DA_T1) * 16);
+                    const __half2 *ll = reinterpret_cast<const __half2 *>(&xl);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float2 f = __half22float2(ll[i]);
+                        x8[2 * i] += f.x;
+                        x8[2 * i + 1] += f.y;
+                    }
+                }
+                const float4 *wp = reinterpret_cast<const float4 *>(fixw + ((size_t)which * 32 + co) * 64 + sl * 8);
+                const float4 wa = __ldg(wp), wb = __ldg(wp + 1);
+                float acc = wa.x * x8[0];
+                acc = fmaf(wa.y, x8[1], acc), acc = fmaf(wa.z, x8[2], acc), acc = fmaf(wa.w, x8[3], acc);
+                acc = fmaf(wb.x, x8[4], acc), acc = fmaf(wb.y, x8[5], acc), acc = fmaf(wb.z, x8[6], acc), acc = fmaf(wb.w, x8[7], acc);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+                if (sl == 0) s_fix[which][co] = acc;
+            }
+            fence_proxy_async();  // generic-proxy writes of the intermediate -> visible to the tensor-core proxy
+            tc_fence_before();
+            named_bar_sync(1, 32 * DA_EW);  // s_fix complete
+            if (lane == 0) mbar_arrive(&done_bar[0]);
+            // ---- decoder.convs.2 -> global (B, 375, 32) 16-bit; this warp: channels [8 cs, 8 cs + 8) of both phases
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                mbar_wait(&acc_full[1 + t], par);
+                tc_fence_after();
+                const int s = 128 * t + r;
+                if (t == 0 || lq < 2) {  // rows 192 .. 255 do not exist
+                    const uint32_t tacc = tmem_base + 128u + 64u * t + ((uint32_t)(lq * 32) << 16);
+                    uint32_t r0[8], r1[8];
+                    tmem_ld8_nowait(tacc + (uint32_t)(8 * cs), r0);
+                    tmem_ld8_nowait(tacc + (uint32_t)(32 + 8 * cs), r1);
+                    tmem_ld_wait();
+                    if (s < DA_T1) {
+                        float v0[8], v1[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            float a0 = __uint_as_float(r0[i]), a1 = __uint_as_float(r1[i]);
+                            if (s == DA_T1 - 2) a1 -= s_fix[0][8 * cs + i];  // output 373 = row 186, phase 1
+                            if (s == DA_T1 - 1) a0 -= s_fix[1][8 * cs + i];  // output 374 = row 187, phase 0
+                            v0[i] = fmaxf(a0 + s_bias[128 + 8 * cs + i], 0.f);
+                            v1[i] = fmaxf(a1 + s_bias[128 + 32 + 8 * cs + i], 0.f);
+                        }
+                        uint4 h0, l0, h1, l1;
+                        da_pack8<SPLIT>(v0, h0, l0);
+                        da_pack8<SPLIT>(v1, h1, l1);
+                        uint16_t *yb = yg + ((long long)b * DA_T2 + 2 * s) * 32 + 8 * cs;
+                        *reinterpret_cast<uint4 *>(yb) = h0;
+                        if (SPLIT == 2) *reinterpret_cast<uint4 *>(yb + p.y_split) = l0;
+                        if (2 * s + 1 < DA_T2) {
+                            *reinterpret_cast<uint4 *>(yb + 32) = h1;
+                            if (SPLIT == 2) *reinterpret_cast<uint4 *>(yb + 32 + p.y_split) = l1;
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&done_bar[1 + t]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 256);
+}
+
+// ------------------------------------------------------------------------------------------ host
+int deca_build(DecAPlan &plan, const TcLayer &dec1, const TcLayer &dec2p, int split, const float *const *w2 /*3 x (32, 64, 5)*/) {
+    FzDecA &p = plan.p;
+    std::memset(&p, 0, sizeof(p));
+    plan.split = split;
+    plan.ready = false;
+    const int G = 3;
+    VP_REQUIRE(dec1.ph == 2 && dec1.nout == 128 && dec1.sched_taps == 3 && dec1.sched_nq == 4 && dec1.row0 == -1 && dec1.groups == G,
+               VP_ERR_UNSUPPORTED, "deca: decoder.convs.1 is not the compiled (N 128, 3 taps, 4 pairs) polyphase layer");
+    VP_REQUIRE(dec2p.ph == 2 && dec2p.nout == 64 && dec2p.sched_taps == 3 && dec2p.sched_nq == 4 && dec2p.row0 == -1 && dec2p.groups == G,
+               VP_ERR_UNSUPPORTED, "deca: decoder.convs.2 is not the compiled (N 64, 3 taps, 4 pairs) polyphase layer");
+    VP_REQUIRE(!dec1.blocks.empty() && !dec2p.blocks.empty(), VP_ERR_ARG, "deca: host weight blocks are gone");
+    auto up128 = [](size_t v) { return (v + 127) & ~(size_t)127; };
+    const size_t in_bytes = (size_t)split * 8 * DA_IN_ROWS * 16, mid_bytes = (size_t)split * 8 * DA_MID_ROWS * 16;
+    const size_t w1_bytes = up128((size_t)dec1.n_blocks * split * 2 * 128 * 16), w2_bytes = up128((size_t)dec2p.n_blocks * split * 2 * 64 * 16);
+    const size_t bias_bytes = up128((128 + 64) * sizeof(float));
+    p.blob_off = (int)up128(in_bytes + mid_bytes);
+    p.w1_off = p.blob_off;
+    p.w2_off = p.blob_off + (int)w1_bytes;
+    p.bias_off = p.w2_off + (int)w2_bytes;
+    p.blob_bytes = (int)(w1_bytes + w2_bytes + bias_bytes);
+    p.smem_bytes = p.blob_off + p.blob_bytes;
+    VP_REQUIRE(p.smem_bytes <= 226 * 1024, VP_ERR_UNSUPPORTED, "deca: %d bytes of shared memory", p.smem_bytes);
+    plan.blob.assign((size_t)G * p.blob_bytes / 2, 0);
+    plan.fixw.assign((size_t)G * 2 * 32 * 64, 0.f);
+    const size_t e1 = (size_t)dec1.n_blocks * split * 2 * 128 * 8, e2 = (size_t)dec2p.n_blocks * split * 2 * 64 * 8;
+    for (int g = 0; g < G; ++g) {
+        uint16_t *dst = plan.blob.data() + (size_t)g * p.blob_bytes / 2;
+        std::memcpy(dst, dec1.blocks.data() + (size_t)g * e1, e1 * sizeof(uint16_t));
+        std::memcpy(dst + w1_bytes / 2, dec2p.blocks.data() + (size_t)g * e2, e2 * sizeof(uint16_t));
+        float *bd = reinterpret_cast<float *>(dst + (w1_bytes + w2_bytes) / 2);
+        for (int n = 0; n < 128; ++n) bd[n] = dec1.bias[(size_t)g * 128 + n];
+        for (int n = 0; n < 64; ++n) bd[128 + n] = dec2p.bias[(size_t)g * 64 + n];
+        for (int co = 0; co < 32; ++co)
+            for (int ci = 0; ci < 64; ++ci) {
+                plan.fixw[(((size_t)g * 2 + 0) * 32 + co) * 64 + ci] = w2[g][((size_t)co * 64 + ci) * 5 + 4];
+                plan.fixw[(((size_t)g * 2 + 1) * 32 + co) * 64 + ci] = w2[g][((size_t)co * 64 + ci) * 5 + 3];
+            }
+    }
+    return VP_OK;
+}
+
+int deca_upload(DecAPlan &plan) {
+    VP_CUDA_CHECK(cudaMalloc(&plan.d_blob, plan.blob.size() * sizeof(uint16_t)));
+    VP_CUDA_CHECK(cudaMemcpy(plan.d_blob, plan.blob.data(), plan.blob.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    VP_CUDA_CHECK(cudaMalloc(&plan.d_fixw, plan.fixw.size() * sizeof(float)));
+    VP_CUDA_CHECK(cudaMemcpy(plan.d_fixw, plan.fixw.data(), plan.fixw.size() * sizeof(float), cudaMemcpyHostToDevice));
+    plan.blob.clear();
+    plan.blob.shrink_to_fit();
+    plan.ready = true;
+    return VP_OK;
+}
+
+void deca_free(DecAPlan &plan) {
+    if (plan.d_blob) cudaFree(plan.d_blob);
+    if (plan.d_fixw) cudaFree(plan.d_fixw);
+    plan.d_blob = nullptr;
+    plan.d_fixw = nullptr;
+    plan.ready = false;
+}
+
+template <int SPLIT>
+static int deca_launch_t(const FzDecA &p, dim3 grid, cudaStream_t s) {
+    auto kern = deca_kernel<SPLIT>;
+    static int attr = 0;
+    if (p.smem_bytes > attr) {
+        VP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes));
+        attr = p.smem_bytes;
+    }
+    kern<<<grid, DA_THREADS, p.smem_bytes, s>>>(p);
+    VP_LAUNCH_CHECK();
+    return VP_OK;
+}
+
+int deca_launch(const DecAPlan &plan, const uint16_t *x, long long x_split, long long x_gs, int B, uint16_t *y, long long y_split,
+                long long y_gs, cudaStream_t s) {
+    VP_REQUIRE(plan.ready, VP_ERR_UNSUPPORTED, "deca: plan not uploaded");
+    if (B == 0) return VP_OK;
+    FzDecA p = plan.p;
+    p.x = x;
+    p.x_split = x_split;
+    p.x_gs = x_gs;
+    p.y = y;
+    p.y_split = y_split;
+    p.y_gs = y_gs;
+    p.B = B;
+    p.blob = plan.d_blob;
+    p.fixw = plan.d_fixw;
+    dim3 grid((unsigned)std::min(49, B), 3);
+    return plan.split == 2 ? deca_launch_t<2>(p, grid, s) : deca_launch_t<1>(p, grid, s);
+}
+
+}  // namespace vp

@@ -213,6 +213,7 @@ struct vp_model {
         float *d_b = nullptr;
         bool ready = false;
         DecBPlan decb;  // fused decoder tail (fused_dec.cu)
+        DecAPlan deca;  // fused decoder middle, convs.1 + convs.2 (fused_deca.cu)
     } tc[2];
 };
 
@@ -385,6 +386,13 @@ static int build_eqt(vp_model *m, Cursor &cur, Packed &pk) {
         if (const char *e = getenv(split == 2 ? "VP_DECB_M2" : "VP_DECB_M1")) tile_m = atoi(e);  // tuning / debugging aid
         rc = decb_build(ts.decb, ts.dec, split, tile_m, head_w, head_b);
         if (rc != VP_OK) return rc;
+        {   // fused decoder middle: decoder.convs.2 in polyphase form (the crop is corrected inside the kernel)
+            TcLayer dec2p;
+            const float *w2[3] = {dW[0][2], dW[1][2], dW[2][2]}, *b2[3] = {dB[0][2], dB[1][2], dB[2][2]};
+            rc = tc_build_layer(dec2p, TC_POLYPHASE, kDecC[2], kDecC[3], kDecK[2], 0, split, 3, w2, b2);
+            if (rc == VP_OK) rc = deca_build(ts.deca, ts.dec[1], dec2p, split, w2);
+            if (rc != VP_OK) return rc;
+        }
     }
     return VP_OK;
 }
@@ -812,9 +820,18 @@ static int run_eqt(Runner &r, const float *x, float *y, Arena &ar) {
         const uint16_t *cur16 = Q16;
         static const bool fused_off = getenv("VP_FUSED") && atoi(getenv("VP_FUSED")) == 0;
         const bool fused = ts.decb.ready && !fused_off;
+        static const bool deca_off = getenv("VP_FUSED_A") && atoi(getenv("VP_FUSED_A")) == 0;
+        const bool fused_a = fused && ts.deca.ready && !deca_off;
         for (int i = 0; i < 7; ++i) {
             const TcLayer &tl = ts.dec[i];
             uint16_t *dst = pp16[i & 1];
+            if (fused_a && i == 1) {  // decoder.convs.1 + convs.2 in one kernel: (3, B, 94, 64) -> (3, B, 375, 32)
+                if (r.go())
+                    r.rc = deca_launch(ts.deca, cur16, split16, B * (int64_t)64 * dlen[1], (int)B, pp16[1], split16, B * (int64_t)32 * dlen[3], r.s);
+                cur16 = pp16[1];
+                i = 2;  // continue with decoder.convs.3 (the fused tail)
+                continue;
+            }
             if (fused && i == 3) {  // decoder.convs.3-6 + heads in one kernel, activations in shared memory
                 if (r.go())
                     r.rc = decb_launch(ts.decb, cur16, split16, B * (int64_t)tl.cin * dlen[i], (int)B, y, r.keep_lo, r.keep_hi, r.s);
@@ -1066,6 +1083,7 @@ extern "C" int vp_model_create(int kind, const float *weights, int64_t n_floats,
         for (int set = 0; set < 2; ++set) {
             int rc = upload_tc(m->tc[set]);
             if (rc == VP_OK) rc = decb_upload(m->tc[set].decb);
+            if (rc == VP_OK) rc = deca_upload(m->tc[set].deca);
             if (rc != VP_OK) {
                 vp_model_destroy(m);
                 return rc;
@@ -1083,6 +1101,7 @@ extern "C" int vp_model_destroy(vp_model *m) {
         if (m->tc[set].d_w) cudaFree(m->tc[set].d_w);
         if (m->tc[set].d_b) cudaFree(m->tc[set].d_b);
         decb_free(m->tc[set].decb);
+        deca_free(m->tc[set].deca);
     }
     delete m;
     return VP_OK;

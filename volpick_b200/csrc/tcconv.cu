@@ -676,7 +676,7 @@ int tc_launch(const TcLayer &L, const TcIO &io, cudaStream_t s) {
     // epilogue options of this launch; the compile-time epilogue needs the common case: 16-bit output, ReLU (or the
     // res-CNN extras carrying the activation), no padding columns
     const bool extra = io.res || io.y32 || io.post_scale;
-    const bool plain = io.out_fmt == 0 && L.nout == L.ph * L.cout && io.cout_cl == L.cout && !p.dbg &&
+    const bool plain = io.out_fmt == 0 && L.nout == L.ph * L.cout && io.cout_cl == L.cout &&
                        (extra ? (io.act == ACT_RELU || io.act == ACT_NONE) : io.act == ACT_RELU);
     const int flags = plain ? ((io.pool == 2 ? 1 : 0) | (L.ph == 2 ? 2 : 0) | (extra ? 4 : 0)) : -1;
 #define VP_TC_FIXED(N, T, Q, F)                                                                                  \
