@@ -57,6 +57,7 @@ struct FzDecB {
     long long x_split, x_gs;
     int T0, cin0, in_lo0, c0, in_slot_bytes;
     int tiles_per_seq, B;
+    int dbg;             // profiling aid (env VP_DECB_DBG): 1 no MMAs, 2 no layer epilogues, 4 no head, 8 no input loads
     int row_off0;        // 375-level row of tile 0 (> 0 when the leading output samples are blinded and need not be computed)
     int pipe_stride;     // bytes of one pipeline's arena (in[2] | X | Y)
     int blob_off;        // resident weight blob: smem byte offset, bytes per group

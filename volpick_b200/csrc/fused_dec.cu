@@ -24,6 +24,7 @@
 // warps (TMEM -> ReLU -> fp16 hi/lo planes of the next layer's A operand) that also run the head.  The
 // decoder's weights are resident in shared memory and shared by the pipelines.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "fused.cuh"
@@ -123,29 +124,46 @@ __device__ __forceinline__ void fz_epi32(const FzLayer &L, const float *bias, ui
 
 // sigmoid(conv k11, 8 -> 1) on the CUDA cores: thread e = OPT consecutive output samples.
 template <int OPT>
-__device__ __forceinline__ void fz_head(const FzDecB &p, int g, int b, int R0, int e, const uint8_t *arena) {
+__device__ __forceinline__ void fz_head(const FzDecB &p, const float *hw /*shared: [8][12] weights, [96] bias*/, int g, int b, int R0, int e,
+                                        const uint8_t *arena) {
     const int tl0 = OPT * e;
     if (tl0 >= p.W) return;
     const float *d6 = reinterpret_cast<const float *>(arena + p.head_in_off) + tl0;
     const int RP = p.head_rp;
     float acc[OPT];
 #pragma unroll
-    for (int o = 0; o < OPT; ++o) acc[o] = p.head_b[g];
+    for (int o = 0; o < OPT; ++o) acc[o] = hw[96];
+    // the loads of channel c + 1 are issued before the FMAs of channel c (with two warps per scheduler nothing
+    // else hides the shared-memory latency: measured ~45 % of the head's cycles were short-scoreboard stalls)
+    constexpr int NV = (OPT + 12) / 2;
+    float2 cur[NV], nxt[NV];
+#pragma unroll
+    for (int q = 0; q < NV; ++q) cur[q] = *reinterpret_cast<const float2 *>(d6 + 2 * q);
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
+        if (c + 1 < 8) {
+#pragma unroll
+            for (int q = 0; q < NV; ++q) nxt[q] = *reinterpret_cast<const float2 *>(d6 + (size_t)(c + 1) * RP + 2 * q);
+        }
         float xv[OPT + 12];
 #pragma unroll
-        for (int q = 0; q < (OPT + 12) / 2; ++q) {
-            const float2 v2 = *reinterpret_cast<const float2 *>(d6 + (size_t)c * RP + 2 * q);
-            xv[2 * q] = v2.x;
-            xv[2 * q + 1] = v2.y;
+        for (int q = 0; q < NV; ++q) {
+            xv[2 * q] = cur[q].x;
+            xv[2 * q + 1] = cur[q].y;
         }
+        // weights of this channel: three broadcast 16-byte reads (a kernel-parameter array indexed by the run-time
+        // group costs one constant load with a register offset per FMA)
+        const float4 w0 = *reinterpret_cast<const float4 *>(hw + c * 12), w1 = *reinterpret_cast<const float4 *>(hw + c * 12 + 4),
+                     w2 = *reinterpret_cast<const float4 *>(hw + c * 12 + 8);
+        const float wk[12] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w};
 #pragma unroll
         for (int k = 0; k < 11; ++k) {
-            const float w = p.head_w[g][c * 11 + k];
+            const float w = wk[k];
 #pragma unroll
             for (int o = 0; o < OPT; ++o) acc[o] = fmaf(w, xv[o + k + 1], acc[o]);  // buffer row 0 = output - 6
         }
+#pragma unroll
+        for (int q = 0; q < NV; ++q) cur[q] = nxt[q];
     }
     const int t_out = 16 * R0 + tl0;
     float *yb = p.y + ((size_t)b * 3 + g) * p.L_out + t_out;
@@ -191,7 +209,8 @@ __device__ __forceinline__ void fz_issue_layer(const FzDecB &p, int pp, int slot
         const uint32_t a16 = in16 + (uint32_t)t * 128u;
         const uint32_t d_tmem = tmem_base + (pp * FZ_NBUF + buf) * FZ_NCOLS;
         if (elect_one()) {
-            if constexpr (STACK)
+            if (p.dbg & 1) {
+            } else if constexpr (STACK)
                 umma_conv_tile_stacked<NOUT, FZ_DEC_NTAPS[l], FZ_DEC_NQ[l]>(d_tmem, a16, in_rows, w16, umma_idesc(2 * NOUT, 0), idesc, 0u);
             else
                 umma_conv_tile<NOUT, SPLIT, FZ_DEC_NTAPS[l], FZ_DEC_NQ[l]>(d_tmem, a16, in_rows, w16, idesc, 0u);
@@ -253,7 +272,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) decb_kernel(const __grid_consta
             const int b = item / p.tiles_per_seq, j = item - b * p.tiles_per_seq;
             const int row_base = p.c0 * j + p.row_off0 + p.in_lo0;
             const uint32_t dst0 = sbase + pp * p.pipe_stride + p.L[0].in_off + slot * p.in_slot_bytes;
-            for (int idx = lane; idx < per_split; idx += 32) {
+            for (int idx = lane; idx < ((p.dbg & 8) ? 0 : per_split); idx += 32) {
                 const int pl = idx % c8, r = idx / c8;
                 const int gr = row_base + r;
                 const bool ok = (unsigned)gr < (unsigned)p.T0;
@@ -300,7 +319,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) decb_kernel(const __grid_consta
                     // rows of this warp: outputs [2 (s_lo + 128 t + 32 q) - out_lo, + 64); a warp whose rows all fall
                     // outside the output buffer (partially filled last tile of a layer) has nothing to convert
                     const int wrow0 = 2 * (L.s_lo + 128 * t + 32 * q) - L.out_lo;
-                    if (wrow0 < L.out_rows && wrow0 + 64 > 0) {
+                    if (wrow0 < L.out_rows && wrow0 + 64 > 0 && !(p.dbg & 2)) {
                         if (l == 0) fz_epi16<32, SPLIT, ST && FZ_DEC_STACK[0]>(L, bias, tacc, t, r, R0, arena);
                         else if (l == 3) fz_epi32<ST && FZ_DEC_STACK[3]>(L, bias, tacc, t, r, R0, arena);
                         else fz_epi16<16, SPLIT, ST && FZ_DEC_STACK[1]>(L, bias, tacc, t, r, R0, arena);
@@ -312,7 +331,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) decb_kernel(const __grid_consta
                 }
             }
             named_bar_sync(1 + pp, 128);  // the last layer's rows are in shared memory
-            fz_head<OPT>(p, g, b, R0, r, arena);
+            if (!(p.dbg & 4)) fz_head<OPT>(p, reinterpret_cast<const float *>(fz_smem + p.bias_off) + FZ_MAX_LAYERS * FZ_NCOLS, g, b, R0, r, arena);
             named_bar_sync(1 + pp, 128);  // head done reading X before the next item's epilogues overwrite it
         }
     }
@@ -381,8 +400,8 @@ int decb_build(DecBPlan &plan, const TcLayer *dec, int split, int m, const float
         w_rel[l] = blob;
         blob += up128((size_t)TL.n_blocks * split * 2 * TL.nout * 16);
     }
-    const size_t bias_rel = blob;  // fp32 [layer][FZ_NCOLS]
-    blob += up128((size_t)NL * FZ_NCOLS * sizeof(float));
+    const size_t bias_rel = blob;  // fp32 [layer][FZ_NCOLS], then the head: weights [8][12] (11 taps + pad), bias at [96]
+    blob += up128(((size_t)FZ_MAX_LAYERS * FZ_NCOLS + 128) * sizeof(float));
     p.blob_bytes = (int)blob;
     p.bias_off = p.blob_off + (int)bias_rel;
     plan.blob.assign((size_t)G * blob / 2, 0);
@@ -471,6 +490,10 @@ int decb_build(DecBPlan &plan, const TcLayer *dec, int split, int m, const float
     for (int g = 0; g < G; ++g) {
         std::memcpy(p.head_w[g], head_w[g], 88 * sizeof(float));
         p.head_b[g] = head_b[g];
+        float *hd = reinterpret_cast<float *>(plan.blob.data() + (size_t)g * blob / 2 + bias_rel / 2) + (size_t)FZ_MAX_LAYERS * FZ_NCOLS;
+        for (int c = 0; c < 8; ++c)
+            for (int k = 0; k < 11; ++k) hd[c * 12 + k] = head_w[g][c * 11 + k];
+        hd[96] = head_b[g];
     }
     p.smem_bytes = p.blob_off + p.blob_bytes;
     VP_REQUIRE(p.smem_bytes <= 226 * 1024, VP_ERR_UNSUPPORTED, "decb: %d bytes of shared memory", p.smem_bytes);
@@ -522,6 +545,10 @@ int decb_launch(const DecBPlan &plan, const uint16_t *x, long long x_split, long
     p.B = B;
     p.blob = plan.d_blob;
     p.y = y;
+    {
+        const char *e = getenv("VP_DECB_DBG");
+        p.dbg = e ? atoi(e) : 0;
+    }
     const int n_items = B * p.tiles_per_seq;
     if (n_items == 0) return VP_OK;
     dim3 grid((unsigned)std::min(49, (n_items + FZ_NPIPE - 1) / FZ_NPIPE), 3);
