@@ -13,7 +13,8 @@ constexpr int FZ_MAX_LAYERS = 4;
 constexpr int FZ_NPIPE = 2;        // independent work-item pipelines per CTA (each: loader, issuer, 4 epilogue warps)
 constexpr int FZ_NBUF = 4;         // TMEM accumulator buffers per pipeline
 constexpr int FZ_NCOLS = 64;       // TMEM columns per accumulator (max MMA N of the chain)
-constexpr int FZ_THREADS = 32 * (2 * FZ_NPIPE + 4 * FZ_NPIPE);
+// warps: NPIPE loaders, NPIPE issuers, 4 NPIPE layer-epilogue warps, 4 NPIPE head warps
+constexpr int FZ_THREADS = 32 * (2 * FZ_NPIPE + 4 * FZ_NPIPE + 4 * FZ_NPIPE);
 
 // One x2-up-sampling conv layer (polyphase form, see tcconv.cu) inside a fused chain.  All row indices are
 // relative to the work item: global row at level k = c_k * tile_index + relative row.

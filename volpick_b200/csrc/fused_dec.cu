@@ -43,25 +43,27 @@ __device__ __forceinline__ void fz_pack8(const float *v, bool valid, uint4 &hi, 
     }
 }
 
-// Accumulator columns [phase][channel] of this thread's row -> v[2 * COUTP] = relu(acc (+ stacked half) + bias).
-template <int COUTP, bool STACK>
-__device__ __forceinline__ void fz_load_row(const float *bias /*shared memory, [2 * COUTP]*/, uint32_t tacc, float (&v)[2 * COUTP]) {
-    constexpr int N = 2 * COUTP;
-    uint32_t r[STACK ? 2 * N : N];
-#pragma unroll
-    for (int c0 = 0; c0 < (STACK ? 2 * N : N); c0 += 16) {
-        uint32_t(&r16)[16] = *reinterpret_cast<uint32_t(*)[16]>(&r[c0]);
-        tmem_ld16_nowait(tacc + (uint32_t)c0, r16);
+// CH accumulator columns starting at col0 (+ the stacked half at col0 + NST when NST > 0) -> relu(acc + bias).
+template <int CH, int NST>
+__device__ __forceinline__ void fz_load_cols(const float *bias /*shared memory, column col0*/, uint32_t tacc, int col0, float (&v)[CH]) {
+    uint32_t r[CH], r2[NST > 0 ? CH : 1];
+    if constexpr (CH == 16) {
+        tmem_ld16_nowait(tacc + (uint32_t)col0, r);
+        if constexpr (NST > 0) tmem_ld16_nowait(tacc + (uint32_t)(col0 + NST), r2);
+    } else {
+        static_assert(CH == 8, "column slice");
+        tmem_ld8_nowait(tacc + (uint32_t)col0, r);
+        if constexpr (NST > 0) tmem_ld8_nowait(tacc + (uint32_t)(col0 + NST), r2);
     }
     tmem_ld_wait();
 #pragma unroll
-    for (int n = 0; n < N; n += 4) {
+    for (int n = 0; n < CH; n += 4) {
         const float4 b4 = *reinterpret_cast<const float4 *>(bias + n);
         const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             float a = __uint_as_float(r[n + e]);
-            if (STACK) a += __uint_as_float(r[N + n + e]);
+            if constexpr (NST > 0) a += __uint_as_float(r2[n + e]);
             v[n + e] = fmaxf(a + bb[e], 0.f);
         }
     }
@@ -70,33 +72,39 @@ __device__ __forceinline__ void fz_load_row(const float *bias /*shared memory, [
 // Polyphase layer -> 16-bit planes of the next layer.  Thread = one input row s; it owns output rows 2s, 2s+1.
 // The two rows are 32 bytes apart: a plain "phase 0, then phase 1" store has consecutive lanes 32 bytes apart
 // (2-way bank conflict).  Instead lanes with bit 2 set store phase 1 first: every quarter warp then covers eight
-// distinct 16-byte bank groups.
+// distinct 16-byte bank groups.  16 channels (two planes) of both phases are in registers at a time.
 template <int COUTP, int SPLIT, bool STACK>
 __device__ __forceinline__ void fz_epi16(const FzLayer &L, const float *bias, uint32_t tacc, int t, int r, int R0, uint8_t *arena) {
     constexpr int P = COUTP / 8;
+    constexpr int NST = STACK ? 2 * COUTP : 0;
     const int s_rel = L.s_lo + 128 * t + r;
     const int lrow0 = 2 * s_rel - L.out_lo;
     const int grow0 = 2 * ((R0 << L.lvl) + s_rel);  // R0: 375-level row of the work item's origin
     const uint32_t plane = (uint32_t)L.out_rows * 16u;
-    float v[2 * COUTP];
-    fz_load_row<COUTP, STACK>(bias, tacc, v);
     const int sel = (r >> 2) & 1;  // phase stored first by this lane
     const int rowA = lrow0 + sel, rowB = lrow0 + 1 - sel;
     const bool inA = (unsigned)rowA < (unsigned)L.out_rows, inB = (unsigned)rowB < (unsigned)L.out_rows;
     const bool valid0 = (unsigned)grow0 < (unsigned)L.T_out, valid1 = (unsigned)(grow0 + 1) < (unsigned)L.T_out;
     uint8_t *dstA = arena + L.out_off + (size_t)rowA * 16, *dstB = arena + L.out_off + (size_t)rowB * 16;
 #pragma unroll
-    for (int pl = 0; pl < P; ++pl) {
-        uint4 h0, l0, h1, l1;
-        fz_pack8<SPLIT>(&v[pl * 8], valid0, h0, l0);
-        fz_pack8<SPLIT>(&v[COUTP + pl * 8], valid1, h1, l1);
-        const uint4 hA = sel ? h1 : h0, hB = sel ? h0 : h1;
-        if (inA) *reinterpret_cast<uint4 *>(dstA + pl * plane) = hA;
-        if (inB) *reinterpret_cast<uint4 *>(dstB + pl * plane) = hB;
-        if (SPLIT == 2) {
-            const uint4 lA = sel ? l1 : l0, lB = sel ? l0 : l1;
-            if (inA) *reinterpret_cast<uint4 *>(dstA + (P + pl) * plane) = lA;
-            if (inB) *reinterpret_cast<uint4 *>(dstB + (P + pl) * plane) = lB;
+    for (int c0 = 0; c0 < COUTP; c0 += 16) {
+        float v0[16], v1[16];
+        fz_load_cols<16, NST>(bias + c0, tacc, c0, v0);
+        fz_load_cols<16, NST>(bias + COUTP + c0, tacc, COUTP + c0, v1);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int pl = c0 / 8 + k;
+            uint4 h0, l0, h1, l1;
+            fz_pack8<SPLIT>(&v0[k * 8], valid0, h0, l0);
+            fz_pack8<SPLIT>(&v1[k * 8], valid1, h1, l1);
+            const uint4 hA = sel ? h1 : h0, hB = sel ? h0 : h1;
+            if (inA) *reinterpret_cast<uint4 *>(dstA + pl * plane) = hA;
+            if (inB) *reinterpret_cast<uint4 *>(dstB + pl * plane) = hB;
+            if (SPLIT == 2) {
+                const uint4 lA = sel ? l1 : l0, lB = sel ? l0 : l1;
+                if (inA) *reinterpret_cast<uint4 *>(dstA + (P + pl) * plane) = lA;
+                if (inB) *reinterpret_cast<uint4 *>(dstB + (P + pl) * plane) = lB;
+            }
         }
     }
 }
@@ -108,7 +116,7 @@ __device__ __forceinline__ void fz_epi32(const FzLayer &L, const float *bias, ui
     const int lrow0 = 2 * s_rel - L.out_lo;  // even
     const int grow0 = 2 * ((R0 << L.lvl) + s_rel);
     float v[16];
-    fz_load_row<8, STACK>(bias, tacc, v);
+    fz_load_cols<16, STACK ? 16 : 0>(bias, tacc, 0, v);
     if ((unsigned)lrow0 < (unsigned)L.out_rows) {  // out_rows is even: both phases are in range together
         const bool valid = (unsigned)grow0 < (unsigned)L.T_out;  // T_out even: both phases valid together
         float *d = reinterpret_cast<float *>(arena + L.out_off) + lrow0;
@@ -226,7 +234,7 @@ template <int SPLIT, int OPT>
 __global__ void __launch_bounds__(FZ_THREADS, 1) decb_kernel(const __grid_constant__ FzDecB p) {
     extern __shared__ __align__(128) uint8_t fz_smem[];
     __shared__ __align__(8) uint64_t in_full[FZ_NPIPE][2], in_empty[FZ_NPIPE][2], acc_full[FZ_NPIPE][FZ_NBUF],
-        done_bar[FZ_NPIPE][FZ_NBUF];
+        done_bar[FZ_NPIPE][FZ_NBUF], head_go[FZ_NPIPE], head_done[FZ_NPIPE];
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -244,6 +252,8 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) decb_kernel(const __grid_consta
                 mbar_init(&acc_full[pp][i], 1);
                 mbar_init(&done_bar[pp][i], 4);
             }
+            mbar_init(&head_go[pp], 4);
+            mbar_init(&head_done[pp], 4);
         }
         fence_barrier_init();
     }
@@ -298,17 +308,21 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) decb_kernel(const __grid_consta
             fz_issue_layer<2, SPLIT>(p, pp, slot, n, i, tmem_base, arena16, sB16, in_full, in_empty, acc_full, done_bar);
             fz_issue_layer<3, SPLIT>(p, pp, slot, n, i, tmem_base, arena16, sB16, in_full, in_empty, acc_full, done_bar);
         }
-    } else {
-        // ================= epilogue warps + head =================
+    } else if (warp < 6 * FZ_NPIPE) {
+        // ================= layer epilogue warps =================
         const int pp = (warp - 2 * FZ_NPIPE) >> 2, q = warp & 3;
         const int r = q * 32 + lane;
         uint8_t *arena = fz_smem + pp * p.pipe_stride;
         uint32_t i = 0;
-        for (int item = blockIdx.x + pp * gridDim.x; item < n_items; item += FZ_NPIPE * gridDim.x) {
+        int n = 0;
+        for (int item = blockIdx.x + pp * gridDim.x; item < n_items; item += FZ_NPIPE * gridDim.x, ++n) {
             const int b = item / p.tiles_per_seq, j = item - b * p.tiles_per_seq;
             const int R0 = p.c0 * j + p.row_off0;
+            (void)b;
             for (int l = 0; l < p.n_layers; ++l) {
                 const FzLayer &L = p.L[l];
+                // layer 1 is the first writer of buffer X, which the head warps may still be reading (previous item)
+                if (l == 1 && n > 0) mbar_wait(&head_done[pp], (n - 1) & 1);
                 for (int t = 0; t < L.n_tiles; ++t, ++i) {
                     const uint32_t buf = i & (FZ_NBUF - 1);
                     mbar_wait(&acc_full[pp][buf], (i / FZ_NBUF) & 1);
@@ -330,9 +344,22 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) decb_kernel(const __grid_consta
                     if (lane == 0) mbar_arrive(&done_bar[pp][buf]);
                 }
             }
-            named_bar_sync(1 + pp, 128);  // the last layer's rows are in shared memory
-            if (!(p.dbg & 4)) fz_head<OPT>(p, reinterpret_cast<const float *>(fz_smem + p.bias_off) + FZ_MAX_LAYERS * FZ_NCOLS, g, b, R0, r, arena);
-            named_bar_sync(1 + pp, 128);  // head done reading X before the next item's epilogues overwrite it
+            if (lane == 0) mbar_arrive(&head_go[pp]);  // the last layer's rows of this warp are in shared memory
+        }
+    } else {
+        // ================= head warps: sigmoid(conv k11) of the previous item while the pipeline runs the next one
+        const int pp = (warp - 6 * FZ_NPIPE) >> 2;
+        const int e = ((warp - 6 * FZ_NPIPE) & 3) * 32 + lane;
+        const uint8_t *arena = fz_smem + pp * p.pipe_stride;
+        const float *hw = reinterpret_cast<const float *>(fz_smem + p.bias_off) + FZ_MAX_LAYERS * FZ_NCOLS;
+        int n = 0;
+        for (int item = blockIdx.x + pp * gridDim.x; item < n_items; item += FZ_NPIPE * gridDim.x, ++n) {
+            const int b = item / p.tiles_per_seq, j = item - b * p.tiles_per_seq;
+            const int R0 = p.c0 * j + p.row_off0;
+            mbar_wait(&head_go[pp], n & 1);
+            if (!(p.dbg & 4)) fz_head<OPT>(p, hw, g, b, R0, e, arena);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&head_done[pp]);
         }
     }
     tc_fence_before();
