@@ -31,6 +31,18 @@ sys.path.insert(0, ROOT)
 N_DAY = 8_640_000
 N_HOUR = 360_000
 FLOP_PER_WINDOW = {"eqtransformer": 257.04e6, "phasenet": 38.92e6}
+# Algorithmic FLOPs per window of the kernel classes that can dominate a step (2 x the reference's conv MACs on the
+# up-sampled / full-length input; blinded margins and polyphase savings are NOT subtracted):
+#   decb = decoder.convs.3-6 + head of the three EQTransformer decoders:
+#          3 x (32*32*7*750 + 16*32*7*1500 + 16*16*9*3000 + 8*16*11*6000 + 1*8*11*6000) MAC = 79.92 MMAC
+#   conv1d_f32 (PhaseNet fp32 path) = all Conv1d layers = 19.46 - 2.71 (ConvTranspose1d) MMAC
+KCLASS_FLOP_PER_WINDOW = {
+    ("eqtransformer", "decb"): 2 * 3 * (32 * 32 * 7 * 750 + 16 * 32 * 7 * 1500 + 16 * 16 * 9 * 3000 + 8 * 16 * 11 * 6000 + 8 * 11 * 6000),
+    ("phasenet", "conv1d_f32"): 2 * (19.46e6 - (128 * 64 * 12 + 64 * 32 * 47 + 32 * 16 * 188 + 16 * 8 * 751) * 7),
+}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture (profiles/):
+KCLASS_NCU_TRAFFIC = {("eqtransformer", "decb", "f16x3"): {"bytes_per_launch": 535.19e6 + 231.43e6, "windows_per_launch": 4096,
+                                                            "source": "profiles/r01b_f16x3_top_kernels_ncu_full.md"}}
 CONFIGS = {
     "eqtransformer": dict(overlap=5500, blinding=(500, 500), stacking="avg", P_threshold=0.2, S_threshold=0.2),
     "phasenet": dict(overlap=1500, blinding=(0, 0), stacking="avg", P_threshold=0.2, S_threshold=0.2),
@@ -252,6 +264,27 @@ def run_ours(args):
 
     ms, launches, clocks, last = timed(step_device, args.steps, args.warmup, sample_clocks=True)
     ms_e2e, _, _, last_e2e = timed(step_host, args.steps, max(1, args.warmup // 2))
+
+    # ---- per-kernel-class CUDA-event timing over K more device-resident steps (events bracket every launch on the
+    # launching stream inside the library; a separate pass so that the headline numbers above carry no event overhead)
+    kernels = {}
+    if rank == 0:
+        lib.vp_kernel_timing(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(args.steps):
+            step_device(i)
+        e1.record()
+        torch.cuda.synchronize()
+        for k, name in enumerate(lib.vp_kernel_class_names().decode().split(",")):
+            tot, cnt = C.c_double(0.0), C.c_int64(0)
+            _lib.check(lib.vp_kernel_timing_read(k, C.byref(tot), C.byref(cnt)))
+            if cnt.value:
+                kernels[name] = {"ms_per_step": tot.value / args.steps, "launches_per_step": cnt.value / args.steps,
+                                 "ms_per_launch": tot.value / cnt.value}
+        lib.vp_kernel_timing(0)
+        kernels_step_ms = e0.elapsed_time(e1) / args.steps
     n_trig = len(last[1])
     nwin = int(lib.vp_window_count(n, model.in_samples, argdict["overlap"]))
     days = n / N_DAY
@@ -273,12 +306,30 @@ def run_ours(args):
     if rank == 0:
         fwd_ms = stages.get("forward_ms")
         flops = FLOP_PER_WINDOW[kind] * nwin
-        achieved = flops / (fwd_ms / 1e3) / 1e12 if fwd_ms else None
-        roofline = {"kernel": "forward (conv1d/convT/LSTM/attention kernels of vp_forward)", "bound": "tensor",
-                    "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                    "frac": (achieved / peaks["tf_sustained"]) if achieved else None, "traffic": None,
-                    "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['src']})",
-                    "note": "fp32 exact mode runs on the CUDA cores (FFMA); fraction is against the bf16 tensor peak"}
+        fwd_tf = flops / (fwd_ms / 1e3) / 1e12 if fwd_ms else None
+        dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"]) if kernels else None
+        share = {k: v["ms_per_step"] / sum(x["ms_per_step"] for x in kernels.values()) for k, v in kernels.items()}
+        if dom and (kind, dom) in KCLASS_FLOP_PER_WINDOW:
+            kf = KCLASS_FLOP_PER_WINDOW[(kind, dom)] * nwin  # per step
+            achieved = kf / (kernels[dom]["ms_per_step"] / 1e3) / 1e12
+            tr = KCLASS_NCU_TRAFFIC.get((kind, dom, args.precision))
+            roofline = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                        "frac": achieved / peaks["tf_sustained"],
+                        "traffic": (tr["bytes_per_launch"] if tr else None),
+                        "traffic_note": (f"ncu dram bytes of one {tr['windows_per_launch']}-window launch, {tr['source']}" if tr else None),
+                        "ms_per_launch": kernels[dom]["ms_per_launch"], "launches_per_step": kernels[dom]["launches_per_step"],
+                        "share_of_kernel_time": share[dom],
+                        "algorithmic_flop_per_window": KCLASS_FLOP_PER_WINDOW[(kind, dom)],
+                        "peak_source": f"bf16_tflops_sustained ({peaks['src']}); kernel timed inside a long step",
+                        "note": ("f16x3 issues 3 fp16 MMAs per algorithmic product (hi*hi + hi*lo + lo*hi) for fp32-grade results; "
+                                 "the fraction is algorithmic FLOP/s against the single-pass bf16 peak") if args.precision == "f16x3" else
+                                ("fp32 mode runs on the CUDA cores (FFMA); fraction is against the bf16 tensor peak" if args.precision == "fp32" else "")}
+        else:
+            roofline = {"kernel": "forward (all network kernels of vp_forward)", "bound": "tensor", "achieved": fwd_tf,
+                        "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": (fwd_tf / peaks["tf_sustained"]) if fwd_tf else None,
+                        "traffic": None, "peak_source": f"bf16_tflops_sustained ({peaks['src']})"}
+        roofline["forward_tflops"] = fwd_tf  # whole network: 2 x MACs of SURVEY 8(d) / CUDA-event time of the forward stage
+        roofline["forward_frac"] = (fwd_tf / peaks["tf_sustained"]) if fwd_tf else None
         line = {
             "metric": "station_days_per_s", "value": value, "unit": "station-days/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -288,6 +339,8 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "station-days/s", "h2d_bytes_per_step": 3 * n * 4,
                     "d2h_bytes_per_step": int(len(last_e2e[1]) * 32 + 56), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "stages": stages,
+            "kernels": {"per_class": kernels, "ms_per_step_with_events": kernels_step_ms,
+                        "note": "CUDA events around every launch of the class on the launching stream, K extra steps"},
             "picks_per_record": n_trig, "gather_ms": gather_ms,
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -323,8 +376,9 @@ def stage_timings(model, lib, rec_dev, argdict, thresholds, kind, reps: int = 3,
     d_ann = torch.empty((3, n), dtype=torch.float32, device="cuda")
     ws_bytes = int(lib.vp_forward_workspace_bytes(model._handle, chunk, precision))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
-    sb = int(lib.vp_pick_scratch_bytes(n))
-    scratch = torch.empty(sb, dtype=torch.uint8, device="cuda")
+    thr_on = np.array([max(float(v), 0.0) for v in thresholds], dtype=np.float32)
+    thr_off = thr_on / np.float32(2)
+    bounds = torch.empty(6, dtype=torch.int64, device="cuda")
     picks = torch.empty(65536 * 32, dtype=torch.uint8, device="cuda")
     count = torch.zeros(1, dtype=torch.int64, device="cuda")
     stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -362,10 +416,8 @@ def stage_timings(model, lib, rec_dev, argdict, thresholds, kind, reps: int = 3,
                                 _lib.STACK[argdict["stacking"]], d_ann.data_ptr(), n, stream))
         b.record()
         count.zero_()
-        for li in range(3):
-            if thresholds[li] > 0:
-                _lib.check(lib.vp_pick(d_ann.data_ptr() + 4 * n * li, n, thresholds[li], thresholds[li] / 2, li, picks.data_ptr(), 65536,
-                                       count.data_ptr(), scratch.data_ptr(), sb, stream))
+        _lib.check(lib.vp_pick_labels(d_ann.data_ptr(), 3, n, thr_on.ctypes.data, thr_off.ctypes.data, picks.data_ptr(), 65536,
+                                      count.data_ptr(), bounds.data_ptr(), stream))
         c.record()
         torch.cuda.synchronize()
         for (x0, x1, x2) in evs:
@@ -376,10 +428,9 @@ def stage_timings(model, lib, rec_dev, argdict, thresholds, kind, reps: int = 3,
         if rep > 0:
             for k in acc:
                 acc[k] += t[k] / reps
-    n_labels_picked = sum(1 for v in thresholds if v > 0)
     bytes_slice = 3 * n * 4 + nwin * 3 * L * 4
     bytes_stack = nwin * 3 * L * 4 + 3 * n * 4
-    bytes_pick = n_labels_picked * n * 4
+    bytes_pick = 3 * n * 4  # one pass over all three labels: picks of the thresholded ones + the _trim_nan bounds of each
     out = {f"{k}_ms": v for k, v in acc.items()}
     out["forward_includes_slicing"] = bool(fused)  # True: K1 runs inside the first encoder kernel; slice_ms is the stand-alone K1
     for k, by in (("slice", bytes_slice), ("stack", bytes_stack), ("pick", bytes_pick)):

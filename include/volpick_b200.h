@@ -78,6 +78,13 @@ VP_API int vp_version(void);
 VP_API const char *vp_last_error(void);
 /* Number of kernel launches issued by this library on the calling thread since the last reset. */
 VP_API int64_t vp_launch_count(int reset);
+/* Per-kernel-class timing with CUDA events on the launching stream (calling thread; measurement aid of bench.py).
+ * vp_kernel_timing(1) clears the record and starts bracketing every launch; vp_kernel_timing(0) stops and clears.
+ * vp_kernel_timing_read synchronises on the recorded events and returns the summed duration (ms) and the
+ * number of launches of class `kclass` (index into the comma-separated vp_kernel_class_names()). */
+VP_API int vp_kernel_timing(int enable);
+VP_API const char *vp_kernel_class_names(void);
+VP_API int vp_kernel_timing_read(int kclass, double *total_ms, int64_t *launches);
 
 /* ---- model handle: SeisBenchModel.from_pretrained -> load_state_dict ------------------- */
 /* weights: every float tensor of the SeisBench state dict, concatenated in state-dict order
@@ -149,10 +156,18 @@ VP_API int vp_nan_bounds(const float *annotation, int n_labels, int64_t pred_len
 /* picks_from_annotations / detections_from_annotations (trigger_onset + first argmax;
  * /root/reference/volpick/model/eval_taks0.py:46-56).  Appends to picks[*count...] (device),
  * unordered; *count (device int64) may exceed capacity -> caller must treat as overflow.
- * scratch: device buffer of vp_pick_scratch_bytes(n) bytes. */
+ * One pass over the trace (tiles staged in shared memory); scratch is unused and kept for ABI
+ * stability (vp_pick_scratch_bytes returns a token size, NULL is accepted). */
 VP_API int64_t vp_pick_scratch_bytes(int64_t n_samples);
 VP_API int vp_pick(const float *trace, int64_t n_samples, float thr_on, float thr_off, int label, vp_trigger *picks,
             int64_t capacity, int64_t *count, void *scratch, int64_t scratch_bytes, void *stream);
+
+/* classify_aggregate for a whole (n_labels, pred_len) annotation in ONE launch: _trim_nan bounds
+ * (as vp_nan_bounds; bounds may be NULL) and the picks of every label whose thr_on[c] > 0
+ * (thr_on / thr_off: HOST arrays of n_labels floats; n_labels <= 4).  Appends like vp_pick. */
+VP_API int vp_pick_labels(const float *annotation, int n_labels, int64_t pred_len, const float *thr_on,
+                   const float *thr_off, vp_trigger *picks, int64_t capacity, int64_t *count, int64_t *bounds,
+                   void *stream);
 
 /* ---- the whole path for one gap-free record: WaveformModel.annotate + classify_aggregate -- */
 VP_API int64_t vp_annotate_workspace_bytes(const vp_model *m, int64_t n_samples, const vp_annotate_params *p,

@@ -320,6 +320,81 @@ def test_picks_long_runs_and_edges(lib):
     assert k == 50 and len(got) == 8
 
 
+def test_pick_labels_tiles_alignment_and_trim(lib):
+    """vp_pick_labels: all labels + _trim_nan bounds in one launch; runs crossing the 4096-sample tiles, label rows at
+    every 16-byte misalignment (pred_len % 4 != 0), a label without picks (threshold 0)."""
+    rng = np.random.default_rng(11)
+    dt = np.dtype([("s0", "<i8"), ("s1", "<i8"), ("s_peak", "<i8"), ("value", "<f4"), ("label", "<i4")])
+    for n in (4093, 4096, 12_289, 30_001, 70_002, 3):
+        ann = np.empty((3, n), np.float32)
+        for c in range(3):
+            w = np.abs(np.cumsum(rng.standard_normal(n))).astype(np.float32)
+            w /= max(float(w.max()), 1e-6)
+            if c == 1:
+                w = np.round(w, 1)  # plateaus and long runs
+            w[rng.random(n) < 0.002] = np.nan
+            lead, trail = int(rng.integers(0, min(n, 600))), int(rng.integers(0, min(n, 600)))
+            w[:lead] = np.nan
+            w[n - trail:] = np.nan
+            ann[c] = w
+        thr = np.array([0.3, 0.45, 0.0], np.float32)
+        thr_off = thr / np.float32(2)
+        d_a = torch.from_numpy(ann).cuda()
+        cap = n
+        picks = torch.zeros(cap * 32, dtype=torch.uint8, device="cuda")
+        count = torch.zeros(1, dtype=torch.int64, device="cuda")
+        bounds = torch.empty(6, dtype=torch.int64, device="cuda")
+        _lib.check(lib.vp_pick_labels(d_a.data_ptr(), 3, n, thr.ctypes.data, thr_off.ctypes.data, picks.data_ptr(), cap,
+                                      count.data_ptr(), bounds.data_ptr(), _stream()))
+        k = int(count.item())
+        arr = np.sort(np.frombuffer(picks.cpu().numpy().tobytes(), dtype=dt, count=k), order=["label", "s0"])
+        b = bounds.cpu().numpy().reshape(3, 2)
+        ref_all = []
+        for c in range(3):
+            _, f, back = pipeline.trim_nan(ann[c])
+            if np.isnan(ann[c]).all():
+                assert (b[c, 0], b[c, 1]) == (n, -1)
+            else:
+                assert (b[c, 0], b[c, 1]) == (f, n - 1 - back), (n, c)
+            if thr[c] > 0:
+                ref_all += [(c,) + tuple(r) for r in pipeline.picks_from_trace(ann[c], thr[c])]
+        assert k == len(ref_all), (n, k, len(ref_all))
+        for g, r in zip(arr, ref_all):
+            assert (g["label"], g["s0"], g["s1"], g["s_peak"]) == r[:4] and g["value"] == np.float32(r[4]), (n, g, r)
+        # bounds are optional
+        count.zero_()
+        _lib.check(lib.vp_pick_labels(d_a.data_ptr(), 3, n, thr.ctypes.data, thr_off.ctypes.data, picks.data_ptr(), cap,
+                                      count.data_ptr(), None, _stream()))
+        assert int(count.item()) == k
+
+
+def test_picks_full_size_properties(lib):
+    """Station-day size: one launch, picks sorted/disjoint, every pick satisfies the trigger rule (size-independent)."""
+    n = 8_640_000
+    rng = np.random.default_rng(5)
+    x = np.abs(np.cumsum(rng.standard_normal(n))).astype(np.float32)
+    x = (x % 97.0) / 97.0
+    thr = np.float32(0.6)
+    k, got = _gpu_picks(lib, x, float(thr))
+    assert k == len(got) and k > 0
+    above = x > thr / np.float32(2)
+    n_runs_on = 0
+    edges = np.flatnonzero(np.diff(np.concatenate(([0], above.view(np.int8), [0]))))
+    for a, b in zip(edges[::2], edges[1::2]):
+        if (x[a:b] > thr).any():
+            n_runs_on += 1
+    assert k == n_runs_on
+    assert np.all(got["s0"][1:] > got["s1"][:-1])
+    for g in got[:: max(1, k // 500)]:
+        s0, s1, sp = int(g["s0"]), int(g["s1"]), int(g["s_peak"])
+        a = s0
+        while a > 0 and above[a - 1]:
+            a -= 1
+        assert x[s0] > thr and not (x[a:s0] > thr).any()
+        assert above[s0:s1 + 1].all() and (s1 + 1 == n or not above[s1 + 1])
+        assert sp == s0 + int(np.argmax(x[s0:s1 + 1])) and g["value"] == x[sp]
+
+
 # ------------------------------------------------------------------------------------------ whole path
 def _oracle_triggers(kind, sd, x, overlap, blinding, stacking, thr):
     ann = pipeline.annotate_array(kind, sd, x, overlap, blinding, stacking)

@@ -48,6 +48,9 @@ SIGNATURES = {
     "vp_version": (_i32, []),
     "vp_last_error": (C.c_char_p, []),
     "vp_launch_count": (_i64, [_i32]),
+    "vp_kernel_timing": (_i32, [_i32]),
+    "vp_kernel_class_names": (C.c_char_p, []),
+    "vp_kernel_timing_read": (_i32, [_i32, C.POINTER(C.c_double), C.POINTER(_i64)]),
     "vp_model_create": (_i32, [_i32, _vp, _i64, _i32, C.POINTER(_vp)]),
     "vp_model_destroy": (_i32, [_vp]),
     "vp_model_kind": (_i32, [_vp]),
@@ -69,6 +72,7 @@ SIGNATURES = {
     "vp_nan_bounds": (_i32, [_vp, _i32, _i64, _vp, _vp]),
     "vp_pick_scratch_bytes": (_i64, [_i64]),
     "vp_pick": (_i32, [_vp, _i64, _f32, _f32, _i32, _vp, _i64, _vp, _vp, _i64, _vp]),
+    "vp_pick_labels": (_i32, [_vp, _i32, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "vp_annotate_workspace_bytes": (_i64, [_vp, _i64, C.POINTER(AnnotateParams), _i32, _i64]),
     "vp_annotate": (_i32, [_vp, _vp, _i32, _i32, _i64, _i64, C.POINTER(AnnotateParams), _vp, _i32, _vp, _i64,
                            C.POINTER(_i64), _vp, _vp, _i64, _vp]),

@@ -200,17 +200,18 @@ extern "C" int vp_annotate(vp_model *m, const void *trace, int trace_on_host, in
     rc = vp_stack(d_y, d_starts, lo.nwin, L, 3, p->overlap, p->blinding[0], p->blinding[1], p->stacking, d_annot,
                   lo.pred_len, s);
     if (rc != VP_OK) return rc;
+    // _trim_nan bounds + trigger_onset / first-argmax picks of all labels: one pass over the annotation
     int64_t *d_bounds = (int64_t *)(ws + lo.off_bounds);
-    rc = vp_nan_bounds(d_annot, 3, lo.pred_len, d_bounds, s);
-    if (rc != VP_OK) return rc;
     int64_t *d_count = (int64_t *)(ws + lo.off_count);
     vp_trigger *d_picks = (vp_trigger *)(ws + lo.off_picks);
     VP_CUDA_CHECK(cudaMemsetAsync(d_count, 0, 8, s));
-    for (int c = 0; c < 3; ++c) {
-        const float thr = p->threshold[c];
-        if (!(thr > 0.f) || pick_capacity == 0) continue;
-        rc = vp_pick(d_annot + (int64_t)c * lo.pred_len, lo.pred_len, thr, thr / 2, c, d_picks, pick_capacity, d_count,
-                     ws + lo.off_scratch, vp_pick_scratch_bytes(lo.pred_len), s);
+    {
+        float thr_on[3], thr_off[3];
+        for (int c = 0; c < 3; ++c) {
+            thr_on[c] = p->threshold[c];
+            thr_off[c] = p->threshold[c] / 2;
+        }
+        rc = vp_pick_labels(d_annot, 3, lo.pred_len, thr_on, thr_off, d_picks, pick_capacity, d_count, d_bounds, s);
         if (rc != VP_OK) return rc;
     }
     int64_t h_count = 0;

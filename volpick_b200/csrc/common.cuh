@@ -15,6 +15,24 @@ namespace vp {
 void set_error(const char *fmt, ...);
 void count_launch(int n = 1);
 
+// Per-kernel-class CUDA-event timing (vp_kernel_timing): off by default, one branch per launch when off.
+enum KClass {
+    KC_SLICE = 0, KC_SLICE_ENC0, KC_TCCONV, KC_DECA, KC_DECB, KC_CONV_F32, KC_CONVT_F32, KC_LSTM, KC_ATTN, KC_PACK,
+    KC_STACK, KC_TRIM, KC_PICK, KC_COUNT
+};
+extern thread_local bool g_ktimer_on;
+void ktimer_mark(int cls, cudaStream_t s, bool end);
+struct KTimer {  // scoped: events on the launching stream around everything launched while it lives
+    int cls;
+    cudaStream_t s;
+    KTimer(int c, cudaStream_t st) : cls(c), s(st) {
+        if (g_ktimer_on) ktimer_mark(cls, s, false);
+    }
+    ~KTimer() {
+        if (g_ktimer_on) ktimer_mark(cls, s, true);
+    }
+};
+
 #define VP_CUDA_CHECK(expr)                                                                     \
     do {                                                                                        \
         cudaError_t _e = (expr);                                                                \

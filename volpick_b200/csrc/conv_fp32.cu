@@ -154,6 +154,7 @@ static int launch_conv(const ConvP &p, int B, int G, cudaStream_t s) {
         }
     }
     dim3 grid((p.Lconv + TILE - 1) / TILE, B, G);
+    KTimer kt(KC_CONV_F32, s);
     kern<<<grid, 32 * NW, SMEM, s>>>(p);
     VP_LAUNCH_CHECK();
     return VP_OK;
@@ -276,6 +277,7 @@ __global__ void __launch_bounds__(128) convt_k7s4_kernel(const ConvTP p) {
 template <int CIN, int COUT, int CCH>
 static int launch_convt(const ConvTP &p, int B, cudaStream_t s) {
     dim3 grid((p.Lout + 127) / 128, B);
+    KTimer kt(KC_CONVT_F32, s);
     convt_k7s4_kernel<CIN, COUT, CCH><<<grid, 128, 0, s>>>(p);
     VP_LAUNCH_CHECK();
     return VP_OK;

@@ -550,6 +550,7 @@ static int decb_launch_t(const FzDecB &p, dim3 grid, cudaStream_t s) {
         VP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes));
         attr = p.smem_bytes;
     }
+    KTimer kt(KC_DECB, s);
     kern<<<grid, FZ_THREADS, p.smem_bytes, s>>>(p);
     VP_LAUNCH_CHECK();
     return VP_OK;

@@ -325,6 +325,7 @@ static int deca_launch_t(const FzDecA &p, dim3 grid, cudaStream_t s) {
         VP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes));
         attr = p.smem_bytes;
     }
+    KTimer kt(KC_DECA, s);
     kern<<<grid, DA_THREADS, p.smem_bytes, s>>>(p);
     VP_LAUNCH_CHECK();
     return VP_OK;

@@ -31,6 +31,43 @@ void set_error(const char *fmt, ...) {
 }
 void count_launch(int n) { g_launches += n; }
 
+thread_local bool g_ktimer_on = false;
+namespace {
+struct KSpan {
+    int cls;
+    cudaEvent_t e0, e1;
+};
+thread_local std::vector<KSpan> g_kspans;
+thread_local std::vector<cudaEvent_t> g_kevent_pool;
+cudaEvent_t ktimer_event() {
+    if (!g_kevent_pool.empty()) {
+        cudaEvent_t e = g_kevent_pool.back();
+        g_kevent_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+const char *const KCLASS_NAMES =
+    "slice_normalize,slice_enc0,tcconv,deca,decb,conv1d_f32,convt_f32,lstm,attention,pack_cl16,stack,nan_bounds,pick";
+}  // namespace
+void ktimer_mark(int cls, cudaStream_t s, bool end) {
+    if (!end) {
+        KSpan sp{cls, ktimer_event(), nullptr};
+        cudaEventRecord(sp.e0, s);
+        g_kspans.push_back(sp);
+    } else {
+        for (size_t i = g_kspans.size(); i-- > 0;) {
+            if (g_kspans[i].cls == cls && g_kspans[i].e1 == nullptr) {
+                g_kspans[i].e1 = ktimer_event();
+                cudaEventRecord(g_kspans[i].e1, s);
+                break;
+            }
+        }
+    }
+}
+
 constexpr double BN_EPS = 1e-3;
 constexpr int64_t EQT_FLOATS = 378823;
 constexpr int64_t PN_FLOATS = 269675;
@@ -1035,6 +1072,35 @@ extern "C" int64_t vp_launch_count(int reset) {
     const int64_t v = g_launches;
     if (reset) g_launches = 0;
     return v;
+}
+
+extern "C" int vp_kernel_timing(int enable) {
+    for (auto &sp : vp::g_kspans) {
+        if (sp.e0) vp::g_kevent_pool.push_back(sp.e0);
+        if (sp.e1) vp::g_kevent_pool.push_back(sp.e1);
+    }
+    vp::g_kspans.clear();
+    vp::g_ktimer_on = enable != 0;
+    return VP_OK;
+}
+
+extern "C" const char *vp_kernel_class_names(void) { return vp::KCLASS_NAMES; }
+
+extern "C" int vp_kernel_timing_read(int kclass, double *total_ms, int64_t *launches) {
+    VP_REQUIRE(kclass >= 0 && kclass < vp::KC_COUNT && total_ms && launches, VP_ERR_ARG, "vp_kernel_timing_read: bad argument");
+    double tot = 0.0;
+    int64_t cnt = 0;
+    for (auto &sp : vp::g_kspans) {
+        if (sp.cls != kclass || !sp.e1) continue;
+        VP_CUDA_CHECK(cudaEventSynchronize(sp.e1));
+        float ms = 0.f;
+        VP_CUDA_CHECK(cudaEventElapsedTime(&ms, sp.e0, sp.e1));
+        tot += ms;
+        ++cnt;
+    }
+    *total_ms = tot;
+    *launches = cnt;
+    return VP_OK;
 }
 extern "C" int64_t vp_model_expected_floats(int kind) {
     return kind == VP_KIND_EQTRANSFORMER ? EQT_FLOATS : kind == VP_KIND_PHASENET ? PN_FLOATS : -1;

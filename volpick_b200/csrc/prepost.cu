@@ -287,6 +287,7 @@ int launch_slice_enc0(const void *trace, int dtype, int64_t ch_stride, const int
         }                                                                                                                   \
         kern<<<(unsigned)nw, E0_NT, smem, s>>>((const T *)trace, ch_stride, starts, L, scope, taper, tap, wt, out, out_split); \
     } while (0)
+    KTimer kt(KC_SLICE_ENC0, s);
     if (dtype == VP_DTYPE_F32 && split == 2) VP_E0_LAUNCH(float, 2);
     else if (dtype == VP_DTYPE_F32) VP_E0_LAUNCH(float, 1);
     else if (split == 2) VP_E0_LAUNCH(int32_t, 2);
@@ -304,6 +305,7 @@ static int launch_slice(const Tin *trace, int64_t ch_stride, const int64_t *star
         const double a = M_PI + (M_PI * i) / 5.0;
         tap.t[i] = (float)(0.5 * (1.0 + std::cos(a)));
     }
+    KTimer kt(KC_SLICE, s);
     if (L <= 6 * 512) {
         slice_normalize_kernel<Tin, 6, 512><<<(unsigned)nw, 512, 0, s>>>(trace, ch_stride, starts, L, scope, taper, tap, out);
     } else if (L <= 12 * 512) {
@@ -558,69 +560,203 @@ __global__ void __launch_bounds__(256) nan_bounds_kernel(const float *__restrict
 }
 
 // ------------------------------------------------------------------------------------------ K10
-// Pass A: every sample that opens a run of x > thr_off appends its index to run_starts.
-__global__ void __launch_bounds__(256) run_starts_kernel(const float *__restrict__ x, int64_t n, float thr_off,
-                                                         int64_t *__restrict__ run_starts, int64_t cap,
-                                                         unsigned long long *__restrict__ nruns) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const bool cur = __ldg(x + i) > thr_off;  // NaN compares false
-    const bool prev = (i > 0) && (__ldg(x + i - 1) > thr_off);
-    if (cur && !prev) {
-        const unsigned long long slot = atomicAdd(nruns, 1ULL);
-        if ((int64_t)slot < cap) run_starts[slot] = i;
+// trigger_onset + first argmax (+ _trim_nan bounds) in ONE pass over the annotation: a CTA stages a tile of
+// PK_TILE samples of one label in shared memory with aligned 16-byte loads, turns it into three bit masks
+// (x > thr_off, x > thr_on, !isnan) with warp ballots, finds the run starts of the tile from the mask words and lets
+// one warp resolve each run out of shared memory (end = next zero bit, onset = first set bit of the on-mask, first
+// maximum by a strided scan).  Only a run that leaves the tile is continued from global memory.
+constexpr int PK_TILE = 4096;
+constexpr int PK_NT = 256;
+constexpr int PK_WORDS = PK_TILE / 32;
+constexpr int PK_MAXLAB = 4;
+
+struct PickLabels {
+    const float *x[PK_MAXLAB];
+    float thr_on[PK_MAXLAB], thr_off[PK_MAXLAB];
+    int label[PK_MAXLAB];
+    int pick[PK_MAXLAB];  // 0: only the NaN bounds of this label are wanted
+    int bound_slot[PK_MAXLAB];
+};
+
+// Continues a run over global memory from `base` (a multiple-of-nothing absolute index), 32 samples at a time.
+__device__ __forceinline__ void pick_walk_global(const float *__restrict__ x, int64_t n, int64_t base, float thr_on,
+                                                 float thr_off, int lane, int64_t &on, int64_t &pk, float &best,
+                                                 int64_t &end) {
+    for (;; base += 32) {
+        const int64_t idx = base + lane;
+        const float v = (idx < n) ? __ldg(x + idx) : CUDART_NAN_F;
+        const bool above = v > thr_off;  // NaN compares false
+        const unsigned not_above = __ballot_sync(0xffffffffu, !above);
+        const int nvalid = not_above ? (__ffs(not_above) - 1) : 32;
+        const bool in_run = lane < nvalid;
+        if (on < 0) {
+            const unsigned m_on = __ballot_sync(0xffffffffu, in_run && v > thr_on);
+            if (m_on) on = base + (__ffs(m_on) - 1);
+        }
+        if (on >= 0) {
+            float bv = (in_run && idx >= on) ? v : -CUDART_INF_F;
+            int64_t bi = idx;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int64_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > bv || (ov == bv && oi < bi)) {
+                    bv = ov;
+                    bi = oi;
+                }
+            }
+            if (bv > best) {  // strict: the earliest chunk keeps ties -> first maximum
+                best = bv;
+                pk = bi;
+            }
+        }
+        if (nvalid < 32) {
+            end = base + nvalid - 1;
+            return;
+        }
     }
 }
 
-// Pass B: one warp walks one run 32 samples at a time.
-__global__ void __launch_bounds__(128) run_picks_kernel(const float *__restrict__ x, int64_t n, float thr_on,
-                                                        float thr_off, int label,
-                                                        const int64_t *__restrict__ run_starts, int64_t cap,
-                                                        const unsigned long long *__restrict__ nruns_p,
-                                                        vp_trigger *__restrict__ picks, int64_t pick_cap,
-                                                        unsigned long long *__restrict__ npicks) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    int64_t nruns = (int64_t)*nruns_p;
-    if (nruns > cap) nruns = cap;
-    for (int64_t r = warp; r < nruns; r += nwarps) {
-        const int64_t s = run_starts[r];
-        int64_t on = -1, pk = -1, end = -1;
-        float best = -CUDART_INF_F;
-        for (int64_t base = s;; base += 32) {
-            const int64_t idx = base + lane;
-            const float v = (idx < n) ? __ldg(x + idx) : CUDART_NAN_F;
-            const bool above = v > thr_off;
-            const unsigned not_above = __ballot_sync(0xffffffffu, !above);
-            const int nvalid = not_above ? (__ffs(not_above) - 1) : 32;
-            const bool in_run = lane < nvalid;
-            if (on < 0) {
-                const unsigned m_on = __ballot_sync(0xffffffffu, in_run && v > thr_on);
-                if (m_on) on = base + (__ffs(m_on) - 1);
-            }
-            if (on >= 0) {
-                float bv = (in_run && idx >= on) ? v : -CUDART_INF_F;
-                int64_t bi = idx;
+__global__ void __launch_bounds__(PK_NT) pick_tile_kernel(const PickLabels P, int64_t n, vp_trigger *__restrict__ picks,
+                                                          int64_t pick_cap, unsigned long long *__restrict__ npicks,
+                                                          int64_t *__restrict__ bounds) {
+    __shared__ __align__(16) float sv[PK_TILE];
+    __shared__ uint32_t m_off[PK_WORDS], m_on[PK_WORDS];
+    __shared__ uint16_t run_start[PK_TILE / 2];
+    __shared__ int n_runs, s_lo, s_hi, s_prev;
+    const int li = blockIdx.y;
+    const float *__restrict__ x = P.x[li];
+    const float thr_on = P.thr_on[li], thr_off = P.thr_off[li];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int shift = (int)((reinterpret_cast<uintptr_t>(x) >> 2) & 3);  // elements past a 16-byte boundary
+    const int64_t t0 = (int64_t)blockIdx.x * PK_TILE - shift;
+    if (tid == 0) {
+        n_runs = 0;
+        s_lo = PK_TILE;
+        s_hi = -1;
+        s_prev = (t0 > 0 && t0 - 1 < n && __ldg(x + t0 - 1) > thr_off) ? 1 : 0;
+    }
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                    const int64_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                    if (ov > bv || (ov == bv && oi < bi)) {
-                        bv = ov;
-                        bi = oi;
-                    }
-                }
-                if (bv > best) {  // strict: the earliest chunk keeps ties -> first maximum
-                    best = bv;
-                    pk = bi;
-                }
+    for (int it = 0; it < PK_TILE / (4 * PK_NT); ++it) {
+        const int o = (it * PK_NT + tid) * 4;
+        const int64_t g = t0 + o;
+        float4 v;
+        if (g >= 0 && g + 3 < n) {
+            v = __ldg(reinterpret_cast<const float4 *>(x + g));
+        } else {
+            v.x = (g >= 0 && g < n) ? __ldg(x + g) : CUDART_NAN_F;
+            v.y = (g + 1 >= 0 && g + 1 < n) ? __ldg(x + g + 1) : CUDART_NAN_F;
+            v.z = (g + 2 >= 0 && g + 2 < n) ? __ldg(x + g + 2) : CUDART_NAN_F;
+            v.w = (g + 3 >= 0 && g + 3 < n) ? __ldg(x + g + 3) : CUDART_NAN_F;
+        }
+        *reinterpret_cast<float4 *>(sv + o) = v;
+    }
+    __syncthreads();
+    int lo = PK_TILE, hi = -1;
+#pragma unroll 4
+    for (int j = 0; j < PK_WORDS / (PK_NT / 32); ++j) {
+        const int word = warp * (PK_WORDS / (PK_NT / 32)) + j;
+        const float v = sv[word * 32 + lane];
+        const unsigned b_off = __ballot_sync(0xffffffffu, v > thr_off);
+        const unsigned b_on = __ballot_sync(0xffffffffu, v > thr_on);
+        const unsigned b_ok = __ballot_sync(0xffffffffu, !isnan(v));
+        if (lane == 0) {
+            m_off[word] = b_off;
+            m_on[word] = b_on;
+        }
+        if (b_ok) {
+            lo = min(lo, word * 32 + __ffs(b_ok) - 1);
+            hi = max(hi, word * 32 + 31 - __clz(b_ok));
+        }
+    }
+    if (bounds != nullptr && lane == 0 && hi >= 0) {
+        atomicMin(&s_lo, lo);
+        atomicMax(&s_hi, hi);
+    }
+    __syncthreads();
+    if (bounds != nullptr && tid == 0 && s_hi >= 0) {
+        const int slot = P.bound_slot[li];
+        atomicMin(reinterpret_cast<long long *>(bounds + 2 * slot), (long long)(t0 + s_lo));
+        atomicMax(reinterpret_cast<long long *>(bounds + 2 * slot + 1), (long long)(t0 + s_hi));
+    }
+    if (!P.pick[li]) return;
+    if (tid < PK_WORDS) {
+        const uint32_t m = m_off[tid];
+        const uint32_t carry = tid > 0 ? (m_off[tid - 1] >> 31) : (uint32_t)s_prev;
+        uint32_t st = m & ~((m << 1) | carry);
+        while (st) {
+            const int b = __ffs(st) - 1;
+            st &= st - 1;
+            run_start[atomicAdd(&n_runs, 1)] = (uint16_t)(tid * 32 + b);
+        }
+    }
+    __syncthreads();
+    const int nr = n_runs;
+    for (int r = warp; r < nr; r += PK_NT / 32) {
+        const int s = run_start[r];
+        const int w = s >> 5;
+        const uint32_t from_s = 0xffffffffu << (s & 31);
+        // last sample of the run inside the tile
+        int end_in = PK_TILE - 1;
+        bool leaves = true;
+        for (int wb = w; wb < PK_WORDS; wb += 32) {
+            const int wi = wb + lane;
+            uint32_t inv = 0;
+            if (wi < PK_WORDS) {
+                inv = ~m_off[wi];
+                if (wi == w) inv &= from_s;
             }
-            if (nvalid < 32) {
-                end = base + nvalid - 1;
+            const unsigned bal = __ballot_sync(0xffffffffu, inv != 0);
+            if (bal) {
+                const int l = __ffs(bal) - 1;
+                const uint32_t iv = __shfl_sync(0xffffffffu, inv, l);
+                end_in = (wb + l) * 32 + __ffs(iv) - 2;
+                leaves = false;
                 break;
             }
         }
+        // first sample above thr_on inside [s, end_in]
+        int on_in = -1;
+        const int we = end_in >> 5;
+        for (int wb = w; wb <= we; wb += 32) {
+            const int wi = wb + lane;
+            uint32_t mo = 0;
+            if (wi <= we) {
+                mo = m_on[wi];
+                if (wi == w) mo &= from_s;
+                if (wi == we) mo &= (2u << (end_in & 31)) - 1u;
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, mo != 0);
+            if (bal) {
+                const int l = __ffs(bal) - 1;
+                const uint32_t mv = __shfl_sync(0xffffffffu, mo, l);
+                on_in = (wb + l) * 32 + __ffs(mv) - 1;
+                break;
+            }
+        }
+        float bv = -CUDART_INF_F;
+        int bi = 0x7fffffff;
+        if (on_in >= 0) {
+            for (int i = on_in + lane; i <= end_in; i += 32) {
+                const float v = sv[i];
+                if (v > bv) {
+                    bv = v;
+                    bi = i;
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > bv || (ov == bv && oi < bi)) {
+                    bv = ov;
+                    bi = oi;
+                }
+            }
+        }
+        int64_t on = on_in >= 0 ? t0 + on_in : -1, pk = on_in >= 0 ? t0 + bi : -1, end = t0 + end_in;
+        float best = bv;
+        if (leaves) pick_walk_global(x, n, t0 + PK_TILE, thr_on, thr_off, lane, on, pk, best, end);
         if (on >= 0 && lane == 0) {
             const unsigned long long slot = atomicAdd(npicks, 1ULL);
             if ((int64_t)slot < pick_cap) {
@@ -629,7 +765,7 @@ __global__ void __launch_bounds__(128) run_picks_kernel(const float *__restrict_
                 q.s1 = end;
                 q.s_peak = pk;
                 q.value = best;
-                q.label = label;
+                q.label = P.label[li];
                 picks[slot] = q;
             }
         }
@@ -690,6 +826,7 @@ extern "C" int vp_stack(const float *y, const int64_t *starts, int64_t n_windows
     const int64_t stride = in_samples - overlap;
     const bool small = n_windows < (1LL << 30) && in_samples < (1LL << 30) && blind0 <= in_samples && blind1 <= in_samples;
     const unsigned grid4 = (unsigned)((pred_len + 1023) / 1024);
+    KTimer kt(KC_STACK, s);
     static const bool scalar_only = getenv("VP_STACK_SCALAR") && atoi(getenv("VP_STACK_SCALAR")) != 0;  // debugging aid
     if (cov == 3 && small && !scalar_only)
         stack4_kernel<3><<<grid4, 256, 0, s>>>(y, starts, (int)n_windows, (int)in_samples, n_labels, (int)stride, (int)blind0,
@@ -709,6 +846,7 @@ extern "C" int vp_stack(const float *y, const int64_t *starts, int64_t n_windows
 extern "C" int vp_nan_bounds(const float *annotation, int n_labels, int64_t pred_len, int64_t *bounds, void *stream) {
     VP_REQUIRE(annotation && bounds && n_labels > 0 && n_labels <= 32, VP_ERR_ARG, "vp_nan_bounds: bad argument");
     cudaStream_t s = (cudaStream_t)stream;
+    KTimer kt(KC_TRIM, s);
     nan_bounds_init_kernel<<<1, 32, 0, s>>>(bounds, n_labels, pred_len);
     VP_LAUNCH_CHECK();
     if (pred_len > 0) {
@@ -720,26 +858,61 @@ extern "C" int vp_nan_bounds(const float *annotation, int n_labels, int64_t pred
 }
 
 extern "C" int64_t vp_pick_scratch_bytes(int64_t n_samples) {
-    // run starts (at most ceil(n/2)) + the run counter
-    return align_up((n_samples / 2 + 2) * (int64_t)sizeof(int64_t), 256) + 256;
+    (void)n_samples;  // the single-pass kernel keeps its run list in shared memory; the argument is kept for the ABI
+    return 256;
+}
+
+static int launch_pick_tiles(const PickLabels &P, int n_lab, int64_t n, vp_trigger *picks, int64_t capacity,
+                             int64_t *count, int64_t *bounds, cudaStream_t s) {
+    // +1 tile: the tile grid of a label starts up to 3 samples before its first sample (16-byte alignment)
+    const unsigned tiles = (unsigned)((n + 3 + PK_TILE - 1) / PK_TILE);
+    KTimer kt(KC_PICK, s);
+    pick_tile_kernel<<<dim3(tiles, n_lab), PK_NT, 0, s>>>(P, n, picks, capacity, (unsigned long long *)count, bounds);
+    VP_LAUNCH_CHECK();
+    return VP_OK;
 }
 
 extern "C" int vp_pick(const float *trace, int64_t n_samples, float thr_on, float thr_off, int label, vp_trigger *picks,
                        int64_t capacity, int64_t *count, void *scratch, int64_t scratch_bytes, void *stream) {
-    VP_REQUIRE(trace && picks && count && scratch, VP_ERR_ARG, "vp_pick: null pointer");
-    VP_REQUIRE(scratch_bytes >= vp_pick_scratch_bytes(n_samples), VP_ERR_WORKSPACE,
-               "vp_pick: scratch too small (%lld < %lld)", (long long)scratch_bytes,
-               (long long)vp_pick_scratch_bytes(n_samples));
+    VP_REQUIRE(trace && picks && count, VP_ERR_ARG, "vp_pick: null pointer");
+    (void)scratch;
+    (void)scratch_bytes;
     if (n_samples <= 0) return VP_OK;
+    PickLabels P = {};
+    P.x[0] = trace;
+    P.thr_on[0] = thr_on;
+    P.thr_off[0] = thr_off;
+    P.label[0] = label;
+    P.pick[0] = 1;
+    return launch_pick_tiles(P, 1, n_samples, picks, capacity, count, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int vp_pick_labels(const float *annotation, int n_labels, int64_t pred_len, const float *thr_on,
+                              const float *thr_off, vp_trigger *picks, int64_t capacity, int64_t *count, int64_t *bounds,
+                              void *stream) {
+    VP_REQUIRE(annotation && thr_on && thr_off && count, VP_ERR_ARG, "vp_pick_labels: null pointer");
+    VP_REQUIRE(n_labels > 0 && n_labels <= PK_MAXLAB, VP_ERR_ARG, "vp_pick_labels: n_labels %d outside [1, %d]", n_labels,
+               PK_MAXLAB);
+    VP_REQUIRE(capacity == 0 || picks, VP_ERR_ARG, "vp_pick_labels: pick buffer missing");
     cudaStream_t s = (cudaStream_t)stream;
-    unsigned long long *nruns = (unsigned long long *)scratch;
-    int64_t *run_starts = (int64_t *)((char *)scratch + 256);
-    const int64_t cap = n_samples / 2 + 2;
-    VP_CUDA_CHECK(cudaMemsetAsync(nruns, 0, sizeof(unsigned long long), s));
-    run_starts_kernel<<<(unsigned)((n_samples + 255) / 256), 256, 0, s>>>(trace, n_samples, thr_off, run_starts, cap, nruns);
-    VP_LAUNCH_CHECK();
-    run_picks_kernel<<<148 * 4, 128, 0, s>>>(trace, n_samples, thr_on, thr_off, label, run_starts, cap, nruns, picks,
-                                             capacity, (unsigned long long *)count);
-    VP_LAUNCH_CHECK();
-    return VP_OK;
+    if (bounds) {
+        nan_bounds_init_kernel<<<1, 32, 0, s>>>(bounds, n_labels, pred_len);
+        VP_LAUNCH_CHECK();
+    }
+    if (pred_len <= 0) return VP_OK;
+    PickLabels P = {};
+    int nl = 0;
+    for (int c = 0; c < n_labels; ++c) {
+        const bool pick = thr_on[c] > 0.f && capacity > 0;  // <= 0 or NaN: no picks for that label
+        if (!pick && !bounds) continue;
+        P.x[nl] = annotation + (int64_t)c * pred_len;
+        P.thr_on[nl] = thr_on[c];
+        P.thr_off[nl] = thr_off[c];
+        P.label[nl] = c;
+        P.pick[nl] = pick ? 1 : 0;
+        P.bound_slot[nl] = c;
+        ++nl;
+    }
+    if (nl == 0) return VP_OK;
+    return launch_pick_tiles(P, nl, pred_len, picks, capacity, count, bounds, s);
 }

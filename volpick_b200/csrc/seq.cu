@@ -102,6 +102,7 @@ int launch_lstm(int cin, const LstmP &p, int G, cudaStream_t s) {
     const int64_t nseq = (int64_t)p.B * p.ndir;
     dim3 grid((unsigned)((nseq + 7) / 8), G);
     const size_t smem = (size_t)p.ndir * cin * 16 * sizeof(float4);
+    KTimer kt(KC_LSTM, s);
     if (cin == 64) {
         lstm_kernel<64><<<grid, 128, smem, s>>>(p);
     } else if (cin == 16) {
@@ -324,6 +325,7 @@ int launch_attention(const AttnP &p, int G, cudaStream_t s) {
         VP_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
+    KTimer kt(KC_ATTN, s);
     attention_kernel<<<grid, 128, smem, s>>>(p);
     VP_LAUNCH_CHECK();
     return VP_OK;

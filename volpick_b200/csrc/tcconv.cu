@@ -436,6 +436,7 @@ int launch_pack_cl16(const float *x, int64_t x_ss, int64_t x_cs, int NS, int C, 
                      int c8, cudaStream_t s) {
     const int64_t n = (int64_t)NS * T;
     if (n == 0) return VP_OK;
+    KTimer kt(KC_PACK, s);
     pack_cl16_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(x, x_ss, x_cs, NS, C, T, split, split == 2 ? 0 : 1, y, y_split, c8);
     VP_LAUNCH_CHECK();
     return VP_OK;
@@ -584,6 +585,7 @@ static int launch_tc(const TcP &p, dim3 grid, size_t smem, cudaStream_t s) {
         VP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = smem;
     }
+    KTimer kt(KC_TCCONV, s);
     kern<<<grid, 32 * (EW + 4), smem, s>>>(p);
     VP_LAUNCH_CHECK();
     return VP_OK;
