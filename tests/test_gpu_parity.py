@@ -170,6 +170,60 @@ def test_eqt_forward_tensor_core(eqt, sd_eqt, precision, atol):
     assert float(np.abs(got - ref).max()) <= atol
 
 
+PN_TC_TAPS = ["inc", "down0_same", "down0_down", "down1_same", "down1_down", "down2_same", "down2_down", "down3_same",
+              "down3_down", "down4_same", "up0_same", "up1_same", "up2_same", "up3_same"]
+
+
+@pytest.mark.parametrize("precision,atol", [("f16x3", PROB_ATOL), ("bf16", 5e-2)])
+def test_pn_forward_tensor_core(pn, sd_pn, precision, atol):
+    """PhaseNet on tcgen05: stride-4 convs / ConvTranspose1d as k = 2 convs on the row-reshaped buffers, two-source
+    concat conv, fused 1x1 + softmax head.  Layer by layer against the oracle, then the probabilities."""
+    x = _windows("phasenet", 7, seed=22)
+    xt = torch.from_numpy(x)
+    xd = xt.cuda()
+    taps = {}
+    ref = nets.phasenet_forward(sd_pn, xt, taps).numpy()
+    lines, worst = [], []
+    for name in PN_TC_TAPS:
+        r = taps[name].numpy()
+        got = pn.forward_tap(xd, name, precision=precision).cpu().numpy().reshape(r.shape)
+        err, scale = float(np.abs(got - r).max()), float(np.abs(r).max())
+        lines.append(f"{name:12s} max|diff|={err:.3e}  max|ref|={scale:.3e}")
+        if precision == "f16x3" and err > 1e-4 * max(1.0, scale):
+            worst.append(name)
+    print("\n".join(lines))
+    got = pn.forward(xd, precision=precision).cpu().numpy()
+    print(f"{precision}: probabilities max|diff| = {np.abs(got - ref).max():.3e}")
+    assert not worst, "\n".join(lines)
+    assert ref[:, :2].max() > 0.5
+    assert float(np.abs(got - ref).max()) <= atol
+    np.testing.assert_allclose(got.sum(1), 1.0, atol=1e-5)
+
+
+@pytest.mark.parametrize("B", [1, 130])
+def test_pn_tensor_core_batch_sizes(pn, sd_pn, B):
+    x = _windows("phasenet", B, seed=60 + B)
+    got = pn.forward(torch.from_numpy(x).cuda(), precision="f16x3").cpu().numpy()
+    ref = pipeline.forward_batches("phasenet", sd_pn, x, 64).transpose(0, 2, 1)
+    assert float(np.abs(got - ref).max()) <= PROB_ATOL
+
+
+def test_pn_annotate_tensor_core_exact_mode(pn, sd_pn):
+    """f16x3 end to end for PhaseNet: probabilities within 1e-4 of the oracle, picks identical to the fp32 CUDA-core path."""
+    x = synthetic_record(41, 45_000)
+    thr = {"P_threshold": 0.2, "S_threshold": 0.2}
+    a32 = pn._argdict(dict(overlap=1500, blinding=(0, 0), stacking="avg", precision="fp32", **thr))
+    atc = pn._argdict(dict(overlap=1500, blinding=(0, 0), stacking="avg", precision="f16x3", **thr))
+    ann32, trig32, _ = pn.annotate_array(x, a32, True, pn._thresholds(a32))
+    anntc, trigtc, _ = pn.annotate_array(x, atc, True, pn._thresholds(atc))
+    ref = pipeline.annotate_array("phasenet", sd_pn, x, 1500, (0, 0), "avg")
+    ok = ~np.isnan(ref)
+    assert float(np.abs(anntc.T[ok] - ref[ok]).max()) <= PROB_ATOL
+    assert len(trig32) == len(trigtc) and len(trigtc) > 0
+    assert np.array_equal(trigtc["label"], trig32["label"])
+    assert np.abs(trigtc["s_peak"] - trig32["s_peak"]).max() <= 1
+
+
 @pytest.mark.parametrize("precision", ["f16x3", "bf16", "fp32"])
 @pytest.mark.parametrize("lo,hi", [(500, 5500), (0, 6000), (496, 5505), (1234, 2345), (5999, 6000), (0, 1), (3000, 3000)])
 def test_forward_range_matches_full_forward(lib, eqt, precision, lo, hi):

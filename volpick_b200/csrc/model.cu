@@ -252,7 +252,47 @@ struct vp_model {
         DecBPlan decb;  // fused decoder tail (fused_dec.cu)
         DecAPlan deca;  // fused decoder middle, convs.1 + convs.2 (fused_deca.cu)
     } tc[2];
+    // PhaseNet on the tensor cores (same precision sets).  Stride-4 convs and the stride-4 ConvTranspose1d run as k = 2
+    // convs on the row-reshaped channel-last buffers ([T][C] seen as [T / 4][4 C]); see build_pn_tc.
+    struct PnTcSet {
+        TcLayer inc, ds[5], dd[4], ut[4], us[4];
+        uint16_t *d_w = nullptr;
+        float *d_b = nullptr;
+        bool ready = false;
+    } pn_tc[2];
+    float pn_head_w[24] = {0}, pn_head_b[3] = {0};  // `out` conv (3, 8, 1) + bias, fused into the last layer's epilogue
 };
+
+template <class Set>
+static int upload_tc_layers(Set &ts, const std::vector<TcLayer *> &layers) {
+    size_t nw = 0, nb = 0;
+    for (TcLayer *L : layers) {
+        L->w_off = (int64_t)nw;
+        L->b_off = (int64_t)nb;
+        nw += (L->blocks.size() + 63) / 64 * 64;
+        nb += (L->bias.size() + 63) / 64 * 64;
+    }
+    VP_CUDA_CHECK(cudaMalloc(&ts.d_w, nw * sizeof(uint16_t) + 256));
+    VP_CUDA_CHECK(cudaMalloc(&ts.d_b, nb * sizeof(float) + 256));
+    for (TcLayer *L : layers) {
+        VP_CUDA_CHECK(cudaMemcpy(ts.d_w + L->w_off, L->blocks.data(), L->blocks.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+        VP_CUDA_CHECK(cudaMemcpy(ts.d_b + L->b_off, L->bias.data(), L->bias.size() * sizeof(float), cudaMemcpyHostToDevice));
+        L->blocks.clear();
+        L->blocks.shrink_to_fit();
+    }
+    ts.ready = true;
+    return VP_OK;
+}
+static int upload_pn_tc(vp_model::PnTcSet &ts) {
+    std::vector<TcLayer *> layers{&ts.inc};
+    for (int i = 0; i < 5; ++i) layers.push_back(&ts.ds[i]);
+    for (int i = 0; i < 4; ++i) {
+        layers.push_back(&ts.dd[i]);
+        layers.push_back(&ts.ut[i]);
+        layers.push_back(&ts.us[i]);
+    }
+    return upload_tc_layers(ts, layers);
+}
 
 static int upload_tc(vp_model::TcSet &ts) {
     std::vector<TcLayer *> layers;
@@ -434,40 +474,137 @@ static int build_eqt(vp_model *m, Cursor &cur, Packed &pk) {
     return VP_OK;
 }
 
-static void build_pn(vp_model *m, Cursor &cur, Packed &pk) {
-    {
-        const float *W = cur.take(8 * 3 * 7), *b = cur.take(8);
-        BN bn = take_bn(cur, 8);
-        m->inc = pack_conv(pk, W, b, &bn, 8, 3, 7);
+// Conv (cout, cin, k) [+ bias] + BatchNorm folded in double -> fp32 (cout, cin_pad, k) + (cout)
+struct FoldedConv {
+    std::vector<float> w, b;
+};
+static FoldedConv fold_conv(const float *W, const float *bias, const BN &bn, int cout, int cin, int k, int cin_pad) {
+    FoldedConv f;
+    std::vector<double> sc, sh;
+    bn_affine(bn, sc, sh);
+    f.w.assign((size_t)cout * cin_pad * k, 0.f);
+    f.b.assign(cout, 0.f);
+    for (int co = 0; co < cout; ++co) {
+        for (int ci = 0; ci < cin; ++ci)
+            for (int kk = 0; kk < k; ++kk)
+                f.w[((size_t)co * cin_pad + ci) * k + kk] = (float)((double)W[((size_t)co * cin + ci) * k + kk] * sc[co]);
+        f.b[co] = (float)((bias ? (double)bias[co] : 0.0) * sc[co] + sh[co]);
     }
+    return f;
+}
+
+// PhaseNet layers as tensor-core convs.  With channel-last rows a buffer [T][C] is also [T / 4][4 C], so
+//   * the stride-4 Conv1d (k = 7, SeisBench's manual left pad pl): out[s] = sum_j w[j] xp[4 s + j] over the padded signal
+//     xp becomes a k = 2 'valid' conv over rows of 4 C channels (tap 0: w[0..3], tap 1: w[4..6] and a zero), and
+//   * the stride-4 ConvTranspose1d (k = 7): out[4 r + q] = w[q] x[r] + w[q + 4] x[r - 1] becomes a k = 2 conv (left pad 1)
+//     with 4 C_out output columns per row, which is again the channel-last layout of the up-sampled signal.
+// Wide layers are split along the output columns into `groups` launches-in-one (grid.y) so that the resident weights
+// fit in shared memory.
+static int build_pn_tc(vp_model *m, const float *incW, const float *incB, const BN &incBN, const float *const *dsW, const BN *dsBN,
+                       const float *const *ddW, const BN *ddBN, const float *const *utW, const BN *utBN,
+                       const float *const *usW, const BN *usBN) {
+    for (int set = 0; set < 2; ++set) {
+        const int split = set == 0 ? 2 : 1;
+        vp_model::PnTcSet &ts = m->pn_tc[set];
+        auto build = [&](TcLayer &L, const FoldedConv &f, int cin, int cout, int k, int groups, int pad_left) -> int {
+            std::vector<const float *> wl(groups), bl(groups);
+            const int cg = cout / groups;
+            for (int g = 0; g < groups; ++g) {
+                wl[g] = f.w.data() + (size_t)g * cg * cin * k;
+                bl[g] = f.b.data() + (size_t)g * cg;
+            }
+            return tc_build_layer(L, TC_DIRECT, cin, cg, k, 0, split, groups, wl.data(), bl.data(), pad_left);
+        };
+        int rc = build(ts.inc, fold_conv(incW, incB, incBN, 8, 3, 7, 8), 8, 8, 7, 1, 3);
+        if (rc != VP_OK) return rc;
+        int last = 8;
+        for (int i = 0; i < 5; ++i) {
+            const int f = kPnC[i];
+            rc = build(ts.ds[i], fold_conv(dsW[i], nullptr, dsBN[i], f, last, 7, last), last, f, 7, f == 128 ? 2 : 1, 3);
+            if (rc != VP_OK) return rc;
+            last = f;
+            if (i == 4) break;
+            // stride-4 conv on the [T / 4][4 f] view: W2[co][q f + ci][tap] = w[co][ci][4 tap + q]
+            const FoldedConv fd = fold_conv(ddW[i], nullptr, ddBN[i], f, f, 7, f);
+            FoldedConv v;
+            v.b = fd.b;
+            v.w.assign((size_t)f * 4 * f * 2, 0.f);
+            for (int co = 0; co < f; ++co)
+                for (int ci = 0; ci < f; ++ci)
+                    for (int j = 0; j < 7; ++j)
+                        v.w[((size_t)co * 4 * f + (j & 3) * f + ci) * 2 + (j >> 2)] = fd.w[((size_t)co * f + ci) * 7 + j];
+            rc = build(ts.dd[i], v, 4 * f, f, 2, f == 64 ? 4 : 1, 0);
+            if (rc != VP_OK) return rc;
+        }
+        for (int i = 0; i < 4; ++i) {
+            const int f = kPnC[3 - i];
+            // ConvTranspose1d W (cin = last, cout = f, 7) + BN -> k = 2 conv with 4 f columns: row r, column q f + co
+            std::vector<double> sc, sh;
+            bn_affine(utBN[i], sc, sh);
+            FoldedConv v;
+            v.w.assign((size_t)4 * f * last * 2, 0.f);
+            v.b.assign((size_t)4 * f, 0.f);
+            for (int q = 0; q < 4; ++q)
+                for (int co = 0; co < f; ++co) {
+                    v.b[(size_t)q * f + co] = (float)sh[co];
+                    for (int ci = 0; ci < last; ++ci) {
+                        const float *w7 = utW[i] + ((size_t)ci * f + co) * 7;
+                        float *dst = &v.w[(((size_t)q * f + co) * last + ci) * 2];
+                        dst[1] = (float)((double)w7[q] * sc[co]);                  // x[r]
+                        dst[0] = q < 3 ? (float)((double)w7[q + 4] * sc[co]) : 0.f;  // x[r - 1]
+                    }
+                }
+            rc = build(ts.ut[i], v, last, 4 * f, 2, 4 * f > 128 ? 4 : 1, 1);
+            if (rc != VP_OK) return rc;
+            last = f;
+            rc = build(ts.us[i], fold_conv(usW[i], nullptr, usBN[i], f, 2 * f, 7, 2 * f), 2 * f, f, 7, f == 64 ? 4 : 1, 3);
+            if (rc != VP_OK) return rc;
+        }
+    }
+    return VP_OK;
+}
+
+static int build_pn(vp_model *m, Cursor &cur, Packed &pk) {
+    const float *incW = cur.take(8 * 3 * 7), *incB = cur.take(8);
+    const BN incBN = take_bn(cur, 8);
+    m->inc = pack_conv(pk, incW, incB, &incBN, 8, 3, 7);
+    const float *dsW[5], *ddW[4], *utW[4], *usW[4];
+    BN dsBN[5], ddBN[4], utBN[4], usBN[4];
     int last = 8;
     for (int i = 0; i < 5; ++i) {
         const int f = kPnC[i];
-        const float *W = cur.take((int64_t)f * last * 7);
-        BN bn = take_bn(cur, f);
-        m->down_same[i] = pack_conv(pk, W, nullptr, &bn, f, last, 7);
+        dsW[i] = cur.take((int64_t)f * last * 7);
+        dsBN[i] = take_bn(cur, f);
+        m->down_same[i] = pack_conv(pk, dsW[i], nullptr, &dsBN[i], f, last, 7);
         last = f;
         if (i < 4) {
-            const float *W2 = cur.take((int64_t)f * f * 7);
-            BN bn2 = take_bn(cur, f);
-            m->down_down[i] = pack_conv(pk, W2, nullptr, &bn2, f, f, 7);
+            ddW[i] = cur.take((int64_t)f * f * 7);
+            ddBN[i] = take_bn(cur, f);
+            m->down_down[i] = pack_conv(pk, ddW[i], nullptr, &ddBN[i], f, f, 7);
         }
     }
     for (int i = 0; i < 4; ++i) {
         const int f = kPnC[3 - i];
-        const float *W = cur.take((int64_t)last * f * 7);
-        BN bn = take_bn(cur, f);
-        m->up_t[i] = pack_convt(pk, W, bn, last, f);
+        utW[i] = cur.take((int64_t)last * f * 7);
+        utBN[i] = take_bn(cur, f);
+        m->up_t[i] = pack_convt(pk, utW[i], utBN[i], last, f);
         last = f;
-        const float *W2 = cur.take((int64_t)f * 2 * f * 7);
-        BN bn2 = take_bn(cur, f);
-        m->up_same[i] = pack_conv(pk, W2, nullptr, &bn2, f, 2 * f, 7);
+        usW[i] = cur.take((int64_t)f * 2 * f * 7);
+        usBN[i] = take_bn(cur, f);
+        m->up_same[i] = pack_conv(pk, usW[i], nullptr, &usBN[i], f, 2 * f, 7);
     }
     const float *W = cur.take(3 * 8), *b = cur.take(3);
     m->outc = pack_conv(pk, W, b, nullptr, 3, 8, 1);
+    std::memcpy(m->pn_head_w, W, sizeof(m->pn_head_w));
+    std::memcpy(m->pn_head_b, b, sizeof(m->pn_head_b));
+    if (cur.left == 0) {
+        int rc = build_pn_tc(m, incW, incB, incBN, dsW, dsBN, ddW, ddBN, utW, utBN, usW, usBN);
+        if (rc != VP_OK) return rc;
+    }
     m->tap_names =
         "inc,down0_same,down0_down,down1_same,down1_down,down2_same,down2_down,down3_same,down3_down,down4_same,"
         "up0_cat,up0_same,up1_cat,up1_same,up2_cat,up2_same,up3_cat,up3_same";
+    return VP_OK;
 }
 
 // ---- forward plan ---------------------------------------------------------------------------------
@@ -937,7 +1074,170 @@ static int run_eqt(Runner &r, const float *x, float *y, Arena &ar) {
     return r.rc;
 }
 
+// PhaseNet on the tensor cores.  Buffers are 16-bit channel-last [split][B][rows][C]:
+//   Bk  dense activations,  Al  skip_l stored at row offset padl[l] inside a zero-padded pitch of 4 * (len[l+1] + 1) rows
+//   (the stride-4 conv reads it as [rows / 4][4 C]),  Ul  ConvTranspose1d output, written as [Lin + 1][4 C] = [4 (Lin + 1)][C].
+// The channel concatenation [skip | up] is never materialised: the last conv of an up level stages its tile from both
+// buffers (TcIO::x2), the crop [1:-2] and the centring offset being row offsets of the second source.
+static int run_pn_tc(Runner &r, const float *x, float *y, Arena &ar) {
+    vp_model *m = r.m;
+    const int64_t B = r.B;
+    const int L0 = m->in_samples;
+    const int split = (r.precision == VP_PREC_F16X3) ? 2 : 1;
+    vp_model::PnTcSet &ts = m->pn_tc[split == 2 ? 0 : 1];
+    static const int padl[4] = {3, 2, 1, 2}, padr[4] = {3, 3, 3, 3};
+    int len[5], pitchA[4];
+    len[0] = L0;
+    for (int i = 0; i < 4; ++i) {
+        len[i + 1] = (len[i] + padl[i] + padr[i] - 7) / 4 + 1;
+        pitchA[i] = 4 * (len[i + 1] + 1);
+        if (pitchA[i] < padl[i] + len[i]) {
+            set_error("PhaseNet: padded pitch %d too small for level %d", pitchA[i], i);
+            return VP_ERR_ARG;
+        }
+    }
+    auto take16 = [&](int64_t rows, int c) { return reinterpret_cast<uint16_t *>(ar.take((B * rows * c * split + 1) / 2)); };
+    uint16_t *X16 = take16(L0, 8), *B0 = take16(L0, 8);
+    uint16_t *A[4], *Bd[5], *U[4], *Bu[4];
+    for (int i = 0; i < 4; ++i) {
+        A[i] = take16(pitchA[i], kPnC[i]);
+        Bd[i] = take16(len[i + 1], kPnC[i]);
+    }
+    Bd[4] = take16(len[4], 128);
+    for (int i = 0; i < 4; ++i) {
+        const int lvl = 3 - i;
+        U[i] = take16(pitchA[lvl], kPnC[lvl]);  // 4 * (len[lvl + 1] + 1) rows
+        Bu[i] = take16(len[lvl], kPnC[lvl]);
+    }
+    float *tapbuf = ar.take(B * 8 * (int64_t)L0);  // debug taps: any layer as fp32 (B, C, T), C * T <= 8 * L0
+    if (r.dry) return VP_OK;
+    if (!ts.ready) {
+        set_error("tensor-core weight set is not available");
+        return VP_ERR_UNSUPPORTED;
+    }
+    auto base_io = [&](const TcLayer &tl, const uint16_t *src, int rows_in, int c_in, int T_in) {
+        TcIO io;
+        io.x = src;
+        io.x_split = B * (int64_t)rows_in * c_in;
+        io.x_gs = 0;
+        io.T_in = T_in;
+        io.NS = (int)B;
+        io.w_dev = ts.d_w + tl.w_off;
+        io.b_dev = ts.d_b + tl.b_off;
+        io.act = ACT_RELU;
+        io.pool = 1;
+        io.out_fmt = 0;
+        io.y = nullptr;
+        io.y_split = 0;
+        io.y_gs = 0;
+        io.y_ss = 0;
+        io.y_cs = 0;
+        io.cout_cl = 0;
+        io.x_pitch = rows_in;
+        return io;
+    };
+    // dense 16-bit output [B][rows_out][c_total] (+ group column offset), or the fp32 debug tap
+    auto run_layer = [&](const char *name, const TcLayer &tl, TcIO io, uint16_t *dst, int rows_out, int y_roff, int c_total,
+                         int T_store) -> bool {
+        const bool tapped = r.stop_name && !r.stopped && name && std::strcmp(r.stop_name, name) == 0;
+        if (tapped) {
+            io.out_fmt = 1;
+            io.y = tapbuf;
+            io.y_split = 0;
+            io.y_gs = (int64_t)tl.cout * T_store;  // group g holds channels [g * cout, (g + 1) * cout)
+            io.y_ss = (int64_t)c_total * T_store;
+            io.y_cs = T_store;
+            io.cout_cl = 0;
+        } else {
+            io.y = dst;
+            io.y_split = B * (int64_t)rows_out * c_total;
+            io.y_gs = tl.cout;
+            io.cout_cl = c_total;
+            io.y_pitch = rows_out;
+            io.y_roff = y_roff;
+        }
+        if (r.go()) r.rc = tc_launch(tl, io, r.s);
+        if (tapped) r.tap(name, tapbuf, B * c_total * T_store);
+        return r.stopped || r.rc != VP_OK;
+    };
+    if (r.go()) r.rc = launch_pack_cl16(x, 3 * (int64_t)L0, L0, (int)B, 3, L0, split, X16, B * (int64_t)L0 * 8, 1, r.s);
+    if (run_layer("inc", ts.inc, base_io(ts.inc, X16, L0, 8, L0), B0, L0, 0, 8, L0)) return r.rc;
+    static const char *ds_names[5] = {"down0_same", "down1_same", "down2_same", "down3_same", "down4_same"};
+    static const char *dd_names[4] = {"down0_down", "down1_down", "down2_down", "down3_down"};
+    static const char *us_names[4] = {"up0_same", "up1_same", "up2_same", "up3_same"};
+    const uint16_t *cur = B0;
+    int cur_c = 8;
+    for (int i = 0; i < 4; ++i) {
+        const int f = kPnC[i];
+        if (r.go()) {  // zero rows around skip_i inside its padded pitch (read by the stride-4 conv as conv padding)
+            const size_t pitch_b = (size_t)pitchA[i] * f * 2, head_b = (size_t)padl[i] * f * 2;
+            const size_t tail_b = (size_t)(pitchA[i] - padl[i] - len[i]) * f * 2;
+            cudaError_t e = cudaMemset2DAsync(A[i], pitch_b, 0, head_b, (size_t)B * split, r.s);
+            if (e == cudaSuccess && tail_b)
+                e = cudaMemset2DAsync(A[i] + (size_t)(padl[i] + len[i]) * f, pitch_b, 0, tail_b, (size_t)B * split, r.s);
+            if (e != cudaSuccess) {
+                set_error("PhaseNet: clearing the skip padding failed: %s", cudaGetErrorString(e));
+                return VP_ERR_CUDA;
+            }
+        }
+        if (run_layer(ds_names[i], ts.ds[i], base_io(ts.ds[i], cur, len[i], cur_c, len[i]), A[i], pitchA[i], padl[i], f, len[i])) return r.rc;
+        {   // stride-4 conv: A_i seen as [pitch / 4][4 f], k = 2, 'valid': len[i + 1] output rows
+            TcIO io = base_io(ts.dd[i], A[i], pitchA[i] / 4, 4 * f, pitchA[i] / 4);
+            io.T_valid = len[i + 1];
+            if (run_layer(dd_names[i], ts.dd[i], io, Bd[i], len[i + 1], 0, f, len[i + 1])) return r.rc;
+        }
+        cur = Bd[i];
+        cur_c = f;
+    }
+    if (run_layer(ds_names[4], ts.ds[4], base_io(ts.ds[4], cur, len[4], cur_c, len[4]), Bd[4], len[4], 0, 128, len[4])) return r.rc;
+    cur = Bd[4];
+    cur_c = 128;
+    int cur_len = len[4];
+    for (int i = 0; i < 4; ++i) {
+        const int lvl = 3 - i;
+        const int f = kPnC[lvl];
+        const int Ls = len[lvl];
+        const int Lt = (cur_len - 1) * 4 + 7 - 3;  // ConvTranspose1d output, cropped [1:-2]
+        const int off = (Lt - Ls) / 2;
+        if (off < 0 || off + Ls > Lt || 4 * (cur_len + 1) != pitchA[lvl]) {
+            set_error("PhaseNet: skip merge mismatch (Lt=%d, Ls=%d)", Lt, Ls);
+            return VP_ERR_ARG;
+        }
+        {   // ConvTranspose1d as a k = 2 conv with 4 f columns: rows 0..cur_len of the [cur_len + 1][4 f] view of U
+            TcIO io = base_io(ts.ut[i], cur, cur_len, cur_c, cur_len);
+            io.T_valid = cur_len + 1;
+            if (run_layer(nullptr, ts.ut[i], io, U[i], cur_len + 1, 0, 4 * f, cur_len + 1)) return r.rc;
+        }
+        {   // conv over [skip | up] without the concatenation
+            TcIO io = base_io(ts.us[i], A[lvl], pitchA[lvl], f, Ls);
+            io.x_roff = padl[lvl];
+            io.x2 = U[i];
+            io.x2_split = B * (int64_t)pitchA[lvl] * f;
+            io.x2_pitch = pitchA[lvl];
+            io.x2_roff = 1 + off;
+            io.cin_a = f;
+            const bool tapped = r.stop_name && std::strcmp(r.stop_name, us_names[i]) == 0;
+            if (i == 3 && !tapped) {  // last layer: + `out` 1x1 conv + softmax -> (B, 3, L0) fp32
+                io.out_fmt = 2;
+                io.y = y;
+                io.y_ss = 3 * (int64_t)L0;
+                io.y_cs = L0;
+                io.head_w = m->pn_head_w;
+                io.head_b = m->pn_head_b;
+                if (r.go()) r.rc = tc_launch(ts.us[i], io, r.s);
+                return r.rc;
+            }
+            if (run_layer(us_names[i], ts.us[i], io, Bu[i], Ls, 0, f, Ls)) return r.rc;
+        }
+        cur = Bu[i];
+        cur_c = f;
+        cur_len = Ls;
+    }
+    return r.rc;
+}
+
 static int run_pn(Runner &r, const float *x, float *y, Arena &ar) {
+    if (r.precision != VP_PREC_FP32) return run_pn_tc(r, x, y, ar);
     vp_model *m = r.m;
     const int64_t B = r.B;
     const int L0 = m->in_samples;
@@ -1030,10 +1330,6 @@ static int run_forward(vp_model *m, const float *x, int64_t B, float *y, void *w
     if (precision != VP_PREC_FP32 && precision != VP_PREC_F16X3 && precision != VP_PREC_BF16) {
         set_error("unknown precision mode %d", precision);
         return VP_ERR_ARG;
-    }
-    if (precision != VP_PREC_FP32 && m->kind != VP_KIND_EQTRANSFORMER) {
-        set_error("the tensor-core precision modes are implemented for EQTransformer only (PhaseNet: fp32)");
-        return VP_ERR_UNSUPPORTED;
     }
     Runner r;
     r.precision = precision;
@@ -1129,7 +1425,11 @@ extern "C" int vp_model_create(int kind, const float *weights, int64_t n_floats,
             return rc;
         }
     } else {
-        build_pn(m, cur, pk);
+        int rc = build_pn(m, cur, pk);
+        if (rc != VP_OK) {
+            delete m;
+            return rc;
+        }
     }
     if (cur.left != 0) {
         set_error("vp_model_create: weight walk left %lld floats (layout mismatch)", (long long)cur.left);
@@ -1156,6 +1456,15 @@ extern "C" int vp_model_create(int kind, const float *weights, int64_t n_floats,
             }
         }
     }
+    if (kind == VP_KIND_PHASENET) {
+        for (int set = 0; set < 2; ++set) {
+            int rc = upload_pn_tc(m->pn_tc[set]);
+            if (rc != VP_OK) {
+                vp_model_destroy(m);
+                return rc;
+            }
+        }
+    }
     *out = m;
     return VP_OK;
 }
@@ -1168,6 +1477,8 @@ extern "C" int vp_model_destroy(vp_model *m) {
         if (m->tc[set].d_b) cudaFree(m->tc[set].d_b);
         decb_free(m->tc[set].decb);
         deca_free(m->tc[set].deca);
+        if (m->pn_tc[set].d_w) cudaFree(m->pn_tc[set].d_w);
+        if (m->pn_tc[set].d_b) cudaFree(m->pn_tc[set].d_b);
     }
     delete m;
     return VP_OK;

@@ -623,7 +623,7 @@ __global__ void __launch_bounds__(PK_NT) pick_tile_kernel(const PickLabels P, in
     __shared__ __align__(16) float sv[PK_TILE];
     __shared__ uint32_t m_off[PK_WORDS], m_on[PK_WORDS];
     __shared__ uint16_t run_start[PK_TILE / 2];
-    __shared__ int n_runs, s_lo, s_hi, s_prev;
+    __shared__ int n_runs, s_lo, s_hi, s_prev, s_prev_ok, s_next_ok;
     const int li = blockIdx.y;
     const float *__restrict__ x = P.x[li];
     const float thr_on = P.thr_on[li], thr_off = P.thr_off[li];
@@ -634,8 +634,11 @@ __global__ void __launch_bounds__(PK_NT) pick_tile_kernel(const PickLabels P, in
         n_runs = 0;
         s_lo = PK_TILE;
         s_hi = -1;
-        s_prev = (t0 > 0 && t0 - 1 < n && __ldg(x + t0 - 1) > thr_off) ? 1 : 0;
+        const float pv = (t0 > 0 && t0 - 1 < n) ? __ldg(x + t0 - 1) : CUDART_NAN_F;
+        s_prev = pv > thr_off ? 1 : 0;
+        s_prev_ok = isnan(pv) ? 0 : 1;
     }
+    if (tid == 32) s_next_ok = (t0 + PK_TILE < n && !isnan(__ldg(x + t0 + PK_TILE))) ? 1 : 0;
 #pragma unroll
     for (int it = 0; it < PK_TILE / (4 * PK_NT); ++it) {
         const int o = (it * PK_NT + tid) * 4;
@@ -675,9 +678,12 @@ __global__ void __launch_bounds__(PK_NT) pick_tile_kernel(const PickLabels P, in
     }
     __syncthreads();
     if (bounds != nullptr && tid == 0 && s_hi >= 0) {
+        // the first (last) non-NaN sample of the label follows (precedes) a NaN or the edge of the trace: a tile whose
+        // valid samples continue into its neighbours cannot hold it, so interior tiles issue no same-address atomics
         const int slot = P.bound_slot[li];
-        atomicMin(reinterpret_cast<long long *>(bounds + 2 * slot), (long long)(t0 + s_lo));
-        atomicMax(reinterpret_cast<long long *>(bounds + 2 * slot + 1), (long long)(t0 + s_hi));
+        if (s_lo > 0 || !s_prev_ok) atomicMin(reinterpret_cast<long long *>(bounds + 2 * slot), (long long)(t0 + s_lo));
+        if (s_hi < PK_TILE - 1 || !s_next_ok)
+            atomicMax(reinterpret_cast<long long *>(bounds + 2 * slot + 1), (long long)(t0 + s_hi));
     }
     if (!P.pick[li]) return;
     if (tid < PK_WORDS) {

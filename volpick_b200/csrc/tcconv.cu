@@ -214,7 +214,8 @@ __global__ void __launch_bounds__(32 * (EW + 4), EW == 16 ? 1 : EW == 8 ? 2 : 4)
     if (warp > EW) {
         // ================= producers =================
         const int ptid = tid - 32 * (EW + 1);
-        const int CIN = cin8 * 8;
+        const int cinA8 = p.cinA8;
+        const int CA = cinA8 * 8, CB = (cin8 - cinA8) * 8;
         const uint16_t *xg = p.x + (int64_t)g * p.x_gs;
         int stage = 0;
         uint32_t phase = 0;
@@ -232,13 +233,17 @@ __global__ void __launch_bounds__(32 * (EW + 4), EW == 16 ? 1 : EW == 8 ? 2 : 4)
                     valid = (seq < p.NS) && (u < p.T_eff);
                 }
                 const int srow = (p.ups == 2) ? (u >> 1) : u;
-                const uint16_t *src = valid ? (xg + ((int64_t)seq * p.T_in + srow) * CIN) : xg;
+                const uint16_t *src = valid ? (xg + ((int64_t)seq * p.x_pitch + p.x_roff + srow) * CA) : xg;
+                const uint16_t *src2 = (valid && CB) ? (p.x2 + ((int64_t)seq * p.x2_pitch + p.x2_roff + srow) * CB) : xg;
                 const uint32_t nb = valid ? 16u : 0u;
 #pragma unroll
                 for (int s = 0; s < SPLIT; ++s) {
                     const uint16_t *ss = valid ? (src + (int64_t)s * p.x_split) : xg;
-                    for (int c = 0; c < cin8; ++c)
+                    for (int c = 0; c < cinA8; ++c)
                         cp_async16(sbase + (uint32_t)((s * cin8 + c) * n_rows + r) * 16u, ss + c * 8, nb);
+                    const uint16_t *s2 = (valid && CB) ? (src2 + (int64_t)s * p.x2_split) : xg;
+                    for (int c = cinA8; c < cin8; ++c)
+                        cp_async16(sbase + (uint32_t)((s * cin8 + c) * n_rows + r) * 16u, s2 + (c - cinA8) * 8, nb);
                 }
             }
             cp_async_mbar_arrive_noinc(&full_bar[stage]);
@@ -308,7 +313,7 @@ __global__ void __launch_bounds__(32 * (EW + 4), EW == 16 ? 1 : EW == 8 ? 2 : 4)
             // output row bases (polyphase: row 2 srow + phi; pool: row srow >> 1, written by the even lane)
             const bool st = (p.pool == 2) ? (row_ok && !(lane & 1)) : row_ok;
             const int t0 = (p.pool == 2) ? (srow >> 1) : p.ph * srow;
-            const int64_t orow0 = (int64_t)seq * p.T_out + t0;
+            const int64_t orow0 = (int64_t)seq * p.y_pitch + p.y_roff + t0;
             if constexpr (FLAGS >= 0) {
                 if (!(p.dbg & 4)) tc_epilogue_fixed<NOUT, SPLIT, EW, FLAGS>(p, trow, half, lane, seq, srow, row_ok, g, s_bias, s_psc, s_psh);
             } else if (!(p.dbg & 4)) {
@@ -371,7 +376,23 @@ __global__ void __launch_bounds__(32 * (EW + 4), EW == 16 ? 1 : EW == 8 ? 2 : 4)
                             for (int i = 0; i < 8; ++i) w8[i] = fmaxf(fmaf(w8[i], s_psc[n0 + i], s_psh[n0 + i]), 0.f);
                         }
                         if (!ok) continue;
-                        if (p.out_fmt == 0) {
+                        if (p.out_fmt == 2) {  // PhaseNet head: 1x1 conv (8 -> 3) + softmax over the classes, fp32 (seq, 3, T)
+                            float z[3];
+#pragma unroll
+                            for (int j = 0; j < 3; ++j) {
+                                float a0 = p.head_b[j];
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) a0 = fmaf(p.head_w[j * 8 + i], w8[i], a0);
+                                z[j] = a0;
+                            }
+                            const float zm = fmaxf(z[0], fmaxf(z[1], z[2]));
+                            const float e0 = expf(z[0] - zm), e1 = expf(z[1] - zm), e2 = expf(z[2] - zm);
+                            const float inv = 1.f / (e0 + e1 + e2);
+                            float *yb = reinterpret_cast<float *>(p.y) + (int64_t)seq * p.y_ss + t_out;
+                            yb[0] = e0 * inv;
+                            yb[p.y_cs] = e1 * inv;
+                            yb[2 * p.y_cs] = e2 * inv;
+                        } else if (p.out_fmt == 0) {
                             uint4 hi, lo;
                             tc_pack8<SPLIT>(w8, hi, lo);
                             uint16_t *yb = reinterpret_cast<uint16_t *>(p.y) + (int64_t)g * p.y_gs + (orow0 + phi) * p.cout_cl + c0;
@@ -598,6 +619,15 @@ int tc_launch(const TcLayer &L, const TcIO &io, cudaStream_t s) {
     p.x_split = io.x_split;
     p.x_gs = io.x_gs;
     p.T_in = io.T_in;
+    p.x_pitch = io.x_pitch > 0 ? io.x_pitch : io.T_in;
+    p.x_roff = io.x_roff;
+    p.x2 = io.x2;
+    p.x2_split = io.x2_split;
+    p.x2_pitch = io.x2_pitch;
+    p.x2_roff = io.x2_roff;
+    p.cinA8 = io.x2 ? io.cin_a / 8 : L.cin / 8;
+    VP_REQUIRE(!io.x2 || (io.cin_a % 8 == 0 && io.cin_a > 0 && io.cin_a < L.cin && L.cin != 8 && L.ups == 1), VP_ERR_UNSUPPORTED,
+               "tc conv: bad two-source split (%d of %d channels)", io.cin_a, L.cin);
     p.ups = L.ups;
     p.T_eff = (L.ups == 2) ? 2 * io.T_in - L.crop : io.T_in;
     const int left = -L.row0, right = L.halo + L.row0;
@@ -641,6 +671,20 @@ int tc_launch(const TcLayer &L, const TcIO &io, cudaStream_t s) {
     p.coutp = (L.cout + 7) / 8 * 8;
     p.T_valid = (L.ph == 2) ? io.T_in : p.T_eff;
     p.T_out = tc_out_len(L, io.T_in, io.pool);
+    if (io.T_valid > 0) {  // explicit number of output rows per sequence ('valid' convs of the reshaped stride-4 layers)
+        VP_REQUIRE(L.ph == 1 && io.pool != 2 && io.T_valid <= Tp, VP_ERR_UNSUPPORTED, "tc conv: T_valid override needs a direct un-pooled layer");
+        p.T_valid = io.T_valid;
+        p.T_out = io.T_valid;
+    }
+    p.y_pitch = io.y_pitch > 0 ? io.y_pitch : p.T_out;
+    p.y_roff = io.y_roff;
+    if (io.out_fmt == 2) {
+        VP_REQUIRE(io.head_w && io.head_b && L.cout == 8 && L.ph == 1, VP_ERR_UNSUPPORTED, "tc conv: the softmax head needs an 8-channel direct layer");
+        std::memcpy(p.head_w, io.head_w, sizeof(p.head_w));
+        std::memcpy(p.head_b, io.head_b, sizeof(p.head_b));
+    }
+    const bool custom = io.x2 || p.x_pitch != io.T_in || p.x_roff != 0 || p.y_pitch != p.T_out || p.y_roff != 0 || io.T_valid > 0 ||
+                        io.out_fmt == 2;
     p.out_fmt = io.out_fmt;
     p.y = io.y;
     p.y_split = io.y_split;
@@ -678,7 +722,7 @@ int tc_launch(const TcLayer &L, const TcIO &io, cudaStream_t s) {
     // epilogue options of this launch; the compile-time epilogue needs the common case: 16-bit output, ReLU (or the
     // res-CNN extras carrying the activation), no padding columns
     const bool extra = io.res || io.y32 || io.post_scale;
-    const bool plain = io.out_fmt == 0 && L.nout == L.ph * L.cout && io.cout_cl == L.cout &&
+    const bool plain = !custom && io.out_fmt == 0 && L.nout == L.ph * L.cout && io.cout_cl == L.cout &&
                        (extra ? (io.act == ACT_RELU || io.act == ACT_NONE) : io.act == ACT_RELU);
     const int flags = plain ? ((io.pool == 2 ? 1 : 0) | (L.ph == 2 ? 2 : 0) | (extra ? 4 : 0)) : -1;
 #define VP_TC_FIXED(N, T, Q, F)                                                                                  \

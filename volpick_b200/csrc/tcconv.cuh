@@ -7,7 +7,7 @@
 
 namespace vp {
 
-constexpr int TC_MAX_MMA = 48;
+constexpr int TC_MAX_MMA = 64;
 constexpr int TC_MAX_TERMS = 3 * TC_MAX_MMA;
 
 struct TcMma {
@@ -19,8 +19,14 @@ struct TcMma {
 
 // Kernel parameters of one tensor-core conv layer launch (see tcconv.cu for the data layouts).
 struct TcP {
-    const uint16_t *x;  // channel-last 16-bit activations [SPLIT][G][NS][T_in][CIN]
+    const uint16_t *x;  // channel-last 16-bit activations [SPLIT][G][NS][x_pitch][CIN_A]; row (seq, u) lives at seq * x_pitch + x_roff + u
     int64_t x_split, x_gs;
+    int x_pitch, x_roff;
+    // optional second source (channel concatenation without a copy: PhaseNet skip | up-sampled): planes cinA8.. of the
+    // staged tile come from x2, [SPLIT][NS][x2_pitch][CIN - CIN_A]
+    const uint16_t *x2;
+    int64_t x2_split;
+    int x2_pitch, x2_roff, cinA8;
     int T_in, T_eff, ups, Tp, NS, row0, n_rows, cin8, n_stages;
     const uint16_t *w;  // [G][n_blocks][SPLIT][2][NOUT][8]
     int64_t w_gs;
@@ -34,10 +40,12 @@ struct TcP {
     int fmt16;  // 0: fp16, 1: bf16
     int dbg;    // profiling aid (env VP_TC_DBG): 1 skip A loads, 2 skip MMAs, 4 skip epilogue body
     int act, pool, ph, cout, coutp, T_valid, T_out;
-    int out_fmt;  // 0: channel-last 16-bit [SPLIT][G][NS][T_out][cout_cl]; 1: fp32 (seq stride y_ss, channel stride y_cs)
+    int out_fmt;  // 0: channel-last 16-bit [SPLIT][G][NS][y_pitch][cout_cl], row (seq, t) at seq * y_pitch + y_roff + t;
+                  // 1: fp32 (seq stride y_ss, channel stride y_cs); 2: fp32 like 1 after the fused 1x1 conv (8 -> 3) + softmax head
     void *y;
     int64_t y_split, y_gs, y_ss, y_cs;
-    int cout_cl;
+    int cout_cl, y_pitch, y_roff;
+    float head_w[24], head_b[3];  // out_fmt 2: PhaseNet `out` conv, [class][channel]
     // epilogue extras (single group, direct, un-pooled layers: the res-CNN stack)
     const float *post_scale, *post_shift;  // [NOUT]: 16-bit output = relu(v * scale + shift) (pre-activation BN + ReLU of the next conv)
     const float *res;                      // fp32 row-major [NS][T_out][cout] added to v
@@ -79,6 +87,13 @@ struct TcIO {
     int cout_cl;
     const float *post_scale = nullptr, *post_shift = nullptr, *res = nullptr;
     float *y32 = nullptr;
+    // storage overrides (0 / negative: dense defaults): rows per sequence and first row of the input / output buffers,
+    // output rows to store per sequence, second input source, fused softmax head
+    int x_pitch = 0, x_roff = 0, y_pitch = 0, y_roff = 0, T_valid = 0;
+    const uint16_t *x2 = nullptr;
+    int64_t x2_split = 0;
+    int x2_pitch = 0, x2_roff = 0, cin_a = 0;  // cin_a: channels taken from x when x2 is set
+    const float *head_w = nullptr, *head_b = nullptr;  // HOST pointers, out_fmt 2
 };
 int tc_out_len(const TcLayer &L, int T_in, int pool);
 int tc_launch(const TcLayer &L, const TcIO &io, cudaStream_t s);
