@@ -39,6 +39,7 @@ FLOP_PER_WINDOW = {"eqtransformer": 257.04e6, "phasenet": 38.92e6}  # BASELINE.m
 KCLASS_FLOP_PER_WINDOW = {
     ("eqtransformer", "decb"): 2 * 3 * (32 * 32 * 7 * 750 + 16 * 32 * 7 * 1500 + 16 * 16 * 9 * 3000 + 8 * 16 * 11 * 6000 + 8 * 11 * 6000),
     ("phasenet", "conv1d_f32"): 2 * (19.46e6 - (128 * 64 * 12 + 64 * 32 * 47 + 32 * 16 * 188 + 16 * 8 * 751) * 7),
+    ("phasenet", "tcconv"): 38.92e6,  # every Conv1d / ConvTranspose1d of the network runs in tcconv_kernel
 }
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture (profiles/):
 KCLASS_NCU_TRAFFIC = {("eqtransformer", "decb", "f16x3"): {"bytes_per_launch": 535.19e6 + 231.43e6, "windows_per_launch": 4096,

@@ -271,6 +271,24 @@ def test_annotate_tensor_core_exact_mode(eqt, sd_eqt):
     assert errbf <= 5e-2
 
 
+@pytest.mark.parametrize("kind", ["eqtransformer", "phasenet"])
+@pytest.mark.parametrize("on_host", [True, False])
+def test_annotate_chunked_two_lanes_bit_identical(eqt, pn, kind, on_host):
+    """Chunks of a record alternate between two streams (own forward workspace each, piecewise H2D of host records):
+    any chunking must give bit-identical annotations and triggers to the single-chunk run."""
+    model = eqt if kind == "eqtransformer" else pn
+    x = synthetic_record(43, 90_000)
+    rec = x if on_host else torch.from_numpy(x).cuda()
+    base = dict(overlap=model.in_samples - 500, blinding=(250, 250), stacking="avg", P_threshold=0.2, S_threshold=0.2)
+    a1 = model._argdict(dict(base, chunk_windows=4096))
+    ann1, trig1, trim1 = model.annotate_array(rec, a1, True, model._thresholds(a1))
+    for chunk in (7, 32, 100):
+        ac = model._argdict(dict(base, chunk_windows=chunk))
+        annc, trigc, trimc = model.annotate_array(rec, ac, True, model._thresholds(ac))
+        np.testing.assert_array_equal(annc.view(np.uint32), ann1.view(np.uint32))
+        assert np.array_equal(trigc, trig1) and np.array_equal(np.asarray(trimc), np.asarray(trim1))
+
+
 def test_golden_window_probabilities(eqt, pn, golden):
     for name, g in golden.items():
         model = eqt if str(g["kind"]) == "eqtransformer" else pn

@@ -41,7 +41,9 @@ namespace {
 
 struct Layout {
     int64_t off_trace, off_starts, off_x, off_fwd, off_y, off_annot, off_bounds, off_count, off_picks, off_scratch;
+    int64_t off_x2, off_fwd2;  // second forward lane (odd chunks run on a second stream)
     int64_t fwd_bytes, total;
+    bool two_lanes;
     int64_t nwin, chunk, pred_len;
 };
 
@@ -49,6 +51,8 @@ struct Layout {
 struct CopyPipe {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_ready = nullptr, ev_piece = nullptr;
+    cudaStream_t lane = nullptr;  // second forward lane
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int device = -1;
 };
 CopyPipe *copy_pipe() {
@@ -60,12 +64,26 @@ CopyPipe *copy_pipe() {
         if (cudaStreamCreateWithFlags(&cp.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
         if (cudaEventCreateWithFlags(&cp.ev_ready, cudaEventDisableTiming) != cudaSuccess) return nullptr;
         if (cudaEventCreateWithFlags(&cp.ev_piece, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaStreamCreateWithFlags(&cp.lane, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&cp.ev_fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&cp.ev_join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
         cp.device = dev;
     }
     return &cp;
 }
 
-int64_t default_chunk(const vp_model *) { return 4096; }  // measured: 1024 -> 4096 windows per launch group = -10 % forward time (EQTransformer)
+// measured: EQTransformer 1024 -> 4096 windows per launch group = -10 % forward time; PhaseNet host records: 2048 overlaps
+// the H2D pieces best (158 vs 152 station-days/s end to end), device-resident 4096 is 3 % faster
+int64_t default_chunk(const vp_model *m) { return vp_model_kind(m) == VP_KIND_PHASENET ? 2048 : 4096; }
+
+// Two forward lanes: consecutive chunks of a record are independent until the stacker, so odd chunks run on a second
+// stream with their own forward workspace.  The latency-bound kernels of one chunk (LSTM recurrences, attention, the
+// drain / fill of ~40 launches) then overlap the tensor-core kernels of the other.  VP_LANES=1 disables it; the
+// per-kernel timing pass (vp_kernel_timing) runs single-lane so that kernel durations are not inflated by co-runners.
+bool two_lanes_wanted(int64_t nwin, int64_t chunk) {
+    static const bool off = getenv("VP_LANES") && atoi(getenv("VP_LANES")) == 1;
+    return !off && !vp::g_ktimer_on && nwin > chunk;
+}
 
 int make_layout(const vp_model *m, int64_t n, const vp_annotate_params *p, int trace_on_host, int64_t pick_cap,
                 Layout *lo) {
@@ -88,6 +106,10 @@ int make_layout(const vp_model *m, int64_t n, const vp_annotate_params *p, int t
     lo->fwd_bytes = vp_forward_workspace_bytes(m, std::min(lo->chunk, std::max<int64_t>(lo->nwin, 1)), p->precision);
     if (lo->fwd_bytes < 0) return (int)lo->fwd_bytes;
     lo->off_fwd = take(lo->fwd_bytes);
+    lo->two_lanes = two_lanes_wanted(lo->nwin, lo->chunk);
+    // the second lane is always laid out (a workspace sized with the timing pass on must fit a later untimed call)
+    lo->off_x2 = take(lo->nwin > lo->chunk ? lo->chunk * 3 * L * 4 : 0);
+    lo->off_fwd2 = take(lo->nwin > lo->chunk ? lo->fwd_bytes : 0);
     lo->off_y = take(std::max<int64_t>(lo->nwin, 1) * 3 * L * 4);
     lo->off_annot = take(3 * std::max<int64_t>(lo->pred_len, 1) * 4);
     lo->off_bounds = take(6 * 8);
@@ -148,8 +170,12 @@ extern "C" int vp_annotate(vp_model *m, const void *trace, int trace_on_host, in
         d_trace = ws + lo.off_trace;
         d_stride = n;
     }
-    auto copy_upto = [&](int64_t end) -> int {  // make samples [0, end) available to stream s
-        if (!trace_on_host || end <= copied) return VP_OK;
+    auto copy_upto = [&](int64_t end, cudaStream_t waiter) -> int {  // make samples [0, end) available to `waiter`
+        if (!trace_on_host) return VP_OK;
+        if (end <= copied) {  // already issued (by the other lane's chunk): order this lane after the latest piece
+            if (copied > 0) VP_CUDA_CHECK(cudaStreamWaitEvent(waiter, pipe->ev_piece, 0));
+            return VP_OK;
+        }
         end = std::min(end, n);
         char *dst = ws + lo.off_trace;
         for (int c = 0; c < 3; ++c)
@@ -157,7 +183,7 @@ extern "C" int vp_annotate(vp_model *m, const void *trace, int trace_on_host, in
                                           (end - copied) * 4, cudaMemcpyHostToDevice, pipe->stream));
         copied = end;
         VP_CUDA_CHECK(cudaEventRecord(pipe->ev_piece, pipe->stream));
-        VP_CUDA_CHECK(cudaStreamWaitEvent(s, pipe->ev_piece, 0));
+        VP_CUDA_CHECK(cudaStreamWaitEvent(waiter, pipe->ev_piece, 0));
         return VP_OK;
     };
     int64_t *d_starts = (int64_t *)(ws + lo.off_starts);
@@ -169,17 +195,27 @@ extern "C" int vp_annotate(vp_model *m, const void *trace, int trace_on_host, in
         // pageable source: the runtime stages the copy before the call returns, h_starts may be reused freely
         VP_CUDA_CHECK(cudaMemcpyAsync(d_starts, h_starts.data(), (size_t)lo.nwin * 8, cudaMemcpyHostToDevice, s));
     }
-    float *d_x = (float *)(ws + lo.off_x);
     float *d_y = (float *)(ws + lo.off_y);
+    CopyPipe *lanes = lo.two_lanes ? copy_pipe() : nullptr;
+    VP_REQUIRE(!lo.two_lanes || lanes != nullptr, VP_ERR_CUDA, "vp_annotate: cannot create the second forward lane");
+    if (lanes) {  // fork: the second lane starts after the window starts are uploaded (and after earlier users of the workspace)
+        VP_CUDA_CHECK(cudaEventRecord(lanes->ev_fork, s));
+        VP_CUDA_CHECK(cudaStreamWaitEvent(lanes->lane, lanes->ev_fork, 0));
+    }
     const int taper = (kind == VP_KIND_EQTRANSFORMER) ? 1 : 0;
     static const bool fused_off = getenv("VP_FUSED_SLICE") && atoi(getenv("VP_FUSED_SLICE")) == 0;  // debugging aid
     const bool fused_slice = !fused_off && kind == VP_KIND_EQTRANSFORMER && (p->precision == VP_PREC_F16X3 || p->precision == VP_PREC_BF16);
-    for (int64_t w0 = 0; w0 < lo.nwin; w0 += lo.chunk) {
+    int64_t chunk_no = 0;
+    for (int64_t w0 = 0; w0 < lo.nwin; w0 += lo.chunk, ++chunk_no) {
         const int64_t nw = std::min(lo.chunk, lo.nwin - w0);
+        const bool odd = lanes && (chunk_no & 1);
+        cudaStream_t cs = odd ? lanes->lane : s;
+        float *d_x = (float *)(ws + (odd ? lo.off_x2 : lo.off_x));
+        char *fwd_ws = ws + (odd ? lo.off_fwd2 : lo.off_fwd);
         {   // the record samples this chunk's windows read (starts ascend; the tail window ends at n)
             int64_t need = 0;
             for (int64_t i = w0 + nw - 1; i >= w0 && i >= w0 + nw - 2; --i) need = std::max(need, h_starts[(size_t)i] + L);
-            rc = copy_upto(w0 + nw >= lo.nwin ? n : need);
+            rc = copy_upto(w0 + nw >= lo.nwin ? n : need, cs);
             if (rc != VP_OK) return rc;
         }
         // vp_stack discards the blinded margins of every window: the forward need not compute them
@@ -187,14 +223,18 @@ extern "C" int vp_annotate(vp_model *m, const void *trace, int trace_on_host, in
         const int64_t keep_hi = std::min(std::max<int64_t>(L - p->blinding[1], keep_lo), L);
         if (fused_slice) {  // K1 lives inside the first encoder kernel: the fp32 windows are never materialised
             rc = vp_slice_forward(m, d_trace, dtype, n, d_stride, d_starts + w0, nw, p->peak_scope, taper, d_y + w0 * 3 * L,
-                                  ws + lo.off_fwd, lo.fwd_bytes, p->precision, keep_lo, keep_hi, s);
+                                  fwd_ws, lo.fwd_bytes, p->precision, keep_lo, keep_hi, cs);
             if (rc != VP_OK) return rc;
             continue;
         }
-        rc = vp_slice_normalize(d_trace, dtype, n, d_stride, d_starts + w0, nw, L, p->peak_scope, taper, d_x, s);
+        rc = vp_slice_normalize(d_trace, dtype, n, d_stride, d_starts + w0, nw, L, p->peak_scope, taper, d_x, cs);
         if (rc != VP_OK) return rc;
-        rc = vp_forward_range(m, d_x, nw, d_y + w0 * 3 * L, ws + lo.off_fwd, lo.fwd_bytes, p->precision, keep_lo, keep_hi, s);
+        rc = vp_forward_range(m, d_x, nw, d_y + w0 * 3 * L, fwd_ws, lo.fwd_bytes, p->precision, keep_lo, keep_hi, cs);
         if (rc != VP_OK) return rc;
+    }
+    if (lanes) {  // join before the stacker reads every window
+        VP_CUDA_CHECK(cudaEventRecord(lanes->ev_join, lanes->lane));
+        VP_CUDA_CHECK(cudaStreamWaitEvent(s, lanes->ev_join, 0));
     }
     float *d_annot = (float *)(ws + lo.off_annot);
     rc = vp_stack(d_y, d_starts, lo.nwin, L, 3, p->overlap, p->blinding[0], p->blinding[1], p->stacking, d_annot,

@@ -578,41 +578,54 @@ struct PickLabels {
     int bound_slot[PK_MAXLAB];
 };
 
-// Continues a run over global memory from `base` (a multiple-of-nothing absolute index), 32 samples at a time.
+// Continues a run over global memory from `base`, PK_WALK * 32 samples per round trip (the loads of a round are
+// independent; a run that leaves its tile is latency bound: 32 samples per trip made a 2000-sample detection run the
+// critical path of the whole launch).
+constexpr int PK_WALK = 8;
 __device__ __forceinline__ void pick_walk_global(const float *__restrict__ x, int64_t n, int64_t base, float thr_on,
                                                  float thr_off, int lane, int64_t &on, int64_t &pk, float &best,
                                                  int64_t &end) {
-    for (;; base += 32) {
-        const int64_t idx = base + lane;
-        const float v = (idx < n) ? __ldg(x + idx) : CUDART_NAN_F;
-        const bool above = v > thr_off;  // NaN compares false
-        const unsigned not_above = __ballot_sync(0xffffffffu, !above);
-        const int nvalid = not_above ? (__ffs(not_above) - 1) : 32;
-        const bool in_run = lane < nvalid;
-        if (on < 0) {
-            const unsigned m_on = __ballot_sync(0xffffffffu, in_run && v > thr_on);
-            if (m_on) on = base + (__ffs(m_on) - 1);
-        }
-        if (on >= 0) {
-            float bv = (in_run && idx >= on) ? v : -CUDART_INF_F;
-            int64_t bi = idx;
+    for (;; base += 32 * PK_WALK) {
+        float vv[PK_WALK];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                const int64_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (ov > bv || (ov == bv && oi < bi)) {
-                    bv = ov;
-                    bi = oi;
+        for (int k = 0; k < PK_WALK; ++k) {
+            const int64_t idx = base + 32 * k + lane;
+            vv[k] = (idx < n) ? __ldg(x + idx) : CUDART_NAN_F;
+        }
+#pragma unroll
+        for (int k = 0; k < PK_WALK; ++k) {
+            const int64_t b0 = base + 32 * k;
+            const int64_t idx = b0 + lane;
+            const float v = vv[k];
+            const bool above = v > thr_off;  // NaN compares false
+            const unsigned not_above = __ballot_sync(0xffffffffu, !above);
+            const int nvalid = not_above ? (__ffs(not_above) - 1) : 32;
+            const bool in_run = lane < nvalid;
+            if (on < 0) {
+                const unsigned m_on = __ballot_sync(0xffffffffu, in_run && v > thr_on);
+                if (m_on) on = b0 + (__ffs(m_on) - 1);
+            }
+            if (on >= 0) {
+                float bv = (in_run && idx >= on) ? v : -CUDART_INF_F;
+                int64_t bi = idx;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                    const int64_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    if (ov > bv || (ov == bv && oi < bi)) {
+                        bv = ov;
+                        bi = oi;
+                    }
+                }
+                if (bv > best) {  // strict: the earliest chunk keeps ties -> first maximum
+                    best = bv;
+                    pk = bi;
                 }
             }
-            if (bv > best) {  // strict: the earliest chunk keeps ties -> first maximum
-                best = bv;
-                pk = bi;
+            if (nvalid < 32) {
+                end = b0 + nvalid - 1;
+                return;
             }
-        }
-        if (nvalid < 32) {
-            end = base + nvalid - 1;
-            return;
         }
     }
 }
@@ -621,7 +634,7 @@ __global__ void __launch_bounds__(PK_NT) pick_tile_kernel(const PickLabels P, in
                                                           int64_t pick_cap, unsigned long long *__restrict__ npicks,
                                                           int64_t *__restrict__ bounds) {
     __shared__ __align__(16) float sv[PK_TILE];
-    __shared__ uint32_t m_off[PK_WORDS], m_on[PK_WORDS];
+    __shared__ uint32_t m_off[PK_WORDS];
     __shared__ uint16_t run_start[PK_TILE / 2];
     __shared__ int n_runs, s_lo, s_hi, s_prev, s_prev_ok, s_next_ok;
     const int li = blockIdx.y;
@@ -639,6 +652,7 @@ __global__ void __launch_bounds__(PK_NT) pick_tile_kernel(const PickLabels P, in
         s_prev_ok = isnan(pv) ? 0 : 1;
     }
     if (tid == 32) s_next_ok = (t0 + PK_TILE < n && !isnan(__ldg(x + t0 + PK_TILE))) ? 1 : 0;
+    int n_ok = 0;  // non-NaN samples loaded by this thread
 #pragma unroll
     for (int it = 0; it < PK_TILE / (4 * PK_NT); ++it) {
         const int o = (it * PK_NT + tid) * 4;
@@ -652,29 +666,41 @@ __global__ void __launch_bounds__(PK_NT) pick_tile_kernel(const PickLabels P, in
             v.z = (g + 2 >= 0 && g + 2 < n) ? __ldg(x + g + 2) : CUDART_NAN_F;
             v.w = (g + 3 >= 0 && g + 3 < n) ? __ldg(x + g + 3) : CUDART_NAN_F;
         }
+        n_ok += (v.x == v.x) + (v.y == v.y) + (v.z == v.z) + (v.w == v.w);
         *reinterpret_cast<float4 *>(sv + o) = v;
     }
-    __syncthreads();
+    // tile-wide census: all samples valid (the common case), none, or mixed (only then the NaN positions are searched)
+    const int all_ok = __syncthreads_and(n_ok == PK_TILE / PK_NT);
+    const int none_ok = all_ok ? 0 : __syncthreads_and(n_ok == 0);
+    const bool want_pick = P.pick[li] != 0;
+    if (none_ok) return;  // NaN only: no run, no bound
     int lo = PK_TILE, hi = -1;
 #pragma unroll 4
     for (int j = 0; j < PK_WORDS / (PK_NT / 32); ++j) {
         const int word = warp * (PK_WORDS / (PK_NT / 32)) + j;
         const float v = sv[word * 32 + lane];
-        const unsigned b_off = __ballot_sync(0xffffffffu, v > thr_off);
-        const unsigned b_on = __ballot_sync(0xffffffffu, v > thr_on);
-        const unsigned b_ok = __ballot_sync(0xffffffffu, !isnan(v));
-        if (lane == 0) {
-            m_off[word] = b_off;
-            m_on[word] = b_on;
+        if (want_pick) {
+            const unsigned b_off = __ballot_sync(0xffffffffu, v > thr_off);  // NaN compares false
+            if (lane == 0) m_off[word] = b_off;
         }
-        if (b_ok) {
-            lo = min(lo, word * 32 + __ffs(b_ok) - 1);
-            hi = max(hi, word * 32 + 31 - __clz(b_ok));
+        if (!all_ok && bounds != nullptr) {
+            const unsigned b_ok = __ballot_sync(0xffffffffu, v == v);
+            if (b_ok) {
+                lo = min(lo, word * 32 + __ffs(b_ok) - 1);
+                hi = max(hi, word * 32 + 31 - __clz(b_ok));
+            }
         }
     }
-    if (bounds != nullptr && lane == 0 && hi >= 0) {
-        atomicMin(&s_lo, lo);
-        atomicMax(&s_hi, hi);
+    if (bounds != nullptr) {
+        if (all_ok) {
+            if (tid == 0) {
+                s_lo = 0;
+                s_hi = PK_TILE - 1;
+            }
+        } else if (lane == 0 && hi >= 0) {
+            atomicMin(&s_lo, lo);
+            atomicMax(&s_hi, hi);
+        }
     }
     __syncthreads();
     if (bounds != nullptr && tid == 0 && s_hi >= 0) {
@@ -685,7 +711,7 @@ __global__ void __launch_bounds__(PK_NT) pick_tile_kernel(const PickLabels P, in
         if (s_hi < PK_TILE - 1 || !s_next_ok)
             atomicMax(reinterpret_cast<long long *>(bounds + 2 * slot + 1), (long long)(t0 + s_hi));
     }
-    if (!P.pick[li]) return;
+    if (!want_pick) return;
     if (tid < PK_WORDS) {
         const uint32_t m = m_off[tid];
         const uint32_t carry = tid > 0 ? (m_off[tid - 1] >> 31) : (uint32_t)s_prev;
@@ -721,35 +747,23 @@ __global__ void __launch_bounds__(PK_NT) pick_tile_kernel(const PickLabels P, in
                 break;
             }
         }
-        // first sample above thr_on inside [s, end_in]
+        // first sample above thr_on and the first maximum from there on, one pass over [s, end_in] in shared memory
         int on_in = -1;
-        const int we = end_in >> 5;
-        for (int wb = w; wb <= we; wb += 32) {
-            const int wi = wb + lane;
-            uint32_t mo = 0;
-            if (wi <= we) {
-                mo = m_on[wi];
-                if (wi == w) mo &= from_s;
-                if (wi == we) mo &= (2u << (end_in & 31)) - 1u;
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, mo != 0);
-            if (bal) {
-                const int l = __ffs(bal) - 1;
-                const uint32_t mv = __shfl_sync(0xffffffffu, mo, l);
-                on_in = (wb + l) * 32 + __ffs(mv) - 1;
-                break;
-            }
-        }
         float bv = -CUDART_INF_F;
         int bi = 0x7fffffff;
-        if (on_in >= 0) {
-            for (int i = on_in + lane; i <= end_in; i += 32) {
-                const float v = sv[i];
-                if (v > bv) {
-                    bv = v;
-                    bi = i;
-                }
+        for (int base = s; base <= end_in; base += 32) {
+            const int i = base + lane;
+            const float v = (i <= end_in) ? sv[i] : -CUDART_INF_F;
+            if (on_in < 0) {
+                const unsigned m_on = __ballot_sync(0xffffffffu, v > thr_on);
+                if (m_on) on_in = base + __ffs(m_on) - 1;
             }
+            if (on_in >= 0 && i >= on_in && v > bv) {  // strict: the earliest index of a lane keeps ties
+                bv = v;
+                bi = i;
+            }
+        }
+        if (on_in >= 0) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
