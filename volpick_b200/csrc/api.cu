@@ -41,7 +41,9 @@ namespace {
 
 struct Layout {
     int64_t off_trace, off_starts, off_x, off_fwd, off_y, off_annot, off_bounds, off_count, off_picks, off_scratch;
-    int64_t off_x2, off_fwd2;  // second forward lane (odd chunks run on a second stream)
+    int64_t off_x2, off_fwd2;  // extra forward lanes (chunk c runs on lane c % n_lanes): MAX_LANES - 1 slots of x_bytes / fwd_bytes
+    int64_t x_bytes;
+    int n_lanes;
     int64_t fwd_bytes, total;
     bool two_lanes;
     int64_t nwin, chunk, pred_len;
@@ -51,8 +53,8 @@ struct Layout {
 struct CopyPipe {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_ready = nullptr, ev_piece = nullptr;
-    cudaStream_t lane = nullptr;  // second forward lane
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t lane[3] = {nullptr, nullptr, nullptr};  // extra forward lanes
+    cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
     int device = -1;
 };
 CopyPipe *copy_pipe() {
@@ -64,9 +66,11 @@ CopyPipe *copy_pipe() {
         if (cudaStreamCreateWithFlags(&cp.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
         if (cudaEventCreateWithFlags(&cp.ev_ready, cudaEventDisableTiming) != cudaSuccess) return nullptr;
         if (cudaEventCreateWithFlags(&cp.ev_piece, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        if (cudaStreamCreateWithFlags(&cp.lane, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
         if (cudaEventCreateWithFlags(&cp.ev_fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        if (cudaEventCreateWithFlags(&cp.ev_join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        for (int i = 0; i < 3; ++i) {
+            if (cudaStreamCreateWithFlags(&cp.lane[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+            if (cudaEventCreateWithFlags(&cp.ev_join[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        }
         cp.device = dev;
     }
     return &cp;
@@ -80,9 +84,12 @@ int64_t default_chunk(const vp_model *m) { return vp_model_kind(m) == VP_KIND_PH
 // stream with their own forward workspace.  The latency-bound kernels of one chunk (LSTM recurrences, attention, the
 // drain / fill of ~40 launches) then overlap the tensor-core kernels of the other.  VP_LANES=1 disables it; the
 // per-kernel timing pass (vp_kernel_timing) runs single-lane so that kernel durations are not inflated by co-runners.
-bool two_lanes_wanted(int64_t nwin, int64_t chunk) {
-    static const bool off = getenv("VP_LANES") && atoi(getenv("VP_LANES")) == 1;
-    return !off && !vp::g_ktimer_on && nwin > chunk;
+constexpr int MAX_LANES = 4;
+int lanes_wanted(int64_t nwin, int64_t chunk) {
+    static const int env = getenv("VP_LANES") ? atoi(getenv("VP_LANES")) : 2;
+    const int want = std::min(std::max(env, 1), MAX_LANES);
+    if (vp::g_ktimer_on || nwin <= chunk) return 1;
+    return (int)std::min<int64_t>(want, (nwin + chunk - 1) / chunk);
 }
 
 int make_layout(const vp_model *m, int64_t n, const vp_annotate_params *p, int trace_on_host, int64_t pick_cap,
@@ -105,11 +112,15 @@ int make_layout(const vp_model *m, int64_t n, const vp_annotate_params *p, int t
     lo->off_x = take(std::min(lo->chunk, std::max<int64_t>(lo->nwin, 1)) * 3 * L * 4);
     lo->fwd_bytes = vp_forward_workspace_bytes(m, std::min(lo->chunk, std::max<int64_t>(lo->nwin, 1)), p->precision);
     if (lo->fwd_bytes < 0) return (int)lo->fwd_bytes;
+    lo->fwd_bytes = align_up(lo->fwd_bytes, 256);
     lo->off_fwd = take(lo->fwd_bytes);
-    lo->two_lanes = two_lanes_wanted(lo->nwin, lo->chunk);
-    // the second lane is always laid out (a workspace sized with the timing pass on must fit a later untimed call)
-    lo->off_x2 = take(lo->nwin > lo->chunk ? lo->chunk * 3 * L * 4 : 0);
-    lo->off_fwd2 = take(lo->nwin > lo->chunk ? lo->fwd_bytes : 0);
+    lo->n_lanes = lanes_wanted(lo->nwin, lo->chunk);
+    // the extra lanes are laid out whenever chunking happens (a workspace sized with the timing pass on must fit a later untimed call)
+    static const int env_lanes = getenv("VP_LANES") ? std::min(std::max(atoi(getenv("VP_LANES")), 1), MAX_LANES) : 2;
+    const int extra = lo->nwin > lo->chunk ? env_lanes - 1 : 0;
+    lo->x_bytes = align_up(lo->chunk * 3 * L * 4, 256);
+    lo->off_x2 = take(extra * lo->x_bytes);
+    lo->off_fwd2 = take(extra * lo->fwd_bytes);
     lo->off_y = take(std::max<int64_t>(lo->nwin, 1) * 3 * L * 4);
     lo->off_annot = take(3 * std::max<int64_t>(lo->pred_len, 1) * 4);
     lo->off_bounds = take(6 * 8);
@@ -196,11 +207,11 @@ extern "C" int vp_annotate(vp_model *m, const void *trace, int trace_on_host, in
         VP_CUDA_CHECK(cudaMemcpyAsync(d_starts, h_starts.data(), (size_t)lo.nwin * 8, cudaMemcpyHostToDevice, s));
     }
     float *d_y = (float *)(ws + lo.off_y);
-    CopyPipe *lanes = lo.two_lanes ? copy_pipe() : nullptr;
-    VP_REQUIRE(!lo.two_lanes || lanes != nullptr, VP_ERR_CUDA, "vp_annotate: cannot create the second forward lane");
-    if (lanes) {  // fork: the second lane starts after the window starts are uploaded (and after earlier users of the workspace)
+    CopyPipe *lanes = lo.n_lanes > 1 ? copy_pipe() : nullptr;
+    VP_REQUIRE(lo.n_lanes == 1 || lanes != nullptr, VP_ERR_CUDA, "vp_annotate: cannot create the extra forward lanes");
+    if (lanes) {  // fork: the extra lanes start after the window starts are uploaded (and after earlier users of the workspace)
         VP_CUDA_CHECK(cudaEventRecord(lanes->ev_fork, s));
-        VP_CUDA_CHECK(cudaStreamWaitEvent(lanes->lane, lanes->ev_fork, 0));
+        for (int i = 1; i < lo.n_lanes; ++i) VP_CUDA_CHECK(cudaStreamWaitEvent(lanes->lane[i - 1], lanes->ev_fork, 0));
     }
     const int taper = (kind == VP_KIND_EQTRANSFORMER) ? 1 : 0;
     static const bool fused_off = getenv("VP_FUSED_SLICE") && atoi(getenv("VP_FUSED_SLICE")) == 0;  // debugging aid
@@ -208,10 +219,10 @@ extern "C" int vp_annotate(vp_model *m, const void *trace, int trace_on_host, in
     int64_t chunk_no = 0;
     for (int64_t w0 = 0; w0 < lo.nwin; w0 += lo.chunk, ++chunk_no) {
         const int64_t nw = std::min(lo.chunk, lo.nwin - w0);
-        const bool odd = lanes && (chunk_no & 1);
-        cudaStream_t cs = odd ? lanes->lane : s;
-        float *d_x = (float *)(ws + (odd ? lo.off_x2 : lo.off_x));
-        char *fwd_ws = ws + (odd ? lo.off_fwd2 : lo.off_fwd);
+        const int ln = lanes ? (int)(chunk_no % lo.n_lanes) : 0;
+        cudaStream_t cs = ln ? lanes->lane[ln - 1] : s;
+        float *d_x = (float *)(ws + (ln ? lo.off_x2 + (ln - 1) * lo.x_bytes : lo.off_x));
+        char *fwd_ws = ws + (ln ? lo.off_fwd2 + (ln - 1) * lo.fwd_bytes : lo.off_fwd);
         {   // the record samples this chunk's windows read (starts ascend; the tail window ends at n)
             int64_t need = 0;
             for (int64_t i = w0 + nw - 1; i >= w0 && i >= w0 + nw - 2; --i) need = std::max(need, h_starts[(size_t)i] + L);
@@ -232,9 +243,9 @@ extern "C" int vp_annotate(vp_model *m, const void *trace, int trace_on_host, in
         rc = vp_forward_range(m, d_x, nw, d_y + w0 * 3 * L, fwd_ws, lo.fwd_bytes, p->precision, keep_lo, keep_hi, cs);
         if (rc != VP_OK) return rc;
     }
-    if (lanes) {  // join before the stacker reads every window
-        VP_CUDA_CHECK(cudaEventRecord(lanes->ev_join, lanes->lane));
-        VP_CUDA_CHECK(cudaStreamWaitEvent(s, lanes->ev_join, 0));
+    for (int i = 1; lanes && i < lo.n_lanes; ++i) {  // join before the stacker reads every window
+        VP_CUDA_CHECK(cudaEventRecord(lanes->ev_join[i - 1], lanes->lane[i - 1]));
+        VP_CUDA_CHECK(cudaStreamWaitEvent(s, lanes->ev_join[i - 1], 0));
     }
     float *d_annot = (float *)(ws + lo.off_annot);
     rc = vp_stack(d_y, d_starts, lo.nwin, L, 3, p->overlap, p->blinding[0], p->blinding[1], p->stacking, d_annot,
