@@ -388,9 +388,9 @@ def stage_timings(model, lib, rec_dev, argdict, thresholds, kind, reps: int = 3,
     def ev():
         return torch.cuda.Event(enable_timing=True)
 
-    # EQTransformer tensor-core modes: vp_annotate runs K1 inside the first encoder kernel (vp_slice_forward); the
+    # tensor-core modes: vp_annotate runs K1 inside the first conv kernel (vp_slice_forward); the
     # stand-alone K1 is still timed (it is the stage-level API and the PhaseNet / fp32 path) but is not part of "forward"
-    fused = kind == "eqtransformer" and precision != _lib.PRECISION["fp32"]
+    fused = precision != _lib.PRECISION["fp32"]
     keep_lo, keep_hi = argdict["blinding"][0], L - argdict["blinding"][1]
     acc = {"slice": 0.0, "forward": 0.0, "stack": 0.0, "pick": 0.0}
     for rep in range(reps + 1):
@@ -405,7 +405,7 @@ def stage_timings(model, lib, rec_dev, argdict, thresholds, kind, reps: int = 3,
             b.record()
             if fused:
                 _lib.check(lib.vp_slice_forward(model._handle, rec_dev.data_ptr(), 0, n, rec_dev.stride(0), d_starts.data_ptr() + 8 * w0, nw,
-                                                0, 1, d_y.data_ptr() + 4 * 3 * L * w0, ws.data_ptr(), ws_bytes, precision, keep_lo, keep_hi, stream))
+                                                0, 1 if kind == "eqtransformer" else 0, d_y.data_ptr() + 4 * 3 * L * w0, ws.data_ptr(), ws_bytes, precision, keep_lo, keep_hi, stream))
             else:
                 _lib.check(lib.vp_forward_range(model._handle, d_x.data_ptr(), nw, d_y.data_ptr() + 4 * 3 * L * w0, ws.data_ptr(), ws_bytes,
                                                 precision, keep_lo, keep_hi, stream))

@@ -120,9 +120,10 @@ VP_API int vp_forward(vp_model *m, const float *x, int64_t n_windows, float *y, 
  * written; work that only feeds the discarded samples may be skipped. */
 VP_API int vp_forward_range(vp_model *m, const float *x, int64_t n_windows, float *y, void *workspace,
                             int64_t workspace_bytes, int precision, int64_t keep_lo, int64_t keep_hi, void *stream);
-/* vp_slice_normalize + vp_forward_range in one call, for the EQTransformer tensor-core modes: the windows are cut
+/* vp_slice_normalize + vp_forward_range in one call, for the tensor-core modes of both models: the windows are cut
  * and normalised from the record (device pointer, (3, n_samples) with channel stride ch_stride) inside the kernel
- * that also runs encoder.convs.0, so the fp32 windows never reach HBM.  Same results as the two-call sequence
+ * that also runs the first conv (EQTransformer encoder.convs.0 + pool, PhaseNet inc + in_bn), so the fp32 windows
+ * never reach HBM.  Same results as the two-call sequence
  * within the mode's tolerance (the first conv runs in fp32 instead of f16x3 / bf16). */
 VP_API int vp_slice_forward(vp_model *m, const void *trace, int dtype, int64_t n_samples, int64_t ch_stride,
                             const int64_t *starts, int64_t n_windows, int peak_scope, int taper, float *y, void *workspace,

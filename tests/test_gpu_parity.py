@@ -272,6 +272,38 @@ def test_annotate_tensor_core_exact_mode(eqt, sd_eqt):
 
 
 @pytest.mark.parametrize("kind", ["eqtransformer", "phasenet"])
+@pytest.mark.parametrize("dtype", ["f32", "i32"])
+def test_slice_forward_matches_two_call_sequence(lib, eqt, pn, sd_eqt, sd_pn, kind, dtype):
+    """vp_slice_forward (K1 inside the first conv kernel, fp32 first layer) against vp_slice_normalize + vp_forward and
+    against the oracle on the same record."""
+    model, sd = (eqt, sd_eqt) if kind == "eqtransformer" else (pn, sd_pn)
+    L = model.in_samples
+    x = synthetic_record(44, 40_000)
+    if dtype == "i32":
+        x = np.round(x).astype(np.int32)
+    starts = pipeline.window_starts(x.shape[1], L, L - 700)
+    nw = len(starts)
+    d_tr = torch.from_numpy(x).cuda()
+    d_st = torch.from_numpy(starts).cuda()
+    prec = _lib.PRECISION["f16x3"]
+    need = _lib.check(lib.vp_forward_workspace_bytes(model._handle, nw, prec))
+    ws = torch.empty(need, dtype=torch.uint8, device="cuda")
+    y1 = torch.empty((nw, 3, L), dtype=torch.float32, device="cuda")
+    y2 = torch.empty_like(y1)
+    taper = 1 if kind == "eqtransformer" else 0
+    dt = 0 if dtype == "f32" else 1
+    _lib.check(lib.vp_slice_forward(model._handle, d_tr.data_ptr(), dt, x.shape[1], x.shape[1], d_st.data_ptr(), nw, 0, taper,
+                                    y1.data_ptr(), ws.data_ptr(), need, prec, 0, L, _stream()))
+    xw = torch.empty((nw, 3, L), dtype=torch.float32, device="cuda")
+    _lib.check(lib.vp_slice_normalize(d_tr.data_ptr(), dt, x.shape[1], x.shape[1], d_st.data_ptr(), nw, L, 0, taper, xw.data_ptr(), _stream()))
+    _lib.check(lib.vp_forward(model._handle, xw.data_ptr(), nw, y2.data_ptr(), ws.data_ptr(), need, prec, _stream()))
+    torch.cuda.synchronize()
+    assert float((y1 - y2).abs().max()) <= 2e-5
+    ref = pipeline.forward_batches(kind, sd, xw.cpu().numpy(), 64).transpose(0, 2, 1)
+    assert float(np.abs(y1.cpu().numpy() - ref).max()) <= PROB_ATOL
+
+
+@pytest.mark.parametrize("kind", ["eqtransformer", "phasenet"])
 @pytest.mark.parametrize("on_host", [True, False])
 def test_annotate_chunked_two_lanes_bit_identical(eqt, pn, kind, on_host):
     """Chunks of a record alternate between two streams (own forward workspace each, piecewise H2D of host records):

@@ -215,7 +215,7 @@ extern "C" int vp_annotate(vp_model *m, const void *trace, int trace_on_host, in
     }
     const int taper = (kind == VP_KIND_EQTRANSFORMER) ? 1 : 0;
     static const bool fused_off = getenv("VP_FUSED_SLICE") && atoi(getenv("VP_FUSED_SLICE")) == 0;  // debugging aid
-    const bool fused_slice = !fused_off && kind == VP_KIND_EQTRANSFORMER && (p->precision == VP_PREC_F16X3 || p->precision == VP_PREC_BF16);
+    const bool fused_slice = !fused_off && (p->precision == VP_PREC_F16X3 || p->precision == VP_PREC_BF16);
     int64_t chunk_no = 0;
     for (int64_t w0 = 0; w0 < lo.nwin; w0 += lo.chunk, ++chunk_no) {
         const int64_t nw = std::min(lo.chunk, lo.nwin - w0);

@@ -261,6 +261,7 @@ struct vp_model {
         bool ready = false;
     } pn_tc[2];
     float pn_head_w[24] = {0}, pn_head_b[3] = {0};  // `out` conv (3, 8, 1) + bias, fused into the last layer's epilogue
+    float pn_inc_w[8 * 3 * 7] = {0}, pn_inc_b[8] = {0};  // `inc` conv + in_bn folded, for the fused slicer kernel
 };
 
 template <class Set>
@@ -597,6 +598,11 @@ static int build_pn(vp_model *m, Cursor &cur, Packed &pk) {
     m->outc = pack_conv(pk, W, b, nullptr, 3, 8, 1);
     std::memcpy(m->pn_head_w, W, sizeof(m->pn_head_w));
     std::memcpy(m->pn_head_b, b, sizeof(m->pn_head_b));
+    {
+        const FoldedConv f = fold_conv(incW, incB, incBN, 8, 3, 7, 3);
+        std::memcpy(m->pn_inc_w, f.w.data(), sizeof(m->pn_inc_w));
+        std::memcpy(m->pn_inc_b, f.b.data(), sizeof(m->pn_inc_b));
+    }
     if (cur.left == 0) {
         int rc = build_pn_tc(m, incW, incB, incBN, dsW, dsBN, ddW, ddBN, utW, utBN, usW, usBN);
         if (rc != VP_OK) return rc;
@@ -1160,8 +1166,14 @@ static int run_pn_tc(Runner &r, const float *x, float *y, Arena &ar) {
         if (tapped) r.tap(name, tapbuf, B * c_total * T_store);
         return r.stopped || r.rc != VP_OK;
     };
-    if (r.go()) r.rc = launch_pack_cl16(x, 3 * (int64_t)L0, L0, (int)B, 3, L0, split, X16, B * (int64_t)L0 * 8, 1, r.s);
-    if (run_layer("inc", ts.inc, base_io(ts.inc, X16, L0, 8, L0), B0, L0, 0, 8, L0)) return r.rc;
+    if (r.trace) {  // K1 + inc + in_bn + ReLU on the CUDA cores, straight from the record (the fp32 windows never exist)
+        if (r.go())
+            r.rc = launch_slice_enc0(r.trace, r.trace_dtype, r.ch_stride, r.starts, B, L0, r.peak_scope, r.taper, m->pn_inc_w,
+                                     m->pn_inc_b, split, B0, B * (int64_t)L0 * 8, r.s, 7);
+    } else {
+        if (r.go()) r.rc = launch_pack_cl16(x, 3 * (int64_t)L0, L0, (int)B, 3, L0, split, X16, B * (int64_t)L0 * 8, 1, r.s);
+        if (run_layer("inc", ts.inc, base_io(ts.inc, X16, L0, 8, L0), B0, L0, 0, 8, L0)) return r.rc;
+    }
     static const char *ds_names[5] = {"down0_same", "down1_same", "down2_same", "down3_same", "down4_same"};
     static const char *dd_names[4] = {"down0_down", "down1_down", "down2_down", "down3_down"};
     static const char *us_names[4] = {"up0_same", "up1_same", "up2_same", "up3_same"};
@@ -1527,8 +1539,8 @@ extern "C" int vp_slice_forward(vp_model *m, const void *trace, int dtype, int64
                                 const int64_t *starts, int64_t n_windows, int peak_scope, int taper, float *y, void *workspace,
                                 int64_t workspace_bytes, int precision, int64_t keep_lo, int64_t keep_hi, void *stream) {
     VP_REQUIRE(m && trace && starts && y && workspace, VP_ERR_ARG, "vp_slice_forward: null pointer");
-    VP_REQUIRE(m->kind == VP_KIND_EQTRANSFORMER && (precision == VP_PREC_F16X3 || precision == VP_PREC_BF16), VP_ERR_UNSUPPORTED,
-               "vp_slice_forward: implemented for the EQTransformer tensor-core modes (use vp_slice_normalize + vp_forward otherwise)");
+    VP_REQUIRE(precision == VP_PREC_F16X3 || precision == VP_PREC_BF16, VP_ERR_UNSUPPORTED,
+               "vp_slice_forward: implemented for the tensor-core modes (use vp_slice_normalize + vp_forward otherwise)");
     VP_REQUIRE(dtype == VP_DTYPE_F32 || dtype == VP_DTYPE_I32, VP_ERR_ARG, "vp_slice_forward: unknown dtype %d", dtype);
     VP_REQUIRE(keep_lo >= 0 && keep_lo <= keep_hi, VP_ERR_ARG, "vp_slice_forward: bad sample range [%lld, %lld)", (long long)keep_lo,
                (long long)keep_hi);

@@ -154,7 +154,9 @@ struct Enc0W {
 };
 constexpr int E0_NT = 512, E0_PT = 12, E0_HALO = 5;
 
-template <typename Tin, int SPLIT>
+// POOL = true: EQTransformer (k = 11, ReLU, MaxPool1d(2)); POOL = false: PhaseNet `inc` (k = 7, folded BatchNorm, ReLU),
+// one thread per output sample.
+template <typename Tin, int SPLIT, bool POOL>
 __global__ void __launch_bounds__(E0_NT, 2) slice_enc0_kernel(const Tin *__restrict__ trace, int64_t ch_stride,
                                                               const int64_t *__restrict__ starts, int L, int peak_scope,
                                                               int taper, Taper tap, const __grid_constant__ Enc0W wt,
@@ -226,6 +228,31 @@ __global__ void __launch_bounds__(E0_NT, 2) slice_enc0_kernel(const Tin *__restr
     }
     __syncthreads();
 
+    if constexpr (!POOL) {
+        // PhaseNet: conv (3 -> 8, k = 7, 'same') + ReLU, weights as [co][ci][7]
+        for (int p = tid; p < L; p += E0_NT) {
+            float a0[8];
+#pragma unroll
+            for (int co = 0; co < 8; ++co) a0[co] = wt.b[co];
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int q = 0; q < 7; ++q) {
+                    const float x = xs[c * XP + p + E0_HALO - 3 + q];
+#pragma unroll
+                    for (int co = 0; co < 8; ++co) a0[co] = fmaf(x, wt.w[(co * 3 + c) * 7 + q], a0[co]);
+                }
+            float v[8];
+#pragma unroll
+            for (int co = 0; co < 8; ++co) v[co] = fmaxf(a0[co], 0.f);
+            uint4 hi, lo;
+            pack8_split16<SPLIT>(v, hi, lo);
+            uint16_t *yb = out + (w * L + p) * 8;
+            *reinterpret_cast<uint4 *>(yb) = hi;
+            if (SPLIT == 2) *reinterpret_cast<uint4 *>(yb + out_split) = lo;
+        }
+        return;
+    }
     // conv + ReLU + pool: one thread = one pooled output sample p (conv outputs 2p, 2p + 1), all 8 channels
     const int LP = L >> 1;
     for (int p = tid; p < LP; p += E0_NT) {
@@ -264,9 +291,10 @@ __global__ void __launch_bounds__(E0_NT, 2) slice_enc0_kernel(const Tin *__restr
 }
 
 int launch_slice_enc0(const void *trace, int dtype, int64_t ch_stride, const int64_t *starts, int64_t nw, int L, int scope,
-                      int taper, const float *w_host /*(8,3,11)*/, const float *b_host /*(8)*/, int split, uint16_t *out,
-                      int64_t out_split, cudaStream_t s) {
-    VP_REQUIRE(L % 2 == 0 && L <= E0_PT * E0_NT, VP_ERR_UNSUPPORTED, "fused slicer + encoder.convs.0: window length %d unsupported", L);
+                      int taper, const float *w_host /*(8,3,k)*/, const float *b_host /*(8)*/, int split, uint16_t *out,
+                      int64_t out_split, cudaStream_t s, int k) {
+    VP_REQUIRE((k == 11 && L % 2 == 0 || k == 7) && L <= E0_PT * E0_NT, VP_ERR_UNSUPPORTED,
+               "fused slicer + first conv: window length %d / kernel size %d unsupported", L, k);
     if (nw == 0) return VP_OK;
     Taper tap;
     for (int i = 0; i < 6; ++i) {
@@ -274,16 +302,17 @@ int launch_slice_enc0(const void *trace, int dtype, int64_t ch_stride, const int
         tap.t[i] = (float)(0.5 * (1.0 + std::cos(a)));
     }
     Enc0W wt;
-    std::memcpy(wt.w, w_host, sizeof(wt.w));
+    std::memset(&wt, 0, sizeof(wt));
+    std::memcpy(wt.w, w_host, sizeof(float) * 8 * 3 * k);
     std::memcpy(wt.b, b_host, sizeof(wt.b));
     const size_t smem = (size_t)3 * (L + 12) * sizeof(float);
 #define VP_E0_LAUNCH(T, S)                                                                                                  \
     do {                                                                                                                    \
-        auto kern = slice_enc0_kernel<T, S>;                                                                                \
-        static bool attr = false;                                                                                           \
-        if (!attr) {                                                                                                        \
+        auto kern = k == 11 ? slice_enc0_kernel<T, S, true> : slice_enc0_kernel<T, S, false>;                               \
+        static bool attr[2] = {false, false};                                                                               \
+        if (!attr[k == 11]) {                                                                                               \
             VP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (E0_PT * E0_NT + 12) * 4)); \
-            attr = true;                                                                                                    \
+            attr[k == 11] = true;                                                                                           \
         }                                                                                                                   \
         kern<<<(unsigned)nw, E0_NT, smem, s>>>((const T *)trace, ch_stride, starts, L, scope, taper, tap, wt, out, out_split); \
     } while (0)
