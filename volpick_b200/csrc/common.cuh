@@ -109,7 +109,7 @@ int launch_convt_fp32(int cin, int cout, const ConvTP &p, int B, cudaStream_t s)
 // K1 fused with encoder.convs.0 (+ ReLU + MaxPool1d(2)) for the tensor-core path (prepost.cu)
 int launch_slice_enc0(const void *trace, int dtype, int64_t ch_stride, const int64_t *starts, int64_t nw, int L, int scope,
                       int taper, const float *w_host, const float *b_host, int split, uint16_t *out, int64_t out_split,
-                      cudaStream_t s, int k = 11);
+                      cudaStream_t s, int k = 11, int out_pitch = 0);
 
 struct LstmP {
     const float *x;  // (B, CIN, T), group stride x_gs

@@ -256,6 +256,7 @@ struct vp_model {
     // convs on the row-reshaped channel-last buffers ([T][C] seen as [T / 4][4 C]); see build_pn_tc.
     struct PnTcSet {
         TcLayer inc, ds[5], dd[4], ut[4], us[4];
+        TcLayer ds0f, us3f;  // level-0 'same' convs with 4 time steps folded into the MMA K / N (see fold_same_conv)
         uint16_t *d_w = nullptr;
         float *d_b = nullptr;
         bool ready = false;
@@ -285,7 +286,7 @@ static int upload_tc_layers(Set &ts, const std::vector<TcLayer *> &layers) {
     return VP_OK;
 }
 static int upload_pn_tc(vp_model::PnTcSet &ts) {
-    std::vector<TcLayer *> layers{&ts.inc};
+    std::vector<TcLayer *> layers{&ts.inc, &ts.ds0f, &ts.us3f};
     for (int i = 0; i < 5; ++i) layers.push_back(&ts.ds[i]);
     for (int i = 0; i < 4; ++i) {
         layers.push_back(&ts.dd[i]);
@@ -494,6 +495,53 @@ static FoldedConv fold_conv(const float *W, const float *bias, const BN &bn, int
     return f;
 }
 
+// 'same' Conv1d (k = 7, pad 3) with F time steps folded into the channels.  Small-channel layers are bound by the
+// shared-memory reads of the A operand (4 KB per tcgen05.mma whatever its N: ncu shows the tc pipe 91 % busy with the
+// tensor math at 18 % for N = 16), so fewer, wider MMAs win: on the [T / F][F C] view of the channel-last buffers
+// (the same bytes) the conv needs ceil-wise 3 row taps instead of 7 and yields F * C_out columns.
+// Source s holds sample t at position t + o_in[s] of its buffer (row (t + o_in) / F, lane (t + o_in) % F), the output
+// sample t goes to position t + o_out.  Returns the (F * cout, sum_s F * c_s, 3) weights (+ replicated bias) of the
+// row conv and its left padding in rows; the offsets must give every source the same first row tap.
+constexpr int PN_FOLD = 4;
+static int fold_same_conv(const FoldedConv &f, int cout, const int *c_src, const int *o_in, int n_src, int o_out, FoldedConv &out,
+                          int &pad_rows) {
+    const int F = PN_FOLD, K = 7, P = 3;
+    int cin = 0;
+    for (int s = 0; s < n_src; ++s) cin += c_src[s];
+    auto fdiv = [](int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); };
+    int d_min = 0, d_max = 0;
+    for (int s = 0; s < n_src; ++s) {
+        const int a = o_in[s] - P - o_out;  // buffer position (relative to F * row) of the first sample read by lane 0
+        const int lo = fdiv(a, F), hi = fdiv(a + (F - 1) + (K - 1), F);
+        if (s == 0) d_min = lo, d_max = hi;
+        VP_REQUIRE(lo == d_min && hi - lo <= 2, VP_ERR_UNSUPPORTED, "fold_same_conv: source %d needs row taps [%d, %d] (first source: from %d)", s, lo, hi, d_min);
+        d_max = std::max(d_max, hi);
+    }
+    const int ntap = 3;
+    VP_REQUIRE(d_max - d_min + 1 <= ntap, VP_ERR_UNSUPPORTED, "fold_same_conv: %d row taps", d_max - d_min + 1);
+    pad_rows = -d_min;
+    const int cinF = F * cin, coutF = F * cout;
+    out.w.assign((size_t)coutF * cinF * ntap, 0.f);
+    out.b.assign(coutF, 0.f);
+    for (int q = 0; q < F; ++q)
+        for (int co = 0; co < cout; ++co) {
+            out.b[(size_t)q * cout + co] = f.b[co];
+            int ch0 = 0, col0 = 0;  // first channel of the source in the original / folded channel order
+            for (int s = 0; s < n_src; ++s) {
+                for (int j = 0; j < K; ++j) {
+                    const int pos = q + j - P + o_in[s] - o_out;  // source buffer position relative to F * row
+                    const int d = fdiv(pos, F), lane = pos - d * F;
+                    for (int ci = 0; ci < c_src[s]; ++ci)
+                        out.w[(((size_t)q * cout + co) * cinF + col0 + lane * c_src[s] + ci) * ntap + (d - d_min)] =
+                            f.w[((size_t)co * cin + ch0 + ci) * K + j];
+                }
+                ch0 += c_src[s];
+                col0 += F * c_src[s];
+            }
+        }
+    return VP_OK;
+}
+
 // PhaseNet layers as tensor-core convs.  With channel-last rows a buffer [T][C] is also [T / 4][4 C], so
 //   * the stride-4 Conv1d (k = 7, SeisBench's manual left pad pl): out[s] = sum_j w[j] xp[4 s + j] over the padded signal
 //     xp becomes a k = 2 'valid' conv over rows of 4 C channels (tap 0: w[0..3], tap 1: w[4..6] and a zero), and
@@ -523,6 +571,14 @@ static int build_pn_tc(vp_model *m, const float *incW, const float *incB, const 
             const int f = kPnC[i];
             rc = build(ts.ds[i], fold_conv(dsW[i], nullptr, dsBN[i], f, last, 7, last), last, f, 7, f == 128 ? 2 : 1, 3);
             if (rc != VP_OK) return rc;
+            if (i == 0) {  // folded form: B0 (offset 0) -> skip_0 stored at offset 3 (the stride-4 conv's left pad)
+                FoldedConv v;
+                int pad_rows = 0;
+                const int cs[1] = {8}, oi[1] = {0};
+                rc = fold_same_conv(fold_conv(dsW[0], nullptr, dsBN[0], 8, 8, 7, 8), 8, cs, oi, 1, 3, v, pad_rows);
+                if (rc == VP_OK) rc = build(ts.ds0f, v, PN_FOLD * 8, PN_FOLD * 8, 3, 1, pad_rows);
+                if (rc != VP_OK) return rc;
+            }
             last = f;
             if (i == 4) break;
             // stride-4 conv on the [T / 4][4 f] view: W2[co][q f + ci][tap] = w[co][ci][4 tap + q]
@@ -560,6 +616,14 @@ static int build_pn_tc(vp_model *m, const float *incW, const float *incB, const 
             last = f;
             rc = build(ts.us[i], fold_conv(usW[i], nullptr, usBN[i], f, 2 * f, 7, 2 * f), 2 * f, f, 7, f == 64 ? 4 : 1, 3);
             if (rc != VP_OK) return rc;
+            if (i == 3) {  // folded form: [skip_0 at offset 3 | up at offset 1 + off = 2] -> head, output offset 3 (3 row taps each)
+                FoldedConv v;
+                int pad_rows = 0;
+                const int cs[2] = {8, 8}, oi[2] = {3, 2};
+                rc = fold_same_conv(fold_conv(usW[3], nullptr, usBN[3], 8, 16, 7, 16), 8, cs, oi, 2, 3, v, pad_rows);
+                if (rc == VP_OK) rc = build(ts.us3f, v, PN_FOLD * 16, PN_FOLD * 8, 3, 1, pad_rows);
+                if (rc != VP_OK) return rc;
+            }
         }
     }
     return VP_OK;
@@ -1103,7 +1167,10 @@ static int run_pn_tc(Runner &r, const float *x, float *y, Arena &ar) {
         }
     }
     auto take16 = [&](int64_t rows, int c) { return reinterpret_cast<uint16_t *>(ar.take((B * rows * c * split + 1) / 2)); };
-    uint16_t *X16 = take16(L0, 8), *B0 = take16(L0, 8);
+    static const bool fold_off = getenv("VP_PN_FOLD") && atoi(getenv("VP_PN_FOLD")) == 0;  // debugging aid
+    const bool fold = !fold_off;
+    const int pitchB0 = fold ? (L0 + PN_FOLD - 1) / PN_FOLD * PN_FOLD : L0;  // folded reads need whole rows of 4 samples
+    uint16_t *X16 = take16(L0, 8), *B0 = take16(pitchB0, 8);
     uint16_t *A[4], *Bd[5], *U[4], *Bu[4];
     for (int i = 0; i < 4; ++i) {
         A[i] = take16(pitchA[i], kPnC[i]);
@@ -1147,13 +1214,15 @@ static int run_pn_tc(Runner &r, const float *x, float *y, Arena &ar) {
                          int T_store) -> bool {
         const bool tapped = r.stop_name && !r.stopped && name && std::strcmp(r.stop_name, name) == 0;
         if (tapped) {
+            const int c_tap = io.fold > 1 ? io.fold_c : c_total;  // folded layers: channels of one sample
             io.out_fmt = 1;
             io.y = tapbuf;
             io.y_split = 0;
             io.y_gs = (int64_t)tl.cout * T_store;  // group g holds channels [g * cout, (g + 1) * cout)
-            io.y_ss = (int64_t)c_total * T_store;
+            io.y_ss = (int64_t)c_tap * T_store;
             io.y_cs = T_store;
             io.cout_cl = 0;
+            c_total = c_tap;
         } else {
             io.y = dst;
             io.y_split = B * (int64_t)rows_out * c_total;
@@ -1169,10 +1238,17 @@ static int run_pn_tc(Runner &r, const float *x, float *y, Arena &ar) {
     if (r.trace) {  // K1 + inc + in_bn + ReLU on the CUDA cores, straight from the record (the fp32 windows never exist)
         if (r.go())
             r.rc = launch_slice_enc0(r.trace, r.trace_dtype, r.ch_stride, r.starts, B, L0, r.peak_scope, r.taper, m->pn_inc_w,
-                                     m->pn_inc_b, split, B0, B * (int64_t)L0 * 8, r.s, 7);
+                                     m->pn_inc_b, split, B0, B * (int64_t)pitchB0 * 8, r.s, 7, pitchB0);
     } else {
         if (r.go()) r.rc = launch_pack_cl16(x, 3 * (int64_t)L0, L0, (int)B, 3, L0, split, X16, B * (int64_t)L0 * 8, 1, r.s);
-        if (run_layer("inc", ts.inc, base_io(ts.inc, X16, L0, 8, L0), B0, L0, 0, 8, L0)) return r.rc;
+        if (r.go() && pitchB0 > L0) {  // rows past the window inside B0's pitch are conv zero padding for the folded reader
+            const cudaError_t e = cudaMemset2DAsync(B0 + (size_t)L0 * 8, (size_t)pitchB0 * 16, 0, (size_t)(pitchB0 - L0) * 16, (size_t)B * split, r.s);
+            if (e != cudaSuccess) {
+                set_error("PhaseNet: clearing the B0 tail failed: %s", cudaGetErrorString(e));
+                return VP_ERR_CUDA;
+            }
+        }
+        if (run_layer("inc", ts.inc, base_io(ts.inc, X16, L0, 8, L0), B0, pitchB0, 0, 8, L0)) return r.rc;
     }
     static const char *ds_names[5] = {"down0_same", "down1_same", "down2_same", "down3_same", "down4_same"};
     static const char *dd_names[4] = {"down0_down", "down1_down", "down2_down", "down3_down"};
@@ -1181,7 +1257,16 @@ static int run_pn_tc(Runner &r, const float *x, float *y, Arena &ar) {
     int cur_c = 8;
     for (int i = 0; i < 4; ++i) {
         const int f = kPnC[i];
-        if (r.go()) {  // zero rows around skip_i inside its padded pitch (read by the stride-4 conv as conv padding)
+        if (i == 0 && fold) {
+            // level 0, folded: every row of A0 is written (samples outside the sequence as zeros), no clearing needed
+            TcIO io = base_io(ts.ds0f, cur, pitchB0 / PN_FOLD, PN_FOLD * 8, pitchB0 / PN_FOLD);
+            io.T_valid = pitchA[0] / PN_FOLD;
+            io.fold = PN_FOLD;
+            io.fold_c = 8;
+            io.fold_o = padl[0];
+            io.fold_T = len[0];
+            if (run_layer(ds_names[0], ts.ds0f, io, A[0], pitchA[0] / PN_FOLD, 0, PN_FOLD * 8, len[0])) return r.rc;
+        } else if (r.go()) {  // zero rows around skip_i inside its padded pitch (read by the stride-4 conv as conv padding)
             const size_t pitch_b = (size_t)pitchA[i] * f * 2, head_b = (size_t)padl[i] * f * 2;
             const size_t tail_b = (size_t)(pitchA[i] - padl[i] - len[i]) * f * 2;
             cudaError_t e = cudaMemset2DAsync(A[i], pitch_b, 0, head_b, (size_t)B * split, r.s);
@@ -1192,7 +1277,10 @@ static int run_pn_tc(Runner &r, const float *x, float *y, Arena &ar) {
                 return VP_ERR_CUDA;
             }
         }
-        if (run_layer(ds_names[i], ts.ds[i], base_io(ts.ds[i], cur, len[i], cur_c, len[i]), A[i], pitchA[i], padl[i], f, len[i])) return r.rc;
+        if (!(i == 0 && fold)) {
+            TcIO io = base_io(ts.ds[i], cur, i == 0 ? pitchB0 : len[i], cur_c, len[i]);
+            if (run_layer(ds_names[i], ts.ds[i], io, A[i], pitchA[i], padl[i], f, len[i])) return r.rc;
+        }
         {   // stride-4 conv: A_i seen as [pitch / 4][4 f], k = 2, 'valid': len[i + 1] output rows
             TcIO io = base_io(ts.dd[i], A[i], pitchA[i] / 4, 4 * f, pitchA[i] / 4);
             io.T_valid = len[i + 1];
@@ -1218,16 +1306,38 @@ static int run_pn_tc(Runner &r, const float *x, float *y, Arena &ar) {
         {   // ConvTranspose1d as a k = 2 conv with 4 f columns: rows 0..cur_len of the [cur_len + 1][4 f] view of U
             TcIO io = base_io(ts.ut[i], cur, cur_len, cur_c, cur_len);
             io.T_valid = cur_len + 1;
+            if (i == 3 && fold) {  // the folded reader sees whole rows: samples outside the crop [1 + off, 1 + off + Ls) become zeros
+                io.fold = 4;
+                io.fold_c = f;
+                io.fold_o = 1 + off;
+                io.fold_T = Ls;
+            }
             if (run_layer(nullptr, ts.ut[i], io, U[i], cur_len + 1, 0, 4 * f, cur_len + 1)) return r.rc;
         }
         {   // conv over [skip | up] without the concatenation
-            TcIO io = base_io(ts.us[i], A[lvl], pitchA[lvl], f, Ls);
-            io.x_roff = padl[lvl];
+            const bool fo = i == 3 && fold;
+            const TcLayer &tu = fo ? ts.us3f : ts.us[i];
+            TcIO io = base_io(tu, A[lvl], fo ? pitchA[lvl] / PN_FOLD : pitchA[lvl], fo ? PN_FOLD * f : f, fo ? pitchA[lvl] / PN_FOLD : Ls);
             io.x2 = U[i];
             io.x2_split = B * (int64_t)pitchA[lvl] * f;
-            io.x2_pitch = pitchA[lvl];
-            io.x2_roff = 1 + off;
-            io.cin_a = f;
+            if (fo) {  // offsets (skip 3, up 1 + off = 2, output 3) live in the folded weights
+                if (padl[lvl] != 3 || 1 + off != 2) {
+                    set_error("PhaseNet: folded level-0 layer built for offsets (3, 2), got (%d, %d)", padl[lvl], 1 + off);
+                    return VP_ERR_ARG;
+                }
+                io.x2_pitch = pitchA[lvl] / PN_FOLD;
+                io.cin_a = PN_FOLD * f;
+                io.T_valid = (Ls + 3 + PN_FOLD - 1) / PN_FOLD;
+                io.fold = PN_FOLD;
+                io.fold_c = f;
+                io.fold_o = 3;
+                io.fold_T = Ls;
+            } else {
+                io.x_roff = padl[lvl];
+                io.x2_pitch = pitchA[lvl];
+                io.x2_roff = 1 + off;
+                io.cin_a = f;
+            }
             const bool tapped = r.stop_name && std::strcmp(r.stop_name, us_names[i]) == 0;
             if (i == 3 && !tapped) {  // last layer: + `out` 1x1 conv + softmax -> (B, 3, L0) fp32
                 io.out_fmt = 2;
@@ -1236,10 +1346,10 @@ static int run_pn_tc(Runner &r, const float *x, float *y, Arena &ar) {
                 io.y_cs = L0;
                 io.head_w = m->pn_head_w;
                 io.head_b = m->pn_head_b;
-                if (r.go()) r.rc = tc_launch(ts.us[i], io, r.s);
+                if (r.go()) r.rc = tc_launch(tu, io, r.s);
                 return r.rc;
             }
-            if (run_layer(us_names[i], ts.us[i], io, Bu[i], Ls, 0, f, Ls)) return r.rc;
+            if (run_layer(us_names[i], tu, io, Bu[i], Ls, 0, f, Ls)) return r.rc;
         }
         cur = Bu[i];
         cur_c = f;

@@ -160,7 +160,7 @@ template <typename Tin, int SPLIT, bool POOL>
 __global__ void __launch_bounds__(E0_NT, 2) slice_enc0_kernel(const Tin *__restrict__ trace, int64_t ch_stride,
                                                               const int64_t *__restrict__ starts, int L, int peak_scope,
                                                               int taper, Taper tap, const __grid_constant__ Enc0W wt,
-                                                              uint16_t *__restrict__ out, int64_t out_split) {
+                                                              uint16_t *__restrict__ out, int64_t out_split, int out_pitch) {
     extern __shared__ __align__(16) float e0_smem[];
     __shared__ float red[96];
     const int XP = L + 12;  // xs[c][i + 5] = normalised sample i; zero halo on both sides
@@ -247,9 +247,14 @@ __global__ void __launch_bounds__(E0_NT, 2) slice_enc0_kernel(const Tin *__restr
             for (int co = 0; co < 8; ++co) v[co] = fmaxf(a0[co], 0.f);
             uint4 hi, lo;
             pack8_split16<SPLIT>(v, hi, lo);
-            uint16_t *yb = out + (w * L + p) * 8;
+            uint16_t *yb = out + (w * out_pitch + p) * 8;
             *reinterpret_cast<uint4 *>(yb) = hi;
             if (SPLIT == 2) *reinterpret_cast<uint4 *>(yb + out_split) = lo;
+        }
+        for (int p = L + tid; p < out_pitch; p += E0_NT) {  // rows past the window inside the output pitch: conv zero padding
+            uint16_t *yb = out + (w * out_pitch + p) * 8;
+            *reinterpret_cast<uint4 *>(yb) = make_uint4(0u, 0u, 0u, 0u);
+            if (SPLIT == 2) *reinterpret_cast<uint4 *>(yb + out_split) = make_uint4(0u, 0u, 0u, 0u);
         }
         return;
     }
@@ -292,7 +297,7 @@ __global__ void __launch_bounds__(E0_NT, 2) slice_enc0_kernel(const Tin *__restr
 
 int launch_slice_enc0(const void *trace, int dtype, int64_t ch_stride, const int64_t *starts, int64_t nw, int L, int scope,
                       int taper, const float *w_host /*(8,3,k)*/, const float *b_host /*(8)*/, int split, uint16_t *out,
-                      int64_t out_split, cudaStream_t s, int k) {
+                      int64_t out_split, cudaStream_t s, int k, int out_pitch) {
     VP_REQUIRE((k == 11 && L % 2 == 0 || k == 7) && L <= E0_PT * E0_NT, VP_ERR_UNSUPPORTED,
                "fused slicer + first conv: window length %d / kernel size %d unsupported", L, k);
     if (nw == 0) return VP_OK;
@@ -314,7 +319,8 @@ int launch_slice_enc0(const void *trace, int dtype, int64_t ch_stride, const int
             VP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (E0_PT * E0_NT + 12) * 4)); \
             attr[k == 11] = true;                                                                                           \
         }                                                                                                                   \
-        kern<<<(unsigned)nw, E0_NT, smem, s>>>((const T *)trace, ch_stride, starts, L, scope, taper, tap, wt, out, out_split); \
+        kern<<<(unsigned)nw, E0_NT, smem, s>>>((const T *)trace, ch_stride, starts, L, scope, taper, tap, wt, out, out_split, \
+                                               out_pitch > 0 ? out_pitch : L);                                              \
     } while (0)
     KTimer kt(KC_SLICE_ENC0, s);
     if (dtype == VP_DTYPE_F32 && split == 2) VP_E0_LAUNCH(float, 2);

@@ -344,8 +344,13 @@ __global__ void __launch_bounds__(32 * (EW + 4), EW == 16 ? 1 : EW == 8 ? 2 : 4)
                         const float4 b0 = *reinterpret_cast<const float4 *>(&s_bias[n0]), b1 = *reinterpret_cast<const float4 *>(&s_bias[n0 + 4]);
                         w8[0] += b0.x, w8[1] += b0.y, w8[2] += b0.z, w8[3] += b0.w;
                         w8[4] += b1.x, w8[5] += b1.y, w8[6] += b1.z, w8[7] += b1.w;
-                        const int t_out = t0 + phi;
-                        const bool ok = st && t_out < p.T_out;
+                        int t_out = t0 + phi;
+                        bool ok = st && t_out < p.T_out;
+                        bool fold_zero = false;  // folded output sample outside the sequence: 16-bit rows get zeros
+                        if (p.fold > 1) {
+                            t_out = p.fold * srow + n0 / p.fold_c - p.fold_o;
+                            fold_zero = t_out < 0 || t_out >= p.fold_T;
+                        }
                         if (p.res != nullptr && ok) {  // residual stream, fp32 row-major [seq][t][cout]
                             const float4 *rp = reinterpret_cast<const float4 *>(p.res + (orow0 + phi) * p.cout + c0);
                             const float4 r0 = rp[0], r1 = rp[1];  // plain loads: y32 may alias res (in-place residual stream)
@@ -376,6 +381,11 @@ __global__ void __launch_bounds__(32 * (EW + 4), EW == 16 ? 1 : EW == 8 ? 2 : 4)
                             for (int i = 0; i < 8; ++i) w8[i] = fmaxf(fmaf(w8[i], s_psc[n0 + i], s_psh[n0 + i]), 0.f);
                         }
                         if (!ok) continue;
+                        if (fold_zero) {
+                            if (p.out_fmt != 0) continue;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) w8[i] = 0.f;
+                        }
                         if (p.out_fmt == 2) {  // PhaseNet head: 1x1 conv (8 -> 3) + softmax over the classes, fp32 (seq, 3, T)
                             float z[3];
 #pragma unroll
@@ -400,9 +410,10 @@ __global__ void __launch_bounds__(32 * (EW + 4), EW == 16 ? 1 : EW == 8 ? 2 : 4)
                             if (SPLIT == 2) *reinterpret_cast<uint4 *>(yb + p.y_split) = lo;
                         } else {
                             float *yb = reinterpret_cast<float *>(p.y) + (int64_t)g * p.y_gs + (int64_t)seq * p.y_ss + t_out;
+                            const int cb = p.fold > 1 ? c0 % p.fold_c : c0;  // folded: channel inside the sample
 #pragma unroll
                             for (int i = 0; i < 8; ++i)
-                                if (c0 + i < p.cout) yb[(int64_t)(c0 + i) * p.y_cs] = w8[i];
+                                if (c0 + i < p.cout) yb[(int64_t)(cb + i) * p.y_cs] = w8[i];
                         }
                     }
                 }
@@ -679,11 +690,19 @@ int tc_launch(const TcLayer &L, const TcIO &io, cudaStream_t s) {
     p.y_pitch = io.y_pitch > 0 ? io.y_pitch : p.T_out;
     p.y_roff = io.y_roff;
     if (io.out_fmt == 2) {
-        VP_REQUIRE(io.head_w && io.head_b && L.cout == 8 && L.ph == 1, VP_ERR_UNSUPPORTED, "tc conv: the softmax head needs an 8-channel direct layer");
+        VP_REQUIRE(io.head_w && io.head_b && (L.cout == 8 || (io.fold > 1 && io.fold_c == 8)) && L.ph == 1, VP_ERR_UNSUPPORTED,
+                   "tc conv: the softmax head needs an 8-channel direct layer");
         std::memcpy(p.head_w, io.head_w, sizeof(p.head_w));
         std::memcpy(p.head_b, io.head_b, sizeof(p.head_b));
     }
-    const bool custom = io.x2 || p.x_pitch != io.T_in || p.x_roff != 0 || p.y_pitch != p.T_out || p.y_roff != 0 || io.T_valid > 0 ||
+    p.fold = io.fold > 1 ? io.fold : 1;
+    p.fold_c = io.fold_c;
+    p.fold_o = io.fold_o;
+    p.fold_T = io.fold_T;
+    VP_REQUIRE(p.fold == 1 || (L.ph == 1 && io.pool != 2 && io.fold_c % 8 == 0 && io.fold_c > 0 && L.cout == io.fold * io.fold_c &&
+                               !io.res && !io.y32 && !io.post_scale),
+               VP_ERR_UNSUPPORTED, "tc conv: folded output needs a plain direct layer with fold * fold_c output columns");
+    const bool custom = p.fold > 1 || io.x2 || p.x_pitch != io.T_in || p.x_roff != 0 || p.y_pitch != p.T_out || p.y_roff != 0 || io.T_valid > 0 ||
                         io.out_fmt == 2;
     p.out_fmt = io.out_fmt;
     p.y = io.y;
@@ -742,6 +761,18 @@ int tc_launch(const TcLayer &L, const TcIO &io, cudaStream_t s) {
     VP_TC_FIXED(128, 3, 4, 2);  // decoder.convs.1 polyphase (64 -> 2 x 64)
     VP_TC_FIXED(32, 5, 4, 0);   // decoder.convs.2 (64 -> 32, k5, loader-side up-sampling)
 #undef VP_TC_FIXED
+    // generic instances with 8 epilogue warps (two per TMEM lane quarter) when at most two CTAs fit an SM: with four, the
+    // TMEM -> convert -> store chain of a wide tile is the serial bottleneck of the CTA
+    static const bool ew8_off = getenv("VP_TC_EW8") && atoi(getenv("VP_TC_EW8")) == 0;
+#define VP_TC_CASE8(N, S) \
+    if (!ew8_off && occ <= 2 && L.nout == N && L.split == S) return launch_tc<N, S, 0, 0, 8, -1>(p, grid, smem, s)
+    VP_TC_CASE8(32, 2);
+    VP_TC_CASE8(64, 2);
+    VP_TC_CASE8(128, 2);
+    VP_TC_CASE8(32, 1);
+    VP_TC_CASE8(64, 1);
+    VP_TC_CASE8(128, 1);
+#undef VP_TC_CASE8
 #define VP_TC_CASE(N, S) \
     if (L.nout == N && L.split == S) return launch_tc<N, S, 0, 0, 4, -1>(p, grid, smem, s)
     VP_TC_CASE(16, 2);

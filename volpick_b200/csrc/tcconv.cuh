@@ -46,6 +46,9 @@ struct TcP {
     int64_t y_split, y_gs, y_ss, y_cs;
     int cout_cl, y_pitch, y_roff;
     float head_w[24], head_b[3];  // out_fmt 2: PhaseNet `out` conv, [class][channel]
+    // time folded into the MMA N (fold > 1): accumulator column n holds channel n % fold_c of sample fold * row + n / fold_c - fold_o;
+    // samples outside [0, fold_T) are written as zeros (they are the next layer's conv padding) / not written (fp32 outputs)
+    int fold, fold_c, fold_o, fold_T;
     // epilogue extras (single group, direct, un-pooled layers: the res-CNN stack)
     const float *post_scale, *post_shift;  // [NOUT]: 16-bit output = relu(v * scale + shift) (pre-activation BN + ReLU of the next conv)
     const float *res;                      // fp32 row-major [NS][T_out][cout] added to v
@@ -94,6 +97,7 @@ struct TcIO {
     int64_t x2_split = 0;
     int x2_pitch = 0, x2_roff = 0, cin_a = 0;  // cin_a: channels taken from x when x2 is set
     const float *head_w = nullptr, *head_b = nullptr;  // HOST pointers, out_fmt 2
+    int fold = 1, fold_c = 0, fold_o = 0, fold_T = 0;   // output time folding (see TcP)
 };
 int tc_out_len(const TcLayer &L, int T_in, int pool);
 int tc_launch(const TcLayer &L, const TcIO &io, cudaStream_t s);
