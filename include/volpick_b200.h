@@ -170,6 +170,16 @@ VP_API int vp_pick_labels(const float *annotation, int n_labels, int64_t pred_le
                    const float *thr_off, vp_trigger *picks, int64_t capacity, int64_t *count, int64_t *bounds,
                    void *stream);
 
+/* Window-level picks of the reference's evaluate() path (/root/reference/volpick/model/eval_taks0.py:20-140): for every
+ * window b and every label c with thr_on[c] > 0, trigger_onset + first argmax on y[b, c, lo_b:hi_b] (y: device
+ * (n_windows, n_labels, in_samples) as written by vp_forward; borders: DEVICE int64 (n_windows, 2) = window_borders, or
+ * NULL for whole windows).  Appends vp_trigger records with indices relative to lo_b and
+ * label = b * n_labels + c; unordered, *count may exceed capacity (overflow) as for vp_pick.
+ * thr_on / thr_off: HOST arrays of n_labels floats. */
+VP_API int vp_pick_windows(const float *y, int64_t n_windows, int n_labels, int64_t in_samples, const int64_t *borders,
+                    const float *thr_on, const float *thr_off, vp_trigger *picks, int64_t capacity, int64_t *count,
+                    void *stream);
+
 /* ---- the whole path for one gap-free record: WaveformModel.annotate + classify_aggregate -- */
 VP_API int64_t vp_annotate_workspace_bytes(const vp_model *m, int64_t n_samples, const vp_annotate_params *p,
                                     int trace_on_host, int64_t pick_capacity);

@@ -499,6 +499,42 @@ def test_picks_full_size_properties(lib):
         assert sp == s0 + int(np.argmax(x[s0:s1 + 1])) and g["value"] == x[sp]
 
 
+@pytest.mark.parametrize("kind", ["eqtransformer", "phasenet"])
+def test_pick_windows_evaluate_path(lib, eqt, pn, kind):
+    """Window-level picks (the reference's evaluate(): eval_taks0.py:46-56 per window inside window_borders): bit-exact
+    against the oracle's trigger rule applied to the same probability rows."""
+    model = eqt if kind == "eqtransformer" else pn
+    L = model.in_samples
+    B = 23
+    x = torch.from_numpy(_windows(kind, B, seed=71)).cuda()
+    rng = np.random.default_rng(7)
+    lo = rng.integers(0, L // 2, B)
+    hi = lo + rng.integers(1, L // 2, B)
+    hi[3] = lo[3]  # empty border
+    lo[5], hi[5] = 0, L
+    borders = np.stack([lo, hi], axis=1).astype(np.int64)
+    for wb in (borders, None):
+        got, y = model.pick_windows(x, wb, P_threshold=0.12, S_threshold=0.2, probabilities=True)
+        yh = y.cpu().numpy()
+        assert sorted(got) == ["P", "S"]
+        n_total = 0
+        for lab, thr in (("P", 0.12), ("S", 0.2)):
+            c = model.labels.index(lab)
+            for b in range(B):
+                a, e = (0, L) if wb is None else (int(borders[b, 0]), int(borders[b, 1]))
+                ref = pipeline.picks_from_trace(yh[b, c, a:e], np.float32(thr))
+                picks, scores = got[lab][b]
+                assert list(picks) == [r[2] for r in ref], (lab, b)
+                assert list(scores) == [np.float32(r[3]) for r in ref]
+                n_total += len(ref)
+        assert n_total > 0
+    # one threshold for all phases, detections on request
+    got = model.pick_windows(x, None, threshold=0.3)
+    assert sorted(got) == ["P", "S"]
+    if kind == "eqtransformer":
+        assert "Detection" in model.pick_windows(x, None, threshold=0.3, detection_threshold=0.5)
+
+
 # ------------------------------------------------------------------------------------------ whole path
 def _oracle_triggers(kind, sd, x, overlap, blinding, stacking, thr):
     ann = pipeline.annotate_array(kind, sd, x, overlap, blinding, stacking)

@@ -18,6 +18,10 @@ KIND_EQTRANSFORMER, KIND_PHASENET = 0, 1
 STACK = {"avg": 0, "max": 1}
 PRECISION = {"fp32": 0, "f16x3": 1, "bf16": 2}
 DTYPE_F32, DTYPE_I32 = 0, 1
+# vp_trigger as a NumPy record (include/volpick_b200.h)
+import numpy as _np  # noqa: E402
+
+TRIGGER_DTYPE = _np.dtype([("s0", "<i8"), ("s1", "<i8"), ("s_peak", "<i8"), ("value", "<f4"), ("label", "<i4")])
 PEAK_SCOPE = {"channel": 0, "window": 1}
 
 
@@ -73,6 +77,7 @@ SIGNATURES = {
     "vp_pick_scratch_bytes": (_i64, [_i64]),
     "vp_pick": (_i32, [_vp, _i64, _f32, _f32, _i32, _vp, _i64, _vp, _vp, _i64, _vp]),
     "vp_pick_labels": (_i32, [_vp, _i32, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "vp_pick_windows": (_i32, [_vp, _i64, _i32, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     "vp_annotate_workspace_bytes": (_i64, [_vp, _i64, C.POINTER(AnnotateParams), _i32, _i64]),
     "vp_annotate": (_i32, [_vp, _vp, _i32, _i32, _i64, _i64, C.POINTER(AnnotateParams), _vp, _i32, _vp, _i64,
                            C.POINTER(_i64), _vp, _vp, _i64, _vp]),

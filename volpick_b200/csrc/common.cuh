@@ -121,6 +121,8 @@ struct LstmP {
     float *y;  // (B, 16*ndir, T), group stride y_gs
     int64_t y_bs, y_gs;
     int T, ndir, B;
+    // cin == 0: the input projection W_ih x + b was computed by a tensor-core GEMM: proj[b][t][dir][16 units][4 gates] fp32
+    const float *proj = nullptr;
 };
 int launch_lstm(int cin, const LstmP &p, int G, cudaStream_t s);
 

@@ -246,6 +246,7 @@ struct vp_model {
     struct TcSet {
         TcLayer enc[7], dec[7], head;
         TcLayer res1[7], res2[7];  // res-CNN convs (BatchNorm + ReLU of their inputs live in the producer's epilogue)
+        TcLayer lproj;             // bi_lstm_stack.members.0: input projection of both directions as a 1x1 conv (64 -> 2 x 64 gates)
         uint16_t *d_w = nullptr;
         float *d_b = nullptr;
         bool ready = false;
@@ -301,6 +302,7 @@ static int upload_tc(vp_model::TcSet &ts) {
     for (int i = 0; i < 7; ++i) layers.push_back(&ts.enc[i]);
     for (int i = 0; i < 7; ++i) layers.push_back(&ts.dec[i]);
     layers.push_back(&ts.head);
+    layers.push_back(&ts.lproj);
     for (int i = 0; i < 7; ++i) {
         layers.push_back(&ts.res1[i]);
         layers.push_back(&ts.res2[i]);
@@ -455,6 +457,20 @@ static int build_eqt(vp_model *m, Cursor &cur, Packed &pk) {
                 rc = tc_build_layer(j == 0 ? ts.res1[i] : ts.res2[i], TC_DIRECT, 64, 64, kResK[i], 0, split, 1, w1, b1, kResK[i] == 3 ? 1 : 0);
                 if (rc != VP_OK) return rc;
             }
+        {   // BiLSTM block 0 input projection: column n = dir * 64 + unit * 4 + gate (the order lstm_kernel reads), bias b_ih + b_hh
+            const LstmW &lw = m->bil[0].lstm;
+            std::vector<float> wp((size_t)128 * 64), bp(128);
+            for (int dir = 0; dir < 2; ++dir)
+                for (int j = 0; j < 16; ++j)
+                    for (int g = 0; g < 4; ++g) {
+                        const int n = dir * 64 + j * 4 + g;
+                        bp[n] = pk.host[lw.b + ((int64_t)dir * 16 + j) * 4 + g];
+                        for (int ci = 0; ci < 64; ++ci) wp[(size_t)n * 64 + ci] = pk.host[lw.ih + (((int64_t)dir * 64 + ci) * 16 + j) * 4 + g];
+                    }
+            const float *w1[1] = {wp.data()}, *b1[1] = {bp.data()};
+            rc = tc_build_layer(ts.lproj, TC_DIRECT, 64, 128, 1, 0, split, 1, w1, b1);
+            if (rc != VP_OK) return rc;
+        }
         // fused decoder tail: (1, 8, 11) head weights -> [c * 11 + k]; tile = 47 / 75 rows of the 375-sample level
         float head_w[3][88], head_b[3];
         for (int g = 0; g < 3; ++g) {
@@ -805,6 +821,9 @@ static int run_eqt(Runner &r, const float *x, float *y, Arena &ar) {
     const int64_t split16 = B * big16;  // elements between the hi and lo planes
     float *r0 = ar.take(B * 64 * T), *r1 = ar.take(B * 64 * T), *r2 = ar.take(B * 64 * T);
     float *xres = tc ? ar.take(B * 64 * T) : nullptr;  // tensor-core path: residual stream, fp32 row-major [B][T][64]
+    float *lproj = tc ? ar.take(B * 128 * T) : nullptr;  // tensor-core path: BiLSTM-0 input projection, fp32 [B][T][2][16][4]
+    static const bool lproj_off = getenv("VP_LSTM_PROJ") && atoi(getenv("VP_LSTM_PROJ")) == 0;  // debugging aid
+    const bool use_lproj = tc && !lproj_off && r.stop_name == nullptr;  // the debug taps keep the fp32 (B, 64, T) stack output
     float *lo = ar.take(B * 32 * T);
     float *s0 = ar.take(B * 16 * T), *s1 = ar.take(B * 16 * T);
     float *din = ar.take(3 * B * 16 * T);  // [group][B][16][T]: decoder inputs
@@ -941,6 +960,12 @@ static int run_eqt(Runner &r, const float *x, float *y, Arena &ar) {
                 io2.y32 = xres;
                 io2.post_scale = r.W(m->res[i + 1].n1.scale);
                 io2.post_shift = r.W(m->res[i + 1].n1.shift);
+            } else if (use_lproj) {  // stack output as the 16-bit operand of the BiLSTM input-projection GEMM
+                io2.out_fmt = 0;
+                io2.y = pp16[0];
+                io2.y_split = split16;
+                io2.y_ss = io2.y_cs = 0;
+                io2.cout_cl = 64;
             } else {  // stack output -> BiLSTM input, fp32 (B, 64, T) channel-first
                 io2.out_fmt = 1;
                 io2.y = ra;
@@ -950,6 +975,25 @@ static int run_eqt(Runner &r, const float *x, float *y, Arena &ar) {
                 io2.cout_cl = 0;
             }
             r.rc = tc_launch(ts.res2[i], io2, r.s);
+        }
+        if (use_lproj && r.go()) {  // W_ih x + b of both directions for all time steps: (B T) x 64 x 128 GEMM
+            TcIO io;
+            io.x = pp16[0];
+            io.x_split = split16;
+            io.x_gs = 0;
+            io.T_in = T;
+            io.NS = (int)B;
+            io.w_dev = ts.d_w + ts.lproj.w_off;
+            io.b_dev = ts.d_b + ts.lproj.b_off;
+            io.act = ACT_NONE;
+            io.pool = 1;
+            io.out_fmt = 3;  // only the fp32 row-major second output
+            io.y = nullptr;
+            io.y_split = 0;
+            io.y_gs = io.y_ss = io.y_cs = 0;
+            io.cout_cl = 128;
+            io.y32 = lproj;
+            r.rc = tc_launch(ts.lproj, io, r.s);
         }
         if (r.tap("res6", ra, B * 64 * T)) return r.rc;
     }
@@ -984,7 +1028,8 @@ static int run_eqt(Runner &r, const float *x, float *y, Arena &ar) {
             p.T = T;
             p.ndir = 2;
             p.B = (int)B;
-            r.rc = launch_lstm(seq_c, p, 1, r.s);
+            if (i == 0 && use_lproj) p.proj = lproj;
+            r.rc = launch_lstm(p.proj ? 0 : seq_c, p, 1, r.s);
         }
         if (r.tap(bl_names[i][0], lo, B * 32 * T)) return r.rc;
         float *dst = sp[i & 1];

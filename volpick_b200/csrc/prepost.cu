@@ -612,6 +612,16 @@ struct PickLabels {
     int pick[PK_MAXLAB];  // 0: only the NaN bounds of this label are wanted
     int bound_slot[PK_MAXLAB];
 };
+// Window mode (vp_pick_windows; the reference's evaluate() path): blockIdx.y = window * n_pick + entry; the trace of an
+// entry is the slice [lo, hi) of row (window, label[entry]) of y (n_windows, n_labels, L); trigger indices are relative
+// to lo and the trigger label is window * n_labels + label.
+struct PickWin {
+    const float *y;  // nullptr: trace mode
+    int64_t L;
+    int n_labels, n_pick;
+    int64_t win0;            // absolute index of the first window of this launch
+    const int64_t *borders;  // device (n_windows, 2) = [lo, hi) per window, or nullptr for the whole window
+};
 
 // Continues a run over global memory from `base`, PK_WALK * 32 samples per round trip (the loads of a round are
 // independent; a run that leaves its tile is latency bound: 32 samples per trip made a 2000-sample detection run the
@@ -665,15 +675,30 @@ __device__ __forceinline__ void pick_walk_global(const float *__restrict__ x, in
     }
 }
 
-__global__ void __launch_bounds__(PK_NT) pick_tile_kernel(const PickLabels P, int64_t n, vp_trigger *__restrict__ picks,
-                                                          int64_t pick_cap, unsigned long long *__restrict__ npicks,
+__global__ void __launch_bounds__(PK_NT) pick_tile_kernel(const PickLabels P, const PickWin W, int64_t n,
+                                                          vp_trigger *__restrict__ picks, int64_t pick_cap,
+                                                          unsigned long long *__restrict__ npicks,
                                                           int64_t *__restrict__ bounds) {
     __shared__ __align__(16) float sv[PK_TILE];
     __shared__ uint32_t m_off[PK_WORDS];
     __shared__ uint16_t run_start[PK_TILE / 2];
     __shared__ int n_runs, s_lo, s_hi, s_prev, s_prev_ok, s_next_ok;
-    const int li = blockIdx.y;
+    int li = W.y != nullptr ? 0 : (int)blockIdx.y;
     const float *__restrict__ x = P.x[li];
+    int out_label = P.label[li];
+    if (W.y != nullptr) {  // window mode: this CTA's trace is a slice of one (window, label) row
+        const int64_t win = blockIdx.y / W.n_pick;
+        li = (int)(blockIdx.y - win * W.n_pick);
+        int64_t lo = 0, hi = W.L;
+        if (W.borders != nullptr) {
+            lo = min(max(__ldg(W.borders + 2 * win), (int64_t)0), W.L);
+            hi = min(max(__ldg(W.borders + 2 * win + 1), lo), W.L);
+        }
+        x = W.y + (win * W.n_labels + P.label[li]) * W.L + lo;
+        n = hi - lo;
+        out_label = (int)((W.win0 + win) * W.n_labels + P.label[li]);
+        if ((int64_t)blockIdx.x * PK_TILE - 3 >= n) return;  // tile beyond the slice (uniform for the CTA)
+    }
     const float thr_on = P.thr_on[li], thr_off = P.thr_off[li];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int shift = (int)((reinterpret_cast<uintptr_t>(x) >> 2) & 3);  // elements past a 16-byte boundary
@@ -820,7 +845,7 @@ __global__ void __launch_bounds__(PK_NT) pick_tile_kernel(const PickLabels P, in
                 q.s1 = end;
                 q.s_peak = pk;
                 q.value = best;
-                q.label = P.label[li];
+                q.label = out_label;
                 picks[slot] = q;
             }
         }
@@ -922,7 +947,8 @@ static int launch_pick_tiles(const PickLabels &P, int n_lab, int64_t n, vp_trigg
     // +1 tile: the tile grid of a label starts up to 3 samples before its first sample (16-byte alignment)
     const unsigned tiles = (unsigned)((n + 3 + PK_TILE - 1) / PK_TILE);
     KTimer kt(KC_PICK, s);
-    pick_tile_kernel<<<dim3(tiles, n_lab), PK_NT, 0, s>>>(P, n, picks, capacity, (unsigned long long *)count, bounds);
+    PickWin W = {};
+    pick_tile_kernel<<<dim3(tiles, n_lab), PK_NT, 0, s>>>(P, W, n, picks, capacity, (unsigned long long *)count, bounds);
     VP_LAUNCH_CHECK();
     return VP_OK;
 }
@@ -970,4 +996,44 @@ extern "C" int vp_pick_labels(const float *annotation, int n_labels, int64_t pre
     }
     if (nl == 0) return VP_OK;
     return launch_pick_tiles(P, nl, pred_len, picks, capacity, count, bounds, s);
+}
+
+extern "C" int vp_pick_windows(const float *y, int64_t n_windows, int n_labels, int64_t in_samples, const int64_t *borders,
+                               const float *thr_on, const float *thr_off, vp_trigger *picks, int64_t capacity, int64_t *count,
+                               void *stream) {
+    VP_REQUIRE(y && thr_on && thr_off && picks && count, VP_ERR_ARG, "vp_pick_windows: null pointer");
+    VP_REQUIRE(n_labels > 0 && n_labels <= PK_MAXLAB && in_samples > 0 && n_windows >= 0, VP_ERR_ARG,
+               "vp_pick_windows: bad sizes (windows %lld, labels %d, samples %lld)", (long long)n_windows, n_labels, (long long)in_samples);
+    VP_REQUIRE(n_windows * n_labels < (1LL << 31), VP_ERR_ARG, "vp_pick_windows: window * label index exceeds the trigger label field");
+    PickLabels P = {};
+    PickWin W = {};
+    int np = 0;
+    for (int c = 0; c < n_labels; ++c) {
+        if (!(thr_on[c] > 0.f)) continue;  // <= 0 or NaN: the label is not picked
+        P.thr_on[np] = thr_on[c];
+        P.thr_off[np] = thr_off[c];
+        P.label[np] = c;
+        P.pick[np] = 1;
+        ++np;
+    }
+    if (np == 0 || n_windows == 0 || capacity <= 0) return VP_OK;
+    W.y = y;
+    W.L = in_samples;
+    W.n_labels = n_labels;
+    W.n_pick = np;
+    W.borders = borders;
+    cudaStream_t s = (cudaStream_t)stream;
+    const unsigned tiles = (unsigned)((in_samples + 3 + PK_TILE - 1) / PK_TILE);
+    KTimer kt(KC_PICK, s);
+    const int64_t max_win = 65535 / np;  // grid.y limit
+    for (int64_t w0 = 0; w0 < n_windows; w0 += max_win) {
+        const int64_t nw = std::min(max_win, n_windows - w0);
+        PickWin Wc = W;
+        Wc.y = y + w0 * n_labels * in_samples;
+        Wc.borders = borders ? borders + 2 * w0 : nullptr;
+        Wc.win0 = w0;
+        pick_tile_kernel<<<dim3(tiles, (unsigned)(nw * np)), PK_NT, 0, s>>>(P, Wc, in_samples, picks, capacity, (unsigned long long *)count, nullptr);
+        VP_LAUNCH_CHECK();
+    }
+    return VP_OK;
 }

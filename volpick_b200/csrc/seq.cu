@@ -57,9 +57,11 @@ __global__ void __launch_bounds__(128) lstm_kernel(const LstmP p) {
 #pragma unroll
         for (int k = 0; k < 16; ++k) whh[k] = __ldg(src + k * 16 + j);
     }
-    const float4 bias = __ldg(reinterpret_cast<const float4 *>(p.bias + (int64_t)g * p.w_gs_b) + dir * 16 + j);
+    const float4 bias = CIN == 0 ? make_float4(0.f, 0.f, 0.f, 0.f)
+                                 : __ldg(reinterpret_cast<const float4 *>(p.bias + (int64_t)g * p.w_gs_b) + dir * 16 + j);
     const float4 *wi = wih + dir * CIN * 16 + j;
-    const float *xb = p.x + (int64_t)g * p.x_gs + b * p.x_bs;
+    const float *xb = CIN == 0 ? nullptr : p.x + (int64_t)g * p.x_gs + b * p.x_bs;
+    const float4 *pj = CIN == 0 ? reinterpret_cast<const float4 *>(p.proj) + ((b * p.T) * ndir + dir) * 16 + j : nullptr;
     float *yb = p.y + (int64_t)g * p.y_gs + b * p.y_bs + (int64_t)(dir * 16 + j) * p.T;
     const int T = p.T;
 
@@ -67,6 +69,7 @@ __global__ void __launch_bounds__(128) lstm_kernel(const LstmP p) {
     // loads and FMAs overlap the shuffle / transcendental chain of the current step.  (Blocking it over 4 steps to
     // save W_ih reads was measured SLOWER: 168 registers, one CTA fewer per SM, 1.31 -> 1.66 ms per station-day.)
     auto in_proj = [&](int t) {
+        if constexpr (CIN == 0) return __ldg(pj + (int64_t)t * ndir * 16);  // bias included by the GEMM
         float4 a0 = bias, a1 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 8
         for (int ci = 0; ci < CIN; ci += 2) {
@@ -103,7 +106,9 @@ int launch_lstm(int cin, const LstmP &p, int G, cudaStream_t s) {
     dim3 grid((unsigned)((nseq + 7) / 8), G);
     const size_t smem = (size_t)p.ndir * cin * 16 * sizeof(float4);
     KTimer kt(KC_LSTM, s);
-    if (cin == 64) {
+    if (cin == 0 && p.proj != nullptr) {
+        lstm_kernel<0><<<grid, 128, 0, s>>>(p);
+    } else if (cin == 64) {
         lstm_kernel<64><<<grid, 128, smem, s>>>(p);
     } else if (cin == 16) {
         lstm_kernel<16><<<grid, 128, smem, s>>>(p);
@@ -117,17 +122,20 @@ int launch_lstm(int cin, const LstmP &p, int G, cudaStream_t s) {
 
 // ---------------------------------------------------------------------------------------------
 // Additive self-attention (+ optional transformer tail).  One thread = one query time step of one
-// window; a 128-thread CTA handles 2 windows.
+// window; a 192-thread CTA handles 4 windows in 48-thread slots (T = 47: 98 % of the lanes work; 64-thread slots left
+// 27 % of them idle) and loads the 21.6 KB parameter block once for the four.
 constexpr int AT_MAXT = 48;   // T <= 48 (T = 47 for 6000-sample windows)
 constexpr int AT_XP = 17;     // pitch of Xs rows (time-major x)
 constexpr int AT_KP = 36;     // pitch of the k-projection rows (float4 aligned)
 constexpr int AT_EP = 49;     // pitch of the emission rows
 constexpr int AT_OFF_K = (AW_SIZE + 3) & ~3;                      // 16-byte aligned (float4 reads)
-constexpr int AT_OFF_X = AT_OFF_K + 2 * AT_MAXT * AT_KP;
-constexpr int AT_OFF_E = AT_OFF_X + 2 * AT_MAXT * AT_XP;
-constexpr int AT_SMEM_FLOATS = AT_OFF_E + 2 * AT_MAXT * AT_EP;
+constexpr int AT_WPC = 4;     // windows per CTA
+constexpr int AT_NT = AT_WPC * AT_MAXT;
+constexpr int AT_OFF_X = AT_OFF_K + AT_WPC * AT_MAXT * AT_KP;
+constexpr int AT_OFF_E = AT_OFF_X + AT_WPC * AT_MAXT * AT_XP;
+constexpr int AT_SMEM_FLOATS = AT_OFF_E + AT_WPC * AT_MAXT * AT_EP;
 
-__global__ void __launch_bounds__(128) attention_kernel(const AttnP p) {
+__global__ void __launch_bounds__(AT_NT) attention_kernel(const AttnP p) {
     extern __shared__ __align__(16) float at_smem[];
     float *wsm = at_smem;                                               // [AW_SIZE]
     float(*Ks)[AT_MAXT * AT_KP] = reinterpret_cast<float(*)[AT_MAXT * AT_KP]>(at_smem + AT_OFF_K);
@@ -140,18 +148,18 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnP p) {
     {
         const float *src = p.w + (int64_t)g * p.w_gs;
         const int n = (p.mode == 0) ? AW_SIZE : AW_G1;
-        for (int i = tid; i < n; i += 128) {
+        for (int i = tid; i < n; i += AT_NT) {
             const float v = __ldg(src + i);
             wsm[i] = (i >= AW_WA && i < AW_WA + 32) ? -2.f * v : v;  // Wa is only used as -2 Wa (see the emission loop)
         }
     }
-    const int wl = tid >> 6;  // window slot in the CTA
-    const int i = tid & 63;   // query time step
-    const int64_t b = (int64_t)blockIdx.x * 2 + wl;
+    const int wl = tid / AT_MAXT;      // window slot in the CTA
+    const int i = tid - wl * AT_MAXT;  // query time step
+    const int64_t b = (int64_t)blockIdx.x * AT_WPC + wl;
     const bool bval = b < p.B;
     const float *xb = p.x + (int64_t)g * p.x_gs + (bval ? b : 0) * p.x_bs;
     // transpose-load x (16, T) -> Xs[t][c]
-    for (int idx = i; idx < 16 * T; idx += 64) {
+    for (int idx = i; idx < 16 * T; idx += AT_MAXT) {
         const int c = idx / T, t = idx - c * T;
         Xs[wl][t * AT_XP + c] = bval ? __ldg(xb + idx) : 0.f;
     }
@@ -318,7 +326,7 @@ int launch_attention(const AttnP &p, int G, cudaStream_t s) {
         set_error("attention kernel supports T <= %d (got %d)", AT_MAXT, p.T);
         return VP_ERR_UNSUPPORTED;
     }
-    dim3 grid((unsigned)((p.B + 1) / 2), G);
+    dim3 grid((unsigned)((p.B + AT_WPC - 1) / AT_WPC), G);
     constexpr size_t smem = AT_SMEM_FLOATS * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
@@ -326,7 +334,7 @@ int launch_attention(const AttnP &p, int G, cudaStream_t s) {
         attr_set = true;
     }
     KTimer kt(KC_ATTN, s);
-    attention_kernel<<<grid, 128, smem, s>>>(p);
+    attention_kernel<<<grid, AT_NT, smem, s>>>(p);
     VP_LAUNCH_CHECK();
     return VP_OK;
 }

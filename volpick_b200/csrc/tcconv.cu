@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(32 * (EW + 4), EW == 16 ? 1 : EW == 8 ? 2 : 4)
 #pragma unroll
                             for (int i = 0; i < 8; ++i) w8[i] = fmaxf(fmaf(w8[i], s_psc[n0 + i], s_psh[n0 + i]), 0.f);
                         }
-                        if (!ok) continue;
+                        if (!ok || p.out_fmt == 3) continue;  // out_fmt 3: the fp32 second output was the only one
                         if (fold_zero) {
                             if (p.out_fmt != 0) continue;
 #pragma unroll

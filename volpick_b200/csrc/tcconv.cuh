@@ -41,7 +41,8 @@ struct TcP {
     int dbg;    // profiling aid (env VP_TC_DBG): 1 skip A loads, 2 skip MMAs, 4 skip epilogue body
     int act, pool, ph, cout, coutp, T_valid, T_out;
     int out_fmt;  // 0: channel-last 16-bit [SPLIT][G][NS][y_pitch][cout_cl], row (seq, t) at seq * y_pitch + y_roff + t;
-                  // 1: fp32 (seq stride y_ss, channel stride y_cs); 2: fp32 like 1 after the fused 1x1 conv (8 -> 3) + softmax head
+                  // 1: fp32 (seq stride y_ss, channel stride y_cs); 2: fp32 like 1 after the fused 1x1 conv (8 -> 3) + softmax head;
+                  // 3: none (only the fp32 row-major second output y32 is written)
     void *y;
     int64_t y_split, y_gs, y_ss, y_cs;
     int cout_cl, y_pitch, y_roff;

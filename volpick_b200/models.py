@@ -334,6 +334,66 @@ class WaveformModel:
 
     __call__ = forward
 
+    def pick_windows(self, x, window_borders=None, precision: Optional[str] = None, probabilities: bool = False, **kwargs):
+        """Window-level picks, the inner loop of the reference's ``evaluate`` (volpick/model/eval_taks0.py:20-140):
+        forward on pre-cut, pre-normalised windows ``x`` (B, 3, in_samples; CUDA tensor) and, per window and phase label,
+        ``trigger_onset(prob, thr, thr / 2)`` + first argmax inside ``window_borders[b] = (lo, hi)`` (whole window when
+        None).  Thresholds: ``P_threshold`` / ``S_threshold`` (/ ``detection_threshold``) or ``threshold=`` for all phases.
+        Returns ``{label: [(picks, scores), ...]}`` with one ``(int64 array, float32 array)`` per window, indices relative
+        to ``lo`` and in trigger order; with ``probabilities=True`` also the (B, 3, in_samples) tensor of the forward."""
+        import torch
+
+        self._require_gpu()
+        y = self.forward(x, precision=precision)
+        y = torch.stack(y, dim=1) if isinstance(y, tuple) else y
+        y = y.contiguous()
+        B = y.shape[0]
+        lib = _lib.load()
+        argdict = self._argdict({k: v for k, v in kwargs.items() if k != "threshold"})
+        if "threshold" in kwargs:
+            for lab in self.labels:
+                if lab not in ("N", "Detection"):
+                    argdict[f"{lab}_threshold"] = kwargs["threshold"]
+        thr = self._thresholds(argdict)
+        if "detection_threshold" not in kwargs and "Detection" in self.labels:
+            thr[self.labels.index("Detection")] = 0.0  # evaluate() picks phases only
+        thr_on = np.asarray([max(float(t), 0.0) for t in thr], dtype=np.float32)
+        thr_off = thr_on / np.float32(2)
+        d_b = None
+        if window_borders is not None:
+            wb = np.ascontiguousarray(np.asarray(window_borders.cpu() if hasattr(window_borders, "cpu") else window_borders, dtype=np.int64))
+            if wb.shape != (B, 2):
+                raise ValueError(f"window_borders must have shape ({B}, 2), got {wb.shape}")
+            d_b = torch.from_numpy(wb).to(y.device)
+        cap = max(1024, 16 * B)
+        while True:
+            picks = torch.empty(cap * 32, dtype=torch.uint8, device=y.device)
+            count = torch.zeros(1, dtype=torch.int64, device=y.device)
+            with torch.cuda.device(y.device):
+                _lib.check(lib.vp_pick_windows(C.c_void_p(y.data_ptr()), B, 3, self.in_samples,
+                                               C.c_void_p(d_b.data_ptr()) if d_b is not None else None, thr_on.ctypes.data,
+                                               thr_off.ctypes.data, C.c_void_p(picks.data_ptr()), cap, C.c_void_p(count.data_ptr()),
+                                               self._stream_ptr()))
+            k = int(count.item())
+            if k <= cap:
+                break
+            cap = k  # overflow is reported through the count: retry with the exact size
+        arr = np.frombuffer(picks[: k * 32].cpu().numpy().tobytes(), dtype=_lib.TRIGGER_DTYPE, count=k)
+        arr = np.sort(arr, order=["label", "s0"])
+        out = {lab: [(np.empty(0, np.int64), np.empty(0, np.float32)) for _ in range(B)] for lab, t in zip(self.labels, thr_on) if t > 0}
+        win, lab_idx = arr["label"] // 3, arr["label"] % 3
+        for c, lab in enumerate(self.labels):
+            if lab not in out:
+                continue
+            sel = arr[lab_idx == c]
+            w = win[lab_idx == c]
+            cuts = np.searchsorted(w, np.arange(B + 1))
+            for b in range(B):
+                seg = sel[cuts[b]:cuts[b + 1]]
+                if len(seg):
+                    out[lab][b] = (seg["s_peak"].astype(np.int64), seg["value"].astype(np.float32))
+        return (out, y) if probabilities else out
+
     def forward_tap(self, x, tap: str, precision: Optional[str] = None):
         """Debug/parity helper: the named intermediate activation as a flat CUDA tensor."""
         import torch
