@@ -90,6 +90,25 @@ void decb_free(DecBPlan &plan);
 int decb_launch(const DecBPlan &plan, const uint16_t *x, long long x_split, long long x_gs, int B, float *y, int keep_lo,
                 int keep_hi, cudaStream_t s);
 
+// res-CNN stack: the 14 convs of res_cnn_stack.members.0-6 in one persistent launch (fused_res.cu).
+constexpr int RS_MAX_LAYERS = 14;
+struct ResLayerP {
+    const uint16_t *x;  // [split][NS][T][64] channel-last 16-bit operand
+    uint16_t *y;        // 16-bit output, same layout: relu(v * psc + psh) when affine, else v
+    const uint16_t *w;  // tcconv weight blocks [ntaps * 4][split][2][64][8]
+    const float *bias, *psc, *psh;  // [64]
+    float *res;         // fp32 residual stream [NS][T][64] added to the conv output (nullptr: none)
+    int ntaps;          // 3: 'same' conv; 2: one zero on the right
+    int affine;         // post-affine + ReLU on the 16-bit output
+    int write_res;      // store the sum back to res (in place)
+};
+struct ResStackP {
+    ResLayerP l[RS_MAX_LAYERS];
+    int n_layers, NS, T, fmt16;
+    long long split16;  // elements between the hi and lo planes of x / y
+};
+int resstack_launch(const ResStackP &p, int split, cudaStream_t s);
+
 // Decoder middle: decoder.convs.1 + decoder.convs.2 (fused_deca.cu).
 struct FzDecA {
     const uint16_t *x;  // [split][group][B][94][64] channel-last 16-bit (decoder.convs.0 output)

@@ -919,7 +919,48 @@ static int run_eqt(Runner &r, const float *x, float *y, Arena &ar) {
     if (tc) {
         // tensor cores: conv1 reads relu(bn1(x)) (16-bit, written by the previous epilogue) and writes relu(bn2(y));
         // conv2 adds the fp32 residual stream in place and writes the next block's relu(bn1(x))
-        for (int i = 0; i < 7 && r.go(); ++i) {
+        static const bool resfuse_off = getenv("VP_FUSED_RES") && atoi(getenv("VP_FUSED_RES")) == 0;  // debugging aid
+        const bool fused_res = use_lproj && !resfuse_off && T + 1 <= 64;
+        if (fused_res && r.go()) {  // all 14 convs in one persistent launch (fused_res.cu)
+            ResStackP sp;
+            std::memset(&sp, 0, sizeof(sp));
+            sp.n_layers = 14;
+            sp.NS = (int)B;
+            sp.T = T;
+            sp.fmt16 = split == 2 ? 0 : 1;
+            sp.split16 = split16;
+            for (int i = 0; i < 7; ++i) {
+                ResLayerP &a = sp.l[2 * i], &b = sp.l[2 * i + 1];
+                a.x = pp16[0];
+                a.y = pp16[1];
+                a.w = ts.d_w + ts.res1[i].w_off;
+                a.bias = ts.d_b + ts.res1[i].b_off;
+                a.psc = r.W(m->res[i].n2.scale);
+                a.psh = r.W(m->res[i].n2.shift);
+                a.res = nullptr;
+                a.ntaps = kResK[i];
+                a.affine = 1;
+                a.write_res = 0;
+                b.x = pp16[1];
+                b.y = pp16[0];
+                b.w = ts.d_w + ts.res2[i].w_off;
+                b.bias = ts.d_b + ts.res2[i].b_off;
+                b.res = xres;
+                b.ntaps = kResK[i];
+                if (i < 6) {
+                    b.psc = r.W(m->res[i + 1].n1.scale);
+                    b.psh = r.W(m->res[i + 1].n1.shift);
+                    b.affine = 1;
+                    b.write_res = 1;
+                } else {  // stack output as the 16-bit operand of the BiLSTM input-projection GEMM
+                    b.psc = b.psh = nullptr;
+                    b.affine = 0;
+                    b.write_res = 0;
+                }
+            }
+            r.rc = resstack_launch(sp, split, r.s);
+        }
+        for (int i = 0; i < 7 && r.go() && !fused_res; ++i) {
             TcIO io;
             io.x = pp16[0];
             io.x_split = split16;
