@@ -958,7 +958,19 @@ static int run_eqt(Runner &r, const float *x, float *y, Arena &ar) {
                     b.write_res = 0;
                 }
             }
-            r.rc = resstack_launch(sp, split, r.s);
+            // optional sub-chunks (the working set, 36 KB per window, then fits the 126 MB L2): no gain measured, the layer sync costs as much
+            static const int res_sub = getenv("VP_RES_SUB") ? atoi(getenv("VP_RES_SUB")) : 0;  // measured: 0 (whole chunk) 8.32 ms, 2048 8.35 ms, 1024 8.89 ms
+            const int64_t sub = res_sub > 0 ? (res_sub + 1) / 2 * 2 : B;  // even: tiles hold two sequences
+            for (int64_t b0 = 0; b0 < B && r.rc == VP_OK; b0 += sub) {
+                ResStackP sq = sp;
+                sq.NS = (int)std::min<int64_t>(sub, B - b0);
+                for (int l = 0; l < sq.n_layers; ++l) {
+                    sq.l[l].x += b0 * T * 64;
+                    sq.l[l].y += b0 * T * 64;
+                    if (sq.l[l].res) sq.l[l].res += b0 * T * 64;
+                }
+                r.rc = resstack_launch(sq, split, r.s);
+            }
         }
         for (int i = 0; i < 7 && r.go() && !fused_res; ++i) {
             TcIO io;
