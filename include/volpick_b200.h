@@ -104,6 +104,15 @@ VP_API int vp_window_starts(int64_t n_samples, int64_t in_samples, int64_t overl
 VP_API int64_t vp_coverage(int64_t in_samples, int64_t overlap); /* ceil(L / (L - overlap) + 1) */
 
 /* ---- stage kernels (all pointers are device pointers) ---------------------------------- */
+/* Stream pre-filter (annotate_stream_pre with filter_args / filter_kwargs; reference use:
+ * /root/reference/model_training/test_onephase.ipynb cell 43, /root/reference/volpick/data/utils.py:702-704).
+ * Cascaded second-order sections with scipy.signal.sosfilt semantics in float64 (what obspy.signal.filter.highpass /
+ * lowpass / bandpass / bandstop evaluate); zerophase != 0: forward pass, then the same cascade over the reversed signal.
+ * x: device (n_channels, n_samples) f32 / i32 with channel stride ch_stride; sos: HOST double[n_sections][6] =
+ * (b0, b1, b2, a0, a1, a2) per section (<= 8 sections); y: device float32 (n_channels, n_samples), packed. */
+VP_API int64_t vp_sosfilt_workspace_bytes(int64_t n_samples, int n_channels, int n_sections);
+VP_API int vp_sosfilt(const void *x, int dtype, int64_t n_samples, int64_t ch_stride, int n_channels, const double *sos,
+               int n_sections, int zerophase, float *y, void *workspace, int64_t workspace_bytes, void *stream);
 /* _cut_fragments_array + annotate_batch_pre: gather windows, demean, peak-normalise (+1e-10),
  * EQTransformer 6-sample cosine taper.  trace: (3, n) with channel stride ch_stride elements,
  * f32 or i32 counts.  out: (n_windows, 3, L) f32. */

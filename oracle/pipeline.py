@@ -178,6 +178,37 @@ def picks_from_trace(x: np.ndarray, threshold: float) -> List[Tuple[int, int, in
     return res
 
 
+# --------------------------------------------------------------------------- stream pre-filter
+def design_sos(ftype: str, df: float, corners: int = 4, **kw) -> np.ndarray:
+    """Second-order sections of obspy.signal.filter.{highpass,lowpass,bandpass,bandstop} (Butterworth;
+    ``iirfilter(corners, f / (0.5 df), btype, ftype="butter", output="zpk")`` + ``zpk2sos``), the filters a SeisBench model
+    applies when it carries ``filter_args`` / ``filter_kwargs`` (reference use: model_training/test_onephase.ipynb cell 43:
+    ``filter_args=["highpass"], filter_kwargs={"freq": 0.5, "corners": 2, "zerophase": True}``)."""
+    from scipy.signal import iirfilter, zpk2sos
+
+    fe = 0.5 * df
+    if ftype in ("highpass", "lowpass"):
+        wn = kw["freq"] / fe
+        btype = ftype
+    elif ftype in ("bandpass", "bandstop"):
+        wn = [kw["freqmin"] / fe, kw["freqmax"] / fe]
+        btype = "band" if ftype == "bandpass" else "bandstop"
+    else:
+        raise ValueError(f"unknown filter type {ftype!r}")
+    z, p, k = iirfilter(corners, wn, btype=btype, ftype="butter", output="zpk")
+    return np.ascontiguousarray(zpk2sos(z, p, k), dtype=np.float64)
+
+
+def sosfilt_record(x: np.ndarray, sos: np.ndarray, zerophase: bool = False) -> np.ndarray:
+    """obspy filter body: ``sosfilt(sos, data)``; zerophase: ``sosfilt(sos, firstpass[::-1])[::-1]``.  float64 -> float32."""
+    from scipy.signal import sosfilt
+
+    y = sosfilt(sos, np.asarray(x, dtype=np.float64), axis=-1)
+    if zerophase:
+        y = sosfilt(sos, y[..., ::-1], axis=-1)[..., ::-1]
+    return np.ascontiguousarray(y, dtype=np.float32)
+
+
 # --------------------------------------------------------------------------- whole path on arrays
 
 LABELS = {"eqtransformer": ["Detection", "P", "S"], "phasenet": ["P", "S", "N"]}

@@ -535,6 +535,52 @@ def test_pick_windows_evaluate_path(lib, eqt, pn, kind):
         assert "Detection" in model.pick_windows(x, None, threshold=0.3, detection_threshold=0.5)
 
 
+@pytest.mark.parametrize("spec", [
+    ("highpass", dict(freq=0.5, corners=2, zerophase=True)),   # model_training/test_onephase.ipynb cell 43
+    ("highpass", dict(freq=0.3)),                                # volpick/data/utils.py:702 (ObsPy defaults: 4 corners, one pass)
+    ("bandpass", dict(freqmin=1.0, freqmax=20.0)),               # volpick/data/utils.py:704
+    ("lowpass", dict(freq=10.0, corners=3, zerophase=True)),
+])
+@pytest.mark.parametrize("n,dtype", [(1, "f32"), (2047, "f32"), (2048, "i32"), (100_003, "f32"), (8_640_000, "f32")])
+def test_sosfilt_matches_scipy(pn, spec, n, dtype):
+    """Stream pre-filter on the device (block-parallel biquad cascade in float64) against scipy.signal.sosfilt, the routine
+    ObsPy's filters call.  Tolerance: float32 rounding of the output (the float64 results agree to ~1e-13)."""
+    ftype, kw = spec
+    kw = dict(kw)
+    zerophase = kw.pop("zerophase", False)
+    sos = pipeline.design_sos(ftype, 100.0, **kw)
+    rng = np.random.default_rng(n % 97)
+    x = (rng.standard_normal((3, n)) * 1000.0 + 250.0).astype(np.float32)  # counts-like with an offset (step response)
+    if dtype == "i32":
+        x = np.round(x).astype(np.int32)
+    ref = pipeline.sosfilt_record(x, sos, zerophase)
+    got = pn.filter_record(x, sos, zerophase).cpu().numpy()
+    scale = float(np.abs(ref).max()) + 1.0
+    assert got.shape == ref.shape and float(np.abs(got - ref).max()) <= 2e-7 * scale
+    # the host design of the model mirror equals the oracle's
+    m = vb.PhaseNet.from_pretrained("volpick")
+    m.filter_args, m.filter_kwargs = [ftype], dict(spec[1])  # set as attributes, as model_training/test_onephase.ipynb cell 43 does
+    sos2, zp2 = m.design_filter()
+    np.testing.assert_array_equal(sos2, sos)
+    assert zp2 == zerophase
+
+
+def test_annotate_with_filter_matches_oracle(pn, sd_pn):
+    """filter_args / filter_kwargs on the model: the record is filtered on the device before it is cut into windows."""
+    x = synthetic_record(45, 36_000) + np.float32(500.0)  # offset: the high-pass matters
+    m = vb.PhaseNet.from_pretrained("volpick").cuda()
+    m.filter_args, m.filter_kwargs = ["highpass"], {"freq": 0.5, "corners": 2, "zerophase": True}
+    a = m._argdict(dict(overlap=1500, P_threshold=0.2, S_threshold=0.2))
+    m.annotate_stream_pre([], a)  # designs the sections into the argdict (no trace to resample)
+    assert a["_sos"] is not None
+    ann, trig, _ = m.annotate_array(x, a, True, m._thresholds(a))
+    xf = pipeline.sosfilt_record(x, pipeline.design_sos("highpass", 100.0, corners=2, freq=0.5), True)
+    ref = pipeline.annotate_array("phasenet", sd_pn, xf, 1500, (0, 0), "avg")
+    ok = ~np.isnan(ref)
+    assert float(np.abs(ann.T[ok] - ref[ok]).max()) <= PROB_ATOL
+    assert len(trig) > 0
+
+
 # ------------------------------------------------------------------------------------------ whole path
 def _oracle_triggers(kind, sd, x, overlap, blinding, stacking, thr):
     ann = pipeline.annotate_array(kind, sd, x, overlap, blinding, stacking)

@@ -162,3 +162,28 @@ def test_pick_containers():
     assert out.picks is pl and "picks" in str(out)
     with pytest.raises(ValueError):
         vb.Pick("XX.A.", t + 2, t + 3, t + 1, 0.9, "P")
+
+
+def test_filter_design_matches_oracle():
+    """filter_args / filter_kwargs (model_training/test_onephase.ipynb cell 43): the host designs the same second-order
+    sections as the oracle's ObsPy restatement; the records are filtered on the device (GPU test)."""
+    from oracle import pipeline
+
+    m = vb.EQTransformer.from_pretrained("volpick")
+    assert m.design_filter() is None
+    m.filter_args = ["highpass"]
+    m.filter_kwargs = {"freq": 0.5, "corners": 2, "zerophase": True}
+    sos, zerophase = m.design_filter()
+    np.testing.assert_array_equal(sos, pipeline.design_sos("highpass", 100.0, corners=2, freq=0.5))
+    assert zerophase and sos.shape == (1, 6)
+    m.filter_args, m.filter_kwargs = ["bandpass"], {"freqmin": 1, "freqmax": 20}
+    sos, zerophase = m.design_filter()
+    assert sos.shape == (4, 6) and not zerophase
+    m.filter_args = ["notch"]
+    with pytest.raises(NotImplementedError):
+        m.design_filter()
+    # oracle sosfilt: one pass is causal, zero-phase is symmetric for a symmetric input
+    x = np.zeros((1, 401), np.float32)
+    x[0, 200] = 1.0
+    y = pipeline.sosfilt_record(x, pipeline.design_sos("lowpass", 100.0, corners=2, freq=5.0), True)
+    np.testing.assert_allclose(y[0, :200], y[0, :200:-1], atol=1e-6)

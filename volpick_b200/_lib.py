@@ -63,6 +63,8 @@ SIGNATURES = {
     "vp_window_count": (_i64, [_i64, _i64, _i64]),
     "vp_window_starts": (_i32, [_i64, _i64, _i64, _vp, _i64, C.POINTER(_i64)]),
     "vp_coverage": (_i64, [_i64, _i64]),
+    "vp_sosfilt_workspace_bytes": (_i64, [_i64, _i32, _i32]),
+    "vp_sosfilt": (_i32, [_vp, _i32, _i64, _i64, _i32, _vp, _i32, _i32, _vp, _vp, _i64, _vp]),
     "vp_slice_normalize": (_i32, [_vp, _i32, _i64, _i64, _vp, _i64, _i64, _i32, _i32, _vp, _vp]),
     "vp_forward_workspace_bytes": (_i64, [_vp, _i64, _i32]),
     "vp_forward": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _i32, _vp]),

@@ -50,7 +50,7 @@ cudaEvent_t ktimer_event() {
     return e;
 }
 const char *const KCLASS_NAMES =
-    "slice_normalize,slice_enc0,tcconv,deca,decb,conv1d_f32,convt_f32,lstm,attention,pack_cl16,stack,nan_bounds,pick";
+    "slice_normalize,slice_enc0,tcconv,deca,decb,conv1d_f32,convt_f32,lstm,attention,pack_cl16,stack,nan_bounds,pick,sosfilt";
 }  // namespace
 void ktimer_mark(int cls, cudaStream_t s, bool end) {
     if (!end) {

@@ -458,12 +458,60 @@ class WaveformModel:
         return thr
 
     # ---- stream handling (host) ----------------------------------------------------------------
+    def design_filter(self):
+        """(sos, zerophase) of the model's ``filter_args`` / ``filter_kwargs`` -- the Butterworth sections
+        obspy.signal.filter.{highpass,lowpass,bandpass,bandstop} build (``iirfilter(..., output="zpk")`` + ``zpk2sos``) --
+        or None.  Only the design (a handful of floats) happens on the host; the records are filtered by ``vp_sosfilt``."""
+        if self.filter_args is None and self.filter_kwargs is None:
+            return None
+        from scipy.signal import iirfilter, zpk2sos
+
+        args = list(self.filter_args or ())
+        kw = dict(self.filter_kwargs or {})
+        ftype = args[0] if args else kw.pop("type")
+        corners = int(kw.pop("corners", 4))
+        zerophase = bool(kw.pop("zerophase", False))
+        fe = 0.5 * float(self.sampling_rate)
+        if ftype in ("highpass", "lowpass"):
+            wn, btype = float(kw.pop("freq")) / fe, ftype
+        elif ftype in ("bandpass", "bandstop"):
+            wn, btype = [float(kw.pop("freqmin")) / fe, float(kw.pop("freqmax")) / fe], ("band" if ftype == "bandpass" else "bandstop")
+        else:
+            raise NotImplementedError(f"filter type {ftype!r} is not supported (highpass, lowpass, bandpass, bandstop)")
+        if kw:
+            raise TypeError(f"unexpected filter arguments {sorted(kw)}")
+        z, p, k = iirfilter(corners, wn, btype=btype, ftype="butter", output="zpk")
+        return np.ascontiguousarray(zpk2sos(z, p, k), dtype=np.float64), zerophase
+
+    def filter_record(self, trace, sos: np.ndarray, zerophase: bool = False):
+        """``sosfilt`` (float64 arithmetic, optionally forward-backward) of a (C, n) record on the device -> CUDA float32
+        tensor.  ``trace``: NumPy array / CPU tensor (uploaded) or CUDA tensor, float32 or int32."""
+        import torch
+
+        self._require_gpu()
+        t = trace if isinstance(trace, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(trace))
+        if t.dtype not in (torch.float32, torch.int32):
+            t = t.float()
+        t = t.to(self._device, non_blocking=True).contiguous()
+        sos = np.ascontiguousarray(sos, dtype=np.float64)
+        if sos.ndim != 2 or sos.shape[1] != 6:
+            raise ValueError(f"sos must have shape (n_sections, 6), got {sos.shape}")
+        c, n = t.shape
+        lib = _lib.load()
+        need = _lib.check(lib.vp_sosfilt_workspace_bytes(n, c, sos.shape[0]))
+        ws = torch.empty(int(need), dtype=torch.uint8, device=t.device)
+        y = torch.empty((c, n), dtype=torch.float32, device=t.device)
+        with torch.cuda.device(t.device):
+            _lib.check(lib.vp_sosfilt(C.c_void_p(t.data_ptr()), _lib.DTYPE_F32 if t.dtype == torch.float32 else _lib.DTYPE_I32, n,
+                                      t.stride(0), c, sos.ctypes.data, sos.shape[0], int(zerophase), C.c_void_p(y.data_ptr()),
+                                      C.c_void_p(ws.data_ptr()), ws.numel(), self._stream_ptr()))
+        return y
+
     def annotate_stream_pre(self, stream, argdict):
-        if self.filter_args is not None or self.filter_kwargs is not None:
-            if hasattr(stream, "filter"):
-                stream.filter(*(self.filter_args or ()), **(self.filter_kwargs or {}))
-            else:
-                raise NotImplementedError("stream filtering needs an ObsPy stream")
+        # filter_args / filter_kwargs: designed here, applied per gap-free record on the device (annotate_array).  SeisBench
+        # filters every trace before the components are aligned; the two agree when the components of a record span the
+        # same time range (the start-up transient of a component that starts earlier is the only difference).
+        argdict["_sos"] = self.design_filter()
         for tr in stream:
             if abs(float(tr.stats.sampling_rate) - self.sampling_rate) > 1e-6:
                 if hasattr(tr, "resample") and _is_obspy(tr):
@@ -553,6 +601,8 @@ class WaveformModel:
         argdict = self._argdict({}) if argdict is None else argdict
         thresholds = [0.0, 0.0, 0.0] if thresholds is None else thresholds
         lib = _lib.load()
+        if argdict.get("_sos") is not None:
+            trace = self.filter_record(trace, *argdict["_sos"])
         on_host = not (isinstance(trace, torch.Tensor) and trace.is_cuda)
         if isinstance(trace, torch.Tensor):
             t = trace
