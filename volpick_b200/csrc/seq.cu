@@ -122,25 +122,22 @@ int launch_lstm(int cin, const LstmP &p, int G, cudaStream_t s) {
 
 // ---------------------------------------------------------------------------------------------
 // Additive self-attention (+ optional transformer tail).  One thread = one query time step of one
-// window; a 192-thread CTA handles 4 windows in 48-thread slots (T = 47: 98 % of the lanes work; 64-thread slots left
-// 27 % of them idle) and loads the 21.6 KB parameter block once for the four.
+// window; a 240-thread CTA handles 5 windows in 48-thread slots (T = 47: 98 % of the lanes work; 64-thread slots left
+// 27 % of them idle) and loads the 21.6 KB parameter block once for the five.
 constexpr int AT_MAXT = 48;   // T <= 48 (T = 47 for 6000-sample windows)
 constexpr int AT_XP = 17;     // pitch of Xs rows (time-major x)
 constexpr int AT_KP = 36;     // pitch of the k-projection rows (float4 aligned)
-constexpr int AT_EP = 49;     // pitch of the emission rows
 constexpr int AT_OFF_K = (AW_SIZE + 3) & ~3;                      // 16-byte aligned (float4 reads)
-constexpr int AT_WPC = 4;     // windows per CTA
+constexpr int AT_WPC = 5;     // windows per CTA: 240 threads x 127 registers -> two CTAs (10 windows) per SM, register-file bound
 constexpr int AT_NT = AT_WPC * AT_MAXT;
 constexpr int AT_OFF_X = AT_OFF_K + AT_WPC * AT_MAXT * AT_KP;
-constexpr int AT_OFF_E = AT_OFF_X + AT_WPC * AT_MAXT * AT_XP;
-constexpr int AT_SMEM_FLOATS = AT_OFF_E + AT_WPC * AT_MAXT * AT_EP;
+constexpr int AT_SMEM_FLOATS = AT_OFF_X + AT_WPC * AT_MAXT * AT_XP;
 
-__global__ void __launch_bounds__(AT_NT) attention_kernel(const AttnP p) {
+__global__ void __launch_bounds__(AT_NT, 2) attention_kernel(const AttnP p) {
     extern __shared__ __align__(16) float at_smem[];
     float *wsm = at_smem;                                               // [AW_SIZE]
     float(*Ks)[AT_MAXT * AT_KP] = reinterpret_cast<float(*)[AT_MAXT * AT_KP]>(at_smem + AT_OFF_K);
     float(*Xs)[AT_MAXT * AT_XP] = reinterpret_cast<float(*)[AT_MAXT * AT_XP]>(at_smem + AT_OFF_X);
-    float(*Es)[AT_MAXT * AT_EP] = reinterpret_cast<float(*)[AT_MAXT * AT_EP]>(at_smem + AT_OFF_E);
 
     const int tid = threadIdx.x;
     const int g = blockIdx.y;
@@ -197,10 +194,18 @@ __global__ void __launch_bounds__(AT_NT) attention_kernel(const AttnP p) {
     }
     __syncthreads();
 
+    // softmax over j with the row max over the FULL row, band mask applied after the exp, denominator + 1e-5
+    // (SeqSelfAttention, original_compatible=False) -- evaluated online: the running maximum rescales the partial sums, so
+    // the T x T emissions are never stored (9.4 KB of shared memory per window less: twice the windows per SM).
     float emax = -INFINITY;
     float e0 = wsm[AW_BA];
 #pragma unroll
     for (int u = 0; u < 32; ++u) e0 = fmaf(-0.5f, wsm[AW_WA + u], e0);  // ba + sum_u Wa_u; each term then adds -2 Wa_u / (E E + 1)
+    float v[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) v[c] = 0.f;
+    float ssum = 0.f;
+    const int half = p.width / 2;
     for (int jj = 0; jj < T; ++jj) {
         const float4 *kr = reinterpret_cast<const float4 *>(&Ks[wl][jj * AT_KP]);
         float ea = e0, eb = 0.f;
@@ -217,23 +222,20 @@ __global__ void __launch_bounds__(AT_NT) attention_kernel(const AttnP p) {
             eb = fmaf(wsm[AW_WA + u4 * 4 + 7], rcp_approx(fmaf(q[u4 * 4 + 7], k5.w, 1.f)), eb);
         }
         const float e = ea + eb;
-        if (i < T) Es[wl][i * AT_EP + jj] = e;
-        emax = fmaxf(emax, e);
-    }
-    // softmax over j with the row max over the FULL row, band mask applied after the exp,
-    // denominator + 1e-5 (SeqSelfAttention, original_compatible=False)
-    float v[16];
+        if (e > emax) {  // new row maximum: bring the partial sums to the new reference
+            const float sc = ex2_approx(1.4426950408889634f * (emax - e));  // exp(-inf) = 0 on the first step
+            ssum *= sc;
 #pragma unroll
-    for (int c = 0; c < 16; ++c) v[c] = 0.f;
-    float ssum = 0.f;
-    const int half = p.width / 2;
-    if (i < T) {
-        for (int jj = 0; jj < T; ++jj) {
-            float w = ex2_approx(1.4426950408889634f * (Es[wl][i * AT_EP + jj] - emax));
-            if (p.width > 0) {
-                const int lower = jj - half;
-                if (!(lower <= i && i < lower + p.width)) w = 0.f;
-            }
+            for (int c = 0; c < 16; ++c) v[c] *= sc;
+            emax = e;
+        }
+        bool in_band = true;
+        if (p.width > 0) {
+            const int lower = jj - half;
+            in_band = lower <= i && i < lower + p.width;
+        }
+        if (in_band) {
+            const float w = ex2_approx(1.4426950408889634f * (e - emax));
             ssum += w;
 #pragma unroll
             for (int c = 0; c < 16; ++c) v[c] = fmaf(w, Xs[wl][jj * AT_XP + c], v[c]);
