@@ -51,12 +51,18 @@ CONFIGS = {
 
 
 def measured_peaks():
+    fallback = dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")  # B200_PROFILING.md
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
-        with open(path) as f:
-            p = json.load(f)
-        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sustained=p["bf16_tflops_sustained"], src="measured")
-    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+        try:
+            with open(path) as f:
+                p = json.load(f)
+            burst = float(p.get("bf16_tflops", p.get("bf16_tflops_burst", fallback["tf_burst"])))
+            return dict(hbm=float(p["hbm_gbs"]), tf_burst=burst, tf_sustained=float(p.get("bf16_tflops_sustained", burst)),
+                        src="measured")
+        except (OSError, ValueError, KeyError, TypeError):
+            pass
+    return fallback
 
 
 class ClockSampler(threading.Thread):
