@@ -202,6 +202,17 @@ VP_API int vp_annotate(vp_model *m, const void *trace, int trace_on_host, int dt
                 int64_t pick_capacity, int64_t *n_picks, int64_t *trim, void *workspace, int64_t workspace_bytes,
                 void *stream);
 
+/* The same in two halves, to keep several records in flight on different streams (H2D of record i + 1 under the compute
+ * of record i): vp_annotate_begin enqueues everything on `stream` and returns without waiting (host buffers must be pinned
+ * for that; workspace and buffers stay owned by the caller until _end); vp_annotate_end waits for the stream, copies the
+ * picks (HOST buffer, sorted by (label, s0)), fills n_picks / trim and releases the pending record -- also on error.
+ * Every begin must be matched by exactly one end on the same host thread. */
+typedef struct vp_pending vp_pending;
+VP_API int vp_annotate_begin(vp_model *m, const void *trace, int trace_on_host, int dtype, int64_t n_samples, int64_t ch_stride,
+                      const vp_annotate_params *p, float *annotation, int annotation_on_host, int64_t pick_capacity,
+                      void *workspace, int64_t workspace_bytes, void *stream, vp_pending **pending);
+VP_API int vp_annotate_end(vp_pending *pending, vp_trigger *picks, int64_t pick_capacity, int64_t *n_picks, int64_t *trim);
+
 #ifdef __cplusplus
 }
 #endif

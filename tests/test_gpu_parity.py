@@ -321,6 +321,29 @@ def test_annotate_chunked_two_lanes_bit_identical(eqt, pn, kind, on_host):
         assert np.array_equal(trigc, trig1) and np.array_equal(np.asarray(trimc), np.asarray(trim1))
 
 
+@pytest.mark.parametrize("kind", ["eqtransformer", "phasenet"])
+def test_annotate_async_two_records_in_flight(eqt, pn, kind):
+    """vp_annotate_begin / vp_annotate_end: two records in flight on two streams with their own workspaces give the results
+    of the blocking call, whatever the order the handles are collected in."""
+    model = eqt if kind == "eqtransformer" else pn
+    recs = [torch.from_numpy(synthetic_record(50 + i, 70_000 + 1000 * i)).pin_memory() for i in range(4)]
+    a = model._argdict(dict(overlap=model.in_samples - 600, P_threshold=0.2, S_threshold=0.2, chunk_windows=32))
+    thr = model._thresholds(a)
+    ref = [model.annotate_array(r, a, True, thr) for r in recs]
+    streams = [torch.cuda.Stream() for _ in range(2)]
+    wss = [torch.empty(model.annotate_workspace_bytes(80_000, a, True), dtype=torch.uint8, device="cuda") for _ in range(2)]
+    h01 = [model.annotate_array_async(recs[i], a, True, thr, stream=streams[i], workspace=wss[i]) for i in range(2)]
+    out = {1: h01[1].result(), 0: h01[0].result()}  # collected out of order
+    h23 = [model.annotate_array_async(recs[2 + i], a, True, thr, stream=streams[i], workspace=wss[i]) for i in range(2)]
+    out[2], out[3] = h23[0].result(), h23[1].result()
+    for i in range(4):
+        np.testing.assert_array_equal(out[i][0].view(np.uint32), ref[i][0].view(np.uint32))
+        assert np.array_equal(out[i][1], ref[i][1]) and np.array_equal(out[i][2], ref[i][2])
+    assert h01[0].result() is out[0]  # idempotent
+    with pytest.raises(ValueError, match="workspace too small"):
+        model.annotate_array_async(recs[0], a, True, thr, workspace=torch.empty(16, dtype=torch.uint8, device="cuda"))
+
+
 def test_golden_window_probabilities(eqt, pn, golden):
     for name, g in golden.items():
         model = eqt if str(g["kind"]) == "eqtransformer" else pn

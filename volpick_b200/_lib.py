@@ -83,6 +83,9 @@ SIGNATURES = {
     "vp_annotate_workspace_bytes": (_i64, [_vp, _i64, C.POINTER(AnnotateParams), _i32, _i64]),
     "vp_annotate": (_i32, [_vp, _vp, _i32, _i32, _i64, _i64, C.POINTER(AnnotateParams), _vp, _i32, _vp, _i64,
                            C.POINTER(_i64), _vp, _vp, _i64, _vp]),
+    "vp_annotate_begin": (_i32, [_vp, _vp, _i32, _i32, _i64, _i64, C.POINTER(AnnotateParams), _vp, _i32, _i64, _vp, _i64, _vp,
+                                 C.POINTER(_vp)]),
+    "vp_annotate_end": (_i32, [_vp, _vp, _i64, C.POINTER(_i64), _vp]),
 }
 
 _lib: Optional[C.CDLL] = None

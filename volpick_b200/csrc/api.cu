@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "common.cuh"
@@ -57,6 +58,34 @@ struct CopyPipe {
     cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
     int device = -1;
 };
+}  // namespace
+
+// One record in flight between vp_annotate_begin and vp_annotate_end.
+struct vp_pending {
+    cudaStream_t stream = nullptr;
+    const int64_t *d_count = nullptr, *d_bounds = nullptr;
+    const vp_trigger *d_picks = nullptr;
+    int64_t *h_pinned = nullptr;  // pinned: [0] pick count, [1..6] trim bounds
+    int64_t pred_len = 0, pick_capacity = 0;
+    bool empty = false;           // record shorter than one window
+};
+
+namespace {
+// pinned 64-byte result blocks, recycled per host thread (cudaHostAlloc costs tens of microseconds)
+thread_local std::vector<int64_t *> g_pinned_blocks;
+int64_t *pinned_block_get() {
+    if (!g_pinned_blocks.empty()) {
+        int64_t *b = g_pinned_blocks.back();
+        g_pinned_blocks.pop_back();
+        return b;
+    }
+    int64_t *b = nullptr;
+    return cudaHostAlloc((void **)&b, 8 * sizeof(int64_t), cudaHostAllocDefault) == cudaSuccess ? b : nullptr;
+}
+void pinned_block_put(int64_t *b) {
+    if (b) g_pinned_blocks.push_back(b);
+}
+
 CopyPipe *copy_pipe() {
     static thread_local CopyPipe pipes[16];
     int dev = 0;
@@ -141,15 +170,16 @@ extern "C" int64_t vp_annotate_workspace_bytes(const vp_model *m, int64_t n_samp
     return rc == VP_OK ? lo.total : rc;
 }
 
-extern "C" int vp_annotate(vp_model *m, const void *trace, int trace_on_host, int dtype, int64_t n, int64_t ch_stride,
-                           const vp_annotate_params *p, float *annotation, int annotation_on_host, vp_trigger *picks,
-                           int64_t pick_capacity, int64_t *n_picks, int64_t *trim, void *workspace,
-                           int64_t workspace_bytes, void *stream) {
-    VP_REQUIRE(m && trace && p && workspace && n_picks && trim, VP_ERR_ARG, "vp_annotate: null pointer");
+extern "C" int vp_annotate_begin(vp_model *m, const void *trace, int trace_on_host, int dtype, int64_t n, int64_t ch_stride,
+                                 const vp_annotate_params *p, float *annotation, int annotation_on_host,
+                                 int64_t pick_capacity, void *workspace, int64_t workspace_bytes, void *stream,
+                                 vp_pending **pending) {
+    VP_REQUIRE(m && trace && p && workspace && pending, VP_ERR_ARG, "vp_annotate: null pointer");
+    *pending = nullptr;
     VP_REQUIRE(dtype == VP_DTYPE_F32 || dtype == VP_DTYPE_I32, VP_ERR_ARG, "vp_annotate: unknown dtype %d", dtype);
     VP_REQUIRE(p->stacking == VP_STACK_AVG || p->stacking == VP_STACK_MAX, VP_ERR_ARG,
                "Stacking method %d unknown. Known methods are: 'avg' (0), 'max' (1)", p->stacking);
-    VP_REQUIRE(pick_capacity == 0 || picks, VP_ERR_ARG, "vp_annotate: pick buffer missing");
+    VP_REQUIRE(pick_capacity >= 0, VP_ERR_ARG, "vp_annotate: negative pick capacity");
     cudaStream_t s = (cudaStream_t)stream;
     const int kind = vp_model_kind(m);
     const int64_t L = vp_model_in_samples(m);
@@ -158,12 +188,33 @@ extern "C" int vp_annotate(vp_model *m, const void *trace, int trace_on_host, in
     if (rc != VP_OK) return rc;
     VP_REQUIRE(workspace_bytes >= lo.total, VP_ERR_WORKSPACE, "vp_annotate: workspace too small (%lld < %lld bytes)",
                (long long)workspace_bytes, (long long)lo.total);
-    *n_picks = 0;
-    for (int i = 0; i < 3; ++i) {
-        trim[2 * i] = lo.pred_len;
-        trim[2 * i + 1] = -1;
+    vp_pending *pd = new vp_pending();
+    pd->stream = s;
+    pd->pred_len = lo.pred_len;
+    pd->pick_capacity = pick_capacity;
+    pd->h_pinned = pinned_block_get();
+    if (pd->h_pinned == nullptr) {
+        delete pd;
+        set_error("vp_annotate: cannot allocate the pinned result block");
+        return VP_ERR_CUDA;
     }
-    if (lo.nwin == 0) return VP_OK;  // record shorter than one window: empty output (SeisBench warns)
+    struct Guard {  // the pending record is released on every error path
+        vp_pending *&pd;
+        bool armed = true;
+        ~Guard() {
+            if (armed && pd) {
+                pinned_block_put(pd->h_pinned);
+                delete pd;
+                pd = nullptr;
+            }
+        }
+    } guard{pd};
+    if (lo.nwin == 0) {  // record shorter than one window: empty output (SeisBench warns)
+        pd->empty = true;
+        guard.armed = false;
+        *pending = pd;
+        return VP_OK;
+    }
 
     char *ws = (char *)workspace;
     const void *d_trace = trace;
@@ -271,22 +322,61 @@ extern "C" int vp_annotate(vp_model *m, const void *trace, int trace_on_host, in
         rc = vp_pick_labels(d_annot, 3, lo.pred_len, thr_on, thr_off, d_picks, pick_capacity, d_count, d_bounds, s);
         if (rc != VP_OK) return rc;
     }
-    int64_t h_count = 0;
-    VP_CUDA_CHECK(cudaMemcpyAsync(&h_count, d_count, 8, cudaMemcpyDeviceToHost, s));
-    VP_CUDA_CHECK(cudaMemcpyAsync(trim, d_bounds, 6 * 8, cudaMemcpyDeviceToHost, s));
+    VP_CUDA_CHECK(cudaMemcpyAsync(pd->h_pinned, d_count, 8, cudaMemcpyDeviceToHost, s));
+    VP_CUDA_CHECK(cudaMemcpyAsync(pd->h_pinned + 1, d_bounds, 6 * 8, cudaMemcpyDeviceToHost, s));
     if (annotation)
         VP_CUDA_CHECK(cudaMemcpyAsync(annotation, d_annot, 3 * lo.pred_len * 4,
                                       annotation_on_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, s));
-    VP_CUDA_CHECK(cudaStreamSynchronize(s));
+    pd->d_count = d_count;
+    pd->d_bounds = d_bounds;
+    pd->d_picks = d_picks;
+    guard.armed = false;
+    *pending = pd;
+    return VP_OK;
+}
+
+extern "C" int vp_annotate_end(vp_pending *pd, vp_trigger *picks, int64_t pick_capacity, int64_t *n_picks, int64_t *trim) {
+    VP_REQUIRE(pd && n_picks && trim, VP_ERR_ARG, "vp_annotate_end: null pointer");
+    struct Release {
+        vp_pending *pd;
+        ~Release() {
+            pinned_block_put(pd->h_pinned);
+            delete pd;
+        }
+    } release{pd};
+    *n_picks = 0;
+    for (int i = 0; i < 3; ++i) {
+        trim[2 * i] = pd->pred_len;
+        trim[2 * i + 1] = -1;
+    }
+    if (pd->empty) return VP_OK;
+    VP_CUDA_CHECK(cudaStreamSynchronize(pd->stream));
+    const int64_t h_count = pd->h_pinned[0];
+    std::memcpy(trim, pd->h_pinned + 1, 6 * sizeof(int64_t));
     *n_picks = h_count;
-    VP_REQUIRE(h_count <= pick_capacity, VP_ERR_CAPACITY, "vp_annotate: %lld picks exceed the pick capacity %lld",
-               (long long)h_count, (long long)pick_capacity);
+    const int64_t cap = std::min(pick_capacity, pd->pick_capacity);
+    VP_REQUIRE(h_count <= cap, VP_ERR_CAPACITY, "vp_annotate: %lld picks exceed the pick capacity %lld", (long long)h_count,
+               (long long)cap);
     if (h_count > 0) {
-        VP_CUDA_CHECK(cudaMemcpyAsync(picks, d_picks, (size_t)h_count * sizeof(vp_trigger), cudaMemcpyDeviceToHost, s));
-        VP_CUDA_CHECK(cudaStreamSynchronize(s));
+        VP_REQUIRE(picks != nullptr, VP_ERR_ARG, "vp_annotate: pick buffer missing");
+        VP_CUDA_CHECK(cudaMemcpyAsync(picks, pd->d_picks, (size_t)h_count * sizeof(vp_trigger), cudaMemcpyDeviceToHost, pd->stream));
+        VP_CUDA_CHECK(cudaStreamSynchronize(pd->stream));
         std::sort(picks, picks + h_count, [](const vp_trigger &a, const vp_trigger &b) {
             return a.label != b.label ? a.label < b.label : a.s0 < b.s0;
         });
     }
     return VP_OK;
+}
+
+extern "C" int vp_annotate(vp_model *m, const void *trace, int trace_on_host, int dtype, int64_t n, int64_t ch_stride,
+                           const vp_annotate_params *p, float *annotation, int annotation_on_host, vp_trigger *picks,
+                           int64_t pick_capacity, int64_t *n_picks, int64_t *trim, void *workspace,
+                           int64_t workspace_bytes, void *stream) {
+    VP_REQUIRE(n_picks && trim, VP_ERR_ARG, "vp_annotate: null pointer");
+    VP_REQUIRE(pick_capacity == 0 || picks, VP_ERR_ARG, "vp_annotate: pick buffer missing");
+    vp_pending *pd = nullptr;
+    int rc = vp_annotate_begin(m, trace, trace_on_host, dtype, n, ch_stride, p, annotation, annotation_on_host, pick_capacity,
+                               workspace, workspace_bytes, stream, &pd);
+    if (rc != VP_OK) return rc;
+    return vp_annotate_end(pd, picks, pick_capacity, n_picks, trim);
 }

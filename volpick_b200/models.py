@@ -140,6 +140,38 @@ def _ns(t) -> int:
     return int(t.ns)
 
 
+class _PendingRecord:
+    """A record between ``vp_annotate_begin`` and ``vp_annotate_end``; keeps the host buffers alive until ``result()``."""
+
+    def __init__(self, model, pending, annotation, pick_capacity, keep):
+        self._model, self._pending, self._annotation, self._cap, self._keep = model, pending, annotation, pick_capacity, keep
+        self._result = None
+
+    def result(self):
+        if self._result is None:
+            import torch
+
+            lib = _lib.load()
+            trig = (_lib.Trigger * self._cap)()
+            n_picks = C.c_int64(0)
+            trim = np.zeros(6, dtype=np.int64)
+            pending, self._pending = self._pending, None
+            with torch.cuda.device(self._model._device_index):
+                _lib.check(lib.vp_annotate_end(pending, C.cast(trig, C.c_void_p), self._cap, C.byref(n_picks),
+                                               C.c_void_p(trim.ctypes.data)))
+            triggers = np.frombuffer(trig, dtype=_lib.TRIGGER_DTYPE, count=n_picks.value).copy()
+            self._result = (self._annotation, triggers, trim.reshape(3, 2))
+            self._keep = None
+        return self._result
+
+    def __del__(self):  # never leave a begin without its end
+        if getattr(self, "_pending", None) is not None:
+            try:
+                self.result()
+            except Exception:  # noqa: BLE001
+                pass
+
+
 class WaveformModel:
     """Common machinery; see the module docstring.  Sub-classes: ``EQTransformer``, ``PhaseNet``."""
 
@@ -595,6 +627,16 @@ class WaveformModel:
         ``annotation`` a float32 NumPy array (3, pred_len) or None, ``triggers`` a structured
         NumPy array (s0, s1, s_peak, value, label) sorted by (label, s0), ``trim`` int64 (3, 2).
         """
+        return self.annotate_array_async(trace, argdict, want_annotation, thresholds, pick_capacity).result()
+
+    def annotate_array_async(self, trace, argdict: Optional[Dict[str, Any]] = None, want_annotation: bool = True,
+                             thresholds: Optional[Sequence[float]] = None, pick_capacity: int = 1 << 16, stream=None,
+                             workspace=None):
+        """``annotate_array`` in two halves (``vp_annotate_begin`` / ``vp_annotate_end``): enqueues the whole record on
+        ``stream`` (a ``torch.cuda.Stream``; default: the current one) and returns a handle whose ``result()`` waits and
+        returns ``(annotation, triggers, trim)``.  Records in flight at the same time need their own ``workspace`` (uint8
+        CUDA tensor of ``annotate_workspace_bytes`` bytes) and stream; a pinned host record is then copied while the
+        previous record computes."""
         import torch
 
         self._require_gpu()
@@ -626,21 +668,28 @@ class WaveformModel:
             raise ValueError(f"expected a (3, n) record, got {tuple(keep.shape)}")
         params = self._params(argdict, thresholds)
         need = _lib.check(lib.vp_annotate_workspace_bytes(self._handle, n, C.byref(params), int(on_host), pick_capacity))
-        ws = self._get_workspace(need)
+        if workspace is None:
+            ws = self._get_workspace(need)
+        else:
+            ws = workspace
+            if ws.numel() < need:
+                raise ValueError(f"workspace too small: {ws.numel()} < {need} bytes")
         pred_len = n if lib.vp_window_count(n, self.in_samples, params.overlap) > 0 else 0
         annotation = np.empty((3, pred_len), dtype=np.float32) if want_annotation else None
-        trig = (_lib.Trigger * pick_capacity)()
-        n_picks = C.c_int64(0)
-        trim = np.zeros(6, dtype=np.int64)
+        pending = C.c_void_p(None)
+        sptr = C.c_void_p(stream.cuda_stream) if stream is not None else self._stream_ptr()
         with torch.cuda.device(self._device_index):
-            _lib.check(lib.vp_annotate(
+            _lib.check(lib.vp_annotate_begin(
                 self._handle, C.c_void_p(ptr), int(on_host), dtype, n, ch_stride, C.byref(params),
-                C.c_void_p(annotation.ctypes.data) if want_annotation and pred_len else None, 1,
-                C.cast(trig, C.c_void_p), pick_capacity, C.byref(n_picks), C.c_void_p(trim.ctypes.data),
-                C.c_void_p(ws.data_ptr()), ws.numel(), self._stream_ptr()))
-        trig_dtype = np.dtype([("s0", "<i8"), ("s1", "<i8"), ("s_peak", "<i8"), ("value", "<f4"), ("label", "<i4")])
-        triggers = np.frombuffer(trig, dtype=trig_dtype, count=n_picks.value).copy()
-        return annotation, triggers, trim.reshape(3, 2)
+                C.c_void_p(annotation.ctypes.data) if want_annotation and pred_len else None, 1, pick_capacity,
+                C.c_void_p(ws.data_ptr()), ws.numel(), sptr, C.byref(pending)))
+        return _PendingRecord(self, pending, annotation, pick_capacity, (keep, ws, params))
+
+    def annotate_workspace_bytes(self, n_samples: int, argdict: Optional[Dict[str, Any]] = None, on_host: bool = True,
+                                 pick_capacity: int = 1 << 16) -> int:
+        argdict = self._argdict({}) if argdict is None else argdict
+        params = self._params(argdict, [0.0, 0.0, 0.0])
+        return int(_lib.check(_lib.load().vp_annotate_workspace_bytes(self._handle, n_samples, C.byref(params), int(on_host), pick_capacity)))
 
     def _run(self, stream, kwargs, want_annotation: bool, want_picks: bool):
         self._require_gpu()
