@@ -677,6 +677,8 @@ class WaveformModel:
         pred_len = n if lib.vp_window_count(n, self.in_samples, params.overlap) > 0 else 0
         annotation = np.empty((3, pred_len), dtype=np.float32) if want_annotation else None
         pending = C.c_void_p(None)
+        if stream is not None:  # whatever produced the record (e.g. the pre-filter) ran on the current stream
+            stream.wait_stream(torch.cuda.current_stream(self._device_index))
         sptr = C.c_void_p(stream.cuda_stream) if stream is not None else self._stream_ptr()
         with torch.cuda.device(self._device_index):
             _lib.check(lib.vp_annotate_begin(
@@ -712,6 +714,39 @@ class WaveformModel:
         rate = self.sampling_rate
         out_traces = []
         picks, detections = [], []
+        import torch
+        from collections import deque
+
+        # two records in flight (vp_annotate_begin / _end): record i + 1 is uploaded and started while record i finishes
+        if getattr(self, "_slots", None) is None or self._slots[0] != self._device_index:
+            self._slots = (self._device_index, [torch.cuda.Stream(self._device_index) for _ in range(2)], [None, None])
+        slot_streams, slot_ws = self._slots[1], self._slots[2]
+        in_flight = deque()
+
+        def collect():
+            (s0, trace_id, t0), handle = in_flight.popleft()
+            annotation, triggers, trim = handle.result()
+            for li, label in enumerate(self.labels):
+                first, last = int(trim[li, 0]), int(trim[li, 1])
+                if last < first:
+                    continue
+                tstart = t0 + first / rate  # _predictions_to_stream: t0 + f / rate
+                if want_annotation:
+                    out_traces.append(TraceT(annotation[li, first : last + 1].copy(), {
+                        "starttime": tstart, "sampling_rate": rate, "network": s0.network,
+                        "station": s0.station, "location": s0.location, "channel": f"{self.name}_{label}"}))
+                if want_picks:
+                    for tg in triggers[triggers["label"] == li]:
+                        # picks_from_annotations: starttime + times()[idx], times() = arange(npts) / rate
+                        ts = tstart + float((int(tg["s0"]) - first) / rate)
+                        te = tstart + float((int(tg["s1"]) - first) / rate)
+                        if label == "Detection":
+                            detections.append(Detection(trace_id, ts, te, float(tg["value"])))
+                        else:
+                            tp = tstart + float((int(tg["s_peak"]) - first) / rate)
+                            picks.append(Pick(trace_id, ts, te, tp, float(tg["value"]), label))
+
+        n_rec = 0
         for key in groups:
             trs = groups[key]
             s0 = trs[0].stats
@@ -721,26 +756,19 @@ class WaveformModel:
                     logger.warning("Parts of the input stream consist of fragments shorter than the number of "
                                    "input samples. Output might be empty.")
                     continue
-                annotation, triggers, trim = self.annotate_array(arr, argdict, want_annotation, thresholds)
-                for li, label in enumerate(self.labels):
-                    first, last = int(trim[li, 0]), int(trim[li, 1])
-                    if last < first:
-                        continue
-                    tstart = t0 + first / rate  # _predictions_to_stream: t0 + f / rate
-                    if want_annotation:
-                        out_traces.append(TraceT(annotation[li, first : last + 1].copy(), {
-                            "starttime": tstart, "sampling_rate": rate, "network": s0.network,
-                            "station": s0.station, "location": s0.location, "channel": f"{self.name}_{label}"}))
-                    if want_picks:
-                        for tg in triggers[triggers["label"] == li]:
-                            # picks_from_annotations: starttime + times()[idx], times() = arange(npts) / rate
-                            ts = tstart + float((int(tg["s0"]) - first) / rate)
-                            te = tstart + float((int(tg["s1"]) - first) / rate)
-                            if label == "Detection":
-                                detections.append(Detection(trace_id, ts, te, float(tg["value"])))
-                            else:
-                                tp = tstart + float((int(tg["s_peak"]) - first) / rate)
-                                picks.append(Pick(trace_id, ts, te, tp, float(tg["value"]), label))
+                k = n_rec & 1
+                n_rec += 1
+                need = self.annotate_workspace_bytes(arr.shape[1], argdict, True)
+                if slot_ws[k] is None or slot_ws[k].numel() < need:
+                    slot_ws[k] = None
+                    slot_ws[k] = torch.empty(need, dtype=torch.uint8, device=self._device)
+                handle = self.annotate_array_async(arr, argdict, want_annotation, thresholds, stream=slot_streams[k],
+                                                   workspace=slot_ws[k])
+                in_flight.append(((s0, trace_id, t0), handle))
+                if len(in_flight) == 2:
+                    collect()
+        while in_flight:
+            collect()
         return StreamT(out_traces), PickList(sorted(picks)), DetectionList(sorted(detections))
 
     def annotate(self, stream, copy: bool = True, **kwargs):
