@@ -40,6 +40,15 @@ extern "C" int vp_window_starts(int64_t n, int64_t L, int64_t overlap, int64_t *
 
 namespace {
 
+// device twin of vp_window_starts: starts[i] = i * stride for the regular windows, the last entry is the tail window n - L
+// when the regular grid does not end at the record end (cnt regular + optional tail == n_win)
+__global__ void window_starts_kernel(int64_t *__restrict__ starts, int64_t n_win, int64_t stride, int64_t tail) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_win) return;
+    const int64_t v = i * stride;
+    starts[i] = v <= tail ? v : tail;
+}
+
 struct Layout {
     int64_t off_trace, off_starts, off_x, off_fwd, off_y, off_annot, off_bounds, off_count, off_picks, off_scratch;
     int64_t off_x2, off_fwd2;  // extra forward lanes (chunk c runs on lane c % n_lanes): MAX_LANES - 1 slots of x_bytes / fwd_bytes
@@ -254,8 +263,9 @@ extern "C" int vp_annotate_begin(vp_model *m, const void *trace, int trace_on_ho
         int64_t cnt = 0;
         rc = vp_window_starts(n, L, p->overlap, h_starts.data(), lo.nwin, &cnt);
         if (rc != VP_OK) return rc;
-        // pageable source: the runtime stages the copy before the call returns, h_starts may be reused freely
-        VP_CUDA_CHECK(cudaMemcpyAsync(d_starts, h_starts.data(), (size_t)lo.nwin * 8, cudaMemcpyHostToDevice, s));
+        // the device copy is generated in place (same integer rule): no pageable H2D copy on the path of a record
+        window_starts_kernel<<<(unsigned)((lo.nwin + 255) / 256), 256, 0, s>>>(d_starts, lo.nwin, L - p->overlap, n - L);
+        VP_LAUNCH_CHECK();
     }
     float *d_y = (float *)(ws + lo.off_y);
     CopyPipe *lanes = lo.n_lanes > 1 ? copy_pipe() : nullptr;
