@@ -25,7 +25,8 @@ struct FzLayer {
     int n_tiles;   // M tiles per work item
     int n_terms;   // MMAs per tile (without the bias MMA)
     int in_off;    // input buffer: byte offset inside the pipeline's arena (layer 0: slot 0)
-    int in_rows;   // rows per input plane (= plane pitch in 16-byte units)
+    int in_rows;   // rows per input plane
+    int in_pitch;  // plane pitch of the input buffer in 16-byte rows (>= in_rows; layer 0: padded for conflict-free cp.async stores)
     int out_off;   // output buffer byte offset inside the pipeline's arena
     int out_rows;  // rows per output plane / valid rows of the fp32 planar buffer
     int out_rp;    // fp32 planar output: row pitch in floats

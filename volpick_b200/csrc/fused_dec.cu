@@ -199,7 +199,7 @@ __device__ __forceinline__ void fz_issue_layer(const FzDecB &p, int pp, int slot
     const uint32_t idesc = umma_idesc(NOUT, SPLIT == 2 ? 0 : 1);
     const uint32_t in16 = arena16 + ((uint32_t)(L.in_off + (l == 0 ? slot * p.in_slot_bytes : 0)) >> 4) + (uint32_t)L.a_row0;
     const uint32_t w16 = sB16 + ((uint32_t)L.w_off >> 4);
-    const uint32_t in_rows = (uint32_t)L.in_rows;
+    const uint32_t in_rows = (uint32_t)L.in_pitch;
     for (int t = 0; t < L.n_tiles; ++t, ++i) {
         const uint32_t buf = i & (FZ_NBUF - 1);
         mbar_wait(&done_bar[pp][buf], ((i / FZ_NBUF) & 1) ^ 1);  // accumulator free: step i - NBUF retired
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) decb_kernel(const __grid_consta
     if (warp < FZ_NPIPE) {
         // ================= loaders: input rows of the pipeline's next work item (zero rows outside the sequence)
         const int pp = warp;
-        const int R0 = p.L[0].in_rows, c8 = p.L[0].cin8;
+        const int R0 = p.L[0].in_rows, PT = p.L[0].in_pitch, c8 = p.L[0].cin8;
         const int per_split = R0 * c8;
         const uint16_t *xg = p.x + (long long)g * p.x_gs;
         int n = 0;
@@ -282,6 +282,8 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) decb_kernel(const __grid_consta
             const int b = item / p.tiles_per_seq, j = item - b * p.tiles_per_seq;
             const int row_base = p.c0 * j + p.row_off0 + p.in_lo0;
             const uint32_t dst0 = sbase + pp * p.pipe_stride + p.L[0].in_off + slot * p.in_slot_bytes;
+            // consecutive lanes copy the planes of one 64-byte global row, then the next row (coalesced); the plane pitch PT
+            // is 2 (mod 4) rows, so 8 lanes (4 planes x 2 rows) store to 8 different 16-byte bank groups
             for (int idx = lane; idx < ((p.dbg & 8) ? 0 : per_split); idx += 32) {
                 const int pl = idx % c8, r = idx / c8;
                 const int gr = row_base + r;
@@ -289,7 +291,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) decb_kernel(const __grid_consta
                 const uint16_t *src = ok ? xg + ((long long)b * p.T0 + gr) * p.cin0 + pl * 8 : xg;
 #pragma unroll
                 for (int s = 0; s < SPLIT; ++s)
-                    cp_async16(dst0 + (uint32_t)(((s * c8 + pl) * R0 + r) * 16), ok ? src + (long long)s * p.x_split : xg, ok ? 16u : 0u);
+                    cp_async16(dst0 + (uint32_t)(((s * c8 + pl) * PT + r) * 16), ok ? src + (long long)s * p.x_split : xg, ok ? 16u : 0u);
             }
             cp_async_mbar_arrive_noinc(&in_full[pp][slot]);
         }
@@ -407,10 +409,17 @@ int decb_build(DecBPlan &plan, const TcLayer *dec, int split, int m, const float
     static_assert(FZ_DEC_STACK[1] == FZ_DEC_STACK[2] && !FZ_DEC_STACK[0], "epilogue dispatch in decb_kernel");
     // shared memory: per pipeline { in[2] | X | Y }, then the weight blob
     const int esz = 16 * split;  // bytes per (row, plane)
+    // input slot: plane pitch 2 (mod 4) rows for the 4-plane (32-channel) input, odd for 8 planes (see the loader)
+    int pitch0 = hi[0] - lo[0];
+    {
+        const int c8 = dec[3].cin / 8;
+        if (c8 == 4) while ((pitch0 & 3) != 2) ++pitch0;
+        else if (c8 >= 8) pitch0 |= 1;
+    }
     auto lvl_bytes = [&](int k) {
         if (k == NL) return (size_t)8 * (size_t)(((hi[k] - lo[k]) + 12 + 3) & ~3) * 4;
         const int ch = (k == 0) ? dec[3].cin : dec[3 + k - 1].cout;
-        return (size_t)(hi[k] - lo[k]) * (ch / 8) * esz;
+        return (size_t)(k == 0 ? pitch0 : hi[k] - lo[k]) * (ch / 8) * esz;
     };
     auto up128 = [](size_t v) { return (v + 127) & ~(size_t)127; };
     p.in_slot_bytes = (int)up128(lvl_bytes(0));
@@ -446,6 +455,7 @@ int decb_build(DecBPlan &plan, const TcLayer *dec, int split, int m, const float
         L.n_tiles = n_tiles[l];
         L.in_off = (int)lvl_off[l];
         L.in_rows = hi[l] - lo[l];
+        L.in_pitch = (l == 0) ? pitch0 : L.in_rows;
         L.out_off = (int)lvl_off[l + 1];
         L.out_rows = hi[l + 1] - lo[l + 1];
         L.out_rp = (l == NL - 1) ? ((L.out_rows + 12 + 3) & ~3) : 0;

@@ -27,6 +27,10 @@ namespace vp {
 
 constexpr int DA_T0 = 94, DA_T1 = 188, DA_T2 = 375;
 constexpr int DA_IN_ROWS = DA_T0 + 2, DA_MID_ROWS = DA_T1 + 2;  // one zero row before and after the sequence
+// plane pitch of the input slot in 16-byte rows, ODD: the loader's 8 lanes that copy the 8 planes of one 128-byte global
+// row then hit 8 different 16-byte bank groups (with the even pitch 96 the cp.async stores serialised 8 ways: ncu counted
+// 26 shared-memory wavefronts per LDGSTS instead of 4)
+constexpr int DA_IN_PITCH = DA_IN_ROWS + 1;
 constexpr int DA_EW = 16;
 constexpr int DA_THREADS = 32 * (2 + DA_EW);
 
@@ -45,7 +49,7 @@ __global__ void __launch_bounds__(DA_THREADS, 1) deca_kernel(const __grid_consta
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = blockIdx.y;
     const uint32_t sbase = smem_u32(da_smem);
-    constexpr uint32_t IN_BYTES = SPLIT * 8 * DA_IN_ROWS * 16, MID_BYTES = SPLIT * 8 * DA_MID_ROWS * 16;
+    constexpr uint32_t IN_BYTES = SPLIT * 8 * DA_IN_PITCH * 16, MID_BYTES = SPLIT * 8 * DA_MID_ROWS * 16;
     uint8_t *s_in = da_smem, *s_mid = da_smem + IN_BYTES;
     const float *s_bias = reinterpret_cast<const float *>(da_smem + p.bias_off);  // [128] dec1, [64] dec2
 
@@ -65,7 +69,7 @@ __global__ void __launch_bounds__(DA_THREADS, 1) deca_kernel(const __grid_consta
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
         for (int idx = tid; idx < SPLIT * 8 * 2; idx += DA_THREADS) {
             const int pl = idx >> 1, e = idx & 1;
-            *reinterpret_cast<uint4 *>(s_in + ((size_t)pl * DA_IN_ROWS + (e ? DA_IN_ROWS - 1 : 0)) * 16) = z;
+            *reinterpret_cast<uint4 *>(s_in + ((size_t)pl * DA_IN_PITCH + (e ? DA_IN_ROWS - 1 : 0)) * 16) = z;
             *reinterpret_cast<uint4 *>(s_mid + ((size_t)pl * DA_MID_ROWS + (e ? DA_MID_ROWS - 1 : 0)) * 16) = z;
         }
     }
@@ -88,7 +92,7 @@ __global__ void __launch_bounds__(DA_THREADS, 1) deca_kernel(const __grid_consta
                 const int pl = idx & 7, t = idx >> 3;
 #pragma unroll
                 for (int s = 0; s < SPLIT; ++s)
-                    cp_async16(sbase + (uint32_t)(((s * 8 + pl) * DA_IN_ROWS + 1 + t) * 16), src0 + (long long)s * p.x_split + t * 64 + pl * 8, 16u);
+                    cp_async16(sbase + (uint32_t)(((s * 8 + pl) * DA_IN_PITCH + 1 + t) * 16), src0 + (long long)s * p.x_split + t * 64 + pl * 8, 16u);
             }
             cp_async_mbar_arrive_noinc(&in_full);
         }
@@ -107,7 +111,7 @@ __global__ void __launch_bounds__(DA_THREADS, 1) deca_kernel(const __grid_consta
             fence_proxy_async();
             tc_fence_after();
             if (elect_one()) {
-                umma_conv_tile<128, SPLIT, 3, 4>(tmem_base, in16, DA_IN_ROWS, w1, umma_idesc(128, fmt), 0u);
+                umma_conv_tile<128, SPLIT, 3, 4>(tmem_base, in16, DA_IN_PITCH, w1, umma_idesc(128, fmt), 0u);
                 umma_commit(&acc_full[0]);
                 umma_commit(&in_free);
             }
@@ -269,7 +273,7 @@ int deca_build(DecAPlan &plan, const TcLayer &dec1, const TcLayer &dec2p, int sp
                VP_ERR_UNSUPPORTED, "deca: decoder.convs.2 is not the compiled (N 64, 3 taps, 4 pairs) polyphase layer");
     VP_REQUIRE(!dec1.blocks.empty() && !dec2p.blocks.empty(), VP_ERR_ARG, "deca: host weight blocks are gone");
     auto up128 = [](size_t v) { return (v + 127) & ~(size_t)127; };
-    const size_t in_bytes = (size_t)split * 8 * DA_IN_ROWS * 16, mid_bytes = (size_t)split * 8 * DA_MID_ROWS * 16;
+    const size_t in_bytes = (size_t)split * 8 * DA_IN_PITCH * 16, mid_bytes = (size_t)split * 8 * DA_MID_ROWS * 16;
     const size_t w1_bytes = up128((size_t)dec1.n_blocks * split * 2 * 128 * 16), w2_bytes = up128((size_t)dec2p.n_blocks * split * 2 * 64 * 16);
     const size_t bias_bytes = up128((128 + 64) * sizeof(float));
     p.blob_off = (int)up128(in_bytes + mid_bytes);

@@ -26,57 +26,82 @@ constexpr int RS_EW = 16;                       // epilogue warps
 constexpr int RS_THREADS = 32 * (RS_EW + 4);    // + issuer + 3 producer warps
 constexpr int RS_PRODUCERS = 96;
 constexpr int RS_ROWS = 130;                    // staged rows per tile: in-tile rows -1 .. 128
+constexpr int RS_PITCH = 131;                   // plane pitch in 16-byte rows, ODD (see the producers)
 constexpr int RS_NST = 3;                       // A-tile ring depth
 constexpr int RS_N = 64;                        // channels in = out = MMA N
 constexpr int RS_NACC = 4;                      // TMEM accumulator buffers (the issuer runs up to 4 tiles ahead of the epilogue)
 
+// The fields of a layer the epilogue needs, copied to registers once per layer (indexing the kernel-parameter array with
+// the run-time layer number inside the tile loop costs a constant load with a long scoreboard wait per use).
+struct RsEpi {
+    uint16_t *y;
+    float *res;
+    int affine, write_res;
+};
+
+// 256-bit global accesses (sm_100: LDG / STG .256).  The epilogue's traffic is 16-byte pieces per lane at a 128 / 256-byte
+// lane stride: the L1 data pipe (58 %) and the L2 tag stage (54 %, 1.2 sectors per request) were the busiest units of the
+// kernel, i.e. it is bound by the NUMBER of memory transactions.  A thread now moves whole 32-byte sectors.
+__device__ __forceinline__ void ld_global_256(const float *p, float4 &a, float4 &b) {
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p)
+                 : "memory");
+}
+__device__ __forceinline__ void st_global_256(float *p, const float *v) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]),
+                 "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void st_global_256(uint16_t *p, const uint4 &a, const uint4 &b) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y),
+                 "r"(b.z), "r"(b.w)
+                 : "memory");
+}
+
+// One 16-column round of a row: accumulator + bias (+ residual, stored back) -> [BN + ReLU] -> 16-bit split store.
 template <int SPLIT>
-__device__ __forceinline__ void rs_epilogue(const ResLayerP &L, int T, int64_t y_split, uint32_t trow, int half, int seq, int srow,
+__device__ __forceinline__ void rs_epilogue(const RsEpi &L, int T, int64_t y_split, uint32_t trow, int half, int seq, int srow,
                                             bool row_ok, const float4 (&rres)[4], const float *s_bias, const float *s_psc,
                                             const float *s_psh) {
-    constexpr int COLS = RS_N / (RS_EW / 4);  // 16 columns per epilogue warp
     const int64_t orow = (int64_t)seq * T + srow;
-    const int nb = half * COLS;
-    uint32_t r[COLS];
-    {
-        uint32_t(&r16)[16] = *reinterpret_cast<uint32_t(*)[16]>(&r[0]);
-        tmem_ld16_nowait(trow + (uint32_t)nb, r16);
-    }
+    const int nb = half * 16;
+    uint32_t r[16];
+    tmem_ld16_nowait(trow + (uint32_t)nb, r);
     tmem_ld_wait();
+    if (!row_ok) return;
+    float w[16];
 #pragma unroll
-    for (int g8 = 0; g8 < COLS; g8 += 8) {
-        const int n0 = nb + g8;
-        float w8[8];
-        const float4 b0 = *reinterpret_cast<const float4 *>(&s_bias[n0]), b1 = *reinterpret_cast<const float4 *>(&s_bias[n0 + 4]);
-        w8[0] = __uint_as_float(r[g8 + 0]) + b0.x, w8[1] = __uint_as_float(r[g8 + 1]) + b0.y;
-        w8[2] = __uint_as_float(r[g8 + 2]) + b0.z, w8[3] = __uint_as_float(r[g8 + 3]) + b0.w;
-        w8[4] = __uint_as_float(r[g8 + 4]) + b1.x, w8[5] = __uint_as_float(r[g8 + 5]) + b1.y;
-        w8[6] = __uint_as_float(r[g8 + 6]) + b1.z, w8[7] = __uint_as_float(r[g8 + 7]) + b1.w;
-        if (!row_ok) continue;
-        if (L.res != nullptr) {  // fp32 residual stream [seq][t][64], updated in place by the thread that owns the row
-            float4 *rp = reinterpret_cast<float4 *>(L.res + orow * RS_N + n0);
-            const float4 r0 = rres[g8 / 4], r1 = rres[g8 / 4 + 1];  // loaded before the accumulator wait
-            w8[0] += r0.x, w8[1] += r0.y, w8[2] += r0.z, w8[3] += r0.w;
-            w8[4] += r1.x, w8[5] += r1.y, w8[6] += r1.z, w8[7] += r1.w;
-            if (L.write_res) {
-                rp[0] = make_float4(w8[0], w8[1], w8[2], w8[3]);
-                rp[1] = make_float4(w8[4], w8[5], w8[6], w8[7]);
-            }
-        }
-        if (L.affine) {  // pre-activation BatchNorm + ReLU of the next conv
-            const float4 s0 = *reinterpret_cast<const float4 *>(&s_psc[n0]), s1 = *reinterpret_cast<const float4 *>(&s_psc[n0 + 4]);
-            const float4 h0 = *reinterpret_cast<const float4 *>(&s_psh[n0]), h1 = *reinterpret_cast<const float4 *>(&s_psh[n0 + 4]);
-            w8[0] = fmaxf(fmaf(w8[0], s0.x, h0.x), 0.f), w8[1] = fmaxf(fmaf(w8[1], s0.y, h0.y), 0.f);
-            w8[2] = fmaxf(fmaf(w8[2], s0.z, h0.z), 0.f), w8[3] = fmaxf(fmaf(w8[3], s0.w, h0.w), 0.f);
-            w8[4] = fmaxf(fmaf(w8[4], s1.x, h1.x), 0.f), w8[5] = fmaxf(fmaf(w8[5], s1.y, h1.y), 0.f);
-            w8[6] = fmaxf(fmaf(w8[6], s1.z, h1.z), 0.f), w8[7] = fmaxf(fmaf(w8[7], s1.w, h1.w), 0.f);
-        }
-        uint4 hi, lo;
-        pack8_split16<SPLIT>(w8, hi, lo);
-        uint16_t *yb = L.y + orow * RS_N + n0;
-        *reinterpret_cast<uint4 *>(yb) = hi;
-        if (SPLIT == 2) *reinterpret_cast<uint4 *>(yb + y_split) = lo;
+    for (int q = 0; q < 4; ++q) {
+        const float4 b4 = *reinterpret_cast<const float4 *>(&s_bias[nb + 4 * q]);
+        w[4 * q + 0] = __uint_as_float(r[4 * q + 0]) + b4.x, w[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + b4.y;
+        w[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + b4.z, w[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + b4.w;
     }
+    if (L.res != nullptr) {  // fp32 residual stream [seq][t][64], updated in place by the thread that owns the row
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            w[4 * q + 0] += rres[q].x, w[4 * q + 1] += rres[q].y, w[4 * q + 2] += rres[q].z, w[4 * q + 3] += rres[q].w;
+        }
+        if (L.write_res) {
+            float *rp = L.res + orow * RS_N + nb;
+            st_global_256(rp, &w[0]);
+            st_global_256(rp + 8, &w[8]);
+        }
+    }
+    if (L.affine) {  // pre-activation BatchNorm + ReLU of the next conv
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 s4 = *reinterpret_cast<const float4 *>(&s_psc[nb + 4 * q]), h4 = *reinterpret_cast<const float4 *>(&s_psh[nb + 4 * q]);
+            w[4 * q + 0] = fmaxf(fmaf(w[4 * q + 0], s4.x, h4.x), 0.f), w[4 * q + 1] = fmaxf(fmaf(w[4 * q + 1], s4.y, h4.y), 0.f);
+            w[4 * q + 2] = fmaxf(fmaf(w[4 * q + 2], s4.z, h4.z), 0.f), w[4 * q + 3] = fmaxf(fmaf(w[4 * q + 3], s4.w, h4.w), 0.f);
+        }
+    }
+    uint4 hi0, lo0, hi1, lo1;
+    pack8_split16<SPLIT>(&w[0], hi0, lo0);
+    pack8_split16<SPLIT>(&w[8], hi1, lo1);
+    uint16_t *yb = L.y + orow * RS_N + nb;
+    st_global_256(yb, hi0, hi1);
+    if (SPLIT == 2) st_global_256(yb + y_split, lo0, lo1);
 }
 
 template <int SPLIT>
@@ -86,7 +111,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) resstack_kernel(const __grid_co
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(16) float s_bias[2][RS_N], s_psc[2][RS_N], s_psh[2][RS_N];
     constexpr uint32_t W_BYTES = 12u * SPLIT * 2 * RS_N * 16;                          // weights of a k = 3 layer
-    constexpr uint32_t A_BYTES = ((uint32_t)SPLIT * 8 * RS_ROWS * 16 + 127u) & ~127u;  // one staged tile
+    constexpr uint32_t A_BYTES = ((uint32_t)SPLIT * 8 * RS_PITCH * 16 + 127u) & ~127u;  // one staged tile
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t sW_u = smem_u32(rs_smem);
@@ -101,7 +126,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) resstack_kernel(const __grid_co
         }
         for (int i = 0; i < RS_NACC; ++i) {
             mbar_init(&accf_bar[i], 1);
-            mbar_init(&acce_bar[i], 32 * RS_EW);
+            mbar_init(&acce_bar[i], 32 * 4);  // the four warps of the group that owns the accumulator
         }
         fence_barrier_init();
     }
@@ -125,7 +150,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) resstack_kernel(const __grid_co
     const uint32_t tmem_base = tmem_base_s;
 
     // pipeline state of this thread's role, alive across the layers
-    int stage = 0, acc = 0;
+    int stage = 0, acc = 0, nseq = 0;
     uint32_t phase = 0, acc_phase = 0;
     for (int l = 0; l < P.n_layers; ++l) {
         const ResLayerP &L = P.l[l];
@@ -141,18 +166,20 @@ __global__ void __launch_bounds__(RS_THREADS, 1) resstack_kernel(const __grid_co
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 mbar_wait(&empty_bar[stage], phase ^ 1u);
                 const uint32_t sbase = sA_u + (uint32_t)stage * A_BYTES;
-                for (int r = ptid; r < RS_ROWS; r += RS_PRODUCERS) {
+                // 8 consecutive lanes copy the 8 planes (one 128-byte global row) of one staged row: coalesced on the global
+                // side, and with the odd plane pitch the 8 stores hit 8 different 16-byte bank groups.  (One thread per
+                // row with a loop over the planes cost 36 shared-memory wavefronts per LDGSTS instead of 4.)
+                for (int idx = ptid; idx < RS_ROWS * 8; idx += RS_PRODUCERS) {
+                    const int c = idx & 7, r = idx >> 3;
                     const int v = r - 1;
                     const int seq = 2 * tile + (v >> 6), u = v & 63;
                     const bool valid = v >= 0 && v < 128 && seq < P.NS && u < T;
-                    const uint16_t *src = valid ? L.x + ((int64_t)seq * T + u) * RS_N : L.x;
+                    const uint16_t *src = valid ? L.x + ((int64_t)seq * T + u) * RS_N + c * 8 : L.x;
                     const uint32_t nb = valid ? 16u : 0u;
+                    const uint32_t dst = sbase + (uint32_t)(c * RS_PITCH + r) * 16u;
 #pragma unroll
-                    for (int s = 0; s < SPLIT; ++s) {
-                        const uint16_t *ss = valid ? src + (int64_t)s * P.split16 : L.x;
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) cp_async16(sbase + (uint32_t)((s * 8 + c) * RS_ROWS + r) * 16u, ss + c * 8, nb);
-                    }
+                    for (int s = 0; s < SPLIT; ++s)
+                        cp_async16(dst + (uint32_t)(s * 8 * RS_PITCH) * 16u, valid ? src + (int64_t)s * P.split16 : L.x, nb);
                 }
                 cp_async_mbar_arrive_noinc(&full_bar[stage]);
                 if (++stage == RS_NST) {
@@ -173,8 +200,8 @@ __global__ void __launch_bounds__(RS_THREADS, 1) resstack_kernel(const __grid_co
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * RS_N);
                 if (elect_one()) {
                     // k = 3 ('same'): tap j reads staged rows j ..; k = 2 (one zero on the right): rows j + 1 ..
-                    if (L.ntaps == 3) umma_conv_tile<RS_N, SPLIT, 3, 4>(d_tmem, sA16, RS_ROWS, sB16, idesc, 0u);
-                    else umma_conv_tile<RS_N, SPLIT, 2, 4>(d_tmem, sA16 + 1u, RS_ROWS, sB16, idesc, 0u);
+                    if (L.ntaps == 3) umma_conv_tile<RS_N, SPLIT, 3, 4>(d_tmem, sA16, RS_PITCH, sB16, idesc, 0u);
+                    else umma_conv_tile<RS_N, SPLIT, 2, 4>(d_tmem, sA16 + 1u, RS_PITCH, sB16, idesc, 0u);
                     umma_commit(&empty_bar[stage]);
                     umma_commit(&accf_bar[acc]);
                 }
@@ -189,31 +216,49 @@ __global__ void __launch_bounds__(RS_THREADS, 1) resstack_kernel(const __grid_co
                 }
             }
         } else {
-            // ================= epilogue (16 warps: TMEM lane quarter = warp & 3, 16-column slice = warp >> 2) =================
-            const int quarter = warp & 3, half = warp >> 2;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            // ================= epilogue: 4 groups of 4 warps (TMEM lane quarter = warp & 3) =================
+            // Group g owns accumulator buffer g, i.e. every 4th tile of this CTA, and converts all 64 columns of it in four
+            // 16-column rounds.  (With the 16 warps on ONE tile, 16 columns each, the CTA converted a single tile at a
+            // time and the chain accumulator wait -> TMEM load -> residual (global) -> stores ran at ~7400 cycles per
+            // tile against ~1400 cycles of MMAs; four tiles in flight overlap those latencies.)
+            const int quarter = warp & 3, grp = warp >> 2;
+            RsEpi E;
+            E.y = L.y;
+            E.res = L.res;
+            E.affine = L.affine;
+            E.write_res = L.write_res;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++nseq) {
+                if ((nseq & 3) != grp) continue;
                 const int v = quarter * 32 + lane;
                 const int seq = 2 * tile + (v >> 6), srow = v & 63;
                 const bool row_ok = seq < P.NS && srow < T;
-                float4 rres[4];  // this thread's 16 residual values: in flight while the accumulator is still being computed
-                if (L.res != nullptr && row_ok) {
-                    const float4 *rp = reinterpret_cast<const float4 *>(L.res + ((int64_t)seq * T + srow) * RS_N + half * 16);
+                const bool has_res = E.res != nullptr && row_ok;
+                const float *rp = E.res + ((int64_t)seq * T + srow) * RS_N;
+                float4 cur[4], nxt[4];  // residual values of the current / next 16-column round
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) rres[i] = rp[i];
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) rres[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int i = 0; i < 4; ++i) cur[i] = make_float4(0.f, 0.f, 0.f, 0.f), nxt[i] = cur[i];
+                if (has_res) {
+                    ld_global_256(rp, cur[0], cur[1]);
+                    ld_global_256(rp + 8, cur[2], cur[3]);
                 }
-                mbar_wait(&accf_bar[acc], acc_phase);
+                mbar_wait(&accf_bar[grp], acc_phase);
                 tc_fence_after();
-                const uint32_t trow = tmem_base + (uint32_t)(acc * RS_N) + ((uint32_t)(quarter * 32) << 16);
-                rs_epilogue<SPLIT>(L, T, P.split16, trow, half, seq, srow, row_ok, rres, s_bias[l & 1], s_psc[l & 1], s_psh[l & 1]);
-                tc_fence_before();
-                mbar_arrive(&acce_bar[acc]);
-                if (++acc == RS_NACC) {
-                    acc = 0;
-                    acc_phase ^= 1u;
+                const uint32_t trow = tmem_base + (uint32_t)(grp * RS_N) + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (c < 3 && has_res) {
+                        ld_global_256(rp + 16 * (c + 1), nxt[0], nxt[1]);
+                        ld_global_256(rp + 16 * (c + 1) + 8, nxt[2], nxt[3]);
+                    }
+                    rs_epilogue<SPLIT>(E, T, P.split16, trow, c, seq, srow, row_ok, cur, s_bias[l & 1], s_psc[l & 1], s_psh[l & 1]);
+                    if (c < 3) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
+                    }
                 }
+                tc_fence_before();
+                mbar_arrive(&acce_bar[grp]);
+                acc_phase ^= 1u;
             }
             __threadfence();  // this layer's outputs before the CTA barrier that releases the next layer's loads
         }
@@ -229,8 +274,12 @@ int resstack_launch(const ResStackP &p, int split, cudaStream_t s) {
                "res-CNN stack: %d layers, T = %d unsupported", p.n_layers, p.T);
     VP_REQUIRE(p.T + 1 <= 64, VP_ERR_UNSUPPORTED, "res-CNN stack: sequences of %d rows do not fit the 64-row pitch", p.T);
     if (p.NS == 0) return VP_OK;
+    for (int l = 0; l < p.n_layers; ++l)  // the epilogue moves 32-byte pieces (256-bit loads / stores)
+        VP_REQUIRE(reinterpret_cast<uintptr_t>(p.l[l].y) % 32 == 0 && reinterpret_cast<uintptr_t>(p.l[l].res) % 32 == 0 &&
+                       (p.split16 * 2) % 32 == 0,
+                   VP_ERR_ARG, "res-CNN stack: layer %d buffers are not 32-byte aligned", l);
     const size_t w_bytes = (size_t)12 * split * 2 * RS_N * 16;
-    const size_t a_bytes = ((size_t)split * 8 * RS_ROWS * 16 + 127) & ~(size_t)127;
+    const size_t a_bytes = ((size_t)split * 8 * RS_PITCH * 16 + 127) & ~(size_t)127;
     const size_t smem = 2 * w_bytes + RS_NST * a_bytes;
     const int n_tiles = (p.NS + 1) / 2;
     const unsigned grid = (unsigned)std::min(148, n_tiles);

@@ -713,21 +713,29 @@ __global__ void __launch_bounds__(PK_NT) pick_tile_kernel(const PickLabels P, co
     }
     if (tid == 32) s_next_ok = (t0 + PK_TILE < n && !isnan(__ldg(x + t0 + PK_TILE))) ? 1 : 0;
     int n_ok = 0;  // non-NaN samples loaded by this thread
+    {
+        // all loads of the tile are issued before the first use: with the bounds test inside the loop the compiler kept one
+        // 16-byte load in flight per thread (four serial DRAM round trips per CTA, 24 % of the HBM peak)
+        constexpr int NIT = PK_TILE / (4 * PK_NT);
+        float4 v[NIT];
+        if (t0 >= 0 && t0 + PK_TILE <= n) {  // interior tile (uniform for the CTA)
 #pragma unroll
-    for (int it = 0; it < PK_TILE / (4 * PK_NT); ++it) {
-        const int o = (it * PK_NT + tid) * 4;
-        const int64_t g = t0 + o;
-        float4 v;
-        if (g >= 0 && g + 3 < n) {
-            v = __ldg(reinterpret_cast<const float4 *>(x + g));
+            for (int it = 0; it < NIT; ++it) v[it] = __ldg(reinterpret_cast<const float4 *>(x + t0 + (it * PK_NT + tid) * 4));
         } else {
-            v.x = (g >= 0 && g < n) ? __ldg(x + g) : CUDART_NAN_F;
-            v.y = (g + 1 >= 0 && g + 1 < n) ? __ldg(x + g + 1) : CUDART_NAN_F;
-            v.z = (g + 2 >= 0 && g + 2 < n) ? __ldg(x + g + 2) : CUDART_NAN_F;
-            v.w = (g + 3 >= 0 && g + 3 < n) ? __ldg(x + g + 3) : CUDART_NAN_F;
+#pragma unroll
+            for (int it = 0; it < NIT; ++it) {
+                const int64_t g = t0 + (it * PK_NT + tid) * 4;
+                v[it].x = (g >= 0 && g < n) ? __ldg(x + g) : CUDART_NAN_F;
+                v[it].y = (g + 1 >= 0 && g + 1 < n) ? __ldg(x + g + 1) : CUDART_NAN_F;
+                v[it].z = (g + 2 >= 0 && g + 2 < n) ? __ldg(x + g + 2) : CUDART_NAN_F;
+                v[it].w = (g + 3 >= 0 && g + 3 < n) ? __ldg(x + g + 3) : CUDART_NAN_F;
+            }
         }
-        n_ok += (v.x == v.x) + (v.y == v.y) + (v.z == v.z) + (v.w == v.w);
-        *reinterpret_cast<float4 *>(sv + o) = v;
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            n_ok += (v[it].x == v[it].x) + (v[it].y == v[it].y) + (v[it].z == v[it].z) + (v[it].w == v[it].w);
+            *reinterpret_cast<float4 *>(sv + (it * PK_NT + tid) * 4) = v[it];
+        }
     }
     // tile-wide census: all samples valid (the common case), none, or mixed (only then the NaN positions are searched)
     const int all_ok = __syncthreads_and(n_ok == PK_TILE / PK_NT);

@@ -19,12 +19,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "{\n\t"
         ".reg .pred P1;\n\t"
         "LAB_WAIT:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
         "@P1 bra DONE;\n\t"
         "bra LAB_WAIT;\n\t"
         "DONE:\n\t"
         "}" ::"r"(smem_u32(bar)),
-        "r"(parity)
+        "r"(parity), "r"(0x989680u)  // suspend-time hint: the warp sleeps in hardware until the phase completes instead of
+                                     // re-polling every ~30 cycles (polls were 27 - 67 % of the executed instructions)
         : "memory");
 }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {

@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(32 * (EW + 4), EW == 16 ? 1 : EW == 8 ? 2 : 4)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = blockIdx.y;
     const int n_rows = p.n_rows, cin8 = p.cin8, nstage = p.n_stages;
-    const uint32_t PL = (uint32_t)n_rows * 16u;  // bytes per 8-channel plane
+    const uint32_t PL = (uint32_t)p.pitch * 16u;  // bytes per 8-channel plane
     const uint32_t a_bytes = ((uint32_t)SPLIT * cin8 * PL + 127u) & ~127u;
     const uint32_t w_bytes = ((uint32_t)p.n_blocks * SPLIT * 2 * NOUT * 16u + 127u) & ~127u;
     const uint32_t sB_u = smem_u32(tc_smem);
@@ -223,6 +223,39 @@ __global__ void __launch_bounds__(32 * (EW + 4), EW == 16 ? 1 : EW == 8 ? 2 : 4)
             mbar_wait(&empty_bar[stage], phase ^ 1u);
             const int m0 = tile * 128;
             const uint32_t sbase = sA_u + (uint32_t)stage * a_bytes;
+            if (p.coal_sh > 0) {
+                // coalesced mapping: thread = (plane c, rows r0, r0 + step, ...); the cin8 lanes of a row read its
+                // contiguous 16 cin8 bytes.  (seq, u) advance incrementally: no division per row.
+                const int sh = p.coal_sh, step = TC_PRODUCERS >> sh;
+                const int c = ptid & (cin8 - 1);
+                int r = ptid >> sh;
+                int v = m0 + p.row0 + r, seq, u;
+                if (v >= 0) {
+                    seq = v / p.Tp;
+                    u = v - seq * p.Tp;
+                } else {
+                    seq = -1;
+                    u = v + p.Tp;  // row0 > -Tp
+                }
+                const bool fromA = c < cinA8;
+                const uint16_t *base = fromA ? xg + c * 8 : p.x2 + (c - cinA8) * 8;
+                const int64_t pitchX = fromA ? p.x_pitch : p.x2_pitch, splitX = fromA ? p.x_split : p.x2_split;
+                const int roffX = fromA ? p.x_roff : p.x2_roff, CX = fromA ? CA : CB;
+                for (; r < n_rows && !(p.dbg & 1); r += step) {
+                    const bool valid = seq >= 0 && seq < p.NS && u < p.T_eff;
+                    const int srow = (p.ups == 2) ? (u >> 1) : u;
+                    const uint16_t *src = valid ? base + ((int64_t)seq * pitchX + roffX + srow) * CX : xg;
+                    const uint32_t nb = valid ? 16u : 0u;
+                    const uint32_t dst = sbase + (uint32_t)c * PL + (uint32_t)r * 16u;
+#pragma unroll
+                    for (int s = 0; s < SPLIT; ++s) cp_async16(dst + (uint32_t)(s * cin8) * PL, valid ? src + (int64_t)s * splitX : xg, nb);
+                    u += step;
+                    while (u >= p.Tp) {
+                        u -= p.Tp;
+                        ++seq;
+                    }
+                }
+            } else
             for (int r = ptid; r < n_rows && !(p.dbg & 1); r += TC_PRODUCERS) {
                 const int v = m0 + p.row0 + r;
                 bool valid = v >= 0;
@@ -240,10 +273,10 @@ __global__ void __launch_bounds__(32 * (EW + 4), EW == 16 ? 1 : EW == 8 ? 2 : 4)
                 for (int s = 0; s < SPLIT; ++s) {
                     const uint16_t *ss = valid ? (src + (int64_t)s * p.x_split) : xg;
                     for (int c = 0; c < cinA8; ++c)
-                        cp_async16(sbase + (uint32_t)((s * cin8 + c) * n_rows + r) * 16u, ss + c * 8, nb);
+                        cp_async16(sbase + (uint32_t)(s * cin8 + c) * PL + (uint32_t)r * 16u, ss + c * 8, nb);
                     const uint16_t *s2 = (valid && CB) ? (src2 + (int64_t)s * p.x2_split) : xg;
                     for (int c = cinA8; c < cin8; ++c)
-                        cp_async16(sbase + (uint32_t)((s * cin8 + c) * n_rows + r) * 16u, s2 + (c - cinA8) * 8, nb);
+                        cp_async16(sbase + (uint32_t)(s * cin8 + c) * PL + (uint32_t)r * 16u, s2 + (c - cinA8) * 8, nb);
                 }
             }
             cp_async_mbar_arrive_noinc(&full_bar[stage]);
@@ -273,8 +306,7 @@ __global__ void __launch_bounds__(32 * (EW + 4), EW == 16 ? 1 : EW == 8 ? 2 : 4)
             if (elect_one()) {
                 if constexpr (NTAPS > 0) {
                     if (p.dbg & 2) umma_f16(d_tmem, desc_hi | (uint64_t)(sA16 + p.term_a[0]), desc_hi | (uint64_t)(sB16 + p.term_b[0]), idesc, 0u); else {
-                    constexpr uint32_t ROWS = 128 + (NQ == 0 ? 2 * NTAPS - 1 : NTAPS - 1);  // == p.n_rows
-                    umma_conv_tile<NOUT, SPLIT, NTAPS, NQ>(d_tmem, sA16, ROWS, sB16, idesc, 0u);
+                    umma_conv_tile<NOUT, SPLIT, NTAPS, NQ>(d_tmem, sA16, (uint32_t)p.pitch, sB16, idesc, 0u);
                     }
                 } else {
                     umma_f16(d_tmem, desc_hi | (uint64_t)(sA16 + p.term_a[0]), desc_hi | (uint64_t)(sB16 + p.term_b[0]), idesc, 0u);
@@ -649,20 +681,33 @@ int tc_launch(const TcLayer &L, const TcIO &io, cudaStream_t s) {
     p.row0 = L.row0;
     p.n_rows = 128 + L.halo;
     p.cin8 = L.cin / 8;
+    p.pitch = p.n_rows;
+    p.coal_sh = -1;
+    {
+        static const bool coal_off = getenv("VP_TC_COAL") && atoi(getenv("VP_TC_COAL")) == 0;
+        const int c8 = p.cin8;
+        if (!coal_off && c8 >= 2 && (c8 & (c8 - 1)) == 0 && TC_PRODUCERS % c8 == 0) {
+            int sh = 0;
+            while ((1 << sh) < c8) ++sh;
+            p.coal_sh = sh;
+            const int q = 8 / std::min(c8, 8);  // staged rows covered by a group of 8 lanes
+            while (p.pitch % (2 * q) != q) ++p.pitch;
+        }
+    }
     p.w = io.w_dev;
     p.w_gs = (int64_t)L.n_blocks * L.split * 2 * L.nout * 8;
     p.n_blocks = L.n_blocks;
     p.bias = io.b_dev;
     p.b_gs = L.nout;
     {
-        const uint32_t PL16 = (uint32_t)p.n_rows;  // plane pitch in 16-byte units
+        const uint32_t PL16 = (uint32_t)p.pitch;  // plane pitch in 16-byte units
         const int nterm = (L.split == 2) ? 3 : 1;
         p.n_terms = 0;
         for (const TcMma &e : L.mma)
             for (int t = 0; t < nterm; ++t) {
                 const int sa = (t == 2) ? 1 : 0;  // hi*hi, hi*lo, lo*hi
                 const int sb = (t == 1) ? 1 : 0;
-                const uint32_t a_off = (uint32_t)((sa * p.cin8 + e.a_plane) * p.n_rows + e.a_row);
+                const uint32_t a_off = (uint32_t)((sa * p.cin8 + e.a_plane) * p.pitch + e.a_row);
                 const uint32_t lbo16 = e.a_rowk ? 1u : PL16;
                 const uint32_t b_off = (uint32_t)((e.b_block * L.split + sb) * 2 * L.nout);
                 p.term_a[p.n_terms] = a_off | (lbo16 << 16);
@@ -720,7 +765,7 @@ int tc_launch(const TcLayer &L, const TcIO &io, cudaStream_t s) {
     VP_REQUIRE(!(io.pool == 2 && L.ph == 2), VP_ERR_UNSUPPORTED, "tc conv: pooling with polyphase output is not supported");
     const int64_t rows = (int64_t)io.NS * Tp;
     const int64_t n_tiles = (rows + 127) / 128;
-    const size_t a_bytes = ((size_t)L.split * p.cin8 * p.n_rows * 16 + 127) & ~(size_t)127;
+    const size_t a_bytes = ((size_t)L.split * p.cin8 * p.pitch * 16 + 127) & ~(size_t)127;
     const size_t w_bytes = ((size_t)L.n_blocks * L.split * 2 * L.nout * 16 + 127) & ~(size_t)127;
     // ring depth / residency: two CTAs per SM when a >= 2-stage ring fits in half the shared memory
     // ring depth / residency: several CTAs per SM (one MMA issuer each) when >= 2 stages fit in the share
