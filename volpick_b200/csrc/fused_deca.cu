@@ -215,7 +215,9 @@ __global__ void __launch_bounds__(DA_THREADS, 1) deca_kernel(const __grid_consta
             tc_fence_before();
             named_bar_sync(1, 32 * DA_EW);  // s_fix complete
             if (lane == 0) mbar_arrive(&done_bar[0]);
-            // ---- decoder.convs.2 -> global (B, 375, 32) 16-bit; this warp: channels [8 cs, 8 cs + 8) of both phases
+            // ---- decoder.convs.2 -> global (B, 375, 32) 16-bit; this warp: channels [16 hc, 16 hc + 16) of phase ph, i.e. 32
+            // contiguous bytes of one output row per thread and split (one 256-bit store instead of two 16-byte pieces)
+            const int ph = cs >> 1, hc = cs & 1;
 #pragma unroll
             for (int t = 0; t < 2; ++t) {
                 mbar_wait(&acc_full[1 + t], par);
@@ -223,30 +225,24 @@ __global__ void __launch_bounds__(DA_THREADS, 1) deca_kernel(const __grid_consta
                 const int s = 128 * t + r;
                 if (t == 0 || lq < 2) {  // rows 192 .. 255 do not exist
                     const uint32_t tacc = tmem_base + 128u + 64u * t + ((uint32_t)(lq * 32) << 16);
-                    uint32_t r0[8], r1[8];
-                    tmem_ld8_nowait(tacc + (uint32_t)(8 * cs), r0);
-                    tmem_ld8_nowait(tacc + (uint32_t)(32 + 8 * cs), r1);
+                    uint32_t r0[16];
+                    tmem_ld16_nowait(tacc + (uint32_t)(32 * ph + 16 * hc), r0);
                     tmem_ld_wait();
-                    if (s < DA_T1) {
-                        float v0[8], v1[8];
+                    if (s < DA_T1 && 2 * s + ph < DA_T2) {
+                        float v[16];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            float a0 = __uint_as_float(r0[i]), a1 = __uint_as_float(r1[i]);
-                            if (s == DA_T1 - 2) a1 -= s_fix[0][8 * cs + i];  // output 373 = row 186, phase 1
-                            if (s == DA_T1 - 1) a0 -= s_fix[1][8 * cs + i];  // output 374 = row 187, phase 0
-                            v0[i] = fmaxf(a0 + s_bias[128 + 8 * cs + i], 0.f);
-                            v1[i] = fmaxf(a1 + s_bias[128 + 32 + 8 * cs + i], 0.f);
+                        for (int i = 0; i < 16; ++i) {
+                            float a = __uint_as_float(r0[i]);
+                            if (ph == 1 && s == DA_T1 - 2) a -= s_fix[0][16 * hc + i];  // output 373 = row 186, phase 1
+                            if (ph == 0 && s == DA_T1 - 1) a -= s_fix[1][16 * hc + i];  // output 374 = row 187, phase 0
+                            v[i] = fmaxf(a + s_bias[128 + 32 * ph + 16 * hc + i], 0.f);
                         }
                         uint4 h0, l0, h1, l1;
-                        da_pack8<SPLIT>(v0, h0, l0);
-                        da_pack8<SPLIT>(v1, h1, l1);
-                        uint16_t *yb = yg + ((long long)b * DA_T2 + 2 * s) * 32 + 8 * cs;
-                        *reinterpret_cast<uint4 *>(yb) = h0;
-                        if (SPLIT == 2) *reinterpret_cast<uint4 *>(yb + p.y_split) = l0;
-                        if (2 * s + 1 < DA_T2) {
-                            *reinterpret_cast<uint4 *>(yb + 32) = h1;
-                            if (SPLIT == 2) *reinterpret_cast<uint4 *>(yb + 32 + p.y_split) = l1;
-                        }
+                        da_pack8<SPLIT>(&v[0], h0, l0);
+                        da_pack8<SPLIT>(&v[8], h1, l1);
+                        uint16_t *yb = yg + ((long long)b * DA_T2 + 2 * s + ph) * 32 + 16 * hc;
+                        st_pair16(yb, h0, yb + 8, h1);
+                        if (SPLIT == 2) st_pair16(yb + p.y_split, l0, yb + 8 + p.y_split, l1);
                     }
                 }
                 tc_fence_before();

@@ -39,26 +39,6 @@ struct RsEpi {
     int affine, write_res;
 };
 
-// 256-bit global accesses (sm_100: LDG / STG .256).  The epilogue's traffic is 16-byte pieces per lane at a 128 / 256-byte
-// lane stride: the L1 data pipe (58 %) and the L2 tag stage (54 %, 1.2 sectors per request) were the busiest units of the
-// kernel, i.e. it is bound by the NUMBER of memory transactions.  A thread now moves whole 32-byte sectors.
-__device__ __forceinline__ void ld_global_256(const float *p, float4 &a, float4 &b) {
-    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
-                 : "l"(p)
-                 : "memory");
-}
-__device__ __forceinline__ void st_global_256(float *p, const float *v) {
-    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]),
-                 "f"(v[5]), "f"(v[6]), "f"(v[7])
-                 : "memory");
-}
-__device__ __forceinline__ void st_global_256(uint16_t *p, const uint4 &a, const uint4 &b) {
-    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y),
-                 "r"(b.z), "r"(b.w)
-                 : "memory");
-}
-
 // One 16-column round of a row: accumulator + bias (+ residual, stored back) -> [BN + ReLU] -> 16-bit split store.
 template <int SPLIT>
 __device__ __forceinline__ void rs_epilogue(const RsEpi &L, int T, int64_t y_split, uint32_t trow, int half, int seq, int srow,

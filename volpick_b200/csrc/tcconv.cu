@@ -88,6 +88,8 @@ __device__ __forceinline__ void tc_epilogue_fixed(const TcP &p, uint32_t trow, i
     const int t0 = POOL ? (srow >> 1) : (PH2 ? 2 * srow : srow);
     const int64_t orow0 = (int64_t)seq * p.T_out + t0;
     uint16_t *y16 = reinterpret_cast<uint16_t *>(p.y) + (int64_t)g * p.y_gs + orow0 * COUT;
+    uint16_t *pend = nullptr;  // even 8-channel group waiting for its neighbour (same row, same phase: `ok` is the same for both)
+    uint4 pend_hi = make_uint4(0u, 0u, 0u, 0u), pend_lo = pend_hi;
 #pragma unroll
     for (int rc = 0; rc < COLS; rc += RC) {
         const int nb = half * COLS + rc;
@@ -149,10 +151,30 @@ __device__ __forceinline__ void tc_epilogue_fixed(const TcP &p, uint32_t trow, i
                     w8[6] = fmaxf(fmaf(w8[6], s1.z, h1.z), 0.f), w8[7] = fmaxf(fmaf(w8[7], s1.w, h1.w), 0.f);
                 }
             }
-            if (ok) {
-                uint4 hi, lo;
-                pack8_split16<SPLIT>(w8, hi, lo);
-                uint16_t *yb = y16 + phi * COUT + c0;
+            uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
+            if (ok) pack8_split16<SPLIT>(w8, hi, lo);
+            uint16_t *yb = y16 + phi * COUT + c0;
+            if constexpr (RC >= 16) {
+                // two adjacent 8-channel groups leave as one 32-byte store per split (whole sectors: half the L1 / L2
+                // transactions of 16-byte pieces at a row-pitch lane stride)
+                if ((g8 & 8) == 0) {
+                    pend = ok ? yb : nullptr;
+                    pend_hi = hi;
+                    pend_lo = lo;
+                } else {
+                    if (ok && pend != nullptr) {
+                        st_pair16(pend, pend_hi, yb, hi);
+                        if (SPLIT == 2) st_pair16(pend + p.y_split, pend_lo, yb + p.y_split, lo);
+                    } else {
+                        uint16_t *one = ok ? yb : pend;
+                        if (one != nullptr) {
+                            *reinterpret_cast<uint4 *>(one) = ok ? hi : pend_hi;
+                            if (SPLIT == 2) *reinterpret_cast<uint4 *>(one + p.y_split) = ok ? lo : pend_lo;
+                        }
+                    }
+                    pend = nullptr;
+                }
+            } else if (ok) {
                 *reinterpret_cast<uint4 *>(yb) = hi;
                 if (SPLIT == 2) *reinterpret_cast<uint4 *>(yb + p.y_split) = lo;
             }
@@ -366,6 +388,8 @@ __global__ void __launch_bounds__(32 * (EW + 4), EW == 16 ? 1 : EW == 8 ? 2 : 4)
 #pragma unroll
                         for (int i = 0; i < CH; ++i) a[i] = __uint_as_float(r[i]);
                     }
+                    uint16_t *pend = nullptr;  // 16-bit output: even 8-channel group waiting for its neighbour
+                    uint4 pend_hi = make_uint4(0u, 0u, 0u, 0u), pend_lo = pend_hi;
 #pragma unroll
                     for (int g8 = 0; g8 < CH; g8 += 8) {
                         const int n0 = nb + g8;
@@ -438,8 +462,18 @@ __global__ void __launch_bounds__(32 * (EW + 4), EW == 16 ? 1 : EW == 8 ? 2 : 4)
                             uint4 hi, lo;
                             tc_pack8<SPLIT>(w8, hi, lo);
                             uint16_t *yb = reinterpret_cast<uint16_t *>(p.y) + (int64_t)g * p.y_gs + (orow0 + phi) * p.cout_cl + c0;
-                            *reinterpret_cast<uint4 *>(yb) = hi;
-                            if (SPLIT == 2) *reinterpret_cast<uint4 *>(yb + p.y_split) = lo;
+                            if (CH == 16 && g8 == 0) {  // wait for the neighbouring group: one 32-byte store when it follows
+                                pend = yb;
+                                pend_hi = hi;
+                                pend_lo = lo;
+                            } else if (pend != nullptr) {
+                                st_pair16(pend, pend_hi, yb, hi);
+                                if (SPLIT == 2) st_pair16(pend + p.y_split, pend_lo, yb + p.y_split, lo);
+                                pend = nullptr;
+                            } else {
+                                *reinterpret_cast<uint4 *>(yb) = hi;
+                                if (SPLIT == 2) *reinterpret_cast<uint4 *>(yb + p.y_split) = lo;
+                            }
                         } else {
                             float *yb = reinterpret_cast<float *>(p.y) + (int64_t)g * p.y_gs + (int64_t)seq * p.y_ss + t_out;
                             const int cb = p.fold > 1 ? c0 % p.fold_c : c0;  // folded: channel inside the sample
@@ -447,6 +481,10 @@ __global__ void __launch_bounds__(32 * (EW + 4), EW == 16 ? 1 : EW == 8 ? 2 : 4)
                             for (int i = 0; i < 8; ++i)
                                 if (c0 + i < p.cout) yb[(int64_t)(cb + i) * p.y_cs] = w8[i];
                         }
+                    }
+                    if (pend != nullptr) {  // the neighbouring group was a padding / masked column group
+                        *reinterpret_cast<uint4 *>(pend) = pend_hi;
+                        if (SPLIT == 2) *reinterpret_cast<uint4 *>(pend + p.y_split) = pend_lo;
                     }
                 }
             }
