@@ -88,8 +88,7 @@ __device__ __forceinline__ void tc_epilogue_fixed(const TcP &p, uint32_t trow, i
     const int t0 = POOL ? (srow >> 1) : (PH2 ? 2 * srow : srow);
     const int64_t orow0 = (int64_t)seq * p.T_out + t0;
     uint16_t *y16 = reinterpret_cast<uint16_t *>(p.y) + (int64_t)g * p.y_gs + orow0 * COUT;
-    uint16_t *pend = nullptr;  // even 8-channel group waiting for its neighbour (same row, same phase: `ok` is the same for both)
-    uint4 pend_hi = make_uint4(0u, 0u, 0u, 0u), pend_lo = pend_hi;
+    uint4 pend_hi = make_uint4(0u, 0u, 0u, 0u), pend_lo = pend_hi;  // even 8-channel group waiting for its neighbour
 #pragma unroll
     for (int rc = 0; rc < COLS; rc += RC) {
         const int nb = half * COLS + rc;
@@ -154,25 +153,24 @@ __device__ __forceinline__ void tc_epilogue_fixed(const TcP &p, uint32_t trow, i
             uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
             if (ok) pack8_split16<SPLIT>(w8, hi, lo);
             uint16_t *yb = y16 + phi * COUT + c0;
-            if constexpr (RC >= 16) {
-                // two adjacent 8-channel groups leave as one 32-byte store per split (whole sectors: half the L1 / L2
-                // transactions of 16-byte pieces at a row-pitch lane stride)
+            if constexpr (RC >= 16 && COUT % 16 == 0) {
+                // two adjacent 8-channel groups (same row, same phase, same `ok`) leave as one 32-byte store per split:
+                // whole sectors, half the L1 / L2 transactions of 16-byte pieces at a row-pitch lane stride
                 if ((g8 & 8) == 0) {
-                    pend = ok ? yb : nullptr;
                     pend_hi = hi;
                     pend_lo = lo;
-                } else {
-                    if (ok && pend != nullptr) {
-                        st_pair16(pend, pend_hi, yb, hi);
-                        if (SPLIT == 2) st_pair16(pend + p.y_split, pend_lo, yb + p.y_split, lo);
+                } else if (ok) {
+                    if (p.st256) {
+                        st_global_256(yb - 8, pend_hi, hi);
+                        if (SPLIT == 2) st_global_256(yb - 8 + p.y_split, pend_lo, lo);
                     } else {
-                        uint16_t *one = ok ? yb : pend;
-                        if (one != nullptr) {
-                            *reinterpret_cast<uint4 *>(one) = ok ? hi : pend_hi;
-                            if (SPLIT == 2) *reinterpret_cast<uint4 *>(one + p.y_split) = ok ? lo : pend_lo;
+                        *reinterpret_cast<uint4 *>(yb - 8) = pend_hi;
+                        *reinterpret_cast<uint4 *>(yb) = hi;
+                        if (SPLIT == 2) {
+                            *reinterpret_cast<uint4 *>(yb - 8 + p.y_split) = pend_lo;
+                            *reinterpret_cast<uint4 *>(yb + p.y_split) = lo;
                         }
                     }
-                    pend = nullptr;
                 }
             } else if (ok) {
                 *reinterpret_cast<uint4 *>(yb) = hi;
@@ -788,6 +786,10 @@ int tc_launch(const TcLayer &L, const TcIO &io, cudaStream_t s) {
     const bool custom = p.fold > 1 || io.x2 || p.x_pitch != io.T_in || p.x_roff != 0 || p.y_pitch != p.T_out || p.y_roff != 0 || io.T_valid > 0 ||
                         io.out_fmt == 2;
     p.out_fmt = io.out_fmt;
+    p.st256 = (io.out_fmt == 0 && reinterpret_cast<uintptr_t>(io.y) % 32 == 0 && (io.y_split * 2) % 32 == 0 && (io.y_gs * 2) % 32 == 0 &&
+               L.cout % 16 == 0)
+                  ? 1
+                  : 0;
     p.y = io.y;
     p.y_split = io.y_split;
     p.y_gs = io.y_gs;

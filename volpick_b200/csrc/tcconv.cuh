@@ -32,6 +32,7 @@ struct TcP {
     // thread per row): cin8 consecutive lanes copy the planes of ONE global row, and the pitch is chosen so that 8 lanes
     // store to 8 different 16-byte bank groups (pitch odd for >= 8 planes, 2 mod 4 for 4, 4 mod 8 for 2)
     int pitch, coal_sh;
+    int st256;  // 1: the 16-bit output rows, group and split offsets are 32-byte aligned -> adjacent 8-channel groups leave as one 256-bit store
     const uint16_t *w;  // [G][n_blocks][SPLIT][2][NOUT][8]
     int64_t w_gs;
     int n_blocks;
