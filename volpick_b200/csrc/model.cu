@@ -245,6 +245,7 @@ struct vp_model {
     // tensor-core (tcgen05) weight sets: [0] = fp16 hi/lo split (f16x3), [1] = bf16
     struct TcSet {
         TcLayer enc[7], dec[7], head;
+        TcLayer encf[3];           // encoder.convs.1 / .2 with 4 time steps folded into the MMA K / N (index = layer; see fold4_same)
         TcLayer res1[7], res2[7];  // res-CNN convs (BatchNorm + ReLU of their inputs live in the producer's epilogue)
         TcLayer lproj;             // bi_lstm_stack.members.0: input projection of both directions as a 1x1 conv (64 -> 2 x 64 gates)
         uint16_t *d_w = nullptr;
@@ -300,6 +301,7 @@ static int upload_pn_tc(vp_model::PnTcSet &ts) {
 static int upload_tc(vp_model::TcSet &ts) {
     std::vector<TcLayer *> layers;
     for (int i = 0; i < 7; ++i) layers.push_back(&ts.enc[i]);
+    for (int i = 1; i < 3; ++i) layers.push_back(&ts.encf[i]);
     for (int i = 0; i < 7; ++i) layers.push_back(&ts.dec[i]);
     layers.push_back(&ts.head);
     layers.push_back(&ts.lproj);
@@ -324,6 +326,26 @@ static int upload_tc(vp_model::TcSet &ts) {
     }
     ts.ready = true;
     return VP_OK;
+}
+
+// 'same' Conv1d (odd k <= 9, pad (k - 1) / 2) with 4 time steps folded into the channels: on the [T / 4][4 C] view of a
+// channel-last buffer (the same bytes) it is a 3-tap row conv (row pad 1) from 4 cin to 4 cout columns; column = sample *
+// cout + channel.  The 8 / 16-channel encoder layers are bound by the shared-memory reads of the A operand (4 KB per
+// tcgen05.mma whatever its N), so 2.5x / 1.75x fewer, wider MMAs win.
+static void fold4_same(const float *W, const float *bias, int cout, int cin, int k, std::vector<float> &wf, std::vector<float> &bf) {
+    const int F = 4, P = (k - 1) / 2;
+    wf.assign((size_t)F * cout * F * cin * 3, 0.f);
+    bf.assign((size_t)F * cout, 0.f);
+    for (int q = 0; q < F; ++q)
+        for (int co = 0; co < cout; ++co) {
+            bf[(size_t)q * cout + co] = bias ? bias[co] : 0.f;
+            for (int j = 0; j < k; ++j) {
+                const int pos = q + j - P;  // input sample relative to 4 * row
+                const int d = pos >= 0 ? pos / F : -((-pos + F - 1) / F), lane = pos - d * F;  // row tap d in {-1, 0, 1}
+                for (int ci = 0; ci < cin; ++ci)
+                    wf[(((size_t)q * cout + co) * (F * cin) + lane * cin + ci) * 3 + (d + 1)] = W[((size_t)co * cin + ci) * k + j];
+            }
+        }
 }
 
 static const int kEncC[8] = {3, 8, 16, 16, 32, 32, 64, 64};
@@ -441,6 +463,13 @@ static int build_eqt(vp_model *m, Cursor &cur, Packed &pk) {
             const float *wl[1] = {W}, *bl[1] = {eB[i]};
             int rc = tc_build_layer(ts.enc[i], TC_DIRECT, cin, kEncC[i + 1], kEncK[i], 0, split, 1, wl, bl);
             if (rc != VP_OK) return rc;
+            if (i == 1 || i == 2) {  // 8 -> 16 (k9) and 16 -> 16 (k7): folded x4 -> 32 / 64 -> 64 columns, 3 row taps
+                std::vector<float> wf, bf;
+                fold4_same(W, eB[i], kEncC[i + 1], cin, kEncK[i], wf, bf);
+                const float *wfl[1] = {wf.data()}, *bfl[1] = {bf.data()};
+                rc = tc_build_layer(ts.encf[i], TC_DIRECT, 4 * cin, 4 * kEncC[i + 1], 3, 0, split, 1, wfl, bfl, 1);
+                if (rc != VP_OK) return rc;
+            }
         }
         for (int i = 0; i < 7; ++i) {
             const float *wl[3] = {dW[0][i], dW[1][i], dW[2][i]}, *bl[3] = {dB[0][i], dB[1][i], dB[2][i]};
@@ -877,6 +906,26 @@ static int run_eqt(Runner &r, const float *x, float *y, Arena &ar) {
                 io.b_dev = ts.d_b + tl.b_off;
                 io.act = ACT_RELU;
                 io.pool = 2;
+                static const bool encfold_off = getenv("VP_ENC_FOLD") && atoi(getenv("VP_ENC_FOLD")) == 0;  // debugging aid
+                if ((i == 1 || i == 2) && !encfold_off && len[i] % 4 == 0) {
+                    // encoder.convs.1 / .2 on the [T / 4][4 C] view: conv + ReLU + MaxPool inside the accumulator row
+                    const TcLayer &tf = ts.encf[i];
+                    io.T_in = len[i] / 4;
+                    io.w_dev = ts.d_w + tf.w_off;
+                    io.b_dev = ts.d_b + tf.b_off;
+                    io.pool = 1;
+                    io.foldpool = 1;
+                    io.out_fmt = 0;
+                    io.y = pp16[i & 1];
+                    io.y_split = split16;
+                    io.y_gs = 0;
+                    io.y_ss = 0;
+                    io.y_cs = 0;
+                    io.cout_cl = tf.cout;
+                    r.rc = tc_launch(tf, io, r.s);
+                    cur16 = pp16[i & 1];
+                    continue;
+                }
                 if (i == 6 && !enc6_tap) {
                     // last encoder stage feeds the res-CNN stack: fp32 residual stream (row-major) + the 16-bit
                     // relu(bn1(x)) operand of res_cnn_stack.members.0.conv1

@@ -180,6 +180,57 @@ __device__ __forceinline__ void tc_epilogue_fixed(const TcP &p, uint32_t trow, i
     }
 }
 
+// FLAGS == 8: 'same' Conv1d on the [T / 4][4 C_in] view of the channel-last input (time folded into the MMA K / N: column
+// = sample * 16 + channel, 4 samples x 16 output channels per accumulator row) + ReLU + MaxPool1d(2).  The pool pairs
+// (samples 2j, 2j + 1) live in the same accumulator row, so no shuffle is needed; a thread writes the 16 pooled channels
+// of pooled sample j as 32 contiguous bytes per split of the [T / 4][2 x 16] = [T / 2][16] output.  T % 4 == 0: a row is
+// entirely inside or outside the sequence.  EW = 4: both pooled samples per warp; EW = 8: pooled sample = column half.
+template <int SPLIT, int EW>
+__device__ __forceinline__ void tc_epilogue_foldpool(const TcP &p, uint32_t trow, int half, int seq, int srow, bool row_ok,
+                                                     const float *s_bias) {
+    static_assert(EW == 4 || EW == 8, "fold + pool epilogue: one or two warps per TMEM lane quarter");
+    constexpr int PER = EW == 4 ? 2 : 1;
+    uint16_t *y16 = reinterpret_cast<uint16_t *>(p.y) + ((int64_t)seq * p.T_out + srow) * 32;
+#pragma unroll
+    for (int jj = 0; jj < PER; ++jj) {
+        const int j = half * PER + jj;
+        uint32_t r[32];
+        {
+            uint32_t(&r0)[16] = *reinterpret_cast<uint32_t(*)[16]>(&r[0]);
+            uint32_t(&r1)[16] = *reinterpret_cast<uint32_t(*)[16]>(&r[16]);
+            tmem_ld16_nowait(trow + (uint32_t)(32 * j), r0);
+            tmem_ld16_nowait(trow + (uint32_t)(32 * j + 16), r1);
+        }
+        tmem_ld_wait();
+        if (!row_ok) continue;
+        float w[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 ba = *reinterpret_cast<const float4 *>(&s_bias[32 * j + 4 * q]);
+            const float4 bb = *reinterpret_cast<const float4 *>(&s_bias[32 * j + 16 + 4 * q]);
+            w[4 * q + 0] = fmaxf(fmaxf(__uint_as_float(r[4 * q + 0]) + ba.x, __uint_as_float(r[16 + 4 * q + 0]) + bb.x), 0.f);
+            w[4 * q + 1] = fmaxf(fmaxf(__uint_as_float(r[4 * q + 1]) + ba.y, __uint_as_float(r[16 + 4 * q + 1]) + bb.y), 0.f);
+            w[4 * q + 2] = fmaxf(fmaxf(__uint_as_float(r[4 * q + 2]) + ba.z, __uint_as_float(r[16 + 4 * q + 2]) + bb.z), 0.f);
+            w[4 * q + 3] = fmaxf(fmaxf(__uint_as_float(r[4 * q + 3]) + ba.w, __uint_as_float(r[16 + 4 * q + 3]) + bb.w), 0.f);
+        }
+        uint4 h0, l0, h1, l1;
+        pack8_split16<SPLIT>(&w[0], h0, l0);
+        pack8_split16<SPLIT>(&w[8], h1, l1);
+        uint16_t *yb = y16 + 16 * j;
+        if (p.st256) {
+            st_global_256(yb, h0, h1);
+            if (SPLIT == 2) st_global_256(yb + p.y_split, l0, l1);
+        } else {
+            *reinterpret_cast<uint4 *>(yb) = h0;
+            *reinterpret_cast<uint4 *>(yb + 8) = h1;
+            if (SPLIT == 2) {
+                *reinterpret_cast<uint4 *>(yb + p.y_split) = l0;
+                *reinterpret_cast<uint4 *>(yb + 8 + p.y_split) = l1;
+            }
+        }
+    }
+}
+
 // NTAPS > 0: the tile's MMA schedule is fixed at compile time (umma_conv_tile); NTAPS == 0: generic
 // instance that walks the host-built schedule table (any layer shape; slower issue).
 // FLAGS >= 0: epilogue options fixed at compile time (tc_epilogue_fixed); FLAGS < 0: run-time options (any layer).
@@ -366,7 +417,9 @@ __global__ void __launch_bounds__(32 * (EW + 4), EW == 16 ? 1 : EW == 8 ? 2 : 4)
             const bool st = (p.pool == 2) ? (row_ok && !(lane & 1)) : row_ok;
             const int t0 = (p.pool == 2) ? (srow >> 1) : p.ph * srow;
             const int64_t orow0 = (int64_t)seq * p.y_pitch + p.y_roff + t0;
-            if constexpr (FLAGS >= 0) {
+            if constexpr (FLAGS == 8) {
+                if (!(p.dbg & 4)) tc_epilogue_foldpool<SPLIT, EW>(p, trow, half, seq, srow, row_ok, s_bias);
+            } else if constexpr (FLAGS >= 0) {
                 if (!(p.dbg & 4)) tc_epilogue_fixed<NOUT, SPLIT, EW, FLAGS>(p, trow, half, lane, seq, srow, row_ok, g, s_bias, s_psc, s_psh);
             } else if (!(p.dbg & 4)) {
 #pragma unroll
@@ -828,7 +881,19 @@ int tc_launch(const TcLayer &L, const TcIO &io, cudaStream_t s) {
     const bool extra = io.res || io.y32 || io.post_scale;
     const bool plain = !custom && io.out_fmt == 0 && L.nout == L.ph * L.cout && io.cout_cl == L.cout &&
                        (extra ? (io.act == ACT_RELU || io.act == ACT_NONE) : io.act == ACT_RELU);
-    const int flags = plain ? ((io.pool == 2 ? 1 : 0) | (L.ph == 2 ? 2 : 0) | (extra ? 4 : 0)) : -1;
+    int flags = plain ? ((io.pool == 2 ? 1 : 0) | (L.ph == 2 ? 2 : 0) | (extra ? 4 : 0)) : -1;
+    if (io.foldpool) {
+        VP_REQUIRE(plain && flags == 0 && L.nout == 64 && st == 3 && (sq == 2 || sq == 4), VP_ERR_UNSUPPORTED,
+                   "tc conv: fold + pool epilogue needs a plain 64-column 3-tap layer (N=%d, %d taps, %d pairs)", L.nout, st, sq);
+        flags = 8;
+        // ReLU + MaxPool inside the accumulator row; EW = 4 at >= 3 CTAs per SM (32 -> 4 x 16), 8 otherwise (64 -> 4 x 16)
+        if (sq == 2) {
+            if (L.split == 2) return launch_tc<64, 2, 3, 2, 4, 8>(p, grid, smem, s);
+            return launch_tc<64, 1, 3, 2, 4, 8>(p, grid, smem, s);
+        }
+        if (L.split == 2) return launch_tc<64, 2, 3, 4, 8, 8>(p, grid, smem, s);
+        return launch_tc<64, 1, 3, 4, 8, 8>(p, grid, smem, s);
+    }
 #define VP_TC_FIXED(N, T, Q, F)                                                                                  \
     if (!generic_only && L.nout == N && st == T && sq == Q && flags == F) {                                      \
         if (L.split == 2) return launch_tc<N, 2, T, Q, tc_epi_warps<N, 2, T, Q>(), F>(p, grid, smem, s);         \

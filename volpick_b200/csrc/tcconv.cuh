@@ -104,6 +104,9 @@ struct TcIO {
     int x2_pitch = 0, x2_roff = 0, cin_a = 0;  // cin_a: channels taken from x when x2 is set
     const float *head_w = nullptr, *head_b = nullptr;  // HOST pointers, out_fmt 2
     int fold = 1, fold_c = 0, fold_o = 0, fold_T = 0;   // output time folding (see TcP)
+    // 1: the layer is a 'same' conv folded over 4 samples (64 columns = 4 samples x 16 channels) followed by ReLU + MaxPool1d(2):
+    // the epilogue pools inside the accumulator row and writes [T / 4][2 x 16] = [T / 2][16] (tc_epilogue_foldpool)
+    int foldpool = 0;
 };
 int tc_out_len(const TcLayer &L, int T_in, int pool);
 int tc_launch(const TcLayer &L, const TcIO &io, cudaStream_t s);
