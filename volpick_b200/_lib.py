@@ -10,7 +10,7 @@ import os
 from typing import Optional
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libvolpick_b200.so")
+LIB_PATH = os.environ.get("VP_LIB_PATH") or os.path.join(HERE, "libvolpick_b200.so")  # VP_LIB_PATH: A/B builds
 
 VP_OK = 0
 VP_ERR_ARG, VP_ERR_CUDA, VP_ERR_CAPACITY, VP_ERR_WORKSPACE, VP_ERR_UNSUPPORTED = -1, -2, -3, -4, -5

@@ -294,39 +294,6 @@ __global__ void __launch_bounds__(32 * (EW + 4), EW == 16 ? 1 : EW == 8 ? 2 : 4)
             mbar_wait(&empty_bar[stage], phase ^ 1u);
             const int m0 = tile * 128;
             const uint32_t sbase = sA_u + (uint32_t)stage * a_bytes;
-            if (p.coal_sh > 0) {
-                // coalesced mapping: thread = (plane c, rows r0, r0 + step, ...); the cin8 lanes of a row read its
-                // contiguous 16 cin8 bytes.  (seq, u) advance incrementally: no division per row.
-                const int sh = p.coal_sh, step = TC_PRODUCERS >> sh;
-                const int c = ptid & (cin8 - 1);
-                int r = ptid >> sh;
-                int v = m0 + p.row0 + r, seq, u;
-                if (v >= 0) {
-                    seq = v / p.Tp;
-                    u = v - seq * p.Tp;
-                } else {
-                    seq = -1;
-                    u = v + p.Tp;  // row0 > -Tp
-                }
-                const bool fromA = c < cinA8;
-                const uint16_t *base = fromA ? xg + c * 8 : p.x2 + (c - cinA8) * 8;
-                const int64_t pitchX = fromA ? p.x_pitch : p.x2_pitch, splitX = fromA ? p.x_split : p.x2_split;
-                const int roffX = fromA ? p.x_roff : p.x2_roff, CX = fromA ? CA : CB;
-                for (; r < n_rows && !(p.dbg & 1); r += step) {
-                    const bool valid = seq >= 0 && seq < p.NS && u < p.T_eff;
-                    const int srow = (p.ups == 2) ? (u >> 1) : u;
-                    const uint16_t *src = valid ? base + ((int64_t)seq * pitchX + roffX + srow) * CX : xg;
-                    const uint32_t nb = valid ? 16u : 0u;
-                    const uint32_t dst = sbase + (uint32_t)c * PL + (uint32_t)r * 16u;
-#pragma unroll
-                    for (int s = 0; s < SPLIT; ++s) cp_async16(dst + (uint32_t)(s * cin8) * PL, valid ? src + (int64_t)s * splitX : xg, nb);
-                    u += step;
-                    while (u >= p.Tp) {
-                        u -= p.Tp;
-                        ++seq;
-                    }
-                }
-            } else
             for (int r = ptid; r < n_rows && !(p.dbg & 1); r += TC_PRODUCERS) {
                 const int v = m0 + p.row0 + r;
                 bool valid = v >= 0;
@@ -513,7 +480,7 @@ __global__ void __launch_bounds__(32 * (EW + 4), EW == 16 ? 1 : EW == 8 ? 2 : 4)
                             uint4 hi, lo;
                             tc_pack8<SPLIT>(w8, hi, lo);
                             uint16_t *yb = reinterpret_cast<uint16_t *>(p.y) + (int64_t)g * p.y_gs + (orow0 + phi) * p.cout_cl + c0;
-                            if (CH == 16 && g8 == 0) {  // wait for the neighbouring group: one 32-byte store when it follows
+                            if (CH == 16 && g8 == 0 && p.st256) {  // wait for the neighbouring group: one 32-byte store when it follows
                                 pend = yb;
                                 pend_hi = hi;
                                 pend_lo = lo;
@@ -771,18 +738,6 @@ int tc_launch(const TcLayer &L, const TcIO &io, cudaStream_t s) {
     p.n_rows = 128 + L.halo;
     p.cin8 = L.cin / 8;
     p.pitch = p.n_rows;
-    p.coal_sh = -1;
-    {
-        static const bool coal_off = getenv("VP_TC_COAL") && atoi(getenv("VP_TC_COAL")) == 0;
-        const int c8 = p.cin8;
-        if (!coal_off && c8 >= 2 && (c8 & (c8 - 1)) == 0 && TC_PRODUCERS % c8 == 0) {
-            int sh = 0;
-            while ((1 << sh) < c8) ++sh;
-            p.coal_sh = sh;
-            const int q = 8 / std::min(c8, 8);  // staged rows covered by a group of 8 lanes
-            while (p.pitch % (2 * q) != q) ++p.pitch;
-        }
-    }
     p.w = io.w_dev;
     p.w_gs = (int64_t)L.n_blocks * L.split * 2 * L.nout * 8;
     p.n_blocks = L.n_blocks;
@@ -839,7 +794,8 @@ int tc_launch(const TcLayer &L, const TcIO &io, cudaStream_t s) {
     const bool custom = p.fold > 1 || io.x2 || p.x_pitch != io.T_in || p.x_roff != 0 || p.y_pitch != p.T_out || p.y_roff != 0 || io.T_valid > 0 ||
                         io.out_fmt == 2;
     p.out_fmt = io.out_fmt;
-    p.st256 = (io.out_fmt == 0 && reinterpret_cast<uintptr_t>(io.y) % 32 == 0 && (io.y_split * 2) % 32 == 0 && (io.y_gs * 2) % 32 == 0 &&
+    static const bool st256_off = getenv("VP_TC_ST256") && atoi(getenv("VP_TC_ST256")) == 0;  // debugging aid
+    p.st256 = (!st256_off && io.out_fmt == 0 && reinterpret_cast<uintptr_t>(io.y) % 32 == 0 && (io.y_split * 2) % 32 == 0 && (io.y_gs * 2) % 32 == 0 &&
                L.cout % 16 == 0)
                   ? 1
                   : 0;

@@ -28,10 +28,11 @@ struct TcP {
     int64_t x2_split;
     int x2_pitch, x2_roff, cinA8;
     int T_in, T_eff, ups, Tp, NS, row0, n_rows, cin8, n_stages;
-    // plane pitch of the staged tile in 16-byte rows (>= n_rows) and log2(cin8) of the coalesced producer mapping (-1: one
-    // thread per row): cin8 consecutive lanes copy the planes of ONE global row, and the pitch is chosen so that 8 lanes
-    // store to 8 different 16-byte bank groups (pitch odd for >= 8 planes, 2 mod 4 for 4, 4 mod 8 for 2)
-    int pitch, coal_sh;
+    // plane pitch of the staged tile in 16-byte rows (>= n_rows).  The producers copy one staged row per thread, plane after
+    // plane (16-byte pieces at the row-pitch lane stride).  A coalesced mapping (consecutive lanes = consecutive planes of one
+    // row, conflict-free padded pitch) cut the LDGSTS shared-memory wavefronts 4-7x but was measured SLOWER (EQT tcconv class
+    // 6.29 -> 6.36 ms, PhaseNet 3.31 -> 3.43 ms): the per-piece index arithmetic costs more issue slots than the wavefronts.
+    int pitch;
     int st256;  // 1: the 16-bit output rows, group and split offsets are 32-byte aligned -> adjacent 8-channel groups leave as one 256-bit store
     const uint16_t *w;  // [G][n_blocks][SPLIT][2][NOUT][8]
     int64_t w_gs;
