@@ -42,8 +42,8 @@ KCLASS_FLOP_PER_WINDOW = {
     ("phasenet", "tcconv"): 38.92e6,  # every Conv1d / ConvTranspose1d of the network runs in tcconv_kernel
 }
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture (profiles/):
-KCLASS_NCU_TRAFFIC = {("eqtransformer", "decb", "f16x3"): {"bytes_per_launch": 535.10e6 + 230.38e6, "windows_per_launch": 4096,
-                                                            "source": "profiles/r01e_f16x3_top_kernels_ncu_full.md"}}
+KCLASS_NCU_TRAFFIC = {("eqtransformer", "decb", "f16x3"): {"bytes_per_launch": 535.12e6 + 229.44e6, "windows_per_launch": 4096,
+                                                            "source": "profiles/r01g_f16x3_top_kernels_ncu_full.md"}}
 CONFIGS = {
     "eqtransformer": dict(overlap=5500, blinding=(500, 500), stacking="avg", P_threshold=0.2, S_threshold=0.2),
     "phasenet": dict(overlap=1500, blinding=(0, 0), stacking="avg", P_threshold=0.2, S_threshold=0.2),
