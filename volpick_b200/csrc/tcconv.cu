@@ -867,23 +867,8 @@ int tc_launch(const TcLayer &L, const TcIO &io, cudaStream_t s) {
     VP_TC_FIXED(128, 3, 4, 2);  // decoder.convs.1 polyphase (64 -> 2 x 64)
     VP_TC_FIXED(32, 5, 4, 0);   // decoder.convs.2 (64 -> 32, k5, loader-side up-sampling)
 #undef VP_TC_FIXED
-    // compile-time MMA schedule + run-time epilogue: PhaseNet's k = 7 concat convs and folded level-0 layers issue 36 - 168
-    // MMAs per tile, where the schedule-table walk of the generic instance (~80 cycles per MMA) is the issuer's bottleneck
-#define VP_TC_SCHED(N, T, Q)                                                                                          \
-    if (!generic_only && flags < 0 && L.nout == N && st == T && sq == Q) {                                            \
-        if (occ <= 2 && N >= 32) {                                                                                    \
-            if (L.split == 2) return launch_tc<N, 2, T, Q, 8, -1>(p, grid, smem, s);                                  \
-            return launch_tc<N, 1, T, Q, 8, -1>(p, grid, smem, s);                                                    \
-        }                                                                                                             \
-        if (L.split == 2) return launch_tc<N, 2, T, Q, 4, -1>(p, grid, smem, s);                                      \
-        return launch_tc<N, 1, T, Q, 4, -1>(p, grid, smem, s);                                                        \
-    }
-    VP_TC_SCHED(32, 3, 4);  // PhaseNet up3 concat conv, folded x4 (64 -> 4 x 8)
-    VP_TC_SCHED(32, 3, 2);  // PhaseNet down0 'same' conv, folded x4 (32 -> 4 x 8)
-    VP_TC_SCHED(16, 7, 2);  // PhaseNet up2 concat conv (32 -> 16, k7)
-    VP_TC_SCHED(32, 7, 4);  // PhaseNet up1 concat conv (64 -> 32, k7)
-    VP_TC_SCHED(16, 7, 8);  // PhaseNet up0 concat conv (128 -> 4 x 16, k7)
-#undef VP_TC_SCHED
+    // (Compile-time MMA schedules with the run-time epilogue for PhaseNet's k = 7 concat convs and folded level-0 layers were
+    // measured neutral, 3.41 vs 3.43 ms per station-day: their issue rate is not the limit.  They run the generic instances.)
     // generic instances with 8 epilogue warps (two per TMEM lane quarter) when at most two CTAs fit an SM: with four, the
     // TMEM -> convert -> store chain of a wide tile is the serial bottleneck of the CTA
     static const bool ew8_off = getenv("VP_TC_EW8") && atoi(getenv("VP_TC_EW8")) == 0;
