@@ -27,6 +27,10 @@ CASES = [
     ("dec6_poly_k11", 2, 16, 3000, 8, 11, 1, 0, 1, 1),
     ("cin3_padded", 2, 3, 700, 8, 11, 0, 0, 1, 2),
     ("single_row_tile", 1, 16, 5, 16, 7, 0, 0, 0, 1),
+    # mode 3: the same conv on the [T / 4][4 C] view, ReLU + MaxPool1d(2) inside the accumulator row (encoder.convs.1 / .2)
+    ("enc1_fold4_pool", 3, 8, 3000, 16, 9, 3, 0, 1, 2),
+    ("enc2_fold4_pool", 5, 16, 1500, 16, 7, 3, 0, 1, 2),
+    ("fold4_pool_short", 2, 16, 8, 16, 7, 3, 0, 1, 2),
 ]
 
 

@@ -245,7 +245,7 @@ struct vp_model {
     // tensor-core (tcgen05) weight sets: [0] = fp16 hi/lo split (f16x3), [1] = bf16
     struct TcSet {
         TcLayer enc[7], dec[7], head;
-        TcLayer encf[3];           // encoder.convs.1 / .2 with 4 time steps folded into the MMA K / N (index = layer; see fold4_same)
+        TcLayer encf[3];           // encoder.convs.1 / .2 with 4 time steps folded into the MMA K / N (index = layer; see tc_fold4_same)
         TcLayer res1[7], res2[7];  // res-CNN convs (BatchNorm + ReLU of their inputs live in the producer's epilogue)
         TcLayer lproj;             // bi_lstm_stack.members.0: input projection of both directions as a 1x1 conv (64 -> 2 x 64 gates)
         uint16_t *d_w = nullptr;
@@ -326,26 +326,6 @@ static int upload_tc(vp_model::TcSet &ts) {
     }
     ts.ready = true;
     return VP_OK;
-}
-
-// 'same' Conv1d (odd k <= 9, pad (k - 1) / 2) with 4 time steps folded into the channels: on the [T / 4][4 C] view of a
-// channel-last buffer (the same bytes) it is a 3-tap row conv (row pad 1) from 4 cin to 4 cout columns; column = sample *
-// cout + channel.  The 8 / 16-channel encoder layers are bound by the shared-memory reads of the A operand (4 KB per
-// tcgen05.mma whatever its N), so 2.5x / 1.75x fewer, wider MMAs win.
-static void fold4_same(const float *W, const float *bias, int cout, int cin, int k, std::vector<float> &wf, std::vector<float> &bf) {
-    const int F = 4, P = (k - 1) / 2;
-    wf.assign((size_t)F * cout * F * cin * 3, 0.f);
-    bf.assign((size_t)F * cout, 0.f);
-    for (int q = 0; q < F; ++q)
-        for (int co = 0; co < cout; ++co) {
-            bf[(size_t)q * cout + co] = bias ? bias[co] : 0.f;
-            for (int j = 0; j < k; ++j) {
-                const int pos = q + j - P;  // input sample relative to 4 * row
-                const int d = pos >= 0 ? pos / F : -((-pos + F - 1) / F), lane = pos - d * F;  // row tap d in {-1, 0, 1}
-                for (int ci = 0; ci < cin; ++ci)
-                    wf[(((size_t)q * cout + co) * (F * cin) + lane * cin + ci) * 3 + (d + 1)] = W[((size_t)co * cin + ci) * k + j];
-            }
-        }
 }
 
 static const int kEncC[8] = {3, 8, 16, 16, 32, 32, 64, 64};
@@ -465,7 +445,7 @@ static int build_eqt(vp_model *m, Cursor &cur, Packed &pk) {
             if (rc != VP_OK) return rc;
             if (i == 1 || i == 2) {  // 8 -> 16 (k9) and 16 -> 16 (k7): folded x4 -> 32 / 64 -> 64 columns, 3 row taps
                 std::vector<float> wf, bf;
-                fold4_same(W, eB[i], kEncC[i + 1], cin, kEncK[i], wf, bf);
+                tc_fold4_same(W, eB[i], kEncC[i + 1], cin, kEncK[i], wf, bf);
                 const float *wfl[1] = {wf.data()}, *bfl[1] = {bf.data()};
                 rc = tc_build_layer(ts.encf[i], TC_DIRECT, 4 * cin, 4 * kEncC[i + 1], 3, 0, split, 1, wfl, bfl, 1);
                 if (rc != VP_OK) return rc;

@@ -562,6 +562,24 @@ int launch_pack_cl16(const float *x, int64_t x_ss, int64_t x_cs, int NS, int C, 
     return VP_OK;
 }
 
+// channel-last 16-bit rows [split][NS][T][C] -> fp32 channel-first (NS, C, T) (layer-level tests of 16-bit outputs)
+__global__ void unpack_cl16_kernel(const uint16_t *__restrict__ x, int64_t x_split, int split, int fmt16, int NS, int C, int T,
+                                   float *__restrict__ y) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // ((seq, t), c)
+    if (i >= (int64_t)NS * T * C) return;
+    const int c = (int)(i % C);
+    const int64_t st = i / C, seq = st / T;
+    const int t = (int)(st - seq * T);
+    float v;
+    if (fmt16 == 0) {
+        v = __half2float(__ushort_as_half(x[i]));
+        if (split == 2) v += __half2float(__ushort_as_half(x[i + x_split]));
+    } else {
+        v = __bfloat162float(__ushort_as_bfloat16(x[i]));
+    }
+    y[(seq * C + c) * T + t] = v;
+}
+
 // ------------------------------------------------------------------------------------------ host: layer builder
 static inline int floordiv2(int a) { return (a >= 0) ? a / 2 : -((-a + 1) / 2); }
 
@@ -574,6 +592,26 @@ static void to16(float w, int split, uint16_t &hi, uint16_t &lo) {
         hi = __bfloat16_as_ushort(__float2bfloat16_rn(w));
         lo = 0;
     }
+}
+
+// 'same' Conv1d (odd k <= 9, pad (k - 1) / 2) with 4 time steps folded into the channels: on the [T / 4][4 C] view of a
+// channel-last buffer (the same bytes) it is a 3-tap row conv (row pad 1) from 4 cin to 4 cout columns; column = sample *
+// cout + channel.  The 8 / 16-channel encoder layers are bound by the shared-memory reads of the A operand (4 KB per
+// tcgen05.mma whatever its N), so 2.5x / 1.75x fewer, wider MMAs win.
+void tc_fold4_same(const float *W, const float *bias, int cout, int cin, int k, std::vector<float> &wf, std::vector<float> &bf) {
+    const int F = 4, P = (k - 1) / 2;
+    wf.assign((size_t)F * cout * F * cin * 3, 0.f);
+    bf.assign((size_t)F * cout, 0.f);
+    for (int q = 0; q < F; ++q)
+        for (int co = 0; co < cout; ++co) {
+            bf[(size_t)q * cout + co] = bias ? bias[co] : 0.f;
+            for (int j = 0; j < k; ++j) {
+                const int pos = q + j - P;  // input sample relative to 4 * row
+                const int d = pos >= 0 ? pos / F : -((-pos + F - 1) / F), lane = pos - d * F;  // row tap d in {-1, 0, 1}
+                for (int ci = 0; ci < cin; ++ci)
+                    wf[(((size_t)q * cout + co) * (F * cin) + lane * cin + ci) * 3 + (d + 1)] = W[((size_t)co * cin + ci) * k + j];
+            }
+        }
 }
 
 int tc_build_layer(TcLayer &L, int mode, int cin, int cout, int k, int crop, int split, int groups,
@@ -904,7 +942,8 @@ using namespace vp;
 // Layer-level parity hook: one Conv1d through the tensor-core path.
 //   x: device fp32 (NS, CIN, T_in); w_host: (COUT, CIN, K) fp32 on the HOST; y: device fp32 (NS, COUT, T_out)
 //   mode: 0 direct 'same' conv, 1 x2 nearest up-sampling folded into the weights (polyphase),
-//         2 direct conv on the x2 up-sampled (loader-side) input minus `crop` trailing samples
+//         2 direct conv on the x2 up-sampled (loader-side) input minus `crop` trailing samples,
+//         3 the direct 'same' conv + ReLU + MaxPool1d(2) on the time-folded [T / 4][4 C] view (encoder.convs.1 / .2: 8 / 16 -> 16)
 //   precision: VP_PREC_F16X3 | VP_PREC_BF16
 extern "C" VP_API int vp_tcconv_debug(const float *x, int NS, int CIN, int T_in, const float *w_host, const float *bias_host,
                                       int COUT, int K, int mode, int crop, int act, int pool, int precision, float *y,
@@ -923,7 +962,18 @@ extern "C" VP_API int vp_tcconv_debug(const float *x, int NS, int CIN, int T_in,
     TcLayer L;
     const float *wl[1] = {wp.data()};
     const float *bl[1] = {bias_host};
-    int rc = tc_build_layer(L, mode, cin_p, COUT, K, crop, split, 1, wl, bl);
+    int rc;
+    const bool foldpool = mode == 3;  // 'same' conv on the [T / 4][4 C] view + ReLU + MaxPool1d(2) inside the accumulator row
+    std::vector<float> wf, bf;
+    if (foldpool) {
+        VP_REQUIRE(COUT == 16 && (cin_p == 8 || cin_p == 16) && T_in % 4 == 0 && pool == 2 && act == ACT_RELU && (K & 1) && K <= 9,
+                   VP_ERR_UNSUPPORTED, "vp_tcconv_debug: mode 3 is the folded encoder layer (8 / 16 -> 16 channels, ReLU, pool 2, T %% 4 == 0)");
+        tc_fold4_same(wp.data(), bias_host, COUT, cin_p, K, wf, bf);
+        const float *wfl[1] = {wf.data()}, *bfl[1] = {bf.data()};
+        rc = tc_build_layer(L, TC_DIRECT, 4 * cin_p, 4 * COUT, 3, 0, split, 1, wfl, bfl, 1);
+    } else {
+        rc = tc_build_layer(L, mode, cin_p, COUT, K, crop, split, 1, wl, bl);
+    }
     if (rc != VP_OK) return rc;
     uint16_t *d_x = nullptr, *d_w = nullptr;
     float *d_b = nullptr;
@@ -953,7 +1003,29 @@ extern "C" VP_API int vp_tcconv_debug(const float *x, int NS, int CIN, int T_in,
         io.y_ss = (int64_t)COUT * T_out;
         io.y_cs = T_out;
         io.cout_cl = 0;
-        rc = tc_launch(L, io, s);
+        if (foldpool) {  // 16-bit channel-last output [split][NS][T / 4][2 x 16] = [NS][T / 2][16], unpacked to fp32 (NS, 16, T / 2)
+            const int64_t ys = (int64_t)NS * (T_in / 2) * 16;
+            uint16_t *d_y16 = nullptr;
+            VP_CUDA_CHECK(cudaMalloc(&d_y16, (size_t)split * ys * 2 + 64));
+            io.T_in = T_in / 4;
+            io.pool = 1;
+            io.foldpool = 1;
+            io.out_fmt = 0;
+            io.y = d_y16;
+            io.y_split = ys;
+            io.y_ss = 0;
+            io.y_cs = 0;
+            io.cout_cl = L.cout;
+            rc = tc_launch(L, io, s);
+            if (rc == VP_OK) {
+                const int64_t n = ys;
+                unpack_cl16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_y16, ys, split, split == 2 ? 0 : 1, NS, 16, T_in / 2, y);
+            }
+            cudaStreamSynchronize(s);
+            cudaFree(d_y16);
+        } else {
+            rc = tc_launch(L, io, s);
+        }
     }
     cudaError_t e = cudaStreamSynchronize(s);
     cudaFree(d_x);

@@ -84,6 +84,9 @@ enum { TC_DIRECT = 0, TC_POLYPHASE = 1, TC_DIRECT_UPS = 2 };
 int tc_build_layer(TcLayer &L, int mode, int cin, int cout, int k, int crop, int split, int groups,
                    const float *const *weights, const float *const *bias, int pad_left = -1);
 
+// 'same' Conv1d (odd k <= 9) folded over 4 time steps: (4 cout, 4 cin, 3) row-conv weights + replicated bias (tcconv.cu)
+void tc_fold4_same(const float *W, const float *bias, int cout, int cin, int k, std::vector<float> &wf, std::vector<float> &bf);
+
 struct TcIO {
     const uint16_t *x;
     int64_t x_split, x_gs;
