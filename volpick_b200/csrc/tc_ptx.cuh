@@ -38,8 +38,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "bra LAB_WAIT;\n\t"
         "DONE:\n\t"
         "}" ::"r"(smem_u32(bar)),
-        "r"(parity), "r"(0x989680u)  // suspend-time hint: the warp sleeps in hardware until the phase completes instead of
-                                     // re-polling every ~30 cycles (polls were 27 - 67 % of the executed instructions)
+        "r"(parity), "r"(0x989680u)  // suspend-time hint (as CUTLASS passes it).  Measured neutral on sm_100a: the polls stay
+                                     // 27 - 67 % of the executed instructions of these kernels, with or without the hint
         : "memory");
 }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
