@@ -1334,6 +1334,7 @@ static int run_pn_tc(Runner &r, const float *x, float *y, Arena &ar) {
         io.y_cs = 0;
         io.cout_cl = 0;
         io.x_pitch = rows_in;
+        io.ca = 1;  // PhaseNet: L1-cached staging loads (see TcIO::ca)
         return io;
     };
     // dense 16-bit output [B][rows_out][c_total] (+ group column offset), or the fp32 debug tap

@@ -310,11 +310,18 @@ __global__ void __launch_bounds__(32 * (EW + 4), EW == 16 ? 1 : EW == 8 ? 2 : 4)
 #pragma unroll
                 for (int s = 0; s < SPLIT; ++s) {
                     const uint16_t *ss = valid ? (src + (int64_t)s * p.x_split) : xg;
-                    for (int c = 0; c < cinA8; ++c)
-                        cp_async16(sbase + (uint32_t)(s * cin8 + c) * PL + (uint32_t)r * 16u, ss + c * 8, nb);
                     const uint16_t *s2 = (valid && CB) ? (src2 + (int64_t)s * p.x2_split) : xg;
-                    for (int c = cinA8; c < cin8; ++c)
-                        cp_async16(sbase + (uint32_t)(s * cin8 + c) * PL + (uint32_t)r * 16u, s2 + (c - cinA8) * 8, nb);
+                    if (p.ca) {
+                        for (int c = 0; c < cinA8; ++c)
+                            cp_async16_ca(sbase + (uint32_t)(s * cin8 + c) * PL + (uint32_t)r * 16u, ss + c * 8, nb);
+                        for (int c = cinA8; c < cin8; ++c)
+                            cp_async16_ca(sbase + (uint32_t)(s * cin8 + c) * PL + (uint32_t)r * 16u, s2 + (c - cinA8) * 8, nb);
+                    } else {
+                        for (int c = 0; c < cinA8; ++c)
+                            cp_async16(sbase + (uint32_t)(s * cin8 + c) * PL + (uint32_t)r * 16u, ss + c * 8, nb);
+                        for (int c = cinA8; c < cin8; ++c)
+                            cp_async16(sbase + (uint32_t)(s * cin8 + c) * PL + (uint32_t)r * 16u, s2 + (c - cinA8) * 8, nb);
+                    }
                 }
             }
             cp_async_mbar_arrive_noinc(&full_bar[stage]);
@@ -776,6 +783,10 @@ int tc_launch(const TcLayer &L, const TcIO &io, cudaStream_t s) {
     p.n_rows = 128 + L.halo;
     p.cin8 = L.cin / 8;
     p.pitch = p.n_rows;
+    {
+        static const int ca = getenv("VP_TC_CA") ? atoi(getenv("VP_TC_CA")) : 1;  // debugging aid
+        p.ca = (ca && io.ca && p.cin8 >= 2) ? 1 : 0;  // rows of >= 32 bytes: two 16-byte pieces per sector
+    }
     p.w = io.w_dev;
     p.w_gs = (int64_t)L.n_blocks * L.split * 2 * L.nout * 8;
     p.n_blocks = L.n_blocks;

@@ -33,6 +33,7 @@ struct TcP {
     // row, conflict-free padded pitch) cut the LDGSTS shared-memory wavefronts 4-7x but was measured SLOWER (EQT tcconv class
     // 6.29 -> 6.36 ms, PhaseNet 3.31 -> 3.43 ms): the per-piece index arithmetic costs more issue slots than the wavefronts.
     int pitch;
+    int ca;  // 1: producers use cp.async.ca (the sector of a 16-byte piece stays in L1 for the next plane of the row)
     int st256;  // 1: the 16-bit output rows, group and split offsets are 32-byte aligned -> adjacent 8-channel groups leave as one 256-bit store
     const uint16_t *w;  // [G][n_blocks][SPLIT][2][NOUT][8]
     int64_t w_gs;
@@ -111,6 +112,9 @@ struct TcIO {
     // 1: the layer is a 'same' conv folded over 4 samples (64 columns = 4 samples x 16 channels) followed by ReLU + MaxPool1d(2):
     // the epilogue pools inside the accumulator row and writes [T / 4][2 x 16] = [T / 2][16] (tc_epilogue_foldpool)
     int foldpool = 0;
+    // 1: stage the input with cp.async.ca (sectors kept in L1 between the two 16-byte pieces of a row).  Measured: PhaseNet
+    // tcconv class 3.30 -> 3.21 ms per station-day, EQTransformer 6.23 -> 6.30 ms: set by the PhaseNet forward only.
+    int ca = 0;
 };
 int tc_out_len(const TcLayer &L, int T_in, int pool);
 int tc_launch(const TcLayer &L, const TcIO &io, cudaStream_t s);
