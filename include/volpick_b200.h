@@ -147,7 +147,9 @@ VP_API const char *vp_forward_tap_names(const vp_model *m); /* comma separated *
 /* Debug/parity: ONE Conv1d through the tcgen05 path (volpick_b200/csrc/tcconv.cu).  x: device fp32
  * (NS, CIN, T_in); w_host / bias_host: HOST fp32 (COUT, CIN, K) / (COUT) or NULL; y: device fp32
  * (NS, COUT, T_out).  mode 0: 'same' conv; 1: x2 nearest up-sampling folded into the weights; 2: conv on
- * the x2 up-sampled input minus `crop` trailing samples.  act: 0 none, 1 ReLU, 2 sigmoid.  pool: 1 | 2. */
+ * the x2 up-sampled input minus `crop` trailing samples; 3: the 'same' conv + ReLU + MaxPool1d(2) on the time-folded
+ * [T / 4][4 C] view (encoder.convs.1 / .2: CIN 8 | 16, COUT 16, odd K <= 9, T_in % 4 == 0, act 1, pool 2).
+ * act: 0 none, 1 ReLU, 2 sigmoid.  pool: 1 | 2. */
 VP_API int vp_tcconv_debug(const float *x, int NS, int CIN, int T_in, const float *w_host, const float *bias_host, int COUT,
                            int K, int mode, int crop, int act, int pool, int precision, float *y, void *stream);
 
