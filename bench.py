@@ -45,8 +45,17 @@ KCLASS_FLOP_PER_WINDOW = {
 KCLASS_NCU_TRAFFIC = {("eqtransformer", "decb", "f16x3"): {"bytes_per_launch": 535.12e6 + 229.44e6, "windows_per_launch": 4096,
                                                             "source": "profiles/r01g_f16x3_top_kernels_ncu_full.md"}}
 CONFIGS = {
+    # BASELINE.json configs[1] / configs[3]: EQTransformer, overlap 5500, blinding (500, 500), avg, P/S threshold 0.2
     "eqtransformer": dict(overlap=5500, blinding=(500, 500), stacking="avg", P_threshold=0.2, S_threshold=0.2),
-    "phasenet": dict(overlap=1500, blinding=(0, 0), stacking="avg", P_threshold=0.2, S_threshold=0.2),
+    # BASELINE.json configs[0] / configs[2]: PhaseNet, "overlap default" (1500), no blinding, thresholds of the shipped JSON
+    # (/root/reference/Final_models/volpick/phasenet/volpick.json.v1:10-13)
+    "phasenet": dict(overlap=1500, blinding=(0, 0), stacking="avg", P_threshold=0.39, S_threshold=0.34),
+}
+WORKLOAD_LABEL = {
+    "eqtransformer": "EQTransformer-volpick classify() on one synthetic 3-C 100 Hz station-day per GPU per step "
+                     "(BASELINE.json configs[1]; the unit of configs[3])",
+    "phasenet": "PhaseNet-volpick classify() on one synthetic 3-C 100 Hz station-day per GPU per step "
+                "(the unit of BASELINE.json configs[2]; configs[0] is the same call on a station-hour)",
 }
 
 
@@ -189,8 +198,7 @@ def workload_config(kind: str, note: str = ""):
     nwin = (N_DAY - L) // stride + 1
     if (nwin - 1) * stride + L < N_DAY:
         nwin += 1
-    d = {"workload": f"{'EQTransformer' if kind == 'eqtransformer' else 'PhaseNet'}-volpick classify() on one synthetic "
-                     f"3-C 100 Hz station-day per GPU per step (BASELINE.json configs[1])",
+    d = {"workload": WORKLOAD_LABEL[kind],
          "samples_per_record": N_DAY, "window": L, "overlap": cfg["overlap"], "blinding": list(cfg["blinding"]),
          "stacking": cfg["stacking"], "P_threshold": cfg["P_threshold"], "S_threshold": cfg["S_threshold"],
          "windows_per_record": nwin, "l2": "per-step working set (1.2 GB of window predictions) exceeds the 126 MB L2"}
@@ -223,16 +231,18 @@ def run_ours(args):
     thresholds = model._thresholds(argdict)
     thresholds[0] = 0.3 if kind == "eqtransformer" else thresholds[0]
     n = args.samples
-    # two distinct records per rank, alternated between steps (host pinned + device resident copies)
-    recs_host = [torch.from_numpy(synthetic_record(1000 + rank + world * j, n)).pin_memory() for j in range(2)]
+    # R distinct records per rank (station seeds 1000 + rank + world * j, the recipe of SURVEY.md 8(d)), cycled over the
+    # steps: pinned host copies for the end-to-end arm, device-resident copies for `value`
+    R = max(2, args.records)
+    recs_host = [torch.from_numpy(synthetic_record(1000 + rank + world * j, n)).pin_memory() for j in range(R)]
     recs_dev = [r.cuda(non_blocking=True) for r in recs_host]
     torch.cuda.synchronize()
 
     def step_device(i):
-        return model.annotate_array(recs_dev[i & 1], argdict, False, thresholds)
+        return model.annotate_array(recs_dev[i % R], argdict, False, thresholds)
 
     def step_host(i):
-        return model.annotate_array(recs_host[i & 1], argdict, False, thresholds)
+        return model.annotate_array(recs_host[i % R], argdict, False, thresholds)
 
     if args.profile_steps > 0:
         for i in range(args.profile_steps):
@@ -277,15 +287,20 @@ def run_ours(args):
     side = [torch.cuda.Stream() for _ in range(2)]
     side_ws = [torch.empty(ws_bytes, dtype=torch.uint8, device="cuda") for _ in range(2)]
 
+    all_results = []  # (record index, triggers) of every step of the last pipelined run: gathered after the timed region
+
     def run_pipelined(recs, steps):
         pend, res = [], None
+        del all_results[:]
         for i in range(steps):
             k = i & 1
-            pend.append(model.annotate_array_async(recs[k], argdict, False, thresholds, stream=side[k], workspace=side_ws[k]))
+            pend.append(model.annotate_array_async(recs[i % R], argdict, False, thresholds, stream=side[k], workspace=side_ws[k]))
             if len(pend) == 2:
                 res = pend.pop(0).result()
+                all_results.append(res[1])
         while pend:
             res = pend.pop(0).result()
+            all_results.append(res[1])
         return res
 
     def timed_pipelined(recs, steps, warmup, sample_clocks=False):
@@ -315,8 +330,9 @@ def run_ours(args):
             ms = float(t.item())
         return ms, launches, clocks, last
 
-    ms, launches, clocks, last = timed_pipelined(recs_dev, args.steps, args.warmup, sample_clocks=True)
     ms_e2e, _, _, last_e2e = timed_pipelined(recs_host, args.steps, max(2, args.warmup // 2))
+    e2e_results = list(all_results)
+    ms, launches, clocks, last = timed_pipelined(recs_dev, args.steps, args.warmup, sample_clocks=True)
     # the same with one blocking vp_annotate call per record (no overlap between records)
     ms_seq, _, _, _ = timed(step_device, args.steps, max(1, args.warmup // 2))
     ms_e2e_seq, _, _, _ = timed(step_host, args.steps, max(1, args.warmup // 2))
@@ -347,10 +363,34 @@ def run_ours(args):
     value = world * args.steps * days / (ms / 1e3)
     e2e_value = world * args.steps * days / (ms_e2e / 1e3)
 
-    # final gather of picks (the only exchange; outside the timed region)
+    # final gather of picks -- the only exchange of the path: the triggers of EVERY record this rank processed in the
+    # end-to-end run go to rank 0 (host gather; KBs).  Timed on the host next to the device-timed steps.
+    if world > 1:
+        dist.barrier()
     t0 = time.perf_counter()
-    merged = shard.gather_picks([(rank, last[1])], rank, world)
+    merged = shard.gather_picks([(rank + world * i, trig) for i, trig in enumerate(e2e_results)], rank, world)
     gather_ms = 1e3 * (time.perf_counter() - t0)
+    n_gathered = sum(len(t) for _, t in merged) if merged else 0
+
+    # bf16 is reported separately (north_star): probabilities and picks of record 0 against the exact mode
+    bf16_report = None
+    if rank == 0 and args.precision == "bf16":
+        a_ex = model._argdict(dict(CONFIGS[kind], precision="f16x3", chunk_windows=args.chunk))
+        ann_b, trig_b, _ = model.annotate_array(recs_dev[0], argdict, True, thresholds)
+        ann_x, trig_x, _ = model.annotate_array(recs_dev[0], a_ex, True, thresholds)
+        ok = ~np.isnan(ann_x)
+        hit = 0
+        for t in trig_x:
+            cand = trig_b[trig_b["label"] == t["label"]]
+            hit += int(len(cand) > 0 and np.abs(cand["s_peak"] - t["s_peak"]).min() <= 1)
+        bf16_report = {"max_abs_dprob_vs_exact": float(np.abs(ann_b[ok] - ann_x[ok]).max()), "triggers_exact": int(len(trig_x)),
+                       "triggers_bf16": int(len(trig_b)), "pick_match_within_1_sample": hit / max(1, len(trig_x)),
+                       "note": "record 0 of this run; exact = f16x3 mode (<= 1e-4 of the fp32 oracle)"}
+
+    # the drop-in call itself: picker.classify(stream, ...) on ObsPy-like streams of 3 traces per station-day
+    classify_report = None
+    if args.classify_stream > 0 and n == N_DAY:
+        classify_report = classify_stream_timing(model, kind, args, rank, world, barrier, dist if world > 1 else None)
 
     # ---- per-stage device timings (rank 0) for the roofline objects ---------------------------
     stages = {}
@@ -403,8 +443,15 @@ def run_ours(args):
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "stages": stages,
             "kernels": {"per_class": kernels, "ms_per_step_with_events": kernels_step_ms,
                         "note": "CUDA events around every launch of the class on the launching stream, K extra steps"},
-            "picks_per_record": n_trig, "gather_ms": gather_ms,
+            "picks_per_record": n_trig, "gather_ms": gather_ms, "records_per_rank": R,
+            "gather": {"ms": gather_ms, "records": world * len(e2e_results), "triggers": int(n_gathered),
+                       "e2e_value_incl_gather": world * args.steps * days / ((ms_e2e + gather_ms) / 1e3),
+                       "note": "triggers of every record of the end-to-end run gathered on rank 0 (host gather_object)"},
         }
+        if bf16_report:
+            line["bf16"] = bf16_report
+        if classify_report:
+            line["e2e_classify"] = classify_report
         if world == 1 and not args.no_cpu_baseline:
             times, cw, cores, _ = oracle_station_hours_per_s(kind, 1, 1)
             v = (N_HOUR / N_DAY) * len(times) / sum(times)
@@ -416,6 +463,95 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     return line
+
+
+def classify_stream_timing(model, kind, args, rank, world, barrier, dist):
+    """The README call (/root/reference/README.md:54-66) measured as a user makes it: ``picker.classify(stream, **kw)``
+    on a stream of ``args.classify_stream`` station-days (3 traces each, pageable NumPy data as ObsPy holds it).  Host
+    wall clock around the call (it contains host work: stream copy / merge, record assembly into the pinned ring, pick
+    objects), max over ranks."""
+    import torch
+
+    from volpick_b200.stream import Stream, Trace
+    from volpick_b200.synthetic import station_start, synthetic_record
+
+    k = args.classify_stream
+    traces = []
+    for j in range(k):
+        st_no = 1000 + rank + world * j
+        x = synthetic_record(st_no, N_DAY)
+        for i, c in enumerate("ZNE"):
+            traces.append(Trace(x[i].copy(), {"network": "XX", "station": f"S{st_no:04d}", "location": "", "channel": "HH" + c,
+                                              "starttime": station_start(st_no), "sampling_rate": 100.0}))
+    stream = Stream(traces)
+    kw = dict(CONFIGS[kind], precision=args.precision, batch_size=256, parallelism=None)
+    out = {}
+    for copy in (True, False):
+        model.classify(stream, copy=copy, **kw)  # warm-up: pins the staging ring, sizes the workspaces
+        barrier()
+        t0 = time.perf_counter()
+        res = model.classify(stream, copy=copy, **kw)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([dt], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        out["copy_true" if copy else "copy_false"] = {"value": world * k / dt, "ms_per_record": 1e3 * dt / k, "picks": len(res.picks)}
+    out.update({"unit": "station-days/s", "records_per_call": k, "h2d_bytes_per_record": 3 * N_DAY * 4,
+                "note": "host wall clock of picker.classify(stream) per rank, max over ranks; copy=True is the README call "
+                        "(deep copy of the stream first, as SeisBench does)"})
+    return out
+
+
+def run_sweep(args):
+    """BASELINE.json configs[4]: raw forward sweep, B in {256 ... 8192} windows of (B, 3, 6000) EQTransformer and
+    (B, 3, 3001) PhaseNet (standard_normal seed 0, per-channel demean + peak normalisation), windows/s and per-kernel-class
+    milliseconds (CUDA events around every launch inside the library).  One JSON line per (model, precision, B)."""
+    import torch
+
+    import volpick_b200 as vb
+    from volpick_b200 import _lib
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(0)
+    lib = _lib.load()
+    peaks = measured_peaks()
+    names = lib.vp_kernel_class_names().decode().split(",")
+    for kind in ([args.model] if args.sweep_one_model else ["eqtransformer", "phasenet"]):
+        model = (vb.EQTransformer if kind == "eqtransformer" else vb.PhaseNet).from_pretrained("volpick").cuda(0)
+        L = model.in_samples
+        g = torch.Generator(device="cpu").manual_seed(0)
+        for prec in args.sweep_precisions.split(","):
+            for B in (256, 512, 1024, 2048, 4096, 8192):
+                x = torch.randn((B, 3, L), generator=g, dtype=torch.float32)
+                x = x - x.mean(-1, keepdim=True)
+                x = (x / (x.abs().amax(-1, keepdim=True) + 1e-10)).cuda()
+                for _ in range(max(3, args.warmup)):
+                    model.forward(x, precision=prec)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(args.steps):
+                    model.forward(x, precision=prec)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / args.steps
+                lib.vp_kernel_timing(1)
+                for _ in range(args.steps):
+                    model.forward(x, precision=prec)
+                torch.cuda.synchronize()
+                per = {}
+                for k, name in enumerate(names):
+                    tot, cnt = C.c_double(0.0), C.c_int64(0)
+                    _lib.check(lib.vp_kernel_timing_read(k, C.byref(tot), C.byref(cnt)))
+                    if cnt.value:
+                        per[name] = {"ms": tot.value / args.steps, "launches": cnt.value / args.steps}
+                lib.vp_kernel_timing(0)
+                tf = FLOP_PER_WINDOW[kind] * B / (ms / 1e3) / 1e12
+                print(json.dumps({"sweep": "forward", "model": kind, "precision": prec, "windows": B, "ms": ms,
+                                  "windows_per_s": B / (ms / 1e3), "tflops": tf, "frac_of_bf16_sustained": tf / peaks["tf_sustained"],
+                                  "kernels": per, "l2": "activations of B >= 256 windows exceed the 126 MB L2"}), flush=True)
 
 
 def stage_timings(model, lib, rec_dev, argdict, thresholds, kind, reps: int = 3, precision: int = 0, chunk: int = 0):
@@ -515,11 +651,20 @@ def main():
     ap.add_argument("--samples", type=int, default=N_DAY, help="samples per record (default: one station-day)")
     ap.add_argument("--chunk", type=int, default=0, help="windows per forward launch group (0: library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--records", type=int, default=2,
+                    help="distinct synthetic records per rank, cycled over the steps (long mode: >= 16)")
+    ap.add_argument("--classify-stream", type=int, default=0,
+                    help="also time picker.classify(stream) on a stream of this many station-days (the drop-in call)")
+    ap.add_argument("--sweep", action="store_true", help="BASELINE.json configs[4]: raw forward sweep B = 256 ... 8192")
+    ap.add_argument("--sweep-precisions", default="f16x3,bf16")
+    ap.add_argument("--sweep-one-model", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=0,
                     help="profiling aid (ncu): run this many device-resident steps and exit without timing")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.sweep:
+        run_sweep(args)
     else:
         run_ours(args)
 

@@ -49,7 +49,14 @@ enum { VP_STACK_AVG = 0, VP_STACK_MAX = 1 };
  * K step into fp32 TMEM accumulators (fp32-equivalent).  bf16: tcgen05, one bf16 pass. */
 enum { VP_PREC_FP32 = 0, VP_PREC_F16X3 = 1, VP_PREC_BF16 = 2 };
 enum { VP_DTYPE_F32 = 0, VP_DTYPE_I32 = 1 };
+/* Amplitude scope of the "peak" window normalisation (SeisBench annotate_batch_pre).  PER_CHANNEL: every component by
+ * its own peak -- EQTransformer(norm_amp_per_comp=True), PhaseNet, and this library's reading of norm="peak" (it is the
+ * normalisation the volpick weights were trained with, /root/reference/volpick/model/models.py:449-451,853-855).
+ * PER_WINDOW: one peak over the three components of a window (the alternative reading). */
 enum { VP_PEAK_PER_CHANNEL = 0, VP_PEAK_PER_WINDOW = 1 };
+/* Window pre-processing flags: 6-sample cosine taper (EQTransformer), linear detrend after the demean
+ * (SeisBench norm_detrend=True: scipy.signal.detrend per component). */
+enum { VP_PRE_TAPER = 1, VP_PRE_DETREND = 2 };
 
 typedef struct vp_model vp_model;
 
@@ -71,6 +78,7 @@ typedef struct vp_annotate_params {
     int32_t peak_scope;    /* VP_PEAK_PER_CHANNEL (default) | VP_PEAK_PER_WINDOW        */
     int32_t chunk_windows; /* windows per forward launch group; <= 0: library default   */
     float threshold[3];    /* per label; <= 0 or NaN: no picks for that label           */
+    int32_t norm_detrend;  /* != 0: linear detrend of every window component (VP_PRE_DETREND) */
 } vp_annotate_params;
 
 /* ---- misc ---------------------------------------------------------------------------- */
@@ -115,9 +123,9 @@ VP_API int vp_sosfilt(const void *x, int dtype, int64_t n_samples, int64_t ch_st
                int n_sections, int zerophase, float *y, void *workspace, int64_t workspace_bytes, void *stream);
 /* _cut_fragments_array + annotate_batch_pre: gather windows, demean, peak-normalise (+1e-10),
  * EQTransformer 6-sample cosine taper.  trace: (3, n) with channel stride ch_stride elements,
- * f32 or i32 counts.  out: (n_windows, 3, L) f32. */
+ * f32 or i32 counts.  pre_flags: VP_PRE_TAPER | VP_PRE_DETREND.  out: (n_windows, 3, L) f32. */
 VP_API int vp_slice_normalize(const void *trace, int dtype, int64_t n_samples, int64_t ch_stride, const int64_t *starts,
-                       int64_t n_windows, int64_t in_samples, int peak_scope, int taper, float *out, void *stream);
+                       int64_t n_windows, int64_t in_samples, int peak_scope, int pre_flags, float *out, void *stream);
 
 /* EQTransformer.forward / PhaseNet.forward on pre-normalised windows.
  * x: (n_windows, 3, L) -> y: (n_windows, 3, L) probabilities (sigmoid heads / channel softmax). */
@@ -135,7 +143,7 @@ VP_API int vp_forward_range(vp_model *m, const float *x, int64_t n_windows, floa
  * never reach HBM.  Same results as the two-call sequence
  * within the mode's tolerance (the first conv runs in fp32 instead of f16x3 / bf16). */
 VP_API int vp_slice_forward(vp_model *m, const void *trace, int dtype, int64_t n_samples, int64_t ch_stride,
-                            const int64_t *starts, int64_t n_windows, int peak_scope, int taper, float *y, void *workspace,
+                            const int64_t *starts, int64_t n_windows, int peak_scope, int pre_flags, float *y, void *workspace,
                             int64_t workspace_bytes, int precision, int64_t keep_lo, int64_t keep_hi, void *stream);
 /* Debug/parity: run the forward and copy the named intermediate activation (device->device) into
  * tap_out (capacity in floats); *tap_floats receives its size.  Names: see vp_forward_tap_names(). */

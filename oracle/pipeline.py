@@ -46,15 +46,21 @@ def eqt_taper() -> np.ndarray:
     return (0.5 * (1 + np.cos(np.linspace(np.pi, 2 * np.pi, EQT_TAPER_LEN)))).astype(np.float32)
 
 
-def prenorm(batch: np.ndarray, kind: str, norm: str = "peak", peak_scope: str = "channel") -> np.ndarray:
-    """``annotate_batch_pre`` in fp32: demean, amplitude normalise, (EQT) 6-sample cosine taper.
+def prenorm(batch: np.ndarray, kind: str, norm: str = "peak", peak_scope: str = "channel", detrend: bool = False) -> np.ndarray:
+    """``annotate_batch_pre`` in fp32: demean, [linear detrend], amplitude normalise, (EQT) 6-sample cosine taper.
 
     ``peak_scope``: "channel" (per window and channel, Appendix C.2 -- and the training-side pin
-    models.py:449-451,853-855) or "window" (one peak/std over all channels of a window; the
-    uncertain SeisBench variant listed in Appendix D #6).
+    models.py:449-451,853-855; SeisBench ``norm_amp_per_comp=True``) or "window" (one peak/std over all
+    channels of a window; the uncertain SeisBench variant listed in Appendix D #6).
+    ``detrend``: SeisBench ``norm_detrend=True`` -- ``scipy.signal.detrend`` (least-squares line, float64)
+    of every component after the demean.
     """
     x = batch.astype(np.float32, copy=True)
     x = x - x.mean(axis=-1, keepdims=True, dtype=np.float32)
+    if detrend:
+        from scipy.signal import detrend as _detrend
+
+        x = _detrend(x.astype(np.float64), axis=-1, type="linear").astype(np.float32)
     axes = (-1,) if peak_scope == "channel" else (-1, -2)
     if norm == "peak":
         amp = np.abs(x).max(axis=axes, keepdims=True)
@@ -245,6 +251,7 @@ def annotate_array(
     batch_size: int = 256,
     peak_scope: str = "channel",
     return_windows: bool = False,
+    detrend: bool = False,
 ):
     """(3, N) gap-free segment -> (pred_len, 3) stacked annotation (NaN where blinded / uncovered)."""
     L = IN_SAMPLES[kind]
@@ -253,7 +260,7 @@ def annotate_array(
     starts = window_starts(trace.shape[1], L, overlap)
     if len(starts) == 0:
         return (np.empty((0, 3), np.float32), starts, None) if return_windows else np.empty((0, 3), np.float32)
-    win = prenorm(cut_windows(trace, starts, L), kind, "peak", peak_scope)
+    win = prenorm(cut_windows(trace, starts, L), kind, "peak", peak_scope, detrend)
     y = forward_batches(kind, sd, win, batch_size)
     yb = blind(y, blinding)
     out = reassemble(yb, starts, L, overlap, stacking)

@@ -725,9 +725,10 @@ def test_edge_records(eqt, pn):
                                                       starttime=tr.stats.starttime + 150.0, sampling_rate=100.0)))
     a = pn.annotate(parts)
     assert len(a) == 6 and sorted({t.stats.npts for t in a}) == [12_000, 15_000]
-    # pick buffer overflow is an error, never a truncation
-    with pytest.raises(_lib.VolpickError, match="exceed the pick capacity"):
-        pn.annotate_array(synthetic_record(4, 30_000), None, False, [1e-6, 1e-6, 0.0], pick_capacity=1)
+    # pick buffer overflow is never a truncation: the C ABI reports it (tests/test_gpu_round2.py::test_pick_capacity_retry)
+    # and the Python API re-runs the record with the reported count
+    _, trig, _ = pn.annotate_array(synthetic_record(4, 30_000), None, False, [1e-6, 1e-6, 0.0], pick_capacity=1)
+    assert len(trig) > 1
 
 
 def test_station_day_properties(eqt):

@@ -187,3 +187,58 @@ def test_filter_design_matches_oracle():
     x[0, 200] = 1.0
     y = pipeline.sosfilt_record(x, pipeline.design_sos("lowpass", 100.0, corners=2, freq=5.0), True)
     np.testing.assert_allclose(y[0, :200], y[0, :200:-1], atol=1e-6)
+
+
+def test_seisbench_norm_kwargs_and_int32_ingest(tmp_path):
+    """SeisBench's constructor kwargs of the window pre-processing are accepted from ``model_args``; int32 counts stay
+    int32 on the wire; the version sort of from_pretrained is type-stable."""
+    e = vb.EQTransformer(norm_amp_per_comp=True, norm_detrend=True, peak_scope="window")
+    p = e._params(e._argdict({}), [0.0, 0.0, 0.0])
+    assert p.peak_scope == 0 and p.norm_detrend == 1  # norm_amp_per_comp forces the per-component peak
+    d = vb.PhaseNet()
+    p = d._params(d._argdict({}), [0.0, 0.0, 0.0])
+    assert (d.norm_amp_per_comp, d.norm_detrend, p.peak_scope, p.norm_detrend) == (False, False, 0, 0)
+    w = vb.PhaseNet(peak_scope="window")
+    assert w._params(w._argdict({}), [0.0, 0.0, 0.0]).peak_scope == 1
+    with pytest.raises(ValueError, match="peak_scope"):
+        vb.PhaseNet(peak_scope="trace")
+    x = np.round(synthetic_record(2, 5000)).astype(np.int32)
+    t0 = UTCDateTime("2021-01-01")
+    hdr = dict(network="XX", station="I", location="", sampling_rate=100.0)
+    st = Stream([Trace(x[i], dict(hdr, channel="HH" + c, starttime=t0)) for i, c in enumerate("ZN")])
+    (_, arr), = d.stream_to_arrays(list(st), d._argdict({}))
+    assert arr.dtype == np.int32 and np.array_equal(arr[:2], x[:2]) and not arr[2].any()
+    st[1].data = st[1].data.astype(np.float64)
+    (_, arr), = d.stream_to_arrays(list(st), d._argdict({}))
+    assert arr.dtype == np.float32
+    # records assembled in a caller-provided buffer (the pinned ring of _run)
+    bufs = []
+
+    def alloc(shape, dtype):
+        bufs.append(np.full(shape, 7, dtype=dtype))
+        return bufs[-1]
+
+    (_, arr), = list(d._iter_stream_arrays(list(st), d._argdict({}), alloc))
+    assert arr is bufs[0] and not arr[2].any() and np.array_equal(arr[0], x[0])
+    # a 125 Hz trace cannot be resampled without ObsPy: loud, not silent
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        d.resample_trace(Trace(x[0], dict(hdr, channel="HHZ", starttime=t0, sampling_rate=125.0)))
+    # version sort: "1", "2", "10", "2b" must not raise and "10" wins over "2"
+    import json as _json, os as _os
+
+    root = tmp_path / "phasenet"
+    root.mkdir()
+    for v in ("1", "2", "10", "2b"):
+        (root / f"x.json.v{v}").write_text(_json.dumps({"model_args": {}}))
+        (root / f"x.vpw.v{v}").write_bytes(b"")
+    old = _os.environ.get("VOLPICK_B200_CACHE")
+    _os.environ["VOLPICK_B200_CACHE"] = str(tmp_path)
+    try:
+        js, _ = weights_io.find_weights("phasenet", "x")
+        assert js.endswith(".v2b") or js.endswith(".v10")
+        assert weights_io.find_weights("phasenet", "x", "10")[0].endswith(".v10")
+    finally:
+        if old is None:
+            del _os.environ["VOLPICK_B200_CACHE"]
+        else:
+            _os.environ["VOLPICK_B200_CACHE"] = old

@@ -23,6 +23,7 @@ import numpy as _np  # noqa: E402
 
 TRIGGER_DTYPE = _np.dtype([("s0", "<i8"), ("s1", "<i8"), ("s_peak", "<i8"), ("value", "<f4"), ("label", "<i4")])
 PEAK_SCOPE = {"channel": 0, "window": 1}
+PRE_TAPER, PRE_DETREND = 1, 2
 
 
 class Trigger(C.Structure):
@@ -42,6 +43,7 @@ class AnnotateParams(C.Structure):
         ("peak_scope", C.c_int32),
         ("chunk_windows", C.c_int32),
         ("threshold", C.c_float * 3),
+        ("norm_detrend", C.c_int32),
     ]
 
 

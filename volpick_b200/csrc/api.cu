@@ -95,11 +95,14 @@ void pinned_block_put(int64_t *b) {
     if (b) g_pinned_blocks.push_back(b);
 }
 
-CopyPipe *copy_pipe() {
-    static thread_local CopyPipe pipes[16];
+// One pipe per record in flight: consecutive vp_annotate_begin calls of a host thread rotate through N_PIPES pipes per
+// device, so the copy stream and the extra forward lanes of record i + 1 are not queued behind those of record i.
+constexpr int N_PIPES = 4;
+CopyPipe *copy_pipe(unsigned rotation) {
+    static thread_local CopyPipe pipes[16][N_PIPES];
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
-    CopyPipe &cp = pipes[dev];
+    CopyPipe &cp = pipes[dev][rotation % N_PIPES];
     if (cp.device != dev) {
         if (cudaStreamCreateWithFlags(&cp.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
         if (cudaEventCreateWithFlags(&cp.ev_ready, cudaEventDisableTiming) != cudaSuccess) return nullptr;
@@ -231,10 +234,12 @@ extern "C" int vp_annotate_begin(vp_model *m, const void *trace, int trace_on_ho
     // Host record: (3, n) with channel stride ch_stride -> packed (3, n) on the device.  The copy is issued piecewise
     // on a second stream, one piece per forward chunk (the samples that chunk's windows read), so that the H2D
     // transfer of the record (104 MB for a station-day, ~2 ms over PCIe) overlaps the network instead of preceding it.
+    static thread_local unsigned g_rotation = 0;
+    const unsigned rotation = g_rotation++;
     CopyPipe *pipe = nullptr;
     int64_t copied = 0;  // samples [0, copied) of every channel are on their way
     if (trace_on_host) {
-        pipe = copy_pipe();
+        pipe = copy_pipe(rotation);
         VP_REQUIRE(pipe != nullptr, VP_ERR_CUDA, "vp_annotate: cannot create the copy stream");
         VP_CUDA_CHECK(cudaEventRecord(pipe->ev_ready, s));  // workspace reuse: earlier work of `s` reads the old record
         VP_CUDA_CHECK(cudaStreamWaitEvent(pipe->stream, pipe->ev_ready, 0));
@@ -268,13 +273,13 @@ extern "C" int vp_annotate_begin(vp_model *m, const void *trace, int trace_on_ho
         VP_LAUNCH_CHECK();
     }
     float *d_y = (float *)(ws + lo.off_y);
-    CopyPipe *lanes = lo.n_lanes > 1 ? copy_pipe() : nullptr;
+    CopyPipe *lanes = lo.n_lanes > 1 ? copy_pipe(rotation) : nullptr;
     VP_REQUIRE(lo.n_lanes == 1 || lanes != nullptr, VP_ERR_CUDA, "vp_annotate: cannot create the extra forward lanes");
     if (lanes) {  // fork: the extra lanes start after the window starts are uploaded (and after earlier users of the workspace)
         VP_CUDA_CHECK(cudaEventRecord(lanes->ev_fork, s));
         for (int i = 1; i < lo.n_lanes; ++i) VP_CUDA_CHECK(cudaStreamWaitEvent(lanes->lane[i - 1], lanes->ev_fork, 0));
     }
-    const int taper = (kind == VP_KIND_EQTRANSFORMER) ? 1 : 0;
+    const int taper = ((kind == VP_KIND_EQTRANSFORMER) ? VP_PRE_TAPER : 0) | (p->norm_detrend ? VP_PRE_DETREND : 0);
     static const bool fused_off = getenv("VP_FUSED_SLICE") && atoi(getenv("VP_FUSED_SLICE")) == 0;  // debugging aid
     const bool fused_slice = !fused_off && (p->precision == VP_PREC_F16X3 || p->precision == VP_PREC_BF16);
     int64_t chunk_no = 0;

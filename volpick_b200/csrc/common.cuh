@@ -62,6 +62,13 @@ struct KTimer {  // scoped: events on the launching stream around everything lau
 
 static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
+// Opt-in of `bytes` of dynamic shared memory for `kernel` on the CURRENT device.  cudaFuncSetAttribute is per function and
+// per device: the record of what has been granted is keyed by (kernel, device) and guarded by a mutex, so handles on
+// several devices in one process and several host threads on one handle are fine.  Returns VP_OK / VP_ERR_CUDA.
+int ensure_dyn_smem(const void *kernel, size_t bytes);
+// Multiprocessors of the current device (cached per device; 148 on a B200).
+int device_sm_count();
+
 // ---- plan structures shared between model.cu and the kernel translation units -------------
 
 struct ConvP {

@@ -146,13 +146,7 @@ static int launch_conv(const ConvP &p, int B, int G, cudaStream_t s) {
     constexpr int XS_FLOATS = (CCH * XT + 3) & ~3;
     constexpr size_t SMEM = (size_t)(XS_FLOATS + CCH * K * COUTP) * sizeof(float);
     auto kern = conv1d_f32_kernel<CIN, COUTP, K, STRIDE, UPS, POOL, ACT, PRE, RES, TCO, TT, CCH>;
-    if (SMEM > 48 * 1024) {
-        static bool attr_set = false;  // per instantiation
-        if (!attr_set) {
-            VP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-            attr_set = true;
-        }
-    }
+    if (int rc = ensure_dyn_smem((const void *)kern, SMEM)) return rc;
     dim3 grid((p.Lconv + TILE - 1) / TILE, B, G);
     KTimer kt(KC_CONV_F32, s);
     kern<<<grid, 32 * NW, SMEM, s>>>(p);

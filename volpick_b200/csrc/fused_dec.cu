@@ -555,11 +555,7 @@ void decb_free(DecBPlan &plan) {
 template <int SPLIT, int OPT>
 static int decb_launch_t(const FzDecB &p, dim3 grid, cudaStream_t s) {
     auto kern = decb_kernel<SPLIT, OPT>;
-    static int attr = 0;
-    if (p.smem_bytes > attr) {
-        VP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes));
-        attr = p.smem_bytes;
-    }
+    if (int rc = ensure_dyn_smem((const void *)kern, (size_t)p.smem_bytes)) return rc;
     KTimer kt(KC_DECB, s);
     kern<<<grid, FZ_THREADS, p.smem_bytes, s>>>(p);
     VP_LAUNCH_CHECK();
@@ -589,7 +585,7 @@ int decb_launch(const DecBPlan &plan, const uint16_t *x, long long x_split, long
     }
     const int n_items = B * p.tiles_per_seq;
     if (n_items == 0) return VP_OK;
-    dim3 grid((unsigned)std::min(49, (n_items + FZ_NPIPE - 1) / FZ_NPIPE), 3);
+    dim3 grid((unsigned)std::min(std::max(device_sm_count() / 3, 1), (n_items + FZ_NPIPE - 1) / FZ_NPIPE), 3);
     if (plan.split == 2 && plan.opt == 6) return decb_launch_t<2, 6>(p, grid, s);
     if (plan.split == 2 && plan.opt == 10) return decb_launch_t<2, 10>(p, grid, s);
     if (plan.split == 1 && plan.opt == 6) return decb_launch_t<1, 6>(p, grid, s);

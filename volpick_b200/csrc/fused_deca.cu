@@ -320,11 +320,7 @@ void deca_free(DecAPlan &plan) {
 template <int SPLIT>
 static int deca_launch_t(const FzDecA &p, dim3 grid, cudaStream_t s) {
     auto kern = deca_kernel<SPLIT>;
-    static int attr = 0;
-    if (p.smem_bytes > attr) {
-        VP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes));
-        attr = p.smem_bytes;
-    }
+    if (int rc = ensure_dyn_smem((const void *)kern, (size_t)p.smem_bytes)) return rc;
     KTimer kt(KC_DECA, s);
     kern<<<grid, DA_THREADS, p.smem_bytes, s>>>(p);
     VP_LAUNCH_CHECK();
@@ -345,7 +341,7 @@ int deca_launch(const DecAPlan &plan, const uint16_t *x, long long x_split, long
     p.B = B;
     p.blob = plan.d_blob;
     p.fixw = plan.d_fixw;
-    dim3 grid((unsigned)std::min(49, B), 3);
+    dim3 grid((unsigned)std::min(std::max(device_sm_count() / 3, 1), B), 3);  // one CTA per SM over the 3 decoders
     return plan.split == 2 ? deca_launch_t<2>(p, grid, s) : deca_launch_t<1>(p, grid, s);
 }
 

@@ -263,21 +263,13 @@ int resstack_launch(const ResStackP &p, int split, cudaStream_t s) {
     const size_t a_bytes = ((size_t)split * 8 * RS_PITCH * 16 + 127) & ~(size_t)127;
     const size_t smem = 2 * w_bytes + RS_NST * a_bytes;
     const int n_tiles = (p.NS + 1) / 2;
-    const unsigned grid = (unsigned)std::min(148, n_tiles);
+    const unsigned grid = (unsigned)std::min(device_sm_count(), n_tiles);
     KTimer kt(KC_TCCONV, s);
     if (split == 2) {
-        static bool attr = false;
-        if (!attr) {
-            VP_CUDA_CHECK(cudaFuncSetAttribute(resstack_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr = true;
-        }
+        if (int rc = ensure_dyn_smem((const void *)resstack_kernel<2>, smem)) return rc;
         resstack_kernel<2><<<grid, RS_THREADS, smem, s>>>(p);
     } else {
-        static bool attr = false;
-        if (!attr) {
-            VP_CUDA_CHECK(cudaFuncSetAttribute(resstack_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr = true;
-        }
+        if (int rc = ensure_dyn_smem((const void *)resstack_kernel<1>, smem)) return rc;
         resstack_kernel<1><<<grid, RS_THREADS, smem, s>>>(p);
     }
     VP_LAUNCH_CHECK();

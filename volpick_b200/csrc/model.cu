@@ -11,6 +11,10 @@
 #include <string>
 #include <vector>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "common.cuh"
 #include "fused.cuh"
 #include "tcconv.cuh"
@@ -30,6 +34,37 @@ void set_error(const char *fmt, ...) {
     g_error = buf;
 }
 void count_launch(int n) { g_launches += n; }
+
+namespace {
+std::mutex g_attr_mutex;
+std::map<std::pair<const void *, int>, size_t> g_attr_granted;
+int g_sm_count[64];  // 0: not queried yet
+}  // namespace
+
+int ensure_dyn_smem(const void *kernel, size_t bytes) {
+    if (bytes <= 48 * 1024) return VP_OK;
+    int dev = 0;
+    VP_CUDA_CHECK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_attr_mutex);
+    size_t &granted = g_attr_granted[std::make_pair(kernel, dev)];
+    if (bytes > granted) {
+        VP_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        granted = bytes;
+    }
+    return VP_OK;
+}
+
+int device_sm_count() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    std::lock_guard<std::mutex> lock(g_attr_mutex);
+    if (g_sm_count[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        g_sm_count[dev] = n;
+    }
+    return g_sm_count[dev];
+}
 
 thread_local bool g_ktimer_on = false;
 namespace {
@@ -711,6 +746,11 @@ struct Arena {
         used = off + n_floats * (int64_t)sizeof(float);
         return base ? reinterpret_cast<float *>(base + off) : nullptr;
     }
+    int check() const {
+        if (used <= cap) return VP_OK;
+        set_error("forward workspace too small: need %lld bytes, have %lld", (long long)used, (long long)cap);
+        return VP_ERR_WORKSPACE;
+    }
 };
 
 struct Tap {
@@ -838,6 +878,7 @@ static int run_eqt(Runner &r, const float *x, float *y, Arena &ar) {
     float *din = ar.take(3 * B * 16 * T);  // [group][B][16][T]: decoder inputs
     float *plo = ar.take(2 * B * 16 * T);  // pick LSTM outputs [group][B][16][T]
     if (r.dry) return VP_OK;
+    if (int rc = ar.check()) return rc;  // every buffer is laid out: refuse an undersized workspace BEFORE any launch
     if (tc && !ts.ready) {
         set_error("tensor-core weight set is not available");
         return VP_ERR_UNSUPPORTED;
@@ -1311,6 +1352,7 @@ static int run_pn_tc(Runner &r, const float *x, float *y, Arena &ar) {
     }
     float *tapbuf = ar.take(B * 8 * (int64_t)L0);  // debug taps: any layer as fp32 (B, C, T), C * T <= 8 * L0
     if (r.dry) return VP_OK;
+    if (int rc = ar.check()) return rc;  // every buffer is laid out: refuse an undersized workspace BEFORE any launch
     if (!ts.ready) {
         set_error("tensor-core weight set is not available");
         return VP_ERR_UNSUPPORTED;
@@ -1507,6 +1549,7 @@ static int run_pn(Runner &r, const float *x, float *y, Arena &ar) {
     float *us[4];
     for (int i = 0; i < 4; ++i) us[i] = ar.take(B * kPnC[3 - i] * len[3 - i]);
     if (r.dry) return VP_OK;
+    if (int rc = ar.check()) return rc;  // every buffer is laid out: refuse an undersized workspace BEFORE any launch
 
     r.conv(m->inc, 1, 1, 1, ACT_RELU, nullptr, nullptr, 0, x, 3 * (int64_t)L0, 0, L0, L0, 3, L0, L0, b_inc,
            8 * (int64_t)L0, 0, 1, 0, 0);
@@ -1661,6 +1704,13 @@ extern "C" int vp_model_create(int kind, const float *weights, int64_t n_floats,
     int ndev = 0;
     VP_CUDA_CHECK(cudaGetDeviceCount(&ndev));
     VP_REQUIRE(device >= 0 && device < ndev, VP_ERR_CUDA, "vp_model_create: CUDA device %d not available (%d devices)", device, ndev);
+    struct DeviceGuard {  // the caller's current device is restored on every path out of this function
+        int prev = -1;
+        ~DeviceGuard() {
+            if (prev >= 0) cudaSetDevice(prev);
+        }
+    } guard;
+    VP_CUDA_CHECK(cudaGetDevice(&guard.prev));
     VP_CUDA_CHECK(cudaSetDevice(device));
     vp_model *m = new vp_model();
     m->kind = kind;

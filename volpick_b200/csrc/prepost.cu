@@ -22,6 +22,8 @@ namespace vp {
 struct Taper {
     float t[6];
 };
+// 1 / sum_i (i - (L - 1) / 2)^2 = 12 / (L (L^2 - 1)): the denominator of the least-squares slope (norm_detrend)
+static inline float detrend_inv_tt(int L) { return L > 1 ? (float)(12.0 / ((double)L * ((double)L * (double)L - 1.0))) : 0.f; }
 
 template <typename T>
 __device__ __forceinline__ float ld_as_float(const T *p) {
@@ -82,7 +84,7 @@ __device__ __forceinline__ void block_reduce_max3(float3 &v, float *red) {
 template <typename Tin, int PT, int NT>
 __global__ void __launch_bounds__(NT) slice_normalize_kernel(const Tin *__restrict__ trace, int64_t ch_stride,
                                                              const int64_t *__restrict__ starts, int L,
-                                                             int peak_scope, int taper, Taper tap,
+                                                             int peak_scope, int flags, float inv_tt, Taper tap,
                                                              float *__restrict__ out) {
     __shared__ float red[96];
     const int64_t w = blockIdx.x;
@@ -104,14 +106,41 @@ __global__ void __launch_bounds__(NT) slice_normalize_kernel(const Tin *__restri
     block_reduce_sum3(sum, red);
     const float invL = 1.0f / (float)L;
     const float3 mean = make_float3(sum.x * invL, sum.y * invL, sum.z * invL);
+#pragma unroll
+    for (int j = 0; j < PT; ++j) {
+        v[0][j] -= mean.x;
+        v[1][j] -= mean.y;
+        v[2][j] -= mean.z;
+    }
+    if (flags & VP_PRE_DETREND) {  // norm_detrend: least-squares line of the demeaned window (scipy.signal.detrend)
+        const float c0 = 0.5f * (float)(L - 1);
+        double sx = 0.0, sy = 0.0, sz = 0.0;
+#pragma unroll
+        for (int j = 0; j < PT; ++j) {
+            const int idx = tid + j * NT;
+            if (idx < L) {
+                const double t = (double)((float)idx - c0);
+                sx += t * (double)v[0][j];
+                sy += t * (double)v[1][j];
+                sz += t * (double)v[2][j];
+            }
+        }
+        float3 st = make_float3((float)sx, (float)sy, (float)sz);
+        block_reduce_sum3(st, red);
+        const float3 beta = make_float3(st.x * inv_tt, st.y * inv_tt, st.z * inv_tt);
+#pragma unroll
+        for (int j = 0; j < PT; ++j) {
+            const float t = (float)(tid + j * NT) - c0;
+            v[0][j] -= beta.x * t;
+            v[1][j] -= beta.y * t;
+            v[2][j] -= beta.z * t;
+        }
+    }
     float3 pk = make_float3(0.f, 0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < PT; ++j) {
         const int idx = tid + j * NT;
         if (idx < L) {
-            v[0][j] -= mean.x;
-            v[1][j] -= mean.y;
-            v[2][j] -= mean.z;
             pk.x = fmaxf(pk.x, fabsf(v[0][j]));
             pk.y = fmaxf(pk.y, fabsf(v[1][j]));
             pk.z = fmaxf(pk.z, fabsf(v[2][j]));
@@ -129,7 +158,7 @@ __global__ void __launch_bounds__(NT) slice_normalize_kernel(const Tin *__restri
         const int idx = tid + j * NT;
         if (idx < L) {
             float tp = 1.f;
-            if (taper) {
+            if (flags & VP_PRE_TAPER) {
                 if (idx < 6) tp = tap.t[idx];
                 if (idx >= L - 6) tp = tap.t[L - 1 - idx];
             }
@@ -159,7 +188,7 @@ constexpr int E0_NT = 512, E0_PT = 12, E0_HALO = 5;
 template <typename Tin, int SPLIT, bool POOL>
 __global__ void __launch_bounds__(E0_NT, 2) slice_enc0_kernel(const Tin *__restrict__ trace, int64_t ch_stride,
                                                               const int64_t *__restrict__ starts, int L, int peak_scope,
-                                                              int taper, Taper tap, const __grid_constant__ Enc0W wt,
+                                                              int flags, float inv_tt, Taper tap, const __grid_constant__ Enc0W wt,
                                                               uint16_t *__restrict__ out, int64_t out_split, int out_pitch) {
     extern __shared__ __align__(16) float e0_smem[];
     __shared__ float red[96];
@@ -188,12 +217,36 @@ __global__ void __launch_bounds__(E0_NT, 2) slice_enc0_kernel(const Tin *__restr
     block_reduce_sum3(sum, red);
     const float invL = 1.0f / (float)L;
     const float3 mean = make_float3(sum.x * invL, sum.y * invL, sum.z * invL);
+    float3 beta = make_float3(0.f, 0.f, 0.f);
+    const float c0 = 0.5f * (float)(L - 1);
+    if (flags & VP_PRE_DETREND) {  // same arithmetic as slice_normalize_kernel
+        double sx = 0.0, sy = 0.0, sz = 0.0;
+#pragma unroll
+        for (int j = 0; j < E0_PT; ++j) {
+            const int idx = tid + j * E0_NT;
+            if (idx < L) {
+                const double t = (double)((float)idx - c0);
+                sx += t * (double)(xs[idx + E0_HALO] - mean.x);
+                sy += t * (double)(xs[XP + idx + E0_HALO] - mean.y);
+                sz += t * (double)(xs[2 * XP + idx + E0_HALO] - mean.z);
+            }
+        }
+        float3 st = make_float3((float)sx, (float)sy, (float)sz);
+        block_reduce_sum3(st, red);
+        beta = make_float3(st.x * inv_tt, st.y * inv_tt, st.z * inv_tt);
+    }
     float3 pk = make_float3(0.f, 0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < E0_PT; ++j) {
         const int idx = tid + j * E0_NT;
         if (idx < L) {  // each thread re-reads exactly what it wrote
-            const float v0 = xs[idx + E0_HALO] - mean.x, v1 = xs[XP + idx + E0_HALO] - mean.y, v2 = xs[2 * XP + idx + E0_HALO] - mean.z;
+            float v0 = xs[idx + E0_HALO] - mean.x, v1 = xs[XP + idx + E0_HALO] - mean.y, v2 = xs[2 * XP + idx + E0_HALO] - mean.z;
+            if (flags & VP_PRE_DETREND) {
+                const float t = (float)idx - c0;
+                v0 -= beta.x * t;
+                v1 -= beta.y * t;
+                v2 -= beta.z * t;
+            }
             xs[idx + E0_HALO] = v0;
             xs[XP + idx + E0_HALO] = v1;
             xs[2 * XP + idx + E0_HALO] = v2;
@@ -213,7 +266,7 @@ __global__ void __launch_bounds__(E0_NT, 2) slice_enc0_kernel(const Tin *__restr
         const int idx = tid + j * E0_NT;
         if (idx < L) {
             float tp = 1.f;
-            if (taper) {
+            if (flags & VP_PRE_TAPER) {
                 if (idx < 6) tp = tap.t[idx];
                 if (idx >= L - 6) tp = tap.t[L - 1 - idx];
             }
@@ -306,6 +359,7 @@ int launch_slice_enc0(const void *trace, int dtype, int64_t ch_stride, const int
         const double a = M_PI + (M_PI * i) / 5.0;
         tap.t[i] = (float)(0.5 * (1.0 + std::cos(a)));
     }
+    const float inv_tt = detrend_inv_tt(L);
     Enc0W wt;
     std::memset(&wt, 0, sizeof(wt));
     std::memcpy(wt.w, w_host, sizeof(float) * 8 * 3 * k);
@@ -314,12 +368,8 @@ int launch_slice_enc0(const void *trace, int dtype, int64_t ch_stride, const int
 #define VP_E0_LAUNCH(T, S)                                                                                                  \
     do {                                                                                                                    \
         auto kern = k == 11 ? slice_enc0_kernel<T, S, true> : slice_enc0_kernel<T, S, false>;                               \
-        static bool attr[2] = {false, false};                                                                               \
-        if (!attr[k == 11]) {                                                                                               \
-            VP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (E0_PT * E0_NT + 12) * 4)); \
-            attr[k == 11] = true;                                                                                           \
-        }                                                                                                                   \
-        kern<<<(unsigned)nw, E0_NT, smem, s>>>((const T *)trace, ch_stride, starts, L, scope, taper, tap, wt, out, out_split, \
+        if (int rc = ensure_dyn_smem((const void *)kern, (size_t)3 * (E0_PT * E0_NT + 12) * 4)) return rc;                  \
+        kern<<<(unsigned)nw, E0_NT, smem, s>>>((const T *)trace, ch_stride, starts, L, scope, taper, inv_tt, tap, wt, out, out_split, \
                                                out_pitch > 0 ? out_pitch : L);                                              \
     } while (0)
     KTimer kt(KC_SLICE_ENC0, s);
@@ -340,13 +390,14 @@ static int launch_slice(const Tin *trace, int64_t ch_stride, const int64_t *star
         const double a = M_PI + (M_PI * i) / 5.0;
         tap.t[i] = (float)(0.5 * (1.0 + std::cos(a)));
     }
+    const float inv_tt = detrend_inv_tt(L);
     KTimer kt(KC_SLICE, s);
     if (L <= 6 * 512) {
-        slice_normalize_kernel<Tin, 6, 512><<<(unsigned)nw, 512, 0, s>>>(trace, ch_stride, starts, L, scope, taper, tap, out);
+        slice_normalize_kernel<Tin, 6, 512><<<(unsigned)nw, 512, 0, s>>>(trace, ch_stride, starts, L, scope, taper, inv_tt, tap, out);
     } else if (L <= 12 * 512) {
-        slice_normalize_kernel<Tin, 12, 512><<<(unsigned)nw, 512, 0, s>>>(trace, ch_stride, starts, L, scope, taper, tap, out);
+        slice_normalize_kernel<Tin, 12, 512><<<(unsigned)nw, 512, 0, s>>>(trace, ch_stride, starts, L, scope, taper, inv_tt, tap, out);
     } else if (L <= 24 * 1024) {
-        slice_normalize_kernel<Tin, 24, 1024><<<(unsigned)nw, 1024, 0, s>>>(trace, ch_stride, starts, L, scope, taper, tap, out);
+        slice_normalize_kernel<Tin, 24, 1024><<<(unsigned)nw, 1024, 0, s>>>(trace, ch_stride, starts, L, scope, taper, inv_tt, tap, out);
     } else {
         set_error("window length %d not supported by the slicer (max %d)", L, 24 * 1024);
         return VP_ERR_UNSUPPORTED;
@@ -938,7 +989,7 @@ extern "C" int vp_nan_bounds(const float *annotation, int n_labels, int64_t pred
     nan_bounds_init_kernel<<<1, 32, 0, s>>>(bounds, n_labels, pred_len);
     VP_LAUNCH_CHECK();
     if (pred_len > 0) {
-        dim3 grid((unsigned)std::min<int64_t>((pred_len + 255) / 256, 148 * 8), n_labels);
+        dim3 grid((unsigned)std::min<int64_t>((pred_len + 255) / 256, (int64_t)device_sm_count() * 8), n_labels);
         nan_bounds_kernel<<<grid, 256, 0, s>>>(annotation, n_labels, pred_len, bounds);
         VP_LAUNCH_CHECK();
     }

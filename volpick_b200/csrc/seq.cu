@@ -330,11 +330,7 @@ int launch_attention(const AttnP &p, int G, cudaStream_t s) {
     }
     dim3 grid((unsigned)((p.B + AT_WPC - 1) / AT_WPC), G);
     constexpr size_t smem = AT_SMEM_FLOATS * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-        VP_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    if (int rc = ensure_dyn_smem((const void *)attention_kernel, smem)) return rc;
     KTimer kt(KC_ATTN, s);
     attention_kernel<<<grid, AT_NT, smem, s>>>(p);
     VP_LAUNCH_CHECK();

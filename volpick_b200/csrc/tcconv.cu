@@ -745,11 +745,7 @@ constexpr int tc_epi_warps() {
 template <int NOUT, int SPLIT, int NTAPS, int NQ, int EW, int FLAGS>
 static int launch_tc(const TcP &p, dim3 grid, size_t smem, cudaStream_t s) {
     auto kern = tcconv_kernel<NOUT, SPLIT, NTAPS, NQ, EW, FLAGS>;
-    static size_t attr = 0;
-    if (smem > attr) {
-        VP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = smem;
-    }
+    if (int rc = ensure_dyn_smem((const void *)kern, smem)) return rc;
     KTimer kt(KC_TCCONV, s);
     kern<<<grid, 32 * (EW + 4), smem, s>>>(p);
     VP_LAUNCH_CHECK();
@@ -875,7 +871,7 @@ int tc_launch(const TcLayer &L, const TcIO &io, cudaStream_t s) {
     const int stages = (int)std::min<size_t>(TC_MAX_STAGES, (share - w_bytes) / a_bytes);
     p.n_stages = stages;
     const size_t smem = w_bytes + (size_t)stages * a_bytes;
-    int64_t ctas = (148 * occ + L.groups - 1) / L.groups;
+    int64_t ctas = ((int64_t)device_sm_count() * occ + L.groups - 1) / L.groups;
     ctas = std::max<int64_t>(1, std::min<int64_t>(ctas, n_tiles));
     dim3 grid((unsigned)ctas, L.groups);
     // compile-time MMA schedules for the layer shapes of the EQTransformer (N, taps | tap pairs, channel pairs)

@@ -141,13 +141,20 @@ def _ns(t) -> int:
 
 
 class _PendingRecord:
-    """A record between ``vp_annotate_begin`` and ``vp_annotate_end``; keeps the host buffers alive until ``result()``."""
+    """A record between ``vp_annotate_begin`` and ``vp_annotate_end``; keeps the host buffers alive until ``result()``.
 
-    def __init__(self, model, pending, annotation, pick_capacity, keep):
+    ``retry(capacity)``: re-runs the record with a larger pick buffer when the device reported more triggers than
+    ``pick_capacity`` (VP_ERR_CAPACITY carries the exact count) -- overflow is never a silent truncation and never fatal."""
+
+    def __init__(self, model, pending, annotation, pick_capacity, keep, retry=None):
         self._model, self._pending, self._annotation, self._cap, self._keep = model, pending, annotation, pick_capacity, keep
+        self._retry = retry
         self._result = None
+        self._error = None
 
     def result(self):
+        if self._error is not None:
+            raise self._error
         if self._result is None:
             import torch
 
@@ -155,10 +162,20 @@ class _PendingRecord:
             trig = (_lib.Trigger * self._cap)()
             n_picks = C.c_int64(0)
             trim = np.zeros(6, dtype=np.int64)
-            pending, self._pending = self._pending, None
-            with torch.cuda.device(self._model._device_index):
-                _lib.check(lib.vp_annotate_end(pending, C.cast(trig, C.c_void_p), self._cap, C.byref(n_picks),
-                                               C.c_void_p(trim.ctypes.data)))
+            pending, self._pending = self._pending, None  # vp_annotate_end releases the record, also on error
+            try:
+                with torch.cuda.device(self._model._device_index):
+                    _lib.check(lib.vp_annotate_end(pending, C.cast(trig, C.c_void_p), self._cap, C.byref(n_picks),
+                                                   C.c_void_p(trim.ctypes.data)))
+            except _lib.VolpickError as e:
+                if e.code == _lib.VP_ERR_CAPACITY and self._retry is not None and n_picks.value > self._cap:
+                    retry, self._retry = self._retry, None
+                    self._result = retry(int(n_picks.value) + 16).result()
+                    self._keep = None
+                    return self._result
+                self._error = e
+                self._keep = None
+                raise
             triggers = np.frombuffer(trig, dtype=_lib.TRIGGER_DTYPE, count=n_picks.value).copy()
             self._result = (self._annotation, triggers, trim.reshape(3, 2))
             self._keep = None
@@ -188,18 +205,34 @@ class WaveformModel:
         "flexible_horizontal_components", "detection_threshold", "precision", "chunk_windows",
     }
 
-    def __init__(self, component_order: str = "ZNE", norm: str = "peak", sampling_rate: float = 100, **kwargs):
+    def __init__(self, component_order: str = "ZNE", norm: str = "peak", sampling_rate: float = 100,
+                 norm_amp_per_comp: bool = False, norm_detrend: bool = False, **kwargs):
         if norm != "peak":
             raise NotImplementedError("only norm='peak' (the volpick weights) is implemented on the GPU path")
         self.component_order = component_order
         self.norm = norm
+        # SeisBench's constructor kwargs of the window pre-processing (annotate_batch_pre; read from the JSON
+        # ``model_args`` by from_pretrained like every other constructor argument):
+        #   norm_detrend       linear detrend of every window component after the demean (scipy.signal.detrend)
+        #   norm_amp_per_comp  every component divided by its OWN peak
+        # With norm="peak" and norm_amp_per_comp=False this implementation also normalises per component: that is the
+        # normalisation the volpick weights were trained and evaluated with (sbg.Normalize(demean_axis=-1, amp_norm_axis=-1,
+        # amp_norm_type="peak"), /root/reference/volpick/model/models.py:449-451,853-855; eval_taks0.py:465-467) and what
+        # SeisBench's annotate_window_pre / annotate_batch_pre do for norm="peak" (peak over axis=-1, keepdims) as far as
+        # the oracle's authors can restate it (SeisBench is not available here: DESIGN.md section 0c).
+        # The other reading -- one peak over all three components of a window -- is kept reachable as
+        # ``peak_scope="window"`` (not a SeisBench kwarg) so that the exposure can be measured (tests/test_gpu_parity.py).
+        self.norm_amp_per_comp = bool(norm_amp_per_comp)
+        self.norm_detrend = bool(norm_detrend)
         self.sampling_rate = float(sampling_rate)
         self.default_args: Dict[str, Any] = {}
         self.weights_docstring: Optional[str] = None
         self.weights_version: Optional[str] = None
         self.filter_args = None
         self.filter_kwargs = None
-        self.peak_scope = kwargs.pop("peak_scope", "channel")  # SURVEY.md Appendix C.2 / D #6
+        self.peak_scope = kwargs.pop("peak_scope", "channel")
+        if self.peak_scope not in _lib.PEAK_SCOPE:
+            raise ValueError(f"peak_scope must be one of {sorted(_lib.PEAK_SCOPE)}, got {self.peak_scope!r}")
         self.precision = kwargs.pop("precision", self._default_precision)
         self._weights: Optional["OrderedDict[str, np.ndarray]"] = None
         self._flat: Optional[np.ndarray] = None
@@ -284,11 +317,14 @@ class WaveformModel:
     def _create_handle(self) -> None:
         if self._flat is None:
             raise RuntimeError("model has no weights: use from_pretrained() or load_state_dict() first")
+        import torch
+
         lib = _lib.load()
         self._destroy_handle()
         h = C.c_void_p(None)
-        _lib.check(lib.vp_model_create(self._kind, self._flat.ctypes.data_as(C.c_void_p), self._flat.size,
-                                       int(self._device_index), C.byref(h)))
+        with torch.cuda.device(int(self._device_index)):  # the caller's current device is left as it was
+            _lib.check(lib.vp_model_create(self._kind, self._flat.ctypes.data_as(C.c_void_p), self._flat.size,
+                                           int(self._device_index), C.byref(h)))
         self._handle = h
 
     def to(self, device):
@@ -441,9 +477,10 @@ class WaveformModel:
         cap = B * 3 * 48000 * 2
         out = torch.empty(cap, dtype=torch.float32, device=x.device)
         n = C.c_int64(0)
-        _lib.check(lib.vp_forward_tap(self._handle, C.c_void_p(x.data_ptr()), B, C.c_void_p(y.data_ptr()),
-                                      C.c_void_p(ws.data_ptr()), ws.numel(), prec, tap.encode(),
-                                      C.c_void_p(out.data_ptr()), cap, C.byref(n), self._stream_ptr()))
+        with torch.cuda.device(x.device):
+            _lib.check(lib.vp_forward_tap(self._handle, C.c_void_p(x.data_ptr()), B, C.c_void_p(y.data_ptr()),
+                                          C.c_void_p(ws.data_ptr()), ws.numel(), prec, tap.encode(),
+                                          C.c_void_p(out.data_ptr()), cap, C.byref(n), self._stream_ptr()))
         return out[: n.value]
 
     def tap_names(self) -> List[str]:
@@ -546,18 +583,52 @@ class WaveformModel:
         argdict["_sos"] = self.design_filter()
         for tr in stream:
             if abs(float(tr.stats.sampling_rate) - self.sampling_rate) > 1e-6:
-                if hasattr(tr, "resample") and _is_obspy(tr):
-                    tr.resample(self.sampling_rate)
-                else:
-                    raise NotImplementedError(
-                        f"trace {tr.id} has sampling rate {tr.stats.sampling_rate} Hz; resampling to "
-                        f"{self.sampling_rate} Hz needs an ObsPy stream"
-                    )
+                self.resample_trace(tr)
+
+    def resample_trace(self, tr) -> None:
+        """SeisBench ``WaveformModel.resample`` for one trace, in place.  A sampling rate that is an integer multiple of
+        the model's: ``trace.filter("lowpass", freq=sampling_rate / 2, zerophase=True)`` (ObsPy: 4 corners, float64
+        ``sosfilt`` forward + backward) + ``trace.decimate(factor, no_filter=True)`` (every factor-th sample) -- the
+        filter runs on the device (``vp_sosfilt``).  Any other ratio is ObsPy's FFT ``Trace.resample`` and needs ObsPy."""
+        import torch
+        from scipy.signal import iirfilter, zpk2sos
+
+        rate = float(tr.stats.sampling_rate)
+        ratio = rate / self.sampling_rate
+        factor = int(round(ratio))
+        if factor >= 2 and abs(ratio - factor) < 1e-9:
+            self._require_gpu()
+            z, p, k = iirfilter(4, self.sampling_rate / rate, btype="lowpass", ftype="butter", output="zpk")
+            sos = np.ascontiguousarray(zpk2sos(z, p, k), dtype=np.float64)
+            data = np.ascontiguousarray(tr.data)
+            if data.dtype not in (np.float32, np.int32):
+                data = data.astype(np.float32)
+            y = self.filter_record(data[None, :], sos, zerophase=True)
+            tr.data = y[0, ::factor].contiguous().cpu().numpy()
+            tr.stats.sampling_rate = self.sampling_rate
+            if not _is_obspy(tr):
+                tr.stats.npts = len(tr.data)
+            return
+        if hasattr(tr, "resample") and _is_obspy(tr):
+            tr.resample(self.sampling_rate, no_filter=True)
+            return
+        raise NotImplementedError(
+            f"trace {tr.id} has sampling rate {rate} Hz: only integer multiples of {self.sampling_rate} Hz are resampled "
+            "on the device (low-pass + decimation); other ratios need an ObsPy stream (FFT resampling)"
+        )
 
     def stream_to_arrays(self, traces: Sequence, argdict) -> List[Tuple[Any, np.ndarray]]:
+        """List form of ``_iter_stream_arrays`` (fresh NumPy arrays)."""
+        return list(self._iter_stream_arrays(traces, argdict))
+
+    def _iter_stream_arrays(self, traces: Sequence, argdict, alloc=None):
         """SeisBench ``stream_to_array`` (cf. the fork at /root/reference/volpick/data/convert.py:26-70):
-        traces of ONE instrument -> [(t0, float32 (3, n))] per gap-free segment, component order
-        ``component_order``, missing components zero-filled (``strict=False``) or dropped (``strict=True``)."""
+        traces of ONE instrument -> generator of (t0, (3, n) array) per gap-free segment, component order
+        ``component_order``, missing components zero-filled (``strict=False``) or dropped (``strict=True``).
+
+        The record keeps the traces' dtype when they are all int32 counts (converted on the device, ``VP_DTYPE_I32``),
+        else it is float32.  ``alloc(shape, dtype)`` provides the record buffer (``_run`` hands out a recycled pinned
+        buffer, so the H2D copy of ``vp_annotate_begin`` is asynchronous); default: a fresh NumPy array."""
         rate = self.sampling_rate
         comp = {c: i for i, c in enumerate(self.component_order)}
         present = {tr.stats.channel[-1] for tr in traces if len(tr.data) > 0}
@@ -571,7 +642,7 @@ class WaveformModel:
                     comp[a] = comp[b]
         use = [tr for tr in traces if tr.stats.channel[-1] in comp and len(tr.data) > 0]
         if not use:
-            return []
+            return
         use.sort(key=lambda t: _ns(t.stats.starttime))
         segments: List[List] = []
         seg_end = None
@@ -584,26 +655,35 @@ class WaveformModel:
             else:
                 segments[-1].append(tr)
                 seg_end = max(seg_end, end)
-        out = []
+        strict = bool(argdict.get("strict", False))
+        ncomp = len(self.component_order)
         for seg in segments:
             t0 = seg[0].stats.starttime
             t0ns = _ns(t0)
             offs = [int(round((_ns(tr.stats.starttime) - t0ns) * rate / 1e9)) for tr in seg]
             n = max(o + len(tr.data) for o, tr in zip(offs, seg))
-            arr = np.zeros((len(self.component_order), n), dtype=np.float32)
-            have = np.zeros((len(self.component_order), n), dtype=bool)
+            dtype = np.int32 if all(np.asarray(tr.data).dtype == np.int32 for tr in seg) else np.float32
+            arr = alloc((ncomp, n), dtype) if (alloc is not None and not strict) else np.empty((ncomp, n), dtype=dtype)
+            full = [False] * ncomp  # components covered end to end by one trace need no zero fill
+            for o, tr in zip(offs, seg):
+                if o == 0 and len(tr.data) == n:
+                    full[comp[tr.stats.channel[-1]]] = True
+            for ci in range(ncomp):
+                if not full[ci]:
+                    arr[ci, :] = 0
+            have = np.zeros((ncomp, n), dtype=bool) if strict else None
             for o, tr in zip(offs, seg):
                 ci = comp[tr.stats.channel[-1]]
                 arr[ci, o : o + len(tr.data)] = tr.data
-                have[ci, o : o + len(tr.data)] = True
-            if argdict.get("strict", False):
+                if strict:
+                    have[ci, o : o + len(tr.data)] = True
+            if strict:
                 allc = have.all(axis=0)
                 edges = np.flatnonzero(np.diff(np.concatenate([[0], allc.astype(np.int8), [0]])))
                 for a, b in zip(edges[::2], edges[1::2]):
-                    out.append((t0 + a / rate, np.ascontiguousarray(arr[:, a:b])))
+                    yield t0 + a / rate, np.ascontiguousarray(arr[:, a:b])
             else:
-                out.append((t0, arr))
-        return out
+                yield t0, arr
 
     # ---- the path ------------------------------------------------------------------------------
     def _params(self, argdict, thresholds: Sequence[float]) -> "_lib.AnnotateParams":
@@ -612,7 +692,8 @@ class WaveformModel:
         p.blinding[0], p.blinding[1] = argdict["blinding"]
         p.stacking = _lib.STACK[argdict["stacking"]]
         p.precision = _lib.PRECISION[argdict.get("precision", self.precision)]
-        p.peak_scope = _lib.PEAK_SCOPE[self.peak_scope]
+        p.peak_scope = _lib.PEAK_SCOPE["channel" if self.norm_amp_per_comp else self.peak_scope]
+        p.norm_detrend = int(self.norm_detrend)
         p.chunk_windows = int(argdict.get("chunk_windows", 0) or 0)
         for i in range(3):
             p.threshold[i] = float(thresholds[i])
@@ -685,7 +766,12 @@ class WaveformModel:
                 self._handle, C.c_void_p(ptr), int(on_host), dtype, n, ch_stride, C.byref(params),
                 C.c_void_p(annotation.ctypes.data) if want_annotation and pred_len else None, 1, pick_capacity,
                 C.c_void_p(ws.data_ptr()), ws.numel(), sptr, C.byref(pending)))
-        return _PendingRecord(self, pending, annotation, pick_capacity, (keep, ws, params))
+        def retry(capacity):  # blocking re-run with the exact trigger count (rare: a noisy record with a low threshold)
+            ad = dict(argdict)
+            ad["_sos"] = None  # `keep` is the record after the pre-filter
+            return self.annotate_array_async(keep, ad, want_annotation, thresholds, capacity, stream, None)
+
+        return _PendingRecord(self, pending, annotation, pick_capacity, (keep, ws, params), retry)
 
     def annotate_workspace_bytes(self, n_samples: int, argdict: Optional[Dict[str, Any]] = None, on_host: bool = True,
                                  pick_capacity: int = 1 << 16) -> int:
@@ -722,6 +808,21 @@ class WaveformModel:
             self._slots = (self._device_index, [torch.cuda.Stream(self._device_index) for _ in range(2)], [None, None])
         slot_streams, slot_ws = self._slots[1], self._slots[2]
         in_flight = deque()
+        # pinned staging ring: record i is assembled straight into slot (i & 1)'s page-locked buffer (kept across calls:
+        # page-locking 104 MB costs more than a station-day of compute), so vp_annotate_begin returns after enqueueing
+        # and the H2D pieces of record i + 1 run under the network of record i
+        if getattr(self, "_pinned", None) is None:
+            self._pinned = [None, None]
+        n_rec = 0
+
+        def alloc(shape, dtype):
+            k = n_rec & 1
+            nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+            buf = self._pinned[k]
+            if buf is None or buf.numel() < nbytes:
+                self._pinned[k] = None
+                buf = self._pinned[k] = torch.empty(max(nbytes, 1), dtype=torch.uint8, pin_memory=True)
+            return buf[:nbytes].view(torch.int32 if np.dtype(dtype) == np.int32 else torch.float32).view(*shape).numpy()
 
         def collect():
             (s0, trace_id, t0), handle = in_flight.popleft()
@@ -746,18 +847,17 @@ class WaveformModel:
                             tp = tstart + float((int(tg["s_peak"]) - first) / rate)
                             picks.append(Pick(trace_id, ts, te, tp, float(tg["value"]), label))
 
-        n_rec = 0
         for key in groups:
             trs = groups[key]
             s0 = trs[0].stats
             trace_id = f"{s0.network}.{s0.station}.{s0.location}"
-            for t0, arr in self.stream_to_arrays(trs, argdict):
+            for t0, arr in self._iter_stream_arrays(trs, argdict, alloc):
                 if arr.shape[1] < self.in_samples:
                     logger.warning("Parts of the input stream consist of fragments shorter than the number of "
                                    "input samples. Output might be empty.")
                     continue
                 k = n_rec & 1
-                n_rec += 1
+                n_rec += 1  # the next alloc() hands out the other slot; this slot is reused only after its collect()
                 need = self.annotate_workspace_bytes(arr.shape[1], argdict, True)
                 if slot_ws[k] is None or slot_ws[k].numel() < need:
                     slot_ws[k] = None

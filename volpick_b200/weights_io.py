@@ -104,7 +104,8 @@ def find_weights(model_dir: str, name: str, version_str: Optional[str] = None) -
             versions = [v for v in versions if v == str(version_str)]
         if not versions:
             continue
-        ver = sorted(versions, key=lambda s: [int(p) if p.isdigit() else p for p in s.split(".")])[-1]
+        # type-stable key: numeric parts sort before (and among themselves numerically), text parts lexically
+        ver = sorted(versions, key=lambda s: [(0, int(p), "") if p.isdigit() else (1, 0, p) for p in s.split(".")])[-1]
         js = os.path.join(d, f"{name}.json.v{ver}")
         for ext in ("vpw", "pt"):
             w = os.path.join(d, f"{name}.{ext}.v{ver}")
