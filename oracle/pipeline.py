@@ -56,7 +56,9 @@ def prenorm(batch: np.ndarray, kind: str, norm: str = "peak", peak_scope: str = 
     of every component after the demean.
     """
     x = batch.astype(np.float32, copy=True)
-    x = x - x.mean(axis=-1, keepdims=True, dtype=np.float32)
+    # mean accumulated in float64, applied in float32: SeisBench 0.4 takes it in NumPy's float64 (int32 / float64 traces),
+    # torch's CPU mean of later releases accumulates float32 input in double
+    x = x - x.mean(axis=-1, keepdims=True, dtype=np.float64).astype(np.float32)
     if detrend:
         from scipy.signal import detrend as _detrend
 

@@ -11,6 +11,9 @@ constexpr int FZ_MAX_TERMS = 32;   // tcgen05.mma per M tile of one layer (taps 
 constexpr int FZ_MAX_TILES = 8;    // M tiles (128 rows) of one layer per work item
 constexpr int FZ_MAX_LAYERS = 4;
 constexpr int FZ_NPIPE = 2;        // independent work-item pipelines per CTA (each: loader, issuer, 4 epilogue warps)
+constexpr int FZ_NSLOT = 1;        // input buffers per pipeline: the slot is free again once the first layer's MMAs have retired, long
+                                   // before the item ends, so ONE slot still lets the loader run a whole item ahead (and leaves the
+                                   // shared memory for longer items: 53 instead of 47 rows = 6 instead of 7 items per blinded window)
 constexpr int FZ_NBUF = 4;         // TMEM accumulator buffers per pipeline
 constexpr int FZ_NCOLS = 64;       // TMEM columns per accumulator (max MMA N of the chain)
 // warps: NPIPE loaders, NPIPE issuers, 4 NPIPE layer-epilogue warps, 4 NPIPE head warps
@@ -68,7 +71,7 @@ struct FzDecB {
     const uint16_t *blob;  // device: [group][blob_bytes / 2]
     float head_w[3][88];  // [group][c * 11 + k]
     float head_b[3];
-    int head_in_off, head_rp, W, L_out;
+    int head_in_off, head_rp, head_swz, head_wait_layer, W, L_out;
     float *y;  // (B, 3, L_out) probabilities
     int smem_bytes;
 };

@@ -44,6 +44,9 @@ __device__ __forceinline__ void fz_pack8(const float *v, bool valid, uint4 &hi, 
 }
 
 // CH accumulator columns starting at col0 (+ the stacked half at col0 + NST when NST > 0) -> relu(acc + bias).
+// The biases are read from shared memory as broadcast 16-byte loads (6 % of the kernel's shared-memory wavefronts).  Reading
+// them through the constant bank instead (kernel parameters, one LDC with a register offset per value) was measured
+// SLOWER: 10.38 vs 10.03 ms per station-day.
 template <int CH, int NST>
 __device__ __forceinline__ void fz_load_cols(const float *bias /*shared memory, column col0*/, uint32_t tacc, int col0, float (&v)[CH]) {
     uint32_t r[CH], r2[NST > 0 ? CH : 1];
@@ -109,9 +112,15 @@ __device__ __forceinline__ void fz_epi16(const FzLayer &L, const float *bias, ui
     }
 }
 
+// fp32 planar head input [c][row]: the head reads it as 16-byte units (4 rows).  With 8 outputs per head thread the lane
+// stride is two units, so a quarter warp would hit only four of the eight 16-byte bank groups (2-way conflict on every
+// load); flipping the low unit bit in every other group of eight units makes the eight accesses distinct.  12 outputs per
+// thread (lane stride three units) are conflict-free as they are.
+__device__ __forceinline__ int fz_head_unit(int u, int swz) { return swz ? (u ^ ((u >> 3) & 1)) : u; }
+
 // Last polyphase layer (8 channels per phase) -> fp32 planar [c][row] for the CUDA-core head.
 template <bool STACK>
-__device__ __forceinline__ void fz_epi32(const FzLayer &L, const float *bias, uint32_t tacc, int t, int r, int R0, uint8_t *arena) {
+__device__ __forceinline__ void fz_epi32(const FzLayer &L, const float *bias, uint32_t tacc, int t, int r, int R0, uint8_t *arena, int swz) {
     const int s_rel = L.s_lo + 128 * t + r;
     const int lrow0 = 2 * s_rel - L.out_lo;  // even
     const int grow0 = 2 * ((R0 << L.lvl) + s_rel);
@@ -119,7 +128,7 @@ __device__ __forceinline__ void fz_epi32(const FzLayer &L, const float *bias, ui
     fz_load_cols<16, STACK ? 16 : 0>(bias, tacc, 0, v);
     if ((unsigned)lrow0 < (unsigned)L.out_rows) {  // out_rows is even: both phases are in range together
         const bool valid = (unsigned)grow0 < (unsigned)L.T_out;  // T_out even: both phases valid together
-        float *d = reinterpret_cast<float *>(arena + L.out_off) + lrow0;
+        float *d = reinterpret_cast<float *>(arena + L.out_off) + 4 * fz_head_unit(lrow0 >> 2, swz) + (lrow0 & 3);
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
             float2 o;
@@ -130,34 +139,40 @@ __device__ __forceinline__ void fz_epi32(const FzLayer &L, const float *bias, ui
     }
 }
 
-// sigmoid(conv k11, 8 -> 1) on the CUDA cores: thread e = OPT consecutive output samples.
+// sigmoid(conv k11, 8 -> 1) on the CUDA cores: thread e = OPT consecutive output samples (OPT a multiple of 4).
 template <int OPT>
 __device__ __forceinline__ void fz_head(const FzDecB &p, const float *hw /*shared: [8][12] weights, [96] bias*/, int g, int b, int R0, int e,
                                         const uint8_t *arena) {
+    static_assert(OPT % 4 == 0, "the head reads 16-byte units");
     const int tl0 = OPT * e;
     if (tl0 >= p.W) return;
-    const float *d6 = reinterpret_cast<const float *>(arena + p.head_in_off) + tl0;
-    const int RP = p.head_rp;
+    const float *d6 = reinterpret_cast<const float *>(arena + p.head_in_off);
+    const int RP = p.head_rp, swz = p.head_swz;
     float acc[OPT];
 #pragma unroll
     for (int o = 0; o < OPT; ++o) acc[o] = hw[96];
-    // the loads of channel c + 1 are issued before the FMAs of channel c (with two warps per scheduler nothing
-    // else hides the shared-memory latency: measured ~45 % of the head's cycles were short-scoreboard stalls)
-    constexpr int NV = (OPT + 12) / 2;
-    float2 cur[NV], nxt[NV];
+    // buffer rows tl0 .. tl0 + OPT + 11 (row 0 = output - 6): NU units of 4 rows; the loads of channel c + 1 are issued before
+    // the FMAs of channel c (with two warps per scheduler nothing else hides the shared-memory latency)
+    constexpr int NU = (OPT + 12) / 4;
+    int uo[NU];
 #pragma unroll
-    for (int q = 0; q < NV; ++q) cur[q] = *reinterpret_cast<const float2 *>(d6 + 2 * q);
+    for (int q = 0; q < NU; ++q) uo[q] = 4 * fz_head_unit((tl0 >> 2) + q, swz);
+    float4 cur[NU], nxt[NU];
+#pragma unroll
+    for (int q = 0; q < NU; ++q) cur[q] = *reinterpret_cast<const float4 *>(d6 + uo[q]);
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
         if (c + 1 < 8) {
 #pragma unroll
-            for (int q = 0; q < NV; ++q) nxt[q] = *reinterpret_cast<const float2 *>(d6 + (size_t)(c + 1) * RP + 2 * q);
+            for (int q = 0; q < NU; ++q) nxt[q] = *reinterpret_cast<const float4 *>(d6 + (size_t)(c + 1) * RP + uo[q]);
         }
-        float xv[OPT + 12];
+        float xv[4 * NU];
 #pragma unroll
-        for (int q = 0; q < NV; ++q) {
-            xv[2 * q] = cur[q].x;
-            xv[2 * q + 1] = cur[q].y;
+        for (int q = 0; q < NU; ++q) {
+            xv[4 * q] = cur[q].x;
+            xv[4 * q + 1] = cur[q].y;
+            xv[4 * q + 2] = cur[q].z;
+            xv[4 * q + 3] = cur[q].w;
         }
         // weights of this channel: three broadcast 16-byte reads (a kernel-parameter array indexed by the run-time
         // group costs one constant load with a register offset per FMA)
@@ -171,17 +186,19 @@ __device__ __forceinline__ void fz_head(const FzDecB &p, const float *hw /*share
             for (int o = 0; o < OPT; ++o) acc[o] = fmaf(w, xv[o + k + 1], acc[o]);  // buffer row 0 = output - 6
         }
 #pragma unroll
-        for (int q = 0; q < NV; ++q) cur[q] = nxt[q];
+        for (int q = 0; q < NU; ++q) cur[q] = nxt[q];
     }
     const int t_out = 16 * R0 + tl0;
     float *yb = p.y + ((size_t)b * 3 + g) * p.L_out + t_out;
 #pragma unroll
-    for (int o = 0; o < OPT; o += 2) {
-        if (tl0 + o < p.W && t_out + o < p.L_out) {  // W and L_out are even
-            float2 o2;
-            o2.x = 1.f / (1.f + expf(-acc[o]));
-            o2.y = 1.f / (1.f + expf(-acc[o + 1]));
-            *reinterpret_cast<float2 *>(yb + o) = o2;
+    for (int o = 0; o < OPT; o += 4) {
+        if (tl0 + o < p.W && t_out + o < p.L_out) {  // W, L_out and t_out are multiples of 4 (16-byte store)
+            float4 o4;
+            o4.x = 1.f / (1.f + expf(-acc[o]));
+            o4.y = 1.f / (1.f + expf(-acc[o + 1]));
+            o4.z = 1.f / (1.f + expf(-acc[o + 2]));
+            o4.w = 1.f / (1.f + expf(-acc[o + 3]));
+            *reinterpret_cast<float4 *>(yb + o) = o4;
         }
     }
 }
@@ -190,7 +207,7 @@ __device__ __forceinline__ void fz_head(const FzDecB &p, const float *hw /*share
 // tiles, then issue the layer's compile-time MMA schedule (the first MMA overwrites the accumulator).
 template <int LYR, int SPLIT>
 __device__ __forceinline__ void fz_issue_layer(const FzDecB &p, int pp, int slot, int n, uint32_t &i, uint32_t tmem_base,
-                                               uint32_t arena16, uint32_t sB16, uint64_t (*in_full)[2], uint64_t (*in_empty)[2],
+                                               uint32_t arena16, uint32_t sB16, uint64_t (*in_full)[FZ_NSLOT], uint64_t (*in_empty)[FZ_NSLOT],
                                                uint64_t (*acc_full)[FZ_NBUF], uint64_t (*done_bar)[FZ_NBUF]) {
     constexpr int l = LYR;
     constexpr int NOUT = FZ_DEC_NOUT[l];
@@ -211,7 +228,7 @@ __device__ __forceinline__ void fz_issue_layer(const FzDecB &p, int pp, int slot
                 mbar_wait(&done_bar[pp][d & (FZ_NBUF - 1)], (d / FZ_NBUF) & 1);
             }
         }
-        if (l == 0 && t == 0) mbar_wait(&in_full[pp][slot], (n >> 1) & 1);
+        if (l == 0 && t == 0) mbar_wait(&in_full[pp][slot], (n / FZ_NSLOT) & 1);
         fence_proxy_async();
         tc_fence_after();
         const uint32_t a16 = in16 + (uint32_t)t * 128u;
@@ -233,7 +250,7 @@ __device__ __forceinline__ void fz_issue_layer(const FzDecB &p, int pp, int slot
 template <int SPLIT, int OPT>
 __global__ void __launch_bounds__(FZ_THREADS, 1) decb_kernel(const __grid_constant__ FzDecB p) {
     extern __shared__ __align__(128) uint8_t fz_smem[];
-    __shared__ __align__(8) uint64_t in_full[FZ_NPIPE][2], in_empty[FZ_NPIPE][2], acc_full[FZ_NPIPE][FZ_NBUF],
+    __shared__ __align__(8) uint64_t in_full[FZ_NPIPE][FZ_NSLOT], in_empty[FZ_NPIPE][FZ_NSLOT], acc_full[FZ_NPIPE][FZ_NBUF],
         done_bar[FZ_NPIPE][FZ_NBUF], head_go[FZ_NPIPE], head_done[FZ_NPIPE];
     __shared__ uint32_t tmem_base_s;
 
@@ -244,7 +261,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) decb_kernel(const __grid_consta
 
     if (tid == 0) {
         for (int pp = 0; pp < FZ_NPIPE; ++pp) {
-            for (int i = 0; i < 2; ++i) {
+            for (int i = 0; i < FZ_NSLOT; ++i) {
                 mbar_init(&in_full[pp][i], 32);
                 mbar_init(&in_empty[pp][i], 1);
             }
@@ -277,8 +294,8 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) decb_kernel(const __grid_consta
         const uint16_t *xg = p.x + (long long)g * p.x_gs;
         int n = 0;
         for (int item = blockIdx.x + pp * gridDim.x; item < n_items; item += FZ_NPIPE * gridDim.x, ++n) {
-            const int slot = n & 1;
-            mbar_wait(&in_empty[pp][slot], ((n >> 1) & 1) ^ 1);
+            const int slot = n % FZ_NSLOT;
+            mbar_wait(&in_empty[pp][slot], ((n / FZ_NSLOT) & 1) ^ 1);
             const int b = item / p.tiles_per_seq, j = item - b * p.tiles_per_seq;
             const int row_base = p.c0 * j + p.row_off0 + p.in_lo0;
             const uint32_t dst0 = sbase + pp * p.pipe_stride + p.L[0].in_off + slot * p.in_slot_bytes;
@@ -304,7 +321,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) decb_kernel(const __grid_consta
         uint32_t i = 0;
         int n = 0;
         for (int item = blockIdx.x + pp * gridDim.x; item < n_items; item += FZ_NPIPE * gridDim.x, ++n) {
-            const int slot = n & 1;
+            const int slot = n % FZ_NSLOT;
             fz_issue_layer<0, SPLIT>(p, pp, slot, n, i, tmem_base, arena16, sB16, in_full, in_empty, acc_full, done_bar);
             fz_issue_layer<1, SPLIT>(p, pp, slot, n, i, tmem_base, arena16, sB16, in_full, in_empty, acc_full, done_bar);
             fz_issue_layer<2, SPLIT>(p, pp, slot, n, i, tmem_base, arena16, sB16, in_full, in_empty, acc_full, done_bar);
@@ -324,7 +341,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) decb_kernel(const __grid_consta
             for (int l = 0; l < p.n_layers; ++l) {
                 const FzLayer &L = p.L[l];
                 // layer 1 is the first writer of buffer X, which the head warps may still be reading (previous item)
-                if (l == 1 && n > 0) mbar_wait(&head_done[pp], (n - 1) & 1);
+                if (l == p.head_wait_layer && n > 0) mbar_wait(&head_done[pp], (n - 1) & 1);
                 for (int t = 0; t < L.n_tiles; ++t, ++i) {
                     const uint32_t buf = i & (FZ_NBUF - 1);
                     mbar_wait(&acc_full[pp][buf], (i / FZ_NBUF) & 1);
@@ -337,7 +354,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) decb_kernel(const __grid_consta
                     const int wrow0 = 2 * (L.s_lo + 128 * t + 32 * q) - L.out_lo;
                     if (wrow0 < L.out_rows && wrow0 + 64 > 0 && !(p.dbg & 2)) {
                         if (l == 0) fz_epi16<32, SPLIT, ST && FZ_DEC_STACK[0]>(L, bias, tacc, t, r, R0, arena);
-                        else if (l == 3) fz_epi32<ST && FZ_DEC_STACK[3]>(L, bias, tacc, t, r, R0, arena);
+                        else if (l == 3) fz_epi32<ST && FZ_DEC_STACK[3]>(L, bias, tacc, t, r, R0, arena, p.head_swz);
                         else fz_epi16<16, SPLIT, ST && FZ_DEC_STACK[1]>(L, bias, tacc, t, r, R0, arena);
                     }
                     fence_proxy_async();  // generic-proxy writes -> visible to the tensor-core (async) proxy
@@ -386,8 +403,9 @@ int decb_build(DecBPlan &plan, const TcLayer *dec, int split, int m, const float
     p.tiles_per_seq = (p.T0 + m - 1) / m;
     p.W = 16 * m;
     p.L_out = 6000;
-    plan.opt = ((p.W + 127) / 128 + 1) & ~1;
-    VP_REQUIRE(plan.opt == 6 || plan.opt == 10, VP_ERR_UNSUPPORTED, "decb: no head instance for %d outputs per thread", plan.opt);
+    plan.opt = ((p.W + 127) / 128 + 3) & ~3;  // head: 128 threads per pipeline, a multiple of 4 outputs each (16-byte units)
+    VP_REQUIRE(plan.opt == 8 || plan.opt == 12, VP_ERR_UNSUPPORTED, "decb: no head instance for %d outputs per thread", plan.opt);
+    p.head_swz = plan.opt == 8 ? 1 : 0;
     int lo[5], hi[5], c[5];
     for (int k = 0; k <= NL; ++k) c[k] = m << k;
     lo[NL] = -6;  // the head (k11) needs -5; even so that both phases of a row land on an aligned float2
@@ -417,16 +435,20 @@ int decb_build(DecBPlan &plan, const TcLayer *dec, int split, int m, const float
         else if (c8 >= 8) pitch0 |= 1;
     }
     auto lvl_bytes = [&](int k) {
-        if (k == NL) return (size_t)8 * (size_t)(((hi[k] - lo[k]) + 12 + 3) & ~3) * 4;
+        if (k == NL) return (size_t)8 * (size_t)((((hi[k] - lo[k]) + 12 + 3) & ~3) + 4) * 4;  // + one unit: the swizzle swaps unit pairs
         const int ch = (k == 0) ? dec[3].cin : dec[3 + k - 1].cout;
         return (size_t)(k == 0 ? pitch0 : hi[k] - lo[k]) * (ch / 8) * esz;
     };
     auto up128 = [](size_t v) { return (v + 127) & ~(size_t)127; };
     p.in_slot_bytes = (int)up128(lvl_bytes(0));
-    const size_t off_x = 2 * (size_t)p.in_slot_bytes;
+    const size_t off_x = FZ_NSLOT * (size_t)p.in_slot_bytes;
+    // Buffer X holds level 2 and then the head's input (level 4): the next item's layer 1 stores its output only after the
+    // head of the previous item is done.  (A separate level-2 buffer was measured: 10.61 vs 10.63 ms -- the head is not on
+    // the critical path.)
     const size_t off_y = off_x + up128(std::max(lvl_bytes(2), lvl_bytes(4)));
     p.pipe_stride = (int)(off_y + up128(std::max(lvl_bytes(1), lvl_bytes(3))));
     p.blob_off = FZ_NPIPE * p.pipe_stride;
+    p.head_wait_layer = 1;
     const size_t lvl_off[5] = {0, off_y, off_x, off_y, off_x};
     // blob per group: the weight blocks of the four layers
     size_t blob = 0;
@@ -458,7 +480,7 @@ int decb_build(DecBPlan &plan, const TcLayer *dec, int split, int m, const float
         L.in_pitch = (l == 0) ? pitch0 : L.in_rows;
         L.out_off = (int)lvl_off[l + 1];
         L.out_rows = hi[l + 1] - lo[l + 1];
-        L.out_rp = (l == NL - 1) ? ((L.out_rows + 12 + 3) & ~3) : 0;
+        L.out_rp = (l == NL - 1) ? (((L.out_rows + 12 + 3) & ~3) + 4) : 0;
         L.s_lo = s_lo[l];
         L.lvl = l;
         L.c_in = c[l];
@@ -586,10 +608,10 @@ int decb_launch(const DecBPlan &plan, const uint16_t *x, long long x_split, long
     const int n_items = B * p.tiles_per_seq;
     if (n_items == 0) return VP_OK;
     dim3 grid((unsigned)std::min(std::max(device_sm_count() / 3, 1), (n_items + FZ_NPIPE - 1) / FZ_NPIPE), 3);
-    if (plan.split == 2 && plan.opt == 6) return decb_launch_t<2, 6>(p, grid, s);
-    if (plan.split == 2 && plan.opt == 10) return decb_launch_t<2, 10>(p, grid, s);
-    if (plan.split == 1 && plan.opt == 6) return decb_launch_t<1, 6>(p, grid, s);
-    if (plan.split == 1 && plan.opt == 10) return decb_launch_t<1, 10>(p, grid, s);
+    if (plan.split == 2 && plan.opt == 8) return decb_launch_t<2, 8>(p, grid, s);
+    if (plan.split == 2 && plan.opt == 12) return decb_launch_t<2, 12>(p, grid, s);
+    if (plan.split == 1 && plan.opt == 8) return decb_launch_t<1, 8>(p, grid, s);
+    if (plan.split == 1 && plan.opt == 12) return decb_launch_t<1, 12>(p, grid, s);
     set_error("decb: no kernel instance for split %d, %d outputs per thread", plan.split, plan.opt);
     return VP_ERR_UNSUPPORTED;
 }

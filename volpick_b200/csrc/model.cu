@@ -521,7 +521,8 @@ static int build_eqt(vp_model *m, Cursor &cur, Packed &pk) {
             std::memcpy(head_w[g], hW[g], 88 * sizeof(float));
             head_b[g] = hB[g][0];
         }
-        int tile_m = split == 2 ? 47 : 75;
+        // rows of the 375-sample level per work item: 6 (f16x3) / 4 (bf16) items cover the 5000 kept samples of a blinded window
+        int tile_m = split == 2 ? 53 : 79;
         if (const char *e = getenv(split == 2 ? "VP_DECB_M2" : "VP_DECB_M1")) tile_m = atoi(e);  // tuning / debugging aid
         rc = decb_build(ts.decb, ts.dec, split, tile_m, head_w, head_b);
         if (rc != VP_OK) return rc;

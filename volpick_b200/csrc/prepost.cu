@@ -55,6 +55,29 @@ __device__ __forceinline__ float block_reduce_sum3(float3 &v, float *red /*[3*32
     return 0.f;
 }
 
+// Window means in double: counts with a large DC offset (1e6 counts, +-100 of signal) lose the signal's low bits in an fp32
+// sum; SeisBench 0.4 takes the mean in NumPy's float64 (int32 / float64 traces), torch's CPU mean accumulates in double.
+__device__ __forceinline__ void block_reduce_sum3d(double (&v)[3], double *red /*[3*32]*/) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[c] += __shfl_xor_sync(0xffffffffu, v[c], o);
+    }
+    __syncthreads();  // protect red[] reuse
+    if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) red[32 * c + warp] = v[c];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        double r = 0.0;
+        for (int w = 0; w < nw; ++w) r += red[32 * c + w];  // fixed order: deterministic
+        v[c] = r;
+    }
+}
+
 __device__ __forceinline__ void block_reduce_max3(float3 &v, float *red) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
 #pragma unroll
@@ -86,12 +109,13 @@ __global__ void __launch_bounds__(NT) slice_normalize_kernel(const Tin *__restri
                                                              const int64_t *__restrict__ starts, int L,
                                                              int peak_scope, int flags, float inv_tt, Taper tap,
                                                              float *__restrict__ out) {
-    __shared__ float red[96];
+    __shared__ double redd[96];
+    float *red = reinterpret_cast<float *>(redd);
     const int64_t w = blockIdx.x;
     const int64_t s = __ldg(starts + w);
     const int tid = threadIdx.x;
     float v[3][PT];
-    float3 sum = make_float3(0.f, 0.f, 0.f);
+    double sum[3] = {0.0, 0.0, 0.0};
 #pragma unroll
     for (int j = 0; j < PT; ++j) {
         const int idx = tid + j * NT;
@@ -99,13 +123,12 @@ __global__ void __launch_bounds__(NT) slice_normalize_kernel(const Tin *__restri
         v[0][j] = ok ? ld_as_float(trace + s + idx) : 0.f;
         v[1][j] = ok ? ld_as_float(trace + ch_stride + s + idx) : 0.f;
         v[2][j] = ok ? ld_as_float(trace + 2 * ch_stride + s + idx) : 0.f;
-        sum.x += v[0][j];
-        sum.y += v[1][j];
-        sum.z += v[2][j];
+        sum[0] += (double)v[0][j];
+        sum[1] += (double)v[1][j];
+        sum[2] += (double)v[2][j];
     }
-    block_reduce_sum3(sum, red);
-    const float invL = 1.0f / (float)L;
-    const float3 mean = make_float3(sum.x * invL, sum.y * invL, sum.z * invL);
+    block_reduce_sum3d(sum, redd);
+    const float3 mean = make_float3((float)(sum[0] / (double)L), (float)(sum[1] / (double)L), (float)(sum[2] / (double)L));
 #pragma unroll
     for (int j = 0; j < PT; ++j) {
         v[0][j] -= mean.x;
@@ -191,13 +214,14 @@ __global__ void __launch_bounds__(E0_NT, 2) slice_enc0_kernel(const Tin *__restr
                                                               int flags, float inv_tt, Taper tap, const __grid_constant__ Enc0W wt,
                                                               uint16_t *__restrict__ out, int64_t out_split, int out_pitch) {
     extern __shared__ __align__(16) float e0_smem[];
-    __shared__ float red[96];
+    __shared__ double redd[96];
+    float *red = reinterpret_cast<float *>(redd);
     const int XP = L + 12;  // xs[c][i + 5] = normalised sample i; zero halo on both sides
     float *xs = e0_smem;
     const int64_t w = blockIdx.x;
     const int64_t s = __ldg(starts + w);
     const int tid = threadIdx.x;
-    float3 sum = make_float3(0.f, 0.f, 0.f);
+    double sum[3] = {0.0, 0.0, 0.0};
 #pragma unroll
     for (int j = 0; j < E0_PT; ++j) {
         const int idx = tid + j * E0_NT;
@@ -205,18 +229,17 @@ __global__ void __launch_bounds__(E0_NT, 2) slice_enc0_kernel(const Tin *__restr
         const float v0 = ok ? ld_as_float(trace + s + idx) : 0.f;
         const float v1 = ok ? ld_as_float(trace + ch_stride + s + idx) : 0.f;
         const float v2 = ok ? ld_as_float(trace + 2 * ch_stride + s + idx) : 0.f;
-        sum.x += v0;
-        sum.y += v1;
-        sum.z += v2;
+        sum[0] += (double)v0;
+        sum[1] += (double)v1;
+        sum[2] += (double)v2;
         if (ok) {
             xs[idx + E0_HALO] = v0;
             xs[XP + idx + E0_HALO] = v1;
             xs[2 * XP + idx + E0_HALO] = v2;
         }
     }
-    block_reduce_sum3(sum, red);
-    const float invL = 1.0f / (float)L;
-    const float3 mean = make_float3(sum.x * invL, sum.y * invL, sum.z * invL);
+    block_reduce_sum3d(sum, redd);
+    const float3 mean = make_float3((float)(sum[0] / (double)L), (float)(sum[1] / (double)L), (float)(sum[2] / (double)L));
     float3 beta = make_float3(0.f, 0.f, 0.f);
     const float c0 = 0.5f * (float)(L - 1);
     if (flags & VP_PRE_DETREND) {  // same arithmetic as slice_normalize_kernel
