@@ -18,7 +18,7 @@ void count_launch(int n = 1);
 // Per-kernel-class CUDA-event timing (vp_kernel_timing): off by default, one branch per launch when off.
 enum KClass {
     KC_SLICE = 0, KC_SLICE_ENC0, KC_TCCONV, KC_DECA, KC_DECB, KC_CONV_F32, KC_CONVT_F32, KC_LSTM, KC_ATTN, KC_PACK,
-    KC_STACK, KC_TRIM, KC_PICK, KC_FILTER, KC_COUNT
+    KC_STACK, KC_TRIM, KC_PICK, KC_FILTER, KC_RESSTACK, KC_COUNT
 };
 extern thread_local bool g_ktimer_on;
 void ktimer_mark(int cls, cudaStream_t s, bool end);

@@ -113,6 +113,26 @@ struct ResStackP {
 };
 int resstack_launch(const ResStackP &p, int split, cudaStream_t s);
 
+// The same stack with every activation on chip (fused_res2.cu): the 16-bit operand of a tile lives in shared memory through
+// all 14 layers (each epilogue overwrites it in place), the fp32 residual stream lives in TMEM (conv2 accumulates onto it).
+struct ResStack2P {
+    const uint16_t *x;    // relu(bn1_0(x0)) as the 16-bit operand [split][NS][T][64] (written by the last encoder stage)
+    const float *xres;    // x0: fp32 residual stream [NS][T][64]
+    uint16_t *y;          // stack output as 16-bit operand [split][NS][T][64]
+    long long split16;    // elements between the hi and lo planes of x / y
+    const uint16_t *w[RS_MAX_LAYERS];  // tcconv weight blocks [ntaps * 4][split][2][64][8] of conv1 / conv2 of block l / 2
+    int ntaps[RS_MAX_LAYERS];
+    const float *par;     // device [14][3][64]: bias, scale, shift of the epilogue of layer l (see resstack2_params)
+    int NS, T, fmt16;
+};
+// Host: epilogue parameters.  b1 / b2: conv biases [7][64]; n1 / n2: folded pre-activation BatchNorm (scale, shift) [7][64].
+//   conv1 of block i: out = relu((acc + b1_i) * n2_i.scale + n2_i.shift)
+//   conv2 of block i: acc holds x0 + sum_j conv2_j (biases excluded); out = relu((acc + B_i) * n1_{i+1}.scale + n1_{i+1}.shift),
+//                     B_i = sum_{j <= i} b2_j; the last block writes acc + B_6 without the affine
+void resstack2_params(const float *const *b1, const float *const *b2, const float *const *n1s, const float *const *n1h,
+                      const float *const *n2s, const float *const *n2h, std::vector<float> &par);
+int resstack2_launch(const ResStack2P &p, int split, cudaStream_t s);
+
 // Decoder middle: decoder.convs.1 + decoder.convs.2 (fused_deca.cu).
 struct FzDecA {
     const uint16_t *x;  // [split][group][B][94][64] channel-last 16-bit (decoder.convs.0 output)

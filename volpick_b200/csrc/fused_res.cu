@@ -264,7 +264,7 @@ int resstack_launch(const ResStackP &p, int split, cudaStream_t s) {
     const size_t smem = 2 * w_bytes + RS_NST * a_bytes;
     const int n_tiles = (p.NS + 1) / 2;
     const unsigned grid = (unsigned)std::min(device_sm_count(), n_tiles);
-    KTimer kt(KC_TCCONV, s);
+    KTimer kt(KC_RESSTACK, s);
     if (split == 2) {
         if (int rc = ensure_dyn_smem((const void *)resstack_kernel<2>, smem)) return rc;
         resstack_kernel<2><<<grid, RS_THREADS, smem, s>>>(p);

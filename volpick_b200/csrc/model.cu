@@ -85,7 +85,7 @@ cudaEvent_t ktimer_event() {
     return e;
 }
 const char *const KCLASS_NAMES =
-    "slice_normalize,slice_enc0,tcconv,deca,decb,conv1d_f32,convt_f32,lstm,attention,pack_cl16,stack,nan_bounds,pick,sosfilt";
+    "slice_normalize,slice_enc0,tcconv,deca,decb,conv1d_f32,convt_f32,lstm,attention,pack_cl16,stack,nan_bounds,pick,sosfilt,resstack";
 }  // namespace
 void ktimer_mark(int cls, cudaStream_t s, bool end) {
     if (!end) {
@@ -285,6 +285,8 @@ struct vp_model {
         TcLayer lproj;             // bi_lstm_stack.members.0: input projection of both directions as a 1x1 conv (64 -> 2 x 64 gates)
         uint16_t *d_w = nullptr;
         float *d_b = nullptr;
+        std::vector<float> res_par;   // epilogue parameters of the on-chip res-CNN stack (fused_res2.cu), host copy
+        float *d_res_par = nullptr;
         bool ready = false;
         DecBPlan decb;  // fused decoder tail (fused_dec.cu)
         DecAPlan deca;  // fused decoder middle, convs.1 + convs.2 (fused_deca.cu)
@@ -359,6 +361,8 @@ static int upload_tc(vp_model::TcSet &ts) {
         L->blocks.clear();
         L->blocks.shrink_to_fit();
     }
+    VP_CUDA_CHECK(cudaMalloc(&ts.d_res_par, ts.res_par.size() * sizeof(float) + 256));
+    VP_CUDA_CHECK(cudaMemcpy(ts.d_res_par, ts.res_par.data(), ts.res_par.size() * sizeof(float), cudaMemcpyHostToDevice));
     ts.ready = true;
     return VP_OK;
 }
@@ -501,6 +505,18 @@ static int build_eqt(vp_model *m, Cursor &cur, Packed &pk) {
                 rc = tc_build_layer(j == 0 ? ts.res1[i] : ts.res2[i], TC_DIRECT, 64, 64, kResK[i], 0, split, 1, w1, b1, kResK[i] == 3 ? 1 : 0);
                 if (rc != VP_OK) return rc;
             }
+        {   // epilogue parameters of the on-chip stack: conv biases, folded pre-activation BatchNorms, cumulative conv2 biases
+            const float *b1[7], *b2[7], *n1s[7], *n1h[7], *n2s[7], *n2h[7];
+            for (int i = 0; i < 7; ++i) {
+                b1[i] = ts.res1[i].bias.data();
+                b2[i] = ts.res2[i].bias.data();
+                n1s[i] = pk.host.data() + m->res[i].n1.scale;
+                n1h[i] = pk.host.data() + m->res[i].n1.shift;
+                n2s[i] = pk.host.data() + m->res[i].n2.scale;
+                n2h[i] = pk.host.data() + m->res[i].n2.shift;
+            }
+            resstack2_params(b1, b2, n1s, n1h, n2s, n2h, ts.res_par);
+        }
         {   // BiLSTM block 0 input projection: column n = dir * 64 + unit * 4 + gate (the order lstm_kernel reads), bias b_ih + b_hh
             const LstmW &lw = m->bil[0].lstm;
             std::vector<float> wp((size_t)128 * 64), bp(128);
@@ -992,7 +1008,25 @@ static int run_eqt(Runner &r, const float *x, float *y, Arena &ar) {
         // conv2 adds the fp32 residual stream in place and writes the next block's relu(bn1(x))
         static const bool resfuse_off = getenv("VP_FUSED_RES") && atoi(getenv("VP_FUSED_RES")) == 0;  // debugging aid
         const bool fused_res = use_lproj && !resfuse_off && T + 1 <= 64;
-        if (fused_res && r.go()) {  // all 14 convs in one persistent launch (fused_res.cu)
+        static const bool res_v1 = getenv("VP_RES_V1") && atoi(getenv("VP_RES_V1")) != 0;  // A/B aid: the layer-by-layer-in-L2 variant
+        if (fused_res && !res_v1 && r.go()) {  // all 14 convs with the activations on chip (fused_res2.cu)
+            ResStack2P sp;
+            std::memset(&sp, 0, sizeof(sp));
+            sp.x = pp16[0];
+            sp.xres = xres;
+            sp.y = pp16[0];  // tiles are read completely (TMA) before their stack output is stored, and tiles do not overlap
+            sp.split16 = split16;
+            for (int i = 0; i < 7; ++i) {
+                sp.w[2 * i] = ts.d_w + ts.res1[i].w_off;
+                sp.w[2 * i + 1] = ts.d_w + ts.res2[i].w_off;
+                sp.ntaps[2 * i] = sp.ntaps[2 * i + 1] = kResK[i];
+            }
+            sp.par = ts.d_res_par;
+            sp.NS = (int)B;
+            sp.T = T;
+            sp.fmt16 = split == 2 ? 0 : 1;
+            r.rc = resstack2_launch(sp, split, r.s);
+        } else if (fused_res && r.go()) {  // all 14 convs in one persistent launch, activations through L2 (fused_res.cu)
             ResStackP sp;
             std::memset(&sp, 0, sizeof(sp));
             sp.n_layers = 14;
@@ -1776,6 +1810,7 @@ extern "C" int vp_model_destroy(vp_model *m) {
     for (int set = 0; set < 2; ++set) {
         if (m->tc[set].d_w) cudaFree(m->tc[set].d_w);
         if (m->tc[set].d_b) cudaFree(m->tc[set].d_b);
+        if (m->tc[set].d_res_par) cudaFree(m->tc[set].d_res_par);
         decb_free(m->tc[set].decb);
         deca_free(m->tc[set].deca);
         if (m->pn_tc[set].d_w) cudaFree(m->pn_tc[set].d_w);
