@@ -42,8 +42,8 @@ KCLASS_FLOP_PER_WINDOW = {
     ("phasenet", "tcconv"): 38.92e6,  # every Conv1d / ConvTranspose1d of the network runs in tcconv_kernel
 }
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture (profiles/):
-KCLASS_NCU_TRAFFIC = {("eqtransformer", "decb", "f16x3"): {"bytes_per_launch": 535.12e6 + 229.44e6, "windows_per_launch": 4096,
-                                                            "source": "profiles/r01g_f16x3_top_kernels_ncu_full.md"}}
+KCLASS_NCU_TRAFFIC = {("eqtransformer", "decb", "f16x3"): {"bytes_per_launch": 517.86e6 + 220.91e6, "windows_per_launch": 4096,
+                                                            "source": "profiles/r02_f16x3_top_kernels_ncu_full.md"}}
 CONFIGS = {
     # BASELINE.json configs[1] / configs[3]: EQTransformer, overlap 5500, blinding (500, 500), avg, P/S threshold 0.2
     "eqtransformer": dict(overlap=5500, blinding=(500, 500), stacking="avg", P_threshold=0.2, S_threshold=0.2),
@@ -334,13 +334,17 @@ def run_ours(args):
     e2e_results = list(all_results)
     ms, launches, clocks, last = timed_pipelined(recs_dev, args.steps, args.warmup, sample_clocks=True)
     # the same with one blocking vp_annotate call per record (no overlap between records)
-    ms_seq, _, _, _ = timed(step_device, args.steps, max(1, args.warmup // 2))
-    ms_e2e_seq, _, _, _ = timed(step_host, args.steps, max(1, args.warmup // 2))
+    if args.quick:
+        ms_seq = ms_e2e_seq = float("nan")
+    else:
+        ms_seq, _, _, _ = timed(step_device, args.steps, max(1, args.warmup // 2))
+        ms_e2e_seq, _, _, _ = timed(step_host, args.steps, max(1, args.warmup // 2))
 
     # ---- per-kernel-class CUDA-event timing over K more device-resident steps (events bracket every launch on the
     # launching stream inside the library; a separate pass so that the headline numbers above carry no event overhead)
     kernels = {}
-    if rank == 0:
+    kernels_step_ms = None
+    if rank == 0 and not args.quick:
         lib.vp_kernel_timing(1)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
@@ -394,7 +398,7 @@ def run_ours(args):
 
     # ---- per-stage device timings (rank 0) for the roofline objects ---------------------------
     stages = {}
-    if rank == 0:
+    if rank == 0 and not args.quick:
         stages = stage_timings(model, lib, recs_dev[0], argdict, thresholds, kind, precision=_lib.PRECISION[args.precision],
                                chunk=args.chunk)
     peaks = measured_peaks()
@@ -443,7 +447,7 @@ def run_ours(args):
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "stages": stages,
             "kernels": {"per_class": kernels, "ms_per_step_with_events": kernels_step_ms,
                         "note": "CUDA events around every launch of the class on the launching stream, K extra steps"},
-            "picks_per_record": n_trig, "gather_ms": gather_ms, "records_per_rank": R,
+            "picks_per_record": n_trig, "gather_ms": gather_ms, "records_per_rank": R, "records_total": world * args.steps,
             "gather": {"ms": gather_ms, "records": world * len(e2e_results), "triggers": int(n_gathered),
                        "e2e_value_incl_gather": world * args.steps * days / ((ms_e2e + gather_ms) / 1e3),
                        "note": "triggers of every record of the end-to-end run gathered on rank 0 (host gather_object)"},
@@ -452,7 +456,12 @@ def run_ours(args):
             line["bf16"] = bf16_report
         if classify_report:
             line["e2e_classify"] = classify_report
-        if world == 1 and not args.no_cpu_baseline:
+        if args.quick:  # long multi-GPU evidence runs: only the pipelined device-resident and end-to-end arms
+            line["quick"] = True
+            for k in ("sequential",):
+                line.pop(k, None)
+            line["e2e"].pop("sequential", None)
+        if world == 1 and not args.no_cpu_baseline and not args.quick:
             times, cw, cores, _ = oracle_station_hours_per_s(kind, 1, 1)
             v = (N_HOUR / N_DAY) * len(times) / sum(times)
             line["cpu_baseline"] = {"value": v, "unit": "station-days/s", "cores": cores, "kind": "port",
@@ -651,6 +660,9 @@ def main():
     ap.add_argument("--samples", type=int, default=N_DAY, help="samples per record (default: one station-day)")
     ap.add_argument("--chunk", type=int, default=0, help="windows per forward launch group (0: library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true",
+                    help="only the two headline arms (device-resident value, end-to-end e2e): no blocking arms, per-kernel pass, "
+                         "stage timings or CPU baseline -- for the long sharded runs of BASELINE.json configs[2] / [3]")
     ap.add_argument("--records", type=int, default=2,
                     help="distinct synthetic records per rank, cycled over the steps (long mode: >= 16)")
     ap.add_argument("--classify-stream", type=int, default=0,
