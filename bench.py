@@ -372,7 +372,7 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    merged = shard.gather_picks([(rank + world * i, trig) for i, trig in enumerate(e2e_results)], rank, world)
+    merged = shard.gather_triggers([(rank + world * i, trig) for i, trig in enumerate(e2e_results)], rank, world)
     gather_ms = 1e3 * (time.perf_counter() - t0)
     n_gathered = sum(len(t) for _, t in merged) if merged else 0
 
@@ -450,7 +450,7 @@ def run_ours(args):
             "picks_per_record": n_trig, "gather_ms": gather_ms, "records_per_rank": R, "records_total": world * args.steps,
             "gather": {"ms": gather_ms, "records": world * len(e2e_results), "triggers": int(n_gathered),
                        "e2e_value_incl_gather": world * args.steps * days / ((ms_e2e + gather_ms) / 1e3),
-                       "note": "triggers of every record of the end-to-end run gathered on rank 0 (host gather_object)"},
+                       "note": "triggers of every record of the end-to-end run gathered on rank 0 (two all_gather calls of byte tensors)"},
         }
         if bf16_report:
             line["bf16"] = bf16_report

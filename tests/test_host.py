@@ -242,3 +242,17 @@ def test_seisbench_norm_kwargs_and_int32_ingest(tmp_path):
             del _os.environ["VOLPICK_B200_CACHE"]
         else:
             _os.environ["VOLPICK_B200_CACHE"] = old
+
+
+def test_integration_doc_line_numbers(repo_root):
+    """INTEGRATION.md cites the header line of every entry point it maps a SeisBench function to: keep them exact."""
+    import os
+    import re
+
+    hdr = open(os.path.join(repo_root, "include", "volpick_b200.h")).read().splitlines()
+    doc = open(os.path.join(repo_root, "INTEGRATION.md")).read()
+    refs = re.findall(r"`(vp_\w+)`:(\d+)", doc)
+    assert len(refs) >= 15
+    for fn, line in refs:
+        decl = hdr[int(line) - 1]
+        assert decl.startswith("VP_API") and re.search(r"\b%s\(" % fn, decl), f"{fn} is not declared at include/volpick_b200.h:{line}: {decl!r}"

@@ -21,10 +21,23 @@ def _worker(rank, world, port, q):
     idx = shard.shard_indices(7, rank, world)
     local = [(i, [("P", i * 10 + k) for k in range(i % 3)]) for i in idx]  # variable-length pick lists
     merged = shard.gather_picks(local, rank, world)
+    # the tensor path used by bench.py: structured trigger arrays, variable length, one rank possibly empty-handed
+    import numpy as np
+
+    from volpick_b200 import _lib
+
+    trig_local = []
+    for i in (idx if rank == 0 else idx[:1]):
+        t = np.zeros(i % 4, dtype=_lib.TRIGGER_DTYPE)
+        t["s0"] = i * 100 + np.arange(len(t))
+        t["value"] = 0.5 + i
+        t["label"] = i % 3
+        trig_local.append((i, t))
+    merged_t = shard.gather_triggers(trig_local, rank, world)
     if rank == 0:
-        q.put(merged)
+        q.put((merged, [(i, t.tolist()) for i, t in merged_t]))
     else:
-        assert merged is None
+        assert merged is None and merged_t is None
     dist.barrier()
     dist.destroy_process_group()
 
@@ -48,11 +61,13 @@ def test_gather_picks_world2_gloo():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    merged = q.get(timeout=120)
+    merged, merged_t = q.get(timeout=120)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
     assert [i for i, _ in merged] == list(range(7))
     assert merged[5][1] == [("P", 50), ("P", 51)]
+    assert [i for i, _ in merged_t] == [0, 1, 2, 4, 6]  # rank 0 owns 0, 2, 4, 6; rank 1 sent only its first record (1)
+    assert len(merged_t[2][1]) == 2 and merged_t[2][1][1][0] == 201 and merged_t[4][1][0][3] == 6.5
     single = shard.gather_picks([(1, "b"), (0, "a")], 0, 1)
     assert single == [(0, "a"), (1, "b")]

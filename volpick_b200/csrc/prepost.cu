@@ -15,6 +15,7 @@
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
+#include "tma.cuh"
 
 namespace vp {
 
@@ -188,6 +189,165 @@ __global__ void __launch_bounds__(NT) slice_normalize_kernel(const Tin *__restri
             ob[idx] = (v[0][j] / den.x) * tp;
             ob[(int64_t)L + idx] = (v[1][j] / den.y) * tp;
             ob[2 * (int64_t)L + idx] = (v[2][j] / den.z) * tp;
+        }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------ K1, TMA-staged
+// The stand-alone slicer as a persistent kernel: a window's three components are staged in shared memory by three bulk
+// copies (cp.async.bulk, UBLKCP) issued by one thread two windows ahead, so the 72 KB of a window are in flight while the
+// CTA normalises the previous one; the normalised window leaves as 16-byte stores.  (One CTA per window with 36 scalar
+// loads per thread reached 27 % of the HBM peak: every window paid load latency -> two block reductions -> store in series.)
+// A component's window starts at an arbitrary sample: the copy starts at the 16-byte boundary below it and the samples are
+// read at the remaining offset.  Arithmetic (summation order included) = slice_normalize_kernel's: same results bit for bit.
+constexpr int K1T_NT = 512, K1T_STAGES = 2;
+
+template <typename Tin>
+__global__ void __launch_bounds__(K1T_NT, 1) slice_tma_kernel(const Tin *__restrict__ trace, int64_t ch_stride, int64_t n_alloc,
+                                                              const int64_t *__restrict__ starts, int64_t n_windows, int L, int pitch,
+                                                              int peak_scope, int flags, float inv_tt, Taper tap, float *__restrict__ out) {
+    extern __shared__ __align__(128) uint8_t k1_smem[];
+    __shared__ __align__(8) uint64_t full[K1T_STAGES], empty[K1T_STAGES];
+    __shared__ double redd[96];
+    __shared__ int s_off[K1T_STAGES][3];
+    float *red = reinterpret_cast<float *>(redd);
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int i = 0; i < K1T_STAGES; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], K1T_NT);
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();
+    const uint32_t sbase = smem_u32(k1_smem);
+    const int64_t first = blockIdx.x, step = gridDim.x;
+
+    auto issue = [&](int64_t w, int st) {  // thread 0: the three components of window w -> stage st
+        const int64_t s0 = __ldg(starts + w);
+        uint32_t bytes = 0;
+        int offs[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int64_t a = c * ch_stride + s0, a_al = a & ~(int64_t)3;
+            offs[c] = (int)(a - a_al);
+            int64_t n_el = (offs[c] + L + 3) & ~3;
+            if (a_al + n_el > n_alloc) n_el = (n_alloc - a_al) & ~(int64_t)3;  // never read past the record: the tail is loaded below
+            s_off[st][c] = offs[c] | ((int)n_el << 2);
+            bytes += (uint32_t)n_el * 4u;
+        }
+        mbar_arrive_expect_tx(&full[st], bytes);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int64_t a_al = (c * ch_stride + s0) & ~(int64_t)3;
+            const uint32_t n_el = (uint32_t)(s_off[st][c] >> 2);
+            if (n_el) bulk_load(sbase + (uint32_t)((st * 3 + c) * pitch) * 4u, trace + a_al, n_el * 4u, &full[st]);
+        }
+    };
+
+    int n = 0;
+    if (tid == 0) {
+        for (int k = 0; k < K1T_STAGES; ++k)
+            if (first + k * step < n_windows) issue(first + k * step, k);
+    }
+    for (int64_t w = first; w < n_windows; w += step, ++n) {
+        const int st = n % K1T_STAGES;
+        const uint32_t ph = (uint32_t)(n / K1T_STAGES) & 1u;
+        mbar_wait(&full[st], ph);
+        const int64_t s0 = __ldg(starts + w);
+        const Tin *xs[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int so = s_off[st][c];
+            const int off = so & 3, n_el = so >> 2;
+            Tin *base = reinterpret_cast<Tin *>(k1_smem) + (size_t)(st * 3 + c) * pitch;
+            // samples the bulk copy could not bring without reading past the record end (last window of the last component only)
+            for (int i = n_el - off + tid; i < L; i += K1T_NT)
+                if (i >= 0) base[off + i] = __ldg(trace + c * ch_stride + s0 + i);
+            xs[c] = base + off;
+        }
+        __syncthreads();
+        double sum[3] = {0.0, 0.0, 0.0};
+        constexpr int PT = 12;  // the per-thread sample order of slice_normalize_kernel<Tin, 12, 512>
+        float v[3][PT];
+#pragma unroll
+        for (int j = 0; j < PT; ++j) {
+            const int idx = tid + j * K1T_NT;
+            const bool ok = idx < L;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                v[c][j] = ok ? (float)xs[c][idx] : 0.f;
+                sum[c] += (double)v[c][j];
+            }
+        }
+        // the stage is free as soon as every thread has its samples in registers: release it and refill it two windows ahead
+        mbar_arrive(&empty[st]);
+        if (tid == 0 && w + K1T_STAGES * step < n_windows) {
+            mbar_wait(&empty[st], ph);
+            issue(w + K1T_STAGES * step, st);
+        }
+        block_reduce_sum3d(sum, redd);
+        const float3 mean = make_float3((float)(sum[0] / (double)L), (float)(sum[1] / (double)L), (float)(sum[2] / (double)L));
+#pragma unroll
+        for (int j = 0; j < PT; ++j) {
+            v[0][j] -= mean.x;
+            v[1][j] -= mean.y;
+            v[2][j] -= mean.z;
+        }
+        if (flags & VP_PRE_DETREND) {
+            const float c0 = 0.5f * (float)(L - 1);
+            double sx = 0.0, sy = 0.0, sz = 0.0;
+#pragma unroll
+            for (int j = 0; j < PT; ++j) {
+                const int idx = tid + j * K1T_NT;
+                if (idx < L) {
+                    const double t = (double)((float)idx - c0);
+                    sx += t * (double)v[0][j];
+                    sy += t * (double)v[1][j];
+                    sz += t * (double)v[2][j];
+                }
+            }
+            float3 stt = make_float3((float)sx, (float)sy, (float)sz);
+            block_reduce_sum3(stt, red);
+            const float3 beta = make_float3(stt.x * inv_tt, stt.y * inv_tt, stt.z * inv_tt);
+#pragma unroll
+            for (int j = 0; j < PT; ++j) {
+                const float t = (float)(tid + j * K1T_NT) - c0;
+                v[0][j] -= beta.x * t;
+                v[1][j] -= beta.y * t;
+                v[2][j] -= beta.z * t;
+            }
+        }
+        float3 pk = make_float3(0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < PT; ++j) {
+            if (tid + j * K1T_NT < L) {
+                pk.x = fmaxf(pk.x, fabsf(v[0][j]));
+                pk.y = fmaxf(pk.y, fabsf(v[1][j]));
+                pk.z = fmaxf(pk.z, fabsf(v[2][j]));
+            }
+        }
+        block_reduce_max3(pk, red);
+        if (peak_scope == VP_PEAK_PER_WINDOW) {
+            const float m = fmaxf(pk.x, fmaxf(pk.y, pk.z));
+            pk = make_float3(m, m, m);
+        }
+        const float3 den = make_float3(pk.x + 1e-10f, pk.y + 1e-10f, pk.z + 1e-10f);
+        float *ob = out + w * 3 * (int64_t)L;
+#pragma unroll
+        for (int j = 0; j < PT; ++j) {
+            const int idx = tid + j * K1T_NT;
+            if (idx < L) {
+                float tp = 1.f;
+                if (flags & VP_PRE_TAPER) {
+                    if (idx < 6) tp = tap.t[idx];
+                    if (idx >= L - 6) tp = tap.t[L - 1 - idx];
+                }
+                ob[idx] = (v[0][j] / den.x) * tp;
+                ob[(int64_t)L + idx] = (v[1][j] / den.y) * tp;
+                ob[2 * (int64_t)L + idx] = (v[2][j] / den.z) * tp;
+            }
         }
     }
 }
@@ -406,7 +566,7 @@ int launch_slice_enc0(const void *trace, int dtype, int64_t ch_stride, const int
 }
 
 template <typename Tin>
-static int launch_slice(const Tin *trace, int64_t ch_stride, const int64_t *starts, int64_t nw, int L, int scope,
+static int launch_slice(const Tin *trace, int64_t ch_stride, int64_t n_alloc, const int64_t *starts, int64_t nw, int L, int scope,
                         int taper, float *out, cudaStream_t s) {
     Taper tap;
     for (int i = 0; i < 6; ++i) {  // 0.5 * (1 + cos(linspace(pi, 2 pi, 6))) in double, rounded once
@@ -415,6 +575,18 @@ static int launch_slice(const Tin *trace, int64_t ch_stride, const int64_t *star
     }
     const float inv_tt = detrend_inv_tt(L);
     KTimer kt(KC_SLICE, s);
+    static const bool tma_off = getenv("VP_K1_TMA") && atoi(getenv("VP_K1_TMA")) == 0;  // A/B aid
+    if (!tma_off && L > 4096 && L <= 12 * K1T_NT && (reinterpret_cast<uintptr_t>(trace) & 15) == 0) {  // shorter windows: the one-CTA-per-window kernel below is faster (PhaseNet: 0.13 vs 0.19 ms)
+        // persistent TMA-staged slicer: 2 stages x 3 components x (L + 8) samples of shared memory, one CTA per SM
+        const int pitch = (L + 3 + 3 + 4) & ~3;
+        const size_t smem = (size_t)K1T_STAGES * 3 * pitch * 4;
+        auto kern = slice_tma_kernel<Tin>;
+        if (int rc = ensure_dyn_smem((const void *)kern, smem)) return rc;
+        const unsigned grid = (unsigned)std::min<int64_t>(nw, device_sm_count());
+        kern<<<grid, K1T_NT, smem, s>>>(trace, ch_stride, n_alloc, starts, nw, L, pitch, scope, taper, inv_tt, tap, out);
+        VP_LAUNCH_CHECK();
+        return VP_OK;
+    }
     if (L <= 6 * 512) {
         slice_normalize_kernel<Tin, 6, 512><<<(unsigned)nw, 512, 0, s>>>(trace, ch_stride, starts, L, scope, taper, inv_tt, tap, out);
     } else if (L <= 12 * 512) {
@@ -951,11 +1123,11 @@ extern "C" int vp_slice_normalize(const void *trace, int dtype, int64_t n_sample
     if (n_windows == 0) return VP_OK;
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == VP_DTYPE_F32)
-        return launch_slice<float>((const float *)trace, ch_stride, starts, n_windows, (int)in_samples, peak_scope,
-                                   taper, out, s);
+        return launch_slice<float>((const float *)trace, ch_stride, 2 * ch_stride + n_samples, starts, n_windows, (int)in_samples,
+                                   peak_scope, taper, out, s);
     if (dtype == VP_DTYPE_I32)
-        return launch_slice<int32_t>((const int32_t *)trace, ch_stride, starts, n_windows, (int)in_samples,
-                                     peak_scope, taper, out, s);
+        return launch_slice<int32_t>((const int32_t *)trace, ch_stride, 2 * ch_stride + n_samples, starts, n_windows,
+                                     (int)in_samples, peak_scope, taper, out, s);
     set_error("vp_slice_normalize: unknown dtype %d", dtype);
     return VP_ERR_ARG;
 }
