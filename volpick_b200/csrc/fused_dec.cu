@@ -17,6 +17,12 @@
 // f16x3 mode the layers with N <= 32 stack W_hi and W_lo along N (two A-tile reads per K step instead of three)
 // and the epilogue adds the two column halves, the bias and the ReLU before the 16-bit split + store.
 //
+// Ordering between the generic-proxy actors (layer-epilogue warps, head warps) goes through mbarriers (acc_full / done_bar carry
+// the tensor core's completions, head_go / head_done the hand-over of buffer X).  compute-sanitizer's racecheck only models
+// bar.sync, so -DVP_RACECHECK_BARRIERS adds a named barrier at each of those program points (same positions, same participants:
+// the 4 epilogue warps of a pipeline per step; epilogue + head warps at the two hand-overs): that build is racecheck-clean,
+// which shows that synchronisation AT THESE POINTS orders every shared-memory access pair (profiles/r02_sanitizer.md).
+//
 // A CTA runs FZ_NPIPE independent pipelines over alternating work items (the layer chain of one item is a
 // dependency chain: while one pipeline's epilogue converts a tile, the other pipeline's MMAs own the tensor
 // pipe).  Per pipeline: one cp.async loader warp (next item's input rows, double buffered), one tcgen05
@@ -29,6 +35,7 @@
 
 #include "fused.cuh"
 #include "tc_ptx.cuh"
+#include "tma.cuh"
 
 namespace vp {
 
@@ -247,8 +254,14 @@ __device__ __forceinline__ void fz_issue_layer(const FzDecB &p, int pp, int slot
 }
 
 // ------------------------------------------------------------------------------------------ the kernel
+struct FzDecBK {
+    alignas(64) CUtensorMap x_map;  // (8 channels, t, group * B + window, 8-channel plane, split) over the 375-sample level input
+    FzDecB p;
+};
+
 template <int SPLIT, int OPT>
-__global__ void __launch_bounds__(FZ_THREADS, 1) decb_kernel(const __grid_constant__ FzDecB p) {
+__global__ void __launch_bounds__(FZ_THREADS, 1) decb_kernel(const __grid_constant__ FzDecBK K) {
+    const FzDecB &p = K.p;
     extern __shared__ __align__(128) uint8_t fz_smem[];
     __shared__ __align__(8) uint64_t in_full[FZ_NPIPE][FZ_NSLOT], in_empty[FZ_NPIPE][FZ_NSLOT], acc_full[FZ_NPIPE][FZ_NBUF],
         done_bar[FZ_NPIPE][FZ_NBUF], head_go[FZ_NPIPE], head_done[FZ_NPIPE];
@@ -262,7 +275,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) decb_kernel(const __grid_consta
     if (tid == 0) {
         for (int pp = 0; pp < FZ_NPIPE; ++pp) {
             for (int i = 0; i < FZ_NSLOT; ++i) {
-                mbar_init(&in_full[pp][i], 32);
+                mbar_init(&in_full[pp][i], 1);
                 mbar_init(&in_empty[pp][i], 1);
             }
             for (int i = 0; i < FZ_NBUF; ++i) {
@@ -287,32 +300,23 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) decb_kernel(const __grid_consta
     const uint32_t tmem_base = tmem_base_s;
 
     if (warp < FZ_NPIPE) {
-        // ================= loaders: input rows of the pipeline's next work item (zero rows outside the sequence)
+        // ================= loaders: the input rows of the pipeline's next work item as ONE TMA box
+        // [8 channels][in_rows][1 sequence][cin / 8 planes][split] -> [split][plane][row][16 B]; rows outside the sequence lie outside
+        // the tensor map and arrive as zeros (the conv's padding).  Round 1 copied them as 16-byte cp.async pieces.
         const int pp = warp;
-        const int R0 = p.L[0].in_rows, PT = p.L[0].in_pitch, c8 = p.L[0].cin8;
-        const int per_split = R0 * c8;
-        const uint16_t *xg = p.x + (long long)g * p.x_gs;
-        int n = 0;
-        for (int item = blockIdx.x + pp * gridDim.x; item < n_items; item += FZ_NPIPE * gridDim.x, ++n) {
-            const int slot = n % FZ_NSLOT;
-            mbar_wait(&in_empty[pp][slot], ((n / FZ_NSLOT) & 1) ^ 1);
-            const int b = item / p.tiles_per_seq, j = item - b * p.tiles_per_seq;
-            const int row_base = p.c0 * j + p.row_off0 + p.in_lo0;
-            const uint32_t dst0 = sbase + pp * p.pipe_stride + p.L[0].in_off + slot * p.in_slot_bytes;
-            // consecutive lanes copy the planes of one 64-byte global row, then the next row (coalesced); the plane pitch PT
-            // is 2 (mod 4) rows, so 8 lanes (4 planes x 2 rows) store to 8 different 16-byte bank groups
-            for (int idx = lane; idx < ((p.dbg & 8) ? 0 : per_split); idx += 32) {
-                const int pl = idx % c8, r = idx / c8;
-                const int gr = row_base + r;
-                const bool ok = (unsigned)gr < (unsigned)p.T0;
-                const uint16_t *src = ok ? xg + ((long long)b * p.T0 + gr) * p.cin0 + pl * 8 : xg;
-#pragma unroll
-                for (int s = 0; s < SPLIT; ++s)
-                    cp_async16(dst0 + (uint32_t)(((s * c8 + pl) * PT + r) * 16), ok ? src + (long long)s * p.x_split : xg, ok ? 16u : 0u);
+        if (lane == 0 && !(p.dbg & 8)) {
+            const uint32_t bytes = (uint32_t)(p.L[0].in_rows * p.L[0].cin8 * 16 * SPLIT);
+            int n = 0;
+            for (int item = blockIdx.x + pp * gridDim.x; item < n_items; item += FZ_NPIPE * gridDim.x, ++n) {
+                const int slot = n % FZ_NSLOT;
+                mbar_wait(&in_empty[pp][slot], ((n / FZ_NSLOT) & 1) ^ 1);
+                const int b = item / p.tiles_per_seq, j = item - b * p.tiles_per_seq;
+                const int row_base = p.c0 * j + p.row_off0 + p.in_lo0;
+                const uint32_t dst0 = sbase + pp * p.pipe_stride + p.L[0].in_off + slot * p.in_slot_bytes;
+                mbar_arrive_expect_tx(&in_full[pp][slot], bytes);
+                tma_load_5d(dst0, &K.x_map, &in_full[pp][slot], 0, row_base, g * p.B + b, 0, 0);
             }
-            cp_async_mbar_arrive_noinc(&in_full[pp][slot]);
         }
-        cp_async_wait_all();
     } else if (warp < 2 * FZ_NPIPE) {
         // ================= tcgen05 issuers =================
         const int pp = warp - FZ_NPIPE;
@@ -341,11 +345,19 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) decb_kernel(const __grid_consta
             for (int l = 0; l < p.n_layers; ++l) {
                 const FzLayer &L = p.L[l];
                 // layer 1 is the first writer of buffer X, which the head warps may still be reading (previous item)
-                if (l == p.head_wait_layer && n > 0) mbar_wait(&head_done[pp], (n - 1) & 1);
+                if (l == p.head_wait_layer && n > 0) {
+                    mbar_wait(&head_done[pp], (n - 1) & 1);
+#ifdef VP_RACECHECK_BARRIERS
+                    named_bar_sync(4 + pp, 256);
+#endif
+                }
                 for (int t = 0; t < L.n_tiles; ++t, ++i) {
                     const uint32_t buf = i & (FZ_NBUF - 1);
                     mbar_wait(&acc_full[pp][buf], (i / FZ_NBUF) & 1);
                     tc_fence_after();
+#ifdef VP_RACECHECK_BARRIERS  // debug build for compute-sanitizer racecheck (it models bar.sync, not mbarriers): see the kernel comment
+                    named_bar_sync(6 + pp, 128);
+#endif
                     const uint32_t tacc = tmem_base + (pp * FZ_NBUF + buf) * FZ_NCOLS + ((uint32_t)(q * 32) << 16);
                     constexpr bool ST = SPLIT == 2;  // stacked layers: FZ_DEC_STACK (layers 1-3)
                     const float *bias = reinterpret_cast<const float *>(fz_smem + p.bias_off) + l * FZ_NCOLS;
@@ -364,6 +376,9 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) decb_kernel(const __grid_consta
                 }
             }
             if (lane == 0) mbar_arrive(&head_go[pp]);  // the last layer's rows of this warp are in shared memory
+#ifdef VP_RACECHECK_BARRIERS
+            named_bar_sync(2 + pp, 256);
+#endif
         }
     } else {
         // ================= head warps: sigmoid(conv k11) of the previous item while the pipeline runs the next one
@@ -376,9 +391,15 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) decb_kernel(const __grid_consta
             const int b = item / p.tiles_per_seq, j = item - b * p.tiles_per_seq;
             const int R0 = p.c0 * j + p.row_off0;
             mbar_wait(&head_go[pp], n & 1);
+#ifdef VP_RACECHECK_BARRIERS
+            named_bar_sync(2 + pp, 256);
+#endif
             if (!(p.dbg & 4)) fz_head<OPT>(p, hw, g, b, R0, e, arena);
             __syncwarp();
             if (lane == 0) mbar_arrive(&head_done[pp]);
+#ifdef VP_RACECHECK_BARRIERS
+            if (item + FZ_NPIPE * (int)gridDim.x < n_items) named_bar_sync(4 + pp, 256);  // pairs with the next item's layer-1 wait
+#endif
         }
     }
     tc_fence_before();
@@ -427,13 +448,8 @@ int decb_build(DecBPlan &plan, const TcLayer *dec, int split, int m, const float
     static_assert(FZ_DEC_STACK[1] == FZ_DEC_STACK[2] && !FZ_DEC_STACK[0], "epilogue dispatch in decb_kernel");
     // shared memory: per pipeline { in[2] | X | Y }, then the weight blob
     const int esz = 16 * split;  // bytes per (row, plane)
-    // input slot: plane pitch 2 (mod 4) rows for the 4-plane (32-channel) input, odd for 8 planes (see the loader)
-    int pitch0 = hi[0] - lo[0];
-    {
-        const int c8 = dec[3].cin / 8;
-        if (c8 == 4) while ((pitch0 & 3) != 2) ++pitch0;
-        else if (c8 >= 8) pitch0 |= 1;
-    }
+    // input slot: filled by one TMA box, plane pitch = rows of the box
+    const int pitch0 = hi[0] - lo[0];
     auto lvl_bytes = [&](int k) {
         if (k == NL) return (size_t)8 * (size_t)((((hi[k] - lo[k]) + 12 + 3) & ~3) + 4) * 4;  // + one unit: the swizzle swaps unit pairs
         const int ch = (k == 0) ? dec[3].cin : dec[3 + k - 1].cout;
@@ -577,9 +593,21 @@ void decb_free(DecBPlan &plan) {
 template <int SPLIT, int OPT>
 static int decb_launch_t(const FzDecB &p, dim3 grid, cudaStream_t s) {
     auto kern = decb_kernel<SPLIT, OPT>;
+    FzDecBK K;
+    K.p = p;
+    {
+        const int c8 = p.L[0].cin8;
+        VP_REQUIRE(p.x_gs == (long long)p.B * p.T0 * p.cin0 && (p.x_split * 2) % 16 == 0 && reinterpret_cast<uintptr_t>(p.x) % 16 == 0 &&
+                       p.L[0].in_rows <= 256 && p.L[0].in_pitch == p.L[0].in_rows,
+                   VP_ERR_ARG, "decb: the input groups must be contiguous ([split][group][B][375][32]) and 16-byte aligned");
+        const uint64_t dims[5] = {8, (uint64_t)p.T0, (uint64_t)3 * p.B, (uint64_t)c8, (uint64_t)SPLIT};
+        const uint64_t strides[4] = {(uint64_t)p.cin0 * 2, (uint64_t)p.T0 * p.cin0 * 2, 16, (uint64_t)p.x_split * 2};
+        const uint32_t box[5] = {8, (uint32_t)p.L[0].in_rows, 1, (uint32_t)c8, (uint32_t)SPLIT};
+        if (int rc = tma_encode_u16(&K.x_map, p.x, 5, dims, strides, box)) return rc;
+    }
     if (int rc = ensure_dyn_smem((const void *)kern, (size_t)p.smem_bytes)) return rc;
     KTimer kt(KC_DECB, s);
-    kern<<<grid, FZ_THREADS, p.smem_bytes, s>>>(p);
+    kern<<<grid, FZ_THREADS, p.smem_bytes, s>>>(K);
     VP_LAUNCH_CHECK();
     return VP_OK;
 }

@@ -22,15 +22,23 @@
 
 #include "fused.cuh"
 #include "tc_ptx.cuh"
+#include "tma.cuh"
 
 namespace vp {
 
 constexpr int DA_T0 = 94, DA_T1 = 188, DA_T2 = 375;
 constexpr int DA_IN_ROWS = DA_T0 + 2, DA_MID_ROWS = DA_T1 + 2;  // one zero row before and after the sequence
-// plane pitch of the input slot in 16-byte rows, ODD: the loader's 8 lanes that copy the 8 planes of one 128-byte global
-// row then hit 8 different 16-byte bank groups (with the even pitch 96 the cp.async stores serialised 8 ways: ncu counted
-// 26 shared-memory wavefronts per LDGSTS instead of 4)
-constexpr int DA_IN_PITCH = DA_IN_ROWS + 1;
+// Plane pitch of the input slot in 16-byte rows.  The slot is filled by ONE TMA box per item (round 2): the 5-D tensor map of
+// the channel-last input, box [8 channels][96 rows from t = -1][1 sequence][8 planes][split], lands as [split][plane][96 rows][16 B]
+// -- the UMMA layout -- and the two rows outside the sequence (t = -1, 94) arrive as zeros: they are the conv's padding.  (Round 1
+// copied 1,504 16-byte cp.async pieces per item, ~1,500 shared-memory wavefronts against 192 for the box; the odd pitch 97 that
+// kept those stores conflict-free is no longer needed.)
+constexpr int DA_IN_PITCH = DA_IN_ROWS;
+
+struct FzDecAK {
+    alignas(64) CUtensorMap x_map;  // (8 channels, t, group * B + window, 8-channel plane, split) over p.x
+    FzDecA p;
+};
 constexpr int DA_EW = 16;
 constexpr int DA_THREADS = 32 * (2 + DA_EW);
 
@@ -40,7 +48,8 @@ __device__ __forceinline__ void da_pack8(const float *v, uint4 &hi, uint4 &lo) {
 }
 
 template <int SPLIT>
-__global__ void __launch_bounds__(DA_THREADS, 1) deca_kernel(const __grid_constant__ FzDecA p) {
+__global__ void __launch_bounds__(DA_THREADS, 1) deca_kernel(const __grid_constant__ FzDecAK K) {
+    const FzDecA &p = K.p;
     extern __shared__ __align__(128) uint8_t da_smem[];
     __shared__ __align__(8) uint64_t in_full, in_free, acc_full[3], done_bar[3];
     __shared__ uint32_t tmem_base_s;
@@ -50,11 +59,12 @@ __global__ void __launch_bounds__(DA_THREADS, 1) deca_kernel(const __grid_consta
     const int g = blockIdx.y;
     const uint32_t sbase = smem_u32(da_smem);
     constexpr uint32_t IN_BYTES = SPLIT * 8 * DA_IN_PITCH * 16, MID_BYTES = SPLIT * 8 * DA_MID_ROWS * 16;
-    uint8_t *s_in = da_smem, *s_mid = da_smem + IN_BYTES;
+    uint8_t *s_mid = da_smem + IN_BYTES;  // the input slot [0, IN_BYTES) is written by TMA only
     const float *s_bias = reinterpret_cast<const float *>(da_smem + p.bias_off);  // [128] dec1, [64] dec2
 
     if (tid == 0) {
-        mbar_init(&in_full, 32);
+        mbar_init(&in_full, 1);
+        tma_prefetch_desc(&K.x_map);
         mbar_init(&in_free, 1);
         for (int i = 0; i < 3; ++i) {
             mbar_init(&acc_full[i], 1);
@@ -69,7 +79,6 @@ __global__ void __launch_bounds__(DA_THREADS, 1) deca_kernel(const __grid_consta
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
         for (int idx = tid; idx < SPLIT * 8 * 2; idx += DA_THREADS) {
             const int pl = idx >> 1, e = idx & 1;
-            *reinterpret_cast<uint4 *>(s_in + ((size_t)pl * DA_IN_PITCH + (e ? DA_IN_ROWS - 1 : 0)) * 16) = z;
             *reinterpret_cast<uint4 *>(s_mid + ((size_t)pl * DA_MID_ROWS + (e ? DA_MID_ROWS - 1 : 0)) * 16) = z;
         }
     }
@@ -82,21 +91,15 @@ __global__ void __launch_bounds__(DA_THREADS, 1) deca_kernel(const __grid_consta
     const int n_items = p.B;
 
     if (warp == 0) {
-        // ================= loader: rows 1 .. 94 of the input planes =================
-        const uint16_t *xg = p.x + (long long)g * p.x_gs;
-        int n = 0;
-        for (int b = blockIdx.x; b < n_items; b += gridDim.x, ++n) {
-            mbar_wait(&in_free, (n & 1) ^ 1);
-            const uint16_t *src0 = xg + (long long)b * DA_T0 * 64;
-            for (int idx = lane; idx < DA_T0 * 8; idx += 32) {
-                const int pl = idx & 7, t = idx >> 3;
-#pragma unroll
-                for (int s = 0; s < SPLIT; ++s)
-                    cp_async16(sbase + (uint32_t)(((s * 8 + pl) * DA_IN_PITCH + 1 + t) * 16), src0 + (long long)s * p.x_split + t * 64 + pl * 8, 16u);
+        // ================= loader: one TMA box per item (rows -1 .. 94 of all planes and splits) =================
+        if (lane == 0) {
+            int n = 0;
+            for (int b = blockIdx.x; b < n_items; b += gridDim.x, ++n) {
+                mbar_wait(&in_free, (n & 1) ^ 1);
+                mbar_arrive_expect_tx(&in_full, IN_BYTES);
+                tma_load_5d(sbase, &K.x_map, &in_full, 0, -1, g * n_items + b, 0, 0);
             }
-            cp_async_mbar_arrive_noinc(&in_full);
         }
-        cp_async_wait_all();
     } else if (warp == 1) {
         // ================= tcgen05 issuer =================
         const uint32_t fmt = SPLIT == 2 ? 0 : 1;
@@ -320,9 +323,19 @@ void deca_free(DecAPlan &plan) {
 template <int SPLIT>
 static int deca_launch_t(const FzDecA &p, dim3 grid, cudaStream_t s) {
     auto kern = deca_kernel<SPLIT>;
+    FzDecAK K;
+    K.p = p;
+    {
+        VP_REQUIRE(p.x_gs == (long long)p.B * DA_T0 * 64 && (p.x_split * 2) % 16 == 0 && reinterpret_cast<uintptr_t>(p.x) % 16 == 0,
+                   VP_ERR_ARG, "deca: the input groups must be contiguous ([split][group][B][94][64]) and 16-byte aligned");
+        const uint64_t dims[5] = {8, (uint64_t)DA_T0, (uint64_t)3 * p.B, 8, (uint64_t)SPLIT};
+        const uint64_t strides[4] = {128, (uint64_t)DA_T0 * 128, 16, (uint64_t)p.x_split * 2};
+        const uint32_t box[5] = {8, (uint32_t)DA_IN_ROWS, 1, 8, (uint32_t)SPLIT};
+        if (int rc = tma_encode_u16(&K.x_map, p.x, 5, dims, strides, box)) return rc;
+    }
     if (int rc = ensure_dyn_smem((const void *)kern, (size_t)p.smem_bytes)) return rc;
     KTimer kt(KC_DECA, s);
-    kern<<<grid, DA_THREADS, p.smem_bytes, s>>>(p);
+    kern<<<grid, DA_THREADS, p.smem_bytes, s>>>(K);
     VP_LAUNCH_CHECK();
     return VP_OK;
 }
