@@ -10,6 +10,13 @@ overlap=5500 (17,269 windows), blinding=(500,500), stacking="avg", P/S threshold
 ``value`` = station-days/s over all ranks with the record resident in HBM; ``e2e`` = the same through
 the host-buffer entry point (pinned host record -> vp_annotate -> picks on the host).
 Prints ONE JSON line on rank 0.
+
+Other BASELINE.json configurations (bench lines of every one are tracked under profiles/):
+    --model phasenet [--samples 360000]        configs[0] / the unit of configs[2] (JSON thresholds, overlap 1500)
+    --precision bf16                            bf16 mode of configs[3]; the line carries the +-1-sample pick-match rate
+    --records 16 --steps 1000/N --quick         configs[2] / [3]: 1000 station-days sharded over N GPUs (tools/gpu_r02_scale.sh)
+    --sweep                                     configs[4]: raw forward sweep B = 256 ... 8192, per-kernel-class times
+    --classify-stream K                         the drop-in call itself: picker.classify(stream) on K station-days (``e2e_classify``)
 """
 from __future__ import annotations
 

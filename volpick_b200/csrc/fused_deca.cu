@@ -72,7 +72,8 @@ __global__ void __launch_bounds__(DA_THREADS, 1) deca_kernel(const __grid_consta
         }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(&tmem_base_s, 256);
+    // accumulators: convs.1 at column 0 (128 columns, + 128 for the stacked W_lo half in f16x3), convs.2 tile t at 256 + 128 t (64 + 64)
+    if (warp == 1) tmem_alloc(&tmem_base_s, 512);
     {   // resident weights + biases; zero rows around the sequences (never written again)
         const uint4 *wg = reinterpret_cast<const uint4 *>(p.blob + (long long)g * (p.blob_bytes / 2));
         for (int idx = tid; idx < p.blob_bytes / 16; idx += DA_THREADS) cp_async16(sbase + p.blob_off + idx * 16, wg + idx, 16u);
@@ -114,7 +115,10 @@ __global__ void __launch_bounds__(DA_THREADS, 1) deca_kernel(const __grid_consta
             fence_proxy_async();
             tc_fence_after();
             if (elect_one()) {
-                umma_conv_tile<128, SPLIT, 3, 4>(tmem_base, in16, DA_IN_PITCH, w1, umma_idesc(128, fmt), 0u);
+                // f16x3: W_hi and W_lo stacked along N (A_hi is read once for A_hi W_hi and A_hi W_lo: two instead of three 4 KB
+                // A-tile reads per K step; the shared-memory operand reads bound this kernel), the epilogue adds the two halves
+                if constexpr (SPLIT == 2) umma_conv_tile_stacked<128, 3, 4>(tmem_base, in16, DA_IN_PITCH, w1, umma_idesc(256, 0), umma_idesc(128, 0), 0u);
+                else umma_conv_tile<128, SPLIT, 3, 4>(tmem_base, in16, DA_IN_PITCH, w1, umma_idesc(128, fmt), 0u);
                 umma_commit(&acc_full[0]);
                 umma_commit(&in_free);
             }
@@ -128,7 +132,9 @@ __global__ void __launch_bounds__(DA_THREADS, 1) deca_kernel(const __grid_consta
                 mbar_wait(&done_bar[1 + t], par ^ 1);
                 tc_fence_after();
                 if (elect_one()) {
-                    umma_conv_tile<64, SPLIT, 3, 4>(tmem_base + 128u + 64u * t, mid16 + 128u * t, DA_MID_ROWS, w2, umma_idesc(64, fmt), 0u);
+                    if constexpr (SPLIT == 2)
+                        umma_conv_tile_stacked<64, 3, 4>(tmem_base + 256u + 128u * t, mid16 + 128u * t, DA_MID_ROWS, w2, umma_idesc(128, 0), umma_idesc(64, 0), 0u);
+                    else umma_conv_tile<64, SPLIT, 3, 4>(tmem_base + 256u + 128u * t, mid16 + 128u * t, DA_MID_ROWS, w2, umma_idesc(64, fmt), 0u);
                     umma_commit(&acc_full[1 + t]);
                 }
                 __syncwarp();
@@ -155,6 +161,17 @@ __global__ void __launch_bounds__(DA_THREADS, 1) deca_kernel(const __grid_consta
                 tmem_ld16_nowait(tacc + (uint32_t)(16 * cs), r0);
                 tmem_ld16_nowait(tacc + (uint32_t)(64 + 16 * cs), r1);
                 tmem_ld_wait();
+                if constexpr (SPLIT == 2) {  // + the stacked half A_hi W_lo
+                    uint32_t q0[16], q1[16];
+                    tmem_ld16_nowait(tacc + (uint32_t)(128 + 16 * cs), q0);
+                    tmem_ld16_nowait(tacc + (uint32_t)(192 + 16 * cs), q1);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        r0[i] = __float_as_uint(__uint_as_float(r0[i]) + __uint_as_float(q0[i]));
+                        r1[i] = __float_as_uint(__uint_as_float(r1[i]) + __uint_as_float(q1[i]));
+                    }
+                }
                 if (r < DA_T0) {
                     float v0[16], v1[16];
 #pragma unroll
@@ -227,10 +244,18 @@ __global__ void __launch_bounds__(DA_THREADS, 1) deca_kernel(const __grid_consta
                 tc_fence_after();
                 const int s = 128 * t + r;
                 if (t == 0 || lq < 2) {  // rows 192 .. 255 do not exist
-                    const uint32_t tacc = tmem_base + 128u + 64u * t + ((uint32_t)(lq * 32) << 16);
+                    const uint32_t tacc = tmem_base + 256u + 128u * t + ((uint32_t)(lq * 32) << 16);
                     uint32_t r0[16];
                     tmem_ld16_nowait(tacc + (uint32_t)(32 * ph + 16 * hc), r0);
-                    tmem_ld_wait();
+                    if constexpr (SPLIT == 2) {
+                        uint32_t q0[16];
+                        tmem_ld16_nowait(tacc + (uint32_t)(64 + 32 * ph + 16 * hc), q0);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) r0[i] = __float_as_uint(__uint_as_float(r0[i]) + __uint_as_float(q0[i]));
+                    } else {
+                        tmem_ld_wait();
+                    }
                     if (s < DA_T1 && 2 * s + ph < DA_T2) {
                         float v[16];
 #pragma unroll
@@ -256,7 +281,7 @@ __global__ void __launch_bounds__(DA_THREADS, 1) deca_kernel(const __grid_consta
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 256);
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------ host
@@ -287,8 +312,22 @@ int deca_build(DecAPlan &plan, const TcLayer &dec1, const TcLayer &dec2p, int sp
     const size_t e1 = (size_t)dec1.n_blocks * split * 2 * 128 * 8, e2 = (size_t)dec2p.n_blocks * split * 2 * 64 * 8;
     for (int g = 0; g < G; ++g) {
         uint16_t *dst = plan.blob.data() + (size_t)g * p.blob_bytes / 2;
-        std::memcpy(dst, dec1.blocks.data() + (size_t)g * e1, e1 * sizeof(uint16_t));
-        std::memcpy(dst + w1_bytes / 2, dec2p.blocks.data() + (size_t)g * e2, e2 * sizeof(uint16_t));
+        // TcLayer blocks: [block][split][k-half][nout][8]; the stacked f16x3 schedule wants [block][k-half][split * nout + n][8]
+        auto put = [&](uint16_t *d, const TcLayer &TL, size_t elems) {
+            const uint16_t *src = TL.blocks.data() + (size_t)g * elems;
+            if (split != 2) {
+                std::memcpy(d, src, elems * sizeof(uint16_t));
+                return;
+            }
+            const size_t blk = (size_t)2 * 2 * TL.nout * 8;
+            for (int b = 0; b < TL.n_blocks; ++b)
+                for (int sp = 0; sp < 2; ++sp)
+                    for (int kh = 0; kh < 2; ++kh)
+                        std::memcpy(d + (size_t)b * blk + ((size_t)kh * 2 * TL.nout + (size_t)sp * TL.nout) * 8,
+                                    src + (size_t)b * blk + ((size_t)sp * 2 + kh) * TL.nout * 8, (size_t)TL.nout * 8 * sizeof(uint16_t));
+        };
+        put(dst, dec1, e1);
+        put(dst + w1_bytes / 2, dec2p, e2);
         float *bd = reinterpret_cast<float *>(dst + (w1_bytes + w2_bytes) / 2);
         for (int n = 0; n < 128; ++n) bd[n] = dec1.bias[(size_t)g * 128 + n];
         for (int n = 0; n < 64; ++n) bd[128 + n] = dec2p.bias[(size_t)g * 64 + n];
