@@ -94,6 +94,36 @@ void decb_free(DecBPlan &plan);
 int decb_launch(const DecBPlan &plan, const uint16_t *x, long long x_split, long long x_gs, int B, float *y, int keep_lo,
                 int keep_hi, cudaStream_t s);
 
+// Decoder tail, second generation (fused_dec2.cu): the 1500- and 3000-sample levels live in tensor memory and are read by
+// tcgen05.mma as its A operand; a work item is 128 rows of the 375-sample level, of which 120 carry valid outputs.
+struct FzDecB2 {
+    const uint16_t *x;  // [split][group][B][375][32] channel-last 16-bit
+    long long x_split, x_gs;
+    int B, tiles_per_seq, row_off0;
+    int dbg;  // env VP_DECB_DBG: 4 no head, 16 drain decoder.convs.5 before the next item's first accumulator
+    int T0, L_out;
+    int in_off, s1_off, head_off, xch_off, blob_off, blob_bytes;  // shared-memory byte offsets
+    int w0_off, w1_off, w2_off, w3_off, bias_off;
+    const uint16_t *blob;  // device: [group][blob_bytes / 2]
+    float *y;              // (B, 3, L_out) probabilities
+    int smem_bytes;
+};
+struct DecB2Plan {
+    FzDecB2 p;
+    int split = 0;
+    std::vector<uint16_t> blob;
+    uint16_t *d_blob = nullptr;
+    bool ready = false;
+};
+// dec: the 7 decoder TcLayers (groups = 3, host weight blocks still present); w4 / b4: raw (16, 32, 7) weights and (16) biases of
+// decoder.convs.4 per decoder (folded over two samples here)
+int decb2_build(DecB2Plan &plan, const TcLayer *dec, const float *const *w4, const float *const *b4, int split, const float (*head_w)[88],
+                const float *head_b);
+int decb2_upload(DecB2Plan &plan);
+void decb2_free(DecB2Plan &plan);
+int decb2_launch(const DecB2Plan &plan, const uint16_t *x, long long x_split, long long x_gs, int B, float *y, int keep_lo, int keep_hi,
+                 cudaStream_t s);
+
 // res-CNN stack: the 14 convs of res_cnn_stack.members.0-6 in one persistent launch (fused_res.cu).
 constexpr int RS_MAX_LAYERS = 14;
 struct ResLayerP {

@@ -1,0 +1,849 @@
+// Fused decoder tail, second generation (sm_100a): decoder.convs.3 -> 4 -> 5 -> 6 -> sigmoid(conv k11) with the activations of
+// the two widest levels in TENSOR MEMORY, read by tcgen05.mma as its A operand.
+//
+// Replaces the same reference ops as fused_dec.cu (SeisBench eqtransformer.py Decoder stages 3-6 + conv_d / pick_convs of the
+// three decoders; restated at oracle/nets.py Decoder).  Why a second kernel: fused_dec.cu reads every A operand from shared
+// memory, and a tcgen05.mma of N <= 64 then costs 39 - 48 cycles whatever its math (4 KB of A at 128 B / cycle; measured with
+// tools/ts_probe.cu) -- the 3000- and 6000-sample levels (N = 32 / 16) ran at a quarter of the tensor pipe's rate and the
+// kernel saturated the shared-memory pipe (profiles/r02_decb_experiments.md).  With A in tensor memory the same MMAs cost
+// N / 2 cycles (16 / 9.9 measured) and touch shared memory only for their 0.5 - 1 KB of weights.
+//
+// Layout.  A work item = 128 consecutive rows R0 .. R0 + 127 of the 375-sample level of one (window, decoder); TMEM lane r
+// holds everything that descends from row R0 + r: 2 samples of the 750 level, 4 of the 1500 level, 8 of the 3000 level, 16
+// outputs.  A conv tap cannot shift TMEM lanes, so each level stores, next to a lane's own samples, the halo samples of its
+// two neighbour lanes (copied by warp shuffles in the epilogue that produces the level); a tap is then a COLUMN offset of
+// the A operand:
+//
+//   in (375 level, 32 ch, shared memory, one TMA box)                 --dec3: A from shared memory, taps = row offsets-->
+//   D0[r][phase * 32 + c]  --epilogue A--> S1 (shared memory, rows = lanes, K = 2 samples x 32 ch)
+//                                                     --dec4 folded over 2 samples: 3 row taps, banded weights, N = 4 x 16-->
+//   D1[r][sample * 16 + c] --epilogue A--> A2 (TMEM: 8 slots = samples 4R-2 .. 4R+5 of the 1500 level, 16 ch, fp16 hi | lo)
+//                                                     --dec5: 4 blocks (one input sample -> 2 outputs, N = 32), A from TMEM-->
+//   D2[r][block * 32 + phase * 16 + c] --epilogue B--> A3 (TMEM: 14 slots = samples 8R-3 .. 8R+10 of the 3000 level)
+//                                                     --dec6: 8 blocks (N = 16), A from TMEM-->
+//   D3[r][block * 16 + phase * 8 + c]  --epilogue B--> fp32 planar [c][16 r + i] in shared memory --head warps--> y
+//
+// Every layer loses one lane on each side of the item (its halo comes from the neighbour lane): lanes 4 .. 123 carry valid
+// outputs, an item yields 120 rows = 1920 output samples, three items cover the 5000 kept samples of a blinded window.  Rows
+// outside the sequence are written as zeros at every level (they are the convs' zero padding).
+//
+// TMEM columns (512): [0, 128) A2, which also hosts the accumulators D0 / D1 of the NEXT item while A2 is dead; [128, 352) A3;
+// [352, 480) D2 / D3.  The issuer interleaves the shared-memory half of item n + 1 with the TMEM half of item n
+// (L2(n), L0(n+1), L3(n) first half, L1(n+1), L3(n) second half), so each epilogue runs under the other item's MMAs.
+// Warps: TMA loader, tcgen05 issuer, 4 epilogue warps A (D0 -> S1, D1 -> A2), 4 epilogue warps B (D2 -> A3, D3 -> head buffer),
+// 4 head warps (sigmoid(conv k11), 16 outputs per thread).  Hand-over by mbarriers only.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+#include "fused.cuh"
+#include "tc_ptx.cuh"
+#include "tma.cuh"
+
+namespace vp {
+
+constexpr int D2_THREADS = 32 * 14;
+constexpr int D2_LANE_LO = 4, D2_USE = 120;  // lanes [4, 124) of an item are valid at the output
+constexpr int D2_IN_ROWS = 132;              // input rows R0 - 2 .. R0 + 129
+constexpr int D2_S1_ROWS = 130;              // lanes -1 .. 128 of the 750 level (rows 0 and 129 stay zero)
+constexpr int D2_RP = 2048;                  // floats per channel of the head buffer
+constexpr uint32_t D2_COL_A2 = 0, D2_A2_LO = 64, D2_COL_A3 = 128, D2_A3_LO = 112, D2_COL_D23 = 352;
+// bias block (floats): dec3 [64] | dec4 [16] | dec5 [32] | dec6 [16] | head weights [8][12] | head bias
+constexpr int D2_B0 = 0, D2_B1 = 64, D2_B2 = 80, D2_B3 = 112, D2_HW = 128, D2_BIAS_FLOATS = 256;
+
+// -DVP_D2_PROF build (tools/build_variant.sh): every warp of CTA (0, 0) accumulates the cycles of its sections (waits by barrier,
+// work by epilogue) and decb2_launch prints them.  Empty in the product build.
+#ifdef VP_D2_PROF
+__device__ long long d2_prof_out[14 * 8];
+struct D2Prof {
+    long long acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long t = 0;
+    __device__ __forceinline__ void start() { t = clock64(); }
+    __device__ __forceinline__ void lap(int s) {
+        const long long n = clock64();
+        acc[s] += n - t;
+        t = n;
+    }
+    __device__ __forceinline__ void flush(int warp, int lane) {
+        if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0)
+            for (int i = 0; i < 8; ++i) d2_prof_out[warp * 8 + i] = acc[i];
+    }
+};
+#else
+struct D2Prof {
+    __device__ __forceinline__ void start() {}
+    __device__ __forceinline__ void lap(int) {}
+    __device__ __forceinline__ void flush(int, int) {}
+};
+#endif
+
+struct FzDecB2K {
+    alignas(64) CUtensorMap x_map;  // (8 channels, t, group * B + window, 8-channel plane, split) over the 375-sample level input
+    FzDecB2 p;
+};
+
+// ------------------------------------------------------------------------------------------ PTX: A operand in tensor memory
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+                 "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// One block of a polyphase layer whose input lives in TMEM: input sample slot s0 (8 columns per slot: 16 channels as fp16
+// pairs; the lo split LO_OFF columns further) -> NOUT accumulator columns.  Tap j reads slot s0 + j.  Weight blocks as in
+// tcconv.cu: [tap][split][k-half][NOUT][8].  f16x3: A_hi W_hi + A_hi W_lo + A_lo W_hi.
+template <int NOUT, int SPLIT, int NTAPS>
+__device__ __forceinline__ void umma_ts_block(uint32_t d_tmem, uint32_t a_hi, uint32_t lo_off, uint32_t w16, uint32_t idesc) {
+    constexpr int NTERM = SPLIT == 2 ? 3 : 1;
+    const uint64_t desc_hi = (uint64_t)(0x4000u | (128u >> 4)) << 32;  // version 1 (Blackwell), SBO = 128 B
+    const uint32_t b_base = w16 | ((uint32_t)NOUT << 16);
+#pragma unroll
+    for (int j = 0; j < NTAPS; ++j)
+#pragma unroll
+        for (int t = 0; t < NTERM; ++t) {
+            const int sa = (t == 2) ? 1 : 0, sb = (t == 1) ? 1 : 0;
+            const uint32_t a = a_hi + (uint32_t)(8 * j) + (sa ? lo_off : 0u);
+            const uint32_t b_off = (uint32_t)((j * SPLIT + sb) * 2 * NOUT);
+            umma_f16_ts(d_tmem, a, desc_hi | (uint64_t)(b_base + b_off), idesc, (j == 0 && t == 0) ? 0u : 1u);
+        }
+}
+
+// The shared-memory layers (tc_ptx.cuh umma_conv_tile / umma_conv_tile_stacked) rolled over the taps: one loop iteration = the MMAs
+// of one tap with (base + immediate) descriptors, the tap adds a register offset.  Same MMA order as the unrolled forms.
+template <int NOUT, int SPLIT, int NTAPS, int NQ>
+__device__ __forceinline__ void d2_conv_tile(uint32_t d_tmem, uint32_t a16, uint32_t rows, uint32_t w16, uint32_t idesc) {
+    constexpr int NTERM = SPLIT == 2 ? 3 : 1;
+    constexpr int CIN8 = 2 * NQ;
+    const uint64_t desc_hi = (uint64_t)(0x4000u | (128u >> 4)) << 32;
+    const uint32_t a_base = a16 | (rows << 16);
+    const uint32_t b_base = w16 | ((uint32_t)NOUT << 16);
+#pragma unroll 1
+    for (int j = 0; j < NTAPS; ++j) {
+        const uint32_t aj = a_base + (uint32_t)j, bj = b_base + (uint32_t)(j * NQ * SPLIT * 2 * NOUT);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q)
+#pragma unroll
+            for (int t = 0; t < NTERM; ++t) {
+                const int sa = (t == 2) ? 1 : 0, sb = (t == 1) ? 1 : 0;
+                const uint32_t a_off = (uint32_t)(sa * CIN8 + 2 * q) * rows;
+                const uint32_t b_off = (uint32_t)((q * SPLIT + sb) * 2 * NOUT);
+                umma_f16(d_tmem, desc_hi | (uint64_t)(aj + a_off), desc_hi | (uint64_t)(bj + b_off), idesc, (q == 0 && t == 0) ? (j > 0 ? 1u : 0u) : 1u);
+            }
+    }
+}
+template <int NOUT, int NTAPS, int NQ>
+__device__ __forceinline__ void d2_conv_tile_stacked(uint32_t d_tmem, uint32_t a16, uint32_t rows, uint32_t w16, uint32_t idesc_2n,
+                                                     uint32_t idesc_n) {
+    constexpr int CIN8 = 2 * NQ;
+    const uint64_t desc_hi = (uint64_t)(0x4000u | (128u >> 4)) << 32;
+    const uint32_t a_base = a16 | (rows << 16);
+    const uint32_t b_base = w16 | ((uint32_t)(2 * NOUT) << 16);
+#pragma unroll 1
+    for (int j = 0; j < NTAPS; ++j) {
+        const uint32_t aj = a_base + (uint32_t)j, bj = b_base + (uint32_t)(j * NQ * 4 * NOUT);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const uint32_t a_hi = (uint32_t)(2 * q) * rows, a_lo = (uint32_t)(CIN8 + 2 * q) * rows;
+            const uint32_t b_off = (uint32_t)(q * 4 * NOUT);
+            umma_f16(d_tmem, desc_hi | (uint64_t)(aj + a_hi), desc_hi | (uint64_t)(bj + b_off), idesc_2n, q == 0 ? (j > 0 ? 1u : 0u) : 1u);
+            umma_f16(d_tmem, desc_hi | (uint64_t)(aj + a_lo), desc_hi | (uint64_t)(bj + b_off), idesc_n, 1u);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ epilogue pieces
+// 16 accumulator columns from col0 (+ the stacked half NST columns further) -> relu(acc + bias[0..15])
+template <int NST>
+__device__ __forceinline__ void d2_load16(const float *bias, uint32_t tacc, int col0, float (&v)[16]) {
+    uint32_t r[16], r2[NST > 0 ? 16 : 1];
+    tmem_ld16_nowait(tacc + (uint32_t)col0, r);
+    if constexpr (NST > 0) tmem_ld16_nowait(tacc + (uint32_t)(col0 + NST), r2);
+    tmem_ld_wait();
+#pragma unroll
+    for (int n = 0; n < 16; n += 4) {
+        const float4 b4 = *reinterpret_cast<const float4 *>(bias + n);
+        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float a = __uint_as_float(r[n + e]);
+            if constexpr (NST > 0) a += __uint_as_float(r2[n + e]);
+            v[n + e] = fmaxf(a + bb[e], 0.f);
+        }
+    }
+}
+
+// 16 channels of one sample -> the 8 + 8 packed registers of its TMEM slot (zeros when the row lies outside the sequence)
+template <int SPLIT>
+__device__ __forceinline__ void d2_pack16(const float (&v)[16], bool valid, uint32_t (&h)[8], uint32_t (&l)[8]) {
+    uint4 h0, l0, h1, l1;
+    if (valid) {
+        pack8_split16<SPLIT>(&v[0], h0, l0);
+        pack8_split16<SPLIT>(&v[8], h1, l1);
+    } else {
+        h0 = l0 = h1 = l1 = make_uint4(0u, 0u, 0u, 0u);
+    }
+    h[0] = h0.x, h[1] = h0.y, h[2] = h0.z, h[3] = h0.w, h[4] = h1.x, h[5] = h1.y, h[6] = h1.z, h[7] = h1.w;
+    l[0] = l0.x, l[1] = l0.y, l[2] = l0.z, l[3] = l0.w, l[4] = l1.x, l[5] = l1.y, l[6] = l1.z, l[7] = l1.w;
+}
+
+template <int SPLIT>
+__device__ __forceinline__ void d2_st_slot(uint32_t tl, uint32_t col_hi, uint32_t lo_off, const uint32_t (&h)[8], const uint32_t (&l)[8]) {
+    tmem_st8(tl + col_hi, h);
+    if (SPLIT == 2) tmem_st8(tl + col_hi + lo_off, l);
+}
+
+// Head buffer: fp32 planar [c][sample], addressed in 16-byte units of 4 samples.  Both its writers (lane r stores unit 4 r + bp)
+// and its readers (head thread e loads units 14 + 4 e + q) have a lane stride of four units; XOR-ing the low two unit bits with
+// bits 3-4 spreads the eight lanes of a quarter warp over the eight 16-byte bank groups.
+__device__ __forceinline__ int d2_unit(int u) { return u ^ ((u >> 3) & 3); }
+
+// sigmoid(conv k11, 8 -> 1): head thread e = the 16 outputs of lane 4 + e.
+__device__ __forceinline__ void d2_head(const FzDecB2 &p, const float *hw /*shared: [8][12] weights, bias at [96]*/, int g, int b, int R0,
+                                        int e, const float *buf) {
+    const int row = R0 + D2_LANE_LO + e;
+    if (e >= D2_USE || (unsigned)row >= (unsigned)p.T0) return;
+    const int u0 = 4 * (D2_LANE_LO + e) - 2;  // unit of sample 16 (4 + e) - 8
+    float acc[16];
+#pragma unroll
+    for (int o = 0; o < 16; ++o) acc[o] = hw[96];
+    int uo[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) uo[q] = 4 * d2_unit(u0 + q);
+    float4 cur[8], nxt[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) cur[q] = *reinterpret_cast<const float4 *>(buf + uo[q]);
+    // Rolled over the channels on purpose: fully unrolled, the head alone was 40 KB of straight-line code executed once per item,
+    // next to four other warp roles with bodies of the same size -- the instruction caches (6 KB L0, 32 KB L1.5) served none of them.
+#pragma unroll 1
+    for (int c = 0; c < 8; ++c) {
+        {
+            const int cn = (c + 1) & 7;  // the last iteration re-reads channel 0 (unused)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) nxt[q] = *reinterpret_cast<const float4 *>(buf + (size_t)cn * D2_RP + uo[q]);
+        }
+        float xv[32];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            xv[4 * q] = cur[q].x;
+            xv[4 * q + 1] = cur[q].y;
+            xv[4 * q + 2] = cur[q].z;
+            xv[4 * q + 3] = cur[q].w;
+        }
+        const float4 w0 = *reinterpret_cast<const float4 *>(hw + c * 12), w1 = *reinterpret_cast<const float4 *>(hw + c * 12 + 4),
+                     w2 = *reinterpret_cast<const float4 *>(hw + c * 12 + 8);
+        const float wk[12] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w};
+#pragma unroll
+        for (int k = 0; k < 11; ++k) {
+            const float w = wk[k];
+#pragma unroll
+            for (int o = 0; o < 16; ++o) acc[o] = fmaf(w, xv[o + k + 3], acc[o]);  // xv[0] = sample (first output) - 8
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) cur[q] = nxt[q];
+    }
+    float *yb = p.y + ((size_t)b * 3 + g) * p.L_out + (size_t)16 * row;
+#pragma unroll
+    for (int o = 0; o < 16; o += 4) {
+        float4 o4;
+        o4.x = 1.f / (1.f + expf(-acc[o]));
+        o4.y = 1.f / (1.f + expf(-acc[o + 1]));
+        o4.z = 1.f / (1.f + expf(-acc[o + 2]));
+        o4.w = 1.f / (1.f + expf(-acc[o + 3]));
+        *reinterpret_cast<float4 *>(yb + o) = o4;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ the kernel
+template <int SPLIT>
+__global__ void __launch_bounds__(D2_THREADS, 1) decb2_kernel(const __grid_constant__ FzDecB2K K) {
+    const FzDecB2 &p = K.p;
+    extern __shared__ __align__(128) uint8_t d2_smem[];
+    __shared__ __align__(8) uint64_t in_full, in_empty, d0_full, s1_full, d1_full, a2_full, d2_full[4], a3_full, d3_full[4], d23_free, head_go,
+        head_done;
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = blockIdx.y;
+    const uint32_t sbase = smem_u32(d2_smem);
+    const int n_items = p.B * p.tiles_per_seq;
+    const int n_my = ((int)blockIdx.x < n_items) ? (n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    if (tid == 0) {
+        mbar_init(&in_full, 1);
+        mbar_init(&in_empty, 1);
+        mbar_init(&d0_full, 1);
+        mbar_init(&s1_full, 4);
+        mbar_init(&d1_full, 1);
+        mbar_init(&a2_full, 4);
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(&d2_full[i], 1);
+            mbar_init(&d3_full[i], 1);
+        }
+        mbar_init(&a3_full, 4);
+        mbar_init(&d23_free, 4);
+        mbar_init(&head_go, 4);
+        mbar_init(&head_done, 4);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+    {   // resident weights of this decoder; the two halo rows of S1 that no lane writes
+        const uint4 *wg = reinterpret_cast<const uint4 *>(p.blob + (long long)g * (p.blob_bytes / 2));
+        for (int idx = tid; idx < p.blob_bytes / 16; idx += D2_THREADS) cp_async16(sbase + p.blob_off + idx * 16, wg + idx, 16u);
+        if (tid < SPLIT * 8 * 2) {
+            const int pl = tid >> 1, row = (tid & 1) ? D2_S1_ROWS - 1 : 0;
+            *reinterpret_cast<uint4 *>(d2_smem + p.s1_off + ((size_t)pl * D2_S1_ROWS + row) * 16) = make_uint4(0u, 0u, 0u, 0u);
+        }
+    }
+    cp_async_wait_all();
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    const float *bias = reinterpret_cast<const float *>(d2_smem + p.bias_off);
+
+    if (warp == 0) {
+        // ================= loader: the 132 input rows of the next item as one TMA box (rows outside the sequence arrive as zeros)
+        if (lane == 0) {
+            const uint32_t bytes = (uint32_t)(D2_IN_ROWS * 4 * 16 * SPLIT);
+            for (int k = 0; k < n_my; ++k) {
+                const int it = blockIdx.x + k * gridDim.x;
+                const int b = it / p.tiles_per_seq, j = it - b * p.tiles_per_seq;
+                const int R0 = p.row_off0 + D2_USE * j - D2_LANE_LO;
+                mbar_wait(&in_empty, (k & 1) ^ 1);
+                mbar_arrive_expect_tx(&in_full, bytes);
+                tma_load_5d(sbase + p.in_off, &K.x_map, &in_full, 0, R0 - 2, g * p.B + b, 0, 0);
+            }
+        }
+    } else if (warp == 1) {
+        // ================= tcgen05 issuer
+        const uint32_t fmt = SPLIT == 2 ? 0u : 1u;
+        const uint32_t id16 = umma_idesc(16, fmt), id32 = umma_idesc(32, fmt), id64 = umma_idesc(64, fmt), id128 = umma_idesc(128, fmt);
+        const uint32_t in16 = (sbase + p.in_off) >> 4, s116 = (sbase + p.s1_off) >> 4;
+        const uint32_t w0 = (sbase + p.w0_off) >> 4, w1 = (sbase + p.w1_off) >> 4, w2 = (sbase + p.w2_off) >> 4, w3 = (sbase + p.w3_off) >> 4;
+        (void)id128;
+        D2Prof prof;  // 0 in_full, 1 s1_full, 2 a2_full, 3 d23_free, 4 a3_full, 5 issue
+        prof.start();
+        auto issue_L0 = [&](int m) {  // dec3: in (shared) -> D0 = columns [0, 64)
+            mbar_wait(&in_full, m & 1);
+            prof.lap(0);
+            fence_proxy_async();
+            tc_fence_after();
+            if (elect_one()) {
+                d2_conv_tile<64, SPLIT, 5, 2>(tmem_base + D2_COL_A2, in16, D2_IN_ROWS, w0, id64);
+                umma_commit(&d0_full);
+                umma_commit(&in_empty);
+            }
+            __syncwarp();
+        };
+        auto issue_L1 = [&](int m) {  // dec4 folded: S1 (shared) -> D1 = columns [0, 64) (+ [64, 128): the stacked W_lo half)
+            mbar_wait(&s1_full, m & 1);
+            prof.lap(1);
+            fence_proxy_async();
+            tc_fence_after();
+            if (elect_one()) {
+                if constexpr (SPLIT == 2)
+                    d2_conv_tile_stacked<64, 3, 4>(tmem_base + D2_COL_A2, s116, D2_S1_ROWS, w1, id128, id64);
+                else
+                    d2_conv_tile<64, 1, 3, 4>(tmem_base + D2_COL_A2, s116, D2_S1_ROWS, w1, id64);
+                umma_commit(&d1_full);
+            }
+            __syncwarp();
+        };
+        auto issue_L2 = [&](int n) {  // dec5: A2 (TMEM) -> D2 blocks
+            mbar_wait(&a2_full, n & 1);
+            prof.lap(2);
+            if (n > 0) mbar_wait(&d23_free, (n - 1) & 1);
+            prof.lap(3);
+            tc_fence_after();
+            if (elect_one()) {
+#pragma unroll 1
+                for (int b = 0; b < 4; ++b) {
+                    umma_ts_block<32, SPLIT, 5>(tmem_base + D2_COL_D23 + 32 * b, tmem_base + D2_COL_A2 + 8 * b, D2_A2_LO, w2, id32);
+                    umma_commit(&d2_full[b]);
+                }
+            }
+            __syncwarp();
+        };
+        auto issue_L3 = [&](int n, int half) {  // dec6: A3 (TMEM) -> D3 blocks
+            if (half == 0) {
+                mbar_wait(&a3_full, n & 1);
+                prof.lap(4);
+                tc_fence_after();
+            }
+            if (elect_one()) {
+#pragma unroll 1
+                for (int bb = 0; bb < 4; ++bb) {
+                    const int b = 4 * half + bb;
+                    umma_ts_block<16, SPLIT, 7>(tmem_base + D2_COL_D23 + 16 * b, tmem_base + D2_COL_A3 + 8 * b, D2_A3_LO, w3, id16);
+                    if (b & 1) umma_commit(&d3_full[b >> 1]);
+                }
+            }
+            __syncwarp();
+        };
+        if (n_my > 0) {
+            issue_L0(0);
+            prof.lap(5);
+            issue_L1(0);
+            prof.lap(5);
+        }
+        for (int n = 0; n < n_my; ++n) {
+            issue_L2(n);
+            prof.lap(5);
+            if (n + 1 < n_my) {
+                if (p.dbg & 16) {  // debug: drain L2 before the next item's D0 lands in the A2 columns
+                    mbar_wait(&d2_full[3], n & 1);
+                    tc_fence_after();
+                }
+                issue_L0(n + 1);
+                prof.lap(5);
+            }
+            issue_L3(n, 0);
+            prof.lap(5);
+            if (n + 1 < n_my) {
+                issue_L1(n + 1);
+                prof.lap(5);
+            }
+            issue_L3(n, 1);
+            prof.lap(5);
+        }
+        prof.flush(warp, lane);
+    } else if (warp < 6) {
+        // ================= epilogue warps A: D0 -> S1 (shared memory), D1 -> A2 (tensor memory)
+        const int q = warp & 3, r = q * 32 + lane;
+        const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
+        uint32_t *xa = reinterpret_cast<uint32_t *>(d2_smem + p.xch_off);  // [parity][quarter][side][sample 2][16]
+        uint8_t *s1 = d2_smem + p.s1_off;
+        D2Prof prof;  // 0 d0_full, 1 d1_full, 2 d2_full[3], 3 E0, 4 E1
+        prof.start();
+        for (int m = 0; m < n_my; ++m) {
+            const int it = blockIdx.x + m * gridDim.x;
+            const int b = it / p.tiles_per_seq, j = it - b * p.tiles_per_seq;
+            const int R0 = p.row_off0 + D2_USE * j - D2_LANE_LO;
+            const bool valid = (unsigned)(R0 + r) < (unsigned)p.T0;
+            // ---- E0
+            mbar_wait(&d0_full, m & 1);
+            prof.lap(0);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c0 = 0; c0 < 64; c0 += 16) {
+                float v[16];
+                d2_load16<0>(bias + D2_B0 + c0, tl + D2_COL_A2, c0, v);
+                uint32_t h[8], l[8];
+                d2_pack16<SPLIT>(v, valid, h, l);
+                const int pl = (c0 >> 5) * 4 + ((c0 & 31) >> 3);  // plane' = phase * 4 + channel plane
+                uint8_t *d = s1 + ((size_t)pl * D2_S1_ROWS + r + 1) * 16;
+                *reinterpret_cast<uint4 *>(d) = make_uint4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<uint4 *>(d + (size_t)D2_S1_ROWS * 16) = make_uint4(h[4], h[5], h[6], h[7]);
+                if (SPLIT == 2) {
+                    *reinterpret_cast<uint4 *>(d + (size_t)8 * D2_S1_ROWS * 16) = make_uint4(l[0], l[1], l[2], l[3]);
+                    *reinterpret_cast<uint4 *>(d + (size_t)9 * D2_S1_ROWS * 16) = make_uint4(l[4], l[5], l[6], l[7]);
+                }
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s1_full);
+            prof.lap(3);
+            // ---- E1: D1 sits in the A2 columns -> read all of it before the first store
+            mbar_wait(&d1_full, m & 1);
+            prof.lap(1);
+            if (m > 0) mbar_wait(&d2_full[3], (m - 1) & 1);  // dec5 of the previous item has read A2
+            prof.lap(2);
+            tc_fence_after();
+            uint32_t oh[4][8], ol[4][8];
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                float v[16];
+                d2_load16<SPLIT == 2 ? 64 : 0>(bias + D2_B1, tl + D2_COL_A2, 16 * s, v);
+                d2_pack16<SPLIT>(v, valid, oh[s], ol[s]);
+            }
+            uint32_t *xw = xa + (size_t)(((m & 1) * 4 + q) * 2) * 32;
+            if (lane == 0 || lane == 31) {
+                uint32_t *d = xw + (lane == 31 ? 32 : 0);
+#pragma unroll
+                for (int s = 0; s < 2; ++s)
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        d[s * 16 + i] = lane == 31 ? oh[2 + s][i] : oh[s][i];
+                        d[s * 16 + 8 + i] = lane == 31 ? ol[2 + s][i] : ol[s][i];
+                    }
+            }
+#pragma unroll
+            for (int s = 0; s < 4; ++s) d2_st_slot<SPLIT>(tl, D2_COL_A2 + 8 * (2 + s), D2_A2_LO, oh[s], ol[s]);
+            named_bar_sync(1, 128);
+            const uint32_t *xl = xa + (size_t)(((m & 1) * 4 + (q + 3) % 4) * 2 + 1) * 32;  // previous quarter's lane 31: its samples 2, 3
+            const uint32_t *xr = xa + (size_t)(((m & 1) * 4 + (q + 1) % 4) * 2) * 32;      // next quarter's lane 0: its samples 0, 1
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                uint32_t h[8], l[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {  // left halo: slots 0, 1 = samples 2, 3 of lane r - 1
+                    h[i] = __shfl_up_sync(0xffffffffu, oh[2 + s][i], 1);
+                    l[i] = __shfl_up_sync(0xffffffffu, ol[2 + s][i], 1);
+                    if (lane == 0) {
+                        h[i] = q > 0 ? xl[s * 16 + i] : 0u;
+                        l[i] = q > 0 ? xl[s * 16 + 8 + i] : 0u;
+                    }
+                }
+                d2_st_slot<SPLIT>(tl, D2_COL_A2 + 8 * s, D2_A2_LO, h, l);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {  // right halo: slots 6, 7 = samples 0, 1 of lane r + 1
+                    h[i] = __shfl_down_sync(0xffffffffu, oh[s][i], 1);
+                    l[i] = __shfl_down_sync(0xffffffffu, ol[s][i], 1);
+                    if (lane == 31) {
+                        h[i] = q < 3 ? xr[s * 16 + i] : 0u;
+                        l[i] = q < 3 ? xr[s * 16 + 8 + i] : 0u;
+                    }
+                }
+                d2_st_slot<SPLIT>(tl, D2_COL_A2 + 8 * (6 + s), D2_A2_LO, h, l);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a2_full);
+            prof.lap(4);
+        }
+        prof.flush(warp, lane);
+    } else if (warp < 10) {
+        // ================= epilogue warps B: D2 -> A3 (tensor memory), D3 -> head buffer (shared memory)
+        const int q = warp & 3, r = q * 32 + lane;
+        const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
+        uint32_t *xb = reinterpret_cast<uint32_t *>(d2_smem + p.xch_off + 2048);  // [parity][quarter][side][sample 3][16]
+        float *hbuf = reinterpret_cast<float *>(d2_smem + p.head_off);
+        D2Prof prof;  // 0 d2_full, 1 head_done, 2 d3_full, 3 E2 blocks, 4 halo exchange, 5 E3
+        prof.start();
+        for (int n = 0; n < n_my; ++n) {
+            const int it = blockIdx.x + n * gridDim.x;
+            const int b = it / p.tiles_per_seq, j = it - b * p.tiles_per_seq;
+            const int R0 = p.row_off0 + D2_USE * j - D2_LANE_LO;
+            const bool valid = (unsigned)(R0 + r) < (unsigned)p.T0;
+            // ---- E2: block bb = samples 2 bb, 2 bb + 1 of the lane's eight 3000-level samples -> slots 3 + sample
+            uint32_t *xw = xb + (size_t)(((n & 1) * 4 + q) * 2) * 48;
+#pragma unroll 1
+            for (int bb = 0; bb < 4; ++bb) {
+                mbar_wait(&d2_full[bb], n & 1);
+                prof.lap(0);
+                tc_fence_after();
+#pragma unroll
+                for (int ph = 0; ph < 2; ++ph) {
+                    float v[16];
+                    d2_load16<0>(bias + D2_B2 + 16 * ph, tl + D2_COL_D23, 32 * bb + 16 * ph, v);
+                    uint32_t h[8], l[8];
+                    d2_pack16<SPLIT>(v, valid, h, l);
+                    const int s = 2 * bb + ph;
+                    d2_st_slot<SPLIT>(tl, D2_COL_A3 + 8 * (3 + s), D2_A3_LO, h, l);
+                    // the quarter's edge lanes post what their neighbour quarter needs: lane 0 samples 0-2, lane 31 samples 5-7
+                    if (s < 3 && lane == 0) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) xw[s * 16 + i] = h[i], xw[s * 16 + 8 + i] = l[i];
+                    }
+                    if (s >= 5 && lane == 31) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) xw[48 + (s - 5) * 16 + i] = h[i], xw[48 + (s - 5) * 16 + 8 + i] = l[i];
+                    }
+                }
+                prof.lap(3);
+            }
+            tmem_st_wait();
+            named_bar_sync(2, 128);
+            const uint32_t *xl = xb + (size_t)(((n & 1) * 4 + (q + 3) % 4) * 2 + 1) * 48;  // previous quarter's lane 31: samples 5-7
+            const uint32_t *xr = xb + (size_t)(((n & 1) * 4 + (q + 1) % 4) * 2) * 48;      // next quarter's lane 0: samples 0-2
+#pragma unroll 1
+            for (int i3 = 0; i3 < 3; ++i3) {
+                uint32_t h[8], l[8];
+                // right halo: slot 11 + i = sample i of lane r + 1 (its slot 3 + i)
+                tmem_ld8_nowait(tl + D2_COL_A3 + 8 * (3 + i3), h);
+                if (SPLIT == 2) tmem_ld8_nowait(tl + D2_COL_A3 + D2_A3_LO + 8 * (3 + i3), l);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    h[i] = __shfl_down_sync(0xffffffffu, h[i], 1);
+                    if (SPLIT == 2) l[i] = __shfl_down_sync(0xffffffffu, l[i], 1);
+                    if (lane == 31) {
+                        h[i] = q < 3 ? xr[i3 * 16 + i] : 0u;
+                        if (SPLIT == 2) l[i] = q < 3 ? xr[i3 * 16 + 8 + i] : 0u;
+                    }
+                }
+                d2_st_slot<SPLIT>(tl, D2_COL_A3 + 8 * (11 + i3), D2_A3_LO, h, l);
+                // left halo: slot i = sample 5 + i of lane r - 1 (its slot 8 + i)
+                tmem_ld8_nowait(tl + D2_COL_A3 + 8 * (8 + i3), h);
+                if (SPLIT == 2) tmem_ld8_nowait(tl + D2_COL_A3 + D2_A3_LO + 8 * (8 + i3), l);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    h[i] = __shfl_up_sync(0xffffffffu, h[i], 1);
+                    if (SPLIT == 2) l[i] = __shfl_up_sync(0xffffffffu, l[i], 1);
+                    if (lane == 0) {
+                        h[i] = q > 0 ? xl[i3 * 16 + i] : 0u;
+                        if (SPLIT == 2) l[i] = q > 0 ? xl[i3 * 16 + 8 + i] : 0u;
+                    }
+                }
+                d2_st_slot<SPLIT>(tl, D2_COL_A3 + 8 * i3, D2_A3_LO, h, l);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a3_full);
+            prof.lap(4);
+            // ---- E3: blocks 2 bp, 2 bp + 1 = samples 4 bp .. 4 bp + 3 of the lane's 16 outputs -> one 16-byte unit per channel
+            if (n > 0) mbar_wait(&head_done, (n - 1) & 1);
+            prof.lap(1);
+#pragma unroll 1
+            for (int bp = 0; bp < 4; ++bp) {
+                mbar_wait(&d3_full[bp], n & 1);
+                prof.lap(2);
+                tc_fence_after();
+                uint32_t ra[16], rb[16];
+                tmem_ld16_nowait(tl + D2_COL_D23 + 32 * bp, ra);       // samples 4 bp, 4 bp + 1: [phase][8]
+                tmem_ld16_nowait(tl + D2_COL_D23 + 32 * bp + 16, rb);  // samples 4 bp + 2, 4 bp + 3
+                tmem_ld_wait();
+                float *d = hbuf + 4 * d2_unit(4 * r + bp);
+                const float4 b0 = *reinterpret_cast<const float4 *>(bias + D2_B3), b1 = *reinterpret_cast<const float4 *>(bias + D2_B3 + 4);
+                const float bb8[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    float4 o;
+                    o.x = valid ? fmaxf(__uint_as_float(ra[c]) + bb8[c], 0.f) : 0.f;
+                    o.y = valid ? fmaxf(__uint_as_float(ra[8 + c]) + bb8[c], 0.f) : 0.f;
+                    o.z = valid ? fmaxf(__uint_as_float(rb[c]) + bb8[c], 0.f) : 0.f;
+                    o.w = valid ? fmaxf(__uint_as_float(rb[8 + c]) + bb8[c], 0.f) : 0.f;
+                    *reinterpret_cast<float4 *>(d + (size_t)c * D2_RP) = o;
+                }
+                prof.lap(5);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&head_go);
+                mbar_arrive(&d23_free);
+            }
+        }
+        prof.flush(warp, lane);
+    } else {
+        // ================= head warps: sigmoid(conv k11) of item n while the pipeline runs item n + 1
+        const int e = (warp - 10) * 32 + lane;
+        const float *hbuf = reinterpret_cast<const float *>(d2_smem + p.head_off);
+        D2Prof prof;  // 0 head_go, 1 head
+        prof.start();
+        for (int n = 0; n < n_my; ++n) {
+            const int it = blockIdx.x + n * gridDim.x;
+            const int b = it / p.tiles_per_seq, j = it - b * p.tiles_per_seq;
+            const int R0 = p.row_off0 + D2_USE * j - D2_LANE_LO;
+            mbar_wait(&head_go, n & 1);
+            prof.lap(0);
+            if (!(p.dbg & 4)) d2_head(p, bias + D2_HW, g, b, R0, e, hbuf);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&head_done);
+            prof.lap(1);
+        }
+        prof.flush(warp, lane);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------ host: plan
+static inline int d2_floordiv2(int a) { return (a >= 0) ? a / 2 : -((-a + 1) / 2); }
+
+static void d2_to16(float w, int split, uint16_t &hi, uint16_t &lo) {
+    if (split == 2) {
+        const __half h = __float2half_rn(w);
+        hi = __half_as_ushort(h);
+        lo = __half_as_ushort(__float2half_rn(w - __half2float(h)));
+    } else {
+        hi = __bfloat16_as_ushort(__float2bfloat16_rn(w));
+        lo = 0;
+    }
+}
+
+int decb2_build(DecB2Plan &plan, const TcLayer *dec, const float *const *w4, const float *const *b4, int split, const float (*head_w)[88],
+                const float *head_b) {
+    FzDecB2 &p = plan.p;
+    std::memset(&p, 0, sizeof(p));
+    plan.split = split;
+    plan.ready = false;
+    const int G = 3;
+    const TcLayer &L0 = dec[3], &L1 = dec[4], &L2 = dec[5], &L3 = dec[6];
+    VP_REQUIRE(L0.ph == 2 && L0.cin == 32 && L0.nout == 64 && L0.sched_taps == 5 && L0.sched_nq == 2 && L0.row0 == -2 && L0.groups == G,
+               VP_ERR_UNSUPPORTED, "decb2: decoder.convs.3 differs from the compiled schedule");
+    VP_REQUIRE(L1.cin == 32 && L1.cout == 16 && L1.k == 7, VP_ERR_UNSUPPORTED, "decb2: decoder.convs.4 must be 32 -> 16, k = 7");
+    VP_REQUIRE(L2.ph == 2 && L2.cin == 16 && L2.nout == 32 && L2.sched_taps == 5 && L2.sched_nq == 1 && L2.row0 == -2 && L2.groups == G,
+               VP_ERR_UNSUPPORTED, "decb2: decoder.convs.5 differs from the compiled schedule");
+    VP_REQUIRE(L3.ph == 2 && L3.cin == 16 && L3.nout == 16 && L3.sched_taps == 7 && L3.sched_nq == 1 && L3.row0 == -3 && L3.groups == G,
+               VP_ERR_UNSUPPORTED, "decb2: decoder.convs.6 differs from the compiled schedule");
+    VP_REQUIRE(!L0.blocks.empty() && !L2.blocks.empty() && !L3.blocks.empty(), VP_ERR_ARG, "decb2: host weight blocks are gone");
+    p.T0 = 375;
+    p.L_out = 6000;
+    auto up128 = [](size_t v) { return (v + 127) & ~(size_t)127; };
+    // shared memory: input box | S1 | head buffer | shuffle exchange | weight blob
+    size_t off = 0;
+    p.in_off = (int)off;
+    off += up128((size_t)D2_IN_ROWS * 4 * 16 * split);
+    p.s1_off = (int)off;
+    off += up128((size_t)D2_S1_ROWS * 8 * 16 * split);
+    p.head_off = (int)off;
+    off += (size_t)8 * D2_RP * sizeof(float);
+    p.xch_off = (int)off;
+    off += 2048 + 3072;
+    p.blob_off = (int)off;
+    // blob per group
+    const size_t blk0 = (size_t)split * 2 * 64 * 8, blk2 = (size_t)split * 2 * 32 * 8, blk3 = (size_t)split * 2 * 16 * 8;  // 16-bit elements
+    const size_t blk1 = (size_t)split * 2 * 64 * 8;
+    size_t rel = 0;
+    const size_t r0 = rel;
+    rel += up128(10 * blk0 * 2);
+    const size_t r1 = rel;
+    rel += up128(12 * blk1 * 2);
+    const size_t r2 = rel;
+    rel += up128(5 * blk2 * 2);
+    const size_t r3 = rel;
+    rel += up128(7 * blk3 * 2);
+    const size_t rb = rel;
+    rel += up128((size_t)D2_BIAS_FLOATS * sizeof(float));
+    p.blob_bytes = (int)rel;
+    p.w0_off = p.blob_off + (int)r0;
+    p.w1_off = p.blob_off + (int)r1;
+    p.w2_off = p.blob_off + (int)r2;
+    p.w3_off = p.blob_off + (int)r3;
+    p.bias_off = p.blob_off + (int)rb;
+    p.smem_bytes = p.blob_off + p.blob_bytes;
+    VP_REQUIRE(p.smem_bytes <= 227 * 1024 - 256, VP_ERR_UNSUPPORTED, "decb2: %d bytes of shared memory", p.smem_bytes);
+    VP_REQUIRE(L0.n_blocks == 10 && L2.n_blocks == 5 && L3.n_blocks == 7, VP_ERR_UNSUPPORTED, "decb2: weight block counts");
+    plan.blob.assign((size_t)G * rel / 2, 0);
+    for (int g = 0; g < G; ++g) {
+        uint16_t *dst = plan.blob.data() + (size_t)g * rel / 2;
+        std::memcpy(dst + r0 / 2, L0.blocks.data() + (size_t)g * 10 * blk0, 10 * blk0 * 2);
+        std::memcpy(dst + r2 / 2, L2.blocks.data() + (size_t)g * 5 * blk2, 5 * blk2 * 2);
+        std::memcpy(dst + r3 / 2, L3.blocks.data() + (size_t)g * 7 * blk3, 7 * blk3 * 2);
+        // decoder.convs.4 (16, 32, 7) after x2 up-sampling, folded over the two 750-level samples of a 375-level row:
+        //   out1500[4 R + s'] = sum_kk W[kk] xup[4 R + s' + kk - 3],  xup[u] = x750[u div 2]  ->  x750[2 R + d], d in [-2, 3]
+        //   row tap jr = d div 2 + 1 (rows R - 1, R, R + 1), K index = (d mod 2) * 32 + ci, column n = s' * 16 + co.
+        // Block = jr * 4 + K step; f16x3: [k-half][W_hi rows 0..63 | W_lo rows 64..127][8] (stacked along N), bf16: [k-half][64][8].
+        std::vector<float> wf((size_t)3 * 64 * 64, 0.f);  // [jr][kidx][n]
+        const float *W = w4[g];
+        for (int sp = 0; sp < 4; ++sp)
+            for (int kk = 0; kk < 7; ++kk) {
+                const int u = sp + kk - 3;              // up-sampled position relative to 4 R
+                const int d = d2_floordiv2(u);          // 750-level position relative to 2 R
+                const int jr = d2_floordiv2(d) + 1, ph = d - 2 * d2_floordiv2(d);
+                VP_REQUIRE(jr >= 0 && jr < 3, VP_ERR_UNSUPPORTED, "decb2: row tap %d", jr);
+                for (int co = 0; co < 16; ++co)
+                    for (int ci = 0; ci < 32; ++ci)
+                        wf[((size_t)jr * 64 + ph * 32 + ci) * 64 + sp * 16 + co] += W[((size_t)co * 32 + ci) * 7 + kk];
+            }
+        uint16_t *w1 = dst + r1 / 2;
+        for (int jr = 0; jr < 3; ++jr)
+            for (int kidx = 0; kidx < 64; ++kidx)
+                for (int n = 0; n < 64; ++n) {
+                    const int blk = jr * 4 + kidx / 16, kh = (kidx % 16) / 8, e = kidx % 8;
+                    uint16_t hi, lo;
+                    d2_to16(wf[((size_t)jr * 64 + kidx) * 64 + n], split, hi, lo);
+                    if (split == 2) {
+                        w1[(size_t)blk * blk1 + ((size_t)kh * 128 + n) * 8 + e] = hi;
+                        w1[(size_t)blk * blk1 + ((size_t)kh * 128 + 64 + n) * 8 + e] = lo;
+                    } else {
+                        w1[(size_t)blk * blk1 + ((size_t)kh * 64 + n) * 8 + e] = hi;
+                    }
+                }
+        float *bd = reinterpret_cast<float *>(dst + rb / 2);
+        for (int n = 0; n < 64; ++n) bd[D2_B0 + n] = L0.bias[(size_t)g * 64 + n];
+        for (int n = 0; n < 16; ++n) bd[D2_B1 + n] = b4[g] ? b4[g][n] : 0.f;
+        for (int n = 0; n < 32; ++n) bd[D2_B2 + n] = L2.bias[(size_t)g * 32 + n];
+        for (int n = 0; n < 16; ++n) bd[D2_B3 + n] = L3.bias[(size_t)g * 16 + n];
+        for (int c = 0; c < 8; ++c)
+            for (int k = 0; k < 11; ++k) bd[D2_HW + c * 12 + k] = head_w[g][c * 11 + k];
+        bd[D2_HW + 96] = head_b[g];
+    }
+    return VP_OK;
+}
+
+int decb2_upload(DecB2Plan &plan) {
+    VP_CUDA_CHECK(cudaMalloc(&plan.d_blob, plan.blob.size() * sizeof(uint16_t)));
+    VP_CUDA_CHECK(cudaMemcpy(plan.d_blob, plan.blob.data(), plan.blob.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    plan.blob.clear();
+    plan.blob.shrink_to_fit();
+    plan.ready = true;
+    return VP_OK;
+}
+
+void decb2_free(DecB2Plan &plan) {
+    if (plan.d_blob) cudaFree(plan.d_blob);
+    plan.d_blob = nullptr;
+    plan.ready = false;
+}
+
+template <int SPLIT>
+static int decb2_launch_t(const FzDecB2 &p, dim3 grid, cudaStream_t s) {
+    auto kern = decb2_kernel<SPLIT>;
+    FzDecB2K K;
+    K.p = p;
+    {
+        VP_REQUIRE(p.x_gs == (long long)p.B * p.T0 * 32 && (p.x_split * 2) % 16 == 0 && reinterpret_cast<uintptr_t>(p.x) % 16 == 0, VP_ERR_ARG,
+                   "decb2: the input groups must be contiguous ([split][group][B][375][32]) and 16-byte aligned");
+        const uint64_t dims[5] = {8, (uint64_t)p.T0, (uint64_t)3 * p.B, 4, (uint64_t)SPLIT};
+        const uint64_t strides[4] = {64, (uint64_t)p.T0 * 64, 16, (uint64_t)p.x_split * 2};
+        const uint32_t box[5] = {8, (uint32_t)D2_IN_ROWS, 1, 4, (uint32_t)SPLIT};
+        if (int rc = tma_encode_u16(&K.x_map, p.x, 5, dims, strides, box)) return rc;
+    }
+    if (int rc = ensure_dyn_smem((const void *)kern, (size_t)p.smem_bytes)) return rc;
+    KTimer kt(KC_DECB, s);
+    kern<<<grid, D2_THREADS, p.smem_bytes, s>>>(K);
+    VP_LAUNCH_CHECK();
+#ifdef VP_D2_PROF
+    {
+        cudaStreamSynchronize(s);
+        long long h[14 * 8];
+        cudaMemcpyFromSymbol(h, d2_prof_out, sizeof(h));
+        const int n_items = p.B * p.tiles_per_seq, n_my = (n_items - 1) / (int)grid.x + 1;
+        static const char *role[14] = {"loader", "issuer", "epiA", "epiA", "epiA", "epiA", "epiB", "epiB", "epiB", "epiB", "head", "head", "head", "head"};
+        fprintf(stderr, "[decb2 prof] split %d, %d items per CTA; cycles per item by section\n", SPLIT, n_my);
+        for (int w = 1; w < 14; ++w) {
+            fprintf(stderr, "  warp %2d %-6s", w, role[w]);
+            for (int i = 0; i < 8; ++i) fprintf(stderr, " %8.0f", (double)h[w * 8 + i] / n_my);
+            fprintf(stderr, "\n");
+        }
+    }
+#endif
+    return VP_OK;
+}
+
+int decb2_launch(const DecB2Plan &plan, const uint16_t *x, long long x_split, long long x_gs, int B, float *y, int keep_lo, int keep_hi,
+                 cudaStream_t s) {
+    VP_REQUIRE(plan.ready, VP_ERR_UNSUPPORTED, "decb2: plan not uploaded");
+    FzDecB2 p = plan.p;
+    keep_lo = std::max(0, std::min(keep_lo, p.L_out));
+    keep_hi = std::max(keep_lo, std::min(keep_hi, p.L_out));
+    if (keep_hi == keep_lo) return VP_OK;
+    p.row_off0 = keep_lo / 16;
+    const int row_hi = (keep_hi + 15) / 16;
+    p.tiles_per_seq = (row_hi - p.row_off0 + D2_USE - 1) / D2_USE;
+    p.x = x;
+    p.x_split = x_split;
+    p.x_gs = x_gs;
+    p.B = B;
+    p.blob = plan.d_blob;
+    p.y = y;
+    {
+        const char *e = getenv("VP_DECB_DBG");
+        p.dbg = e ? atoi(e) : 0;
+    }
+    const int n_items = B * p.tiles_per_seq;
+    if (n_items == 0) return VP_OK;
+    dim3 grid((unsigned)std::min(std::max(device_sm_count() / 3, 1), n_items), 3);
+    return plan.split == 2 ? decb2_launch_t<2>(p, grid, s) : decb2_launch_t<1>(p, grid, s);
+}
+
+}  // namespace vp

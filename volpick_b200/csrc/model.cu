@@ -289,6 +289,7 @@ struct vp_model {
         float *d_res_par = nullptr;
         bool ready = false;
         DecBPlan decb;  // fused decoder tail (fused_dec.cu)
+        DecB2Plan decb2;  // fused decoder tail with the wide levels in tensor memory (fused_dec2.cu): the default
         DecAPlan deca;  // fused decoder middle, convs.1 + convs.2 (fused_deca.cu)
     } tc[2];
     // PhaseNet on the tensor cores (same precision sets).  Stride-4 convs and the stride-4 ConvTranspose1d run as k = 2
@@ -542,6 +543,11 @@ static int build_eqt(vp_model *m, Cursor &cur, Packed &pk) {
         if (const char *e = getenv(split == 2 ? "VP_DECB_M2" : "VP_DECB_M1")) tile_m = atoi(e);  // tuning / debugging aid
         rc = decb_build(ts.decb, ts.dec, split, tile_m, head_w, head_b);
         if (rc != VP_OK) return rc;
+        {
+            const float *w4[3] = {dW[0][4], dW[1][4], dW[2][4]}, *b4[3] = {dB[0][4], dB[1][4], dB[2][4]};
+            rc = decb2_build(ts.decb2, ts.dec, w4, b4, split, head_w, head_b);
+            if (rc != VP_OK) return rc;
+        }
         {   // fused decoder middle: decoder.convs.2 in polyphase form (the crop is corrected inside the kernel)
             TcLayer dec2p;
             const float *w2[3] = {dW[0][2], dW[1][2], dW[2][2]}, *b2[3] = {dB[0][2], dB[1][2], dB[2][2]};
@@ -1280,8 +1286,11 @@ static int run_eqt(Runner &r, const float *x, float *y, Arena &ar) {
                 continue;
             }
             if (fused && i == 3) {  // decoder.convs.3-6 + heads in one kernel, activations in shared memory
+                static const bool decb_v1 = getenv("VP_DECB_V1") && atoi(getenv("VP_DECB_V1")) != 0;  // A/B arm: the shared-memory-operand kernel
                 if (r.go())
-                    r.rc = decb_launch(ts.decb, cur16, split16, B * (int64_t)tl.cin * dlen[i], (int)B, y, r.keep_lo, r.keep_hi, r.s);
+                    r.rc = (ts.decb2.ready && !decb_v1)
+                               ? decb2_launch(ts.decb2, cur16, split16, B * (int64_t)tl.cin * dlen[i], (int)B, y, r.keep_lo, r.keep_hi, r.s)
+                               : decb_launch(ts.decb, cur16, split16, B * (int64_t)tl.cin * dlen[i], (int)B, y, r.keep_lo, r.keep_hi, r.s);
                 return r.rc;
             }
             if (r.go()) {
@@ -1784,6 +1793,7 @@ extern "C" int vp_model_create(int kind, const float *weights, int64_t n_floats,
         for (int set = 0; set < 2; ++set) {
             int rc = upload_tc(m->tc[set]);
             if (rc == VP_OK) rc = decb_upload(m->tc[set].decb);
+            if (rc == VP_OK) rc = decb2_upload(m->tc[set].decb2);
             if (rc == VP_OK) rc = deca_upload(m->tc[set].deca);
             if (rc != VP_OK) {
                 vp_model_destroy(m);
@@ -1812,6 +1822,7 @@ extern "C" int vp_model_destroy(vp_model *m) {
         if (m->tc[set].d_b) cudaFree(m->tc[set].d_b);
         if (m->tc[set].d_res_par) cudaFree(m->tc[set].d_res_par);
         decb_free(m->tc[set].decb);
+        decb2_free(m->tc[set].decb2);
         deca_free(m->tc[set].deca);
         if (m->pn_tc[set].d_w) cudaFree(m->pn_tc[set].d_w);
         if (m->pn_tc[set].d_b) cudaFree(m->pn_tc[set].d_b);

@@ -15,6 +15,22 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+#ifdef VP_MBAR_SLEEP  // A/B build: back off with nanosleep between polls (the waiting warps of a long hand-over chain otherwise
+                      // take issue slots from the working warps of their scheduler)
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "nanosleep.u32 %2;\n\t"
+        "bra LAB_WAIT;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"((uint32_t)VP_MBAR_SLEEP)
+        : "memory");
+    return;
+#endif
 #ifdef VP_MBAR_NOHINT  // A/B build: default time limit of try_wait (the warp re-polls every ~30 cycles)
     asm volatile(
         "{\n\t"
