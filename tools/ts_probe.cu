@@ -190,6 +190,118 @@ __global__ void __launch_bounds__(256, 1) ldst_rate_kernel(long long *cycles, in
         }                                                                          \
     } while (0)
 
+
+// ---------------------------------------------------------------- tcgen05.ld latency while another warp keeps the tensor pipe busy
+template <int N, bool TS, int RD>
+__global__ void __launch_bounds__(256, 1) ld_under_mma_kernel(long long *out, int nm) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ volatile int go, done;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        fence_barrier_init();
+        go = 0;
+        done = 0;
+    }
+    if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+    for (int idx = tid; idx < 16384; idx += 256) reinterpret_cast<uint32_t *>(smem)[idx] = 0u;
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    if (warp == 0) {
+        if (elect_one()) {
+            const uint64_t desc_hi = (uint64_t)(0x4000u | (128u >> 4)) << 32;
+            const uint32_t s16 = smem_u32(smem) >> 4;
+            const uint32_t a16 = s16 | (136u << 16);
+            const uint32_t b16 = (s16 + 1024) | ((uint32_t)N << 16);
+            const uint32_t idesc = umma_idesc(N, 0);
+            go = 1;
+            const long long t0 = clock64();
+#pragma unroll 1
+            for (int i = 0; i < nm; i += 8) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (TS)
+                        umma_f16_ts(tmem_base + 256, tmem_base + (uint32_t)(8 * j), desc_hi | (uint64_t)(b16 + j * 2 * N), idesc, 1u);
+                    else
+                        umma_f16(tmem_base + 256, desc_hi | (uint64_t)(a16 + j), desc_hi | (uint64_t)(b16 + j * 2 * N), idesc, 1u);
+                }
+            }
+            const long long t1 = clock64();
+            umma_commit(&bar);
+            mbar_wait(&bar, 0);
+            const long long t2 = clock64();
+            done = 1;
+            out[0] = t1 - t0;
+            out[1] = t2 - t0;
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // readers: warps 4-7 (lane quarters 0-3) read 16 columns of an untouched TMEM region in a loop
+        while (!go) {
+        }
+        const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 448;
+        long long tmax = 0, tsum = 0;
+        int cnt = 0;
+        uint32_t acc = 0;
+        while (!done && cnt < 100000) {
+            uint32_t r[16];
+            const long long a = clock64();
+            if (RD == 0) {
+                tmem_ld16_nowait(lane_addr, r);
+                tmem_ld_wait();
+                acc += r[0] ^ r[7];
+            } else if (RD == 1) {  // broadcast 16-byte shared-memory load (the epilogues' bias reads)
+                uint4 v4;
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v4.x), "=r"(v4.y), "=r"(v4.z), "=r"(v4.w) : "r"(smem_u32(smem) + 60000 + (cnt & 3) * 16) : "memory");
+                acc += v4.x ^ v4.w;
+            } else {  // 16-byte store per lane (conflict-free), then a load to wait for it
+                const uint32_t ad = smem_u32(smem) + 61440 + (tid & 127) * 16;
+                uint4 v4;
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(ad), "r"(acc), "r"(1u), "r"(2u), "r"(3u) : "memory");
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v4.x), "=r"(v4.y), "=r"(v4.z), "=r"(v4.w) : "r"(ad) : "memory");
+                acc += v4.x ^ v4.w;
+            }
+            asm volatile("" ::"r"(acc) : "memory");
+            const long long b = clock64();
+            tsum += b - a;
+            tmax = (b - a) > tmax ? (b - a) : tmax;
+            ++cnt;
+        }
+        if ((tid & 31) == 0) {
+            out[2 + (warp - 4) * 3] = cnt;
+            out[3 + (warp - 4) * 3] = cnt ? tsum / cnt : 0;
+            out[4 + (warp - 4) * 3] = tmax;
+        }
+        if (acc == 0x1234567u) out[20] = acc;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+template <int N, bool TS, int RD>
+static int ld_under_mma() {
+    long long *d;
+    CK(cudaMalloc(&d, 32 * sizeof(long long)));
+    CK(cudaMemset(d, 0, 32 * sizeof(long long)));
+    auto kern = ld_under_mma_kernel<N, TS, RD>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    const int nm = 1024;
+    for (int rep = 0; rep < 2; ++rep) kern<<<1, 256, 65536>>>(d, nm);
+    CK(cudaDeviceSynchronize());
+    long long h[32];
+    CK(cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost));
+    printf("%s under %s MMAs N=%3d: MMAs issue %.1f / complete %.1f cycles each; reader warp 4: %lld loads, mean %lld, max %lld cycles per access\n",
+           RD == 0 ? "tcgen05.ld.x16" : RD == 1 ? "LDS.128 broadcast" : "STS.128 + LDS.128", TS ? "TS" : "SS", N, (double)h[0] / nm, (double)h[1] / nm, h[2], h[3], h[4]);
+    cudaFree(d);
+    return 0;
+}
+
 template <int N, int K>
 static int check(int a_col0) {
     float *d;
@@ -263,6 +375,13 @@ int main() {
     rate<32, false>();
     rate<64, false>();
     rate<128, false>();
+    ld_under_mma<64, false, 0>();
+    ld_under_mma<16, true, 0>();
+    ld_under_mma<64, false, 1>();
+    ld_under_mma<16, true, 1>();
+    ld_under_mma<64, false, 2>();
+    ld_under_mma<16, true, 2>();
+    ld_under_mma<128, false, 1>();
     ldst<false>(4);
     ldst<false>(8);
     ldst<true>(4);

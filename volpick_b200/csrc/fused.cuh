@@ -107,6 +107,9 @@ struct FzDecB2 {
     const uint16_t *blob;  // device: [group][blob_bytes / 2]
     float *y;              // (B, 3, L_out) probabilities
     int smem_bytes;
+    // fp32 biases per decoder, read through the constant bank (kernel parameter) so that the epilogues on the hand-over chain do
+    // not wait for the shared-memory pipe: decoder.convs.3 [64] | .4 [16] | .5 [32] | .6 [16]
+    float bias_c[3][128];
 };
 struct DecB2Plan {
     FzDecB2 p;

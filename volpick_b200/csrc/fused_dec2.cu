@@ -30,8 +30,9 @@
 // TMEM columns (512): [0, 128) A2, which also hosts the accumulators D0 / D1 of the NEXT item while A2 is dead; [128, 352) A3;
 // [352, 480) D2 / D3.  The issuer interleaves the shared-memory half of item n + 1 with the TMEM half of item n
 // (L2(n), L0(n+1), L3(n) first half, L1(n+1), L3(n) second half), so each epilogue runs under the other item's MMAs.
-// Warps: TMA loader, tcgen05 issuer, 4 epilogue warps A (D0 -> S1, D1 -> A2), 4 epilogue warps B (D2 -> A3, D3 -> head buffer),
-// 4 head warps (sigmoid(conv k11), 16 outputs per thread).  Hand-over by mbarriers only.
+// Warps (25): tcgen05 issuer; 8 epilogue warps A (D0 -> S1, D1 -> A2; they also issue the TMA load of the next item); 8 epilogue warps
+// B (D2 -> A3, D3 -> head buffer); 8 head warps (sigmoid(conv k11), 8 outputs per thread).  Two epilogue warps share a TMEM lane
+// quarter and split its columns.  Hand-over by mbarriers; the two halves of a group meet at one named barrier per item (halo exchange).
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -42,7 +43,7 @@
 
 namespace vp {
 
-constexpr int D2_THREADS = 32 * 14;
+constexpr int D2_THREADS = 32 * 25;
 constexpr int D2_LANE_LO = 4, D2_USE = 120;  // lanes [4, 124) of an item are valid at the output
 constexpr int D2_IN_ROWS = 132;              // input rows R0 - 2 .. R0 + 129
 constexpr int D2_S1_ROWS = 130;              // lanes -1 .. 128 of the 750 level (rows 0 and 129 stay zero)
@@ -54,7 +55,7 @@ constexpr int D2_B0 = 0, D2_B1 = 64, D2_B2 = 80, D2_B3 = 112, D2_HW = 128, D2_BI
 // -DVP_D2_PROF build (tools/build_variant.sh): every warp of CTA (0, 0) accumulates the cycles of its sections (waits by barrier,
 // work by epilogue) and decb2_launch prints them.  Empty in the product build.
 #ifdef VP_D2_PROF
-__device__ long long d2_prof_out[14 * 8];
+__device__ long long d2_prof_out[25 * 8];
 struct D2Prof {
     long long acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long t = 0;
@@ -183,6 +184,37 @@ __device__ __forceinline__ void d2_load16(const float *bias, uint32_t tacc, int 
     }
 }
 
+// the same with the 16 biases in registers (epilogues on the hand-over chain: no shared-memory access between tcgen05.ld and tcgen05.st)
+template <int NST>
+__device__ __forceinline__ void d2_load16r(const float (&bias)[16], uint32_t tacc, int col0, float (&v)[16]) {
+    uint32_t r[16], r2[NST > 0 ? 16 : 1];
+    tmem_ld16_nowait(tacc + (uint32_t)col0, r);
+    if constexpr (NST > 0) tmem_ld16_nowait(tacc + (uint32_t)(col0 + NST), r2);
+    tmem_ld_wait();
+#pragma unroll
+    for (int n = 0; n < 16; ++n) {
+        float a = __uint_as_float(r[n]);
+        if constexpr (NST > 0) a += __uint_as_float(r2[n]);
+        v[n] = fmaxf(a + bias[n], 0.f);
+    }
+}
+
+// edge exchange between the lane quarters: 8 + 8 packed registers of one sample as four 16-byte shared-memory accesses
+__device__ __forceinline__ void d2_post16(uint32_t *dst, const uint32_t (&h)[8], const uint32_t (&l)[8]) {
+    uint4 *d = reinterpret_cast<uint4 *>(dst);
+    d[0] = make_uint4(h[0], h[1], h[2], h[3]);
+    d[1] = make_uint4(h[4], h[5], h[6], h[7]);
+    d[2] = make_uint4(l[0], l[1], l[2], l[3]);
+    d[3] = make_uint4(l[4], l[5], l[6], l[7]);
+}
+__device__ __forceinline__ void d2_fetch16(const uint32_t *src, bool have, uint32_t (&h)[8], uint32_t (&l)[8]) {
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+    const uint4 a = have ? s4[0] : z, b = have ? s4[1] : z, c = have ? s4[2] : z, d = have ? s4[3] : z;
+    h[0] = a.x, h[1] = a.y, h[2] = a.z, h[3] = a.w, h[4] = b.x, h[5] = b.y, h[6] = b.z, h[7] = b.w;
+    l[0] = c.x, l[1] = c.y, l[2] = c.z, l[3] = c.w, l[4] = d.x, l[5] = d.y, l[6] = d.z, l[7] = d.w;
+}
+
 // 16 channels of one sample -> the 8 + 8 packed registers of its TMEM slot (zeros when the row lies outside the sequence)
 template <int SPLIT>
 __device__ __forceinline__ void d2_pack16(const float (&v)[16], bool valid, uint32_t (&h)[8], uint32_t (&l)[8]) {
@@ -208,37 +240,31 @@ __device__ __forceinline__ void d2_st_slot(uint32_t tl, uint32_t col_hi, uint32_
 // bits 3-4 spreads the eight lanes of a quarter warp over the eight 16-byte bank groups.
 __device__ __forceinline__ int d2_unit(int u) { return u ^ ((u >> 3) & 3); }
 
-// sigmoid(conv k11, 8 -> 1): head thread e = the 16 outputs of lane 4 + e.
+// sigmoid(conv k11, 8 -> 1): head thread e = 8 outputs (half a lane: outputs 8 (e & 1) .. of lane 4 + e / 2).  Rolled over the channels
+// on purpose: fully unrolled, the head alone was 40 KB of straight-line code executed once per item next to the other warp roles with
+// bodies of the same size, and the instruction caches (6 KB L0, 32 KB L1.5) served none of them (9.24 -> 7.38 ms per station-day
+// from rolling the loops of this kernel alone).
 __device__ __forceinline__ void d2_head(const FzDecB2 &p, const float *hw /*shared: [8][12] weights, bias at [96]*/, int g, int b, int R0,
                                         int e, const float *buf) {
-    const int row = R0 + D2_LANE_LO + e;
-    if (e >= D2_USE || (unsigned)row >= (unsigned)p.T0) return;
-    const int u0 = 4 * (D2_LANE_LO + e) - 2;  // unit of sample 16 (4 + e) - 8
-    float acc[16];
+    const int row = R0 + D2_LANE_LO + (e >> 1);
+    if (e >= 2 * D2_USE || (unsigned)row >= (unsigned)p.T0) return;
+    const int u0 = 4 * D2_LANE_LO + 2 * e - 2;  // unit of sample (first output) - 8
+    float acc[8];
 #pragma unroll
-    for (int o = 0; o < 16; ++o) acc[o] = hw[96];
-    int uo[8];
+    for (int o = 0; o < 8; ++o) acc[o] = hw[96];
+    int uo[6];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) uo[q] = 4 * d2_unit(u0 + q);
-    float4 cur[8], nxt[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) cur[q] = *reinterpret_cast<const float4 *>(buf + uo[q]);
-    // Rolled over the channels on purpose: fully unrolled, the head alone was 40 KB of straight-line code executed once per item,
-    // next to four other warp roles with bodies of the same size -- the instruction caches (6 KB L0, 32 KB L1.5) served none of them.
+    for (int q = 0; q < 6; ++q) uo[q] = 4 * d2_unit(u0 + q);
 #pragma unroll 1
     for (int c = 0; c < 8; ++c) {
-        {
-            const int cn = (c + 1) & 7;  // the last iteration re-reads channel 0 (unused)
+        float xv[24];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) nxt[q] = *reinterpret_cast<const float4 *>(buf + (size_t)cn * D2_RP + uo[q]);
-        }
-        float xv[32];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            xv[4 * q] = cur[q].x;
-            xv[4 * q + 1] = cur[q].y;
-            xv[4 * q + 2] = cur[q].z;
-            xv[4 * q + 3] = cur[q].w;
+        for (int q = 0; q < 6; ++q) {
+            const float4 x4 = *reinterpret_cast<const float4 *>(buf + (size_t)c * D2_RP + uo[q]);
+            xv[4 * q] = x4.x;
+            xv[4 * q + 1] = x4.y;
+            xv[4 * q + 2] = x4.z;
+            xv[4 * q + 3] = x4.w;
         }
         const float4 w0 = *reinterpret_cast<const float4 *>(hw + c * 12), w1 = *reinterpret_cast<const float4 *>(hw + c * 12 + 4),
                      w2 = *reinterpret_cast<const float4 *>(hw + c * 12 + 8);
@@ -247,14 +273,12 @@ __device__ __forceinline__ void d2_head(const FzDecB2 &p, const float *hw /*shar
         for (int k = 0; k < 11; ++k) {
             const float w = wk[k];
 #pragma unroll
-            for (int o = 0; o < 16; ++o) acc[o] = fmaf(w, xv[o + k + 3], acc[o]);  // xv[0] = sample (first output) - 8
+            for (int o = 0; o < 8; ++o) acc[o] = fmaf(w, xv[o + k + 3], acc[o]);  // xv[0] = sample (first output) - 8
         }
-#pragma unroll
-        for (int q = 0; q < 8; ++q) cur[q] = nxt[q];
     }
-    float *yb = p.y + ((size_t)b * 3 + g) * p.L_out + (size_t)16 * row;
+    float *yb = p.y + ((size_t)b * 3 + g) * p.L_out + (size_t)16 * row + 8 * (e & 1);
 #pragma unroll
-    for (int o = 0; o < 16; o += 4) {
+    for (int o = 0; o < 8; o += 4) {
         float4 o4;
         o4.x = 1.f / (1.f + expf(-acc[o]));
         o4.y = 1.f / (1.f + expf(-acc[o + 1]));
@@ -265,12 +289,12 @@ __device__ __forceinline__ void d2_head(const FzDecB2 &p, const float *hw /*shar
 }
 
 // ------------------------------------------------------------------------------------------ the kernel
+// Warps: 0 issuer; 1-8 epilogue A (two per TMEM lane quarter: quarter q = warp % 4, half h); 9-16 epilogue B; 17-24 head.
 template <int SPLIT>
 __global__ void __launch_bounds__(D2_THREADS, 1) decb2_kernel(const __grid_constant__ FzDecB2K K) {
     const FzDecB2 &p = K.p;
     extern __shared__ __align__(128) uint8_t d2_smem[];
-    __shared__ __align__(8) uint64_t in_full, in_empty, d0_full, s1_full, d1_full, a2_full, d2_full[4], a3_full, d3_full[4], d23_free, head_go,
-        head_done;
+    __shared__ __align__(8) uint64_t in_full, d0_full, s1_full, d1_full, a2_full, d2_full[4], a3_full, d3_full[4], d23_free, head_go, head_done;
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -281,19 +305,18 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decb2_kernel(const __grid_const
 
     if (tid == 0) {
         mbar_init(&in_full, 1);
-        mbar_init(&in_empty, 1);
         mbar_init(&d0_full, 1);
-        mbar_init(&s1_full, 4);
+        mbar_init(&s1_full, 8);
         mbar_init(&d1_full, 1);
-        mbar_init(&a2_full, 4);
+        mbar_init(&a2_full, 8);
         for (int i = 0; i < 4; ++i) {
             mbar_init(&d2_full[i], 1);
             mbar_init(&d3_full[i], 1);
         }
-        mbar_init(&a3_full, 4);
-        mbar_init(&d23_free, 4);
-        mbar_init(&head_go, 4);
-        mbar_init(&head_done, 4);
+        mbar_init(&a3_full, 8);
+        mbar_init(&d23_free, 8);
+        mbar_init(&head_go, 8);
+        mbar_init(&head_done, 8);
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(&tmem_base_s, 512);
@@ -312,21 +335,17 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decb2_kernel(const __grid_const
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
     const float *bias = reinterpret_cast<const float *>(d2_smem + p.bias_off);
+    // the 132 input rows of item k as one TMA box (rows outside the sequence arrive as zeros); issued by one thread of epilogue A as
+    // soon as the previous item's first layer has retired (its accumulator is full), so there is no loader warp and no "empty" barrier
+    auto load_item = [&](int k) {
+        const int it = blockIdx.x + k * gridDim.x;
+        const int b = it / p.tiles_per_seq, j = it - b * p.tiles_per_seq;
+        const int R0 = p.row_off0 + D2_USE * j - D2_LANE_LO;
+        mbar_arrive_expect_tx(&in_full, (uint32_t)(D2_IN_ROWS * 4 * 16 * SPLIT));
+        tma_load_5d(sbase + p.in_off, &K.x_map, &in_full, 0, R0 - 2, g * p.B + b, 0, 0);
+    };
 
     if (warp == 0) {
-        // ================= loader: the 132 input rows of the next item as one TMA box (rows outside the sequence arrive as zeros)
-        if (lane == 0) {
-            const uint32_t bytes = (uint32_t)(D2_IN_ROWS * 4 * 16 * SPLIT);
-            for (int k = 0; k < n_my; ++k) {
-                const int it = blockIdx.x + k * gridDim.x;
-                const int b = it / p.tiles_per_seq, j = it - b * p.tiles_per_seq;
-                const int R0 = p.row_off0 + D2_USE * j - D2_LANE_LO;
-                mbar_wait(&in_empty, (k & 1) ^ 1);
-                mbar_arrive_expect_tx(&in_full, bytes);
-                tma_load_5d(sbase + p.in_off, &K.x_map, &in_full, 0, R0 - 2, g * p.B + b, 0, 0);
-            }
-        }
-    } else if (warp == 1) {
         // ================= tcgen05 issuer
         const uint32_t fmt = SPLIT == 2 ? 0u : 1u;
         const uint32_t id16 = umma_idesc(16, fmt), id32 = umma_idesc(32, fmt), id64 = umma_idesc(64, fmt), id128 = umma_idesc(128, fmt);
@@ -338,19 +357,16 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decb2_kernel(const __grid_const
         auto issue_L0 = [&](int m) {  // dec3: in (shared) -> D0 = columns [0, 64)
             mbar_wait(&in_full, m & 1);
             prof.lap(0);
-            fence_proxy_async();
             tc_fence_after();
             if (elect_one()) {
                 d2_conv_tile<64, SPLIT, 5, 2>(tmem_base + D2_COL_A2, in16, D2_IN_ROWS, w0, id64);
                 umma_commit(&d0_full);
-                umma_commit(&in_empty);
             }
             __syncwarp();
         };
         auto issue_L1 = [&](int m) {  // dec4 folded: S1 (shared) -> D1 = columns [0, 64) (+ [64, 128): the stacked W_lo half)
             mbar_wait(&s1_full, m & 1);
             prof.lap(1);
-            fence_proxy_async();
             tc_fence_after();
             if (elect_one()) {
                 if constexpr (SPLIT == 2)
@@ -419,36 +435,42 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decb2_kernel(const __grid_const
             prof.lap(5);
         }
         prof.flush(warp, lane);
-    } else if (warp < 6) {
-        // ================= epilogue warps A: D0 -> S1 (shared memory), D1 -> A2 (tensor memory)
-        const int q = warp & 3, r = q * 32 + lane;
+    } else if (warp < 9) {
+        // ================= epilogue warps A: D0 -> S1 (shared memory), D1 -> A2 (tensor memory).  Half h = phase (E0) / sample pair (E1).
+        const int q = warp & 3, h = (warp - 1) >> 2, r = q * 32 + lane;
         const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
         uint32_t *xa = reinterpret_cast<uint32_t *>(d2_smem + p.xch_off);  // [parity][quarter][side][sample 2][16]
         uint8_t *s1 = d2_smem + p.s1_off;
+        float b1r[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) b1r[i] = p.bias_c[g][D2_B1 + i];
         D2Prof prof;  // 0 d0_full, 1 d1_full, 2 d2_full[3], 3 E0, 4 E1
         prof.start();
+        if (warp == 1 && lane == 0 && n_my > 0) load_item(0);
         for (int m = 0; m < n_my; ++m) {
             const int it = blockIdx.x + m * gridDim.x;
             const int b = it / p.tiles_per_seq, j = it - b * p.tiles_per_seq;
             const int R0 = p.row_off0 + D2_USE * j - D2_LANE_LO;
             const bool valid = (unsigned)(R0 + r) < (unsigned)p.T0;
-            // ---- E0
+            // ---- E0: this warp converts phase h (accumulator columns 32 h .. 32 h + 31)
             mbar_wait(&d0_full, m & 1);
             prof.lap(0);
+            if (warp == 1 && lane == 0 && m + 1 < n_my) load_item(m + 1);  // dec3 has retired: the input box is free
             tc_fence_after();
 #pragma unroll 1
-            for (int c0 = 0; c0 < 64; c0 += 16) {
+            for (int cc = 0; cc < 2; ++cc) {
+                const int c0 = 32 * h + 16 * cc;
                 float v[16];
-                d2_load16<0>(bias + D2_B0 + c0, tl + D2_COL_A2, c0, v);
-                uint32_t h[8], l[8];
-                d2_pack16<SPLIT>(v, valid, h, l);
-                const int pl = (c0 >> 5) * 4 + ((c0 & 31) >> 3);  // plane' = phase * 4 + channel plane
+                d2_load16<0>(&p.bias_c[g][D2_B0 + c0], tl + D2_COL_A2, c0, v);
+                uint32_t hh[8], ll[8];
+                d2_pack16<SPLIT>(v, valid, hh, ll);
+                const int pl = h * 4 + 2 * cc;  // plane' = phase * 4 + channel plane
                 uint8_t *d = s1 + ((size_t)pl * D2_S1_ROWS + r + 1) * 16;
-                *reinterpret_cast<uint4 *>(d) = make_uint4(h[0], h[1], h[2], h[3]);
-                *reinterpret_cast<uint4 *>(d + (size_t)D2_S1_ROWS * 16) = make_uint4(h[4], h[5], h[6], h[7]);
+                *reinterpret_cast<uint4 *>(d) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+                *reinterpret_cast<uint4 *>(d + (size_t)D2_S1_ROWS * 16) = make_uint4(hh[4], hh[5], hh[6], hh[7]);
                 if (SPLIT == 2) {
-                    *reinterpret_cast<uint4 *>(d + (size_t)8 * D2_S1_ROWS * 16) = make_uint4(l[0], l[1], l[2], l[3]);
-                    *reinterpret_cast<uint4 *>(d + (size_t)9 * D2_S1_ROWS * 16) = make_uint4(l[4], l[5], l[6], l[7]);
+                    *reinterpret_cast<uint4 *>(d + (size_t)8 * D2_S1_ROWS * 16) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+                    *reinterpret_cast<uint4 *>(d + (size_t)9 * D2_S1_ROWS * 16) = make_uint4(ll[4], ll[5], ll[6], ll[7]);
                 }
             }
             fence_proxy_async();
@@ -456,58 +478,58 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decb2_kernel(const __grid_const
             __syncwarp();
             if (lane == 0) mbar_arrive(&s1_full);
             prof.lap(3);
-            // ---- E1: D1 sits in the A2 columns -> read all of it before the first store
+            // ---- E1: this warp converts samples 2 h, 2 h + 1.  D1 sits in the A2 columns: the own slots (columns 16 .. 47 / 80 .. 111)
+            // may be stored right away -- warp h = 0 reads columns 0 .. 31 / 64 .. 95 and stores 16 .. 31 / 80 .. 95, warp h = 1 reads
+            // 32 .. 63 / 96 .. 127 and stores 32 .. 47 / 96 .. 111 -- the halo slots only after the group barrier (everyone has read).
             mbar_wait(&d1_full, m & 1);
             prof.lap(1);
             if (m > 0) mbar_wait(&d2_full[3], (m - 1) & 1);  // dec5 of the previous item has read A2
             prof.lap(2);
             tc_fence_after();
-            uint32_t oh[4][8], ol[4][8];
-#pragma unroll
-            for (int s = 0; s < 4; ++s) {
-                float v[16];
-                d2_load16<SPLIT == 2 ? 64 : 0>(bias + D2_B1, tl + D2_COL_A2, 16 * s, v);
-                d2_pack16<SPLIT>(v, valid, oh[s], ol[s]);
-            }
-            uint32_t *xw = xa + (size_t)(((m & 1) * 4 + q) * 2) * 32;
-            if (lane == 0 || lane == 31) {
-                uint32_t *d = xw + (lane == 31 ? 32 : 0);
-#pragma unroll
-                for (int s = 0; s < 2; ++s)
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        d[s * 16 + i] = lane == 31 ? oh[2 + s][i] : oh[s][i];
-                        d[s * 16 + 8 + i] = lane == 31 ? ol[2 + s][i] : ol[s][i];
-                    }
-            }
-#pragma unroll
-            for (int s = 0; s < 4; ++s) d2_st_slot<SPLIT>(tl, D2_COL_A2 + 8 * (2 + s), D2_A2_LO, oh[s], ol[s]);
-            named_bar_sync(1, 128);
-            const uint32_t *xl = xa + (size_t)(((m & 1) * 4 + (q + 3) % 4) * 2 + 1) * 32;  // previous quarter's lane 31: its samples 2, 3
-            const uint32_t *xr = xa + (size_t)(((m & 1) * 4 + (q + 1) % 4) * 2) * 32;      // next quarter's lane 0: its samples 0, 1
+            uint32_t oh[2][8], ol[2][8];
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
-                uint32_t h[8], l[8];
+                float v[16];
+                d2_load16r<SPLIT == 2 ? 64 : 0>(b1r, tl + D2_COL_A2, 16 * (2 * h + s), v);
+                d2_pack16<SPLIT>(v, valid, oh[s], ol[s]);
+            }
+            // edge lanes post what the neighbour quarter needs: lane 0 of h = 0 its samples 0, 1; lane 31 of h = 1 its samples 2, 3
+            uint32_t *xw = xa + (size_t)(((m & 1) * 4 + q) * 2 + h) * 32;
+            if (lane == (h ? 31 : 0)) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {  // left halo: slots 0, 1 = samples 2, 3 of lane r - 1
-                    h[i] = __shfl_up_sync(0xffffffffu, oh[2 + s][i], 1);
-                    l[i] = __shfl_up_sync(0xffffffffu, ol[2 + s][i], 1);
-                    if (lane == 0) {
-                        h[i] = q > 0 ? xl[s * 16 + i] : 0u;
-                        l[i] = q > 0 ? xl[s * 16 + 8 + i] : 0u;
-                    }
-                }
-                d2_st_slot<SPLIT>(tl, D2_COL_A2 + 8 * s, D2_A2_LO, h, l);
+                for (int s = 0; s < 2; ++s) d2_post16(xw + s * 16, oh[s], ol[s]);
+            }
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {  // right halo: slots 6, 7 = samples 0, 1 of lane r + 1
-                    h[i] = __shfl_down_sync(0xffffffffu, oh[s][i], 1);
-                    l[i] = __shfl_down_sync(0xffffffffu, ol[s][i], 1);
-                    if (lane == 31) {
-                        h[i] = q < 3 ? xr[s * 16 + i] : 0u;
-                        l[i] = q < 3 ? xr[s * 16 + 8 + i] : 0u;
+            for (int s = 0; s < 2; ++s) d2_st_slot<SPLIT>(tl, D2_COL_A2 + 8 * (2 + 2 * h + s), D2_A2_LO, oh[s], ol[s]);
+            tc_fence_before();
+            named_bar_sync(1, 256);
+            tc_fence_after();
+            if (h) {  // left halo: slots 0, 1 = samples 2, 3 of lane r - 1
+                const uint32_t *xl = xa + (size_t)(((m & 1) * 4 + (q + 3) % 4) * 2 + 1) * 32;
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    uint32_t hh[8], ll[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        hh[i] = __shfl_up_sync(0xffffffffu, oh[s][i], 1);
+                        ll[i] = __shfl_up_sync(0xffffffffu, ol[s][i], 1);
                     }
+                    if (lane == 0) d2_fetch16(xl + s * 16, q > 0, hh, ll);
+                    d2_st_slot<SPLIT>(tl, D2_COL_A2 + 8 * s, D2_A2_LO, hh, ll);
                 }
-                d2_st_slot<SPLIT>(tl, D2_COL_A2 + 8 * (6 + s), D2_A2_LO, h, l);
+            } else {  // right halo: slots 6, 7 = samples 0, 1 of lane r + 1
+                const uint32_t *xr = xa + (size_t)(((m & 1) * 4 + (q + 1) % 4) * 2) * 32;
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    uint32_t hh[8], ll[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        hh[i] = __shfl_down_sync(0xffffffffu, oh[s][i], 1);
+                        ll[i] = __shfl_down_sync(0xffffffffu, ol[s][i], 1);
+                    }
+                    if (lane == 31) d2_fetch16(xr + s * 16, q < 3, hh, ll);
+                    d2_st_slot<SPLIT>(tl, D2_COL_A2 + 8 * (6 + s), D2_A2_LO, hh, ll);
+                }
             }
             tmem_st_wait();
             tc_fence_before();
@@ -516,12 +538,18 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decb2_kernel(const __grid_const
             prof.lap(4);
         }
         prof.flush(warp, lane);
-    } else if (warp < 10) {
-        // ================= epilogue warps B: D2 -> A3 (tensor memory), D3 -> head buffer (shared memory)
-        const int q = warp & 3, r = q * 32 + lane;
+    } else if (warp < 17) {
+        // ================= epilogue warps B: D2 -> A3 (tensor memory), D3 -> head buffer (shared memory).  Half h = phase (E2) / block
+        // pairs 2 h, 2 h + 1 (E3).
+        const int q = warp & 3, h = (warp - 9) >> 2, r = q * 32 + lane;
         const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
         uint32_t *xb = reinterpret_cast<uint32_t *>(d2_smem + p.xch_off + 2048);  // [parity][quarter][side][sample 3][16]
         float *hbuf = reinterpret_cast<float *>(d2_smem + p.head_off);
+        float b2r[16], b3r[8];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) b2r[i] = p.bias_c[g][D2_B2 + 16 * h + i];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) b3r[i] = p.bias_c[g][D2_B3 + i];
         D2Prof prof;  // 0 d2_full, 1 head_done, 2 d3_full, 3 E2 blocks, 4 halo exchange, 5 E3
         prof.start();
         for (int n = 0; n < n_my; ++n) {
@@ -529,68 +557,60 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decb2_kernel(const __grid_const
             const int b = it / p.tiles_per_seq, j = it - b * p.tiles_per_seq;
             const int R0 = p.row_off0 + D2_USE * j - D2_LANE_LO;
             const bool valid = (unsigned)(R0 + r) < (unsigned)p.T0;
-            // ---- E2: block bb = samples 2 bb, 2 bb + 1 of the lane's eight 3000-level samples -> slots 3 + sample
+            // ---- E2: block bb, phase h = sample s = 2 bb + h of the lane's eight 3000-level samples -> slot 3 + s
             uint32_t *xw = xb + (size_t)(((n & 1) * 4 + q) * 2) * 48;
 #pragma unroll 1
             for (int bb = 0; bb < 4; ++bb) {
                 mbar_wait(&d2_full[bb], n & 1);
                 prof.lap(0);
                 tc_fence_after();
-#pragma unroll
-                for (int ph = 0; ph < 2; ++ph) {
-                    float v[16];
-                    d2_load16<0>(bias + D2_B2 + 16 * ph, tl + D2_COL_D23, 32 * bb + 16 * ph, v);
-                    uint32_t h[8], l[8];
-                    d2_pack16<SPLIT>(v, valid, h, l);
-                    const int s = 2 * bb + ph;
-                    d2_st_slot<SPLIT>(tl, D2_COL_A3 + 8 * (3 + s), D2_A3_LO, h, l);
-                    // the quarter's edge lanes post what their neighbour quarter needs: lane 0 samples 0-2, lane 31 samples 5-7
-                    if (s < 3 && lane == 0) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) xw[s * 16 + i] = h[i], xw[s * 16 + 8 + i] = l[i];
-                    }
-                    if (s >= 5 && lane == 31) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) xw[48 + (s - 5) * 16 + i] = h[i], xw[48 + (s - 5) * 16 + 8 + i] = l[i];
-                    }
-                }
+                float v[16];
+                d2_load16r<0>(b2r, tl + D2_COL_D23, 32 * bb + 16 * h, v);
+                uint32_t hh[8], ll[8];
+                d2_pack16<SPLIT>(v, valid, hh, ll);
+                const int s = 2 * bb + h;
+                d2_st_slot<SPLIT>(tl, D2_COL_A3 + 8 * (3 + s), D2_A3_LO, hh, ll);
+                // the quarter's edge lanes post what their neighbour quarter needs: lane 0 samples 0-2, lane 31 samples 5-7
+                if (s < 3 && lane == 0) d2_post16(xw + s * 16, hh, ll);
+                if (s >= 5 && lane == 31) d2_post16(xw + 48 + (s - 5) * 16, hh, ll);
                 prof.lap(3);
             }
             tmem_st_wait();
-            named_bar_sync(2, 128);
-            const uint32_t *xl = xb + (size_t)(((n & 1) * 4 + (q + 3) % 4) * 2 + 1) * 48;  // previous quarter's lane 31: samples 5-7
-            const uint32_t *xr = xb + (size_t)(((n & 1) * 4 + (q + 1) % 4) * 2) * 48;      // next quarter's lane 0: samples 0-2
+            tc_fence_before();
+            named_bar_sync(2, 256);
+            tc_fence_after();
+            if (h == 0) {  // right halo: slot 11 + i = sample i of lane r + 1 (its slot 3 + i)
+                const uint32_t *xr = xb + (size_t)(((n & 1) * 4 + (q + 1) % 4) * 2) * 48;
 #pragma unroll 1
-            for (int i3 = 0; i3 < 3; ++i3) {
-                uint32_t h[8], l[8];
-                // right halo: slot 11 + i = sample i of lane r + 1 (its slot 3 + i)
-                tmem_ld8_nowait(tl + D2_COL_A3 + 8 * (3 + i3), h);
-                if (SPLIT == 2) tmem_ld8_nowait(tl + D2_COL_A3 + D2_A3_LO + 8 * (3 + i3), l);
-                tmem_ld_wait();
+                for (int i3 = 0; i3 < 3; ++i3) {
+                    uint32_t hh[8], ll[8];
+                    tmem_ld8_nowait(tl + D2_COL_A3 + 8 * (3 + i3), hh);
+                    if (SPLIT == 2) tmem_ld8_nowait(tl + D2_COL_A3 + D2_A3_LO + 8 * (3 + i3), ll);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    h[i] = __shfl_down_sync(0xffffffffu, h[i], 1);
-                    if (SPLIT == 2) l[i] = __shfl_down_sync(0xffffffffu, l[i], 1);
-                    if (lane == 31) {
-                        h[i] = q < 3 ? xr[i3 * 16 + i] : 0u;
-                        if (SPLIT == 2) l[i] = q < 3 ? xr[i3 * 16 + 8 + i] : 0u;
+                    for (int i = 0; i < 8; ++i) {
+                        hh[i] = __shfl_down_sync(0xffffffffu, hh[i], 1);
+                        if (SPLIT == 2) ll[i] = __shfl_down_sync(0xffffffffu, ll[i], 1);
                     }
+                    if (lane == 31) d2_fetch16(xr + i3 * 16, q < 3, hh, ll);
+                    d2_st_slot<SPLIT>(tl, D2_COL_A3 + 8 * (11 + i3), D2_A3_LO, hh, ll);
                 }
-                d2_st_slot<SPLIT>(tl, D2_COL_A3 + 8 * (11 + i3), D2_A3_LO, h, l);
-                // left halo: slot i = sample 5 + i of lane r - 1 (its slot 8 + i)
-                tmem_ld8_nowait(tl + D2_COL_A3 + 8 * (8 + i3), h);
-                if (SPLIT == 2) tmem_ld8_nowait(tl + D2_COL_A3 + D2_A3_LO + 8 * (8 + i3), l);
-                tmem_ld_wait();
+            } else {  // left halo: slot i = sample 5 + i of lane r - 1 (its slot 8 + i)
+                const uint32_t *xl = xb + (size_t)(((n & 1) * 4 + (q + 3) % 4) * 2 + 1) * 48;
+#pragma unroll 1
+                for (int i3 = 0; i3 < 3; ++i3) {
+                    uint32_t hh[8], ll[8];
+                    tmem_ld8_nowait(tl + D2_COL_A3 + 8 * (8 + i3), hh);
+                    if (SPLIT == 2) tmem_ld8_nowait(tl + D2_COL_A3 + D2_A3_LO + 8 * (8 + i3), ll);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    h[i] = __shfl_up_sync(0xffffffffu, h[i], 1);
-                    if (SPLIT == 2) l[i] = __shfl_up_sync(0xffffffffu, l[i], 1);
-                    if (lane == 0) {
-                        h[i] = q > 0 ? xl[i3 * 16 + i] : 0u;
-                        if (SPLIT == 2) l[i] = q > 0 ? xl[i3 * 16 + 8 + i] : 0u;
+                    for (int i = 0; i < 8; ++i) {
+                        hh[i] = __shfl_up_sync(0xffffffffu, hh[i], 1);
+                        if (SPLIT == 2) ll[i] = __shfl_up_sync(0xffffffffu, ll[i], 1);
                     }
+                    if (lane == 0) d2_fetch16(xl + i3 * 16, q > 0, hh, ll);
+                    d2_st_slot<SPLIT>(tl, D2_COL_A3 + 8 * i3, D2_A3_LO, hh, ll);
                 }
-                d2_st_slot<SPLIT>(tl, D2_COL_A3 + 8 * i3, D2_A3_LO, h, l);
             }
             tmem_st_wait();
             tc_fence_before();
@@ -601,7 +621,8 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decb2_kernel(const __grid_const
             if (n > 0) mbar_wait(&head_done, (n - 1) & 1);
             prof.lap(1);
 #pragma unroll 1
-            for (int bp = 0; bp < 4; ++bp) {
+            for (int bq = 0; bq < 2; ++bq) {
+                const int bp = 2 * h + bq;
                 mbar_wait(&d3_full[bp], n & 1);
                 prof.lap(2);
                 tc_fence_after();
@@ -610,15 +631,13 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decb2_kernel(const __grid_const
                 tmem_ld16_nowait(tl + D2_COL_D23 + 32 * bp + 16, rb);  // samples 4 bp + 2, 4 bp + 3
                 tmem_ld_wait();
                 float *d = hbuf + 4 * d2_unit(4 * r + bp);
-                const float4 b0 = *reinterpret_cast<const float4 *>(bias + D2_B3), b1 = *reinterpret_cast<const float4 *>(bias + D2_B3 + 4);
-                const float bb8[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     float4 o;
-                    o.x = valid ? fmaxf(__uint_as_float(ra[c]) + bb8[c], 0.f) : 0.f;
-                    o.y = valid ? fmaxf(__uint_as_float(ra[8 + c]) + bb8[c], 0.f) : 0.f;
-                    o.z = valid ? fmaxf(__uint_as_float(rb[c]) + bb8[c], 0.f) : 0.f;
-                    o.w = valid ? fmaxf(__uint_as_float(rb[8 + c]) + bb8[c], 0.f) : 0.f;
+                    o.x = valid ? fmaxf(__uint_as_float(ra[c]) + b3r[c], 0.f) : 0.f;
+                    o.y = valid ? fmaxf(__uint_as_float(ra[8 + c]) + b3r[c], 0.f) : 0.f;
+                    o.z = valid ? fmaxf(__uint_as_float(rb[c]) + b3r[c], 0.f) : 0.f;
+                    o.w = valid ? fmaxf(__uint_as_float(rb[8 + c]) + b3r[c], 0.f) : 0.f;
                     *reinterpret_cast<float4 *>(d + (size_t)c * D2_RP) = o;
                 }
                 prof.lap(5);
@@ -633,7 +652,7 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decb2_kernel(const __grid_const
         prof.flush(warp, lane);
     } else {
         // ================= head warps: sigmoid(conv k11) of item n while the pipeline runs item n + 1
-        const int e = (warp - 10) * 32 + lane;
+        const int e = (warp - 17) * 32 + lane;
         const float *hbuf = reinterpret_cast<const float *>(d2_smem + p.head_off);
         D2Prof prof;  // 0 head_go, 1 head
         prof.start();
@@ -758,6 +777,10 @@ int decb2_build(DecB2Plan &plan, const TcLayer *dec, const float *const *w4, con
                         w1[(size_t)blk * blk1 + ((size_t)kh * 64 + n) * 8 + e] = hi;
                     }
                 }
+        for (int n = 0; n < 64; ++n) p.bias_c[g][D2_B0 + n] = L0.bias[(size_t)g * 64 + n];
+        for (int n = 0; n < 16; ++n) p.bias_c[g][D2_B1 + n] = b4[g] ? b4[g][n] : 0.f;
+        for (int n = 0; n < 32; ++n) p.bias_c[g][D2_B2 + n] = L2.bias[(size_t)g * 32 + n];
+        for (int n = 0; n < 16; ++n) p.bias_c[g][D2_B3 + n] = L3.bias[(size_t)g * 16 + n];
         float *bd = reinterpret_cast<float *>(dst + rb / 2);
         for (int n = 0; n < 64; ++n) bd[D2_B0 + n] = L0.bias[(size_t)g * 64 + n];
         for (int n = 0; n < 16; ++n) bd[D2_B1 + n] = b4[g] ? b4[g][n] : 0.f;
@@ -805,13 +828,13 @@ static int decb2_launch_t(const FzDecB2 &p, dim3 grid, cudaStream_t s) {
 #ifdef VP_D2_PROF
     {
         cudaStreamSynchronize(s);
-        long long h[14 * 8];
+        long long h[25 * 8];
         cudaMemcpyFromSymbol(h, d2_prof_out, sizeof(h));
         const int n_items = p.B * p.tiles_per_seq, n_my = (n_items - 1) / (int)grid.x + 1;
-        static const char *role[14] = {"loader", "issuer", "epiA", "epiA", "epiA", "epiA", "epiB", "epiB", "epiB", "epiB", "head", "head", "head", "head"};
+        auto role = [](int w) { return w == 0 ? "issuer" : w < 9 ? "epiA" : w < 17 ? "epiB" : "head"; };
         fprintf(stderr, "[decb2 prof] split %d, %d items per CTA; cycles per item by section\n", SPLIT, n_my);
-        for (int w = 1; w < 14; ++w) {
-            fprintf(stderr, "  warp %2d %-6s", w, role[w]);
+        for (int w = 0; w < 25; w += (w == 0 ? 1 : 4)) {
+            fprintf(stderr, "  warp %2d %-6s", w, role(w));
             for (int i = 0; i < 8; ++i) fprintf(stderr, " %8.0f", (double)h[w * 8 + i] / n_my);
             fprintf(stderr, "\n");
         }
