@@ -235,23 +235,40 @@ __device__ __forceinline__ void d2_st_slot(uint32_t tl, uint32_t col_hi, uint32_
     if (SPLIT == 2) tmem_st8(tl + col_hi + lo_off, l);
 }
 
+// d += (a0, a1) * w: one FFMA2 (sm_100: two fp32 FMAs per instruction; the scalar multiplier is broadcast)
+__device__ __forceinline__ void d2_ffma2(float2 &d, float a0, float a1, float w) {
+    unsigned long long dd, aa, ww;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(dd) : "f"(d.x), "f"(d.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(aa) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(ww) : "f"(w));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(dd) : "l"(aa), "l"(ww));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(dd));
+}
+
 // Head buffer: fp32 planar [c][sample], addressed in 16-byte units of 4 samples.  Both its writers (lane r stores unit 4 r + bp)
 // and its readers (head thread e loads units 14 + 4 e + q) have a lane stride of four units; XOR-ing the low two unit bits with
 // bits 3-4 spreads the eight lanes of a quarter warp over the eight 16-byte bank groups.
 __device__ __forceinline__ int d2_unit(int u) { return u ^ ((u >> 3) & 3); }
 
-// sigmoid(conv k11, 8 -> 1): head thread e = 8 outputs (half a lane: outputs 8 (e & 1) .. of lane 4 + e / 2).  Rolled over the channels
-// on purpose: fully unrolled, the head alone was 40 KB of straight-line code executed once per item next to the other warp roles with
-// bodies of the same size, and the instruction caches (6 KB L0, 32 KB L1.5) served none of them (9.24 -> 7.38 ms per station-day
-// from rolling the loops of this kernel alone).
-__device__ __forceinline__ void d2_head(const FzDecB2 &p, const float *hw /*shared: [8][12] weights, bias at [96]*/, int g, int b, int R0,
-                                        int e, const float *buf) {
-    const int row = R0 + D2_LANE_LO + (e >> 1);
-    if (e >= 2 * D2_USE || (unsigned)row >= (unsigned)p.T0) return;
-    const int u0 = 4 * D2_LANE_LO + 2 * e - 2;  // unit of sample (first output) - 8
-    float acc[8];
+// sigmoid(conv k11, 8 -> 1): head thread (rr, half) = the outputs 8 half .. 8 half + 7 of lane 4 + rr.  Consecutive lanes of a warp are
+// consecutive TMEM lanes (16 samples = four 16-byte units apart, the stride d2_unit() is conflict-free for); the two halves of a lane
+// run in different warps.  Weights come through the constant bank.  Rolled over the channels on purpose: fully unrolled, the head alone
+// was 40 KB of straight-line code executed once per item next to the other warp roles with bodies of the same size, and the
+// instruction caches (6 KB L0, 32 KB L1.5) served none of them (9.24 -> 7.38 ms per station-day from rolling this kernel's loops).
+__device__ __forceinline__ void d2_head(const FzDecB2 &p, int g, int b, int R0, int rr, int half, const float *buf) {
+    const int row = R0 + D2_LANE_LO + rr;
+    if (rr >= D2_USE || (unsigned)row >= (unsigned)p.T0) return;
+    const int u0 = 4 * (D2_LANE_LO + rr) + 2 * half - 2;  // unit of sample (first output) - 8
+    const float *hw = p.head_c[g];
+    // Packed FFMA2 (two fp32 FMAs per instruction, scalar weight broadcast): taps with an even first input index pair the
+    // outputs (0,1) .. (6,7) in accA, the others pair (1,2) .. (5,6) in accB and leave outputs 0 and 7 to scalar FMAs: 50 instead of 88
+    // FMA-pipe instructions per channel.
+    float2 accA[4], accB[3];
+    float s0 = 0.f, s7 = 0.f;
 #pragma unroll
-    for (int o = 0; o < 8; ++o) acc[o] = hw[96];
+    for (int i = 0; i < 4; ++i) accA[i] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) accB[i] = make_float2(0.f, 0.f);
     int uo[6];
 #pragma unroll
     for (int q = 0; q < 6; ++q) uo[q] = 4 * d2_unit(u0 + q);
@@ -270,13 +287,23 @@ __device__ __forceinline__ void d2_head(const FzDecB2 &p, const float *hw /*shar
                      w2 = *reinterpret_cast<const float4 *>(hw + c * 12 + 8);
         const float wk[12] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w};
 #pragma unroll
-        for (int k = 0; k < 11; ++k) {
+        for (int k = 0; k < 11; ++k) {  // output o reads xv[o + k + 3] (xv[0] = sample (first output) - 8)
             const float w = wk[k];
+            if (k & 1) {
 #pragma unroll
-            for (int o = 0; o < 8; ++o) acc[o] = fmaf(w, xv[o + k + 3], acc[o]);  // xv[0] = sample (first output) - 8
+                for (int i = 0; i < 4; ++i) d2_ffma2(accA[i], xv[2 * i + k + 3], xv[2 * i + k + 4], w);
+            } else {
+                s0 = fmaf(w, xv[k + 3], s0);
+#pragma unroll
+                for (int i = 0; i < 3; ++i) d2_ffma2(accB[i], xv[2 * i + 1 + k + 3], xv[2 * i + 1 + k + 4], w);
+                s7 = fmaf(w, xv[7 + k + 3], s7);
+            }
         }
     }
-    float *yb = p.y + ((size_t)b * 3 + g) * p.L_out + (size_t)16 * row + 8 * (e & 1);
+    const float hb = hw[96];
+    const float acc[8] = {accA[0].x + s0 + hb,        accA[0].y + accB[0].x + hb, accA[1].x + accB[0].y + hb, accA[1].y + accB[1].x + hb,
+                          accA[2].x + accB[1].y + hb, accA[2].y + accB[2].x + hb, accA[3].x + accB[2].y + hb, accA[3].y + s7 + hb};
+    float *yb = p.y + ((size_t)b * 3 + g) * p.L_out + (size_t)16 * row + 8 * half;
 #pragma unroll
     for (int o = 0; o < 8; o += 4) {
         float4 o4;
@@ -354,12 +381,15 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decb2_kernel(const __grid_const
         (void)id128;
         D2Prof prof;  // 0 in_full, 1 s1_full, 2 a2_full, 3 d23_free, 4 a3_full, 5 issue
         prof.start();
-        auto issue_L0 = [&](int m) {  // dec3: in (shared) -> D0 = columns [0, 64)
+        auto issue_L0 = [&](int m) {  // dec3: in (shared) -> D0 = columns [0, 64) (+ [64, 128): the stacked W_lo half)
             mbar_wait(&in_full, m & 1);
             prof.lap(0);
             tc_fence_after();
             if (elect_one()) {
-                d2_conv_tile<64, SPLIT, 5, 2>(tmem_base + D2_COL_A2, in16, D2_IN_ROWS, w0, id64);
+                if constexpr (SPLIT == 2)
+                    d2_conv_tile_stacked<64, 5, 2>(tmem_base + D2_COL_A2, in16, D2_IN_ROWS, w0, id128, id64);
+                else
+                    d2_conv_tile<64, 1, 5, 2>(tmem_base + D2_COL_A2, in16, D2_IN_ROWS, w0, id64);
                 umma_commit(&d0_full);
             }
             __syncwarp();
@@ -380,6 +410,8 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decb2_kernel(const __grid_const
         auto issue_L2 = [&](int n) {  // dec5: A2 (TMEM) -> D2 blocks
             mbar_wait(&a2_full, n & 1);
             prof.lap(2);
+            // (releasing the D2 / D3 columns pair by pair, so that dec5 of the next item starts under the last head-buffer stores,
+            // was measured SLOWER: 6.99 vs 6.57 ms per station-day)
             if (n > 0) mbar_wait(&d23_free, (n - 1) & 1);
             prof.lap(3);
             tc_fence_after();
@@ -461,7 +493,7 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decb2_kernel(const __grid_const
             for (int cc = 0; cc < 2; ++cc) {
                 const int c0 = 32 * h + 16 * cc;
                 float v[16];
-                d2_load16<0>(&p.bias_c[g][D2_B0 + c0], tl + D2_COL_A2, c0, v);
+                d2_load16<SPLIT == 2 ? 64 : 0>(&p.bias_c[g][D2_B0 + c0], tl + D2_COL_A2, c0, v);
                 uint32_t hh[8], ll[8];
                 d2_pack16<SPLIT>(v, valid, hh, ll);
                 const int pl = h * 4 + 2 * cc;  // plane' = phase * 4 + channel plane
@@ -504,31 +536,21 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decb2_kernel(const __grid_const
             tc_fence_before();
             named_bar_sync(1, 256);
             tc_fence_after();
-            if (h) {  // left halo: slots 0, 1 = samples 2, 3 of lane r - 1
-                const uint32_t *xl = xa + (size_t)(((m & 1) * 4 + (q + 3) % 4) * 2 + 1) * 32;
+            {   // h = 1: left halo, slots 0, 1 = samples 2, 3 of lane r - 1; h = 0: right halo, slots 6, 7 = samples 0, 1 of lane r + 1
+                const uint32_t *xe = h ? xa + (size_t)(((m & 1) * 4 + (q + 3) % 4) * 2 + 1) * 32 : xa + (size_t)(((m & 1) * 4 + (q + 1) % 4) * 2) * 32;
+                const int from = (lane + (h ? 31 : 1)) & 31, edge = h ? 0 : 31;
+                const bool have = h ? q > 0 : q < 3;
+                const uint32_t dst0 = D2_COL_A2 + 8 * (h ? 0 : 6);
 #pragma unroll
                 for (int s = 0; s < 2; ++s) {
                     uint32_t hh[8], ll[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        hh[i] = __shfl_up_sync(0xffffffffu, oh[s][i], 1);
-                        ll[i] = __shfl_up_sync(0xffffffffu, ol[s][i], 1);
+                        hh[i] = __shfl_sync(0xffffffffu, oh[s][i], from);
+                        ll[i] = __shfl_sync(0xffffffffu, ol[s][i], from);
                     }
-                    if (lane == 0) d2_fetch16(xl + s * 16, q > 0, hh, ll);
-                    d2_st_slot<SPLIT>(tl, D2_COL_A2 + 8 * s, D2_A2_LO, hh, ll);
-                }
-            } else {  // right halo: slots 6, 7 = samples 0, 1 of lane r + 1
-                const uint32_t *xr = xa + (size_t)(((m & 1) * 4 + (q + 1) % 4) * 2) * 32;
-#pragma unroll
-                for (int s = 0; s < 2; ++s) {
-                    uint32_t hh[8], ll[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        hh[i] = __shfl_down_sync(0xffffffffu, oh[s][i], 1);
-                        ll[i] = __shfl_down_sync(0xffffffffu, ol[s][i], 1);
-                    }
-                    if (lane == 31) d2_fetch16(xr + s * 16, q < 3, hh, ll);
-                    d2_st_slot<SPLIT>(tl, D2_COL_A2 + 8 * (6 + s), D2_A2_LO, hh, ll);
+                    if (lane == edge) d2_fetch16(xe + s * 16, have, hh, ll);
+                    d2_st_slot<SPLIT>(tl, dst0 + 8 * s, D2_A2_LO, hh, ll);
                 }
             }
             tmem_st_wait();
@@ -579,37 +601,28 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decb2_kernel(const __grid_const
             tc_fence_before();
             named_bar_sync(2, 256);
             tc_fence_after();
-            if (h == 0) {  // right halo: slot 11 + i = sample i of lane r + 1 (its slot 3 + i)
-                const uint32_t *xr = xb + (size_t)(((n & 1) * 4 + (q + 1) % 4) * 2) * 48;
+            {
+                // h = 0: right halo, slot 11 + i = sample i of lane r + 1 (its slot 3 + i); h = 1: left halo, slot i = sample 5 + i of lane
+                // r - 1 (its slot 8 + i).  One code path for both directions and a rolled loop: this kernel's speed follows the size of
+                // its hot code (25 warps in four roles share a 32 KB instruction cache).
+                const uint32_t *xe = h == 0 ? xb + (size_t)(((n & 1) * 4 + (q + 1) % 4) * 2) * 48      // next quarter's lane 0: samples 0-2
+                                            : xb + (size_t)(((n & 1) * 4 + (q + 3) % 4) * 2 + 1) * 48;  // previous quarter's lane 31: samples 5-7
+                const uint32_t src0 = D2_COL_A3 + 8 * (h == 0 ? 3 : 8), dst0 = D2_COL_A3 + 8 * (h == 0 ? 11 : 0);
+                const int from = (lane + (h == 0 ? 1 : 31)) & 31, edge = h == 0 ? 31 : 0;
+                const bool have = h == 0 ? q < 3 : q > 0;
 #pragma unroll 1
                 for (int i3 = 0; i3 < 3; ++i3) {
                     uint32_t hh[8], ll[8];
-                    tmem_ld8_nowait(tl + D2_COL_A3 + 8 * (3 + i3), hh);
-                    if (SPLIT == 2) tmem_ld8_nowait(tl + D2_COL_A3 + D2_A3_LO + 8 * (3 + i3), ll);
+                    tmem_ld8_nowait(tl + src0 + 8 * i3, hh);
+                    if (SPLIT == 2) tmem_ld8_nowait(tl + src0 + D2_A3_LO + 8 * i3, ll);
                     tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        hh[i] = __shfl_down_sync(0xffffffffu, hh[i], 1);
-                        if (SPLIT == 2) ll[i] = __shfl_down_sync(0xffffffffu, ll[i], 1);
+                        hh[i] = __shfl_sync(0xffffffffu, hh[i], from);
+                        if (SPLIT == 2) ll[i] = __shfl_sync(0xffffffffu, ll[i], from);
                     }
-                    if (lane == 31) d2_fetch16(xr + i3 * 16, q < 3, hh, ll);
-                    d2_st_slot<SPLIT>(tl, D2_COL_A3 + 8 * (11 + i3), D2_A3_LO, hh, ll);
-                }
-            } else {  // left halo: slot i = sample 5 + i of lane r - 1 (its slot 8 + i)
-                const uint32_t *xl = xb + (size_t)(((n & 1) * 4 + (q + 3) % 4) * 2 + 1) * 48;
-#pragma unroll 1
-                for (int i3 = 0; i3 < 3; ++i3) {
-                    uint32_t hh[8], ll[8];
-                    tmem_ld8_nowait(tl + D2_COL_A3 + 8 * (8 + i3), hh);
-                    if (SPLIT == 2) tmem_ld8_nowait(tl + D2_COL_A3 + D2_A3_LO + 8 * (8 + i3), ll);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        hh[i] = __shfl_up_sync(0xffffffffu, hh[i], 1);
-                        if (SPLIT == 2) ll[i] = __shfl_up_sync(0xffffffffu, ll[i], 1);
-                    }
-                    if (lane == 0) d2_fetch16(xl + i3 * 16, q > 0, hh, ll);
-                    d2_st_slot<SPLIT>(tl, D2_COL_A3 + 8 * i3, D2_A3_LO, hh, ll);
+                    if (lane == edge) d2_fetch16(xe + i3 * 16, have, hh, ll);
+                    d2_st_slot<SPLIT>(tl, dst0 + 8 * i3, D2_A3_LO, hh, ll);
                 }
             }
             tmem_st_wait();
@@ -652,7 +665,7 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decb2_kernel(const __grid_const
         prof.flush(warp, lane);
     } else {
         // ================= head warps: sigmoid(conv k11) of item n while the pipeline runs item n + 1
-        const int e = (warp - 17) * 32 + lane;
+        const int rr = ((warp - 17) & 3) * 32 + lane, half = (warp - 17) >> 2;
         const float *hbuf = reinterpret_cast<const float *>(d2_smem + p.head_off);
         D2Prof prof;  // 0 head_go, 1 head
         prof.start();
@@ -662,7 +675,7 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decb2_kernel(const __grid_const
             const int R0 = p.row_off0 + D2_USE * j - D2_LANE_LO;
             mbar_wait(&head_go, n & 1);
             prof.lap(0);
-            if (!(p.dbg & 4)) d2_head(p, bias + D2_HW, g, b, R0, e, hbuf);
+            if (!(p.dbg & 4)) d2_head(p, g, b, R0, rr, half, hbuf);
             __syncwarp();
             if (lane == 0) mbar_arrive(&head_done);
             prof.lap(1);
@@ -744,7 +757,16 @@ int decb2_build(DecB2Plan &plan, const TcLayer *dec, const float *const *w4, con
     plan.blob.assign((size_t)G * rel / 2, 0);
     for (int g = 0; g < G; ++g) {
         uint16_t *dst = plan.blob.data() + (size_t)g * rel / 2;
-        std::memcpy(dst + r0 / 2, L0.blocks.data() + (size_t)g * 10 * blk0, 10 * blk0 * 2);
+        if (split == 2) {  // [block][split][k-half][64][8] -> [block][k-half][W_hi rows 0..63 | W_lo rows 64..127][8]
+            const uint16_t *src = L0.blocks.data() + (size_t)g * 10 * blk0;
+            for (int bk = 0; bk < 10; ++bk)
+                for (int sp = 0; sp < 2; ++sp)
+                    for (int kh = 0; kh < 2; ++kh)
+                        std::memcpy(dst + r0 / 2 + (size_t)bk * blk0 + ((size_t)kh * 128 + (size_t)sp * 64) * 8,
+                                    src + (size_t)bk * blk0 + ((size_t)sp * 2 + kh) * 64 * 8, (size_t)64 * 8 * sizeof(uint16_t));
+        } else {
+            std::memcpy(dst + r0 / 2, L0.blocks.data() + (size_t)g * 10 * blk0, 10 * blk0 * 2);
+        }
         std::memcpy(dst + r2 / 2, L2.blocks.data() + (size_t)g * 5 * blk2, 5 * blk2 * 2);
         std::memcpy(dst + r3 / 2, L3.blocks.data() + (size_t)g * 7 * blk3, 7 * blk3 * 2);
         // decoder.convs.4 (16, 32, 7) after x2 up-sampling, folded over the two 750-level samples of a 375-level row:
@@ -781,6 +803,9 @@ int decb2_build(DecB2Plan &plan, const TcLayer *dec, const float *const *w4, con
         for (int n = 0; n < 16; ++n) p.bias_c[g][D2_B1 + n] = b4[g] ? b4[g][n] : 0.f;
         for (int n = 0; n < 32; ++n) p.bias_c[g][D2_B2 + n] = L2.bias[(size_t)g * 32 + n];
         for (int n = 0; n < 16; ++n) p.bias_c[g][D2_B3 + n] = L3.bias[(size_t)g * 16 + n];
+        for (int c = 0; c < 8; ++c)
+            for (int k = 0; k < 12; ++k) p.head_c[g][c * 12 + k] = k < 11 ? head_w[g][c * 11 + k] : 0.f;
+        p.head_c[g][96] = head_b[g];
         float *bd = reinterpret_cast<float *>(dst + rb / 2);
         for (int n = 0; n < 64; ++n) bd[D2_B0 + n] = L0.bias[(size_t)g * 64 + n];
         for (int n = 0; n < 16; ++n) bd[D2_B1 + n] = b4[g] ? b4[g][n] : 0.f;
