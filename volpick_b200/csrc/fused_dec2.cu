@@ -440,31 +440,32 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decb2_kernel(const __grid_const
             }
             __syncwarp();
         };
-        if (n_my > 0) {
-            issue_L0(0);
-            prof.lap(5);
-            issue_L1(0);
-            prof.lap(5);
-        }
-        for (int n = 0; n < n_my; ++n) {
-            issue_L2(n);
-            prof.lap(5);
+        // one call site per layer (the lambdas are inlined; this kernel's speed follows the size of its hot code): iteration n = -1
+        // is the prologue, the first two layers of item 0
+        for (int n = -1; n < n_my; ++n) {
+            if (n >= 0) {
+                issue_L2(n);
+                prof.lap(5);
+            }
             if (n + 1 < n_my) {
-                if (p.dbg & 16) {  // debug: drain L2 before the next item's D0 lands in the A2 columns
+                if (n >= 0 && (p.dbg & 16)) {  // debug: drain dec5 before the next item's first accumulator lands in the A2 columns
                     mbar_wait(&d2_full[3], n & 1);
                     tc_fence_after();
                 }
                 issue_L0(n + 1);
                 prof.lap(5);
             }
-            issue_L3(n, 0);
-            prof.lap(5);
-            if (n + 1 < n_my) {
-                issue_L1(n + 1);
-                prof.lap(5);
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                if (n >= 0) {
+                    issue_L3(n, half);
+                    prof.lap(5);
+                }
+                if (half == 0 && n + 1 < n_my) {
+                    issue_L1(n + 1);
+                    prof.lap(5);
+                }
             }
-            issue_L3(n, 1);
-            prof.lap(5);
         }
         prof.flush(warp, lane);
     } else if (warp < 9) {
