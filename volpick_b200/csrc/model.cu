@@ -1286,7 +1286,9 @@ static int run_eqt(Runner &r, const float *x, float *y, Arena &ar) {
                 continue;
             }
             if (fused && i == 3) {  // decoder.convs.3-6 + heads in one kernel, activations in shared memory
-                static const bool decb_v1 = getenv("VP_DECB_V1") && atoi(getenv("VP_DECB_V1")) != 0;  // A/B arm: the shared-memory-operand kernel
+                // A/B arm (read per launch so that a test can compare the two in one process): the shared-memory-operand kernel
+                const char *v1 = getenv("VP_DECB_V1");
+                const bool decb_v1 = v1 && atoi(v1) != 0;
                 if (r.go())
                     r.rc = (ts.decb2.ready && !decb_v1)
                                ? decb2_launch(ts.decb2, cur16, split16, B * (int64_t)tl.cin * dlen[i], (int)B, y, r.keep_lo, r.keep_hi, r.s)
