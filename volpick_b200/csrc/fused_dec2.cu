@@ -235,16 +235,6 @@ __device__ __forceinline__ void d2_st_slot(uint32_t tl, uint32_t col_hi, uint32_
     if (SPLIT == 2) tmem_st8(tl + col_hi + lo_off, l);
 }
 
-// d += (a0, a1) * w: one FFMA2 (sm_100: two fp32 FMAs per instruction; the scalar multiplier is broadcast)
-__device__ __forceinline__ void d2_ffma2(float2 &d, float a0, float a1, float w) {
-    unsigned long long dd, aa, ww;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(dd) : "f"(d.x), "f"(d.y));
-    asm("mov.b64 %0, {%1, %2};" : "=l"(aa) : "f"(a0), "f"(a1));
-    asm("mov.b64 %0, {%1, %1};" : "=l"(ww) : "f"(w));
-    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(dd) : "l"(aa), "l"(ww));
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(dd));
-}
-
 // Head buffer: fp32 planar [c][sample], addressed in 16-byte units of 4 samples.  Both its writers (lane r stores unit 4 r + bp)
 // and its readers (head thread e loads units 14 + 4 e + q) have a lane stride of four units; XOR-ing the low two unit bits with
 // bits 3-4 spreads the eight lanes of a quarter warp over the eight 16-byte bank groups.
@@ -291,11 +281,11 @@ __device__ __forceinline__ void d2_head(const FzDecB2 &p, int g, int b, int R0, 
             const float w = wk[k];
             if (k & 1) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) d2_ffma2(accA[i], xv[2 * i + k + 3], xv[2 * i + k + 4], w);
+                for (int i = 0; i < 4; ++i) ffma2(accA[i], xv[2 * i + k + 3], xv[2 * i + k + 4], w);
             } else {
                 s0 = fmaf(w, xv[k + 3], s0);
 #pragma unroll
-                for (int i = 0; i < 3; ++i) d2_ffma2(accB[i], xv[2 * i + 1 + k + 3], xv[2 * i + 1 + k + 4], w);
+                for (int i = 0; i < 3; ++i) ffma2(accB[i], xv[2 * i + 1 + k + 3], xv[2 * i + 1 + k + 4], w);
                 s7 = fmaf(w, xv[7 + k + 3], s7);
             }
         }

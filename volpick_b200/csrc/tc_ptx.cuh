@@ -147,6 +147,17 @@ __device__ __forceinline__ void pack8_split16(const float *v, uint4 &hi, uint4 &
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+// d += (a0, a1) * w: one FFMA2 (sm_100: two fp32 FMAs per instruction; the scalar multiplier is broadcast to both halves).  Each
+// half is an ordinary fp32 fused multiply-add (round to nearest): results equal fmaf() per element.
+__device__ __forceinline__ void ffma2(float2 &d, float a0, float a1, float w) {
+    unsigned long long dd, aa, ww;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(dd) : "f"(d.x), "f"(d.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(aa) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(ww) : "f"(w));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(dd) : "l"(aa), "l"(ww));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(dd));
+}
+
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred = 0;
     asm volatile(
