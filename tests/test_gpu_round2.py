@@ -400,3 +400,27 @@ def test_decoder_tail_generations_agree(eqt, precision, atol, B, monkeypatch):
     d = float(np.abs(new - old).max())
     print(f"{precision} B={B}: decoder tail v2 vs v1 max|diff| = {d:.3e}")
     assert d <= atol
+
+
+@pytest.mark.parametrize("precision,atol", [("f16x3", 2e-5), ("bf16", 5e-2)])
+@pytest.mark.parametrize("B", [1, 3, 50])
+def test_fused_encoder_front_agrees_with_layers(eqt, precision, atol, B, monkeypatch):
+    """fused_enc.cu (encoder.convs.1-3 in one kernel, the 1500- / 750-sample levels in tensor memory) against the same three layers
+    run one by one through tcconv.cu (VP_ENC_FUSED=0): encoder output (enc6 tap) and probabilities."""
+    rng = np.random.default_rng(11 + B)
+    x = rng.standard_normal((B, 3, 6000)).astype(np.float32)
+    x[:, :, :40] *= 5.0   # energy at both window ends: the convs' zero padding and the item edges
+    x[:, :, -40:] *= 5.0
+    xd = torch.from_numpy(x).cuda()
+    out = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("VP_ENC_FUSED", flag)
+        out[flag] = (eqt.forward_tap(xd, "enc6", precision=precision).cpu().numpy(),
+                     torch.stack(eqt.forward(xd, precision=precision), dim=1).cpu().numpy())
+    scale = float(np.abs(out["0"][0]).max())
+    d6 = float(np.abs(out["1"][0] - out["0"][0]).max())
+    dp = float(np.abs(out["1"][1] - out["0"][1]).max())
+    print(f"{precision} B={B}: fused encoder front vs layers: enc6 max|diff| = {d6:.3e} (scale {scale:.2f}), probabilities {dp:.3e}")
+    assert np.isfinite(out["1"][1]).all()
+    assert d6 <= (1e-5 if precision == "f16x3" else 5e-2) * max(scale, 1.0)
+    assert dp <= atol

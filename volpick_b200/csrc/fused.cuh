@@ -128,6 +128,33 @@ void decb2_free(DecB2Plan &plan);
 int decb2_launch(const DecB2Plan &plan, const uint16_t *x, long long x_split, long long x_gs, int B, float *y, int keep_lo, int keep_hi,
                  cudaStream_t s);
 
+// Encoder front (fused_enc.cu): encoder.convs.1-3 (Conv1d + ReLU + MaxPool1d(2) each) in one kernel, the 1500- and 750-sample
+// levels in tensor memory; a work item is 128 rows of the 375-sample level, of which 94 carry valid outputs.
+struct FzEncA {
+    const uint16_t *x;  // [split][B][3000][8] channel-last 16-bit (encoder.convs.0 output)
+    long long x_split;
+    uint16_t *y;        // [split][B][375][32] channel-last 16-bit (encoder.convs.4 input)
+    long long y_split;
+    int B, tiles_per_seq, T0;
+    int in_off, xch_off, blob_off, blob_bytes, w1_off, w2_off, w3_off;  // shared-memory byte offsets
+    const uint16_t *blob;  // device
+    int smem_bytes;
+    float bias_c[64];  // convs.1 [16] | convs.2 [16] | convs.3 [32], read through the constant bank
+};
+struct EncAPlan {
+    FzEncA p;
+    int split = 0;
+    std::vector<uint16_t> blob;
+    uint16_t *d_blob = nullptr;
+    bool ready = false;
+};
+// enc2 / enc3: the TcLayers of encoder.convs.2 / .3 (host weight blocks still present); w1 / b1: raw (16, 8, 9) weights and (16)
+// biases of encoder.convs.1 (folded over eight samples here)
+int enca_build(EncAPlan &plan, const TcLayer &enc2, const TcLayer &enc3, const float *w1, const float *b1, int split);
+int enca_upload(EncAPlan &plan);
+void enca_free(EncAPlan &plan);
+int enca_launch(const EncAPlan &plan, const uint16_t *x, long long x_split, int B, uint16_t *y, long long y_split, cudaStream_t s);
+
 // res-CNN stack: the 14 convs of res_cnn_stack.members.0-6 in one persistent launch (fused_res.cu).
 constexpr int RS_MAX_LAYERS = 14;
 struct ResLayerP {

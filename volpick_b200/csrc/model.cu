@@ -290,6 +290,7 @@ struct vp_model {
         bool ready = false;
         DecBPlan decb;  // fused decoder tail (fused_dec.cu)
         DecB2Plan decb2;  // fused decoder tail with the wide levels in tensor memory (fused_dec2.cu): the default
+        EncAPlan enca;    // fused encoder front, convs.1-3 (fused_enc.cu)
         DecAPlan deca;  // fused decoder middle, convs.1 + convs.2 (fused_deca.cu)
     } tc[2];
     // PhaseNet on the tensor cores (same precision sets).  Stride-4 convs and the stride-4 ConvTranspose1d run as k = 2
@@ -490,6 +491,10 @@ static int build_eqt(vp_model *m, Cursor &cur, Packed &pk) {
                 rc = tc_build_layer(ts.encf[i], TC_DIRECT, 4 * cin, 4 * kEncC[i + 1], 3, 0, split, 1, wfl, bfl, 1);
                 if (rc != VP_OK) return rc;
             }
+        }
+        {   // fused encoder front: convs.1 from the raw (16, 8, 9) weights, convs.2 / .3 from their tensor-core layers
+            int rc = enca_build(ts.enca, ts.enc[2], ts.enc[3], eW[1], eB[1], split);
+            if (rc != VP_OK) return rc;
         }
         for (int i = 0; i < 7; ++i) {
             const float *wl[3] = {dW[0][i], dW[1][i], dW[2][i]}, *bl[3] = {dB[0][i], dB[1][i], dB[2][i]};
@@ -939,6 +944,15 @@ static int run_eqt(Runner &r, const float *x, float *y, Arena &ar) {
         const bool enc6_tap = r.stop_name && std::strcmp(r.stop_name, "enc6") == 0;
         for (int i = first_layer; i < 7; ++i) {
             const TcLayer &tl = ts.enc[i];
+            if (i == 1 && ts.enca.ready && len[1] == 3000) {  // convs.1-3 in one kernel (fused_enc.cu); VP_ENC_FUSED=0: layer by layer
+                const char *ef = getenv("VP_ENC_FUSED");
+                if (!(ef && atoi(ef) == 0)) {
+                    if (r.go()) r.rc = enca_launch(ts.enca, cur16, split16, (int)B, pp16[1], split16, r.s);
+                    cur16 = pp16[1];
+                    i = 3;
+                    continue;
+                }
+            }
             if (r.go()) {
                 TcIO io;
                 io.x = cur16;
@@ -1796,6 +1810,7 @@ extern "C" int vp_model_create(int kind, const float *weights, int64_t n_floats,
             int rc = upload_tc(m->tc[set]);
             if (rc == VP_OK) rc = decb_upload(m->tc[set].decb);
             if (rc == VP_OK) rc = decb2_upload(m->tc[set].decb2);
+            if (rc == VP_OK) rc = enca_upload(m->tc[set].enca);
             if (rc == VP_OK) rc = deca_upload(m->tc[set].deca);
             if (rc != VP_OK) {
                 vp_model_destroy(m);
@@ -1825,6 +1840,7 @@ extern "C" int vp_model_destroy(vp_model *m) {
         if (m->tc[set].d_res_par) cudaFree(m->tc[set].d_res_par);
         decb_free(m->tc[set].decb);
         decb2_free(m->tc[set].decb2);
+        enca_free(m->tc[set].enca);
         deca_free(m->tc[set].deca);
         if (m->pn_tc[set].d_w) cudaFree(m->pn_tc[set].d_w);
         if (m->pn_tc[set].d_b) cudaFree(m->pn_tc[set].d_b);
