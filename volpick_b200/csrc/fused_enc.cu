@@ -19,8 +19,8 @@
 //
 // Lanes 3 .. 96 carry valid outputs (94 rows per item, four items per window).  Rows outside the window are zeros at every level
 // (the convs' zero padding); the TMA box delivers the input's zeros.  TMEM columns: [0, 128) D1; [128, 288) A2; [288, 416) A3;
-// [416, 480) D2 / D3.  The issuer interleaves convs.1 of item n + 1 with the TMEM half of item n.  17 warps: tcgen05 issuer, 8
-// epilogue warps A (D1 -> A2; they also issue the TMA loads), 8 epilogue warps B (D2 -> A3, D3 -> HBM).
+// [416, 480) D2 / D3.  The issuer interleaves convs.1 of item n + 1 with the TMEM half of item n.  25 warps: tcgen05 issuer, 16
+// epilogue warps A (D1 -> A2, one pooled sample each; they also issue the TMA loads), 8 epilogue warps B (D2 -> A3, D3 -> HBM).
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -32,11 +32,18 @@
 
 namespace vp {
 
-constexpr int EA_THREADS = 32 * 17;
+constexpr int EA_THREADS = 32 * 25;
 constexpr int EA_LANE_LO = 3, EA_USE = 94;
 constexpr int EA_IN_ROWS = 130;  // input rows R0 - 1 .. R0 + 128
 constexpr uint32_t EA_COL_D1 = 0, EA_COL_A2 = 128, EA_A2_LO = 80, EA_COL_A3 = 288, EA_A3_LO = 64, EA_COL_D23 = 416;
 constexpr int EA_B1 = 0, EA_B2 = 16, EA_B3 = 32;  // bias_c offsets
+
+#ifdef VP_EA_PROF
+__device__ long long ea_prof_out[8];
+#define EA_LAP(i) do { const long long _n = clock64(); ea_acc[i] += _n - ea_t; ea_t = _n; } while (0)
+#else
+#define EA_LAP(i) do { } while (0)
+#endif
 
 struct FzEncAK {
     alignas(64) CUtensorMap x_map;  // (8 channels, row of the 375 level, sample in the row, window, split) over the 3000-sample level input
@@ -116,7 +123,7 @@ __global__ void __launch_bounds__(EA_THREADS, 1) enca_kernel(const __grid_consta
     if (tid == 0) {
         mbar_init(&in_full, 1);
         mbar_init(&d1_full, 1);
-        mbar_init(&a2_full, 8);
+        mbar_init(&a2_full, 16);
         mbar_init(&d2_full, 1);
         mbar_init(&a3_full, 8);
         mbar_init(&d3_full, 1);
@@ -152,10 +159,15 @@ __global__ void __launch_bounds__(EA_THREADS, 1) enca_kernel(const __grid_consta
         const uint32_t id16 = umma_idesc(16, fmt), id32 = umma_idesc(32, fmt), id128 = umma_idesc(128, fmt);
         const uint32_t in16 = (sbase + p.in_off) >> 4;
         const uint32_t w1 = (sbase + p.w1_off) >> 4, w2 = (sbase + p.w2_off) >> 4, w3 = (sbase + p.w3_off) >> 4;
+#ifdef VP_EA_PROF
+        long long ea_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ea_t = clock64();
+#endif
         for (int n = -1; n < n_my; ++n) {
             if (n >= 0) {  // convs.2: A2 (TMEM) -> D2
                 mbar_wait(&a2_full, n & 1);
+                EA_LAP(0);
                 if (n > 0) mbar_wait(&d23_free, (n - 1) & 1);
+                EA_LAP(1);
                 tc_fence_after();
                 if (elect_one()) {
 #pragma unroll 1
@@ -164,18 +176,22 @@ __global__ void __launch_bounds__(EA_THREADS, 1) enca_kernel(const __grid_consta
                     umma_commit(&d2_full);
                 }
                 __syncwarp();
+                EA_LAP(4);
             }
             if (n + 1 < n_my) {  // convs.1 of the next item: input box (shared memory) -> D1
                 mbar_wait(&in_full, (n + 1) & 1);
+                EA_LAP(2);
                 tc_fence_after();
                 if (elect_one()) {
                     ea_conv1_tile<SPLIT>(tmem_base + EA_COL_D1, in16, w1, id128);
                     umma_commit(&d1_full);
                 }
                 __syncwarp();
+                EA_LAP(5);
             }
             if (n >= 0) {  // convs.3: A3 (TMEM) -> D3
                 mbar_wait(&a3_full, n & 1);
+                EA_LAP(3);
                 tc_fence_after();
                 if (elect_one()) {
 #pragma unroll 1
@@ -184,11 +200,17 @@ __global__ void __launch_bounds__(EA_THREADS, 1) enca_kernel(const __grid_consta
                     umma_commit(&d3_full);
                 }
                 __syncwarp();
+                EA_LAP(6);
             }
         }
-    } else if (warp < 9) {
-        // ================= epilogue warps A: D1 -> A2.  Half h converts conv samples 4 h .. 4 h + 3 = pooled samples 2 h, 2 h + 1.
-        const int q = warp & 3, h = (warp - 1) >> 2, r = q * 32 + lane;
+#ifdef VP_EA_PROF
+        if (blockIdx.x == 0 && lane == 0)
+            for (int i = 0; i < 8; ++i) ea_prof_out[i] = ea_acc[i];
+#endif
+    } else if (warp < 17) {
+        // ================= epilogue warps A (16: four per lane quarter): D1 -> A2.  Warp (q, s) converts the conv samples 2 s, 2 s + 1 of
+        // its lanes = pooled sample s, stores slot 3 + s and, from the same registers, the halo slots its neighbours need.
+        const int q = warp & 3, s = (warp - 1) >> 2, r = q * 32 + lane;
         const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
         uint32_t *xa = reinterpret_cast<uint32_t *>(ea_smem + p.xch_off);  // [parity][quarter][first | last][3 samples][16]
         if (warp == 1 && lane == 0 && n_my > 0) load_item(0);
@@ -201,30 +223,34 @@ __global__ void __launch_bounds__(EA_THREADS, 1) enca_kernel(const __grid_consta
             if (m > 0) mbar_wait(&d2_full, (m - 1) & 1);                    // convs.2 of the previous item has read A2
             tc_fence_after();
             uint32_t *xw = xa + (size_t)(((m & 1) * 4 + q) * 2) * 48;
-#pragma unroll 1
-            for (int sl = 0; sl < 2; ++sl) {
-                const int s = 2 * h + sl;  // pooled sample of the lane's four
-                float v[16];
-                ea_load_pool16(&p.bias_c[EA_B1], tl + EA_COL_D1, 32 * s, 32 * s + 16, v);
+            float v[16];
+            ea_load_pool16(&p.bias_c[EA_B1], tl + EA_COL_D1, 32 * s, 32 * s + 16, v);
+            uint32_t oh[8], ol[8];
+            ts_pack16<SPLIT>(v, valid, oh, ol);
+            // edge lanes post what the neighbour quarter needs: lane 0 its samples 0-2, lane 31 its samples 1-3
+            if (lane == 0 && s < 3) ts_post16(xw + s * 16, oh, ol);
+            if (lane == 31 && s >= 1) ts_post16(xw + 48 + (s - 1) * 16, oh, ol);
+            ts_st_slot<SPLIT>(tl, EA_COL_A2 + 8 * (3 + s), EA_A2_LO, oh, ol);
+            named_bar_sync(1, 512);  // the posts are visible
+            if (s < 3) {  // right halo of lane r - 1 ... seen from the receiver: slot 7 + s = sample s of lane r + 1
                 uint32_t hh[8], ll[8];
-                ts_pack16<SPLIT>(v, valid, hh, ll);
-                ts_st_slot<SPLIT>(tl, EA_COL_A2 + 8 * (3 + s), EA_A2_LO, hh, ll);
-                // edge lanes post what the neighbour quarter needs: lane 0 its samples 0-2, lane 31 its samples 1-3
-                if (lane == 0 && s < 3) ts_post16(xw + s * 16, hh, ll);
-                if (lane == 31 && s >= 1) ts_post16(xw + 48 + (s - 1) * 16, hh, ll);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    hh[i] = __shfl_down_sync(0xffffffffu, oh[i], 1);
+                    ll[i] = __shfl_down_sync(0xffffffffu, ol[i], 1);
+                }
+                if (lane == 31) ts_fetch16(xa + (size_t)(((m & 1) * 4 + (q + 1) % 4) * 2) * 48 + s * 16, q < 3, hh, ll);
+                ts_st_slot<SPLIT>(tl, EA_COL_A2 + 8 * (7 + s), EA_A2_LO, hh, ll);
             }
-            tmem_st_wait();
-            tc_fence_before();
-            named_bar_sync(1, 256);
-            tc_fence_after();
-            {   // h = 0: right halo, slots 7 + i = samples i of lane r + 1 (its slots 3 + i); h = 1: left halo, slots i = samples 1 + i of
-                // lane r - 1 (its slots 4 + i)
-                const uint32_t *xe = h == 0 ? xa + (size_t)(((m & 1) * 4 + (q + 1) % 4) * 2) * 48 : xa + (size_t)(((m & 1) * 4 + (q + 3) % 4) * 2 + 1) * 48;
-                const bool have = h == 0 ? q < 3 : q > 0;
-#pragma unroll 1
-                for (int i = 0; i < 3; ++i)
-                    ea_halo_slot<SPLIT>(tl, EA_COL_A2, EA_A2_LO, h == 0 ? 3 + i : 4 + i, h == 0 ? 7 + i : i, h == 0 ? 1 : -1, lane, have, xe + i * 16,
-                                        nullptr);
+            if (s >= 1) {  // left halo: slot s - 1 = sample s of lane r - 1
+                uint32_t hh[8], ll[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    hh[i] = __shfl_up_sync(0xffffffffu, oh[i], 1);
+                    ll[i] = __shfl_up_sync(0xffffffffu, ol[i], 1);
+                }
+                if (lane == 0) ts_fetch16(xa + (size_t)(((m & 1) * 4 + (q + 3) % 4) * 2 + 1) * 48 + (s - 1) * 16, q > 0, hh, ll);
+                ts_st_slot<SPLIT>(tl, EA_COL_A2 + 8 * (s - 1), EA_A2_LO, hh, ll);
             }
             tmem_st_wait();
             tc_fence_before();
@@ -233,7 +259,7 @@ __global__ void __launch_bounds__(EA_THREADS, 1) enca_kernel(const __grid_consta
         }
     } else {
         // ================= epilogue warps B: D2 -> A3 (h = pooled sample of the lane's two), D3 -> y (h = channel half)
-        const int q = warp & 3, h = (warp - 9) >> 2, r = q * 32 + lane;
+        const int q = warp & 3, h = (warp - 17) >> 2, r = q * 32 + lane;
         const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
         uint32_t *xb = reinterpret_cast<uint32_t *>(ea_smem + p.xch_off + 3072);  // [parity][quarter][first | last][3][16]
         for (int n = 0; n < n_my; ++n) {
@@ -415,6 +441,16 @@ static int enca_launch_t(const FzEncA &p, dim3 grid, cudaStream_t s) {
     KTimer kt(KC_TCCONV, s);
     kern<<<grid, EA_THREADS, p.smem_bytes, s>>>(K);
     VP_LAUNCH_CHECK();
+#ifdef VP_EA_PROF
+    {
+        cudaStreamSynchronize(s);
+        long long h[8];
+        cudaMemcpyFromSymbol(h, ea_prof_out, sizeof(h));
+        const int n_my = (p.B * p.tiles_per_seq - 1) / (int)grid.x + 1;
+        fprintf(stderr, "[enca prof] %d items per CTA; issuer cycles per item: waits a2_full %.0f d23_free %.0f in_full %.0f a3_full %.0f | issue convs.2 %.0f convs.1 %.0f convs.3 %.0f\n",
+                n_my, (double)h[0] / n_my, (double)h[1] / n_my, (double)h[2] / n_my, (double)h[3] / n_my, (double)h[4] / n_my, (double)h[5] / n_my, (double)h[6] / n_my);
+    }
+#endif
     return VP_OK;
 }
 
