@@ -281,11 +281,6 @@ __global__ void __launch_bounds__(32 * (EW + 4), EW == 16 ? 1 : EW == 8 ? 2 : 4)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
-    // Programmatic dependent launch: this grid may have been started while its predecessor in the stream was still draining (its
-    // CTAs then ran the prologue above -- barriers, TMEM allocation, resident weights -- under the predecessor's tail); the
-    // activations are only touched after the predecessor has completed and flushed.  The trigger lets the successor do the same.
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (warp > EW) {
         // ================= producers =================
@@ -752,22 +747,9 @@ static int launch_tc(const TcP &p, dim3 grid, size_t smem, cudaStream_t s) {
     auto kern = tcconv_kernel<NOUT, SPLIT, NTAPS, NQ, EW, FLAGS>;
     if (int rc = ensure_dyn_smem((const void *)kern, smem)) return rc;
     KTimer kt(KC_TCCONV, s);
-    static const bool pdl = !(getenv("VP_PDL") && atoi(getenv("VP_PDL")) == 0);  // A/B aid
-    if (pdl) {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = grid;
-        cfg.blockDim = dim3(32 * (EW + 4));
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = s;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        VP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, p));
-    } else {
-        kern<<<grid, 32 * (EW + 4), smem, s>>>(p);
-    }
+    // (programmatic dependent launch -- the prologue of a layer under the tail of the previous one -- was measured neutral for
+    // both networks: PhaseNet 287 vs 290 station-days/s; not kept)
+    kern<<<grid, 32 * (EW + 4), smem, s>>>(p);
     VP_LAUNCH_CHECK();
     return VP_OK;
 }
