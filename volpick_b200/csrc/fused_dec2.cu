@@ -29,7 +29,7 @@
 //
 // TMEM columns (512): [0, 128) A2, which also hosts the accumulators D0 / D1 of the NEXT item while A2 is dead; [128, 352) A3;
 // [352, 480) D2 / D3.  The issuer interleaves the shared-memory half of item n + 1 with the TMEM half of item n
-// (L2(n), L0(n+1), L3(n) first half, L1(n+1), L3(n) second half), so each epilogue runs under the other item's MMAs.
+// (L2(n), L0(n+1), L1(n+1), L3(n)), so each epilogue runs under the other item's MMAs.
 // Warps (25): tcgen05 issuer; 8 epilogue warps A (D0 -> S1, D1 -> A2; they also issue the TMA load of the next item); 8 epilogue warps
 // B (D2 -> A3, D3 -> head buffer); 8 head warps (sigmoid(conv k11), 8 outputs per thread).  Two epilogue warps share a TMEM lane
 // quarter and split its columns.  Hand-over by mbarriers; the two halves of a group meet at one named barrier per item (halo exchange).
@@ -294,13 +294,21 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decb2_kernel(const __grid_const
                 issue_L0(n + 1);
                 prof.lap(5);
             }
+            // The second shared-memory layer of the next item goes BEFORE dec6 of the current one (5.77 ms per station-day; between
+            // the halves of dec6, VP_DECB_DBG bit 5, it is 6.28): its epilogue (D1 -> A2) then runs under all of dec6, and the
+            // level-3000 epilogue, the longest of the chain, under both shared-memory layers.
+            const int l1_at = (p.dbg & 32) ? 0 : -1;
+            if (l1_at < 0 && n + 1 < n_my) {
+                issue_L1(n + 1);
+                prof.lap(5);
+            }
 #pragma unroll 1
             for (int half = 0; half < 2; ++half) {
                 if (n >= 0) {
                     issue_L3(n, half);
                     prof.lap(5);
                 }
-                if (half == 0 && n + 1 < n_my) {
+                if (half == l1_at && n + 1 < n_my) {
                     issue_L1(n + 1);
                     prof.lap(5);
                 }
