@@ -99,7 +99,7 @@ int decb_launch(const DecBPlan &plan, const uint16_t *x, long long x_split, long
 struct FzDecB2 {
     const uint16_t *x;  // [split][group][B][375][32] channel-last 16-bit
     long long x_split, x_gs;
-    int B, tiles_per_seq, row_off0;
+    int B, tiles_per_seq, row_off0, row_hi;  // rows [row_off0, row_hi) of the 375-sample level carry kept output samples
     int dbg;  // env VP_DECB_DBG (timing only, results are wrong): 4 no head, 32 the earlier issue order, 16 drain decoder.convs.5 before the next item's first accumulator
     int T0, L_out;
     int in_off, s1_off, head_off, xch_off, blob_off, blob_bytes;  // shared-memory byte offsets
