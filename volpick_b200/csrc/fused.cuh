@@ -103,7 +103,7 @@ struct FzDecB2 {
     int dbg;  // env VP_DECB_DBG (timing only, results are wrong): 4 no head, 32 the earlier issue order, 16 drain decoder.convs.5 before the next item's first accumulator
     int T0, L_out;
     int in_off, s1_off, head_off, xch_off, blob_off, blob_bytes;  // shared-memory byte offsets
-    int w0_off, w1_off, w2_off, w3_off, bias_off;
+    int w0_off, w1_off, w2_off, w3_off;
     const uint16_t *blob;  // device: [group][blob_bytes / 2]
     float *y;              // (B, 3, L_out) probabilities
     int smem_bytes;

@@ -50,8 +50,8 @@ constexpr int D2_IN_ROWS = 132;              // input rows R0 - 2 .. R0 + 129
 constexpr int D2_S1_ROWS = 130;              // lanes -1 .. 128 of the 750 level (rows 0 and 129 stay zero)
 constexpr int D2_RP = 2048;                  // floats per channel of the head buffer
 constexpr uint32_t D2_COL_A2 = 0, D2_A2_LO = 64, D2_COL_A3 = 128, D2_A3_LO = 112, D2_COL_D23 = 352;
-// bias block (floats): dec3 [64] | dec4 [16] | dec5 [32] | dec6 [16] | head weights [8][12] | head bias
-constexpr int D2_B0 = 0, D2_B1 = 64, D2_B2 = 80, D2_B3 = 112, D2_HW = 128, D2_BIAS_FLOATS = 256;
+// offsets into FzDecB2::bias_c (floats): dec3 [64] | dec4 [16] | dec5 [32] | dec6 [16]
+constexpr int D2_B0 = 0, D2_B1 = 64, D2_B2 = 80, D2_B3 = 112;
 
 // -DVP_D2_PROF build (tools/build_variant.sh): every warp of CTA (0, 0) accumulates the cycles of its sections (waits by barrier,
 // work by epilogue) and decb2_launch prints them.  Empty in the product build.
@@ -201,7 +201,6 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decb2_kernel(const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
-    const float *bias = reinterpret_cast<const float *>(d2_smem + p.bias_off);
     // the 132 input rows of item k as one TMA box (rows outside the sequence arrive as zeros); issued by one thread of epilogue A as
     // soon as the previous item's first layer has retired (its accumulator is full), so there is no loader warp and no "empty" barrier
     auto load_item = [&](int k) {
@@ -606,14 +605,11 @@ int decb2_build(DecB2Plan &plan, const TcLayer *dec, const float *const *w4, con
     rel += up128(5 * blk2 * 2);
     const size_t r3 = rel;
     rel += up128(7 * blk3 * 2);
-    const size_t rb = rel;
-    rel += up128((size_t)D2_BIAS_FLOATS * sizeof(float));
     p.blob_bytes = (int)rel;
     p.w0_off = p.blob_off + (int)r0;
     p.w1_off = p.blob_off + (int)r1;
     p.w2_off = p.blob_off + (int)r2;
     p.w3_off = p.blob_off + (int)r3;
-    p.bias_off = p.blob_off + (int)rb;
     p.smem_bytes = p.blob_off + p.blob_bytes;
     VP_REQUIRE(p.smem_bytes <= 227 * 1024 - 256, VP_ERR_UNSUPPORTED, "decb2: %d bytes of shared memory", p.smem_bytes);
     VP_REQUIRE(L0.n_blocks == 10 && L2.n_blocks == 5 && L3.n_blocks == 7, VP_ERR_UNSUPPORTED, "decb2: weight block counts");
@@ -669,14 +665,6 @@ int decb2_build(DecB2Plan &plan, const TcLayer *dec, const float *const *w4, con
         for (int c = 0; c < 8; ++c)
             for (int k = 0; k < 12; ++k) p.head_c[g][c * 12 + k] = k < 11 ? head_w[g][c * 11 + k] : 0.f;
         p.head_c[g][96] = head_b[g];
-        float *bd = reinterpret_cast<float *>(dst + rb / 2);
-        for (int n = 0; n < 64; ++n) bd[D2_B0 + n] = L0.bias[(size_t)g * 64 + n];
-        for (int n = 0; n < 16; ++n) bd[D2_B1 + n] = b4[g] ? b4[g][n] : 0.f;
-        for (int n = 0; n < 32; ++n) bd[D2_B2 + n] = L2.bias[(size_t)g * 32 + n];
-        for (int n = 0; n < 16; ++n) bd[D2_B3 + n] = L3.bias[(size_t)g * 16 + n];
-        for (int c = 0; c < 8; ++c)
-            for (int k = 0; k < 11; ++k) bd[D2_HW + c * 12 + k] = head_w[g][c * 11 + k];
-        bd[D2_HW + 96] = head_b[g];
     }
     return VP_OK;
 }
