@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decb2_kernel(const __grid_const
             mbar_wait(&a2_full, n & 1);
             prof.lap(2);
             // (releasing the D2 / D3 columns pair by pair, so that dec5 of the next item starts under the last head-buffer stores,
-            // was measured SLOWER: 6.99 vs 6.57 ms per station-day)
+            // was measured SLOWER twice: 6.99 vs 6.57 ms per station-day, and 6.17 vs 5.86 under the final issue order)
             if (n > 0) mbar_wait(&d23_free, (n - 1) & 1);
             prof.lap(3);
             tc_fence_after();
