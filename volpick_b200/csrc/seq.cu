@@ -208,20 +208,20 @@ __global__ void __launch_bounds__(AT_NT, 2) attention_kernel(const AttnP p) {
     const int half = p.width / 2;
     for (int jj = 0; jj < T; ++jj) {
         const float4 *kr = reinterpret_cast<const float4 *>(&Ks[wl][jj * AT_KP]);
-        float ea = e0, eb = 0.f, ec = 0.f, ed = 0.f;  // four partial sums: dependent FMA chains of 8 instead of 16
+        float ea = e0, eb = 0.f;
 #pragma unroll
         for (int u4 = 0; u4 < 8; u4 += 2) {
             const float4 k4 = kr[u4], k5 = kr[u4 + 1];
             ea = fmaf(wsm[AW_WA + u4 * 4 + 0], rcp_approx(fmaf(q[u4 * 4 + 0], k4.x, 1.f)), ea);
             eb = fmaf(wsm[AW_WA + u4 * 4 + 1], rcp_approx(fmaf(q[u4 * 4 + 1], k4.y, 1.f)), eb);
-            ec = fmaf(wsm[AW_WA + u4 * 4 + 2], rcp_approx(fmaf(q[u4 * 4 + 2], k4.z, 1.f)), ec);
-            ed = fmaf(wsm[AW_WA + u4 * 4 + 3], rcp_approx(fmaf(q[u4 * 4 + 3], k4.w, 1.f)), ed);
+            ea = fmaf(wsm[AW_WA + u4 * 4 + 2], rcp_approx(fmaf(q[u4 * 4 + 2], k4.z, 1.f)), ea);
+            eb = fmaf(wsm[AW_WA + u4 * 4 + 3], rcp_approx(fmaf(q[u4 * 4 + 3], k4.w, 1.f)), eb);
             ea = fmaf(wsm[AW_WA + u4 * 4 + 4], rcp_approx(fmaf(q[u4 * 4 + 4], k5.x, 1.f)), ea);
             eb = fmaf(wsm[AW_WA + u4 * 4 + 5], rcp_approx(fmaf(q[u4 * 4 + 5], k5.y, 1.f)), eb);
-            ec = fmaf(wsm[AW_WA + u4 * 4 + 6], rcp_approx(fmaf(q[u4 * 4 + 6], k5.z, 1.f)), ec);
-            ed = fmaf(wsm[AW_WA + u4 * 4 + 7], rcp_approx(fmaf(q[u4 * 4 + 7], k5.w, 1.f)), ed);
+            ea = fmaf(wsm[AW_WA + u4 * 4 + 6], rcp_approx(fmaf(q[u4 * 4 + 6], k5.z, 1.f)), ea);
+            eb = fmaf(wsm[AW_WA + u4 * 4 + 7], rcp_approx(fmaf(q[u4 * 4 + 7], k5.w, 1.f)), eb);
         }
-        const float e = (ea + eb) + (ec + ed);
+        const float e = ea + eb;
         if (e > emax) {  // new row maximum: bring the partial sums to the new reference
             const float sc = ex2_approx(1.4426950408889634f * (emax - e));  // exp(-inf) = 0 on the first step
             ssum *= sc;
