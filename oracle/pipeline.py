@@ -217,6 +217,33 @@ def sosfilt_record(x: np.ndarray, sos: np.ndarray, zerophase: bool = False) -> n
     return np.ascontiguousarray(y, dtype=np.float32)
 
 
+def fft_resample(data: np.ndarray, rate: float, new_rate: float, window: str = "hann") -> np.ndarray:
+    """ObsPy ``Trace.resample(new_rate, window="hann", no_filter=True)`` -- what SeisBench's ``WaveformModel.resample`` calls for a
+    sampling rate that is NOT an integer multiple of the model's -- restated with ``numpy.fft`` (ObsPy is not installable here: the
+    steps are recalled from obspy/core/trace.py, "parity unpinned" like the rest of this package; tests/test_vs_seisbench.py
+    compares with the real one when it imports).  Steps: real FFT; the spectrum times ``ifftshift(get_window(window, npts))`` (1 at
+    DC, 0 at Nyquist for "hann"); real and imaginary parts interpolated linearly (``np.interp``) from the frequency grid
+    ``k / (npts * delta)`` onto ``k * new_rate / num``, ``num = int(npts / (rate / new_rate))``; inverse real FFT of length num;
+    times ``num / npts``.  float64 in, float64 out."""
+    from scipy.signal import get_window
+
+    x = np.asarray(data, dtype=np.float64)
+    npts = x.shape[-1]
+    factor = rate / float(new_rate)
+    spec = np.fft.rfft(x)  # scipy.fftpack.rfft's [y0, Re y1, Im y1, ...] regrouped: x_r = Re, x_i = Im (Im y0 = Im y_nyq = 0)
+    x_r, x_i = spec.real.copy(), spec.imag.copy()
+    large_w = np.fft.ifftshift(get_window(window, npts))
+    x_r *= large_w[: npts // 2 + 1]
+    x_i *= large_w[: npts // 2 + 1]
+    num = int(npts / factor)
+    df = 1.0 / (npts * (1.0 / rate))
+    d_large_f = 1.0 / num * new_rate
+    f = df * np.arange(0, npts // 2 + 1, dtype=np.int32)
+    large_f = d_large_f * np.arange(0, num // 2 + 1, dtype=np.int32)
+    y = np.interp(large_f, f, x_r) + 1j * np.interp(large_f, f, x_i)
+    return np.fft.irfft(y, n=num) * (float(num) / float(npts))  # irfft ignores Im y0 and (num even) Im y_nyq, as fftpack's layout does
+
+
 # --------------------------------------------------------------------------- whole path on arrays
 
 LABELS = {"eqtransformer": ["Detection", "P", "S"], "phasenet": ["P", "S", "N"]}

@@ -285,8 +285,38 @@ def test_resample_200hz_on_device(pn, sd_pn):
         assert len(mine) == len(ref[phase]) and len(mine) > 0
         for q, r in zip(mine, ref[phase]):
             assert abs((q.peak_time - t0) * 100 - r[2]) <= 1 + 1e-6
-    with pytest.raises(NotImplementedError, match="integer multiples"):
-        pn.classify(vb.Stream([vb.Trace(x100[0], dict(hdr, channel="HHZ", starttime=t0, sampling_rate=125.0))]))
+
+
+def test_resample_fractional_ratio_on_device(pn, sd_pn):
+    """A 125 Hz stream (not an integer multiple of 100 Hz): ObsPy's FFT resampling restated on the device (float64, torch.fft)
+    against the oracle's NumPy restatement, then classify() on the stream against the oracle on the resampled record."""
+    rng = np.random.default_rng(6)
+    x100 = synthetic_record(11, 24_000)
+    # a 125 Hz version of the same ground motion: band-limited interpolation of the 100 Hz record + a little noise
+    x125 = np.stack([pipeline.fft_resample(x100[i], 100.0, 125.0) for i in range(3)]).astype(np.float32)
+    x125 += 0.01 * float(np.abs(x125).max()) * rng.standard_normal(x125.shape).astype(np.float32)
+    want = np.stack([pipeline.fft_resample(x125[i], 125.0, 100.0) for i in range(3)])
+    t0 = station_start(11)
+    hdr = dict(network="XX", station="R125", location="", sampling_rate=125.0)
+    st = vb.Stream([vb.Trace(x125[i], dict(hdr, channel="HH" + c, starttime=t0)) for i, c in enumerate("ZNE")])
+    st2 = st.copy()
+    for tr in st2:
+        pn.resample_trace(tr)
+        assert tr.stats.sampling_rate == 100.0 and len(tr.data) == want.shape[1]
+    got = np.stack([tr.data for tr in st2])
+    assert got.dtype == np.float64
+    assert float(np.abs(got - want).max()) <= 1e-9 * float(np.abs(want).max())
+    for odd in (x125[0, :-1], x125[0, :4097]):  # odd lengths: no Nyquist bin
+        g = pn._fft_resample(odd, 125.0)
+        w = pipeline.fft_resample(odd, 125.0, 100.0)
+        assert g.shape == w.shape and float(np.abs(g - w).max()) <= 1e-9 * float(np.abs(w).max())
+    picks = pn.classify(st).picks
+    ref, _ = _oracle_picks_for_record("phasenet", sd_pn, want.astype(np.float32), {"P_threshold": 0.39, "S_threshold": 0.34})
+    for phase in "PS":
+        mine = [q for q in picks if q.phase == phase]
+        assert len(mine) == len(ref[phase]) and len(mine) > 0
+        for q, r in zip(mine, ref[phase]):
+            assert abs((q.peak_time - t0) * 100 - r[2]) <= 1 + 1e-6
 
 
 # ------------------------------------------------------------------------------------------ boundary promises

@@ -128,3 +128,18 @@ def test_cuda_classify_matches_seisbench(kind):
     assert len(p_ref) == len(p_got)
     for a, b in zip(sorted(p_ref), sorted(p_got)):
         assert a.phase == b.phase and abs(a.peak_time - b.peak_time) <= 0.01 + 1e-9
+
+
+def test_fft_resample_matches_obspy():
+    """oracle.pipeline.fft_resample is a restatement from recollection of obspy.Trace.resample(window="hann", no_filter=True): with
+    ObsPy present, pin it."""
+    from oracle import pipeline
+
+    rng = np.random.default_rng(0)
+    for npts, rate in [(4001, 125.0), (4000, 125.0), (3000, 40.0), (2999, 66.6)]:
+        x = rng.standard_normal(npts)
+        tr = obspy.Trace(data=x.copy(), header={"sampling_rate": rate})
+        tr.resample(100.0, no_filter=True)
+        got = pipeline.fft_resample(x, rate, 100.0)
+        assert got.shape == tr.data.shape
+        assert float(np.abs(got - tr.data).max()) <= 1e-9 * float(np.abs(tr.data).max())

@@ -611,7 +611,8 @@ class WaveformModel:
         """SeisBench ``WaveformModel.resample`` for one trace, in place.  A sampling rate that is an integer multiple of
         the model's: ``trace.filter("lowpass", freq=sampling_rate / 2, zerophase=True)`` (ObsPy: 4 corners, float64
         ``sosfilt`` forward + backward) + ``trace.decimate(factor, no_filter=True)`` (every factor-th sample) -- the
-        filter runs on the device (``vp_sosfilt``).  Any other ratio is ObsPy's FFT ``Trace.resample`` and needs ObsPy."""
+        filter runs on the device (``vp_sosfilt``).  Any other ratio is ObsPy's FFT ``Trace.resample``: ObsPy's own for an ObsPy
+        trace, else its restatement on the device (``_fft_resample``)."""
         import torch
         from scipy.signal import iirfilter, zpk2sos
 
@@ -632,12 +633,48 @@ class WaveformModel:
                 tr.stats.npts = len(tr.data)
             return
         if hasattr(tr, "resample") and _is_obspy(tr):
-            tr.resample(self.sampling_rate, no_filter=True)
+            tr.resample(self.sampling_rate, no_filter=True)  # the reference's own code path when ObsPy is there
             return
-        raise NotImplementedError(
-            f"trace {tr.id} has sampling rate {rate} Hz: only integer multiples of {self.sampling_rate} Hz are resampled "
-            "on the device (low-pass + decimation); other ratios need an ObsPy stream (FFT resampling)"
-        )
+        self._require_gpu()
+        tr.data = self._fft_resample(np.ascontiguousarray(tr.data), rate)
+        tr.stats.sampling_rate = self.sampling_rate
+        tr.stats.npts = len(tr.data)
+
+    def _fft_resample(self, data: np.ndarray, rate: float) -> np.ndarray:
+        """ObsPy ``Trace.resample(sampling_rate, window="hann", no_filter=True)`` on the device (float64, cuFFT through
+        ``torch.fft``: library plumbing for a pre-processing step, like the pinned copies): spectrum x ifftshift(hann), linear
+        interpolation of its real and imaginary parts onto the new frequency grid, inverse FFT of the new length, x num / npts.
+        Restated from recollection of obspy/core/trace.py -- the oracle twin is ``oracle.pipeline.fft_resample``."""
+        import math
+
+        import torch
+
+        dev = self._device
+        x = torch.from_numpy(np.asarray(data)).to(dev).to(torch.float64)
+        npts = int(x.numel())
+        new_rate = float(self.sampling_rate)
+        factor = rate / new_rate
+        num = int(npts / factor)
+        if num < 1 or npts < 2:
+            return np.zeros(max(num, 0), dtype=np.float64)
+        spec = torch.fft.rfft(x)
+        nb = npts // 2 + 1
+        k = torch.arange(nb, device=dev, dtype=torch.float64)
+        # ifftshift(get_window("hann", npts))[k] = w[(k + npts // 2) % npts], w[m] = 0.5 - 0.5 cos(2 pi m / npts) (periodic Hann)
+        m = torch.remainder(k + (npts // 2), npts)
+        spec = spec * (0.5 - 0.5 * torch.cos(2.0 * math.pi * m / npts))
+        df = 1.0 / (npts * (1.0 / rate))
+        d_large_f = 1.0 / num * new_rate
+        large_f = d_large_f * torch.arange(num // 2 + 1, device=dev, dtype=torch.float64)
+        # np.interp(large_f, df * arange(nb), .): interval i = floor(large_f / df), clamped; beyond the last bin the last value
+        i0 = torch.clamp(torch.floor(large_f / df).to(torch.int64), 0, nb - 2) if nb >= 2 else torch.zeros_like(large_f, dtype=torch.int64)
+        f0 = df * i0.to(torch.float64)
+        f1 = df * (i0 + 1).to(torch.float64)
+        # floor(large_f / df) may land one interval off when large_f / df rounds across an integer: np.interp is continuous there
+        t = torch.clamp((large_f - f0) / (f1 - f0), 0.0, 1.0)
+        y = spec[i0] + t.to(spec.dtype) * (spec[torch.clamp(i0 + 1, max=nb - 1)] - spec[i0])
+        out = torch.fft.irfft(y, n=num) * (float(num) / float(npts))
+        return out.cpu().numpy()
 
     def stream_to_arrays(self, traces: Sequence, argdict) -> List[Tuple[Any, np.ndarray]]:
         """List form of ``_iter_stream_arrays`` (fresh NumPy arrays)."""
