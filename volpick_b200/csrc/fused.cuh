@@ -204,6 +204,8 @@ struct FzDecA {
     const float *fixw;     // device: per group [2][32][64] = w[:, :, 4], w[:, :, 3] of decoder.convs.2 (crop correction)
     int blob_off, blob_bytes, w1_off, w2_off, bias_off;  // shared-memory byte offsets
     int B, smem_bytes;
+    float bias_c[3][192];  // per decoder: convs.1 [128] | convs.2 [64]; read through the constant bank (the shared-memory pipe is
+                           // saturated by the MMAs' operand reads while the epilogues run: a broadcast LDS waits ~170 cycles there)
 };
 
 struct DecAPlan {

@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(DA_THREADS, 1) deca_kernel(const __grid_consta
     const uint32_t sbase = smem_u32(da_smem);
     constexpr uint32_t IN_BYTES = SPLIT * 8 * DA_IN_PITCH * 16, MID_BYTES = SPLIT * 8 * DA_MID_ROWS * 16;
     uint8_t *s_mid = da_smem + IN_BYTES;  // the input slot [0, IN_BYTES) is written by TMA only
-    const float *s_bias = reinterpret_cast<const float *>(da_smem + p.bias_off);  // [128] dec1, [64] dec2
+    const float *s_bias = p.bias_c[g];  // [128] dec1, [64] dec2: constant bank (kernel parameter)
 
     if (tid == 0) {
         mbar_init(&in_full, 1);
@@ -329,8 +329,8 @@ int deca_build(DecAPlan &plan, const TcLayer &dec1, const TcLayer &dec2p, int sp
         put(dst, dec1, e1);
         put(dst + w1_bytes / 2, dec2p, e2);
         float *bd = reinterpret_cast<float *>(dst + (w1_bytes + w2_bytes) / 2);
-        for (int n = 0; n < 128; ++n) bd[n] = dec1.bias[(size_t)g * 128 + n];
-        for (int n = 0; n < 64; ++n) bd[128 + n] = dec2p.bias[(size_t)g * 64 + n];
+        for (int n = 0; n < 128; ++n) bd[n] = p.bias_c[g][n] = dec1.bias[(size_t)g * 128 + n];
+        for (int n = 0; n < 64; ++n) bd[128 + n] = p.bias_c[g][128 + n] = dec2p.bias[(size_t)g * 64 + n];
         for (int co = 0; co < 32; ++co)
             for (int ci = 0; ci < 64; ++ci) {
                 plan.fixw[(((size_t)g * 2 + 0) * 32 + co) * 64 + ci] = w2[g][((size_t)co * 64 + ci) * 5 + 4];
