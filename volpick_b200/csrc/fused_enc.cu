@@ -85,23 +85,19 @@ __device__ __forceinline__ void ea_load_pool16(const float *bias, uint32_t tacc,
     }
 }
 
-// one halo slot: the packed registers of slot `src` of lane (lane + delta), or the neighbour quarter's posted copy for the lanes whose
-// source lies outside the warp -> slot `dst`
+// one halo slot from the registers of the warp that produced the sample: slot `dst` of every lane <- (oh, ol) of lane (lane + delta)
 template <int SPLIT>
-__device__ __forceinline__ void ea_halo_slot(uint32_t tl, uint32_t col0, uint32_t lo_off, int src, int dst, int delta, int lane, bool have,
-                                             const uint32_t *post_a, const uint32_t *post_b) {
+__device__ __forceinline__ void ea_halo_regs(uint32_t tl, uint32_t col0, uint32_t lo_off, const uint32_t (&oh)[8], const uint32_t (&ol)[8], int dst,
+                                             int delta, int lane, bool have, const uint32_t *post_a, const uint32_t *post_b) {
     uint32_t hh[8], ll[8];
-    tmem_ld8_nowait(tl + col0 + 8 * src, hh);
-    if (SPLIT == 2) tmem_ld8_nowait(tl + col0 + lo_off + 8 * src, ll);
-    tmem_ld_wait();
     const int from = (lane + delta) & 31;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        hh[i] = __shfl_sync(0xffffffffu, hh[i], from);
-        if (SPLIT == 2) ll[i] = __shfl_sync(0xffffffffu, ll[i], from);
+        hh[i] = __shfl_sync(0xffffffffu, oh[i], from);
+        ll[i] = SPLIT == 2 ? __shfl_sync(0xffffffffu, ol[i], from) : 0u;
     }
-    // lanes whose source lane is in the neighbour quarter: delta > 0: lanes 32 - delta .. 31 (the outermost takes post_b when two
-    // lanes are outside), delta < 0: lanes 0 .. -delta - 1
+    // lanes whose source lane is in the neighbour quarter take that quarter's posted copy: delta > 0: lanes 32 - delta .. 31 (the
+    // outermost takes post_b when two lanes are outside), delta < 0: lanes 0 .. -delta - 1
     const int out = delta > 0 ? lane - (32 - delta) : (-delta - 1) - lane;  // >= 0: outside; 0 = nearest the inside
     if (out >= 0) ts_fetch16((out == 0 || post_b == nullptr) ? post_a : post_b, have, hh, ll);
     ts_st_slot<SPLIT>(tl, col0 + 8 * dst, lo_off, hh, ll);
@@ -270,34 +266,35 @@ __global__ void __launch_bounds__(EA_THREADS, 1) enca_kernel(const __grid_consta
             mbar_wait(&d2_full, n & 1);
             tc_fence_after();
             uint32_t *xw = xb + (size_t)(((n & 1) * 4 + q) * 2) * 48;
+            uint32_t oh[8], ol[8];  // this warp's pooled sample h of every lane, kept for the halo slots it supplies
             {
                 float v[16];
                 ea_load_pool16(&p.bias_c[EA_B2], tl + EA_COL_D23, 32 * h, 32 * h + 16, v);
-                uint32_t hh[8], ll[8];
-                ts_pack16<SPLIT>(v, valid, hh, ll);
-                ts_st_slot<SPLIT>(tl, EA_COL_A3 + 8 * (3 + h), EA_A3_LO, hh, ll);
+                ts_pack16<SPLIT>(v, valid, oh, ol);
+                ts_st_slot<SPLIT>(tl, EA_COL_A3 + 8 * (3 + h), EA_A3_LO, oh, ol);
                 // posts: first = [lane 0 sample 0, lane 0 sample 1, lane 1 sample 0]; last = [lane 31 sample 0, lane 31 sample 1, lane 30 sample 1]
-                if (lane == 0) ts_post16(xw + h * 16, hh, ll);
-                if (lane == 1 && h == 0) ts_post16(xw + 2 * 16, hh, ll);
-                if (lane == 31) ts_post16(xw + 48 + h * 16, hh, ll);
-                if (lane == 30 && h == 1) ts_post16(xw + 48 + 2 * 16, hh, ll);
+                if (lane == 0) ts_post16(xw + h * 16, oh, ol);
+                if (lane == 1 && h == 0) ts_post16(xw + 2 * 16, oh, ol);
+                if (lane == 31) ts_post16(xw + 48 + h * 16, oh, ol);
+                if (lane == 30 && h == 1) ts_post16(xw + 48 + 2 * 16, oh, ol);
             }
-            tmem_st_wait();
-            tc_fence_before();
-            named_bar_sync(2, 256);
-            tc_fence_after();
-            if (h == 0) {  // right halo: slot 5 = sample 0 of lane r + 1, slot 6 = its sample 1, slot 7 = sample 0 of lane r + 2
-                const uint32_t *xe = xb + (size_t)(((n & 1) * 4 + (q + 1) % 4) * 2) * 48;
-                const bool have = q < 3;
-                ea_halo_slot<SPLIT>(tl, EA_COL_A3, EA_A3_LO, 3, 5, 1, lane, have, xe, nullptr);
-                ea_halo_slot<SPLIT>(tl, EA_COL_A3, EA_A3_LO, 4, 6, 1, lane, have, xe + 16, nullptr);
-                ea_halo_slot<SPLIT>(tl, EA_COL_A3, EA_A3_LO, 3, 7, 2, lane, have, xe, xe + 32);
-            } else {  // left halo: slot 2 = sample 1 of lane r - 1, slot 1 = its sample 0, slot 0 = sample 1 of lane r - 2
-                const uint32_t *xe = xb + (size_t)(((n & 1) * 4 + (q + 3) % 4) * 2 + 1) * 48;
-                const bool have = q > 0;
-                ea_halo_slot<SPLIT>(tl, EA_COL_A3, EA_A3_LO, 4, 2, -1, lane, have, xe + 16, nullptr);
-                ea_halo_slot<SPLIT>(tl, EA_COL_A3, EA_A3_LO, 3, 1, -1, lane, have, xe, nullptr);
-                ea_halo_slot<SPLIT>(tl, EA_COL_A3, EA_A3_LO, 4, 0, -2, lane, have, xe + 16, xe + 32);
+            named_bar_sync(2, 256);  // the posts are visible
+            {
+                // The six halo slots by OWNER of the data (shuffled from registers, no TMEM re-read): sample 0 (warp h = 0) feeds slot 5
+                // of lane r - 1, slot 7 of lane r - 2 and slot 1 of lane r + 1; sample 1 (warp h = 1) feeds slot 6 of lane r - 1, slot 2
+                // of lane r + 1 and slot 0 of lane r + 2.  Seen from the receiving lane: (destination slot, lane distance of the source).
+                const uint32_t *xn = xb + (size_t)(((n & 1) * 4 + (q + 1) % 4) * 2) * 48;      // next quarter: first = [l0 s0, l0 s1, l1 s0]
+                const uint32_t *xp = xb + (size_t)(((n & 1) * 4 + (q + 3) % 4) * 2 + 1) * 48;  // previous quarter: last = [l31 s0, l31 s1, l30 s1]
+                const bool hn = q < 3, hp = q > 0;
+                if (h == 0) {
+                    ea_halo_regs<SPLIT>(tl, EA_COL_A3, EA_A3_LO, oh, ol, 5, 1, lane, hn, xn, nullptr);
+                    ea_halo_regs<SPLIT>(tl, EA_COL_A3, EA_A3_LO, oh, ol, 7, 2, lane, hn, xn, xn + 32);
+                    ea_halo_regs<SPLIT>(tl, EA_COL_A3, EA_A3_LO, oh, ol, 1, -1, lane, hp, xp, nullptr);
+                } else {
+                    ea_halo_regs<SPLIT>(tl, EA_COL_A3, EA_A3_LO, oh, ol, 6, 1, lane, hn, xn + 16, nullptr);
+                    ea_halo_regs<SPLIT>(tl, EA_COL_A3, EA_A3_LO, oh, ol, 2, -1, lane, hp, xp + 16, nullptr);
+                    ea_halo_regs<SPLIT>(tl, EA_COL_A3, EA_A3_LO, oh, ol, 0, -2, lane, hp, xp + 16, xp + 32);
+                }
             }
             tmem_st_wait();
             tc_fence_before();
