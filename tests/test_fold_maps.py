@@ -128,14 +128,16 @@ def test_encoder_tmem_slots_and_two_lane_halo():
 
 
 def test_item_tiling_covers_the_kept_rows():
-    """decb2_launch / enca_launch: items of 120 (94) valid rows cover the kept rows of a window; lanes outside are never stored."""
+    """decb2_launch / enca_launch: items of 112 (94) used rows cover the kept rows of a window; lanes outside are never stored."""
     for keep_lo, keep_hi in [(0, 6000), (500, 5500), (1000, 5000), (0, 16), (5984, 6000)]:
         row_off0, row_hi = keep_lo // 16, (keep_hi + 15) // 16
-        tiles = (row_hi - row_off0 + 119) // 120
+        tiles = (row_hi - row_off0 + 111) // 112
         covered = set()
         for j in range(tiles):
-            R0 = row_off0 + 120 * j - 4
-            covered |= {R0 + r for r in range(4, 124) if 0 <= R0 + r < 375 and R0 + r < row_hi}
+            R0 = row_off0 + 112 * j - 4
+            covered |= {R0 + r for r in range(4, 116) if 0 <= R0 + r < 375 and R0 + r < row_hi}
         assert covered == set(range(row_off0, min(row_hi, 375)))
+        if (keep_lo, keep_hi) == (500, 5500):
+            assert tiles == 3  # a blinded window: three items, as with the 120 valid lanes
     tiles = (375 + 93) // 94
     assert {94 * j - 3 + r for j in range(tiles) for r in range(3, 97) if 94 * j - 3 + r < 375} == set(range(375))

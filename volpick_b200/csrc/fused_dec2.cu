@@ -24,14 +24,14 @@
 //   D3[r][block * 16 + phase * 8 + c]  --epilogue B--> fp32 planar [c][16 r + i] in shared memory --head warps--> y
 //
 // Every layer loses one lane on each side of the item (its halo comes from the neighbour lane): lanes 4 .. 123 carry valid
-// outputs, an item yields 120 rows = 1920 output samples, three items cover the 5000 kept samples of a blinded window.  Rows
+// outputs; an item uses lanes 4 .. 115 = 112 rows = 1792 output samples, three items cover the 5000 kept samples of a blinded window.  Rows
 // outside the sequence are written as zeros at every level (they are the convs' zero padding).
 //
 // TMEM columns (512): [0, 128) A2, which also hosts the accumulators D0 / D1 of the NEXT item while A2 is dead; [128, 352) A3;
 // [352, 480) D2 / D3.  The issuer interleaves the shared-memory half of item n + 1 with the TMEM half of item n
 // (L2(n), L0(n+1), L1(n+1), L3(n)), so each epilogue runs under the other item's MMAs.
-// Warps (25): tcgen05 issuer; 8 epilogue warps A (D0 -> S1, D1 -> A2; they also issue the TMA load of the next item); 8 epilogue warps
-// B (D2 -> A3, D3 -> head buffer); 8 head warps (sigmoid(conv k11), 8 outputs per thread).  Two epilogue warps share a TMEM lane
+// Warps (24): tcgen05 issuer; 8 epilogue warps A (D0 -> S1, D1 -> A2; they also issue the TMA load of the next item); 8 epilogue warps
+// B (D2 -> A3, D3 -> head buffer); 7 head warps (sigmoid(conv k11), 8 outputs per thread).  Two epilogue warps share a TMEM lane
 // quarter and split its columns.  Hand-over by mbarriers; the two halves of a group meet at one named barrier per item (halo exchange).
 #include <algorithm>
 #include <cstdlib>
@@ -44,8 +44,9 @@
 
 namespace vp {
 
-constexpr int D2_THREADS = 32 * 25;
-constexpr int D2_LANE_LO = 4, D2_USE = 120;  // lanes [4, 124) of an item are valid at the output
+constexpr int D2_THREADS = 32 * 24;
+constexpr int D2_LANE_LO = 4, D2_USE = 112;  // lanes [4, 124) of an item are valid at the output; [4, 116) are used: three items still cover
+                                             // the 313 kept rows of a blinded window, and 2 x 112 head threads are seven warps -> 24 warps, 80 registers
 constexpr int D2_IN_ROWS = 132;              // input rows R0 - 2 .. R0 + 129
 constexpr int D2_S1_ROWS = 130;              // lanes -1 .. 128 of the 750 level (rows 0 and 129 stay zero)
 constexpr int D2_RP = 2048;                  // floats per channel of the head buffer
@@ -183,7 +184,7 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decb2_kernel(const __grid_const
         mbar_init(&a3_full, 8);
         mbar_init(&d23_free, 8);
         mbar_init(&head_go, 8);
-        mbar_init(&head_done, 8);
+        mbar_init(&head_done, 7);
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(&tmem_base_s, 512);
@@ -482,7 +483,7 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decb2_kernel(const __grid_const
             if (n > 0) {
                 mbar_wait(&head_done, (n - 1) & 1);
 #ifdef VP_RACECHECK_BARRIERS
-                named_bar_sync(4, 512);
+                named_bar_sync(4, 480);
 #endif
             }
             prof.lap(1);
@@ -515,13 +516,14 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decb2_kernel(const __grid_const
                 mbar_arrive(&d23_free);
             }
 #ifdef VP_RACECHECK_BARRIERS  // debug build for compute-sanitizer racecheck (it models bar.sync, not mbarriers): same program points
-            named_bar_sync(3, 512);
+            named_bar_sync(3, 480);
 #endif
         }
         prof.flush(warp, lane);
     } else {
         // ================= head warps: sigmoid(conv k11) of item n while the pipeline runs item n + 1
-        const int rr = ((warp - 17) & 3) * 32 + lane, half = (warp - 17) >> 2;
+        const int e = (warp - 17) * 32 + lane;  // 224 head threads: outputs 8 half .. 8 half + 7 of lane 4 + rr
+        const int half = e >= D2_USE ? 1 : 0, rr = e - half * D2_USE;
         const float *hbuf = reinterpret_cast<const float *>(d2_smem + p.head_off);
         D2Prof prof;  // 0 head_go, 1 head
         prof.start();
@@ -531,14 +533,14 @@ __global__ void __launch_bounds__(D2_THREADS, 1) decb2_kernel(const __grid_const
             const int R0 = p.row_off0 + D2_USE * j - D2_LANE_LO;
             mbar_wait(&head_go, n & 1);
 #ifdef VP_RACECHECK_BARRIERS
-            named_bar_sync(3, 512);
+            named_bar_sync(3, 480);
 #endif
             prof.lap(0);
             if (!(p.dbg & 4)) d2_head(p, g, b, R0, rr, half, hbuf);
             __syncwarp();
             if (lane == 0) mbar_arrive(&head_done);
 #ifdef VP_RACECHECK_BARRIERS
-            if (n + 1 < n_my) named_bar_sync(4, 512);  // pairs with the next item's head_done wait of epilogue B
+            if (n + 1 < n_my) named_bar_sync(4, 480);  // pairs with the next item's head_done wait of epilogue B
 #endif
             prof.lap(1);
         }
