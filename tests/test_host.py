@@ -164,6 +164,32 @@ def test_pick_containers():
         vb.Pick("XX.A.", t + 2, t + 3, t + 1, 0.9, "P")
 
 
+def test_pick_lists_come_out_in_sorted_order():
+    """models._run builds the objects per record and orders them with one lexsort over (start ns, end ns, trace_id, phase):
+    the same list as sorted() over the objects (Pick.__lt__ / Detection.__lt__), ties included."""
+    rng = np.random.default_rng(5)
+    base = 1_600_000_000_000_000_000
+    parts, dparts, plain, dplain = [], [], [], []
+    for r in range(6):
+        for lab in ("P", "S"):
+            s0 = np.sort(rng.integers(0, 2000, 300))  # many equal start times across records, stations and phases
+            ns0, ns1, nsp = base + s0 * 10**7, base + (s0 + rng.integers(1, 4, 300)) * 10**7, base + s0 * 10**7 + 5
+            vals = rng.random(300).astype(np.float32)
+            tid = "XX.S%d." % (r % 3)
+            parts.append((tid, lab, ns0, ns1, models.WaveformModel._build_objects(tid, lab, UTCDateTime, ns0, ns1, nsp, vals)))
+            plain += [vb.Pick(tid, UTCDateTime(ns=a), UTCDateTime(ns=b), UTCDateTime(ns=c), v, lab)
+                      for a, b, c, v in zip(ns0.tolist(), ns1.tolist(), nsp.tolist(), vals.tolist())]
+        dparts.append((tid, "", ns0, ns1, models.WaveformModel._build_objects(tid, "", UTCDateTime, ns0, ns1, None, vals)))
+        dplain += [vb.Detection(tid, UTCDateTime(ns=a), UTCDateTime(ns=b), v) for a, b, v in zip(ns0.tolist(), ns1.tolist(), vals.tolist())]
+    got, want = models.WaveformModel._sorted_objects(parts), sorted(plain)
+    assert len(got) == len(want) == 3600 and all(a == b for a, b in zip(got, want))
+    got, want = models.WaveformModel._sorted_objects(dparts), sorted(dplain)
+    assert len(got) == 1800 and all(a == b for a, b in zip(got, want))
+    assert models.WaveformModel._sorted_objects([]) == []
+    with pytest.raises(ValueError):  # Pick.__init__'s ordering check survives the bulk constructor
+        models.WaveformModel._build_objects("XX.A.", "P", UTCDateTime, ns0, ns1, ns1 + 1, vals)
+
+
 def test_filter_design_matches_oracle():
     """filter_args / filter_kwargs (model_training/test_onephase.ipynb cell 43): the host designs the same second-order
     sections as the oracle's ObsPy restatement; the records are filtered on the device (GPU test)."""

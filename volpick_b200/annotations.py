@@ -23,6 +23,13 @@ class Pick:
             if not start_time <= peak_time <= end_time:
                 raise ValueError("peak_time must be between start_time and end_time.")
 
+    @classmethod
+    def _trusted(cls, trace_id, start_time, end_time, peak_time, peak_value, phase):
+        """Constructor without the ordering check, for callers that checked start <= peak <= end on whole arrays."""
+        p = cls.__new__(cls)
+        p.trace_id, p.start_time, p.end_time, p.peak_time, p.peak_value, p.phase = trace_id, start_time, end_time, peak_time, peak_value, phase
+        return p
+
     def _key(self):
         end = self.end_time if self.end_time is not None else self.start_time
         return (self.start_time.ns if hasattr(self.start_time, "ns") else self.start_time,
