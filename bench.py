@@ -49,8 +49,8 @@ KCLASS_FLOP_PER_WINDOW = {
     ("phasenet", "tcconv"): 38.92e6,  # every Conv1d / ConvTranspose1d of the network runs in tcconv_kernel
 }
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture (profiles/):
-KCLASS_NCU_TRAFFIC = {("eqtransformer", "decb", "f16x3"): {"bytes_per_launch": 552.48e6 + 219.49e6, "windows_per_launch": 4096,
-                                                            "source": "profiles/r02c_f16x3_top_kernels_ncu_full.md (decb2_kernel)"}}
+KCLASS_NCU_TRAFFIC = {("eqtransformer", "decb", "f16x3"): {"bytes_per_launch": 552.65e6 + 220.10e6, "windows_per_launch": 4096,
+                                                            "source": "profiles/r02g_f16x3_top_kernels_ncu_full.md (decb2_kernel)"}}
 CONFIGS = {
     # BASELINE.json configs[1] / configs[3]: EQTransformer, overlap 5500, blinding (500, 500), avg, P/S threshold 0.2
     "eqtransformer": dict(overlap=5500, blinding=(500, 500), stacking="avg", P_threshold=0.2, S_threshold=0.2),

@@ -640,6 +640,9 @@ static int fold_same_conv(const FoldedConv &f, int cout, const int *c_src, const
 static int build_pn_tc(vp_model *m, const float *incW, const float *incB, const BN &incBN, const float *const *dsW, const BN *dsBN,
                        const float *const *ddW, const BN *ddBN, const float *const *utW, const BN *utBN,
                        const float *const *usW, const BN *usBN) {
+    // N groups of the three layers whose weights exceed the shared memory (A/B aid: VP_PN_GROUPS="dd,us,ut")
+    int g_dd = 4, g_us = 4, g_ut = 4;
+    if (const char *e = getenv("VP_PN_GROUPS")) sscanf(e, "%d,%d,%d", &g_dd, &g_us, &g_ut);
     for (int set = 0; set < 2; ++set) {
         const int split = set == 0 ? 2 : 1;
         vp_model::PnTcSet &ts = m->pn_tc[set];
@@ -678,7 +681,7 @@ static int build_pn_tc(vp_model *m, const float *incW, const float *incB, const 
                 for (int ci = 0; ci < f; ++ci)
                     for (int j = 0; j < 7; ++j)
                         v.w[((size_t)co * 4 * f + (j & 3) * f + ci) * 2 + (j >> 2)] = fd.w[((size_t)co * f + ci) * 7 + j];
-            rc = build(ts.dd[i], v, 4 * f, f, 2, f == 64 ? 4 : 1, 0);
+            rc = build(ts.dd[i], v, 4 * f, f, 2, f == 64 ? g_dd : 1, 0);
             if (rc != VP_OK) return rc;
         }
         for (int i = 0; i < 4; ++i) {
@@ -699,10 +702,10 @@ static int build_pn_tc(vp_model *m, const float *incW, const float *incB, const 
                         dst[0] = q < 3 ? (float)((double)w7[q + 4] * sc[co]) : 0.f;  // x[r - 1]
                     }
                 }
-            rc = build(ts.ut[i], v, last, 4 * f, 2, 4 * f > 128 ? 4 : 1, 1);
+            rc = build(ts.ut[i], v, last, 4 * f, 2, 4 * f > 128 ? g_ut : 1, 1);
             if (rc != VP_OK) return rc;
             last = f;
-            rc = build(ts.us[i], fold_conv(usW[i], nullptr, usBN[i], f, 2 * f, 7, 2 * f), 2 * f, f, 7, f == 64 ? 4 : 1, 3);
+            rc = build(ts.us[i], fold_conv(usW[i], nullptr, usBN[i], f, 2 * f, 7, 2 * f), 2 * f, f, 7, f == 64 ? g_us : 1, 3);
             if (rc != VP_OK) return rc;
             if (i == 3) {  // folded form: [skip_0 at offset 3 | up at offset 1 + off = 2] -> head, output offset 3 (3 row taps each)
                 FoldedConv v;

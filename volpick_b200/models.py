@@ -145,22 +145,25 @@ _COPY_POOL = None
 
 
 def _copy_jobs(jobs) -> None:
-    """dst[...] = src for every (dst, src): the components of a long record are copied by a few host threads (NumPy
-    releases the GIL in its copy loops; one thread moves ~5 GB/s, a station-day is 104 MB)."""
+    """dst[...] = src for every (dst, src): long records are copied in pieces of 2 M samples by a few host threads (NumPy
+    releases the GIL in its copy loops; one thread moves ~5 GB/s, a station-day is 104 MB -- with PhaseNet the assembly of
+    a record into the pinned ring, not the GPU, paces ``classify(stream)``)."""
     global _COPY_POOL
-    if len(jobs) < 2 or sum(d.size for d, _ in jobs) < (1 << 20):
+    if sum(d.size for d, _ in jobs) < (1 << 20):
         for d, src in jobs:
             d[...] = src
         return
     if _COPY_POOL is None:
         from concurrent.futures import ThreadPoolExecutor
 
-        _COPY_POOL = ThreadPoolExecutor(max_workers=3, thread_name_prefix="vp-copy")
+        _COPY_POOL = ThreadPoolExecutor(max_workers=max(2, min(8, (os.cpu_count() or 4) // 2)), thread_name_prefix="vp-copy")
+    piece = 1 << 21
+    parts = [(d[a : a + piece], src[a : a + piece]) for d, src in jobs for a in range(0, d.shape[0], piece)]
 
     def one(job):
         job[0][...] = job[1]
 
-    list(_COPY_POOL.map(one, jobs))
+    list(_COPY_POOL.map(one, parts))
 
 
 class _PendingRecord:
