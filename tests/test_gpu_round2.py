@@ -240,6 +240,54 @@ def test_multi_segment_stream_vs_oracle(pn, sd_pn):
     assert n_ref >= 4
 
 
+def test_records_assembled_by_the_helper_thread(pn, monkeypatch):
+    """Long streams have their records assembled one ahead by a helper thread into a ring of three pinned buffers (models._run);
+    forced here on a short multi-station stream with a gap and a too-short fragment: same picks, same annotation traces and the
+    same warnings as the inline path; an error in the middle of the stream leaves no thread and no record behind."""
+    import threading
+
+    traces = []
+    for j in range(5):
+        x = synthetic_record(20 + j, 30_000)
+        t0 = station_start(20 + j)
+        hdr = dict(network="XX", station=f"T{j}", location="", sampling_rate=100.0)
+        for i, c in enumerate("ZNE"):
+            traces.append(vb.Trace(x[i, :14_000], dict(hdr, channel="HH" + c, starttime=t0)))
+            traces.append(vb.Trace(x[i, 16_000:], dict(hdr, channel="HH" + c, starttime=t0 + 160.0)))
+        traces.append(vb.Trace(x[0, :1000], dict(hdr, channel="HHZ", starttime=t0 + 1000.0)))  # shorter than a window
+    st = vb.Stream(traces)
+    inline_picks, inline_ann = pn.classify(st).picks, pn.annotate(st)
+    assert len(inline_picks) >= 5
+    pn._prefetch_min_samples = 0
+    try:
+        for _ in range(3):
+            picks, ann = pn.classify(st).picks, pn.annotate(st)
+            assert picks == inline_picks and len(ann) == len(inline_ann) == 30
+            for u, v in zip(ann, inline_ann):
+                assert u.stats.channel == v.stats.channel and u.stats.starttime == v.stats.starttime
+                np.testing.assert_array_equal(u.data, v.data)
+        from volpick_b200 import models
+
+        calls, real = [0], models._copy_jobs
+
+        def failing(jobs):  # the fourth record fails while the helper thread assembles it (two records are in flight then)
+            calls[0] += 1
+            if calls[0] == 4:
+                raise OSError("simulated read error")
+            return real(jobs)
+
+        monkeypatch.setattr(models, "_copy_jobs", failing)
+        with pytest.raises(OSError, match="simulated read error"):
+            pn.classify(st)
+        monkeypatch.setattr(models, "_copy_jobs", real)
+        assert pn.classify(st).picks == inline_picks  # the ring and the slots are usable after the failure
+    finally:
+        del pn._prefetch_min_samples
+    import time
+    time.sleep(0.3)
+    assert not [t for t in threading.enumerate() if t.name == "vp-assemble" and t.is_alive()]
+
+
 def test_int32_stream_equals_float_stream(eqt):
     """Traces of int32 counts stay int32 on the wire (converted by the slicer on the device): same picks and
     probabilities as the float32 stream of the same counts."""

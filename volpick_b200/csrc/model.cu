@@ -640,8 +640,12 @@ static int fold_same_conv(const FoldedConv &f, int cout, const int *c_src, const
 static int build_pn_tc(vp_model *m, const float *incW, const float *incB, const BN &incBN, const float *const *dsW, const BN *dsBN,
                        const float *const *ddW, const BN *ddBN, const float *const *utW, const BN *utBN,
                        const float *const *usW, const BN *usBN) {
-    // N groups of the three layers whose weights exceed the shared memory (A/B aid: VP_PN_GROUPS="dd,us,ut")
-    int g_dd = 4, g_us = 4, g_ut = 4;
+    // N groups of the three layers whose weights exceed the shared memory: the stride-4 conv 64 -> 64 (K = 512), the concat conv
+    // 128 -> 64 (K = 896) and the transposed conv 128 -> 4 x 64 (K = 256).  Two groups of N = 32 leave room for ONE A stage only,
+    // but an N = 16 MMA costs the tensor pipe as much as an N = 32 one and every group re-reads the A tiles: tcconv class 3.24 ->
+    // 3.13 ms per station-day for the first two; the transposed conv is faster with four groups of N = 64 (3.27 with two).
+    // A/B aid: VP_PN_GROUPS="dd,us,ut".
+    int g_dd = 2, g_us = 2, g_ut = 4;
     if (const char *e = getenv("VP_PN_GROUPS")) sscanf(e, "%d,%d,%d", &g_dd, &g_us, &g_ut);
     for (int set = 0; set < 2; ++set) {
         const int split = set == 0 ? 2 : 1;

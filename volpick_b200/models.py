@@ -764,6 +764,8 @@ class WaveformModel:
             p.threshold[i] = float(thresholds[i])
         return p
 
+    _prefetch_min_samples = 1 << 22  # streams at least this long get their records assembled by the helper thread (_run)
+
     def annotate_array(self, trace, argdict: Optional[Dict[str, Any]] = None, want_annotation: bool = True,
                        thresholds: Optional[Sequence[float]] = None, pick_capacity: int = 1 << 16):
         """One gap-free (3, n) record through ``vp_annotate``.
@@ -876,25 +878,88 @@ class WaveformModel:
             self._slots = (self._device_index, [torch.cuda.Stream(self._device_index) for _ in range(2)], [None, None])
         slot_streams, slot_ws = self._slots[1], self._slots[2]
         in_flight = deque()
-        # pinned staging ring: record i is assembled straight into slot (i & 1)'s page-locked buffer (kept across calls:
-        # page-locking 104 MB costs more than a station-day of compute), so vp_annotate_begin returns after enqueueing
-        # and the H2D pieces of record i + 1 run under the network of record i
-        if getattr(self, "_pinned", None) is None:
-            self._pinned = [None, None]
+        # pinned staging ring: a record is assembled straight into one of three page-locked buffers (kept across calls:
+        # page-locking 104 MB costs more than a station-day of compute), so vp_annotate_begin returns after enqueueing and
+        # the H2D pieces of record i + 1 run under the network of record i.  Three buffers = two records in flight + the one
+        # being assembled; `free` counts the buffers nobody holds.
+        import queue
+        import threading
+
+        if getattr(self, "_pinned", None) is None or len(self._pinned) != 3:
+            self._pinned = [None, None, None]
+        ring = {"n": 0}
+        free = threading.Semaphore(3)
+        stop = threading.Event()
         n_rec = 0
 
-        def alloc(shape, dtype):
-            k = n_rec & 1
+        def alloc(shape, dtype):  # runs in whichever thread iterates _iter_stream_arrays
+            while not free.acquire(timeout=0.05):
+                if stop.is_set():
+                    raise RuntimeError("the call that owns this record stream has ended")
+            k = ring["n"] % 3
+            ring["n"] += 1
             nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
             buf = self._pinned[k]
             if buf is None or buf.numel() < nbytes:
                 self._pinned[k] = None
-                buf = self._pinned[k] = torch.empty(max(nbytes, 1), dtype=torch.uint8, pin_memory=True)
+                with torch.cuda.device(self._device_index):
+                    buf = self._pinned[k] = torch.empty(max(nbytes, 1), dtype=torch.uint8, pin_memory=True)
             return buf[:nbytes].view(torch.int32 if np.dtype(dtype) == np.int32 else torch.float32).view(*shape).numpy()
 
+        def all_records():
+            """(stats of the group's first trace, trace_id, t0, record, record sits in a ring buffer) over all instruments."""
+            for key in groups:
+                trs = groups[key]
+                s0 = trs[0].stats
+                trace_id = f"{s0.network}.{s0.station}.{s0.location}"
+                it = self._iter_stream_arrays(trs, argdict, alloc)
+                while True:
+                    before = ring["n"]
+                    try:
+                        t0, arr = next(it)
+                    except StopIteration:
+                        break
+                    yield s0, trace_id, t0, arr, ring["n"] > before
+
+        def prefetched(gen):
+            """``gen`` run by a helper thread, one record ahead: with PhaseNet the assembly of a station-day (2.8 ms of host
+            copies) is as long as its GPU time, so it has to overlap the main thread's begin / collect / pick objects."""
+            q = queue.Queue(maxsize=1)
+
+            def put(x):
+                while not stop.is_set():
+                    try:
+                        q.put(x, timeout=0.05)
+                        return True
+                    except queue.Full:
+                        pass
+                return False
+
+            def run():
+                try:
+                    for item in gen:
+                        if not put(("item", item)):
+                            return
+                    put(("end", None))
+                except BaseException as e:  # re-raised in the calling thread
+                    put(("error", e))
+
+            threading.Thread(target=run, name="vp-assemble", daemon=True).start()
+            while True:
+                kind, val = q.get()
+                if kind == "end":
+                    return
+                if kind == "error":
+                    raise val
+                yield val
+
         def collect():
-            (s0, trace_id, t0), handle = in_flight.popleft()
-            annotation, triggers, trim = handle.result()
+            (s0, trace_id, t0, pinned), handle = in_flight.popleft()
+            try:
+                annotation, triggers, trim = handle.result()
+            finally:
+                if pinned:
+                    free.release()  # the record's H2D copy is over: its ring buffer may be overwritten
             mk = type(t0)  # UTCDateTime-like: built straight from integer nanoseconds
             for li, label in enumerate(self.labels):
                 first, last = int(trim[li, 0]), int(trim[li, 1])
@@ -927,45 +992,54 @@ class WaveformModel:
         prof = os.environ.get("VP_PROFILE_HOST")  # host wall clock by phase of this call (stderr)
         tp = {"pre": _time.perf_counter() - t_run, "assemble": 0.0, "begin": 0.0, "collect": 0.0}
 
-        def timed_records(trs):
-            it = iter(self._iter_stream_arrays(trs, argdict, alloc))
+        # long streams: records assembled one ahead by the helper thread; short ones inline
+        long_stream = sum(len(tr.data) for tr in stream) >= self._prefetch_min_samples
+        source = prefetched(all_records()) if long_stream else all_records()
+        try:
             while True:
                 t_a = _time.perf_counter()
                 try:
-                    item = next(it)
+                    s0, trace_id, t0, arr, pinned = next(source)
                 except StopIteration:
-                    return
+                    break
                 tp["assemble"] += _time.perf_counter() - t_a
-                yield item
-
-        for key in groups:
-            trs = groups[key]
-            s0 = trs[0].stats
-            trace_id = f"{s0.network}.{s0.station}.{s0.location}"
-            for t0, arr in timed_records(trs):
                 if arr.shape[1] < self.in_samples:
                     logger.warning("Parts of the input stream consist of fragments shorter than the number of "
                                    "input samples. Output might be empty.")
+                    if pinned:
+                        free.release()
                     continue
-                k = n_rec & 1
-                n_rec += 1  # the next alloc() hands out the other slot; this slot is reused only after its collect()
+                k = n_rec & 1  # stream / workspace slot; reused only after its collect()
+                n_rec += 1
                 need = self.annotate_workspace_bytes(arr.shape[1], argdict, True)
                 if slot_ws[k] is None or slot_ws[k].numel() < need:
                     slot_ws[k] = None
                     slot_ws[k] = torch.empty(need, dtype=torch.uint8, device=self._device)
                 t_b = _time.perf_counter()
-                handle = self.annotate_array_async(arr, argdict, want_annotation, thresholds, stream=slot_streams[k],
-                                                   workspace=slot_ws[k])
+                try:
+                    handle = self.annotate_array_async(arr, argdict, want_annotation, thresholds, stream=slot_streams[k],
+                                                       workspace=slot_ws[k])
+                except BaseException:
+                    if pinned:
+                        free.release()
+                    raise
                 tp["begin"] += _time.perf_counter() - t_b
-                in_flight.append(((s0, trace_id, t0), handle))
+                in_flight.append(((s0, trace_id, t0, pinned), handle))
                 if len(in_flight) == 2:
                     t_c = _time.perf_counter()
                     collect()
                     tp["collect"] += _time.perf_counter() - t_c
-        while in_flight:
-            t_c = _time.perf_counter()
-            collect()
-            tp["collect"] += _time.perf_counter() - t_c
+            while in_flight:
+                t_c = _time.perf_counter()
+                collect()
+                tp["collect"] += _time.perf_counter() - t_c
+        finally:
+            stop.set()  # an exception above must not leave the helper thread waiting for a buffer or for the queue
+            while in_flight:  # nor a record in flight on a buffer that the next call overwrites
+                try:
+                    in_flight.popleft()[1].result()
+                except Exception:
+                    pass
         t_c = _time.perf_counter()
         result = (StreamT(out_traces), PickList(self._sorted_objects(picks)), DetectionList(self._sorted_objects(detections)))
         tp["order"] = _time.perf_counter() - t_c
