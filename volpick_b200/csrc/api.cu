@@ -118,8 +118,10 @@ CopyPipe *copy_pipe(unsigned rotation) {
 }
 
 // measured: EQTransformer 1024 -> 4096 windows per launch group = -10 % forward time; PhaseNet host records: 2048 overlaps
-// the H2D pieces best (158 vs 152 station-days/s end to end), device-resident 4096 is 3 % faster
-int64_t default_chunk(const vp_model *m) { return vp_model_kind(m) == VP_KIND_PHASENET ? 2048 : 4096; }
+// the H2D pieces best (158 vs 152 station-days/s end to end, round 1), device-resident 4096 is 3 % faster.  Round 2 (first chunk a
+// quarter chunk, two records in flight): 2880 = half a station-day's 5,756 windows per lane: 319.6 device-resident / 276.9 end to end
+// against 302.7 / 272.4 with 2048; 4096 is as fast device-resident but starts later behind the H2D copy
+int64_t default_chunk(const vp_model *m) { return vp_model_kind(m) == VP_KIND_PHASENET ? 2880 : 4096; }
 
 // Two forward lanes: consecutive chunks of a record are independent until the stacker, so odd chunks run on a second
 // stream with their own forward workspace.  The latency-bound kernels of one chunk (LSTM recurrences, attention, the
