@@ -458,6 +458,25 @@ def test_handles_on_two_devices_in_one_process():
         np.testing.assert_array_equal(t0, t1)
 
 
+@pytest.mark.parametrize("B", [1, 7, 64])
+def test_attention_kernels_agree(eqt, B, monkeypatch):
+    """seq.cu: attention2_kernel (two lanes per query time step, halves joined by shuffles; the default) against
+    attention_kernel (one thread per query, VP_ATTN_V1=1): the transformer blocks (full attention + LayerNorm + feed-forward)
+    and the banded pick attentions differ only in summation order -- bottleneck tap and probabilities within fp32 rounding."""
+    rng = np.random.default_rng(40 + B)
+    x = rng.standard_normal((B, 3, 6000)).astype(np.float32)
+    x[:, :, 3100:3500] *= 8.0
+    xd = torch.from_numpy(x).cuda()
+    monkeypatch.setenv("VP_ATTN_V1", "0")
+    new = torch.stack(eqt.forward(xd, precision="f16x3"), dim=1).cpu().numpy()
+    monkeypatch.setenv("VP_ATTN_V1", "1")
+    old = torch.stack(eqt.forward(xd, precision="f16x3"), dim=1).cpu().numpy()
+    assert np.isfinite(new).all() and new.shape == old.shape == (B, 3, 6000)
+    d = float(np.abs(new - old).max())
+    print(f"B={B}: attention v2 vs v1 max|dprob| = {d:.3e}")
+    assert d <= 2e-6
+
+
 # ------------------------------------------------------------------------------------------ decoder tail: TMEM-operand kernel
 @pytest.mark.parametrize("precision,atol", [("f16x3", 2e-5), ("bf16", 5e-2)])
 @pytest.mark.parametrize("B", [1, 3, 50])

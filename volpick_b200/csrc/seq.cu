@@ -6,6 +6,8 @@
 // LayerNormalization, FeedForward and Transformer of seisbench/models/eqtransformer.py
 // (weight shapes from
 // /root/reference/Final_models/volpick/eqtransformer/volpick.pt.v1).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace vp {
@@ -325,6 +327,227 @@ __global__ void __launch_bounds__(AT_NT, 2) attention_kernel(const AttnP p) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The same block with TWO threads per query time step (adjacent lanes): each holds 16 of the 32 attention units, 8 of the 16
+// channels of the weighted sum and 64 of the 128 hidden units of the feed-forward layer; the halves meet in one shuffle per
+// emission (both lanes then take the same softmax path on bit-identical values: a + b == b + a), 8 for the LayerNorm input and 16 for
+// the feed-forward output.  attention_kernel needs 127 registers (q[32], Wa[32], v[16] live in the T x T loop): 15 warps per
+// SM, issue slots 55 % busy, MUFU 36 % (ncu, profiles/r02e) -- latency-bound.  Half the state per thread fits 64 registers:
+// twice the warps for the same work.
+constexpr int A2_TPW = 2 * AT_MAXT;      // threads per window
+constexpr int A2_NT = AT_WPC * A2_TPW;   // 480
+
+__global__ void __launch_bounds__(A2_NT, 2) attention2_kernel(const AttnP p) {
+    extern __shared__ __align__(16) float at_smem[];
+    float *wsm = at_smem;
+    float(*Ks)[AT_MAXT * AT_KP] = reinterpret_cast<float(*)[AT_MAXT * AT_KP]>(at_smem + AT_OFF_K);
+    float(*Xs)[AT_MAXT * AT_XP] = reinterpret_cast<float(*)[AT_MAXT * AT_XP]>(at_smem + AT_OFF_X);
+
+    const int tid = threadIdx.x;
+    const int g = blockIdx.y;
+    const int T = p.T;
+    {
+        const float *src = p.w + (int64_t)g * p.w_gs;
+        const int n = (p.mode == 0) ? AW_SIZE : AW_G1;
+        for (int i = tid; i < n; i += A2_NT) {
+            const float v = __ldg(src + i);
+            wsm[i] = (i >= AW_WA && i < AW_WA + 32) ? -2.f * v : v;  // Wa is only used as -2 Wa
+        }
+    }
+    const int wl = tid / A2_TPW;
+    const int r = tid - wl * A2_TPW;
+    const int i = r >> 1;    // query time step
+    const int hs = r & 1;    // which half of the units / channels / hidden units
+    const int64_t b = (int64_t)blockIdx.x * AT_WPC + wl;
+    const bool bval = b < p.B;
+    const float *xb = p.x + (int64_t)g * p.x_gs + (bval ? b : 0) * p.x_bs;
+    for (int idx = r; idx < 16 * T; idx += A2_TPW) {
+        const int c = idx / T, t = idx - c * T;
+        Xs[wl][t * AT_XP + c] = bval ? __ldg(xb + idx) : 0.f;
+    }
+    __syncthreads();
+
+    const bool act = bval && i < T;
+    const float *xr = &Xs[wl][(i < T ? i : 0) * AT_XP];
+    constexpr float kTwoLog2e = 2.8853900817779268f;
+    float q[16];
+    {
+        float kv[16];
+        const float4 *bh4 = reinterpret_cast<const float4 *>(wsm + AW_BH + hs * 16);
+#pragma unroll
+        for (int u4 = 0; u4 < 4; ++u4) {
+            const float4 t4 = bh4[u4];
+            q[u4 * 4 + 0] = t4.x, q[u4 * 4 + 1] = t4.y, q[u4 * 4 + 2] = t4.z, q[u4 * 4 + 3] = t4.w;
+            kv[u4 * 4 + 0] = kv[u4 * 4 + 1] = kv[u4 * 4 + 2] = kv[u4 * 4 + 3] = 0.f;
+        }
+#pragma unroll 4
+        for (int c = 0; c < 16; ++c) {
+            const float xc = act ? xr[c] : 0.f;
+            const float4 *wt4 = reinterpret_cast<const float4 *>(wsm + AW_WT + c * 32 + hs * 16);
+            const float4 *wx4 = reinterpret_cast<const float4 *>(wsm + AW_WX + c * 32 + hs * 16);
+#pragma unroll
+            for (int u4 = 0; u4 < 4; ++u4) {
+                const float4 a = wt4[u4], k = wx4[u4];
+                q[u4 * 4 + 0] = fmaf(xc, a.x, q[u4 * 4 + 0]), q[u4 * 4 + 1] = fmaf(xc, a.y, q[u4 * 4 + 1]);
+                q[u4 * 4 + 2] = fmaf(xc, a.z, q[u4 * 4 + 2]), q[u4 * 4 + 3] = fmaf(xc, a.w, q[u4 * 4 + 3]);
+                kv[u4 * 4 + 0] = fmaf(xc, k.x, kv[u4 * 4 + 0]), kv[u4 * 4 + 1] = fmaf(xc, k.y, kv[u4 * 4 + 1]);
+                kv[u4 * 4 + 2] = fmaf(xc, k.z, kv[u4 * 4 + 2]), kv[u4 * 4 + 3] = fmaf(xc, k.w, kv[u4 * 4 + 3]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) q[u] = ex2_approx(fminf(fmaxf(kTwoLog2e * q[u], -63.f), 63.f));
+        if (i < T) {
+            float4 *kd = reinterpret_cast<float4 *>(&Ks[wl][i * AT_KP + hs * 16]);
+#pragma unroll
+            for (int u4 = 0; u4 < 4; ++u4)
+                kd[u4] = make_float4(ex2_approx(fminf(fmaxf(kTwoLog2e * kv[u4 * 4 + 0], -63.f), 63.f)),
+                                     ex2_approx(fminf(fmaxf(kTwoLog2e * kv[u4 * 4 + 1], -63.f), 63.f)),
+                                     ex2_approx(fminf(fmaxf(kTwoLog2e * kv[u4 * 4 + 2], -63.f), 63.f)),
+                                     ex2_approx(fminf(fmaxf(kTwoLog2e * kv[u4 * 4 + 3], -63.f), 63.f)));
+        }
+    }
+    __syncthreads();
+
+    float e0 = wsm[AW_BA];
+#pragma unroll 8
+    for (int u = 0; u < 32; ++u) e0 = fmaf(-0.5f, wsm[AW_WA + u], e0);  // ba + sum_u Wa_u
+    float wa[16];
+    {
+        const float4 *wa4 = reinterpret_cast<const float4 *>(wsm + AW_WA + hs * 16);
+#pragma unroll
+        for (int u4 = 0; u4 < 4; ++u4) {
+            const float4 t4 = wa4[u4];
+            wa[u4 * 4 + 0] = t4.x, wa[u4 * 4 + 1] = t4.y, wa[u4 * 4 + 2] = t4.z, wa[u4 * 4 + 3] = t4.w;
+        }
+    }
+    float emax = -INFINITY, ssum = 0.f;
+    float v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] = 0.f;
+    const int half = p.width / 2;
+    for (int jj = 0; jj < T; ++jj) {
+        const float4 *kr = reinterpret_cast<const float4 *>(&Ks[wl][jj * AT_KP + hs * 16]);
+        float ea = 0.f, eb = 0.f;
+#pragma unroll
+        for (int u4 = 0; u4 < 4; ++u4) {
+            const float4 k4 = kr[u4];
+            ea = fmaf(wa[u4 * 4 + 0], rcp_approx(fmaf(q[u4 * 4 + 0], k4.x, 1.f)), ea);
+            eb = fmaf(wa[u4 * 4 + 1], rcp_approx(fmaf(q[u4 * 4 + 1], k4.y, 1.f)), eb);
+            ea = fmaf(wa[u4 * 4 + 2], rcp_approx(fmaf(q[u4 * 4 + 2], k4.z, 1.f)), ea);
+            eb = fmaf(wa[u4 * 4 + 3], rcp_approx(fmaf(q[u4 * 4 + 3], k4.w, 1.f)), eb);
+        }
+        const float mine = ea + eb;
+        const float e = (mine + __shfl_xor_sync(0xffffffffu, mine, 1)) + e0;  // the same bits in both lanes of the pair
+        if (e > emax) {
+            const float sc = ex2_approx(1.4426950408889634f * (emax - e));
+            ssum *= sc;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) v[c] *= sc;
+            emax = e;
+        }
+        bool in_band = true;
+        if (p.width > 0) {
+            const int lower = jj - half;
+            in_band = lower <= i && i < lower + p.width;
+        }
+        if (in_band) {
+            const float w = ex2_approx(1.4426950408889634f * (e - emax));
+            ssum += w;
+            const float *xj = &Xs[wl][jj * AT_XP + hs * 8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) v[c] = fmaf(w, xj[c], v[c]);
+        }
+    }
+    const float inv = 1.f / (ssum + 1e-5f);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] *= inv;
+
+    float *yb = p.y + (int64_t)g * p.y_gs + (bval ? b : 0) * p.y_bs + (int64_t)(hs * 8) * T + i;
+    if (p.mode == 1) {
+        if (act) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) yb[c * T] = v[c];
+        }
+        return;
+    }
+    // transformer tail: y = LN(x + attn); out = LN(y + lin2(relu(lin1(y)))); LayerNorm sums over the pair
+    float y[16];  // [0, 8): this lane's channels, [8, 16): the partner's
+    {
+        float sum = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            y[c] = (act ? xr[hs * 8 + c] : 0.f) + v[c];
+            sum += y[c];
+        }
+        const float mean = (sum + __shfl_xor_sync(0xffffffffu, sum, 1)) * (1.f / 16.f);
+        float var = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float d = y[c] - mean;
+            var = fmaf(d, d, var);
+        }
+        var = (var + __shfl_xor_sync(0xffffffffu, var, 1)) * (1.f / 16.f) + 1e-14f;
+        const float sd = sqrtf(var);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) y[c] = (y[c] - mean) / sd * wsm[AW_G1 + hs * 8 + c] + wsm[AW_B1 + hs * 8 + c];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) y[8 + c] = __shfl_xor_sync(0xffffffffu, y[c], 1);
+    }
+    float o[16];  // same order as y: [own 8 | partner's 8]
+#pragma unroll
+    for (int c = 0; c < 16; ++c) o[c] = 0.f;
+    const int own = hs * 8, oth = 8 - own;
+#pragma unroll 2
+    for (int mm = 0; mm < 64; ++mm) {
+        const int m = hs * 64 + mm;
+        const float4 *w1o = reinterpret_cast<const float4 *>(&wsm[AW_L1W + m * 16 + own]);
+        const float4 *w1p = reinterpret_cast<const float4 *>(&wsm[AW_L1W + m * 16 + oth]);
+        float hsum = wsm[AW_L1B + m];
+#pragma unroll
+        for (int c4 = 0; c4 < 2; ++c4) {
+            const float4 a = w1o[c4], bq = w1p[c4];
+            hsum = fmaf(a.x, y[c4 * 4 + 0], hsum), hsum = fmaf(a.y, y[c4 * 4 + 1], hsum);
+            hsum = fmaf(a.z, y[c4 * 4 + 2], hsum), hsum = fmaf(a.w, y[c4 * 4 + 3], hsum);
+            hsum = fmaf(bq.x, y[8 + c4 * 4 + 0], hsum), hsum = fmaf(bq.y, y[8 + c4 * 4 + 1], hsum);
+            hsum = fmaf(bq.z, y[8 + c4 * 4 + 2], hsum), hsum = fmaf(bq.w, y[8 + c4 * 4 + 3], hsum);
+        }
+        hsum = fmaxf(hsum, 0.f);
+        const float4 *w2o = reinterpret_cast<const float4 *>(&wsm[AW_L2W + m * 16 + own]);
+        const float4 *w2p = reinterpret_cast<const float4 *>(&wsm[AW_L2W + m * 16 + oth]);
+#pragma unroll
+        for (int c4 = 0; c4 < 2; ++c4) {
+            const float4 a = w2o[c4], bq = w2p[c4];
+            o[c4 * 4 + 0] = fmaf(a.x, hsum, o[c4 * 4 + 0]), o[c4 * 4 + 1] = fmaf(a.y, hsum, o[c4 * 4 + 1]);
+            o[c4 * 4 + 2] = fmaf(a.z, hsum, o[c4 * 4 + 2]), o[c4 * 4 + 3] = fmaf(a.w, hsum, o[c4 * 4 + 3]);
+            o[8 + c4 * 4 + 0] = fmaf(bq.x, hsum, o[8 + c4 * 4 + 0]), o[8 + c4 * 4 + 1] = fmaf(bq.y, hsum, o[8 + c4 * 4 + 1]);
+            o[8 + c4 * 4 + 2] = fmaf(bq.z, hsum, o[8 + c4 * 4 + 2]), o[8 + c4 * 4 + 3] = fmaf(bq.w, hsum, o[8 + c4 * 4 + 3]);
+        }
+    }
+    {
+        // this lane's 8 channels: own partial + the partner's partial for them (its "partner's 8")
+        float sum = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float theirs = __shfl_xor_sync(0xffffffffu, o[8 + c], 1);
+            o[c] = ((o[c] + theirs) + wsm[AW_L2B + own + c]) + y[c];
+            sum += o[c];
+        }
+        const float mean = (sum + __shfl_xor_sync(0xffffffffu, sum, 1)) * (1.f / 16.f);
+        float var = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float d = o[c] - mean;
+            var = fmaf(d, d, var);
+        }
+        var = (var + __shfl_xor_sync(0xffffffffu, var, 1)) * (1.f / 16.f) + 1e-14f;
+        const float sd = sqrtf(var);
+        if (act) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) yb[c * T] = (o[c] - mean) / sd * wsm[AW_G2 + own + c] + wsm[AW_B2 + own + c];
+        }
+    }
+}
+
 int launch_attention(const AttnP &p, int G, cudaStream_t s) {
     if (p.T > AT_MAXT) {
         set_error("attention kernel supports T <= %d (got %d)", AT_MAXT, p.T);
@@ -332,9 +555,17 @@ int launch_attention(const AttnP &p, int G, cudaStream_t s) {
     }
     dim3 grid((unsigned)((p.B + AT_WPC - 1) / AT_WPC), G);
     constexpr size_t smem = AT_SMEM_FLOATS * sizeof(float);
-    if (int rc = ensure_dyn_smem((const void *)attention_kernel, smem)) return rc;
+    const char *v1 = getenv("VP_ATTN_V1");  // A/B aid: one thread per query (read per launch)
+    if (v1 && atoi(v1) != 0) {
+        if (int rc = ensure_dyn_smem((const void *)attention_kernel, smem)) return rc;
+        KTimer kt(KC_ATTN, s);
+        attention_kernel<<<grid, AT_NT, smem, s>>>(p);
+        VP_LAUNCH_CHECK();
+        return VP_OK;
+    }
+    if (int rc = ensure_dyn_smem((const void *)attention2_kernel, smem)) return rc;
     KTimer kt(KC_ATTN, s);
-    attention_kernel<<<grid, AT_NT, smem, s>>>(p);
+    attention2_kernel<<<grid, A2_NT, smem, s>>>(p);
     VP_LAUNCH_CHECK();
     return VP_OK;
 }
