@@ -129,7 +129,7 @@ int launch_lstm(int cin, const LstmP &p, int G, cudaStream_t s) {
 // window; a 240-thread CTA handles 5 windows in 48-thread slots (T = 47: 98 % of the lanes work; 64-thread slots left
 // 27 % of them idle) and loads the 21.6 KB parameter block once for the five.
 constexpr int AT_MAXT = 48;   // T <= 48 (T = 47 for 6000-sample windows)
-constexpr int AT_XP = 17;     // pitch of Xs rows (time-major x)
+constexpr int AT_XP = 20;     // pitch of Xs rows (time-major x; float4 aligned: the weighted sum reads a row as two LDS.128 per lane)
 constexpr int AT_KP = 36;     // pitch of the k-projection rows (float4 aligned)
 constexpr int AT_OFF_K = (AW_SIZE + 3) & ~3;                      // 16-byte aligned (float4 reads)
 constexpr int AT_WPC = 5;     // windows per CTA: 240 threads x 127 registers -> two CTAs (10 windows) per SM, register-file bound
@@ -453,9 +453,10 @@ __global__ void __launch_bounds__(A2_NT, 2) attention2_kernel(const AttnP p) {
         if (in_band) {
             const float w = ex2_approx(1.4426950408889634f * (e - emax));
             ssum += w;
-            const float *xj = &Xs[wl][jj * AT_XP + hs * 8];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) v[c] = fmaf(w, xj[c], v[c]);
+            const float4 *xj = reinterpret_cast<const float4 *>(&Xs[wl][jj * AT_XP + hs * 8]);
+            const float4 x0 = xj[0], x1 = xj[1];
+            v[0] = fmaf(w, x0.x, v[0]), v[1] = fmaf(w, x0.y, v[1]), v[2] = fmaf(w, x0.z, v[2]), v[3] = fmaf(w, x0.w, v[3]);
+            v[4] = fmaf(w, x1.x, v[4]), v[5] = fmaf(w, x1.y, v[5]), v[6] = fmaf(w, x1.z, v[6]), v[7] = fmaf(w, x1.w, v[7]);
         }
     }
     const float inv = 1.f / (ssum + 1e-5f);
