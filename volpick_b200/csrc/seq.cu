@@ -335,6 +335,14 @@ __global__ void __launch_bounds__(AT_NT, 2) attention_kernel(const AttnP p) {
 // the feed-forward output.  attention_kernel needs 127 registers (q[32], Wa[32], v[16] live in the T x T loop): 15 warps per
 // SM, issue slots 55 % busy, MUFU 36 % (ncu, profiles/r02e) -- latency-bound.  Half the state per thread fits 64 registers:
 // twice the warps for the same work.
+// ncu source view of this kernel (transformer launch, 4096 windows, round 2 capture r02i): 43 % of the stall samples in the T x T loop --
+// 18 MUFU per 87 instructions, and tools/mufu_probe.cu measures 16 MUFU lanes / clk / SM on B200, so that loop is MUFU-bound (36 XU
+// cycles against 22 issue cycles per warp iteration) -- and 36 % in the feed-forward loop (two wavefronts per LDS.128: the lanes of a
+// pair read different weights).  Measured and left out (2.25 vs 2.24 ms per station-day, bit-compatible): the feed-forward layer on its
+// own thread mapping (thread = query x half of the hidden units, one weight address per warp, LayerNorm rows and partial outputs staged
+// through the dead K / x tiles), together with two reciprocals from one MUFU.RCP (1/x = y rcp(xy), 24 instead of 15.7 elements / clk /
+// SM in the probe) behind a CTA-wide vote that every exponent is within +-31 so that xy stays normal -- the vote fails on the real
+// weights (some units sit beyond tanh saturation), and a clamp per element costs the issue slots the MUFU saved.
 constexpr int A2_TPW = 2 * AT_MAXT;      // threads per window
 constexpr int A2_NT = AT_WPC * A2_TPW;   // 480
 
