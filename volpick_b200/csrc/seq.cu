@@ -341,8 +341,8 @@ __global__ void __launch_bounds__(AT_NT, 2) attention_kernel(const AttnP p) {
 // pair read different weights).  Measured and left out (2.25 vs 2.24 ms per station-day, bit-compatible): the feed-forward layer on its
 // own thread mapping (thread = query x half of the hidden units, one weight address per warp, LayerNorm rows and partial outputs staged
 // through the dead K / x tiles), together with two reciprocals from one MUFU.RCP (1/x = y rcp(xy), 24 instead of 15.7 elements / clk /
-// SM in the probe) behind a CTA-wide vote that every exponent is within +-31 so that xy stays normal -- the vote fails on the real
-// weights (some units sit beyond tanh saturation), and a clamp per element costs the issue slots the MUFU saved.
+// SM in the probe) behind a CTA-wide vote that every exponent is within +-31 so that xy stays normal.  The unchanged time says the
+// vote does not pass on the real weights (not verified further); a clamp per element instead would cost the issue slots the MUFU saves.
 constexpr int A2_TPW = 2 * AT_MAXT;      // threads per window
 constexpr int A2_NT = AT_WPC * A2_TPW;   // 480
 
