@@ -18,7 +18,8 @@ namespace vp {
 // (input channel, unit) = the 4 gates; h is exchanged with width-16 shuffles.  (Measured alternatives of round 2, all slower or
 // neutral: W_hh in shared memory -- 56 instead of 128 registers, twice the warps per SM -- 2.05 vs 1.55 ms per station-day; the
 // gate FMAs as packed FFMA2: 1.59 ms; W_ih of the 16-channel layers in registers too -- no LDS.128 of W_ih, a third of the shared-memory
-// wavefronts per step, but 168 registers and three CTAs per SM -- 1.85 ms: the recurrence needs its 16 warps per SM.)
+// wavefronts per step, but 168 registers and three CTAs per SM -- 1.85 ms: the recurrence needs its 16 warps per SM; h staged in
+// shared memory as [unit][t] and written out as one contiguous run per sequence instead of a strided store per step -- 1.52 ms, unchanged.)
 // Transcendentals on the SFU with fp32-level ABSOLUTE accuracy (about 2e-7): ex2.approx and rcp.approx are good
 // to ~2 ulp; the forms below never cancel (tanh = 1 - 2 / (e^{2x} + 1), sigmoid = 1 / (1 + e^{-x})) and saturate
 // correctly (ex2 -> +inf gives rcp -> 0).  They replace expf / tanhf (about 20 instructions each) with 4-5.
