@@ -190,6 +190,63 @@ def test_pick_lists_come_out_in_sorted_order():
         models.WaveformModel._build_objects("XX.A.", "P", UTCDateTime, ns0, ns1, ns1 + 1, vals)
 
 
+def test_prefetch_helper_thread():
+    """models._prefetched: same items in the same order, at most one item ahead of the consumer plus the one being produced, an
+    exception re-raised at its place, and no helper left behind once the stop event is set."""
+    import threading
+    import time
+
+    produced = []
+
+    def gen(n, fail_at=None):
+        for i in range(n):
+            if i == fail_at:
+                raise OSError("boom")
+            produced.append(i)
+            yield i
+
+    stop = threading.Event()
+    seen = []
+    for x in models._prefetched(gen(20), stop):
+        time.sleep(0.002)
+        seen.append(x)
+        assert len(produced) <= len(seen) + 2  # one in the queue, one being handed over
+    assert seen == list(range(20))
+    del produced[:]
+    stop = threading.Event()
+    got = []
+    with pytest.raises(OSError, match="boom"):
+        for x in models._prefetched(gen(10, fail_at=4), stop):
+            got.append(x)
+    assert got == [0, 1, 2, 3]
+    # the consumer walks away in the middle: the helper must not wait for the queue for ever
+    stop = threading.Event()
+    it = models._prefetched(gen(1000), stop)
+    assert next(it) == 0
+    stop.set()
+    t_end = time.time() + 2.0
+    while time.time() < t_end and [t for t in threading.enumerate() if t.name == "vp-assemble" and t.is_alive()]:
+        time.sleep(0.02)
+    assert not [t for t in threading.enumerate() if t.name == "vp-assemble" and t.is_alive()]
+
+
+def test_copy_jobs_in_pieces():
+    """models._copy_jobs: long records are copied in 2 M-sample pieces on a thread pool; dtype conversion and offsets as plain
+    slice assignment."""
+    rng = np.random.default_rng(9)
+    n = (1 << 22) + 12345
+    src = [rng.integers(-1000, 1000, n).astype(np.int32), rng.standard_normal(n).astype(np.float32), rng.standard_normal(n - 777)]
+    dst = np.zeros((3, n), dtype=np.float32)
+    models._copy_jobs([(dst[0], src[0]), (dst[1], src[1]), (dst[2, 777:], src[2])])
+    np.testing.assert_array_equal(dst[0], src[0].astype(np.float32))
+    np.testing.assert_array_equal(dst[1], src[1])
+    np.testing.assert_array_equal(dst[2, 777:], src[2].astype(np.float32))
+    assert not dst[2, :777].any()
+    small = np.zeros(10, np.float32)
+    models._copy_jobs([(small, np.arange(10))])
+    np.testing.assert_array_equal(small, np.arange(10, dtype=np.float32))
+
+
 def test_filter_design_matches_oracle():
     """filter_args / filter_kwargs (model_training/test_onephase.ipynb cell 43): the host designs the same second-order
     sections as the oracle's ObsPy restatement; the records are filtered on the device (GPU test)."""

@@ -144,6 +144,44 @@ def _ns(t) -> int:
 _COPY_POOL = None
 
 
+def _prefetched(gen, stop):
+    """Iterate ``gen`` in a helper thread, one item ahead of the caller (``WaveformModel._run``: with PhaseNet the assembly of a
+    station-day, 2.8 ms of host copies, is as long as its GPU time, so it has to overlap the main thread's begin / collect / pick
+    objects).  An exception in ``gen`` is re-raised in the caller at the item where it happened; once ``stop`` (a
+    ``threading.Event``) is set the helper gives up within 50 ms whatever it is waiting for."""
+    import queue
+    import threading
+
+    q = queue.Queue(maxsize=1)
+
+    def put(x):
+        while not stop.is_set():
+            try:
+                q.put(x, timeout=0.05)
+                return True
+            except queue.Full:
+                pass
+        return False
+
+    def run():
+        try:
+            for item in gen:
+                if not put(("item", item)):
+                    return
+            put(("end", None))
+        except BaseException as e:  # re-raised in the calling thread
+            put(("error", e))
+
+    threading.Thread(target=run, name="vp-assemble", daemon=True).start()
+    while True:
+        kind, val = q.get()
+        if kind == "end":
+            return
+        if kind == "error":
+            raise val
+        yield val
+
+
 def _copy_jobs(jobs) -> None:
     """dst[...] = src for every (dst, src): long records are copied in pieces of 2 M samples by a few host threads (NumPy
     releases the GIL in its copy loops; one thread moves ~5 GB/s, a station-day is 104 MB -- with PhaseNet the assembly of
@@ -921,38 +959,6 @@ class WaveformModel:
                         break
                     yield s0, trace_id, t0, arr, ring["n"] > before
 
-        def prefetched(gen):
-            """``gen`` run by a helper thread, one record ahead: with PhaseNet the assembly of a station-day (2.8 ms of host
-            copies) is as long as its GPU time, so it has to overlap the main thread's begin / collect / pick objects."""
-            q = queue.Queue(maxsize=1)
-
-            def put(x):
-                while not stop.is_set():
-                    try:
-                        q.put(x, timeout=0.05)
-                        return True
-                    except queue.Full:
-                        pass
-                return False
-
-            def run():
-                try:
-                    for item in gen:
-                        if not put(("item", item)):
-                            return
-                    put(("end", None))
-                except BaseException as e:  # re-raised in the calling thread
-                    put(("error", e))
-
-            threading.Thread(target=run, name="vp-assemble", daemon=True).start()
-            while True:
-                kind, val = q.get()
-                if kind == "end":
-                    return
-                if kind == "error":
-                    raise val
-                yield val
-
         def collect():
             (s0, trace_id, t0, pinned), handle = in_flight.popleft()
             try:
@@ -994,7 +1000,7 @@ class WaveformModel:
 
         # long streams: records assembled one ahead by the helper thread; short ones inline
         long_stream = sum(len(tr.data) for tr in stream) >= self._prefetch_min_samples
-        source = prefetched(all_records()) if long_stream else all_records()
+        source = _prefetched(all_records(), stop) if long_stream else all_records()
         try:
             while True:
                 t_a = _time.perf_counter()
