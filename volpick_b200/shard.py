@@ -2,7 +2,9 @@
 
 Records are independent: each rank (one process per GPU) annotates its own slice of the record
 list with no collective on the data path.  The only exchange is the final gather of the
-variable-length pick lists to rank 0 (``torch.distributed.gather_object``; works with NCCL and gloo).
+variable-length pick lists to rank 0: ``gather_triggers`` (two ``all_gather`` calls of byte tensors, what
+``bench.py`` uses) for trigger tables, ``gather_picks`` (``gather_object``) for arbitrary payloads; both work with
+NCCL and gloo.
 """
 from __future__ import annotations
 
