@@ -186,6 +186,13 @@ def test_pick_lists_come_out_in_sorted_order():
     got, want = models.WaveformModel._sorted_objects(dparts), sorted(dplain)
     assert len(got) == 1800 and all(a == b for a, b in zip(got, want))
     assert models.WaveformModel._sorted_objects([]) == []
+
+    class OtherTime:  # a foreign time class (obspy.UTCDateTime) goes through its ns= keyword
+        def __init__(self, ns=None):
+            self.ns = ns
+
+    objs = models.WaveformModel._build_objects("XX.A.", "P", OtherTime, ns0[:5], ns1[:5], nsp[:5], vals[:5])
+    assert all(type(o.start_time) is OtherTime and o.start_time.ns == int(a) for o, a in zip(objs, ns0[:5]))
     with pytest.raises(ValueError):  # Pick.__init__'s ordering check survives the bulk constructor
         models.WaveformModel._build_objects("XX.A.", "P", UTCDateTime, ns0, ns1, ns1 + 1, vals)
 

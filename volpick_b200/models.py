@@ -1060,7 +1060,9 @@ class WaveformModel:
         """Pick (Detection when ``nsp`` is None) objects of one record and label from integer-nanosecond columns."""
         import gc
 
-        t = getattr(mk, "_from_ns", None) or (lambda ns, _mk=mk: _mk(ns=ns))
+        # this package's UTCDateTime has a constructor without type dispatch; any other time class (obspy.UTCDateTime) is built
+        # through its public ``ns=`` keyword
+        t = UTCDateTime._from_ns if mk is UTCDateTime else (lambda ns, _mk=mk: _mk(ns=ns))
         gc_was_on = gc.isenabled()
         gc.disable()  # thousands of small objects that hold no cycles: the generational collector would only rescan them
         try:
