@@ -96,6 +96,39 @@ def test_stream_merge_and_segments():
     np.testing.assert_array_equal(arr4, x)
 
 
+def test_stream_records_into_caller_buffers():
+    """_iter_stream_arrays(alloc=...): records are assembled straight into the buffers the caller hands out (models._run: a ring of
+    pinned buffers) -- same content as the fresh-array form, int32 counts stay int32, zero fill of what no trace covers even when the
+    buffer holds an older record, one alloc call per non-strict record and none in strict mode."""
+    m = vb.PhaseNet.from_pretrained("volpick")
+    x = np.round(synthetic_record(3, 12_000)).astype(np.int32)
+    t0 = UTCDateTime("2022-02-02T00:00:00")
+    hdr = dict(network="XX", station="R", location="", sampling_rate=100.0)
+    traces = [Trace(x[0, :5000], dict(hdr, channel="HHZ", starttime=t0)),
+              Trace(x[1, 200:5000], dict(hdr, channel="HHN", starttime=t0 + 2.0)),    # late start: zero fill in front
+              Trace(x[0, 6000:], dict(hdr, channel="HHZ", starttime=t0 + 60.0)),     # second segment: N and E missing
+              Trace(x[2, 6000:11_000], dict(hdr, channel="HHE", starttime=t0 + 60.0))]
+    ring = [np.full(3 * 12_000, 7, dtype=np.int32) for _ in range(3)]  # "older records" in the buffers
+    calls = []
+
+    def alloc(shape, dtype):
+        k = len(calls) % 3
+        calls.append((shape, np.dtype(dtype)))
+        return ring[k][: shape[0] * shape[1]].view(dtype).reshape(shape)
+
+    want = m.stream_to_arrays(traces, m._argdict({}))
+    got = [(t, a.copy()) for t, a in m._iter_stream_arrays(traces, m._argdict({}), alloc)]
+    assert len(got) == len(want) == 2 and len(calls) == 2 and all(d == np.int32 for _, d in calls)
+    for (t_g, a_g), (t_w, a_w) in zip(got, want):
+        assert t_g == t_w and a_g.dtype == a_w.dtype == np.int32
+        np.testing.assert_array_equal(a_g, a_w)
+    assert not got[0][1][1, :200].any() and not got[0][1][2].any() and not got[1][1][1].any() and not got[1][1][2, 5000:].any()
+    np.testing.assert_array_equal(got[1][1][2, :5000], x[2, 6000:11_000])
+    del calls[:]
+    strict = list(m._iter_stream_arrays(traces, m._argdict({"strict": True}), alloc))
+    assert not calls and strict == []  # no span holds all three components
+
+
 def test_argdict_defaults_and_validation():
     e = vb.EQTransformer.from_pretrained("volpick")
     p = vb.PhaseNet.from_pretrained("volpick")
